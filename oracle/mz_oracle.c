@@ -1,0 +1,879 @@
+/*
+ * mz_oracle.c -- CPU restatement of deveshjawla/MuZero.jl's hot path.  TEST INFRASTRUCTURE ONLY.
+ * See mz_oracle.h for the parity status ("parity unpinned") and the arithmetic contract.
+ * All file:line citations are relative to /root/reference.
+ *
+ * Build: gcc -O3 -ffp-contract=off -fno-math-errno -mavx2 -mfma -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off matters: every fused multiply-add in the contract is an explicit fmaf();
+ * every other a*b+c is two roundings, exactly like Julia without @fastmath.
+ */
+#include "mz_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+
+/* ------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al. 2011).  Replaces the reference's unseeded global RNG / the
+ * MersenneTwister(1234) at src/SelfPlay.jl:152, which cannot be reproduced in a batched setting.
+ * ------------------------------------------------------------------------------------------ */
+enum { STREAM_TIE = 1, STREAM_ACTION = 2, STREAM_DIRICHLET = 3, STREAM_REPLAY = 4, STREAM_ABSORB = 5, STREAM_INIT = 7 };
+
+void mzo_philox(uint64_t seed, uint32_t stream, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ stream;
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; } /* [0,1) */
+static inline uint32_t u32_below(uint32_t x, uint32_t n) { return (uint32_t)(((uint64_t)x * n) >> 32); }
+
+/* ------------------------------------------------------------------------------------------
+ * Math contract (stands in for Julia Base exp/log/tanh on Float32; parity unpinned).
+ * ------------------------------------------------------------------------------------------ */
+static inline float bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t f2bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+float mzo_expf(float x) {
+    if (x > 88.0f) x = 88.0f;
+    if (x < -87.0f) x = -87.0f;
+    float fn = rintf(x * 1.44269504088896341f);
+    float r = fmaf(fn, -0.693359375f, x);
+    r = fmaf(fn, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float r2 = r * r;
+    float y = fmaf(p, r2, r) + 1.0f;
+    int n = (int)fn;
+    return y * bits2f((uint32_t)(n + 127) << 23);
+}
+
+float mzo_logf(float x) {
+    /* x > 0, normal */
+    uint32_t u = f2bits(x);
+    int e = (int)((u >> 23) & 0xff) - 126;
+    float m = bits2f((u & 0x007fffffu) | 0x3f000000u); /* [0.5, 1) */
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+    float z = m * m;
+    float y = 7.0376836292e-2f;
+    y = fmaf(y, m, -1.1514610310e-1f);
+    y = fmaf(y, m, 1.1676998740e-1f);
+    y = fmaf(y, m, -1.2420140846e-1f);
+    y = fmaf(y, m, 1.4249322787e-1f);
+    y = fmaf(y, m, -1.6668057665e-1f);
+    y = fmaf(y, m, 2.0000714765e-1f);
+    y = fmaf(y, m, -2.4999993993e-1f);
+    y = fmaf(y, m, 3.3333331174e-1f);
+    y = (y * m) * z;
+    float fe = (float)e;
+    y = fmaf(fe, -2.12194440e-4f, y);
+    y = fmaf(z, -0.5f, y);
+    float r = m + y;
+    r = fmaf(fe, 0.693359375f, r);
+    return r;
+}
+
+float mzo_tanhf(float x) {
+    float z = fabsf(x);
+    if (z > 44.0f) return x > 0.0f ? 1.0f : -1.0f;
+    if (z >= 0.625f) {
+        float s = mzo_expf(z + z);
+        z = 1.0f - 2.0f / (s + 1.0f);
+        return x < 0.0f ? -z : z;
+    }
+    float w = x * x;
+    float p = -5.70498872745e-3f;
+    p = fmaf(p, w, 2.06390887954e-2f);
+    p = fmaf(p, w, -5.37397155531e-2f);
+    p = fmaf(p, w, 1.33314422036e-1f);
+    p = fmaf(p, w, -3.33332819422e-1f);
+    return fmaf(p * w, x, x);
+}
+
+/* x^e for select_action's visit_counts .^ (1/temperature) (src/SelfPlay.jl:301): exact repeated
+ * product when e is a small integer (T = 1, 0.5, 0.25 give e = 1, 2, 4), else exp(e*log(x)). */
+static float pow_contract(float x, float e) {
+    if (x == 0.0f) return 0.0f;
+    if (e == rintf(e) && e >= 1.0f && e <= 16.0f) {
+        float r = x;
+        for (int i = 1; i < (int)e; i++) r = r * x;
+        return r;
+    }
+    return mzo_expf(e * mzo_logf(x));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Config
+ * ------------------------------------------------------------------------------------------ */
+/* Julia (<= 1.10) Dict{Int,V} iteration order for keys 1..A inserted ascending into the default
+ * 16-slot table: slot = hash_64_64(3|x| + bits(Float64(x))) & 15, linear probing.  SURVEY Q9. */
+static uint64_t hash_64_64(uint64_t a) {
+    a = ~a + (a << 21);
+    a = a ^ (a >> 24);
+    a = a + (a << 3) + (a << 8);
+    a = a ^ (a >> 14);
+    a = a + (a << 2) + (a << 4);
+    a = a ^ (a >> 28);
+    a = a + (a << 31);
+    return a;
+}
+void mzo_julia_dict_order(int A, int32_t *order) {
+    int sz = 16;
+    while (A * 3 > sz * 2) sz *= 4; /* Dict grows x4 once count*3 > sz*2 (small tables) */
+    int *slots = (int *)calloc((size_t)sz, sizeof(int));
+    for (int k = 1; k <= A; k++) {
+        double d = (double)k; uint64_t b; memcpy(&b, &d, 8);
+        uint64_t h = hash_64_64(3ull * (uint64_t)k + b);
+        int i = (int)(h & (uint64_t)(sz - 1));
+        while (slots[i]) i = (i + 1) & (sz - 1);
+        slots[i] = k;
+    }
+    int n = 0;
+    for (int i = 0; i < sz; i++) if (slots[i]) order[n++] = slots[i];
+    free(slots);
+}
+
+void mzo_default_config(mzo_config *c) { /* games/tictactoe/params.jl:2-29; src/Constructors.jl:18-52 */
+    memset(c, 0, sizeof(*c));
+    c->game = MZO_GAME_TICTACTOE;
+    c->W = 3; c->H = 3; c->C = 3; c->A = 9; c->num_players = 2;
+    c->stacked_observations = 1; c->max_moves = 9; c->num_iters = 10;
+    c->num_unroll_steps = 5; c->td_steps = 5; c->batch_size = 32; c->replay_buffer_size = 10000;
+    c->pb_c_base = 19652; c->pb_c_init = 1.25f; c->discount = 0.997f;
+    c->dirichlet_alpha = 0.25f; c->exploration_eps = 0.25f;
+    c->intermediate_rewards = 0; c->tie_mode = MZO_TIE_PHILOX; c->seed = 1337;
+    mzo_julia_dict_order(c->A, c->child_order);
+    c->width_hidden = 64; c->depth_representation = 3; c->depth_prediction = 3; c->depth_dynamics = 3;
+    c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
+    c->hidden_state_size = 27; c->reward_activation_tanh = 1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Networks: init_representation / init_prediction / init_dynamics (src/Learning.jl:87-142).
+ * Blob layout: nets in order (representation, prediction, dynamics); inside a net the Dense layers
+ * in Flux.params order (trunk, then Split path 1, then Split path 2); per layer W (out,in) in
+ * Julia column-major (W[o + out*k]) followed by b[out].
+ * ------------------------------------------------------------------------------------------ */
+enum { ACT_ID = 0, ACT_RELU = 1, ACT_TANH = 2 };
+typedef struct { int in, out, act, w_off, b_off; } layer_t;
+typedef struct { int n_trunk, n_h1, n_h2; layer_t trunk[24], h1[24], h2[24]; int base, n_params; } net_t;
+
+static int add_layer(layer_t *l, int in, int out, int act, int *off) {
+    l->in = in; l->out = out; l->act = act; l->w_off = *off; *off += in * out; l->b_off = *off; *off += out;
+    return 1;
+}
+static int obs_planes(const mzo_config *c) { return c->C * (c->stacked_observations + 1) + c->stacked_observations; }
+static int stack_size(const mzo_config *c) { return c->W * c->H * obs_planes(c); }
+static int obs_size(const mzo_config *c) { return c->W * c->H * c->C; }
+static int sa_size(const mzo_config *c) { return c->W * c->H * (c->C + 1); }
+
+static void build_net(const mzo_config *c, int which, net_t *n, int base) {
+    int off = base, w = c->width_hidden;
+    memset(n, 0, sizeof(*n)); n->base = base;
+    if (which == 0) { /* Learning.jl:87-98 */
+        n->n_trunk += add_layer(&n->trunk[n->n_trunk], stack_size(c), w, ACT_RELU, &off);
+        for (int i = 0; i < c->depth_representation; i++) n->n_trunk += add_layer(&n->trunk[n->n_trunk], w, w, ACT_RELU, &off);
+        n->n_trunk += add_layer(&n->trunk[n->n_trunk], w, c->hidden_state_size, ACT_ID, &off);
+    } else if (which == 1) { /* Learning.jl:100-116 */
+        n->n_trunk += add_layer(&n->trunk[n->n_trunk], c->hidden_state_size, w, ACT_RELU, &off);
+        for (int i = 0; i < c->depth_prediction; i++) n->n_trunk += add_layer(&n->trunk[n->n_trunk], w, w, ACT_RELU, &off);
+        for (int i = 0; i < c->depth_value; i++) n->n_h1 += add_layer(&n->h1[n->n_h1], w, w, ACT_RELU, &off);
+        n->n_h1 += add_layer(&n->h1[n->n_h1], w, 1, ACT_TANH, &off);
+        for (int i = 0; i < c->depth_policy; i++) n->n_h2 += add_layer(&n->h2[n->n_h2], w, w, ACT_RELU, &off);
+        n->n_h2 += add_layer(&n->h2[n->n_h2], w, c->A, ACT_ID, &off); /* softmax applied by caller */
+    } else { /* Learning.jl:118-142 */
+        n->n_trunk += add_layer(&n->trunk[n->n_trunk], sa_size(c), w, ACT_RELU, &off);
+        for (int i = 0; i < c->depth_dynamics; i++) n->n_trunk += add_layer(&n->trunk[n->n_trunk], w, w, ACT_RELU, &off);
+        for (int i = 0; i < c->depth_state_head; i++) n->n_h1 += add_layer(&n->h1[n->n_h1], w, w, ACT_RELU, &off);
+        n->n_h1 += add_layer(&n->h1[n->n_h1], w, c->hidden_state_size, ACT_ID, &off);
+        for (int i = 0; i < c->depth_reward; i++) n->n_h2 += add_layer(&n->h2[n->n_h2], w, w, ACT_RELU, &off);
+        n->n_h2 += add_layer(&n->h2[n->n_h2], w, 1, c->reward_activation_tanh ? ACT_TANH : ACT_ID, &off);
+    }
+    n->n_params = off - base;
+}
+static void build_nets(const mzo_config *c, net_t nets[3]) {
+    build_net(c, 0, &nets[0], 0);
+    build_net(c, 1, &nets[1], nets[0].n_params);
+    build_net(c, 2, &nets[2], nets[0].n_params + nets[1].n_params);
+}
+int mzo_num_params(const mzo_config *c, int net) {
+    net_t n[3]; build_nets(c, n);
+    return net < 3 ? n[net].n_params : n[0].n_params + n[1].n_params + n[2].n_params;
+}
+
+/* Flux.glorot_uniform: (rand(Float32, out, in) .- 0.5f0) .* sqrt(24f0 / (in + out)); bias zeros.
+ * The reference draws from the unseeded global RNG (conf.seed is never read, Constructors.jl:19);
+ * contract: element i of layer l of net n = Philox(seed, INIT, n, l, i/4)[i%4]. */
+void mzo_init_weights(const mzo_config *c, uint64_t seed, float *blob) {
+    net_t nets[3]; build_nets(c, nets);
+    for (int n = 0; n < 3; n++) {
+        int li = 0;
+        for (int part = 0; part < 3; part++) {
+            int cnt = part == 0 ? nets[n].n_trunk : part == 1 ? nets[n].n_h1 : nets[n].n_h2;
+            layer_t *ls = part == 0 ? nets[n].trunk : part == 1 ? nets[n].h1 : nets[n].h2;
+            for (int l = 0; l < cnt; l++, li++) {
+                float scale = sqrtf(24.0f / (float)(ls[l].in + ls[l].out));
+                int nw = ls[l].in * ls[l].out;
+                for (int i = 0; i < nw; i += 4) {
+                    uint32_t r[4]; mzo_philox(seed, STREAM_INIT, (uint32_t)n, (uint32_t)li, (uint32_t)(i / 4), 0, r);
+                    for (int j = 0; j < 4 && i + j < nw; j++) blob[ls[l].w_off + i + j] = (u32_to_unit(r[j]) - 0.5f) * scale;
+                }
+                for (int o = 0; o < ls[l].out; o++) blob[ls[l].b_off + o] = 0.0f;
+            }
+        }
+    }
+}
+
+/* Dense (Flux 0.12.4, un-vendored): y = act.(W*x .+ b).  Contract: sequential-k fmaf, then + b. */
+static void dense(const float *blob, const layer_t *l, const float *x, float *y) {
+    float acc[256];
+    const float *W = blob + l->w_off, *b = blob + l->b_off;
+    int out = l->out;
+    for (int o = 0; o < out; o++) acc[o] = 0.0f;
+    for (int k = 0; k < l->in; k++) {
+        float xk = x[k];
+        const float *wk = W + (size_t)k * out;
+        for (int o = 0; o < out; o++) acc[o] = fmaf(wk[o], xk, acc[o]);
+    }
+    for (int o = 0; o < out; o++) {
+        float v = acc[o] + b[o];
+        if (l->act == ACT_RELU) v = v > 0.0f ? v : 0.0f;       /* NNlib relu(x) = max(0, x) */
+        else if (l->act == ACT_TANH) v = mzo_tanhf(v);
+        y[o] = v;
+    }
+}
+static void run_layers(const float *blob, const layer_t *ls, int n, const float *x, float *y) {
+    float a[256], b[256];
+    const float *cur = x;
+    for (int i = 0; i < n; i++) {
+        float *dst = (i == n - 1) ? y : ((i & 1) ? b : a);
+        dense(blob, &ls[i], cur, dst);
+        cur = dst;
+    }
+}
+/* NNlib.softmax (un-vendored): exp.(x .- maximum(x)) ./ sum(...), sum in index order. */
+static void softmax(const float *x, int n, float *y) {
+    float m = x[0];
+    for (int i = 1; i < n; i++) m = x[i] > m ? x[i] : m;
+    float s = 0.0f;
+    for (int i = 0; i < n; i++) { y[i] = mzo_expf(x[i] - m); s = s + y[i]; }
+    for (int i = 0; i < n; i++) y[i] = y[i] / s;
+}
+
+typedef struct { mzo_config cfg; net_t nets[3]; const float *blob; } model_t;
+static void model_init(model_t *m, const mzo_config *c, const float *blob) { m->cfg = *c; build_nets(c, m->nets); m->blob = blob; }
+
+static void representation(const model_t *m, const float *stacked, float *hidden) {
+    run_layers(m->blob, m->nets[0].trunk, m->nets[0].n_trunk, stacked, hidden);
+}
+static void prediction(const model_t *m, const float *hidden, float *value, float *policy) {
+    float t[256], logits[MZO_MAX_A];
+    const net_t *n = &m->nets[1];
+    run_layers(m->blob, n->trunk, n->n_trunk, hidden, t);
+    run_layers(m->blob, n->h1, n->n_h1, t, value);
+    run_layers(m->blob, n->h2, n->n_h2, t, logits);
+    softmax(logits, m->cfg.A, policy); /* Learning.jl:114: the policy head ENDS in softmax (Q1) */
+}
+static void dynamics(const model_t *m, const float *sa, float *next_hidden, float *reward) {
+    float t[256];
+    const net_t *n = &m->nets[2];
+    run_layers(m->blob, n->trunk, n->n_trunk, sa, t);
+    run_layers(m->blob, n->h1, n->n_h1, t, next_hidden);
+    run_layers(m->blob, n->h2, n->n_h2, t, reward);
+}
+void mzo_representation(const mzo_config *c, const float *blob, const float *s, float *h) { model_t m; model_init(&m, c, blob); representation(&m, s, h); }
+void mzo_prediction(const mzo_config *c, const float *blob, const float *h, float *v, float *p) { model_t m; model_init(&m, c, blob); prediction(&m, h, v, p); }
+void mzo_dynamics(const mzo_config *c, const float *blob, const float *sa, float *nh, float *r) { model_t m; model_init(&m, c, blob); dynamics(&m, sa, nh, r); }
+
+/* ------------------------------------------------------------------------------------------
+ * Environment: games/tictactoe/game.jl.  Board = BitArray (3,3,3): plane 1 = player-1 marks,
+ * plane 2 = player-2 marks, plane 3 = empty (game.jl:8-13).  Here p1/p2 are bit masks with
+ * bit (a-1) for action a; CartesianIndices((3,3))[a] is column-major so cell index = a-1.
+ * ------------------------------------------------------------------------------------------ */
+static const uint32_t TTT_LINES[8] = { /* game.jl:106-113, bits = row-1 + 3*(col-1) */
+    (1u << 0) | (1u << 3) | (1u << 6), (1u << 1) | (1u << 4) | (1u << 7), (1u << 2) | (1u << 5) | (1u << 8),
+    (1u << 0) | (1u << 1) | (1u << 2), (1u << 3) | (1u << 4) | (1u << 5), (1u << 6) | (1u << 7) | (1u << 8),
+    (1u << 0) | (1u << 4) | (1u << 8), (1u << 6) | (1u << 4) | (1u << 2)};
+
+void mzo_env_reset(const mzo_config *c, mzo_env *e) { (void)c; e->p1 = 0; e->p2 = 0; e->player = 1; e->moves = 0; } /* game.jl:15-20 */
+
+/* is_win(env, player) IGNORES its argument and tests env.player, the side to move (game.jl:102-104, Q14). */
+static int ttt_is_win_side_to_move(const mzo_env *e) {
+    uint32_t b = (uint32_t)(e->player == 1 ? e->p1 : e->p2);
+    for (int i = 0; i < 8; i++) if ((b & TTT_LINES[i]) == TTT_LINES[i]) return 1;
+    return 0;
+}
+static uint64_t cells_mask(const mzo_config *c) { return (c->W * c->H >= 64) ? ~0ull : ((1ull << (c->W * c->H)) - 1ull); }
+
+uint32_t mzo_env_legal_mask(const mzo_config *c, const mzo_env *e) { /* game.jl:35-43 */
+    if (ttt_is_win_side_to_move(e)) return 0; /* is_win(env,1) || is_win(env,2): both test env.player */
+    return (uint32_t)(~(e->p1 | e->p2) & cells_mask(c));
+}
+void mzo_env_step(const mzo_config *c, mzo_env *e, int action) { /* game.jl:45-52 */
+    (void)c;
+    uint64_t bit = 1ull << (action - 1);
+    if (e->player == 1) e->p1 |= bit; else e->p2 |= bit; /* board[a,3]=false; board[a,player]=true */
+    e->moves += 1;
+    e->player = e->player == 1 ? 2 : 1;                  /* mod1(player+1, 2) */
+}
+/* State table (game.jl:117-147): is_terminated = !(has_empty_pos && isnothing(w)), w = 1 when
+ * is_win (of the side to move, Q14-Q15) else nothing; winner is never 2. */
+int mzo_env_is_terminated(const mzo_config *c, const mzo_env *e) { /* game.jl:85 */
+    int has_empty = (~(e->p1 | e->p2) & cells_mask(c)) != 0;
+    return !(has_empty && !ttt_is_win_side_to_move(e));
+}
+int mzo_env_reward(const mzo_config *c, const mzo_env *e, int player) { /* game.jl:87-100 */
+    if (!mzo_env_is_terminated(c, e)) return 0;
+    if (!ttt_is_win_side_to_move(e)) return 0; /* winner === nothing */
+    return player == 1 ? 1 : -1;               /* winner is always 1 (Q15) */
+}
+void mzo_env_observation(const mzo_config *c, const mzo_env *e, float *obs) { /* Float32 copy of board, SelfPlay.jl:352 */
+    int n = c->W * c->H;
+    for (int i = 0; i < n; i++) {
+        int a = (int)((e->p1 >> i) & 1), b = (int)((e->p2 >> i) & 1);
+        obs[i] = (float)a; obs[n + i] = (float)b; obs[2 * n + i] = (float)(!(a | b));
+    }
+}
+
+/* RLBase.walk-style census of the reachable graph (KAT-env-3). */
+typedef struct { const mzo_config *c; uint8_t *seen; int64_t *out; } census_t;
+static uint32_t board_key(const mzo_env *e) { return (uint32_t)(e->p1 | (e->p2 << 9)); }
+static void census_walk(census_t *z, mzo_env e, int len, int last_mover) {
+    uint32_t key = board_key(&e);
+    int term = mzo_env_is_terminated(z->c, &e);
+    if (!z->seen[key]) { z->seen[key] = 1; z->out[0]++; if (term) z->out[1]++; }
+    if (term) {
+        int r = mzo_env_reward(z->c, &e, last_mover);
+        z->out[2]++; z->out[3 + len]++;
+        z->out[32 + len * 6 + (last_mover - 1) * 3 + (r + 1)]++;
+        return;
+    }
+    uint32_t legal = mzo_env_legal_mask(z->c, &e);
+    for (int a = 1; a <= z->c->A; a++) if (legal & (1u << (a - 1))) {
+        mzo_env n = e; int mover = e.player;
+        mzo_env_step(z->c, &n, a);
+        census_walk(z, n, len + 1, mover);
+    }
+}
+void mzo_env_census(const mzo_config *c, int64_t *out) {
+    census_t z; z.c = c; z.out = out;
+    memset(out, 0, sizeof(int64_t) * (32 + 64 * 6));
+    z.seen = (uint8_t *)calloc(1u << 18, 1);
+    mzo_env e; mzo_env_reset(c, &e);
+    census_walk(&z, e, 0, 0 + 1);
+    free(z.seen);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * get_stacked_observations (src/SelfPlay.jl:128-149).  obs_hist is [T][C][H][W] (Julia (W,H,C,T)).
+ * Output planes: current obs (C), then for each past index: action plane (RAW index, Q13) + obs (C).
+ * ------------------------------------------------------------------------------------------ */
+void mzo_stack_observations(const mzo_config *c, const float *obs_hist, const int32_t *action_hist, int index, float *stacked) {
+    int plane = c->W * c->H, on = obs_size(c);
+    memcpy(stacked, obs_hist + (size_t)(index - 1) * on, sizeof(float) * on);
+    float *dst = stacked + on;
+    for (int past = index - 1; past >= index - c->stacked_observations; past--) {
+        if (past >= 1) {
+            float av = (float)action_hist[past - 1]; /* ones .* action_history[past] */
+            for (int i = 0; i < plane; i++) dst[i] = av;
+            memcpy(dst + plane, obs_hist + (size_t)(past - 1) * on, sizeof(float) * on);
+        } else {
+            for (int i = 0; i < plane + on; i++) dst[i] = 0.0f;
+        }
+        dst += plane + on;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * MCTS: src/SelfPlay.jl:16-39 (MinMaxStats), 62-96 (Node, expand_node!), 102-109 (noise),
+ * 157-184 (select_child / ucb_score), 190-217 (backpropagate!), 230-285 (run_mcts).
+ * Pointer-based like the reference; children is the Dict{Int,Node}, iterated in cfg.child_order.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct node {
+    int visit_count, to_play, expanded;
+    float prior, value_sum, reward;
+    struct node *children[MZO_MAX_A]; /* key a -> children[a-1]; NULL = no key */
+    float *hidden_state;              /* the Array{Float32,3} the node references (aliased, Q6) */
+} node_t;
+typedef struct { float min, max; } minmax_t;
+
+typedef struct {
+    const model_t *m;
+    node_t *nodes; int n_nodes;
+    float *hiddens; int n_hiddens;
+    uint64_t game_id; int move_idx;
+} tree_t;
+
+static node_t *new_node(tree_t *t, float prior) { /* Node(prior=...) defaults, SelfPlay.jl:62-70 */
+    node_t *n = &t->nodes[t->n_nodes++];
+    memset(n, 0, sizeof(*n));
+    n->to_play = 1; n->prior = prior;
+    return n;
+}
+static float node_value(const node_t *n) { /* SelfPlay.jl:76-82 */
+    return n->visit_count == 0 ? 0.0f : n->value_sum / (float)n->visit_count;
+}
+/* expand_node! (SelfPlay.jl:88-96): softmax AGAIN over the legal subset of the already-softmaxed
+ * policy (Q1), in ascending action order; children for the given (root's, Q7) legal set. */
+static void expand_node(tree_t *t, node_t *node, uint32_t legal, int to_play, float reward, const float *policy, float *hidden) {
+    const mzo_config *c = &t->m->cfg;
+    float sub[MZO_MAX_A], pv[MZO_MAX_A]; int acts[MZO_MAX_A], n = 0;
+    for (int a = 1; a <= c->A; a++) if (legal & (1u << (a - 1))) { acts[n] = a; sub[n] = policy[a - 1]; n++; }
+    softmax(sub, n, pv);
+    for (int i = 0; i < n; i++) node->children[acts[i] - 1] = new_node(t, pv[i]);
+    node->expanded = 1; node->to_play = to_play; node->reward = reward; node->hidden_state = hidden;
+}
+
+/* Gamma(alpha<1) sampler for the Dirichlet noise (Distributions.jl un-vendored; contract):
+ * Marsaglia-Tsang on alpha+1 with polar-method normals, then * u^(1/alpha), all Float32, draws
+ * from Philox(seed, DIRICHLET, game, move, child j, counter). */
+typedef struct { uint64_t seed; uint32_t c0, c1, c2, ctr; uint32_t buf[4]; int have; } rstream_t;
+static uint32_t rs_next(rstream_t *s) {
+    if (s->have == 0) { mzo_philox(s->seed, STREAM_DIRICHLET, s->c0, s->c1, s->c2, s->ctr++, s->buf); s->have = 4; }
+    return s->buf[4 - (s->have--)];
+}
+static float rs_unit_open(rstream_t *s) { return ((float)(rs_next(s) >> 8) + 0.5f) * 5.9604644775390625e-8f; } /* (0,1) */
+static float rs_normal(rstream_t *s) {
+    for (;;) {
+        float a = 2.0f * rs_unit_open(s) - 1.0f, b = 2.0f * rs_unit_open(s) - 1.0f;
+        float q = a * a + b * b;
+        if (q >= 1.0f || q == 0.0f) continue;
+        return a * sqrtf(-2.0f * mzo_logf(q) / q);
+    }
+}
+static float rs_gamma(rstream_t *s, float alpha) {
+    float a1 = alpha < 1.0f ? alpha + 1.0f : alpha;
+    float d = a1 - 0.333333343f, cc = 1.0f / sqrtf(9.0f * d), g;
+    for (;;) {
+        float x = rs_normal(s), v = 1.0f + cc * x;
+        if (v <= 0.0f) continue;
+        v = v * v * v;
+        float u = rs_unit_open(s);
+        if (mzo_logf(u) < 0.5f * x * x + d - d * v + d * mzo_logf(v)) { g = d * v; break; }
+    }
+    if (alpha < 1.0f) { float u = rs_unit_open(s); g = g * mzo_expf(mzo_logf(u) / alpha); }
+    return g;
+}
+/* add_exploration_noise! (SelfPlay.jl:102-109): noise[i] pairs with the i-th key in Dict order. */
+static void add_exploration_noise(tree_t *t, node_t *root, float alpha, float eps) {
+    const mzo_config *c = &t->m->cfg;
+    float noise[MZO_MAX_A], sum = 0.0f; int n = 0;
+    for (int j = 0; j < c->A; j++) {
+        node_t *ch = root->children[c->child_order[j] - 1];
+        if (!ch) continue;
+        rstream_t s = {c->seed, (uint32_t)t->game_id, (uint32_t)t->move_idx, (uint32_t)n, 0, {0, 0, 0, 0}, 0};
+        noise[n] = rs_gamma(&s, alpha); sum = sum + noise[n]; n++;
+    }
+    n = 0;
+    for (int j = 0; j < c->A; j++) {
+        node_t *ch = root->children[c->child_order[j] - 1];
+        if (!ch) continue;
+        float nz = noise[n++] / sum;
+        ch->prior = ch->prior * (1.0f - eps) + nz * eps;
+    }
+}
+
+/* ucb_score (SelfPlay.jl:171-184): Float64 exploration term, Float32 value term, Float32 result (Q3-Q4). */
+static float ucb_score(const mzo_config *c, const node_t *parent, const node_t *child, const minmax_t *mm) {
+    double pb_c = log2((double)(parent->visit_count + c->pb_c_base + 1) / (double)c->pb_c_base) + (double)c->pb_c_init;
+    pb_c *= sqrt((double)parent->visit_count) / (double)(child->visit_count + 1);
+    double prior_score = pb_c * (double)child->prior;
+    if (child->visit_count > 0) {
+        float nv = node_value(child);
+        float q = child->reward + c->discount * (c->num_players == 1 ? nv : -nv);
+        float vs = (mm->max > mm->min) ? (q - mm->min) / (mm->max - mm->min) : q; /* normalize_tree_value :33-39 */
+        return (float)(prior_score + (double)vs);
+    }
+    return (float)(prior_score + 0.0);
+}
+/* select_child (SelfPlay.jl:157-166).  Ties: the reference draws rand(max_ucbs) from the unseeded
+ * global RNG (Q2); contract: Philox(seed, TIE, game, move, sim, depth) over the tied set in Dict order. */
+static node_t *select_child(tree_t *t, node_t *node, const minmax_t *mm, int sim, int depth, int *action) {
+    const mzo_config *c = &t->m->cfg;
+    float scores[MZO_MAX_A]; int acts[MZO_MAX_A], n = 0;
+    for (int j = 0; j < c->A; j++) {
+        int a = c->child_order[j]; node_t *ch = node->children[a - 1];
+        if (!ch) continue;
+        scores[n] = ucb_score(c, node, ch, mm); acts[n] = a; n++;
+    }
+    float mx = scores[0];
+    for (int i = 1; i < n; i++) mx = scores[i] > mx ? scores[i] : mx;
+    int tied[MZO_MAX_A], nt = 0;
+    for (int i = 0; i < n; i++) if (scores[i] == mx) tied[nt++] = i;
+    int pick = tied[0];
+    if (nt > 1 && c->tie_mode == MZO_TIE_PHILOX) {
+        uint32_t r[4]; mzo_philox(c->seed, STREAM_TIE, (uint32_t)t->game_id, (uint32_t)t->move_idx, (uint32_t)sim, (uint32_t)depth, r);
+        pick = tied[u32_below(r[0], (uint32_t)nt)];
+    }
+    *action = acts[pick];
+    return node->children[acts[pick] - 1];
+}
+static void update_tree(minmax_t *mm, float v) { /* SelfPlay.jl:27-31 */
+    mm->min = mm->min < v ? mm->min : v;
+    mm->max = mm->max > v ? mm->max : v;
+}
+/* backpropagate! (SelfPlay.jl:190-217), including the two-player precedence bug (Q8). */
+static void backpropagate(const mzo_config *c, node_t **path, int n, float value, int to_play, minmax_t *mm) {
+    for (int i = n - 1; i >= 0; i--) {
+        node_t *nd = path[i];
+        if (c->num_players == 1) {
+            nd->value_sum = nd->value_sum + value; nd->visit_count += 1;
+            update_tree(mm, nd->reward + c->discount * node_value(nd));
+            value = nd->reward + c->discount * value;
+        } else {
+            if (nd->to_play == to_play) nd->value_sum = nd->value_sum + value; else nd->value_sum = nd->value_sum - value;
+            nd->visit_count += 1;
+            update_tree(mm, nd->reward + c->discount * node_value(nd));
+            if (nd->to_play == to_play) value = -nd->reward; else value = nd->reward + c->discount * value;
+        }
+    }
+}
+/* make_state_action (SelfPlay.jl:7-14): doubles the CALLER's state in place (Q6); action plane =
+ * Float32(Float64(a) / length(action_space)). */
+static void make_state_action(const mzo_config *c, float *state, int action, float *sa) {
+    int on = obs_size(c), plane = c->W * c->H;
+    float av = (float)((double)action / (double)c->A);
+    for (int i = 0; i < on; i++) { state[i] = state[i] * 2.0f; sa[i] = state[i]; }
+    for (int i = 0; i < plane; i++) sa[on + i] = av;
+}
+
+static void run_mcts(tree_t *t, const float *stacked, uint32_t legal, int to_play, int exploration, node_t **root_out, float *trace) {
+    const model_t *m = t->m; const mzo_config *c = &m->cfg;
+    int hs = c->hidden_state_size;
+    t->n_nodes = 0; t->n_hiddens = 0;
+    node_t *root = new_node(t, 0.0f);                                   /* :232 */
+    float *h0 = t->hiddens + (size_t)(t->n_hiddens++) * hs;
+    representation(m, stacked, h0);                                      /* :234 */
+    float v0, p0[MZO_MAX_A];
+    prediction(m, h0, &v0, p0);                                          /* :239 */
+    expand_node(t, root, legal, to_play, 0.0f, p0, h0);                  /* :245 */
+    if (exploration) add_exploration_noise(t, root, c->dirichlet_alpha, c->exploration_eps); /* :247-249 */
+    minmax_t mm = {INFINITY, -INFINITY};                                 /* :251 */
+    node_t *path[MZO_MAX_T * 8];
+    for (int iter = 1; iter <= c->num_iters; iter++) {                   /* :254 */
+        node_t *node = root; int vtp = to_play, np = 0, action = 0, depth = 0;
+        path[np++] = node;
+        while (node->expanded) {                                         /* :261-268 */
+            depth++;
+            node = select_child(t, node, &mm, iter, depth, &action);
+            path[np++] = node;
+            vtp = vtp % c->num_players + 1;                              /* mod1(vtp+1, nplayers) */
+        }
+        node_t *parent = path[np - 2];                                   /* :270 */
+        float value, policy[MZO_MAX_A], sa[MZO_MAX_OBS + 64], reward;
+        prediction(m, parent->hidden_state, &value, policy);             /* :271 -- PARENT state (Q5) */
+        make_state_action(c, parent->hidden_state, action, sa);          /* :273 */
+        float *nh = t->hiddens + (size_t)(t->n_hiddens++) * hs;
+        dynamics(m, sa, nh, &reward);                                    /* :275 */
+        expand_node(t, node, legal, vtp, reward, policy, nh);            /* :280 -- root's legal set (Q7) */
+        backpropagate(c, path, np, value, vtp, &mm);                     /* :281 */
+        if (trace) { float *tr = trace + 5 * (iter - 1); tr[0] = (float)depth; tr[1] = (float)action; tr[2] = (float)((parent->hidden_state - t->hiddens) / hs); tr[3] = value; tr[4] = reward; }
+    }
+    *root_out = root;
+}
+
+static tree_t *tree_alloc(const model_t *m) {
+    const mzo_config *c = &m->cfg;
+    tree_t *t = (tree_t *)calloc(1, sizeof(tree_t));
+    t->m = m;
+    t->nodes = (node_t *)malloc(sizeof(node_t) * (size_t)(1 + (c->num_iters + 1) * c->A));
+    t->hiddens = (float *)malloc(sizeof(float) * (size_t)(c->num_iters + 1) * c->hidden_state_size);
+    return t;
+}
+static void tree_free(tree_t *t) { free(t->nodes); free(t->hiddens); free(t); }
+
+/* select_action (SelfPlay.jl:293-306): counts and actions in Dict order (Q9); T==0 argmax (first
+ * max), T==Inf uniform, else Categorical(counts.^(1/T) normalised) (Q10).  Draw contract:
+ * Philox(seed, ACTION, game, move)[0] -> Float32 in [0,1), inverse-CDF like Distributions.jl. */
+static int select_action_counts(const mzo_config *c, const int *counts, const int *acts, int n, float temperature, uint64_t game_id, int move_idx) {
+    if (temperature == 0.0f) {
+        int best = 0;
+        for (int i = 1; i < n; i++) if (counts[i] > counts[best]) best = i;
+        return acts[best];
+    }
+    uint32_t r[4]; mzo_philox(c->seed, STREAM_ACTION, (uint32_t)game_id, (uint32_t)move_idx, 0, 0, r);
+    if (isinf(temperature)) return acts[u32_below(r[0], (uint32_t)n)];
+    float d[MZO_MAX_A], s = 0.0f, e = 1.0f / temperature;
+    for (int i = 0; i < n; i++) { d[i] = pow_contract((float)counts[i], e); s = s + d[i]; }
+    for (int i = 0; i < n; i++) d[i] = d[i] / s;
+    float draw = u32_to_unit(r[0]), cp = d[0]; int i = 0;
+    while (cp <= draw && i < n - 1) { i++; cp = cp + d[i]; }
+    return acts[i];
+}
+int mzo_select_action(const mzo_config *c, const int32_t *visit_counts, uint32_t legal, float temperature, uint64_t game_id, int move_idx) {
+    int counts[MZO_MAX_A], acts[MZO_MAX_A], n = 0;
+    for (int j = 0; j < c->A; j++) { int a = c->child_order[j]; if (legal & (1u << (a - 1))) { counts[n] = visit_counts[a - 1]; acts[n] = a; n++; } }
+    return select_action_counts(c, counts, acts, n, temperature, game_id, move_idx);
+}
+
+void mzo_run_mcts(const mzo_config *cfg, const float *blob, const float *stacked, uint32_t legal, int to_play, int exploration,
+                  uint64_t game_id, int move_idx, int32_t *visit_counts, float *root_value, float *root_priors, float *trace) {
+    model_t m; model_init(&m, cfg, blob);
+    tree_t *t = tree_alloc(&m); t->game_id = game_id; t->move_idx = move_idx;
+    node_t *root;
+    run_mcts(t, stacked, legal, to_play, exploration, &root, trace);
+    for (int a = 0; a < cfg->A; a++) {
+        visit_counts[a] = root->children[a] ? root->children[a]->visit_count : 0;
+        if (root_priors) root_priors[a] = root->children[a] ? root->children[a]->prior : 0.0f;
+    }
+    *root_value = node_value(root);
+    tree_free(t);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * play_game (src/SelfPlay.jl:330-382) and the self_play! actor loop (:384-419) over many games.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const model_t *m; uint64_t first_game; int lo, hi; float temperature;
+    int32_t *T; float *obs; int32_t *actions; float *rewards; int32_t *to_play; float *child_visits; float *root_values;
+    int64_t sims;
+} sp_job_t;
+
+static void play_game(const model_t *m, tree_t *t, uint64_t game_id, float temperature, int32_t *T_out, float *obs_h,
+                      int32_t *act_h, float *rew_h, int32_t *tp_h, float *cv_h, float *rv_h, int64_t *sims) {
+    const mzo_config *c = &m->cfg;
+    int on = obs_size(c), T = 0, done = 0;
+    mzo_env env; float stacked[MZO_MAX_OBS * 3];
+    mzo_env_reset(c, &env);
+    while (!done && T <= c->max_moves) {                                  /* :343 */
+        int p = env.player;                                               /* :351 */
+        mzo_env_observation(c, &env, obs_h + (size_t)T * on);             /* :352 (obs of the board before the move) */
+        mzo_stack_observations(c, obs_h, act_h, T + 1, stacked);          /* :355 */
+        uint32_t legal = mzo_env_legal_mask(c, &env);
+        t->game_id = game_id; t->move_idx = T + 1;
+        node_t *root;
+        run_mcts(t, stacked, legal, p, 1, &root, NULL);                   /* :359 exploration hard-coded true (Q11) */
+        *sims += c->num_iters;
+        int counts[MZO_MAX_A], acts[MZO_MAX_A], n = 0, sum_visits = 0;
+        for (int j = 0; j < c->A; j++) { int a = c->child_order[j]; node_t *ch = root->children[a - 1]; if (ch) { counts[n] = ch->visit_count; acts[n] = a; n++; sum_visits += ch->visit_count; } }
+        int action = select_action_counts(c, counts, acts, n, temperature, game_id, T + 1); /* :360 */
+        mzo_env_step(c, &env, action);                                    /* :366 */
+        float reward = (float)mzo_env_reward(c, &env, p);                 /* :367 */
+        done = mzo_env_is_terminated(c, &env);                            /* :368 */
+        for (int a = 1; a <= c->A; a++) {                                 /* store_search_stats! :115-122 (Q12) */
+            node_t *ch = root->children[a - 1];
+            cv_h[(size_t)T * c->A + (a - 1)] = ch ? (float)((double)ch->visit_count / (double)sum_visits) : 0.0f;
+        }
+        rv_h[T] = node_value(root);
+        act_h[T] = action; rew_h[T] = reward; tp_h[T] = p;                /* :377-379 */
+        T++;
+    }
+    *T_out = T;
+}
+static void *sp_worker(void *arg) {
+    sp_job_t *j = (sp_job_t *)arg; const mzo_config *c = &j->m->cfg;
+    int Tmax = c->max_moves + 1, on = obs_size(c);
+    tree_t *t = tree_alloc(j->m);
+    for (int g = j->lo; g < j->hi; g++)
+        play_game(j->m, t, j->first_game + (uint64_t)g, j->temperature, &j->T[g], j->obs + (size_t)g * Tmax * on,
+                  j->actions + (size_t)g * Tmax, j->rewards + (size_t)g * Tmax, j->to_play + (size_t)g * Tmax,
+                  j->child_visits + (size_t)g * Tmax * c->A, j->root_values + (size_t)g * Tmax, &j->sims);
+    tree_free(t);
+    return NULL;
+}
+int64_t mzo_self_play(const mzo_config *cfg, const float *blob, uint64_t first_game, int n_games, float temperature, int nthreads,
+                      int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values) {
+    model_t m; model_init(&m, cfg, blob);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > n_games) nthreads = n_games > 0 ? n_games : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    sp_job_t *jobs = (sp_job_t *)calloc((size_t)nthreads, sizeof(sp_job_t));
+    for (int i = 0; i < nthreads; i++) {
+        sp_job_t *j = &jobs[i];
+        j->m = &m; j->first_game = first_game; j->temperature = temperature;
+        j->lo = (int)((int64_t)n_games * i / nthreads); j->hi = (int)((int64_t)n_games * (i + 1) / nthreads);
+        j->T = T; j->obs = obs; j->actions = actions; j->rewards = rewards; j->to_play = to_play; j->child_visits = child_visits; j->root_values = root_values;
+        if (nthreads == 1) sp_worker(j); else pthread_create(&th[i], NULL, sp_worker, j);
+    }
+    int64_t sims = 0;
+    for (int i = 0; i < nthreads; i++) { if (nthreads > 1) pthread_join(th[i], NULL); sims += jobs[i].sims; }
+    free(th); free(jobs);
+    return sims;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Replay / targets: src/ReplayBuffer.jl.
+ * ------------------------------------------------------------------------------------------ */
+/* conf.discount^i for Float32^Int (Julia Base: i<=3 by products, else llvm.pow.f32). */
+static float discount_pow(float g, int i) {
+    if (i == 0) return 1.0f;
+    if (i == 1) return g;
+    if (i == 2) return g * g;
+    if (i == 3) return g * g * g;
+    return powf(g, (float)i);
+}
+/* compute_target_value (ReplayBuffer.jl:5-20), Q17.  index is 1-based. */
+float mzo_compute_target_value(const mzo_config *c, int T, const float *rewards, const int32_t *to_play, const float *root_values, int index) {
+    int bootstrap = index + c->td_steps;
+    if (bootstrap < T) {
+        float last = to_play[bootstrap - 1] == to_play[index - 1] ? root_values[bootstrap - 1] : -root_values[bootstrap - 1];
+        float value = last * discount_pow(c->discount, c->td_steps);
+        int i = 1;
+        for (int ri = index; ri <= bootstrap; ri++, i++) {               /* enumerate(reward_history[index:bootstrap]) */
+            float r = rewards[ri - 1];
+            value = value + (to_play[index - 1] == to_play[index + i - 1] ? r : -r) * discount_pow(c->discount, i);
+        }
+        return value;
+    }
+    return 0.0f;
+}
+/* get_batch (ReplayBuffer.jl:188-217) with sample_n_games/sample_position uniform branches (:102-104, :80)
+ * and make_target (:25-50, Q18).  RNG contract: Philox(seed, REPLAY, step, b) -> [0]: game, [1]: position;
+ * absorbing-state actions Philox(seed, ABSORB, step, b, unroll offset). */
+void mzo_get_batch(const mzo_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
+                   const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values, uint64_t step,
+                   int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
+                   float *policy_batch, float *gscale) {
+    int Tmax = c->max_moves + 1, on = obs_size(c), ss = stack_size(c), K1 = c->num_unroll_steps + 1, A = c->A;
+    for (int b = 0; b < c->batch_size; b++) {
+        uint32_t r[4]; mzo_philox(c->seed, STREAM_REPLAY, (uint32_t)step, (uint32_t)b, 0, 0, r);
+        int gi = (int)u32_below(r[0], (uint32_t)n_games);
+        int Tg = T[gi];
+        int pos = 1 + (int)u32_below(r[1], (uint32_t)Tg);                 /* rand(1:length(root_values)) */
+        const float *g_obs = obs + (size_t)gi * Tmax * on; const int32_t *g_act = actions + (size_t)gi * Tmax;
+        const float *g_rew = rewards + (size_t)gi * Tmax; const int32_t *g_tp = to_play + (size_t)gi * Tmax;
+        const float *g_cv = child_visits + (size_t)gi * Tmax * A; const float *g_rv = root_values + (size_t)gi * Tmax;
+        index_batch[2 * b] = (int32_t)(first_key + gi); index_batch[2 * b + 1] = pos;
+        for (int k = 0; k < K1; k++) {                                    /* make_target :28-48 */
+            int ci = pos + k; float tv, tr; int act;
+            float *pol = policy_batch + ((size_t)b * K1 + k) * A;
+            if (ci < Tg) {
+                tv = mzo_compute_target_value(c, Tg, g_rew, g_tp, g_rv, ci); tr = g_rew[ci - 1];
+                for (int a = 0; a < A; a++) pol[a] = g_cv[(size_t)(ci - 1) * A + a];
+                act = g_act[ci - 1];
+            } else if (ci == Tg) {
+                tv = 0.0f; tr = g_rew[ci - 1];
+                for (int a = 0; a < A; a++) pol[a] = 1.0f / (float)A;
+                act = g_act[ci - 1];
+            } else {
+                tv = 0.0f; tr = 0.0f;
+                for (int a = 0; a < A; a++) pol[a] = 1.0f / (float)A;
+                uint32_t q[4]; mzo_philox(c->seed, STREAM_ABSORB, (uint32_t)step, (uint32_t)b, (uint32_t)k, 0, q);
+                act = 1 + (int)u32_below(q[0], (uint32_t)A);              /* rand(rng, conf.action_space) */
+            }
+            value_batch[(size_t)b * K1 + k] = tv; reward_batch[(size_t)b * K1 + k] = tr; action_batch[(size_t)b * K1 + k] = (float)act;
+        }
+        mzo_stack_observations(c, g_obs, g_act, pos, obs_batch + (size_t)b * ss);   /* :207 */
+        int gs = Tg + 1 - pos; if (c->num_unroll_steps < gs) gs = c->num_unroll_steps; /* :212 */
+        gscale[b] = (float)gs;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Learner: src/Learning.jl:261-304 (loss, make_dynamics_input), 347-397 (unroll, update).
+ * ------------------------------------------------------------------------------------------ */
+static float sqnorm_net(const float *blob, const net_t *n) { /* sum(sqnorm, params): per array, then across arrays */
+    float total = 0.0f; int first = 1;
+    for (int part = 0; part < 3; part++) {
+        int cnt = part == 0 ? n->n_trunk : part == 1 ? n->n_h1 : n->n_h2;
+        const layer_t *ls = part == 0 ? n->trunk : part == 1 ? n->h1 : n->h2;
+        for (int l = 0; l < cnt; l++) {
+            float sw = 0.0f, sb = 0.0f;
+            for (int i = 0; i < ls[l].in * ls[l].out; i++) sw = sw + blob[ls[l].w_off + i] * blob[ls[l].w_off + i];
+            for (int i = 0; i < ls[l].out; i++) sb = sb + blob[ls[l].b_off + i] * blob[ls[l].b_off + i];
+            if (first) { total = sw; first = 0; } else total = total + sw;
+            total = total + sb;
+        }
+    }
+    return total;
+}
+
+void mzo_learn_forward(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                       const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                       float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
+    model_t m; model_init(&m, c, blob);
+    int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), on = obs_size(c), plane = c->W * c->H;
+    for (int b = 0; b < B; b++) {
+        float h[256], nh[256], sa[MZO_MAX_OBS + 64], v, r;
+        representation(&m, obs_batch + (size_t)b * ss, h);                           /* :347 */
+        prediction(&m, h, &v, pred_policies + ((size_t)b * K1) * A);                 /* :351 */
+        pred_values[(size_t)b * K1] = v; pred_rewards[(size_t)b * K1] = 0.0f;        /* :352 zeros */
+        for (int i = 1; i <= K; i++) {                                               /* :355-370 (Q19) */
+            prediction(&m, h, &v, pred_policies + ((size_t)b * K1 + i) * A);         /* BEFORE stepping dynamics */
+            float av = action_batch[(size_t)b * K1 + (i - 1)] / (float)A;            /* make_dynamics_input :294 (Float32 divide) */
+            for (int j = 0; j < on; j++) sa[j] = h[j] * 2.0f;                         /* :299 (copy, no aliasing) */
+            for (int j = 0; j < plane; j++) sa[on + j] = av;
+            dynamics(&m, sa, nh, &r);                                                /* :362 */
+            memcpy(h, nh, sizeof(float) * (size_t)c->hidden_state_size);
+            pred_values[(size_t)b * K1 + i] = v; pred_rewards[(size_t)b * K1 + i] = r;
+        }
+    }
+    /* loss (:261-288), Q21 */
+    float vsum = 0.0f; double rsum = 0.0;
+    float *S = (float *)malloc(sizeof(float) * (size_t)B);
+    for (int b = 0; b < B; b++) {
+        float sv = 0.0f; double sr = 0.0; float sp = 0.0f;
+        for (int k = 0; k < K1; k++) {
+            float d = pred_values[(size_t)b * K1 + k] - value_batch[(size_t)b * K1 + k];
+            sv = sv + d * d;
+            double dr = (double)pred_rewards[(size_t)b * K1 + k] - (double)reward_batch[(size_t)b * K1 + k];
+            sr = sr + dr * dr;
+            /* logitcrossentropy: -sum(y .* logsoftmax(yhat)) with yhat ALREADY softmaxed */
+            const float *p = pred_policies + ((size_t)b * K1 + k) * A, *y = policy_batch + ((size_t)b * K1 + k) * A;
+            float mx = p[0];
+            for (int a = 1; a < A; a++) mx = p[a] > mx ? p[a] : mx;
+            float se = 0.0f;
+            for (int a = 0; a < A; a++) se = se + mzo_expf(p[a] - mx);
+            float lse = mzo_logf(se), acc = 0.0f;
+            for (int a = 0; a < A; a++) acc = acc + y[a] * ((p[a] - mx) - lse);
+            sp = sp + (-acc);
+        }
+        vsum = vsum + sv / gscale[b];
+        rsum = rsum + sr / (double)gscale[b];
+        S[b] = sp;
+    }
+    float value_loss = vsum / (float)B;
+    /* sum(x,dims=2) is (1,1,B), gscale is (1,B): the broadcast is (1,B,B); mean over all B*B entries */
+    float psum = 0.0f;
+    for (int j = 0; j < B; j++) for (int i = 0; i < B; i++) psum = psum + S[j] / gscale[i];
+    float policy_loss = psum / (float)(B * B);
+    free(S);
+    float data_loss;
+    if (c->intermediate_rewards) data_loss = (float)(((double)value_loss + rsum / (double)B) + (double)policy_loss);
+    else data_loss = (value_loss + 0.0f) + policy_loss;
+    for (int n = 0; n < 3; n++) losses[n] = data_loss + sqnorm_net(blob, &m.nets[n]);
+}
+
+double mzo_cos_schedule(int t) { /* ParameterSchedulers.Cos(l0=1e-4, l1=1e-1, period=10), Learning.jl:319 (Q22) */
+    double l0 = 1e-4, l1 = 1e-1, period = 10.0;
+    double g = (1.0 + cos(2.0 * 3.14159265358979323846 * (double)(t - 1) / period)) / 2.0;
+    return fabs(l0 - l1) * g + (l0 < l1 ? l0 : l1);
+}
+
+/* Flux.ADAM apply! + update! (Flux 0.12.4, un-vendored), Q22.  beta powers = beta^t by repeated product. */
+static void adam_update(float *theta, float *m, float *v, const float *grad, int n, double eta, int t) {
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    double bp1 = b1, bp2 = b2;
+    for (int i = 1; i < t; i++) { bp1 *= b1; bp2 *= b2; }
+    for (int i = 0; i < n; i++) {
+        float g = grad[i];
+        m[i] = (float)(b1 * (double)m[i] + (1.0 - b1) * (double)g);
+        v[i] = (float)(b2 * (double)v[i] + (1.0 - b2) * (double)(g * g));
+        float delta = (float)((double)m[i] / (1.0 - bp1) / (sqrt((double)v[i] / (1.0 - bp2)) + eps) * eta);
+        theta[i] = theta[i] - delta;
+    }
+}
+
+void mzo_learn_step(const mzo_config *c, float *blob, float *adam_m, float *adam_v, int t, int grad_mode, int B,
+                    const float *obs_batch, const float *action_batch, const float *value_batch, const float *reward_batch,
+                    const float *policy_batch, const float *gscale, float *losses) {
+    int K1 = c->num_unroll_steps + 1, A = c->A, np = mzo_num_params(c, 3);
+    float *pv = (float *)malloc(sizeof(float) * (size_t)B * K1), *pr = (float *)malloc(sizeof(float) * (size_t)B * K1);
+    float *pp = (float *)malloc(sizeof(float) * (size_t)B * K1 * A), *grad = (float *)malloc(sizeof(float) * (size_t)np);
+    mzo_learn_forward(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, pv, pr, pp, losses);
+    /* Q20: predictions are computed OUTSIDE Zygote.pullback (Learning.jl:347-374 vs 385-393), so the only
+     * parameter-dependent term is sum(sqnorm, params): grad = 2*theta for every array. */
+    (void)grad_mode;
+    for (int i = 0; i < np; i++) grad[i] = blob[i] + blob[i];
+    adam_update(blob, adam_m, adam_v, grad, np, mzo_cos_schedule(t), t);
+    free(pv); free(pr); free(pp); free(grad);
+}
