@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the self-play hot path (BASELINE.json: "MCTS simulations/sec ... TicTacToe FC;
+learner samples/sec").
+
+A step = one wave of self-play: `--games` (default 4096) concurrent TicTacToe games played to the end with
+`--sims` (default 50) simulations per move on every GPU (BASELINE.json configs[1]): root inference, S x {PUCT select,
+prediction + dynamics, expand, backup}, action sampling, environment step and history writes, all on the device.
+
+  value      simulations/s, whole job, device-timed (CUDA events on the launching stream), inputs resident in HBM
+  e2e        the same wave through the reference-facing API with HOST buffers: weights host->device (what
+             self_play! receives through remote_NNs), the wave, and every GameHistory device->host (what save_game ships)
+  roofline   dominant kernel (mz_k_search) against the measured HBM peak, algorithmic bytes per SURVEY.md section 8d
+  cpu_baseline  the CPU restatement of the reference (oracle/, a port) on the host cores, bounded sample
+  learner    learner samples/s (get_batch gather + K-step unroll forward + loss + gradients + allreduce + ADAM)
+
+`--impl reference` times the reference's CPU path instead (the oracle port: Julia is not available in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "mcts_simulations_per_sec"
+UNIT = "simulations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent self-play games per GPU")
+    ap.add_argument("--sims", type=int, default=50, help="simulations per move (num_iters)")
+    ap.add_argument("--learner-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-learner", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "TicTacToe FC, %d concurrent self-play games x %d simulations/move per GPU, Dirichlet noise on, T=1" % (a.games, a.sims)
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_self_play_rate(ocfg, blob, games, threads, first_game=10 ** 6):
+    from oracle import oracle as O
+    t0 = time.perf_counter()
+    h = O.self_play(ocfg, blob, first_game, games, 1.0, threads)
+    dt = time.perf_counter() - t0
+    return h["sims"] / dt, h["sims"], dt
+
+
+def cpu_baseline(ocfg, blob, target_s):
+    threads = os.cpu_count() or 1
+    rate, _, _ = cpu_self_play_rate(ocfg, blob, 4 * threads, threads)             # calibration
+    per_game = 8.3 * ocfg.num_iters
+    games = int(max(threads, min(200000, rate * target_s / per_game)))
+    rate, sims, dt = cpu_self_play_rate(ocfg, blob, games, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d self-play games (%d simulations) on %d host threads, %.1f s; C restatement of the reference "
+                      "(oracle/mz_oracle.c), the Julia reference cannot run in this image" % (games, sims, threads, dt)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_reference(a):
+    """Reference arm: the reference's own CPU implementation = the oracle port, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    ocfg = O.default_config(num_iters=a.sims)
+    blob = O.init_weights(ocfg, 1337)
+    threads = os.cpu_count() or 1
+    rate, _, _ = cpu_self_play_rate(ocfg, blob, 4 * threads, threads)
+    games = int(max(threads, min(a.games, rate * 3.0 / (8.3 * a.sims))))            # ~3 s per step
+    for i in range(a.warmup):
+        cpu_self_play_rate(ocfg, blob, games, threads, 10 ** 6 + i * games)
+    tot_s, tot_t = 0, 0.0
+    for i in range(a.steps):
+        _, s, dt = cpu_self_play_rate(ocfg, blob, games, threads, 2 * 10 ** 6 + i * games)
+        tot_s += s; tot_t += dt
+    v = tot_s / tot_t
+    sample = "%d of the %d games per step on %d host threads (C restatement of the reference, oracle/mz_oracle.c)" % (games, a.games, threads)
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                      "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from muzero_jl_b200 import capi
+    import common
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    G, S = a.games, a.sims
+    cfg = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G))
+    stream = torch.cuda.Stream()
+    ctx = capi.Context(cfg, device=local, stream=stream.cuda_stream)
+    ctx.init_weights(1337)
+    blob = ctx.get_weights()
+    ocfg = common.oracle_config(ctx.cfg)
+    flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    game_base = rank * (10 ** 7)
+
+    def wave(i, e2e=False):
+        if e2e:
+            ctx.set_weights(blob)
+        sims, moves = ctx.self_play(game_base + i * G, G, 1.0)
+        hist = ctx.history_export(n=G, key0=ctx.replay_info()["first_key"] + ctx.replay_info()["n_games"] - G) if e2e else None
+        return sims, moves, hist
+
+    with torch.cuda.stream(stream):
+        for i in range(a.warmup):
+            wave(i)
+        # ---- device-timed region: K waves, L2 flushed between timed iterations ----
+        barrier()
+        sampler = ClockSampler(local); sampler.start()
+        ctx.kernel_time_reset(True)
+        l0 = ctx.launch_count()
+        ms, sims_total, moves_total = 0.0, 0, 0
+        for i in range(a.steps):
+            flush.zero_(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            s, m, _ = wave(a.warmup + i)
+            e1.record(stream); e1.synchronize()
+            ms += e0.elapsed_time(e1); sims_total += s; moves_total += m
+        barrier()
+        launches = ctx.launch_count() - l0
+        k_ms, k_n = ctx.kernel_time(0)
+        ctx.kernel_time_reset(False)
+        clocks = sampler.stop()
+        stats = ctx.search_stats()
+        # ---- end-to-end region: host weights in, GameHistory out, every step ----
+        e2e_ms, e2e_sims, d2h = 0.0, 0, 0
+        for i in range(a.steps):
+            flush.zero_(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            s, m, hist = wave(a.warmup + a.steps + i, e2e=True)
+            e1.record(stream); e1.synchronize()
+            e2e_ms += e0.elapsed_time(e1); e2e_sims += s
+            d2h = sum(v.nbytes for v in hist.values())
+        barrier()
+        # ---- learner: samples/s at the reference batch (32) ----
+        learner = None
+        if not a.no_learner:
+            if world > 1:
+                uid = torch.from_numpy(capi.Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+                dist.broadcast(uid, 0)
+                ctx.comm_init(rank, world, uid.cpu().numpy())
+            for t in range(1, 4):
+                ctx.learn_step(t)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for t in range(4, 4 + a.learner_steps):
+                losses = ctx.learn_step(t)
+            e1.record(stream); e1.synchronize()
+            lms = e0.elapsed_time(e1)
+            learner = {"batch_per_gpu": cfg.batch_size, "grad_mode": "reference_l2", "ms_per_step": lms / a.learner_steps,
+                       "losses": [float(x) for x in losses]}
+
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0)], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max, learn_ms_max = [float(x) for x in t.cpu()]
+    sims_all, e2e_sims_all, launches_all = [float(x) for x in cnt.cpu()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        Lm, d = stats["mean_legal"], stats["mean_depth"]
+        bytes_per_sim = d * (16 * Lm + 12) + 4 * 27 + (16 + 4 * 27 + 16 * Lm) + (d + 1) * 20
+        sims_per_launch = sims_total / max(k_n, 1)
+        avg_launch_s = (k_ms / max(k_n, 1)) * 1e-3
+        achieved = bytes_per_sim * sims_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": sims_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "games_per_gpu": G, "simulations_per_move": S, "nn_mode": "fp32_exact", "parallelism": "dp%d" % world,
+                       "l2": "L2 flushed (384 MiB memset) between timed iterations", "mean_legal_actions": Lm, "mean_select_depth": d,
+                       "moves_per_step": moves_total / a.steps},
+            "e2e": {"value": e2e_sims_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_simulation": bytes_per_sim, "simulations_per_launch": sims_per_launch,
+                         "avg_launch_ms": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms if ms > 0 else None,
+                         "nn_flops_per_simulation": 111232, "nn_tflops_achieved": 111232 * sims_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0},
+        }
+        if learner:
+            learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
+            out["learner"] = learner
+        if not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(ocfg, blob, a.cpu_seconds)
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

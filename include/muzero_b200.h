@@ -1,0 +1,165 @@
+/*
+ * muzero_b200.h -- C ABI of the B200-native self-play / learner hot path (libmuzero_b200.so).
+ *
+ * This is the drop-in boundary for deveshjawla/MuZero.jl (reference at /root/reference, pure Julia).
+ * The reference has no FFI layer: the seam is a set of Julia functions that read the globals `conf`
+ * and `hyper`.  Each entry point below names the reference function (file:line) it replaces; the Julia
+ * wrapper that keeps those signatures and forwards to these symbols with `ccall` is
+ * muzero.jl_b200/julia/MuZeroB200.jl.
+ *
+ * Conventions
+ *   - plain C types only; the caller allocates and owns every host buffer, the library owns all device
+ *     memory; no pointer outlives a call except mz_ctx*.
+ *   - arrays use the reference's Julia memory order, i.e. a Julia (W,H,C,N) array is a C [N][C][H][W]
+ *     array; actions and players are 1-based like the reference.
+ *   - every function returns 0 on success, <0 on error (MZ_E_*); mz_last_error() returns the message.
+ *     Nothing throws or aborts across the ABI.  There is NO CPU fallback: without a CUDA device
+ *     mz_create fails with MZ_E_CUDA.
+ *   - a ctx is bound to one CUDA device and must be used by one host thread at a time.
+ */
+#ifndef MUZERO_B200_H
+#define MUZERO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_MAX_A 16
+#define MZ_ABI_VERSION 1
+
+enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
+enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
+enum { MZ_TIE_PHILOX = 0, MZ_TIE_FIRST = 1 };
+enum { MZ_GRAD_REFERENCE_L2 = 0, MZ_GRAD_BPTT = 1 };
+/* network arithmetic: exact fp32 (bit-identical to the oracle contract) or bf16 tcgen05 tensor cores */
+enum { MZ_NN_FP32_EXACT = 0, MZ_NN_BF16_TC = 1 };
+enum { MZ_NET_REPRESENTATION = 0, MZ_NET_PREDICTION = 1, MZ_NET_DYNAMICS = 2, MZ_NET_ALL = 3 };
+
+/* POD mirror of Config (src/Constructors.jl:18-52, games/tictactoe/params.jl:2-16) and FeedForwardHP
+ * (src/Constructors.jl:62-75, params.jl:18-29).  Field names follow the reference. */
+typedef struct mz_config {
+    int32_t game;                 /* MZ_GAME_* (the reference ships TicTacToe only) */
+    int32_t W, H, C;              /* observation_shape */
+    int32_t A;                    /* length(action_space) */
+    int32_t num_players;          /* length(players) */
+    int32_t stacked_observations;
+    int32_t max_moves;
+    int32_t num_iters;            /* simulations per move */
+    int32_t num_unroll_steps;
+    int32_t td_steps;
+    int32_t batch_size;
+    int32_t replay_buffer_size;
+    int32_t pb_c_base;
+    int32_t intermediate_rewards;
+    int32_t tie_mode;             /* UCB tie-break contract: MZ_TIE_* */
+    float   pb_c_init;
+    float   discount;
+    float   dirichlet_alpha;      /* dirichlet_α */
+    float   exploration_eps;      /* exploration_ϵ; 0 switches the root noise off bit-exactly */
+    uint64_t seed;
+    int32_t child_order[MZ_MAX_A];/* Julia Dict{Int,Node} iteration order of keys 1..A */
+    int32_t width_hidden, depth_representation, depth_prediction, depth_dynamics;
+    int32_t depth_policy, depth_value, depth_reward, depth_state_head;
+    int32_t hidden_state_size;
+    int32_t reward_activation_tanh;
+    /* B200 execution parameters (no reference counterpart) */
+    int32_t num_slots;            /* concurrent self-play games resident on this GPU (e.g. 4096) */
+    int32_t nn_mode;              /* MZ_NN_* */
+} mz_config;
+
+typedef struct mz_ctx mz_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int mz_abi_version(void);
+int mz_default_config(mz_config *cfg);                       /* games/tictactoe/params.jl:2-29 */
+int mz_julia_dict_order(int A, int32_t *order);              /* Dict iteration order used by SelfPlay.jl:158-159,294-295 */
+int mz_create(const mz_config *cfg, int device, mz_ctx **out);
+int mz_destroy(mz_ctx *ctx);
+const char *mz_last_error(mz_ctx *ctx);                      /* ctx may be NULL: last error of this thread */
+int mz_set_stream(mz_ctx *ctx, void *cuda_stream);           /* run all work on the caller's cudaStream_t */
+int mz_synchronize(mz_ctx *ctx);
+int mz_device_info(mz_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *free_bytes);
+
+/* ---- networks: init_representation / init_prediction / init_dynamics (src/Learning.jl:87,100,118) ----
+ * Weight blob = for each Dense in Flux.params order: W (out,in) column-major (W[o + out*k]) then b[out]. */
+int     mz_num_params(const mz_config *cfg, int net);
+int     mz_init_weights(mz_ctx *ctx, uint64_t seed);         /* Flux.glorot_uniform, Philox-keyed */
+int     mz_set_weights(mz_ctx *ctx, int net, const float *blob, int64_t n);
+int     mz_get_weights(mz_ctx *ctx, int net, float *blob, int64_t n);
+/* batched callables, host buffers: repr(x (W,H,planes,B)) -> (hidden,B); pred(h) -> (value(1,B), policy(A,B));
+ * dyn(sa (W,H,C+1,B)) -> (state(hidden,B), reward(1,B)) */
+int mz_representation(mz_ctx *ctx, int B, const float *stacked_obs, float *hidden);
+int mz_prediction(mz_ctx *ctx, int B, const float *hidden, float *value, float *policy);
+int mz_dynamics(mz_ctx *ctx, int B, const float *state_action, float *next_hidden, float *reward);
+
+/* ---- environment: games/tictactoe/game.jl (reset! :15, env(action) :45-52, legal_action_space :35-43,
+ *      is_terminated :85, reward :87-100), batched over n boards in SoA form ---- */
+int mz_env_reset(mz_ctx *ctx, int n, uint64_t *p1, uint64_t *p2, int32_t *player);
+int mz_env_step(mz_ctx *ctx, int n, uint64_t *p1, uint64_t *p2, int32_t *player, const int32_t *action,
+                float *reward /* RLBase.reward(env, mover) */, int32_t *done, uint32_t *legal_mask);
+int mz_env_legal(mz_ctx *ctx, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, uint32_t *legal_mask);
+int mz_env_observation(mz_ctx *ctx, int n, const uint64_t *p1, const uint64_t *p2, float *obs /* [n][C][H][W] */);
+
+/* ---- MCTS: run_mcts (src/SelfPlay.jl:230-285), batched over n independent roots -------------- */
+int mz_run_mcts(mz_ctx *ctx, int n, const float *stacked_obs /* [n][stack] */, const uint32_t *legal_mask,
+                const int32_t *to_play, int exploration, const uint64_t *game_id, const int32_t *move_idx,
+                int32_t *visit_counts /* [n][A] */, float *root_value /* [n] */, float *root_priors /* [n][A], may be NULL */);
+/* select_action (src/SelfPlay.jl:293-306) */
+int mz_select_action(mz_ctx *ctx, int n, const int32_t *visit_counts, const uint32_t *legal_mask, float temperature,
+                     const uint64_t *game_id, const int32_t *move_idx, int32_t *action);
+
+/* ---- self-play: play_game / self_play! (src/SelfPlay.jl:330-419) + save_game (src/ReplayBuffer.jl:133-161)
+ * Plays games first_game .. first_game+n_games-1 on the ctx's num_slots device-resident game slots and
+ * appends every finished GameHistory to the device replay ring under the next game number. */
+int mz_self_play(mz_ctx *ctx, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves);
+/* replay ring state: number of stored games, key (game number) of the oldest one, total stored positions */
+int mz_replay_info(mz_ctx *ctx, int64_t *n_games, int64_t *first_key, int64_t *total_samples);
+/* GameHistory export (src/Constructors.jl:6-16) for keys key0 .. key0+n-1, padded to Tmax = max_moves+1:
+ * game_id[n], T[n], observation_history [n][Tmax][C][H][W], action_history [n][Tmax], reward_history [n][Tmax],
+ * to_play_history [n][Tmax], child_visits [n][Tmax][A], root_values [n][Tmax] */
+int mz_history_export(mz_ctx *ctx, int64_t key0, int n, int64_t *game_id, int32_t *T, float *obs, int32_t *actions,
+                      float *rewards, int32_t *to_play, float *child_visits, float *root_values);
+/* load n histories (same layout) into the ring, as save_game would (for learner-only runs and tests) */
+int mz_history_import(mz_ctx *ctx, int n, const int64_t *game_id, const int32_t *T, const float *obs, const int32_t *actions,
+                      const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values);
+int mz_replay_clear(mz_ctx *ctx);
+
+/* ---- replay sampling + targets: get_batch (src/ReplayBuffer.jl:188-217) ---------------------- */
+int mz_get_batch(mz_ctx *ctx, uint64_t step, int32_t *index_batch /* [B][2] (game key, position) */, float *obs_batch,
+                 float *action_batch, float *value_batch, float *reward_batch, float *policy_batch, float *gscale);
+
+/* ---- learner: learning! (src/Learning.jl:306-438) --------------------------------------------- */
+/* forward unroll + loss on a caller-supplied batch (parity entry point; Learning.jl:347-374, 261-288) */
+int mz_learn_forward(mz_ctx *ctx, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                     const float *reward_batch, const float *policy_batch, const float *gscale, float *pred_values,
+                     float *pred_rewards, float *pred_policies, float *losses /* [3] */);
+/* one training step t (1-based): get_batch(step=t) on the device ring, unroll, loss, gradients (grad_mode),
+ * gradient allreduce when a communicator is attached, ADAM with the Cos schedule (Learning.jl:382-397) */
+int mz_learn_step(mz_ctx *ctx, int64_t t, int grad_mode, float *losses /* [3] */);
+/* same update on a caller-supplied batch (parity entry point) */
+int mz_learn_step_batch(mz_ctx *ctx, int64_t t, int grad_mode, int B, const float *obs_batch, const float *action_batch,
+                        const float *value_batch, const float *reward_batch, const float *policy_batch,
+                        const float *gscale, float *losses);
+int mz_optimizer_reset(mz_ctx *ctx);
+
+/* ---- multi-GPU: data-parallel learner, one process per GPU (no reference counterpart; the reference's
+ * only transport is Julia Distributed, games/tictactoe/main.jl:1-2,15-21) ------------------------- */
+int mz_comm_unique_id(uint8_t id[128]);
+int mz_comm_init(mz_ctx *ctx, int rank, int nranks, const uint8_t id[128]);
+int mz_comm_destroy(mz_ctx *ctx);
+
+/* ---- instrumentation --------------------------------------------------------------------------- */
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int mz_launch_count(mz_ctx *ctx, int64_t *n);
+/* device time (ms) and launch count accumulated per kernel family since the last reset;
+ * family: 0 self-play move kernel, 1 save/refill, 2 replay gather, 3 learner fwd/loss, 4 adam, 5 nn batch, 6 env */
+int mz_kernel_time(mz_ctx *ctx, int family, double *ms, int64_t *launches);
+int mz_kernel_time_reset(mz_ctx *ctx, int enable);
+/* tree statistics of the last mz_self_play call: mean legal actions L and mean selection depth d */
+int mz_search_stats(mz_ctx *ctx, double *mean_legal, double *mean_depth);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,708 @@
+// mz_api.cu -- the C ABI of libmuzero_b200 (include/muzero_b200.h): context management, host<->device staging
+// and kernel launches.  No torch types, no CPU fallback: every compute entry point launches sm_100a kernels.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "mz_host.h"
+#include "mz_learner.cuh"
+
+namespace {
+
+thread_local std::string tl_error;
+
+struct dev_buf {   // grow-only device scratch
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct timed_launch { cudaEvent_t a, b; int family; };
+
+struct nccl_api {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
+    }
+} g_nccl;
+
+}  // namespace
+
+struct mz_ctx {
+    mz_config cfg; mzh::model M; int device = 0;
+    cudaStream_t stream = nullptr; bool own_stream = false;
+    std::string err;
+    size_t smem_bytes = 0; int sm_count = 0;
+    float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
+    double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
+    void *d_trees = nullptr;
+    mz_slots slots{}; mz_ring ring{};
+    unsigned long long *d_stats = nullptr;
+    mz_batch batch{}; int batch_cap = 0;
+    float *d_pv = nullptr, *d_pr = nullptr, *d_pp = nullptr, *d_rowv = nullptr, *d_rowp = nullptr, *d_rowinvg = nullptr;
+    double *d_rowr = nullptr, *d_lossout = nullptr;
+    int64_t *h_counters = nullptr; double *h_lossout = nullptr; unsigned long long *h_stats = nullptr;   // pinned
+    dev_buf scratch[12];
+    int64_t adam_t = 0; double bp1 = 0.9, bp2 = 0.999;
+    ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    int64_t launches = 0; bool timing = false; std::vector<timed_launch> timed; double fam_ms[8] = {0}; int64_t fam_n[8] = {0};
+    double last_mean_legal = 0, last_mean_depth = 0;
+};
+
+namespace {
+
+int fail(mz_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    tl_error = buf;
+    if (c) c->err = buf;
+    return code;
+}
+#define MZ_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((c), MZ_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define MZ_CHECK_CTX(c) do { if (!(c)) return fail(nullptr, MZ_E_ARG, "ctx is NULL"); MZ_CUDA((c), cudaSetDevice((c)->device)); } while (0)
+
+struct launch_scope {   // counts launches and, when enabled, brackets them with events on the ctx stream
+    mz_ctx *c; int family; cudaEvent_t a = nullptr, b = nullptr;
+    launch_scope(mz_ctx *c_, int fam) : c(c_), family(fam) {
+        c->launches++;
+        if (c->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~launch_scope() { if (c->timing) { cudaEventRecord(b, c->stream); c->timed.push_back({a, b, family}); } }
+};
+
+void collect_timings(mz_ctx *c) {
+    if (c->timed.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto &t : c->timed) {
+        float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
+        c->fam_ms[t.family] += ms; c->fam_n[t.family]++;
+        cudaEventDestroy(t.a); cudaEventDestroy(t.b);
+    }
+    c->timed.clear();
+}
+
+template <typename T> cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
+
+int alloc_batch(mz_ctx *c, int B) {
+    if (B <= c->batch_cap) return MZ_OK;
+    const mz_params &P = c->M.P; int K1 = P.K + 1;
+    void *ptrs[] = {c->batch.index, c->batch.obs, c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale,
+                    c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    MZ_CUDA(c, dmalloc(&c->batch.index, (size_t)B * 2)); MZ_CUDA(c, dmalloc(&c->batch.obs, (size_t)B * P.stack_size));
+    MZ_CUDA(c, dmalloc(&c->batch.actions, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.values, (size_t)B * K1));
+    MZ_CUDA(c, dmalloc(&c->batch.rewards, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.policies, (size_t)B * K1 * P.A));
+    MZ_CUDA(c, dmalloc(&c->batch.gscale, (size_t)B));
+    MZ_CUDA(c, dmalloc(&c->d_pv, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->d_pr, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->d_pp, (size_t)B * K1 * P.A));
+    MZ_CUDA(c, dmalloc(&c->d_rowv, (size_t)B)); MZ_CUDA(c, dmalloc(&c->d_rowp, (size_t)B)); MZ_CUDA(c, dmalloc(&c->d_rowinvg, (size_t)B));
+    MZ_CUDA(c, dmalloc(&c->d_rowr, (size_t)B));
+    c->batch_cap = B;
+    return MZ_OK;
+}
+
+int upload_weights(mz_ctx *c, const std::vector<float> &src) {
+    std::vector<float> dev((size_t)c->M.P.total_floats);
+    mzh::pack_weights(c->M.P, src.data(), dev.data());
+    MZ_CUDA(c, cudaMemcpyAsync(c->d_w, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int download_weights(mz_ctx *c, std::vector<float> &src) {
+    std::vector<float> dev((size_t)c->M.P.total_floats);
+    MZ_CUDA(c, cudaMemcpyAsync(dev.data(), c->d_w, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    src.resize((size_t)c->M.P.n_params);
+    mzh::unpack_weights(c->M.P, dev.data(), src.data());
+    return MZ_OK;
+}
+
+int read_counters(mz_ctx *c) {
+    MZ_CUDA(c, cudaMemcpyAsync(c->h_counters, c->ring.counters, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int write_counters(mz_ctx *c) {
+    MZ_CUDA(c, cudaMemcpyAsync(c->ring.counters, c->h_counters, 8 * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+
+template <typename T> int h2d(mz_ctx *c, dev_buf &b, const T *host, size_t n, T **out) {
+    MZ_CUDA(c, b.ensure(n * sizeof(T) + 16));
+    if (host && n) MZ_CUDA(c, cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = (T *)b.p;
+    return MZ_OK;
+}
+template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
+    if (host && n) MZ_CUDA(c, cudaMemcpyAsync(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return MZ_OK;
+}
+#define MZ_TRY(x) do { int r_ = (x); if (r_ != MZ_OK) return r_; } while (0)
+
+int launch_learn_forward(mz_ctx *c, int B) {
+    const mz_params &P = c->M.P;
+    mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
+    a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
+    { launch_scope ls(c, 3); mz_k_learn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    { launch_scope ls(c, 3); mz_k_loss_rows<<<(B + 127) / 128, 128, 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
+    { launch_scope ls(c, 3); mz_k_loss_reduce<<<1, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
+// losses (Learning.jl:283-287): data loss = value_loss + reward_loss + policy_loss; each net adds its own sum(theta^2)
+int finish_losses(mz_ctx *c, int B, float *losses) {
+    MZ_CUDA(c, cudaMemcpyAsync(c->h_lossout, c->d_lossout, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    const double *o = c->h_lossout;
+    float value_loss = (float)(o[0] / (double)B);
+    float policy_loss = (float)((o[1] / (double)B) * (o[2] / (double)B));   // mean_j(s_j) * mean_i(1/g_i), Q21
+    float data;
+    if (c->cfg.intermediate_rewards) data = (float)(((double)value_loss + o[3] / (double)B) + (double)policy_loss);
+    else data = (value_loss + 0.0f) + policy_loss;
+    for (int n = 0; n < 3; n++) losses[n] = data + (float)o[4 + n];
+    return MZ_OK;
+}
+int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
+    if (grad_mode != MZ_GRAD_REFERENCE_L2) return fail(c, MZ_E_UNSUPPORTED, "grad_mode %d is not implemented yet (only MZ_GRAD_REFERENCE_L2)", grad_mode);
+    const int n = c->M.P.total_floats;
+    if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
+    { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
+    float scale = 1.0f;
+    if (c->comm) {   // data-parallel: sum gradients over ranks, average in the update
+        ncclResult_t r = g_nccl.AllReduce(c->d_grad, c->d_grad, (size_t)n, ncclFloat, ncclSum, c->comm, c->stream);
+        if (r != ncclSuccess) return fail(c, MZ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+        scale = 1.0f / (float)c->nranks;
+    }
+    { launch_scope ls(c, 4); mz_k_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_m, c->d_v, c->d_grad, mzh::cos_schedule(t), c->bp1, c->bp2, scale); }
+    MZ_CUDA(c, cudaGetLastError());
+    c->bp1 *= 0.9; c->bp2 *= 0.999; c->adam_t++;
+    return MZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mz_abi_version(void) { return MZ_ABI_VERSION; }
+int mz_default_config(mz_config *cfg) { if (!cfg) return fail(nullptr, MZ_E_ARG, "cfg is NULL"); mzh::default_config(cfg); return MZ_OK; }
+int mz_julia_dict_order(int A, int32_t *order) { if (A < 1 || A > MZ_MAX_A || !order) return fail(nullptr, MZ_E_ARG, "bad arguments"); mzh::julia_dict_order(A, order); return MZ_OK; }
+const char *mz_last_error(mz_ctx *ctx) { return ctx ? ctx->err.c_str() : tl_error.c_str(); }
+
+int mz_num_params(const mz_config *cfg, int net) {
+    if (!cfg || net < 0 || net > 3) return fail(nullptr, MZ_E_ARG, "bad arguments");
+    mzh::model M; if (const char *e = mzh::build_model(*cfg, M)) return fail(nullptr, MZ_E_ARG, "%s", e);
+    return mzh::net_params(M.P, net);
+}
+
+int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
+    if (!cfg || !out) return fail(nullptr, MZ_E_ARG, "cfg/out is NULL");
+    *out = nullptr;
+    mz_ctx *c = new mz_ctx();
+    c->cfg = *cfg; c->device = device;
+    if (const char *e = mzh::build_model(*cfg, c->M)) { int r = fail(nullptr, MZ_E_ARG, "%s", e); delete c; return r; }
+    if (cfg->replay_buffer_size < cfg->num_slots) { int r = fail(nullptr, MZ_E_ARG, "replay_buffer_size must be >= num_slots"); delete c; return r; }
+    if (cfg->nn_mode != MZ_NN_FP32_EXACT) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "nn_mode %d not available in this build", cfg->nn_mode); delete c; return r; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }
+#define MZ_CREATE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int r_ = fail(nullptr, MZ_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); mz_destroy(c); return r_; } } while (0)
+    MZ_CREATE(cudaSetDevice(device));
+    cudaDeviceProp prop; MZ_CREATE(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); mz_destroy(c); return r; }
+    c->sm_count = prop.multiProcessorCount;
+    const mz_params &P = c->M.P;
+    c->smem_bytes = mz_smem_bytes(c->M.max_dim, c->M.max_layer_floats, P.hidden_pad, P.S);
+    if (c->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
+    MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_API>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    MZ_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
+    const size_t nf = (size_t)P.total_floats;
+    MZ_CREATE(dmalloc(&c->d_w, nf)); MZ_CREATE(dmalloc(&c->d_m, nf)); MZ_CREATE(dmalloc(&c->d_v, nf)); MZ_CREATE(dmalloc(&c->d_grad, nf));
+    MZ_CREATE(cudaMemset(c->d_w, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_m, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_v, 0, nf * 4));
+    MZ_CREATE(dmalloc(&c->d_pbc0, c->M.pbc0.size())); MZ_CREATE(dmalloc(&c->d_sqrtN, c->M.sqrtN.size()));
+    MZ_CREATE(cudaMemcpy(c->d_pbc0, c->M.pbc0.data(), c->M.pbc0.size() * 8, cudaMemcpyHostToDevice));
+    MZ_CREATE(cudaMemcpy(c->d_sqrtN, c->M.sqrtN.data(), c->M.sqrtN.size() * 8, cudaMemcpyHostToDevice));
+    const size_t G = (size_t)cfg->num_slots, Tm = (size_t)P.Tmax, R = (size_t)cfg->replay_buffer_size;
+    MZ_CREATE(cudaMalloc(&c->d_trees, G * (size_t)P.tree_stride_bytes));
+    mz_slots &s = c->slots;
+    MZ_CREATE(dmalloc(&s.p1, G)); MZ_CREATE(dmalloc(&s.p2, G)); MZ_CREATE(dmalloc(&s.player, G)); MZ_CREATE(dmalloc(&s.T, G));
+    MZ_CREATE(dmalloc(&s.status, G)); MZ_CREATE(dmalloc(&s.game_id, G));
+    MZ_CREATE(dmalloc(&s.h_p1, G * Tm)); MZ_CREATE(dmalloc(&s.h_p2, G * Tm)); MZ_CREATE(dmalloc(&s.h_action, G * Tm));
+    MZ_CREATE(dmalloc(&s.h_reward, G * Tm)); MZ_CREATE(dmalloc(&s.h_to_play, G * Tm)); MZ_CREATE(dmalloc(&s.h_cv, G * Tm * P.A)); MZ_CREATE(dmalloc(&s.h_rv, G * Tm));
+    MZ_CREATE(cudaMemset(s.status, 0, G * sizeof(int32_t)));
+    mz_ring &r = c->ring; r.capacity = (int64_t)R;
+    MZ_CREATE(dmalloc(&r.game_id, R)); MZ_CREATE(dmalloc(&r.T, R));
+    MZ_CREATE(dmalloc(&r.h_p1, R * Tm)); MZ_CREATE(dmalloc(&r.h_p2, R * Tm)); MZ_CREATE(dmalloc(&r.h_action, R * Tm));
+    MZ_CREATE(dmalloc(&r.h_reward, R * Tm)); MZ_CREATE(dmalloc(&r.h_to_play, R * Tm)); MZ_CREATE(dmalloc(&r.h_cv, R * Tm * P.A)); MZ_CREATE(dmalloc(&r.h_rv, R * Tm));
+    MZ_CREATE(dmalloc(&r.counters, 8)); MZ_CREATE(cudaMemset(r.counters, 0, 8 * sizeof(int64_t)));
+    MZ_CREATE(cudaMemset(r.T, 0, R * sizeof(int32_t)));
+    MZ_CREATE(dmalloc(&c->d_stats, 4)); MZ_CREATE(cudaMemset(c->d_stats, 0, 4 * sizeof(unsigned long long)));
+    MZ_CREATE(dmalloc(&c->d_lossout, 8));
+    MZ_CREATE(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(int64_t)));
+    MZ_CREATE(cudaMallocHost((void **)&c->h_lossout, 8 * sizeof(double)));
+    MZ_CREATE(cudaMallocHost((void **)&c->h_stats, 4 * sizeof(unsigned long long)));
+    MZ_CREATE(cudaDeviceSynchronize());
+#undef MZ_CREATE
+    *out = c;
+    return MZ_OK;
+}
+
+int mz_destroy(mz_ctx *c) {
+    if (!c) return MZ_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    collect_timings(c);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    void *ptrs[] = {c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+                    c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
+                    c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
+                    c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
+                    c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale, c->d_pv, c->d_pr, c->d_pp,
+                    c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &b : c->scratch) b.release();
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_lossout) cudaFreeHost(c->h_lossout);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MZ_OK;
+}
+
+int mz_set_stream(mz_ctx *c, void *cuda_stream) {
+    MZ_CHECK_CTX(c);
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+    c->stream = (cudaStream_t)cuda_stream;
+    return MZ_OK;
+}
+int mz_synchronize(mz_ctx *c) { MZ_CHECK_CTX(c); MZ_CUDA(c, cudaStreamSynchronize(c->stream)); return MZ_OK; }
+int mz_device_info(mz_ctx *c, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *free_bytes) {
+    MZ_CHECK_CTX(c);
+    cudaDeviceProp prop; MZ_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    size_t fr = 0, tot = 0; MZ_CUDA(c, cudaMemGetInfo(&fr, &tot));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (free_bytes) *free_bytes = (int64_t)fr;
+    return MZ_OK;
+}
+
+// ---- weights ----------------------------------------------------------------------------------------
+int mz_init_weights(mz_ctx *c, uint64_t seed) {
+    MZ_CHECK_CTX(c);
+    std::vector<float> src((size_t)c->M.P.n_params);
+    mzh::init_weights(c->M.P, seed, src.data());
+    return upload_weights(c, src);
+}
+int mz_set_weights(mz_ctx *c, int net, const float *blob, int64_t n) {
+    MZ_CHECK_CTX(c);
+    if (net < 0 || net > 3 || !blob) return fail(c, MZ_E_ARG, "bad net id or NULL blob");
+    if (n != mzh::net_params(c->M.P, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, mzh::net_params(c->M.P, net));
+    std::vector<float> src;
+    MZ_TRY(download_weights(c, src));
+    memcpy(src.data() + mzh::net_src_offset(c->M.P, net), blob, (size_t)n * sizeof(float));
+    return upload_weights(c, src);
+}
+int mz_get_weights(mz_ctx *c, int net, float *blob, int64_t n) {
+    MZ_CHECK_CTX(c);
+    if (net < 0 || net > 3 || !blob) return fail(c, MZ_E_ARG, "bad net id or NULL blob");
+    if (n != mzh::net_params(c->M.P, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, mzh::net_params(c->M.P, net));
+    std::vector<float> src;
+    MZ_TRY(download_weights(c, src));
+    memcpy(blob, src.data() + mzh::net_src_offset(c->M.P, net), (size_t)n * sizeof(float));
+    return MZ_OK;
+}
+
+// ---- batched network callables -------------------------------------------------------------------------
+static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, size_t n1, float *out2, size_t n2) {
+    MZ_CHECK_CTX(c);
+    if (B < 0 || (B > 0 && (!in || !out1))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (B == 0) return MZ_OK;
+    const mz_params &P = c->M.P;
+    const int in_dim = P.layers[P.nets[net].first].in;
+    float *d_in, *d_o1, *d_o2;
+    MZ_TRY(h2d(c, c->scratch[0], in, (size_t)B * in_dim, &d_in));
+    MZ_TRY(h2d<float>(c, c->scratch[1], nullptr, (size_t)B * n1, &d_o1));
+    MZ_TRY(h2d<float>(c, c->scratch[2], nullptr, (size_t)B * (n2 ? n2 : 1), &d_o2));
+    mz_nn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.net = net; a.in = d_in; a.out1 = d_o1; a.out2 = d_o2;
+    { launch_scope ls(c, 5); mz_k_nn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    MZ_CUDA(c, cudaGetLastError());
+    MZ_TRY(d2h(c, out1, d_o1, (size_t)B * n1));
+    if (n2 && out2) MZ_TRY(d2h(c, out2, d_o2, (size_t)B * n2));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int mz_representation(mz_ctx *c, int B, const float *stacked_obs, float *hidden) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    return nn_forward(c, 0, B, stacked_obs, hidden, (size_t)c->M.P.hidden, nullptr, 0);
+}
+int mz_prediction(mz_ctx *c, int B, const float *hidden, float *value, float *policy) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    if (B > 0 && !policy) return fail(c, MZ_E_ARG, "NULL buffer");
+    return nn_forward(c, 1, B, hidden, value, 1, policy, (size_t)c->M.P.A);
+}
+int mz_dynamics(mz_ctx *c, int B, const float *state_action, float *next_hidden, float *reward) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    if (B > 0 && !reward) return fail(c, MZ_E_ARG, "NULL buffer");
+    return nn_forward(c, 2, B, state_action, next_hidden, (size_t)c->M.P.hidden, reward, 1);
+}
+
+// ---- environment -----------------------------------------------------------------------------------------
+int mz_env_reset(mz_ctx *c, int n, uint64_t *p1, uint64_t *p2, int32_t *player) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !player))) return fail(c, MZ_E_ARG, "NULL buffer");
+    for (int i = 0; i < n; i++) { p1[i] = 0; p2[i] = 0; player[i] = 1; }   // reset! (game.jl:15-20): a constant fill, no kernel needed
+    return MZ_OK;
+}
+static int env_call(mz_ctx *c, int n, uint64_t *p1, uint64_t *p2, int32_t *player, const int32_t *action, float *reward, int32_t *done, uint32_t *legal, bool writeback) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !player))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    const mz_params &P = c->M.P;
+    if (action) for (int i = 0; i < n; i++) if (action[i] < 1 || action[i] > P.A) return fail(c, MZ_E_ARG, "action %d out of range at %d", action[i], i);
+    uint64_t *d1, *d2; int32_t *dp, *da = nullptr, *dd; float *dr; uint32_t *dl;
+    MZ_TRY(h2d(c, c->scratch[0], p1, (size_t)n, &d1)); MZ_TRY(h2d(c, c->scratch[1], p2, (size_t)n, &d2)); MZ_TRY(h2d(c, c->scratch[2], player, (size_t)n, &dp));
+    if (action) MZ_TRY(h2d(c, c->scratch[3], action, (size_t)n, &da));
+    MZ_TRY(h2d<float>(c, c->scratch[4], nullptr, (size_t)n, &dr)); MZ_TRY(h2d<int32_t>(c, c->scratch[5], nullptr, (size_t)n, &dd)); MZ_TRY(h2d<uint32_t>(c, c->scratch[6], nullptr, (size_t)n, &dl));
+    { launch_scope ls(c, 6); mz_k_env_step<<<(n + 255) / 256, 256, 0, c->stream>>>(P, n, d1, d2, dp, da, dr, dd, dl); }
+    MZ_CUDA(c, cudaGetLastError());
+    if (writeback) { MZ_TRY(d2h(c, p1, d1, (size_t)n)); MZ_TRY(d2h(c, p2, d2, (size_t)n)); MZ_TRY(d2h(c, player, dp, (size_t)n)); }
+    MZ_TRY(d2h(c, reward, dr, (size_t)n)); MZ_TRY(d2h(c, done, dd, (size_t)n)); MZ_TRY(d2h(c, legal, dl, (size_t)n));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int mz_env_step(mz_ctx *c, int n, uint64_t *p1, uint64_t *p2, int32_t *player, const int32_t *action, float *reward, int32_t *done, uint32_t *legal_mask) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    if (n > 0 && !action) return fail(c, MZ_E_ARG, "NULL action buffer");
+    return env_call(c, n, p1, p2, player, action, reward, done, legal_mask, true);
+}
+int mz_env_legal(mz_ctx *c, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, uint32_t *legal_mask) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    return env_call(c, n, (uint64_t *)p1, (uint64_t *)p2, (int32_t *)player, nullptr, nullptr, nullptr, legal_mask, false);
+}
+int mz_env_observation(mz_ctx *c, int n, const uint64_t *p1, const uint64_t *p2, float *obs) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !obs))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    const mz_params &P = c->M.P;
+    uint64_t *d1, *d2; float *dobs;
+    MZ_TRY(h2d(c, c->scratch[0], p1, (size_t)n, &d1)); MZ_TRY(h2d(c, c->scratch[1], p2, (size_t)n, &d2));
+    MZ_TRY(h2d<float>(c, c->scratch[2], nullptr, (size_t)n * P.obs_size, &dobs));
+    size_t tot = (size_t)n * P.obs_size;
+    { launch_scope ls(c, 6); mz_k_env_obs<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(P, n, d1, d2, dobs); }
+    MZ_CUDA(c, cudaGetLastError());
+    MZ_TRY(d2h(c, obs, dobs, tot));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+
+// ---- MCTS ------------------------------------------------------------------------------------------------
+int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *legal_mask, const int32_t *to_play, int exploration,
+                const uint64_t *game_id, const int32_t *move_idx, int32_t *visit_counts, float *root_value, float *root_priors) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!stacked_obs || !legal_mask || !to_play || !game_id || !move_idx || !visit_counts || !root_value))) return fail(c, MZ_E_ARG, "NULL buffer");
+    const mz_params &P = c->M.P;
+    for (int i = 0; i < n; i++) {
+        if (legal_mask[i] == 0 || (legal_mask[i] >> P.A) != 0) return fail(c, MZ_E_ARG, "legal actions of root %d must be a non-empty subset of the action space (SelfPlay.jl:243-244)", i);
+        if (to_play[i] < 1 || to_play[i] > P.P) return fail(c, MZ_E_ARG, "to_play of root %d out of range", i);
+    }
+    read_counters(c);
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    const int cap = c->cfg.num_slots;
+    for (int off = 0; off < n; off += cap) {
+        int m = n - off < cap ? n - off : cap;
+        float *d_st, *d_rv, *d_pri; uint32_t *d_legal; int32_t *d_tp, *d_mv, *d_vc; uint64_t *d_gid;
+        MZ_TRY(h2d(c, c->scratch[0], stacked_obs + (size_t)off * P.stack_size, (size_t)m * P.stack_size, &d_st));
+        MZ_TRY(h2d(c, c->scratch[1], legal_mask + off, (size_t)m, &d_legal)); MZ_TRY(h2d(c, c->scratch[2], to_play + off, (size_t)m, &d_tp));
+        MZ_TRY(h2d(c, c->scratch[3], game_id + off, (size_t)m, &d_gid)); MZ_TRY(h2d(c, c->scratch[4], move_idx + off, (size_t)m, &d_mv));
+        MZ_TRY(h2d<int32_t>(c, c->scratch[5], nullptr, (size_t)m * P.A, &d_vc)); MZ_TRY(h2d<float>(c, c->scratch[6], nullptr, (size_t)m, &d_rv));
+        MZ_TRY(h2d<float>(c, c->scratch[7], nullptr, (size_t)m * P.A, &d_pri));
+        mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = m; a.max_dim = c->M.max_dim;
+        a.max_layer_floats = c->M.max_layer_floats; a.exploration = exploration; a.stacked = d_st; a.legal = d_legal; a.to_play = d_tp; a.game_id = d_gid;
+        a.move_idx = d_mv; a.visit_counts = d_vc; a.root_value = d_rv; a.root_priors = d_pri; a.stats = nullptr;
+        { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        MZ_CUDA(c, cudaGetLastError());
+        MZ_TRY(d2h(c, visit_counts + (size_t)off * P.A, d_vc, (size_t)m * P.A)); MZ_TRY(d2h(c, root_value + off, d_rv, (size_t)m));
+        if (root_priors) MZ_TRY(d2h(c, root_priors + (size_t)off * P.A, d_pri, (size_t)m * P.A));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return MZ_OK;
+}
+
+int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32_t *legal_mask, float temperature, const uint64_t *game_id,
+                     const int32_t *move_idx, int32_t *action) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!visit_counts || !legal_mask || !game_id || !move_idx || !action))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    const mz_params &P = c->M.P;
+    int32_t *d_vc, *d_mv, *d_act; uint32_t *d_legal; uint64_t *d_gid;
+    MZ_TRY(h2d(c, c->scratch[0], visit_counts, (size_t)n * P.A, &d_vc)); MZ_TRY(h2d(c, c->scratch[1], legal_mask, (size_t)n, &d_legal));
+    MZ_TRY(h2d(c, c->scratch[2], game_id, (size_t)n, &d_gid)); MZ_TRY(h2d(c, c->scratch[3], move_idx, (size_t)n, &d_mv));
+    MZ_TRY(h2d<int32_t>(c, c->scratch[4], nullptr, (size_t)n, &d_act));
+    { launch_scope ls(c, 6); mz_k_select_action<<<(n + 127) / 128, 128, 0, c->stream>>>(P, n, d_vc, d_legal, temperature, d_gid, d_mv, d_act); }
+    MZ_CUDA(c, cudaGetLastError());
+    MZ_TRY(d2h(c, action, d_act, (size_t)n));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+
+// ---- self-play ---------------------------------------------------------------------------------------------
+int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves) {
+    MZ_CHECK_CTX(c);
+    if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
+    if (first_game + (uint64_t)n_games > 0xffffffffull) return fail(c, MZ_E_ARG, "game ids must fit in 32 bits (Philox counter)");
+    const mz_params &P = c->M.P;
+    const int G = c->cfg.num_slots;
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "previous self-play did not finish");
+    c->h_counters[3] = (int64_t)first_game; c->h_counters[4] = (int64_t)first_game + n_games; c->h_counters[5] = 0;
+    MZ_TRY(write_counters(c));
+    MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 4 * sizeof(unsigned long long), c->stream));
+    mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = G; a.max_dim = c->M.max_dim;
+    a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
+    a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;
+    int64_t total_moves = 0;
+    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
+    for (int64_t guard = 0;; guard++) {
+        MZ_CUDA(c, cudaGetLastError());
+        MZ_TRY(read_counters(c));
+        int64_t active = c->h_counters[5];
+        if (active == 0) break;
+        if (guard > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
+        total_moves += active;
+        { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
+    }
+    MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (simulations) *simulations = (int64_t)c->h_stats[1];
+    if (moves) *moves = total_moves;
+    c->last_mean_depth = c->h_stats[1] ? (double)c->h_stats[0] / (double)c->h_stats[1] : 0.0;
+    c->last_mean_legal = c->h_stats[3] ? (double)c->h_stats[2] / (double)c->h_stats[3] : 0.0;
+    return MZ_OK;
+}
+
+int mz_replay_info(mz_ctx *c, int64_t *n_games, int64_t *first_key, int64_t *total_samples) {
+    MZ_CHECK_CTX(c);
+    MZ_TRY(read_counters(c));
+    int64_t played = c->h_counters[0], n = played < c->ring.capacity ? played : c->ring.capacity;
+    if (n_games) *n_games = n;
+    if (first_key) *first_key = played - n + 1;
+    if (total_samples) *total_samples = c->h_counters[2];
+    return MZ_OK;
+}
+int mz_replay_clear(mz_ctx *c) {
+    MZ_CHECK_CTX(c);
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    for (int i = 0; i < 8; i++) c->h_counters[i] = 0;
+    MZ_TRY(write_counters(c));
+    MZ_CUDA(c, cudaMemsetAsync(c->ring.T, 0, (size_t)c->ring.capacity * sizeof(int32_t), c->stream));
+    return MZ_OK;
+}
+
+int mz_history_export(mz_ctx *c, int64_t key0, int n, int64_t *game_id, int32_t *T, float *obs, int32_t *actions, float *rewards,
+                      int32_t *to_play, float *child_visits, float *root_values) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!game_id || !T || !obs || !actions || !rewards || !to_play || !child_visits || !root_values))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(read_counters(c));
+    int64_t played = c->h_counters[0], have = played < c->ring.capacity ? played : c->ring.capacity, first = played - have + 1;
+    if (key0 < first || key0 + n - 1 > played) return fail(c, MZ_E_ARG, "keys %lld..%lld not in the buffer (holds %lld..%lld)", (long long)key0, (long long)(key0 + n - 1), (long long)first, (long long)played);
+    const mz_params &P = c->M.P; const size_t Tm = (size_t)P.Tmax, N = (size_t)n;
+    int64_t *d_gid; int32_t *d_T, *d_act, *d_tp; float *d_obs, *d_rew, *d_cv, *d_rv;
+    MZ_TRY(h2d<int64_t>(c, c->scratch[0], nullptr, N, &d_gid)); MZ_TRY(h2d<int32_t>(c, c->scratch[1], nullptr, N, &d_T));
+    MZ_TRY(h2d<float>(c, c->scratch[2], nullptr, N * Tm * P.obs_size, &d_obs)); MZ_TRY(h2d<int32_t>(c, c->scratch[3], nullptr, N * Tm, &d_act));
+    MZ_TRY(h2d<float>(c, c->scratch[4], nullptr, N * Tm, &d_rew)); MZ_TRY(h2d<int32_t>(c, c->scratch[5], nullptr, N * Tm, &d_tp));
+    MZ_TRY(h2d<float>(c, c->scratch[6], nullptr, N * Tm * P.A, &d_cv)); MZ_TRY(h2d<float>(c, c->scratch[7], nullptr, N * Tm, &d_rv));
+    size_t tot = N * Tm * P.obs_size;
+    { launch_scope ls(c, 2); mz_k_history_export<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(P, c->ring, key0, n, d_gid, d_T, d_obs, d_act, d_rew, d_tp, d_cv, d_rv); }
+    MZ_CUDA(c, cudaGetLastError());
+    MZ_TRY(d2h(c, game_id, d_gid, N)); MZ_TRY(d2h(c, T, d_T, N)); MZ_TRY(d2h(c, obs, d_obs, tot)); MZ_TRY(d2h(c, actions, d_act, N * Tm));
+    MZ_TRY(d2h(c, rewards, d_rew, N * Tm)); MZ_TRY(d2h(c, to_play, d_tp, N * Tm)); MZ_TRY(d2h(c, child_visits, d_cv, N * Tm * P.A)); MZ_TRY(d2h(c, root_values, d_rv, N * Tm));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+
+int mz_history_import(mz_ctx *c, int n, const int64_t *game_id, const int32_t *T, const float *obs, const int32_t *actions, const float *rewards,
+                      const int32_t *to_play, const float *child_visits, const float *root_values) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!game_id || !T || !obs || !actions || !rewards || !to_play || !child_visits || !root_values))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    if (n > c->ring.capacity) return fail(c, MZ_E_ARG, "more histories than replay_buffer_size");
+    const mz_params &P = c->M.P; const size_t Tm = (size_t)P.Tmax, N = (size_t)n;
+    for (int i = 0; i < n; i++) if (T[i] < 1 || T[i] > P.Tmax) return fail(c, MZ_E_ARG, "history %d has length %d outside 1..%d", i, T[i], P.Tmax);
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    // save_game bookkeeping (ReplayBuffer.jl:147-160): counters + FIFO eviction accounting
+    std::vector<int32_t> oldT((size_t)c->ring.capacity);
+    MZ_CUDA(c, cudaMemcpyAsync(oldT.data(), c->ring.T, oldT.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    int64_t played = c->h_counters[0], key0 = played + 1;
+    for (int i = 0; i < n; i++) {
+        int64_t key = key0 + i, pos = (key - 1) % c->ring.capacity;
+        c->h_counters[1] += T[i]; c->h_counters[2] += T[i];
+        if (key > c->ring.capacity) c->h_counters[2] -= oldT[(size_t)pos];
+    }
+    c->h_counters[0] = played + n;
+    int64_t *d_gid; int32_t *d_T, *d_act, *d_tp; float *d_obs, *d_rew, *d_cv, *d_rv;
+    MZ_TRY(h2d(c, c->scratch[0], game_id, N, &d_gid)); MZ_TRY(h2d(c, c->scratch[1], T, N, &d_T));
+    MZ_TRY(h2d(c, c->scratch[2], obs, N * Tm * P.obs_size, &d_obs)); MZ_TRY(h2d(c, c->scratch[3], actions, N * Tm, &d_act));
+    MZ_TRY(h2d(c, c->scratch[4], rewards, N * Tm, &d_rew)); MZ_TRY(h2d(c, c->scratch[5], to_play, N * Tm, &d_tp));
+    MZ_TRY(h2d(c, c->scratch[6], child_visits, N * Tm * P.A, &d_cv)); MZ_TRY(h2d(c, c->scratch[7], root_values, N * Tm, &d_rv));
+    { launch_scope ls(c, 2); mz_k_history_import<<<(unsigned)((N * Tm + 127) / 128), 128, 0, c->stream>>>(P, c->ring, key0, n, d_gid, d_T, d_obs, d_act, d_rew, d_tp, d_cv, d_rv); }
+    MZ_CUDA(c, cudaGetLastError());
+    return write_counters(c);
+}
+
+// ---- replay sampling / learner -----------------------------------------------------------------------------
+static int gather_batch(mz_ctx *c, uint64_t step) {
+    const int B = c->cfg.batch_size;
+    MZ_TRY(alloc_batch(c, B));
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[0] < 1) return fail(c, MZ_E_STATE, "replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)");
+    { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, step, B, c->batch); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
+int mz_get_batch(mz_ctx *c, uint64_t step, int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
+                 float *policy_batch, float *gscale) {
+    MZ_CHECK_CTX(c);
+    if (!index_batch || !obs_batch || !action_batch || !value_batch || !reward_batch || !policy_batch || !gscale) return fail(c, MZ_E_ARG, "NULL buffer");
+    MZ_TRY(gather_batch(c, step));
+    const mz_params &P = c->M.P; const size_t B = (size_t)c->cfg.batch_size, K1 = (size_t)P.K + 1;
+    MZ_TRY(d2h(c, index_batch, c->batch.index, B * 2)); MZ_TRY(d2h(c, obs_batch, c->batch.obs, B * P.stack_size));
+    MZ_TRY(d2h(c, action_batch, c->batch.actions, B * K1)); MZ_TRY(d2h(c, value_batch, c->batch.values, B * K1));
+    MZ_TRY(d2h(c, reward_batch, c->batch.rewards, B * K1)); MZ_TRY(d2h(c, policy_batch, c->batch.policies, B * K1 * P.A));
+    MZ_TRY(d2h(c, gscale, c->batch.gscale, B));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+static int upload_batch(mz_ctx *c, int B, const float *obs, const float *act, const float *val, const float *rew, const float *pol, const float *gs) {
+    if (B < 1 || !obs || !act || !val || !rew || !pol || !gs) return fail(c, MZ_E_ARG, "bad batch");
+    MZ_TRY(alloc_batch(c, B));
+    const mz_params &P = c->M.P; const size_t K1 = (size_t)P.K + 1, b = (size_t)B;
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.obs, obs, b * P.stack_size * 4, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.actions, act, b * K1 * 4, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.values, val, b * K1 * 4, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.rewards, rew, b * K1 * 4, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.policies, pol, b * K1 * P.A * 4, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->batch.gscale, gs, b * 4, cudaMemcpyHostToDevice, c->stream));
+    return MZ_OK;
+}
+int mz_learn_forward(mz_ctx *c, int B, const float *obs_batch, const float *action_batch, const float *value_batch, const float *reward_batch,
+                     const float *policy_batch, const float *gscale, float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
+    MZ_CHECK_CTX(c);
+    if (!losses) return fail(c, MZ_E_ARG, "NULL losses");
+    MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
+    MZ_TRY(launch_learn_forward(c, B));
+    const mz_params &P = c->M.P; const size_t K1 = (size_t)P.K + 1, b = (size_t)B;
+    MZ_TRY(d2h(c, pred_values, c->d_pv, b * K1)); MZ_TRY(d2h(c, pred_rewards, c->d_pr, b * K1)); MZ_TRY(d2h(c, pred_policies, c->d_pp, b * K1 * P.A));
+    return finish_losses(c, B, losses);
+}
+int mz_learn_step_batch(mz_ctx *c, int64_t t, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                        const float *reward_batch, const float *policy_batch, const float *gscale, float *losses) {
+    MZ_CHECK_CTX(c);
+    if (!losses || t < 1) return fail(c, MZ_E_ARG, "bad arguments");
+    MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
+    MZ_TRY(launch_learn_forward(c, B));
+    MZ_TRY(launch_update(c, t, grad_mode));
+    return finish_losses(c, B, losses);
+}
+int mz_learn_step(mz_ctx *c, int64_t t, int grad_mode, float *losses) {
+    MZ_CHECK_CTX(c);
+    if (!losses || t < 1) return fail(c, MZ_E_ARG, "bad arguments");
+    MZ_TRY(gather_batch(c, (uint64_t)t));
+    MZ_TRY(launch_learn_forward(c, c->cfg.batch_size));
+    MZ_TRY(launch_update(c, t, grad_mode));
+    return finish_losses(c, c->cfg.batch_size, losses);
+}
+int mz_optimizer_reset(mz_ctx *c) {
+    MZ_CHECK_CTX(c);
+    MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)c->M.P.total_floats * 4, c->stream));
+    MZ_CUDA(c, cudaMemsetAsync(c->d_v, 0, (size_t)c->M.P.total_floats * 4, c->stream));
+    c->adam_t = 0; c->bp1 = 0.9; c->bp2 = 0.999;
+    return MZ_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------------------------------------------
+int mz_comm_unique_id(uint8_t id[128]) {
+    if (!id) return fail(nullptr, MZ_E_ARG, "id is NULL");
+    if (!g_nccl.load()) return fail(nullptr, MZ_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    ncclUniqueId u; ncclResult_t r = g_nccl.GetUniqueId(&u);
+    if (r != ncclSuccess) return fail(nullptr, MZ_E_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id, &u, 128);
+    return MZ_OK;
+}
+int mz_comm_init(mz_ctx *c, int rank, int nranks, const uint8_t id[128]) {
+    MZ_CHECK_CTX(c);
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MZ_E_ARG, "bad rank/nranks/id");
+    if (!g_nccl.load()) return fail(c, MZ_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId u; memcpy(&u, id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return fail(c, MZ_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    c->rank = rank; c->nranks = nranks;
+    return MZ_OK;
+}
+int mz_comm_destroy(mz_ctx *c) {
+    MZ_CHECK_CTX(c);
+    if (c->comm) { MZ_CUDA(c, cudaStreamSynchronize(c->stream)); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    c->rank = 0; c->nranks = 1;
+    return MZ_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------------------------
+int mz_launch_count(mz_ctx *c, int64_t *n) { if (!c || !n) return fail(c, MZ_E_ARG, "NULL"); *n = c->launches; return MZ_OK; }
+int mz_kernel_time_reset(mz_ctx *c, int enable) {
+    MZ_CHECK_CTX(c);
+    collect_timings(c);
+    for (int i = 0; i < 8; i++) { c->fam_ms[i] = 0; c->fam_n[i] = 0; }
+    c->timing = enable != 0;
+    return MZ_OK;
+}
+int mz_kernel_time(mz_ctx *c, int family, double *ms, int64_t *launches) {
+    MZ_CHECK_CTX(c);
+    if (family < 0 || family >= 8) return fail(c, MZ_E_ARG, "family out of range");
+    collect_timings(c);
+    if (ms) *ms = c->fam_ms[family];
+    if (launches) *launches = c->fam_n[family];
+    return MZ_OK;
+}
+int mz_search_stats(mz_ctx *c, double *mean_legal, double *mean_depth) {
+    if (!c) return fail(nullptr, MZ_E_ARG, "ctx is NULL");
+    if (mean_legal) *mean_legal = c->last_mean_legal;
+    if (mean_depth) *mean_depth = c->last_mean_depth;
+    return MZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+// mz_device.cuh -- sm_100a device machinery shared by the kernels of libmuzero_b200:
+//   * mbarrier + cp.async.bulk (TMA 1-D bulk copy) weight pipeline: each Dense layer's padded {W,b} block is
+//     staged global -> shared by one elected thread while the previous layer computes;
+//   * the exact-fp32 Dense tile: 32 rows x out_pad columns per CTA, 4x4 register tiles, sequential-k fmaf
+//     (bit-identical to the arithmetic contract in DESIGN.md);
+//   * chains of layers for the three networks (src/Learning.jl:87-142).
+#pragma once
+#include <cuda_runtime.h>
+#include "mz_common.h"
+
+#define MZ_ROWS 32        // rows (trees / samples) per CTA
+#define MZ_THREADS 128
+
+__device__ __forceinline__ uint32_t mz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mz_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mz_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mz_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mz_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void mz_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(mz_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mz_mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(mz_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a lost bulk copy must fault the kernel, never hang the GPU
+__device__ __forceinline__ void mz_mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mz_mbar_try_wait(bar, parity); spin++)
+        if (spin > (1u << 24)) __trap();
+}
+
+struct mz_nn_pipe {
+    float *wbuf[2];
+    uint64_t *mbar;        // [2]
+    const float *wglob;    // padded device blob
+    uint32_t q;            // layers executed so far by this CTA (uniform)
+};
+
+__device__ __forceinline__ void mz_nn_issue(const mz_nn_pipe &s, const mz_params &P, int layer, uint32_t slot) {
+    const mz_layer &L = P.layers[layer];
+    uint32_t bytes = (uint32_t)L.floats * 4u;
+    mz_mbar_expect_tx(&s.mbar[slot], bytes);
+    mz_bulk_g2s(s.wbuf[slot], s.wglob + L.w_off, bytes, &s.mbar[slot]);
+}
+
+// y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row]
+__device__ __forceinline__ void mz_dense_tile(const mz_layer &L, const float *__restrict__ wsm, const float *__restrict__ src,
+                                              float *__restrict__ dst) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rg = lane & 7;
+    const int opq = L.out_pad >> 2;
+    const int in = L.in;
+    for (int g = (warp << 2) | (lane >> 3); g < opq; g += 16) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+        const float4 *w4 = reinterpret_cast<const float4 *>(wsm) + g;
+        const float4 *x4 = reinterpret_cast<const float4 *>(src) + rg;
+#pragma unroll 4
+        for (int k = 0; k < in; k++) {
+            const float4 wv = w4[k * opq];
+            const float4 xv = x4[k * (MZ_ROWS / 4)];
+            const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+            const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wj[j], xi[i], acc[i][j]);
+        }
+        const float4 bv = reinterpret_cast<const float4 *>(wsm + in * L.out_pad)[g];
+        const float bj[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float4 r;
+            r.x = mz_activate(acc[0][j] + bj[j], L.act);
+            r.y = mz_activate(acc[1][j] + bj[j], L.act);
+            r.z = mz_activate(acc[2][j] + bj[j], L.act);
+            r.w = mz_activate(acc[3][j] + bj[j], L.act);
+            reinterpret_cast<float4 *>(dst + (4 * g + j) * MZ_ROWS)[rg] = r;
+        }
+    }
+}
+
+// One layer: prefetch `next` (or nothing when next < 0) into the other buffer, wait for this layer's weights,
+// compute, barrier.  Preconditions: this layer's copy was issued earlier; a __syncthreads separates the last
+// reads of the other buffer (layer q-1) and of `dst`'s previous contents from this call.
+__device__ __forceinline__ void mz_nn_layer(mz_nn_pipe &s, const mz_params &P, int layer, int next, const float *src, float *dst) {
+    if (threadIdx.x == 0 && next >= 0) mz_nn_issue(s, P, next, (s.q + 1) & 1u);
+    mz_mbar_wait(&s.mbar[s.q & 1u], (s.q >> 1) & 1u);
+    mz_dense_tile(P.layers[layer], s.wbuf[s.q & 1u], src, dst);
+    __syncthreads();
+    s.q++;
+}
+__device__ __forceinline__ void mz_nn_chain(mz_nn_pipe &s, const mz_params &P, int first, int n, int after, const float *src,
+                                            float *dst, float *t0, float *t1) {
+    const float *cur = src;
+    for (int i = 0; i < n; i++) {
+        float *d = (i == n - 1) ? dst : ((i & 1) ? t1 : t0);
+        mz_nn_layer(s, P, first + i, (i == n - 1) ? after : first + i + 1, cur, d);
+        cur = d;
+    }
+}
+// trunk -> bufT, head 1 -> h1dst, head 2 -> h2dst (Split, src/Learning.jl:60-68); `after` = layer prefetched last
+__device__ __forceinline__ void mz_nn_net(mz_nn_pipe &s, const mz_params &P, int net, int after, const float *src, float *bufT,
+                                          float *h1dst, float *h2dst, float *t0, float *t1) {
+    const mz_net &N = P.nets[net];
+    int f = N.first;
+    if (N.n_h1 == 0) { mz_nn_chain(s, P, f, N.n_trunk, after, src, h1dst, t0, t1); return; }
+    mz_nn_chain(s, P, f, N.n_trunk, f + N.n_trunk, src, bufT, t0, t1);
+    mz_nn_chain(s, P, f + N.n_trunk, N.n_h1, f + N.n_trunk + N.n_h1, bufT, h1dst, t0, t1);
+    mz_nn_chain(s, P, f + N.n_trunk + N.n_h1, N.n_h2, after, bufT, h2dst, t0, t1);
+}
+
+// shared-memory carve-up used by every NN-running kernel
+struct mz_smem_plan {
+    float *wbuf[2]; uint64_t *mbar; float *in0, *in1, *bufT, *t0, *t1, *outV, *outL, *outR, *outH;
+    double *pbc0, *sqrtN;
+};
+__host__ __device__ inline size_t mz_smem_bytes(int max_dim, int max_layer_floats, int hidden_pad, int S) {
+    size_t w = ((size_t)max_layer_floats * 4 + 127) & ~(size_t)127;
+    size_t buf = (size_t)max_dim * MZ_ROWS * 4;
+    size_t small = (size_t)(4 + 16 + 4) * MZ_ROWS * 4 + (size_t)hidden_pad * MZ_ROWS * 4;
+    size_t tab = (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
+    return 2 * w + 128 + 5 * buf + small + tab + 128;
+}
+__device__ __forceinline__ mz_smem_plan mz_smem_carve(unsigned char *base, int max_dim, int max_layer_floats, int hidden_pad, int S) {
+    mz_smem_plan p;
+    size_t w = ((size_t)max_layer_floats * 4 + 127) & ~(size_t)127;
+    size_t buf = (size_t)max_dim * MZ_ROWS * 4;
+    unsigned char *c = base;
+    p.wbuf[0] = (float *)c; c += w;
+    p.wbuf[1] = (float *)c; c += w;
+    p.mbar = (uint64_t *)c; c += 128;
+    p.in0 = (float *)c; c += buf;
+    p.in1 = (float *)c; c += buf;
+    p.bufT = (float *)c; c += buf;
+    p.t0 = (float *)c; c += buf;
+    p.t1 = (float *)c; c += buf;
+    p.outV = (float *)c; c += 4 * MZ_ROWS * 4;
+    p.outL = (float *)c; c += 16 * MZ_ROWS * 4;
+    p.outR = (float *)c; c += 4 * MZ_ROWS * 4;
+    p.outH = (float *)c; c += (size_t)hidden_pad * MZ_ROWS * 4;
+    p.pbc0 = (double *)c; c += ((size_t)S + 2) * 8;
+    p.sqrtN = (double *)c;
+    return p;
+}
+__device__ __forceinline__ void mz_pipe_init(mz_nn_pipe &s, const mz_smem_plan &sp, const float *wglob) {
+    s.wbuf[0] = sp.wbuf[0]; s.wbuf[1] = sp.wbuf[1]; s.mbar = sp.mbar; s.wglob = wglob; s.q = 0;
+    if (threadIdx.x == 0) { mz_mbar_init(&sp.mbar[0], 1); mz_mbar_init(&sp.mbar[1], 1); mz_fence_mbar_init(); }
+}

@@ -1,0 +1,217 @@
+// mz_host.h -- host-side construction of the device parameter block, the padded weight layout and the
+// integer-only UCB tables from an mz_config.  Plain C++ (no CUDA) so the CPU harness can share it.
+#pragma once
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "mz_common.h"
+
+namespace mzh {
+
+// Julia (<= 1.10) Dict{Int,V} iteration order for keys 1..A inserted in ascending order: 16 slots (x4 growth
+// once count*3 > 2*slots), slot = hash_64_64(3|x| + bits(Float64(x))) & (sz-1), linear probing.  This is the
+// order SelfPlay.jl:158-159 (select_child), :103 (noise) and :294-295 (select_action) iterate children in.
+inline uint64_t hash_64_64(uint64_t a) {
+    a = ~a + (a << 21); a = a ^ (a >> 24); a = a + (a << 3) + (a << 8); a = a ^ (a >> 14);
+    a = a + (a << 2) + (a << 4); a = a ^ (a >> 28); a = a + (a << 31);
+    return a;
+}
+inline void julia_dict_order(int A, int32_t *order) {
+    int sz = 16;
+    while (A * 3 > sz * 2) sz *= 4;
+    std::vector<int> slots((size_t)sz, 0);
+    for (int k = 1; k <= A; k++) {
+        double d = (double)k; uint64_t b; memcpy(&b, &d, 8);
+        int i = (int)(hash_64_64(3ull * (uint64_t)k + b) & (uint64_t)(sz - 1));
+        while (slots[(size_t)i]) i = (i + 1) & (sz - 1);
+        slots[(size_t)i] = k;
+    }
+    int n = 0;
+    for (int i = 0; i < sz; i++) if (slots[(size_t)i]) order[n++] = slots[(size_t)i];
+}
+
+inline void default_config(mz_config *c) {   // games/tictactoe/params.jl:2-29, src/Constructors.jl:18-52
+    memset(c, 0, sizeof(*c));
+    c->game = MZ_GAME_TICTACTOE; c->W = 3; c->H = 3; c->C = 3; c->A = 9; c->num_players = 2;
+    c->stacked_observations = 1; c->max_moves = 9; c->num_iters = 10; c->num_unroll_steps = 5; c->td_steps = 5;
+    c->batch_size = 32; c->replay_buffer_size = 10000; c->pb_c_base = 19652; c->intermediate_rewards = 0;
+    c->tie_mode = MZ_TIE_PHILOX; c->pb_c_init = 1.25f; c->discount = 0.997f; c->dirichlet_alpha = 0.25f;
+    c->exploration_eps = 0.25f; c->seed = 1337;
+    julia_dict_order(c->A, c->child_order);
+    c->width_hidden = 64; c->depth_representation = 3; c->depth_prediction = 3; c->depth_dynamics = 3;
+    c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
+    c->hidden_state_size = 27; c->reward_activation_tanh = 1;
+    c->num_slots = 4096; c->nn_mode = MZ_NN_FP32_EXACT;
+}
+
+inline const char *validate(const mz_config &c) {
+    if (c.game != MZ_GAME_TICTACTOE && c.game != MZ_GAME_CONNECT) return "unknown game";
+    if (c.A < 1 || c.A > MZ_MAX_A) return "action space size must be in 1..16";
+    if (c.W < 1 || c.H < 1 || c.C != 3) return "observation_shape must be (W,H,3)";
+    if (c.game == MZ_GAME_TICTACTOE && (c.W != 3 || c.H != 3 || c.A != 9)) return "TicTacToe needs observation_shape (3,3,3) and 9 actions";
+    if (c.game == MZ_GAME_CONNECT && (c.A != c.H || (c.W + 1) * c.H > 64)) return "Connect needs A == H columns and (W+1)*H <= 64";
+    if (c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
+    if (c.num_players < 1 || c.num_players > 2) return "1 or 2 players";
+    if (c.num_iters < 1 || c.num_iters > 1000) return "num_iters must be in 1..1000";
+    if (1 + (c.num_iters + 1) * c.A > 65535) return "tree too large for 16-bit parent links";
+    if (c.max_moves < 1 || c.max_moves > 63) return "max_moves must be in 1..63";
+    if (c.stacked_observations < 0 || c.stacked_observations > 8) return "stacked_observations out of range";
+    if (c.num_unroll_steps < 0 || c.num_unroll_steps > 32 || c.td_steps < 0 || c.td_steps > 64) return "unroll/td steps out of range";
+    if (c.width_hidden < 4 || c.width_hidden % 4) return "width_hidden must be a positive multiple of 4";
+    if (c.batch_size < 1 || c.replay_buffer_size < 1 || c.num_slots < 1) return "batch_size, replay_buffer_size, num_slots must be positive";
+    int order_seen = 0;
+    for (int i = 0; i < c.A; i++) { if (c.child_order[i] < 1 || c.child_order[i] > c.A) return "child_order must be a permutation of 1..A"; order_seen |= 1 << (c.child_order[i] - 1); }
+    if (order_seen != (1 << c.A) - 1) return "child_order must be a permutation of 1..A";
+    return nullptr;
+}
+
+struct model {
+    mz_params P;
+    std::vector<double> pbc0, sqrtN;   // ucb_score's Float64 terms, functions of integers only (Q3)
+    int max_dim;                       // largest layer in/out_pad: activation buffer rows
+    int max_layer_floats;              // largest bulk-copied layer
+};
+
+inline void add_layer(mz_params &P, int in, int out, int act, int &src_off, int &dev_off) {
+    mz_layer &l = P.layers[P.n_layers++];
+    l.in = in; l.out = out; l.out_pad = (out + 3) & ~3; l.act = act;
+    l.src_w_off = src_off; src_off += in * out; l.src_b_off = src_off; src_off += out;
+    l.w_off = dev_off; dev_off += in * l.out_pad; l.b_off = dev_off; dev_off += l.out_pad;
+    l.floats = in * l.out_pad + l.out_pad; l.pad_ = 0;
+}
+
+inline int count_layers(const mz_config &c) {
+    return (c.depth_representation + 2) + (c.depth_prediction + 1 + c.depth_value + 1 + c.depth_policy + 1) +
+           (c.depth_dynamics + 1 + c.depth_state_head + 1 + c.depth_reward + 1);
+}
+
+// Conf.discount^i exactly as Julia evaluates Float32^Int64 (Base: products for i<=3, llvm.pow.f32 beyond).
+inline float discount_pow(float g, int i) {
+    if (i == 0) return 1.0f;
+    if (i == 1) return g;
+    if (i == 2) return g * g;
+    if (i == 3) return g * g * g;
+    return powf(g, (float)i);
+}
+
+inline const char *build_model(const mz_config &c, model &M) {
+    if (const char *e = validate(c)) return e;
+    if (count_layers(c) > MZ_MAX_LAYERS) return "too many layers";
+    mz_params &P = M.P;
+    memset(&P, 0, sizeof(P));
+    P.game = c.game; P.W = c.W; P.H = c.H; P.C = c.C; P.A = c.A; P.P = c.num_players;
+    P.stacked = c.stacked_observations; P.max_moves = c.max_moves; P.Tmax = c.max_moves + 1;
+    P.S = c.num_iters; P.K = c.num_unroll_steps; P.td = c.td_steps;
+    P.cells = c.W * c.H; P.obs_size = P.cells * c.C;
+    P.planes = c.C * (c.stacked_observations + 1) + c.stacked_observations;      // Learning.jl:88
+    P.stack_size = P.cells * P.planes; P.sa_size = P.cells * (c.C + 1);            // Learning.jl:120
+    P.hidden = c.hidden_state_size; P.hidden_pad = (P.hidden + 3) & ~3;
+    P.tie_mode = c.tie_mode; P.pb_c_base = c.pb_c_base; P.intermediate_rewards = c.intermediate_rewards;
+    P.batch_size = c.batch_size;
+    P.pb_c_init = c.pb_c_init; P.discount = c.discount; P.dirichlet_alpha = c.dirichlet_alpha; P.exploration_eps = c.exploration_eps;
+    P.seed = c.seed;
+    for (int i = 0; i < MZ_MAX_A; i++) P.order[i] = c.child_order[i];
+    for (int a = 0; a <= c.A; a++) {
+        P.act_plane_play[a] = (float)((double)a / (double)c.A);   // SelfPlay.jl:8-9: Int/Int -> Float64, stored Float32
+        P.act_plane_learn[a] = (float)a / (float)c.A;             // Learning.jl:294: Float32 ./ Int
+    }
+    for (int i = 0; i < 72; i++) P.disc_pow[i] = discount_pow(c.discount, i);
+    // tree pool geometry
+    P.nodes_per_tree = 1 + (c.num_iters + 1) * c.A;
+    int a_bytes = P.nodes_per_tree * 16, b_bytes = ((P.nodes_per_tree * 4) + 15) & ~15;
+    int h_bytes = (c.num_iters + 1) * P.hidden_pad * 4;
+    P.nodeB_off_bytes = a_bytes; P.hidden_off_bytes = a_bytes + b_bytes;
+    P.tree_stride_bytes = (a_bytes + b_bytes + h_bytes + 127) & ~127;
+    // networks (src/Learning.jl:87-142), Flux.params order
+    int src = 0, dev = 0, w = c.width_hidden;
+    P.nets[0].first = P.n_layers;
+    add_layer(P, P.stack_size, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_representation; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, w, P.hidden, MZ_ACT_ID, src, dev);
+    P.nets[0].n_trunk = c.depth_representation + 2; P.nets[0].n_h1 = 0; P.nets[0].n_h2 = 0;
+    P.nets[1].first = P.n_layers;
+    add_layer(P, P.hidden, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_prediction; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_value; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, w, 1, MZ_ACT_TANH, src, dev);
+    for (int i = 0; i < c.depth_policy; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, w, c.A, MZ_ACT_ID, src, dev);
+    P.nets[1].n_trunk = c.depth_prediction + 1; P.nets[1].n_h1 = c.depth_value + 1; P.nets[1].n_h2 = c.depth_policy + 1;
+    P.nets[2].first = P.n_layers;
+    add_layer(P, P.sa_size, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_dynamics; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_state_head; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, w, P.hidden, MZ_ACT_ID, src, dev);
+    for (int i = 0; i < c.depth_reward; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, w, 1, c.reward_activation_tanh ? MZ_ACT_TANH : MZ_ACT_ID, src, dev);
+    P.nets[2].n_trunk = c.depth_dynamics + 1; P.nets[2].n_h1 = c.depth_state_head + 1; P.nets[2].n_h2 = c.depth_reward + 1;
+    P.n_params = src; P.total_floats = dev;
+    M.max_dim = 4; M.max_layer_floats = 0;
+    for (int i = 0; i < P.n_layers; i++) {
+        if (P.layers[i].in > M.max_dim) M.max_dim = P.layers[i].in;
+        if (P.layers[i].out_pad > M.max_dim) M.max_dim = P.layers[i].out_pad;
+        if (P.layers[i].floats > M.max_layer_floats) M.max_layer_floats = P.layers[i].floats;
+    }
+    M.max_dim = (M.max_dim + 3) & ~3;
+    // ucb_score (SelfPlay.jl:172-174): pb_c = log2((N + base + 1) / base) + init, then * sqrt(N)/(n+1); all Float64
+    M.pbc0.resize((size_t)c.num_iters + 2); M.sqrtN.resize((size_t)c.num_iters + 2);
+    for (int N = 0; N <= c.num_iters + 1; N++) {
+        M.pbc0[(size_t)N] = log2((double)(N + c.pb_c_base + 1) / (double)c.pb_c_base) + (double)c.pb_c_init;
+        M.sqrtN[(size_t)N] = sqrt((double)N);
+    }
+    return nullptr;
+}
+
+inline int net_params(const mz_params &P, int net) {
+    if (net == MZ_NET_ALL) return P.n_params;
+    int first = P.nets[net].first, n = P.nets[net].n_trunk + P.nets[net].n_h1 + P.nets[net].n_h2, s = 0;
+    for (int i = first; i < first + n; i++) s += P.layers[i].in * P.layers[i].out + P.layers[i].out;
+    return s;
+}
+inline int net_src_offset(const mz_params &P, int net) { return net == MZ_NET_ALL ? 0 : P.layers[P.nets[net].first].src_w_off; }
+
+// reference-order blob (W (out,in) column-major: W[o + out*k], then b) <-> padded device layout (W[k][out_pad], b[out_pad])
+inline void pack_weights(const mz_params &P, const float *src, float *dev) {
+    memset(dev, 0, sizeof(float) * (size_t)P.total_floats);
+    for (int i = 0; i < P.n_layers; i++) {
+        const mz_layer &l = P.layers[i];
+        for (int k = 0; k < l.in; k++) for (int o = 0; o < l.out; o++) dev[l.w_off + k * l.out_pad + o] = src[l.src_w_off + k * l.out + o];
+        for (int o = 0; o < l.out; o++) dev[l.b_off + o] = src[l.src_b_off + o];
+    }
+}
+inline void unpack_weights(const mz_params &P, const float *dev, float *src) {
+    for (int i = 0; i < P.n_layers; i++) {
+        const mz_layer &l = P.layers[i];
+        for (int k = 0; k < l.in; k++) for (int o = 0; o < l.out; o++) src[l.src_w_off + k * l.out + o] = dev[l.w_off + k * l.out_pad + o];
+        for (int o = 0; o < l.out; o++) src[l.src_b_off + o] = dev[l.b_off + o];
+    }
+}
+
+// Flux.glorot_uniform (un-vendored): (rand(Float32,out,in) .- 0.5f0) .* sqrt(24f0/(in+out)); bias zeros.  The reference
+// never seeds it (Constructors.jl:19); contract: element i of layer l of net n = Philox(seed, INIT, n, l, i/4)[i%4].
+inline void init_weights(const mz_params &P, uint64_t seed, float *src) {
+    for (int n = 0; n < 3; n++) {
+        int first = P.nets[n].first, cnt = P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2;
+        for (int li = 0; li < cnt; li++) {
+            const mz_layer &l = P.layers[first + li];
+            float scale = sqrtf(24.0f / (float)(l.in + l.out));
+            int nw = l.in * l.out;
+            for (int i = 0; i < nw; i += 4) {
+                mz_u4 r = mz_philox(seed, MZ_STREAM_INIT, (uint32_t)n, (uint32_t)li, (uint32_t)(i / 4), 0);
+                uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                for (int j = 0; j < 4 && i + j < nw; j++) src[l.src_w_off + i + j] = (mz_u32_to_unit(rr[j]) - 0.5f) * scale;
+            }
+            for (int o = 0; o < l.out; o++) src[l.src_b_off + o] = 0.0f;
+        }
+    }
+}
+
+// ParameterSchedulers.Cos(l0=1e-4, l1=1e-1, period=10) (Learning.jl:319), 1-based step.
+inline double cos_schedule(int64_t t) {
+    double l0 = 1e-4, l1 = 1e-1, period = 10.0;
+    double g = (1.0 + cos(2.0 * 3.14159265358979323846 * (double)(t - 1) / period)) / 2.0;
+    return fabs(l0 - l1) * g + (l0 < l1 ? l0 : l1);
+}
+
+}  // namespace mzh

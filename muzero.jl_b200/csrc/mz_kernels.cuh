@@ -1,0 +1,365 @@
+// mz_kernels.cuh -- the self-play kernels.
+//
+//   mz_k_search<MODE>   one CTA = 32 trees.  Root inference (representation + prediction), root expansion,
+//                       then S simulations of {PUCT select -> prediction(parent) + dynamics -> expand -> backup}
+//                       without leaving the SM: weights stream through shared memory (TMA bulk copies),
+//                       activations stay in shared memory, node pools live in HBM/L2.
+//                       MODE_API  : roots come from caller arrays (run_mcts, src/SelfPlay.jl:230-285)
+//                       MODE_SLOTS: roots come from the device-resident game slots; after the search the same
+//                                   kernel samples the action, steps the environment and appends to the game
+//                                   history (play_game's loop body, src/SelfPlay.jl:343-380).
+//   mz_k_save_refill    save_game (src/ReplayBuffer.jl:133-161) for finished slots, in slot order, into the
+//                       device replay ring + assignment of the next game ids to free slots.
+#pragma once
+#include "mz_device.cuh"
+
+enum { MZ_MODE_API = 0, MZ_MODE_SLOTS = 1 };
+enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 };
+
+struct mz_slots {          // device-resident concurrent games, SoA
+    uint64_t *p1, *p2; int32_t *player, *T, *status; int64_t *game_id;
+    // per-slot GameHistory under construction (src/Constructors.jl:6-16); boards are kept as bit masks
+    uint64_t *h_p1, *h_p2;   // [G][Tmax] board before move i
+    int32_t *h_action;       // [G][Tmax]
+    float *h_reward;         // [G][Tmax]
+    uint8_t *h_to_play;      // [G][Tmax]
+    float *h_cv;             // [G][Tmax][A]
+    float *h_rv;             // [G][Tmax]
+};
+struct mz_ring {           // device replay buffer: key k lives at (k-1) % capacity
+    int64_t capacity;
+    int64_t *game_id; int32_t *T;
+    uint64_t *h_p1, *h_p2; int32_t *h_action; float *h_reward; uint8_t *h_to_play; float *h_cv; float *h_rv;
+    // counters (device): [0] num_played_games, [1] num_played_steps, [2] total_samples, [3] next game id to hand out,
+    // [4] end game id (exclusive), [5] active slots after the last refill
+    int64_t *counters;
+};
+struct mz_search_args {
+    const float *wglob; const double *pbc0; const double *sqrtN; void *tree_pool;
+    int32_t n, max_dim, max_layer_floats, exploration;
+    // MODE_API inputs / outputs
+    const float *stacked; const uint32_t *legal; const int32_t *to_play; const uint64_t *game_id; const int32_t *move_idx;
+    int32_t *visit_counts; float *root_value; float *root_priors;
+    // MODE_SLOTS
+    mz_slots slots; float temperature;
+    unsigned long long *stats;   // [0] sum depth, [1] simulations, [2] sum legal, [3] roots
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
+    extern __shared__ __align__(128) unsigned char mz_smem[];
+    const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
+    const int tid = threadIdx.x;
+    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;      // tree / slot handled by this thread (tid < 32)
+    mz_nn_pipe pipe;
+    mz_pipe_init(pipe, sp, a.wglob);
+    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;   // in0,in1,bufT,t0,t1 are contiguous
+    for (int i = tid; i <= P.S + 1; i += MZ_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
+
+    // ---- per-tree state (threads 0..31) ----
+    bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
+    mz_tree tree; tree.A = nullptr; tree.B = nullptr; tree.hidden = nullptr;
+    if (tid < MZ_ROWS && g < a.n) {
+        tree = mz_tree_at(P, a.tree_pool, g);
+        if (MODE == MZ_MODE_API) {
+            active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
+        } else {
+            active = a.slots.status[g] == MZ_SLOT_ACTIVE;
+            if (active) {
+                mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
+                legal = mz_env_legal_b(P, b); to_play = b.player;                       // SelfPlay.jl:351,359
+                game = (uint32_t)a.slots.game_id[g]; move = (uint32_t)a.slots.T[g] + 1u;
+            }
+        }
+        if (legal == 0) active = false;   // run_mcts asserts !isempty(legal_actions) (SelfPlay.jl:243); never reached in play
+    }
+    __syncthreads();   // mbarrier init + zeroed buffers visible
+    if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);
+
+    // ---- stage the stacked observations, k-major (get_stacked_observations, SelfPlay.jl:128-149) ----
+    if (MODE == MZ_MODE_API) {
+        for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+            int r = i / P.stack_size, k = i % P.stack_size;
+            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
+            sp.in0[k * MZ_ROWS + r] = gg < a.n ? a.stacked[gg * P.stack_size + k] : 0.0f;
+        }
+    } else {
+        for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+            int k = i / MZ_ROWS, r = i % MZ_ROWS;
+            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
+            float v = 0.0f;
+            if (gg < a.n && a.slots.status[gg] == MZ_SLOT_ACTIVE) {
+                int T = a.slots.T[gg];
+                v = mz_stacked_value(P, a.slots.h_p1 + gg * P.Tmax, a.slots.h_p2 + gg * P.Tmax, a.slots.h_action + gg * P.Tmax, T + 1, k);
+            }
+            sp.in0[k * MZ_ROWS + r] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- root: representation -> h0; prediction(h0) -> (v0, p0)  (SelfPlay.jl:233-245) ----
+    const int pred_first = P.nets[1].first;
+    mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT, sp.outH, nullptr, sp.t0, sp.t1);
+    mz_nn_net(pipe, P, 1, pred_first, sp.outH, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);   // prefetches the first simulation's layer
+
+    mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;                                    // SelfPlay.jl:251
+    unsigned long long depth_sum = 0;
+    float logits[MZ_MAX_A], policy[MZ_MAX_A];
+    if (active) {
+        for (int k = 0; k < P.hidden; k++) tree.hidden[k] = sp.outH[k * MZ_ROWS + tid];
+        for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
+        mz_softmax(logits, P.A, policy);                                                   // Learning.jl:114
+        mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;   // Node(prior=0), :232
+        tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
+        mz_tree_expand(P, tree, 0, 0, legal, policy, 0.0f);                                // :245
+        if (a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);   // :247-249 (eps = 0 is the identity)
+    }
+
+    // ---- simulations (SelfPlay.jl:254-283) ----
+    const int dyn_first = P.nets[2].first;
+    for (int sim = 1; sim <= P.S; sim++) {
+        mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0;
+        if (active) {
+            leaf = mz_tree_select(P, tree, sp.pbc0, sp.sqrtN, legal, mm, game, move, (uint32_t)sim);
+            depth_sum += (unsigned long long)leaf.depth;
+            uint32_t pb = tree.B[leaf.parent];
+            int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+            const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
+            float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);                             // 2^dbl: state after dbl in-place doublings (Q6)
+            for (int k = 0; k < P.hidden; k++) {
+                float v = h[k] * sc;
+                sp.in1[k * MZ_ROWS + tid] = v;                                              // prediction(parent.hidden_state), :271 (Q5)
+                sp.in0[k * MZ_ROWS + tid] = v * 2.0f;                                       // make_state_action: state .*= 2, :11
+            }
+            float plane = P.act_plane_play[leaf.action];                                    // :8-9
+            for (int k = P.obs_size; k < P.sa_size; k++) sp.in0[k * MZ_ROWS + tid] = plane;
+            tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+        }
+        __syncthreads();
+        mz_nn_net(pipe, P, 1, dyn_first, sp.in1, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);
+        mz_nn_net(pipe, P, 2, sim < P.S ? pred_first : -1, sp.in0, sp.bufT, sp.outH, sp.outR, sp.t0, sp.t1);
+        if (active) {
+            float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
+            for (int k = 0; k < P.hidden; k++) nh[k] = sp.outH[k * MZ_ROWS + tid];
+            for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
+            mz_softmax(logits, P.A, policy);
+            mz_tree_expand(P, tree, leaf.node, sim, legal, policy, sp.outR[tid]);          // :280 (root's legal set, Q7)
+            mz_tree_backup(P, tree, leaf.node, sp.outV[tid], mm);                          // :281
+        }
+        // no barrier needed here: the same thread stages the next inputs, and every NN read of in0/in1/out*
+        // finished before the barrier that ended the last layer
+    }
+
+    // ---- results ----
+    if (active) {
+        int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
+        for (int i = 0; i < P.A; i++) {
+            vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
+            sum_visits += vc[i]; nlegal += (int)((legal >> i) & 1u);
+        }
+        mz_f4 root = tree.A[0];
+        int rvc = (int)mz_f2bits(root.x);
+        float rv = rvc == 0 ? 0.0f : root.y / (float)rvc;                                   // node_value(root)
+        if (a.stats) {
+            atomicAdd(&a.stats[0], depth_sum); atomicAdd(&a.stats[1], (unsigned long long)P.S);
+            atomicAdd(&a.stats[2], (unsigned long long)nlegal); atomicAdd(&a.stats[3], 1ull);
+        }
+        if (MODE == MZ_MODE_API) {
+            for (int i = 0; i < P.A; i++) {
+                a.visit_counts[g * P.A + i] = vc[i];
+                if (a.root_priors) a.root_priors[g * P.A + i] = ((legal >> i) & 1u) ? tree.A[1 + i].z : 0.0f;
+            }
+            a.root_value[g] = rv;
+        } else {
+            // play_game loop body after run_mcts (SelfPlay.jl:360-379)
+            int T = a.slots.T[g];
+            int action = mz_select_action_counts(P, vc, legal, a.temperature, game, move);  // :360
+            mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
+            int p = b.player;
+            mz_env_step_b(P, b, action);                                                    // :366
+            float reward = (float)mz_env_reward_b(P, b, p);                                 // :367
+            bool done = mz_env_terminated_b(P, b);                                          // :368
+            float *cv = a.slots.h_cv + ((size_t)g * P.Tmax + T) * P.A;                      // store_search_stats! :115-122 (Q12)
+            for (int i = 0; i < P.A; i++) cv[i] = ((legal >> i) & 1u) ? (float)((double)vc[i] / (double)sum_visits) : 0.0f;
+            a.slots.h_rv[(size_t)g * P.Tmax + T] = rv;
+            a.slots.h_action[(size_t)g * P.Tmax + T] = action;                              // :377-379
+            a.slots.h_reward[(size_t)g * P.Tmax + T] = reward;
+            a.slots.h_to_play[(size_t)g * P.Tmax + T] = (uint8_t)p;
+            T += 1;
+            a.slots.p1[g] = b.p1; a.slots.p2[g] = b.p2; a.slots.player[g] = b.player; a.slots.T[g] = T;
+            if (T < P.Tmax) { a.slots.h_p1[(size_t)g * P.Tmax + T] = b.p1; a.slots.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
+            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED;              // loop condition :343
+        }
+    }
+}
+
+// save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
+// free slots.  Single CTA: the order in which games receive their game number must be deterministic.
+__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
+    __shared__ int scan[1024];
+    __shared__ int64_t base_key, next_game, end_game;
+    __shared__ int carry_fin, carry_free, active_count;
+    __shared__ long long add_steps, add_samples;
+    const int tid = threadIdx.x;
+    if (tid == 0) { base_key = r.counters[0]; next_game = r.counters[3]; end_game = r.counters[4]; carry_fin = 0; carry_free = 0; active_count = 0; add_steps = 0; add_samples = 0; }
+    __syncthreads();
+    for (int start = 0; start < n_slots; start += 1024) {
+        int g = start + tid;
+        int st = g < n_slots ? s.status[g] : MZ_SLOT_ACTIVE;
+        int fin = st == MZ_SLOT_FINISHED ? 1 : 0;
+        int fre = (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) ? 1 : 0;
+        // inclusive scans of fin and fre (packed: fin in the high half)
+        int v = (fin << 16) | fre;
+        scan[tid] = v; __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) { int t = tid >= off ? scan[tid - off] : 0; __syncthreads(); scan[tid] += t; __syncthreads(); }
+        int inc = scan[tid];
+        int fin_rank = carry_fin + (inc >> 16) - fin, free_rank = carry_free + (inc & 0xffff) - fre;
+        int tot = scan[1023];
+        __syncthreads();
+        if (fin) {   // copy this GameHistory into the ring under key = num_played_games + rank + 1 (:149-154)
+            int64_t key = base_key + fin_rank + 1;
+            int64_t pos = (key - 1) % r.capacity;
+            int T = s.T[g];
+            if (key > r.capacity) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)(-(long long)r.T[pos]));   // evicted history (:156-160)
+            r.game_id[pos] = s.game_id[g]; r.T[pos] = T;
+            for (int i = 0; i < P.Tmax; i++) {
+                size_t so = (size_t)g * P.Tmax + i, ro = (size_t)pos * P.Tmax + i;
+                r.h_p1[ro] = s.h_p1[so]; r.h_p2[ro] = s.h_p2[so]; r.h_action[ro] = s.h_action[so]; r.h_reward[ro] = s.h_reward[so];
+                r.h_to_play[ro] = s.h_to_play[so]; r.h_rv[ro] = s.h_rv[so];
+                for (int a = 0; a < P.A; a++) r.h_cv[ro * P.A + a] = s.h_cv[so * P.A + a];
+            }
+            atomicAdd((unsigned long long *)&add_steps, (unsigned long long)T);
+            atomicAdd((unsigned long long *)&add_samples, (unsigned long long)T);
+        }
+        if (fre) {
+            int64_t id = next_game + free_rank;
+            if (id < end_game) {
+                s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1;   // reset! (game.jl:15-20)
+                s.h_p1[(size_t)g * P.Tmax] = 0; s.h_p2[(size_t)g * P.Tmax] = 0;
+                atomicAdd(&active_count, 1);
+            } else s.status[g] = MZ_SLOT_IDLE;
+        } else if (g < n_slots && st == MZ_SLOT_ACTIVE) atomicAdd(&active_count, 1);
+        __syncthreads();
+        if (tid == 0) { carry_fin += tot >> 16; carry_free += tot & 0xffff; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int64_t handed = next_game + carry_free < end_game ? carry_free : (end_game - next_game > 0 ? end_game - next_game : 0);
+        r.counters[0] = base_key + carry_fin;
+        r.counters[1] += add_steps;
+        r.counters[2] += add_samples;
+        r.counters[3] = next_game + handed;
+        r.counters[5] = active_count;
+    }
+}
+
+// ---- batched network callables (init_*(hyper) callables, src/Learning.jl:87-142) -------------------
+struct mz_nn_args { const float *wglob; int32_t B, max_dim, max_layer_floats, net; const float *in; float *out1; float *out2; };
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_constant__ mz_params P, const mz_nn_args a) {
+    extern __shared__ __align__(128) unsigned char mz_smem[];
+    const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
+    const int tid = threadIdx.x;
+    mz_nn_pipe pipe;
+    mz_pipe_init(pipe, sp, a.wglob);
+    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
+    __syncthreads();
+    const mz_net &N = P.nets[a.net];
+    if (tid == 0) mz_nn_issue(pipe, P, N.first, 0);
+    const int in = P.layers[N.first].in;
+    for (int i = tid; i < MZ_ROWS * in; i += MZ_THREADS) {
+        int r = i / in, k = i % in;
+        int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
+        sp.in0[k * MZ_ROWS + r] = gg < a.B ? a.in[gg * in + k] : 0.0f;
+    }
+    __syncthreads();
+    float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
+    mz_nn_net(pipe, P, a.net, -1, sp.in0, sp.bufT, h1, h2, sp.t0, sp.t1);
+    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
+    if (tid < MZ_ROWS && g < a.B) {
+        if (a.net == 1) {
+            float logits[MZ_MAX_A], policy[MZ_MAX_A];
+            for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
+            mz_softmax(logits, P.A, policy);
+            a.out1[g] = sp.outV[tid];
+            for (int i = 0; i < P.A; i++) a.out2[g * P.A + i] = policy[i];
+        } else {
+            for (int k = 0; k < P.hidden; k++) a.out1[g * P.hidden + k] = sp.outH[k * MZ_ROWS + tid];
+            if (a.net == 2) a.out2[g] = sp.outR[tid];
+        }
+    }
+}
+
+// ---- batched environment verbs (games/tictactoe/game.jl) --------------------------------------------
+__global__ void mz_k_env_step(const __grid_constant__ mz_params P, int n, uint64_t *p1, uint64_t *p2, int32_t *player,
+                              const int32_t *action, float *reward, int32_t *done, uint32_t *legal) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mz_board b; b.p1 = p1[i]; b.p2 = p2[i]; b.player = player[i];
+    if (action) {
+        int p = b.player;
+        mz_env_step_b(P, b, action[i]);
+        p1[i] = b.p1; p2[i] = b.p2; player[i] = b.player;
+        if (reward) reward[i] = (float)mz_env_reward_b(P, b, p);
+    }
+    if (done) done[i] = mz_env_terminated_b(P, b) ? 1 : 0;
+    if (legal) legal[i] = mz_env_legal_b(P, b);
+}
+__global__ void mz_k_env_obs(const __grid_constant__ mz_params P, int n, const uint64_t *p1, const uint64_t *p2, float *obs) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * P.obs_size) return;
+    int g = (int)(i / P.obs_size), k = (int)(i % P.obs_size);
+    mz_board b; b.p1 = p1[g]; b.p2 = p2[g]; b.player = 1;
+    obs[i] = mz_env_obs_value(P, b, k / P.cells, k % P.cells);
+}
+__global__ void mz_k_select_action(const __grid_constant__ mz_params P, int n, const int32_t *vc, const uint32_t *legal, float temperature,
+                                   const uint64_t *game_id, const int32_t *move_idx, int32_t *action) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int32_t c[MZ_MAX_A];
+    for (int k = 0; k < P.A; k++) c[k] = vc[(size_t)i * P.A + k];
+    action[i] = mz_select_action_counts(P, c, legal[i], temperature, (uint32_t)game_id[i], (uint32_t)move_idx[i]);
+}
+
+// ---- GameHistory export / import (src/Constructors.jl:6-16) --------------------------------------------
+__global__ void mz_k_history_export(const __grid_constant__ mz_params P, mz_ring r, int64_t key0, int n, int64_t *game_id, int32_t *T,
+                                    float *obs, int32_t *actions, float *rewards, int32_t *to_play, float *cv, float *rv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)P.Tmax * P.obs_size;
+    if (i >= (int64_t)n * per) return;
+    int j = (int)(i / per); int rem = (int)(i % per); int t = rem / P.obs_size, k = rem % P.obs_size;
+    int64_t pos = (key0 + j - 1) % r.capacity;
+    int Tg = r.T[pos];
+    size_t ro = (size_t)pos * P.Tmax + t;
+    mz_board b; b.p1 = r.h_p1[ro]; b.p2 = r.h_p2[ro]; b.player = 1;
+    obs[i] = t < Tg ? mz_env_obs_value(P, b, k / P.cells, k % P.cells) : 0.0f;
+    if (k == 0) {
+        size_t oo = (size_t)j * P.Tmax + t;
+        bool v = t < Tg;
+        actions[oo] = v ? r.h_action[ro] : 0; rewards[oo] = v ? r.h_reward[ro] : 0.0f; to_play[oo] = v ? (int32_t)r.h_to_play[ro] : 0;
+        rv[oo] = v ? r.h_rv[ro] : 0.0f;
+        for (int a = 0; a < P.A; a++) cv[oo * P.A + a] = v ? r.h_cv[ro * P.A + a] : 0.0f;
+        if (t == 0) { game_id[j] = r.game_id[pos]; T[j] = Tg; }
+    }
+}
+// import: observations come as float planes; boards are recovered from planes 0 and 1.  One thread per (game, move).
+__global__ void mz_k_history_import(const __grid_constant__ mz_params P, mz_ring r, int64_t key0, int n, const int64_t *game_id, const int32_t *T,
+                                    const float *obs, const int32_t *actions, const float *rewards, const int32_t *to_play,
+                                    const float *cv, const float *rv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * P.Tmax) return;
+    int j = i / P.Tmax, t = i % P.Tmax;
+    int64_t pos = (key0 + j - 1) % r.capacity;
+    size_t ro = (size_t)pos * P.Tmax + t, oo = (size_t)j * P.Tmax + t;
+    uint64_t b1 = 0, b2 = 0;
+    const float *o = obs + oo * P.obs_size;
+    for (int c = 0; c < P.cells; c++) {
+        int bit = c;
+        if (P.game == MZ_GAME_CONNECT) bit = (c % P.W) + (P.W + 1) * (c / P.W);
+        if (o[c] != 0.0f) b1 |= 1ull << bit;
+        if (o[P.cells + c] != 0.0f) b2 |= 1ull << bit;
+    }
+    r.h_p1[ro] = b1; r.h_p2[ro] = b2; r.h_action[ro] = actions[oo]; r.h_reward[ro] = rewards[oo]; r.h_to_play[ro] = (uint8_t)to_play[oo];
+    r.h_rv[ro] = rv[oo];
+    for (int a = 0; a < P.A; a++) r.h_cv[ro * P.A + a] = cv[oo * P.A + a];
+    if (t == 0) { r.game_id[pos] = game_id[j]; r.T[pos] = T[j]; }
+}

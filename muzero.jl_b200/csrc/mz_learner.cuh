@@ -1,0 +1,168 @@
+// mz_learner.cuh -- replay sampling + target construction (get_batch, src/ReplayBuffer.jl:188-217) as a gather
+// kernel, the K-step unroll forward (src/Learning.jl:347-374), the loss (:261-288) and the ADAM update (:382-397).
+#pragma once
+#include "mz_kernels.cuh"
+
+struct mz_batch {   // get_batch's tuple (ReplayBuffer.jl:216), device arrays
+    int32_t *index;   // [B][2] (game key, position)
+    float *obs;       // [B][stack]
+    float *actions;   // [B][K+1]
+    float *values;    // [B][K+1]
+    float *rewards;   // [B][K+1]
+    float *policies;  // [B][K+1][A]
+    float *gscale;    // [B]
+};
+
+// One CTA per batch element.  Thread 0 draws (game, position) (sample_n_games :102-104, sample_position :80;
+// Philox(seed, REPLAY, step, b)) and builds the targets (make_target :25-50, Q17-Q18); all threads then gather
+// the stacked observation and the policy rows.
+__global__ void __launch_bounds__(64) mz_k_replay_gather(const __grid_constant__ mz_params P, mz_ring r, uint64_t step, int B, mz_batch out) {
+    __shared__ int s_pos, s_T; __shared__ int64_t s_ring;
+    const int b = blockIdx.x, tid = threadIdx.x, K1 = P.K + 1;
+    if (b >= B) return;
+    if (tid == 0) {
+        int64_t played = r.counters[0];
+        int64_t n_games = played < r.capacity ? played : r.capacity;
+        int64_t first_key = played - n_games + 1;
+        mz_u4 q = mz_philox(P.seed, MZ_STREAM_REPLAY, (uint32_t)step, (uint32_t)b, 0, 0);
+        int64_t gi = (int64_t)mz_u32_below(q.x, (uint32_t)n_games);
+        int64_t key = first_key + gi, ring = (key - 1) % r.capacity;
+        int T = r.T[ring];
+        int pos = 1 + (int)mz_u32_below(q.y, (uint32_t)T);
+        s_pos = pos; s_T = T; s_ring = ring;
+        out.index[2 * b] = (int32_t)key; out.index[2 * b + 1] = pos;
+        const float *rew = r.h_reward + (size_t)ring * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)ring * P.Tmax;
+        const float *rv = r.h_rv + (size_t)ring * P.Tmax; const int32_t *act = r.h_action + (size_t)ring * P.Tmax;
+        for (int k = 0; k < K1; k++) {
+            int ci = pos + k; float tv, tr; int a;
+            if (ci < T) { tv = mz_target_value(P, T, rew, tp, rv, ci); tr = rew[ci - 1]; a = act[ci - 1]; }
+            else if (ci == T) { tv = 0.0f; tr = rew[ci - 1]; a = act[ci - 1]; }
+            else { tv = 0.0f; tr = 0.0f; a = 1 + (int)mz_u32_below(mz_philox(P.seed, MZ_STREAM_ABSORB, (uint32_t)step, (uint32_t)b, (uint32_t)k, 0).x, (uint32_t)P.A); }
+            out.values[(size_t)b * K1 + k] = tv; out.rewards[(size_t)b * K1 + k] = tr; out.actions[(size_t)b * K1 + k] = (float)a;
+        }
+        int gs = T + 1 - pos; if (P.K < gs) gs = P.K;                      // :212
+        out.gscale[b] = (float)gs;
+    }
+    __syncthreads();
+    const int pos = s_pos, T = s_T; const int64_t ring = s_ring;
+    for (int k = tid; k < P.stack_size; k += 64)                            // :207
+        out.obs[(size_t)b * P.stack_size + k] = mz_stacked_value(P, r.h_p1 + (size_t)ring * P.Tmax, r.h_p2 + (size_t)ring * P.Tmax,
+                                                                 r.h_action + (size_t)ring * P.Tmax, pos, k);
+    for (int i = tid; i < K1 * P.A; i += 64) {
+        int k = i / P.A, a = i % P.A, ci = pos + k;
+        out.policies[((size_t)b * K1 + k) * P.A + a] = ci < T ? r.h_cv[((size_t)ring * P.Tmax + ci - 1) * P.A + a] : 1.0f / (float)P.A;
+    }
+}
+
+// K-step unroll forward for 32 samples per CTA (src/Learning.jl:347-370, Q19): row 0 = prediction(h0); for
+// i = 1..K: row i = prediction(h_{i-1}) evaluated BEFORE the dynamics step; rewards row 0 = 0.
+struct mz_learn_args { const float *wglob; int32_t B, max_dim, max_layer_floats, pad_; mz_batch batch; float *pred_values, *pred_rewards, *pred_policies; };
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_constant__ mz_params P, const mz_learn_args a) {
+    extern __shared__ __align__(128) unsigned char mz_smem[];
+    const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
+    const int tid = threadIdx.x, K1 = P.K + 1;
+    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
+    const bool row_ok = tid < MZ_ROWS && g < a.B;
+    mz_nn_pipe pipe;
+    mz_pipe_init(pipe, sp, a.wglob);
+    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
+    __syncthreads();
+    if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);
+    for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+        int r = i / P.stack_size, k = i % P.stack_size;
+        int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
+        sp.in0[k * MZ_ROWS + r] = gg < a.B ? a.batch.obs[gg * P.stack_size + k] : 0.0f;
+    }
+    __syncthreads();
+    const int pred_first = P.nets[1].first, dyn_first = P.nets[2].first;
+    mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT, sp.outH, nullptr, sp.t0, sp.t1);          // :347
+    for (int i = 0; i <= P.K; i++) {
+        // prediction on the current hidden state (outH); row 0 and row 1 both see h0 (Q19)
+        int after = (i == 0) ? (P.K > 0 ? pred_first : -1) : dyn_first;
+        mz_nn_net(pipe, P, 1, after, sp.outH, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);           // :351 / :356
+        if (row_ok) {
+            float logits[MZ_MAX_A], policy[MZ_MAX_A];
+            for (int k = 0; k < P.A; k++) logits[k] = sp.outL[k * MZ_ROWS + tid];
+            mz_softmax(logits, P.A, policy);
+            a.pred_values[g * K1 + i] = sp.outV[tid];
+            for (int k = 0; k < P.A; k++) a.pred_policies[(g * K1 + i) * P.A + k] = policy[k];
+            if (i == 0) a.pred_rewards[g * K1] = 0.0f;                                            // :352
+        }
+        if (i == 0) continue;
+        // make_dynamics_input (:293-304): state * 2 (copy), action plane = Float32(a) / A
+        if (row_ok) {
+            float plane = a.batch.actions[g * K1 + (i - 1)] / (float)P.A;
+            for (int k = 0; k < P.hidden; k++) sp.in0[k * MZ_ROWS + tid] = sp.outH[k * MZ_ROWS + tid] * 2.0f;
+            for (int k = P.obs_size; k < P.sa_size; k++) sp.in0[k * MZ_ROWS + tid] = plane;
+        }
+        __syncthreads();
+        mz_nn_net(pipe, P, 2, i < P.K ? pred_first : -1, sp.in0, sp.bufT, sp.outH, sp.outR, sp.t0, sp.t1);   // :362
+        if (row_ok) a.pred_rewards[g * K1 + i] = sp.outR[tid];
+    }
+}
+
+// loss (src/Learning.jl:261-288, Q21): per-sample partial sums, one thread per sample.
+__global__ void mz_k_loss_rows(const __grid_constant__ mz_params P, int B, mz_batch batch, const float *pv, const float *pr, const float *pp,
+                               float *row_v, double *row_r, float *row_p, float *row_invg) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int K1 = P.K + 1, A = P.A;
+    float sv = 0.0f, spol = 0.0f; double sr = 0.0;
+    for (int k = 0; k < K1; k++) {
+        float d = pv[(size_t)b * K1 + k] - batch.values[(size_t)b * K1 + k];
+        sv = sv + d * d;
+        double dr = (double)pr[(size_t)b * K1 + k] - (double)batch.rewards[(size_t)b * K1 + k];
+        sr = sr + dr * dr;
+        const float *p = pp + ((size_t)b * K1 + k) * A, *y = batch.policies + ((size_t)b * K1 + k) * A;
+        float mx = p[0];
+        for (int i = 1; i < A; i++) mx = p[i] > mx ? p[i] : mx;
+        float se = 0.0f;
+        for (int i = 0; i < A; i++) se = se + mz_expf(p[i] - mx);
+        float lse = mz_logf(se), acc = 0.0f;
+        for (int i = 0; i < A; i++) acc = acc + y[i] * ((p[i] - mx) - lse);   // logitcrossentropy on ALREADY softmaxed P
+        spol = spol + (-acc);
+    }
+    float gs = batch.gscale[b];
+    row_v[b] = sv / gs; row_r[b] = sr / (double)gs; row_p[b] = spol; row_invg[b] = 1.0f / gs;
+}
+// deterministic single-CTA tree reductions: out[0] = sum row_v, out[1] = sum row_p, out[2] = sum row_invg, out[3] = sum row_r,
+// out[4..6] = sum(theta^2) per net (double accumulation; compared against the oracle with a stated tolerance)
+__global__ void __launch_bounds__(1024) mz_k_loss_reduce(const __grid_constant__ mz_params P, int B, const float *row_v, const double *row_r,
+                                                          const float *row_p, const float *row_invg, const float *theta, double *out) {
+    __shared__ double red[1024];
+    const int tid = threadIdx.x;
+    for (int what = 0; what < 7; what++) {
+        double acc = 0.0;
+        if (what < 4) {
+            for (int i = tid; i < B; i += 1024) acc += what == 0 ? (double)row_v[i] : what == 1 ? (double)row_p[i] : what == 2 ? (double)row_invg[i] : row_r[i];
+        } else {
+            const mz_net &N = P.nets[what - 4];
+            int l0 = N.first, l1 = N.first + N.n_trunk + N.n_h1 + N.n_h2;
+            int lo = P.layers[l0].w_off, hi = P.layers[l1 - 1].b_off + P.layers[l1 - 1].out_pad;
+            for (int i = lo + tid; i < hi; i += 1024) { double t = (double)theta[i]; acc += t * t; }   // pad entries are zero
+        }
+        red[tid] = acc; __syncthreads();
+        for (int s = 512; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+        if (tid == 0) out[what] = red[0];
+        __syncthreads();
+    }
+}
+
+// Gradients.  MZ_GRAD_REFERENCE_L2: the reference computes its predictions outside Zygote.pullback
+// (Learning.jl:347-374 vs 385-393), so the gradient of every parameter array is that of sum(abs2, theta): 2*theta (Q20).
+__global__ void mz_k_grad_l2(int n, const float *theta, float *grad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = theta[i] + theta[i];
+}
+// Flux.ADAM apply! + update! (Q22): Float32 state, Float64 arithmetic inside the broadcast, beta powers beta^t.
+__global__ void mz_k_adam(int n, float *theta, float *m, float *v, const float *grad, double eta, double bp1, double bp2, float grad_scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    float g = grad[i] * grad_scale;
+    float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * (double)g);
+    float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * (double)(g * g));
+    m[i] = mi; v[i] = vi;
+    float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+    theta[i] = theta[i] - delta;
+}

@@ -1,0 +1,188 @@
+// host_harness.cpp -- TEST ONLY.  Compiles the product's scalar device building blocks (csrc/mz_common.h,
+// csrc/mz_host.h) with g++ and replays, on the CPU, exactly what one thread of the CUDA kernels does
+// (mz_k_search / mz_k_replay_gather).  tests/test_host_harness.py compares it with the oracle, so the tree logic,
+// weight packing, tables and RNG keying are validated before any GPU time is spent.  It is never shipped or
+// linked into libmuzero_b200.so; the CUDA kernels remain the only product compute path.
+#include <cstdio>
+#include <vector>
+#include "../muzero.jl_b200/csrc/mz_host.h"
+
+namespace {
+struct net_runner {
+    const mz_params &P; std::vector<float> dev;
+    net_runner(const mz_params &P_, const float *src) : P(P_), dev((size_t)P_.total_floats) { mzh::pack_weights(P, src, dev.data()); }
+    void dense(int layer, const float *x, float *y) const {   // same arithmetic as mz_dense_tile, one row
+        const mz_layer &L = P.layers[layer];
+        for (int o = 0; o < L.out_pad; o++) {
+            float acc = 0.0f;
+            for (int k = 0; k < L.in; k++) acc = fmaf(dev[(size_t)L.w_off + (size_t)k * L.out_pad + o], x[k], acc);
+            y[o] = mz_activate(acc + dev[(size_t)L.b_off + o], L.act);
+        }
+    }
+    void chain(int first, int n, const float *x, float *y) const {
+        std::vector<float> a(512), b(512);
+        const float *cur = x;
+        for (int i = 0; i < n; i++) { float *d = (i == n - 1) ? y : ((i & 1) ? b.data() : a.data()); dense(first + i, cur, d); cur = d; }
+    }
+    void net(int n, const float *x, float *h1, float *h2) const {
+        const mz_net &N = P.nets[n];
+        if (N.n_h1 == 0) { chain(N.first, N.n_trunk, x, h1); return; }
+        std::vector<float> t(512);
+        chain(N.first, N.n_trunk, x, t.data());
+        chain(N.first + N.n_trunk, N.n_h1, t.data(), h1);
+        chain(N.first + N.n_trunk + N.n_h1, N.n_h2, t.data(), h2);
+    }
+};
+
+struct search_out { int32_t vc[MZ_MAX_A]; float rv; float priors[MZ_MAX_A]; double depth_sum; };
+
+// one thread of mz_k_search
+void search_one(const mzh::model &M, const net_runner &nn, std::vector<char> &pool, const float *stacked, uint32_t legal, int to_play,
+                int exploration, uint32_t game, uint32_t move, search_out &out) {
+    const mz_params &P = M.P;
+    mz_tree tree = mz_tree_at(P, pool.data(), 0);
+    std::vector<float> h(512), in1(512), in0(512), outV(8), outL(32), outH(512), outR(8);
+    nn.net(0, stacked, outH.data(), nullptr);
+    nn.net(1, outH.data(), outV.data(), outL.data());
+    float logits[MZ_MAX_A], policy[MZ_MAX_A];
+    mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;
+    for (int k = 0; k < P.hidden; k++) tree.hidden[k] = outH[(size_t)k];
+    for (int i = 0; i < P.A; i++) logits[i] = outL[(size_t)i];
+    mz_softmax(logits, P.A, policy);
+    mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
+    tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
+    mz_tree_expand(P, tree, 0, 0, legal, policy, 0.0f);
+    if (exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);
+    out.depth_sum = 0;
+    for (int sim = 1; sim <= P.S; sim++) {
+        mz_leaf leaf = mz_tree_select(P, tree, M.pbc0.data(), M.sqrtN.data(), legal, mm, game, move, (uint32_t)sim);
+        out.depth_sum += leaf.depth;
+        uint32_t pb = tree.B[leaf.parent];
+        int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+        const float *hp = tree.hidden + (size_t)pe * P.hidden_pad;
+        float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);
+        for (int k = 0; k < P.hidden; k++) { float v = hp[k] * sc; in1[(size_t)k] = v; in0[(size_t)k] = v * 2.0f; }
+        float plane = P.act_plane_play[leaf.action];
+        for (int k = P.obs_size; k < P.sa_size; k++) in0[(size_t)k] = plane;
+        tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+        nn.net(1, in1.data(), outV.data(), outL.data());
+        nn.net(2, in0.data(), outH.data(), outR.data());
+        float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
+        for (int k = 0; k < P.hidden; k++) nh[k] = outH[(size_t)k];
+        for (int i = 0; i < P.A; i++) logits[i] = outL[(size_t)i];
+        mz_softmax(logits, P.A, policy);
+        mz_tree_expand(P, tree, leaf.node, sim, legal, policy, outR[0]);
+        mz_tree_backup(P, tree, leaf.node, outV[0], mm);
+    }
+    for (int i = 0; i < P.A; i++) {
+        out.vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
+        out.priors[i] = ((legal >> i) & 1u) ? tree.A[1 + i].z : 0.0f;
+    }
+    mz_f4 r = tree.A[0]; int rvc = (int)mz_f2bits(r.x);
+    out.rv = rvc == 0 ? 0.0f : r.y / (float)rvc;
+}
+}  // namespace
+
+extern "C" {
+
+int hh_default_config(mz_config *c) { mzh::default_config(c); return 0; }
+int hh_num_params(const mz_config *c) { mzh::model M; if (mzh::build_model(*c, M)) return -1; return M.P.n_params; }
+int hh_init_weights(const mz_config *c, uint64_t seed, float *src) { mzh::model M; if (mzh::build_model(*c, M)) return -1; mzh::init_weights(M.P, seed, src); return 0; }
+
+int hh_nn(const mz_config *c, const float *src, int net, const float *in, float *o1, float *o2) {
+    mzh::model M; if (const char *e = mzh::build_model(*c, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    net_runner nn(M.P, src);
+    std::vector<float> a(512), b(512);
+    nn.net(net, in, a.data(), b.data());
+    if (net == 1) { o1[0] = a[0]; float pol[MZ_MAX_A]; mz_softmax(b.data(), M.P.A, pol); for (int i = 0; i < M.P.A; i++) o2[i] = pol[i]; }
+    else { for (int k = 0; k < M.P.hidden; k++) o1[k] = a[(size_t)k]; if (net == 2) o2[0] = b[0]; }
+    return 0;
+}
+
+int hh_run_mcts(const mz_config *c, const float *src, const float *stacked, uint32_t legal, int to_play, int exploration, uint64_t game, int move,
+                int32_t *vc, float *rv, float *priors) {
+    mzh::model M; if (const char *e = mzh::build_model(*c, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    net_runner nn(M.P, src);
+    std::vector<char> pool((size_t)M.P.tree_stride_bytes + 256);
+    search_out o;
+    search_one(M, nn, pool, stacked, legal, to_play, exploration, (uint32_t)game, (uint32_t)move, o);
+    for (int i = 0; i < M.P.A; i++) { vc[i] = o.vc[i]; if (priors) priors[i] = o.priors[i]; }
+    *rv = o.rv;
+    return 0;
+}
+
+// MODE_SLOTS thread of mz_k_search looped over the moves of each game, outputs laid out like the oracle's mzo_self_play
+int64_t hh_self_play(const mz_config *c, const float *src, uint64_t first_game, int n_games, float temperature, int32_t *T_out, float *obs,
+                     int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values) {
+    mzh::model M; if (const char *e = mzh::build_model(*c, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    const mz_params &P = M.P;
+    net_runner nn(P, src);
+    std::vector<char> pool((size_t)P.tree_stride_bytes + 256);
+    int64_t sims = 0;
+    for (int gi = 0; gi < n_games; gi++) {
+        std::vector<uint64_t> h1((size_t)P.Tmax, 0), h2((size_t)P.Tmax, 0); std::vector<int32_t> ha((size_t)P.Tmax, 0);
+        mz_board b; mz_env_reset_b(P, b);
+        int T = 0; bool finished = false;
+        uint32_t game = (uint32_t)(first_game + (uint64_t)gi);
+        while (!finished) {
+            uint32_t legal = mz_env_legal_b(P, b);
+            std::vector<float> stacked((size_t)P.stack_size);
+            for (int k = 0; k < P.stack_size; k++) stacked[(size_t)k] = mz_stacked_value(P, h1.data(), h2.data(), ha.data(), T + 1, k);
+            search_out o;
+            search_one(M, nn, pool, stacked.data(), legal, b.player, 1, game, (uint32_t)T + 1u, o);
+            sims += P.S;
+            int sum_visits = 0; for (int i = 0; i < P.A; i++) sum_visits += o.vc[i];
+            int action = mz_select_action_counts(P, o.vc, legal, temperature, game, (uint32_t)T + 1u);
+            int p = b.player;
+            size_t oo = (size_t)gi * P.Tmax + T;
+            for (int k = 0; k < P.obs_size; k++) obs[oo * P.obs_size + k] = mz_env_obs_value(P, b, k / P.cells, k % P.cells);
+            mz_env_step_b(P, b, action);
+            float reward = (float)mz_env_reward_b(P, b, p);
+            bool done = mz_env_terminated_b(P, b);
+            for (int i = 0; i < P.A; i++) child_visits[oo * P.A + i] = ((legal >> i) & 1u) ? (float)((double)o.vc[i] / (double)sum_visits) : 0.0f;
+            root_values[oo] = o.rv; actions[oo] = action; rewards[oo] = reward; to_play[oo] = p;
+            ha[(size_t)T] = action;
+            T += 1;
+            if (T < P.Tmax) { h1[(size_t)T] = b.p1; h2[(size_t)T] = b.p2; }
+            if (done || T > P.max_moves) finished = true;
+        }
+        T_out[gi] = T;
+    }
+    return sims;
+}
+
+// thread 0 + gather threads of mz_k_replay_gather; the buffer is given like the oracle's (float observations)
+int hh_get_batch(const mz_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions, const float *rewards,
+                 const int32_t *to_play, const float *child_visits, const float *root_values, uint64_t step, int32_t *index_batch, float *obs_batch,
+                 float *action_batch, float *value_batch, float *reward_batch, float *policy_batch, float *gscale) {
+    mzh::model M; if (const char *e = mzh::build_model(*c, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    const mz_params &P = M.P; const int K1 = P.K + 1;
+    for (int b = 0; b < c->batch_size; b++) {
+        mz_u4 q = mz_philox(P.seed, MZ_STREAM_REPLAY, (uint32_t)step, (uint32_t)b, 0, 0);
+        int gi = (int)mz_u32_below(q.x, (uint32_t)n_games);
+        int Tg = T[gi];
+        int pos = 1 + (int)mz_u32_below(q.y, (uint32_t)Tg);
+        index_batch[2 * b] = (int32_t)(first_key + gi); index_batch[2 * b + 1] = pos;
+        std::vector<uint64_t> h1((size_t)P.Tmax, 0), h2((size_t)P.Tmax, 0); std::vector<uint8_t> tp((size_t)P.Tmax, 0);
+        for (int t = 0; t < P.Tmax; t++) {
+            const float *o = obs + ((size_t)gi * P.Tmax + t) * P.obs_size;
+            for (int cell = 0; cell < P.cells; cell++) { if (o[cell] != 0.0f) h1[(size_t)t] |= 1ull << cell; if (o[P.cells + cell] != 0.0f) h2[(size_t)t] |= 1ull << cell; }
+            tp[(size_t)t] = (uint8_t)to_play[(size_t)gi * P.Tmax + t];
+        }
+        const float *rew = rewards + (size_t)gi * P.Tmax, *rv = root_values + (size_t)gi * P.Tmax; const int32_t *act = actions + (size_t)gi * P.Tmax;
+        for (int k = 0; k < K1; k++) {
+            int ci = pos + k; float tv, tr; int a;
+            if (ci < Tg) { tv = mz_target_value(P, Tg, rew, tp.data(), rv, ci); tr = rew[ci - 1]; a = act[ci - 1]; }
+            else if (ci == Tg) { tv = 0.0f; tr = rew[ci - 1]; a = act[ci - 1]; }
+            else { tv = 0.0f; tr = 0.0f; a = 1 + (int)mz_u32_below(mz_philox(P.seed, MZ_STREAM_ABSORB, (uint32_t)step, (uint32_t)b, (uint32_t)k, 0).x, (uint32_t)P.A); }
+            value_batch[(size_t)b * K1 + k] = tv; reward_batch[(size_t)b * K1 + k] = tr; action_batch[(size_t)b * K1 + k] = (float)a;
+            for (int i = 0; i < P.A; i++) policy_batch[((size_t)b * K1 + k) * P.A + i] = ci < Tg ? child_visits[((size_t)gi * P.Tmax + ci - 1) * P.A + i] : 1.0f / (float)P.A;
+        }
+        int gs = Tg + 1 - pos; if (P.K < gs) gs = P.K;
+        gscale[b] = (float)gs;
+        for (int k = 0; k < P.stack_size; k++) obs_batch[(size_t)b * P.stack_size + k] = mz_stacked_value(P, h1.data(), h2.data(), act, pos, k);
+    }
+    return 0;
+}
+
+}  // extern "C"

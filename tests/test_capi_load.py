@@ -1,0 +1,81 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/muzero_b200.h declares, and refuses to run
+without a CUDA device (no CPU fallback).  No compute calls."""
+import ctypes as C
+import os
+import re
+import unicodedata
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+
+def header_symbols():
+    text = open(os.path.join(common.ROOT, "include", "muzero_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from muzero_jl_b200 import capi
+    L = capi.lib()
+    names = header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), "libmuzero_b200.so does not export %s" % n
+    assert set(names) == set(L._mz_symbols), "capi.py binding and header disagree"
+    assert L.mz_abi_version() == 1
+
+
+def test_config_defaults_follow_params_jl():
+    from muzero_jl_b200 import capi
+    c = capi.default_config()
+    assert (c.W, c.H, c.C, c.A, c.num_players) == (3, 3, 3, 9, 2)
+    assert (c.stacked_observations, c.max_moves, c.num_iters, c.num_unroll_steps, c.td_steps, c.batch_size) == (1, 9, 10, 5, 5, 32)
+    assert (c.pb_c_base, c.replay_buffer_size, c.seed) == (19652, 10000, 1337)
+    assert abs(c.discount - 0.997) < 1e-7 and c.pb_c_init == 1.25 and c.dirichlet_alpha == 0.25 and c.exploration_eps == 0.25
+    assert list(c.child_order)[:9] == [7, 4, 9, 2, 3, 5, 8, 6, 1]
+    assert [capi.lib().mz_num_params(C.byref(c), i) for i in range(4)] == [18331, 23242, 33308, 74881]
+
+
+def test_invalid_config_is_rejected_with_message():
+    from muzero_jl_b200 import capi
+    c = capi.default_config(hidden_state_size=28)
+    assert capi.lib().mz_num_params(C.byref(c), 3) == capi.E_ARG
+    assert b"hidden_state_size" in capi.lib().mz_last_error(None)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from muzero_jl_b200 import capi
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        capi.Context()
+    assert e.value.code == capi.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_python_interface_mirrors_reference_names():
+    import muzero_jl_b200 as mz
+    conf = mz.Config()
+    for f in ("seed", "observation_shape", "action_space", "players", "stacked_observations", "muzero_player", "opponent",
+              "intermediate_rewards", "num_workers", "selfplay_on_gpu", "max_moves", "temperature_threshold", "dirichlet_α",
+              "exploration_ϵ", "pb_c_base", "pb_c_init", "discount", "num_iters", "replay_buffer_size", "num_unroll_steps",
+              "td_steps", "PER", "PER_alpha", "results_path", "networks_path", "training_steps", "batch_size",
+              "checkpoint_interval", "value_loss_weight"):
+        # Python NFKC-normalises identifiers (the reference's U+03F5 becomes U+03B5); same spelling at the call site
+        assert hasattr(conf, unicodedata.normalize("NFKC", f)), f      # src/Constructors.jl:18-52
+    hp = mz.FeedForwardHP()
+    for f in ("width_hidden", "depth_representation", "depth_prediction", "depth_dynamics", "depth_policy", "depth_value",
+              "depth_reward", "depth_state_head", "use_batch_norm", "batch_norm_momentum", "hidden_state_size", "reward_activation"):
+        assert hasattr(hp, f), f        # src/Constructors.jl:62-75
+    from muzero_jl_b200.api import to_mz_config
+    c = to_mz_config(conf, hp, num_slots=64)
+    ref = O.default_config()
+    o = common.oracle_config(c)
+    for name, _ in O.Config._fields_:
+        if name in ("replay_buffer_size", "child_order"):
+            continue
+        assert getattr(o, name) == getattr(ref, name), name

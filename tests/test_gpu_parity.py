@@ -1,0 +1,246 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.  Integer / index results (env
+transitions, visit counts, selected actions, sampled indices) must be bit-exact; in MZ_NN_FP32_EXACT mode the
+network outputs, priors, root values, histories and targets are bit-exact too (the arithmetic contract fixes the
+summation order); loss scalars use a parallel reduction and are compared with rtol 2e-6."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from muzero_jl_b200 import capi
+    return capi
+
+
+def make_ctx(capi, **kw):
+    kw.setdefault("num_slots", 256); kw.setdefault("replay_buffer_size", 1024)
+    cfg = capi.default_config(**kw)
+    return capi.Context(cfg), common.oracle_config(cfg)
+
+
+def test_device_is_blackwell(capi):
+    ctx, _ = make_ctx(capi)
+    info = ctx.device_info()
+    assert info["cc"][0] >= 10 and info["sm_count"] >= 100
+    ctx.close()
+
+
+def test_networks_bit_exact(capi):
+    ctx, ocfg = make_ctx(capi)
+    ctx.init_weights(1337)
+    blob = ctx.get_weights()
+    assert np.array_equal(blob, O.init_weights(ocfg, 1337))
+    rng = np.random.default_rng(1)
+    for B in (1, 31, 32, 100):
+        st = rng.normal(size=(B, 63)).astype(np.float32)
+        h = ctx.representation(st)
+        assert np.array_equal(h, np.stack([O.representation(ocfg, blob, x) for x in st]))
+        v, p = ctx.prediction(h)
+        ov, op = zip(*[O.prediction(ocfg, blob, x) for x in h])
+        assert np.array_equal(v, np.array(ov, np.float32)) and np.array_equal(p, np.stack(op))
+        sa = rng.normal(size=(B, 36)).astype(np.float32)
+        nh, r = ctx.dynamics(sa)
+        oh, orr = zip(*[O.dynamics(ocfg, blob, x) for x in sa])
+        assert np.array_equal(nh, np.stack(oh)) and np.array_equal(r, np.array(orr, np.float32))
+    # set/get round trip per net
+    w2 = rng.normal(size=ctx.num_params(capi.NET_PREDICTION)).astype(np.float32)
+    ctx.set_weights(w2, capi.NET_PREDICTION)
+    assert np.array_equal(ctx.get_weights(capi.NET_PREDICTION), w2)
+    assert np.array_equal(ctx.get_weights(capi.NET_DYNAMICS), blob[18331 + 23242:])
+    ctx.close()
+
+
+def test_env_exhaustive_against_state_graph(capi):
+    """Every reachable (board, legal action) pair of games/tictactoe/game.jl's rules: 6046 boards (KAT-env-3)."""
+    ctx, ocfg = make_ctx(capi)
+    L = O.lib()
+    seen = {}
+    stack = [O.Env()]; L.mzo_env_reset(C.byref(ocfg), C.byref(stack[0]))
+    rows = []
+    while stack:
+        e = stack.pop()
+        key = (e.p1, e.p2)
+        if key in seen:
+            continue
+        seen[key] = 1
+        if L.mzo_env_is_terminated(C.byref(ocfg), C.byref(e)):
+            continue
+        m = L.mzo_env_legal_mask(C.byref(ocfg), C.byref(e))
+        for a in range(1, 10):
+            if m >> (a - 1) & 1:
+                n = O.Env(e.p1, e.p2, e.player, e.moves); L.mzo_env_step(C.byref(ocfg), C.byref(n), a)
+                rows.append((e.p1, e.p2, e.player, a, n.p1, n.p2, n.player, L.mzo_env_reward(C.byref(ocfg), C.byref(n), e.player),
+                             L.mzo_env_is_terminated(C.byref(ocfg), C.byref(n)), L.mzo_env_legal_mask(C.byref(ocfg), C.byref(n))))
+                stack.append(n)
+    assert len(seen) == 6046
+    rows = np.array(rows, dtype=np.int64)
+    p1 = rows[:, 0].astype(np.uint64); p2 = rows[:, 1].astype(np.uint64); pl = rows[:, 2].astype(np.int32)
+    assert np.array_equal(ctx.env_legal(p1, p2, pl) != 0, np.ones(len(rows), bool))
+    reward, done, legal = ctx.env_step(p1, p2, pl, rows[:, 3].astype(np.int32))
+    assert np.array_equal(p1, rows[:, 4].astype(np.uint64)) and np.array_equal(p2, rows[:, 5].astype(np.uint64))
+    assert np.array_equal(pl, rows[:, 6].astype(np.int32))
+    assert np.array_equal(reward, rows[:, 7].astype(np.float32))
+    assert np.array_equal(done, rows[:, 8].astype(np.int32))
+    assert np.array_equal(legal, rows[:, 9].astype(np.uint32))
+    obs = ctx.env_observation(p1[:64], p2[:64])
+    for i in range(64):
+        o = np.zeros(27, np.float32); e = O.Env(int(p1[i]), int(p2[i]), 1, 0); L.mzo_env_observation(C.byref(ocfg), C.byref(e), O._p(o))
+        assert np.array_equal(obs[i], o)
+    q1, q2, qp = ctx.env_reset(5)
+    assert not q1.any() and not q2.any() and np.all(qp == 1)
+    ctx.close()
+
+
+@pytest.mark.parametrize("S,eps,tie,n", [(10, 0.0, 0, 70), (50, 0.0, 0, 300), (50, 0.25, 0, 64), (25, 0.0, 1, 33)])
+def test_run_mcts_bit_exact(capi, S, eps, tie, n):
+    ctx, ocfg = make_ctx(capi, num_iters=S, exploration_eps=eps, tie_mode=tie)
+    ctx.init_weights(7); blob = ctx.get_weights()
+    st, legal, tp = common.random_stacked(ocfg, n, seed=S + n)
+    game = np.arange(n, dtype=np.uint64) + 100; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    for i in range(n):
+        ovc, orv, opri = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i]))
+        assert vc[i].tolist() == ovc.tolist(), i
+        assert rv[i] == orv and np.array_equal(pri[i], opri), i
+    assert np.all(vc.sum(1) == S)
+    ctx.close()
+
+
+def test_run_mcts_rejects_empty_legal(capi):
+    ctx, _ = make_ctx(capi)
+    ctx.init_weights(1)
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.run_mcts(np.zeros((1, 63), np.float32), [0], [1], True, [0], [1])
+    ctx.close()
+
+
+def test_golden_mcts(capi):
+    g = np.load(os.path.join(common.ROOT, "tests", "golden", "mcts_s50.npz"))
+    for eps, sfx in ((0.0, ""), (0.25, "_noise")):
+        ctx, _ = make_ctx(capi, num_iters=50, exploration_eps=eps)
+        ctx.init_weights(1337)
+        assert abs(float(ctx.get_weights().astype(np.float64).sum()) - float(g["weight_checksum"])) == 0
+        vc, rv, pri = ctx.run_mcts(g["stacked"], g["legal"], g["to_play"], True, g["game"], g["move"], priors=True)
+        assert np.array_equal(vc, g["vc" + sfx]) and np.array_equal(rv, g["rv" + sfx]) and np.array_equal(pri, g["pri" + sfx])
+        if not sfx:
+            h = ctx.representation(g["stacked"]); v, p = ctx.prediction(h)
+            assert np.array_equal(h, g["hidden"]) and np.array_equal(v, g["value"]) and np.array_equal(p, g["policy"])
+        ctx.close()
+
+
+def test_select_action_bit_exact(capi):
+    ctx, ocfg = make_ctx(capi)
+    rng = np.random.default_rng(5); n = 500
+    legal = rng.integers(1, 512, n).astype(np.uint32)
+    vc = (rng.integers(0, 12, (n, 9)) * ((legal[:, None] >> np.arange(9)) & 1)).astype(np.int32)
+    vc[np.arange(n), [int(np.log2(int(l) & -int(l))) for l in legal]] += 1   # at least one visit
+    game = rng.integers(0, 1 << 20, n).astype(np.uint64); move = rng.integers(1, 10, n).astype(np.int32)
+    for T in (0.0, 1.0, 0.5, 0.25, 0.7, float("inf")):
+        act = ctx.select_action(vc, legal, T, game, move)
+        ref = [O.select_action(ocfg, vc[i], int(legal[i]), T, int(game[i]), int(move[i])) for i in range(n)]
+        assert act.tolist() == ref, T
+    ctx.close()
+
+
+@pytest.mark.parametrize("temperature,eps,slots,games", [(1.0, 0.25, 64, 200), (0.0, 0.0, 96, 96), (1.0, 0.0, 32, 45)])
+def test_self_play_bit_exact(capi, temperature, eps, slots, games):
+    ctx, ocfg = make_ctx(capi, exploration_eps=eps, num_slots=slots, replay_buffer_size=256)
+    ctx.init_weights(3); blob = ctx.get_weights()
+    sims, moves = ctx.self_play(1000, games, temperature)
+    o = O.self_play(ocfg, blob, 1000, games, temperature, 4)
+    assert sims == o["sims"] and moves == int(o["T"].sum())
+    info = ctx.replay_info()
+    assert info["n_games"] == games and info["first_key"] == 1 and info["total_samples"] == int(o["T"].sum())
+    h = ctx.history_export()
+    assert sorted(h["game_id"].tolist()) == list(range(1000, 1000 + games))
+    for j in range(games):
+        i = int(h["game_id"][j]) - 1000
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][i]), (k, i)
+    st = ctx.search_stats()
+    assert 1.0 <= st["mean_depth"] <= 10 and 1.0 <= st["mean_legal"] <= 9
+    ctx.close()
+
+
+def test_self_play_is_independent_of_slot_count(capi):
+    res = []
+    for slots in (32, 160):
+        ctx, _ = make_ctx(capi, num_slots=slots, replay_buffer_size=512)
+        ctx.init_weights(11)
+        ctx.self_play(0, 300, 1.0)
+        h = ctx.history_export(); order = np.argsort(h["game_id"])
+        res.append({k: h[k][order] for k in common.HIST_KEYS}); ctx.close()
+    for k in common.HIST_KEYS:
+        assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_replay_ring_eviction_and_counters(capi):
+    ctx, ocfg = make_ctx(capi, num_slots=32, replay_buffer_size=64)
+    ctx.init_weights(2)
+    ctx.self_play(0, 100, 1.0)
+    info = ctx.replay_info()
+    assert info["n_games"] == 64 and info["first_key"] == 37       # FIFO eviction beyond replay_buffer_size (ReplayBuffer.jl:156-160)
+    h = ctx.history_export()
+    assert info["total_samples"] == int(h["T"].sum())
+    ctx.replay_clear()
+    assert ctx.replay_info()["n_games"] == 0
+    ctx.close()
+
+
+def test_get_batch_and_learner_against_oracle_and_golden(capi):
+    g = np.load(os.path.join(common.ROOT, "tests", "golden", "selfplay_learn.npz"))
+    ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=64)
+    ctx.init_weights(1337); blob = ctx.get_weights()
+    sims, _ = ctx.self_play(0, 64, 1.0)
+    assert sims == int(g["sims"])
+    h = ctx.history_export(); order = np.argsort(h["game_id"])
+    for k in common.HIST_KEYS:
+        assert np.array_equal(h[k][order], g["hist_" + k]), k
+    # the ring's key order is the save order; rebuild it in game-id order so sampled indices match the oracle's buffer
+    ctx.replay_clear()
+    hist = {k: g["hist_" + k] for k in common.HIST_KEYS}
+    ctx.history_import(hist, game_id=np.arange(64))
+    for step in (1, 2, 9):
+        b = ctx.get_batch(step)
+        ob = O.get_batch(ocfg, hist, step, first_key=1)
+        for k in common.BATCH_KEYS:
+            assert np.array_equal(b[k], ob[k]), (k, step)
+    b = ctx.get_batch(1)
+    for k in common.BATCH_KEYS:
+        assert np.array_equal(b[k], g["batch_" + k]), k
+    pv, pr, pp, losses = ctx.learn_forward(b)
+    assert np.array_equal(pv, g["pred_values"]) and np.array_equal(pr, g["pred_rewards"]) and np.array_equal(pp, g["pred_policies"])
+    assert np.allclose(losses, g["losses"], rtol=LOSS_RTOL, atol=0)
+    l1 = ctx.learn_step(1); l2 = ctx.learn_step(2)
+    assert np.allclose(l1, g["losses_step1"], rtol=LOSS_RTOL, atol=0) and np.allclose(l2, g["losses_step2"], rtol=LOSS_RTOL, atol=0)
+    assert np.array_equal(ctx.get_weights(), g["weights_after_2"])     # reference_l2 update is elementwise: bit-exact
+    ctx.close()
+
+
+def test_learner_large_batch_properties(capi):
+    """Size-independent properties at a throughput-sized batch: forward rows 0 and 1 coincide (Q19), rewards row 0 = 0,
+    policies are distributions, and the per-sample result does not depend on the batch it is part of."""
+    ctx, ocfg = make_ctx(capi, num_slots=256, replay_buffer_size=2048, batch_size=4096)
+    ctx.init_weights(4)
+    ctx.self_play(0, 1024, 1.0)
+    b = ctx.get_batch(3)
+    pv, pr, pp, losses = ctx.learn_forward(b)
+    assert np.array_equal(pv[:, 0], pv[:, 1]) and np.array_equal(pp[:, 0], pp[:, 1]) and not pr[:, 0].any()
+    assert np.allclose(pp.sum(-1), 1.0, atol=1e-5) and np.all(np.isfinite(losses))
+    sub = {k: b[k][100:133] for k in ("obs", "actions", "values", "rewards", "policies", "gscale")}
+    pv2, pr2, pp2, _ = ctx.learn_forward(sub)
+    assert np.array_equal(pv2, pv[100:133]) and np.array_equal(pr2, pr[100:133]) and np.array_equal(pp2, pp[100:133])
+    blob = ctx.get_weights()
+    opv, opr, opp, ol = O.learn_forward(common.oracle_config(ctx.cfg), blob, {k: v[:64] for k, v in b.items()})
+    assert np.array_equal(opv, pv[:64]) and np.array_equal(opp, pp[:64])
+    ctx.close()
