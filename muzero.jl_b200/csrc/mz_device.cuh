@@ -1,15 +1,18 @@
 // mz_device.cuh -- sm_100a device machinery shared by the kernels of libmuzero_b200:
 //   * mbarrier + cp.async.bulk (TMA 1-D bulk copy) weight pipeline: each Dense layer's padded {W,b} block is
 //     staged global -> shared by one elected thread while the previous layer computes;
-//   * the exact-fp32 Dense tile: 32 rows x out_pad columns per CTA, 4x4 register tiles, sequential-k fmaf
-//     (bit-identical to the arithmetic contract in DESIGN.md);
-//   * chains of layers for the three networks (src/Learning.jl:87-142).
+//   * the exact-fp32 Dense tile: 32 rows x out_pad columns per 128-thread group, 4x4 register tiles,
+//     sequential-k fmaf (bit-identical to the arithmetic contract in DESIGN.md);
+//   * two independent 128-thread groups per CTA (named barriers), so prediction(parent) and dynamics(parent, a)
+//     -- which are data-independent -- run concurrently, each with its own weight pipeline.
 #pragma once
 #include <cuda_runtime.h>
 #include "mz_common.h"
 
-#define MZ_ROWS 32        // rows (trees / samples) per CTA
-#define MZ_THREADS 128
+#define MZ_ROWS 32          // rows (trees / samples) per CTA
+#define MZ_GROUP 128        // threads per network group
+#define MZ_THREADS 256      // two groups
+#define MZ_LANES 8          // lanes cooperating on one tree in the tree phases (MZ_THREADS / MZ_ROWS)
 
 __device__ __forceinline__ uint32_t mz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mz_mbar_init(uint64_t *bar, uint32_t count) {
@@ -35,12 +38,24 @@ __device__ __forceinline__ void mz_mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t spin = 0; !mz_mbar_try_wait(bar, parity); spin++)
         if (spin > (1u << 24)) __trap();
 }
+// named barrier over one 128-thread group (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void mz_group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(MZ_GROUP) : "memory"); }
 
-struct mz_nn_pipe {
+__device__ __forceinline__ float4 mz_lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mz_sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+struct mz_nn_pipe {          // one per group
     float *wbuf[2];
-    uint64_t *mbar;        // [2]
-    const float *wglob;    // padded device blob
-    uint32_t q;            // layers executed so far by this CTA (uniform)
+    uint64_t *mbar;          // [2]
+    const float *wglob;      // padded device blob
+    uint32_t q;              // layers executed so far by this group (uniform within the group)
+    int grp, gtid;
 };
 
 __device__ __forceinline__ void mz_nn_issue(const mz_nn_pipe &s, const mz_params &P, int layer, uint32_t slot) {
@@ -50,25 +65,26 @@ __device__ __forceinline__ void mz_nn_issue(const mz_nn_pipe &s, const mz_params
     mz_bulk_g2s(s.wbuf[slot], s.wglob + L.w_off, bytes, &s.mbar[slot]);
 }
 
-// y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row]
-__device__ __forceinline__ void mz_dense_tile(const mz_layer &L, const float *__restrict__ wsm, const float *__restrict__ src,
-                                              float *__restrict__ dst) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row].
+// One copy of this code in the binary (noinline): every layer of every network goes through it.
+__device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
+    const int lane = gtid & 31, warp = gtid >> 5;
     const int rg = lane & 7;
-    const int opq = L.out_pad >> 2;
-    const int in = L.in;
+    const int opq = out_pad >> 2;
+    const uint32_t wstride = (uint32_t)out_pad * 4u;
     for (int g = (warp << 2) | (lane >> 3); g < opq; g += 16) {
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
-        const float4 *w4 = reinterpret_cast<const float4 *>(wsm) + g;
-        const float4 *x4 = reinterpret_cast<const float4 *>(src) + rg;
+        uint32_t wa = w_smem + (uint32_t)g * 16u;
+        uint32_t xa = src_smem + (uint32_t)rg * 16u;
 #pragma unroll 4
         for (int k = 0; k < in; k++) {
-            const float4 wv = w4[k * opq];
-            const float4 xv = x4[k * (MZ_ROWS / 4)];
+            const float4 wv = mz_lds128(wa);
+            const float4 xv = mz_lds128(xa);
+            wa += wstride; xa += MZ_ROWS * 4;
             const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
             const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
@@ -76,28 +92,28 @@ __device__ __forceinline__ void mz_dense_tile(const mz_layer &L, const float *__
 #pragma unroll
                 for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wj[j], xi[i], acc[i][j]);
         }
-        const float4 bv = reinterpret_cast<const float4 *>(wsm + in * L.out_pad)[g];
+        const float4 bv = mz_lds128(w_smem + (uint32_t)in * wstride + (uint32_t)g * 16u);
         const float bj[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float4 r;
-            r.x = mz_activate(acc[0][j] + bj[j], L.act);
-            r.y = mz_activate(acc[1][j] + bj[j], L.act);
-            r.z = mz_activate(acc[2][j] + bj[j], L.act);
-            r.w = mz_activate(acc[3][j] + bj[j], L.act);
-            reinterpret_cast<float4 *>(dst + (4 * g + j) * MZ_ROWS)[rg] = r;
+            r.x = acc[0][j] + bj[j]; r.y = acc[1][j] + bj[j]; r.z = acc[2][j] + bj[j]; r.w = acc[3][j] + bj[j];
+            if (act == MZ_ACT_RELU) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
+            else if (act == MZ_ACT_TANH) { r.x = mz_tanhf(r.x); r.y = mz_tanhf(r.y); r.z = mz_tanhf(r.z); r.w = mz_tanhf(r.w); }
+            mz_sts128(dst_smem + (uint32_t)((4 * g + j) * MZ_ROWS * 4) + (uint32_t)rg * 16u, r);
         }
     }
 }
 
-// One layer: prefetch `next` (or nothing when next < 0) into the other buffer, wait for this layer's weights,
-// compute, barrier.  Preconditions: this layer's copy was issued earlier; a __syncthreads separates the last
+// One layer for one group: prefetch `next` (or nothing when next < 0) into the other buffer, wait for this layer's
+// weights, compute, group barrier.  Preconditions: this layer's copy was issued earlier; a barrier separates the last
 // reads of the other buffer (layer q-1) and of `dst`'s previous contents from this call.
 __device__ __forceinline__ void mz_nn_layer(mz_nn_pipe &s, const mz_params &P, int layer, int next, const float *src, float *dst) {
-    if (threadIdx.x == 0 && next >= 0) mz_nn_issue(s, P, next, (s.q + 1) & 1u);
+    if (s.gtid == 0 && next >= 0) mz_nn_issue(s, P, next, (s.q + 1) & 1u);
     mz_mbar_wait(&s.mbar[s.q & 1u], (s.q >> 1) & 1u);
-    mz_dense_tile(P.layers[layer], s.wbuf[s.q & 1u], src, dst);
-    __syncthreads();
+    const mz_layer &L = P.layers[layer];
+    mz_dense_tile(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
+    mz_group_sync(s.grp);
     s.q++;
 }
 __device__ __forceinline__ void mz_nn_chain(mz_nn_pipe &s, const mz_params &P, int first, int n, int after, const float *src,
@@ -110,8 +126,8 @@ __device__ __forceinline__ void mz_nn_chain(mz_nn_pipe &s, const mz_params &P, i
     }
 }
 // trunk -> bufT, head 1 -> h1dst, head 2 -> h2dst (Split, src/Learning.jl:60-68); `after` = layer prefetched last
-__device__ __forceinline__ void mz_nn_net(mz_nn_pipe &s, const mz_params &P, int net, int after, const float *src, float *bufT,
-                                          float *h1dst, float *h2dst, float *t0, float *t1) {
+__device__ __noinline__ void mz_nn_net(mz_nn_pipe &s, const mz_params &P, int net, int after, const float *src, float *bufT,
+                                       float *h1dst, float *h2dst, float *t0, float *t1) {
     const mz_net &N = P.nets[net];
     int f = N.first;
     if (N.n_h1 == 0) { mz_nn_chain(s, P, f, N.n_trunk, after, src, h1dst, t0, t1); return; }
@@ -122,38 +138,48 @@ __device__ __forceinline__ void mz_nn_net(mz_nn_pipe &s, const mz_params &P, int
 
 // shared-memory carve-up used by every NN-running kernel
 struct mz_smem_plan {
-    float *wbuf[2]; uint64_t *mbar; float *in0, *in1, *bufT, *t0, *t1, *outV, *outL, *outR, *outH;
+    float *wbuf[2][2]; uint64_t *mbar[2];        // per group
+    float *bufT[2], *t0[2], *t1[2];              // per group scratch activations
+    float *in0, *in1;                            // staged inputs: in0 = representation / dynamics input, in1 = prediction input
+    float *outV, *outL, *outR, *outH;            // value (4 rows), policy logits (16), reward (4), hidden (hidden_pad)
     double *pbc0, *sqrtN;
+    uint16_t *path;                              // [32][S+2] selection paths
 };
 __host__ __device__ inline size_t mz_smem_bytes(int max_dim, int max_layer_floats, int hidden_pad, int S) {
     size_t w = ((size_t)max_layer_floats * 4 + 127) & ~(size_t)127;
     size_t buf = (size_t)max_dim * MZ_ROWS * 4;
     size_t small = (size_t)(4 + 16 + 4) * MZ_ROWS * 4 + (size_t)hidden_pad * MZ_ROWS * 4;
     size_t tab = (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
-    return 2 * w + 128 + 5 * buf + small + tab + 128;
+    size_t path = (((size_t)S + 2) * 2 * MZ_ROWS + 127) & ~(size_t)127;
+    return 4 * w + 128 + 8 * buf + small + tab + path + 128;
 }
 __device__ __forceinline__ mz_smem_plan mz_smem_carve(unsigned char *base, int max_dim, int max_layer_floats, int hidden_pad, int S) {
     mz_smem_plan p;
     size_t w = ((size_t)max_layer_floats * 4 + 127) & ~(size_t)127;
     size_t buf = (size_t)max_dim * MZ_ROWS * 4;
     unsigned char *c = base;
-    p.wbuf[0] = (float *)c; c += w;
-    p.wbuf[1] = (float *)c; c += w;
-    p.mbar = (uint64_t *)c; c += 128;
-    p.in0 = (float *)c; c += buf;
+    for (int g = 0; g < 2; g++) for (int i = 0; i < 2; i++) { p.wbuf[g][i] = (float *)c; c += w; }
+    p.mbar[0] = (uint64_t *)c; p.mbar[1] = (uint64_t *)(c + 32); c += 128;
+    p.in0 = (float *)c; c += buf;                // in0, in1, bufT[0..1], t0[0..1], t1[0..1] are contiguous (zeroed together)
     p.in1 = (float *)c; c += buf;
-    p.bufT = (float *)c; c += buf;
-    p.t0 = (float *)c; c += buf;
-    p.t1 = (float *)c; c += buf;
+    for (int g = 0; g < 2; g++) { p.bufT[g] = (float *)c; c += buf; p.t0[g] = (float *)c; c += buf; p.t1[g] = (float *)c; c += buf; }
     p.outV = (float *)c; c += 4 * MZ_ROWS * 4;
     p.outL = (float *)c; c += 16 * MZ_ROWS * 4;
     p.outR = (float *)c; c += 4 * MZ_ROWS * 4;
     p.outH = (float *)c; c += (size_t)hidden_pad * MZ_ROWS * 4;
-    p.pbc0 = (double *)c; c += ((size_t)S + 2) * 8;
-    p.sqrtN = (double *)c;
+    p.pbc0 = (double *)c; p.sqrtN = p.pbc0 + (S + 2); c += (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
+    p.path = (uint16_t *)c;
     return p;
 }
+// both pipes are initialised by thread 0 of the CTA; every thread builds the descriptor of its own group
 __device__ __forceinline__ void mz_pipe_init(mz_nn_pipe &s, const mz_smem_plan &sp, const float *wglob) {
-    s.wbuf[0] = sp.wbuf[0]; s.wbuf[1] = sp.wbuf[1]; s.mbar = sp.mbar; s.wglob = wglob; s.q = 0;
-    if (threadIdx.x == 0) { mz_mbar_init(&sp.mbar[0], 1); mz_mbar_init(&sp.mbar[1], 1); mz_fence_mbar_init(); }
+    s.grp = threadIdx.x >> 7; s.gtid = threadIdx.x & (MZ_GROUP - 1);
+    s.wbuf[0] = sp.wbuf[s.grp][0]; s.wbuf[1] = sp.wbuf[s.grp][1]; s.mbar = sp.mbar[s.grp]; s.wglob = wglob; s.q = 0;
+    if (threadIdx.x == 0) {
+        mz_mbar_init(&sp.mbar[0][0], 1); mz_mbar_init(&sp.mbar[0][1], 1); mz_mbar_init(&sp.mbar[1][0], 1); mz_mbar_init(&sp.mbar[1][1], 1);
+        mz_fence_mbar_init();
+    }
+}
+__device__ __forceinline__ void mz_zero_activations(const mz_smem_plan &sp, int max_dim) {
+    for (int i = threadIdx.x; i < 8 * max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
 }

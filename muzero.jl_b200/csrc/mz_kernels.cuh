@@ -45,21 +45,133 @@ struct mz_search_args {
     unsigned long long *stats;   // [0] sum depth, [1] simulations, [2] sum legal, [3] roots
 };
 
+// ---- lane-parallel tree operations: MZ_LANES (8) lanes of a warp cooperate on one tree.  They are the GPU-only
+// counterparts of the scalar mz_tree_select / mz_tree_expand / mz_tree_backup in mz_common.h (which the CPU harness
+// checks against the oracle) and must produce the same bits; tests/test_gpu_parity.py holds them to that. ----
+__device__ __forceinline__ float mz_seg_max(float v, uint32_t segmask) {
+#pragma unroll
+    for (int m = 1; m < MZ_LANES; m <<= 1) { float o = __shfl_xor_sync(segmask, v, m, MZ_LANES); v = o > v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ uint32_t mz_seg_or(uint32_t v, uint32_t segmask) {
+#pragma unroll
+    for (int m = 1; m < MZ_LANES; m <<= 1) v |= __shfl_xor_sync(segmask, v, m, MZ_LANES);
+    return v;
+}
+__device__ __forceinline__ int mz_seg_add(int v, uint32_t segmask) {
+#pragma unroll
+    for (int m = 1; m < MZ_LANES; m <<= 1) v += __shfl_xor_sync(segmask, v, m, MZ_LANES);
+    return v;
+}
+
+// select_child loop (src/SelfPlay.jl:157-166, 261-268): lane ln scores the children at Dict positions ln and ln+8.
+__device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, const mz_tree &t, const double *pbc0, const double *sqrtN, uint32_t legal,
+                                                        uint32_t posmask, mz_minmax mm, uint32_t game, uint32_t move, uint32_t sim, int ln,
+                                                        uint32_t segmask, uint16_t *path) {
+    mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0;
+    const int a0 = ln < P.A ? P.order[ln] : 0, a1 = ln + 8 < P.A ? P.order[ln + 8] : 0;
+    const bool ok0 = (posmask >> ln) & 1u, ok1 = (posmask >> (ln + 8)) & 1u;
+    int e = mz_nodeB_exp(t.B[0]);
+    if (ln == 0) path[0] = 0;
+    while (e >= 0) {
+        L.depth++;
+        const int base = 1 + e * P.A;
+        const int N = (int)mz_f2bits(t.A[L.node].x);
+        float s0 = 0.0f, s1 = 0.0f;
+        if (ok0) s0 = mz_ucb(P, pbc0, sqrtN, N, t.A[base + a0 - 1], mm);
+        if (ok1) s1 = mz_ucb(P, pbc0, sqrtN, N, t.A[base + a1 - 1], mm);
+        float b = ok0 ? s0 : -INFINITY;
+        if (ok1) b = s1 > b ? s1 : b;
+        const float best = mz_seg_max(b, segmask);
+        uint32_t tied = ((ok0 && s0 == best) ? (1u << ln) : 0u) | ((ok1 && s1 == best) ? (1u << (ln + 8)) : 0u);
+        tied = mz_seg_or(tied, segmask);
+        if (tied == 0) tied = posmask & (0u - posmask);
+        const int nt = __popc(tied);
+        int pick = 0;
+        if (nt > 1 && P.tie_mode == MZ_TIE_PHILOX) pick = (int)mz_u32_below(mz_philox(P.seed, MZ_STREAM_TIE, game, move, sim, (uint32_t)L.depth).x, (uint32_t)nt);
+        uint32_t m = tied;
+        for (int i = 0; i < pick; i++) m &= m - 1;
+        const int j = __ffs((int)m) - 1;
+        L.action = P.order[j];
+        L.parent = L.node;
+        L.node = base + L.action - 1;
+        if (ln == 0) path[L.depth] = (uint16_t)L.node;
+        e = mz_nodeB_exp(t.B[L.node]);
+    }
+    return L;
+}
+
+// softmax(logits) (Learning.jl:114) then expand_node!'s second softmax over the legal subset (SelfPlay.jl:88-96, Q1);
+// exp() calls are spread over the lanes, both sums run in ascending action order like the scalar code.
+__device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *logits /* [a*MZ_ROWS] */,
+                                                     float reward, int ln, uint32_t segmask) {
+    const bool v0 = ln < P.A, v1 = ln + 8 < P.A;
+    const float l0 = v0 ? logits[ln * MZ_ROWS] : -INFINITY, l1 = v1 ? logits[(ln + 8) * MZ_ROWS] : -INFINITY;
+    float m = mz_seg_max(l1 > l0 ? l1 : l0, segmask);
+    float e0 = v0 ? mz_expf(l0 - m) : 0.0f, e1 = v1 ? mz_expf(l1 - m) : 0.0f;
+    float s = 0.0f;
+    for (int a = 0; a < P.A; a++) { float v = __shfl_sync(segmask, a < 8 ? e0 : e1, a & 7, MZ_LANES); s = s + v; }
+    const float p0 = e0 / s, p1 = e1 / s;                       // policy[ln], policy[ln+8]
+    const bool g0 = v0 && ((legal >> ln) & 1u), g1 = v1 && ((legal >> (ln + 8)) & 1u);
+    float q = g0 ? p0 : -INFINITY; if (g1) q = p1 > q ? p1 : q;
+    const float m2 = mz_seg_max(q, segmask);
+    const float f0 = g0 ? mz_expf(p0 - m2) : 0.0f, f1 = g1 ? mz_expf(p1 - m2) : 0.0f;
+    float s2 = 0.0f;
+    for (int a = 0; a < P.A; a++) { float v = __shfl_sync(segmask, a < 8 ? f0 : f1, a & 7, MZ_LANES); if ((legal >> a) & 1u) s2 = s2 + v; }
+    const int base = 1 + e * P.A;
+    if (v0) { mz_f4 c; c.x = mz_bits2f(0u); c.y = 0.0f; c.w = 0.0f; c.z = g0 ? f0 / s2 : 0.0f; t.A[base + ln] = c; t.B[base + ln] = mz_nodeB_pack(node, -1, 0); }
+    if (v1) { mz_f4 c; c.x = mz_bits2f(0u); c.y = 0.0f; c.w = 0.0f; c.z = g1 ? f1 / s2 : 0.0f; t.A[base + ln + 8] = c; t.B[base + ln + 8] = mz_nodeB_pack(node, -1, 0); }
+    if (ln == 0) {
+        t.B[node] = mz_nodeB_pack(mz_nodeB_parent(t.B[node]), e, 0);
+        mz_f4 me = t.A[node]; me.w = reward; t.A[node] = me;
+    }
+    __syncwarp(segmask);
+}
+
+// backpropagate! (SelfPlay.jl:190-217, Q8) over the recorded path: the node records of 8 path entries are loaded in
+// parallel, the (cheap, sequential) value recurrence is replayed by every lane, the owning lane writes back.
+__device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const mz_tree &t, const uint16_t *path, int depth, float value, mz_minmax &mm,
+                                                     int ln, uint32_t segmask) {
+    for (int top = depth; top >= 0; top -= MZ_LANES) {
+        const int idx = top - ln;
+        const int nd = idx >= 0 ? (int)path[idx] : 0;
+        mz_f4 rec = t.A[nd];
+        const int cnt = top + 1 < MZ_LANES ? top + 1 : MZ_LANES;
+        for (int u = 0; u < cnt; u++) {
+            const float x = __shfl_sync(segmask, rec.x, u, MZ_LANES), y = __shfl_sync(segmask, rec.y, u, MZ_LANES), w = __shfl_sync(segmask, rec.w, u, MZ_LANES);
+            const int j = depth - (top - u);
+            const bool same = (P.P == 1) || ((j % P.P) == 0);
+            const float ny = same ? y + value : y - value;
+            const int vc = (int)mz_f2bits(x) + 1;
+            const float upd = w + P.discount * (ny / (float)vc);
+            mm.mn = mm.mn < upd ? mm.mn : upd;
+            mm.mx = mm.mx > upd ? mm.mx : upd;
+            if (P.P == 1) value = w + P.discount * value;
+            else value = same ? -w : w + P.discount * value;
+            if (ln == u) { rec.x = mz_bits2f((uint32_t)vc); rec.y = ny; t.A[nd] = rec; }
+        }
+    }
+    __syncwarp(segmask);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
     const int tid = threadIdx.x;
-    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;      // tree / slot handled by this thread (tid < 32)
+    const int r = tid >> 3, ln = tid & (MZ_LANES - 1);              // tree (row) of this thread and its lane within the tree
+    const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
+    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + r;
     mz_nn_pipe pipe;
     mz_pipe_init(pipe, sp, a.wglob);
-    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;   // in0,in1,bufT,t0,t1 are contiguous
+    mz_zero_activations(sp, a.max_dim);
     for (int i = tid; i <= P.S + 1; i += MZ_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
+    uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
-    // ---- per-tree state (threads 0..31) ----
+    // ---- per-tree state, replicated in the 8 lanes of the tree ----
     bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
     mz_tree tree; tree.A = nullptr; tree.B = nullptr; tree.hidden = nullptr;
-    if (tid < MZ_ROWS && g < a.n) {
+    if (g < a.n) {
         tree = mz_tree_at(P, a.tree_pool, g);
         if (MODE == MZ_MODE_API) {
             active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
@@ -73,85 +185,91 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
         }
         if (legal == 0) active = false;   // run_mcts asserts !isempty(legal_actions) (SelfPlay.jl:243); never reached in play
     }
+    uint32_t posmask = 0;                 // legal actions as a mask over Dict positions
+    for (int j = 0; j < P.A; j++) if ((legal >> (P.order[j] - 1)) & 1u) posmask |= 1u << j;
     __syncthreads();   // mbarrier init + zeroed buffers visible
-    if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);
+    const int pred_first = P.nets[1].first, dyn_first = P.nets[2].first;
+    if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);            // group 0: representation, then prediction
+    if (tid == MZ_GROUP) mz_nn_issue(pipe, P, dyn_first, 0);           // group 1: dynamics (first used in simulation 1)
 
     // ---- stage the stacked observations, k-major (get_stacked_observations, SelfPlay.jl:128-149) ----
     if (MODE == MZ_MODE_API) {
         for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
-            int r = i / P.stack_size, k = i % P.stack_size;
-            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
-            sp.in0[k * MZ_ROWS + r] = gg < a.n ? a.stacked[gg * P.stack_size + k] : 0.0f;
+            int rr = i / P.stack_size, k = i % P.stack_size;
+            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + rr;
+            sp.in0[k * MZ_ROWS + rr] = gg < a.n ? a.stacked[gg * P.stack_size + k] : 0.0f;
         }
     } else {
         for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
-            int k = i / MZ_ROWS, r = i % MZ_ROWS;
-            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
+            int k = i / MZ_ROWS, rr = i % MZ_ROWS;
+            int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + rr;
             float v = 0.0f;
             if (gg < a.n && a.slots.status[gg] == MZ_SLOT_ACTIVE) {
                 int T = a.slots.T[gg];
                 v = mz_stacked_value(P, a.slots.h_p1 + gg * P.Tmax, a.slots.h_p2 + gg * P.Tmax, a.slots.h_action + gg * P.Tmax, T + 1, k);
             }
-            sp.in0[k * MZ_ROWS + r] = v;
+            sp.in0[k * MZ_ROWS + rr] = v;
         }
     }
     __syncthreads();
 
-    // ---- root: representation -> h0; prediction(h0) -> (v0, p0)  (SelfPlay.jl:233-245) ----
-    const int pred_first = P.nets[1].first;
-    mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT, sp.outH, nullptr, sp.t0, sp.t1);
-    mz_nn_net(pipe, P, 1, pred_first, sp.outH, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);   // prefetches the first simulation's layer
+    // ---- root: representation -> h0; prediction(h0) -> (v0, p0)  (SelfPlay.jl:233-245), group 0 only ----
+    if (pipe.grp == 0) {
+        mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net(pipe, P, 1, pred_first, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // prefetches simulation 1's first layer
+    }
+    __syncthreads();
 
     mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;                                    // SelfPlay.jl:251
     unsigned long long depth_sum = 0;
-    float logits[MZ_MAX_A], policy[MZ_MAX_A];
     if (active) {
-        for (int k = 0; k < P.hidden; k++) tree.hidden[k] = sp.outH[k * MZ_ROWS + tid];
-        for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
-        mz_softmax(logits, P.A, policy);                                                   // Learning.jl:114
-        mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;   // Node(prior=0), :232
-        tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
-        mz_tree_expand(P, tree, 0, 0, legal, policy, 0.0f);                                // :245
-        if (a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);   // :247-249 (eps = 0 is the identity)
+        for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_ROWS + r];
+        if (ln == 0) {
+            mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;   // Node(prior=0), :232
+            tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
+        }
+        __syncwarp(segmask);
+        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, ln, segmask);        // :245
+        if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);   // :247-249 (eps = 0 is the identity)
+        __syncwarp(segmask);
     }
 
     // ---- simulations (SelfPlay.jl:254-283) ----
-    const int dyn_first = P.nets[2].first;
     for (int sim = 1; sim <= P.S; sim++) {
         mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0;
         if (active) {
-            leaf = mz_tree_select(P, tree, sp.pbc0, sp.sqrtN, legal, mm, game, move, (uint32_t)sim);
+            leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
-            uint32_t pb = tree.B[leaf.parent];
-            int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+            const uint32_t pb = tree.B[leaf.parent];
+            const int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
-            float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);                             // 2^dbl: state after dbl in-place doublings (Q6)
-            for (int k = 0; k < P.hidden; k++) {
+            const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);                       // 2^dbl: state after dbl in-place doublings (Q6)
+            for (int k = ln; k < P.hidden; k += MZ_LANES) {
                 float v = h[k] * sc;
-                sp.in1[k * MZ_ROWS + tid] = v;                                              // prediction(parent.hidden_state), :271 (Q5)
-                sp.in0[k * MZ_ROWS + tid] = v * 2.0f;                                       // make_state_action: state .*= 2, :11
+                sp.in1[k * MZ_ROWS + r] = v;                                                // prediction(parent.hidden_state), :271 (Q5)
+                sp.in0[k * MZ_ROWS + r] = v * 2.0f;                                         // make_state_action: state .*= 2, :11
             }
-            float plane = P.act_plane_play[leaf.action];                                    // :8-9
-            for (int k = P.obs_size; k < P.sa_size; k++) sp.in0[k * MZ_ROWS + tid] = plane;
-            tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+            const float plane = P.act_plane_play[leaf.action];                              // :8-9
+            for (int k = P.obs_size + ln; k < P.sa_size; k += MZ_LANES) sp.in0[k * MZ_ROWS + r] = plane;
+            __syncwarp(segmask);
+            if (ln == 0) tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
         }
         __syncthreads();
-        mz_nn_net(pipe, P, 1, dyn_first, sp.in1, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);
-        mz_nn_net(pipe, P, 2, sim < P.S ? pred_first : -1, sp.in0, sp.bufT, sp.outH, sp.outR, sp.t0, sp.t1);
+        if (pipe.grp == 0) mz_nn_net(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+        else               mz_nn_net(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
+        __syncthreads();
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
-            for (int k = 0; k < P.hidden; k++) nh[k] = sp.outH[k * MZ_ROWS + tid];
-            for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
-            mz_softmax(logits, P.A, policy);
-            mz_tree_expand(P, tree, leaf.node, sim, legal, policy, sp.outR[tid]);          // :280 (root's legal set, Q7)
-            mz_tree_backup(P, tree, leaf.node, sp.outV[tid], mm);                          // :281
+            for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
+            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], ln, segmask);   // :280 (root's legal set, Q7)
+            mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);                  // :281
         }
-        // no barrier needed here: the same thread stages the next inputs, and every NN read of in0/in1/out*
-        // finished before the barrier that ended the last layer
+        // no CTA barrier needed here: the lanes that stage the next inputs are the ones that just read the outputs, and
+        // every network read of in0/in1 finished before the barrier above
     }
 
-    // ---- results ----
-    if (active) {
+    // ---- results (lane 0 of each tree) ----
+    if (active && ln == 0) {
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
         for (int i = 0; i < P.A; i++) {
             vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
@@ -261,7 +379,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_const
     const int tid = threadIdx.x;
     mz_nn_pipe pipe;
     mz_pipe_init(pipe, sp, a.wglob);
-    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
+    mz_zero_activations(sp, a.max_dim);
     __syncthreads();
     const mz_net &N = P.nets[a.net];
     if (tid == 0) mz_nn_issue(pipe, P, N.first, 0);
@@ -273,7 +391,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_const
     }
     __syncthreads();
     float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
-    mz_nn_net(pipe, P, a.net, -1, sp.in0, sp.bufT, h1, h2, sp.t0, sp.t1);
+    if (pipe.grp == 0) mz_nn_net(pipe, P, a.net, -1, sp.in0, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0]);
+    __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
     if (tid < MZ_ROWS && g < a.B) {
         if (a.net == 1) {

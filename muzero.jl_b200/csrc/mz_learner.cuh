@@ -65,39 +65,48 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_co
     const bool row_ok = tid < MZ_ROWS && g < a.B;
     mz_nn_pipe pipe;
     mz_pipe_init(pipe, sp, a.wglob);
-    for (int i = tid; i < 5 * a.max_dim * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
+    mz_zero_activations(sp, a.max_dim);
     __syncthreads();
+    const int pred_first = P.nets[1].first, dyn_first = P.nets[2].first;
     if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);
+    if (tid == MZ_GROUP && P.K > 0) mz_nn_issue(pipe, P, dyn_first, 0);
     for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
         int r = i / P.stack_size, k = i % P.stack_size;
         int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + r;
         sp.in0[k * MZ_ROWS + r] = gg < a.B ? a.batch.obs[gg * P.stack_size + k] : 0.0f;
     }
     __syncthreads();
-    const int pred_first = P.nets[1].first, dyn_first = P.nets[2].first;
-    mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT, sp.outH, nullptr, sp.t0, sp.t1);          // :347
+    // representation (:347) then row 0 = prediction(h0) (:351) on group 0; in1 keeps the current hidden state
+    if (pipe.grp == 0) {
+        mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.in1, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net(pipe, P, 1, P.K > 0 ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+    }
+    __syncthreads();
     for (int i = 0; i <= P.K; i++) {
-        // prediction on the current hidden state (outH); row 0 and row 1 both see h0 (Q19)
-        int after = (i == 0) ? (P.K > 0 ? pred_first : -1) : dyn_first;
-        mz_nn_net(pipe, P, 1, after, sp.outH, sp.bufT, sp.outV, sp.outL, sp.t0, sp.t1);           // :351 / :356
-        if (row_ok) {
+        if (row_ok) {   // store row i of the predictions (value/policy from prediction, reward from the dynamics step before it)
             float logits[MZ_MAX_A], policy[MZ_MAX_A];
             for (int k = 0; k < P.A; k++) logits[k] = sp.outL[k * MZ_ROWS + tid];
             mz_softmax(logits, P.A, policy);
             a.pred_values[g * K1 + i] = sp.outV[tid];
             for (int k = 0; k < P.A; k++) a.pred_policies[(g * K1 + i) * P.A + k] = policy[k];
-            if (i == 0) a.pred_rewards[g * K1] = 0.0f;                                            // :352
+            a.pred_rewards[g * K1 + i] = i == 0 ? 0.0f : sp.outR[tid];                              // :352 zeros for row 0
         }
-        if (i == 0) continue;
+        if (i == P.K) break;
+        // unroll step i+1 (:355-370, Q19): prediction(h_i) is evaluated BEFORE the dynamics step, on the same h_i that
+        // dynamics consumes, so the two networks run concurrently on the two groups.
         // make_dynamics_input (:293-304): state * 2 (copy), action plane = Float32(a) / A
         if (row_ok) {
-            float plane = a.batch.actions[g * K1 + (i - 1)] / (float)P.A;
-            for (int k = 0; k < P.hidden; k++) sp.in0[k * MZ_ROWS + tid] = sp.outH[k * MZ_ROWS + tid] * 2.0f;
+            float plane = a.batch.actions[g * K1 + i] / (float)P.A;
+            for (int k = 0; k < P.hidden; k++) sp.in0[k * MZ_ROWS + tid] = sp.in1[k * MZ_ROWS + tid] * 2.0f;
             for (int k = P.obs_size; k < P.sa_size; k++) sp.in0[k * MZ_ROWS + tid] = plane;
         }
         __syncthreads();
-        mz_nn_net(pipe, P, 2, i < P.K ? pred_first : -1, sp.in0, sp.bufT, sp.outH, sp.outR, sp.t0, sp.t1);   // :362
-        if (row_ok) a.pred_rewards[g * K1 + i] = sp.outR[tid];
+        const bool more = i + 1 < P.K;
+        if (pipe.grp == 0) mz_nn_net(pipe, P, 1, more ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // :356
+        else               mz_nn_net(pipe, P, 2, more ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);     // :362
+        __syncthreads();
+        for (int k = tid; k < P.hidden * MZ_ROWS; k += MZ_THREADS) sp.in1[k] = sp.outH[k];          // h_{i+1}
+        __syncthreads();
     }
 }
 
