@@ -203,9 +203,8 @@ def run_b200(a):
         learner = None
         if not a.no_learner:
             if world > 1:
-                uid = torch.from_numpy(capi.Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
-                dist.broadcast(uid, 0)
-                ctx.comm_init(rank, world, uid.cpu().numpy())
+                from muzero_jl_b200 import dist as mzdist
+                mzdist.attach_communicator(ctx, rank, world, device="cuda")
             for t in range(1, 4):
                 ctx.learn_step(t)
             barrier()

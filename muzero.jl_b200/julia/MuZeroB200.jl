@@ -1,0 +1,170 @@
+# MuZeroB200.jl -- drop-in replacement for the hot path of deveshjawla/MuZero.jl: the same function names and
+# signatures as src/SelfPlay.jl, src/ReplayBuffer.jl and src/Learning.jl, with bodies that `ccall` into
+# libmuzero_b200.so (include/muzero_b200.h).  Include it INSTEAD of those three files, after Constructors.jl,
+# game.jl and params.jl (so that `conf`, `hyper`, `GameHistory`, `Config`, `FeedForwardHP` exist).
+#
+# STATUS: source only.  Julia is not installed in the build image, so this file has never been executed; the
+# identical call sequence is exercised through the Python mirror (muzero.jl_b200/api.py) by the test-suite.
+module MuZeroB200
+
+const LIB = get(ENV, "MUZERO_B200_LIB", joinpath(@__DIR__, "..", "libmuzero_b200.so"))
+const MZ_MAX_A = 16
+
+# POD mirror of mz_config (field order is the ABI)
+mutable struct MzConfig
+    game::Int32; W::Int32; H::Int32; C::Int32; A::Int32; num_players::Int32; stacked_observations::Int32; max_moves::Int32
+    num_iters::Int32; num_unroll_steps::Int32; td_steps::Int32; batch_size::Int32; replay_buffer_size::Int32; pb_c_base::Int32
+    intermediate_rewards::Int32; tie_mode::Int32
+    pb_c_init::Float32; discount::Float32; dirichlet_alpha::Float32; exploration_eps::Float32
+    seed::UInt64
+    child_order::NTuple{MZ_MAX_A,Int32}
+    width_hidden::Int32; depth_representation::Int32; depth_prediction::Int32; depth_dynamics::Int32
+    depth_policy::Int32; depth_value::Int32; depth_reward::Int32; depth_state_head::Int32
+    hidden_state_size::Int32; reward_activation_tanh::Int32
+    num_slots::Int32; nn_mode::Int32
+    MzConfig() = new()
+end
+
+struct MzError <: Exception
+    code::Int32
+    msg::String
+end
+
+mutable struct Engine          # one mz_ctx = one GPU; replaces the RemoteChannels of games/tictactoe/main.jl:15-21
+    ctx::Ptr{Cvoid}
+    cfg::MzConfig
+    training_step::Int
+    next_game::Int
+end
+
+check(e::Engine, rc) = rc == 0 ? nothing : throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx))))
+
+"Build the engine from the reference's `conf::Config` and `hyper::FeedForwardHP` (src/Constructors.jl:18-75)."
+function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
+    c = MzConfig()
+    ccall((:mz_default_config, LIB), Cint, (Ref{MzConfig},), c)
+    c.W, c.H, c.C = conf.observation_shape
+    c.A = length(conf.action_space); c.num_players = length(conf.players)
+    c.stacked_observations = conf.stacked_observations; c.max_moves = conf.max_moves; c.num_iters = conf.num_iters
+    c.num_unroll_steps = conf.num_unroll_steps; c.td_steps = conf.td_steps; c.batch_size = conf.batch_size
+    c.replay_buffer_size = max(conf.replay_buffer_size, num_slots); c.pb_c_base = conf.pb_c_base
+    c.intermediate_rewards = conf.intermediate_rewards; c.pb_c_init = conf.pb_c_init; c.discount = conf.discount
+    c.dirichlet_alpha = conf.dirichlet_α; c.exploration_eps = conf.exploration_ϵ; c.seed = conf.seed
+    order = zeros(Int32, MZ_MAX_A)
+    ccall((:mz_julia_dict_order, LIB), Cint, (Cint, Ptr{Int32}), c.A, order)   # or: collect(keys(Dict(a => 0 for a in conf.action_space)))
+    c.child_order = Tuple(order)
+    c.width_hidden = hyper.width_hidden; c.depth_representation = hyper.depth_representation
+    c.depth_prediction = hyper.depth_prediction; c.depth_dynamics = hyper.depth_dynamics; c.depth_policy = hyper.depth_policy
+    c.depth_value = hyper.depth_value; c.depth_reward = hyper.depth_reward; c.depth_state_head = hyper.depth_state_head
+    c.hidden_state_size = hyper.hidden_state_size; c.reward_activation_tanh = hyper.reward_activation === tanh
+    c.num_slots = num_slots
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mz_create, LIB), Cint, (Ref{MzConfig}, Cint, Ref{Ptr{Cvoid}}), c, device, ctx)
+    rc == 0 || throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+    e = Engine(ctx[], c, 0, 0)
+    finalizer(x -> ccall((:mz_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), e)
+    return e
+end
+
+# ---- networks: init_representation / init_prediction / init_dynamics (src/Learning.jl:87,100,118) ----------------
+"Flatten a Flux Chain of Dense layers into the blob order of the ABI: per Dense `vec(W)` (column-major (out,in)) then `b`."
+flux_blob(model) = reduce(vcat, [vec(Float32.(p)) for p in Flux.params(model)])
+set_weights!(e::Engine, net::Integer, blob::Vector{Float32}) =
+    check(e, ccall((:mz_set_weights, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Int64), e.ctx, net, blob, length(blob)))
+function get_weights(e::Engine, net::Integer=3)
+    n = ccall((:mz_num_params, LIB), Cint, (Ref{MzConfig}, Cint), e.cfg, net)
+    blob = Vector{Float32}(undef, n)
+    check(e, ccall((:mz_get_weights, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Int64), e.ctx, net, blob, n))
+    return blob
+end
+"NNs = (representation=…, prediction=…, dynamics=…): callables with the shapes of the Flux chains, batched on the GPU."
+function init_networks(e::Engine; seed=e.cfg.seed)
+    check(e, ccall((:mz_init_weights, LIB), Cint, (Ptr{Cvoid}, UInt64), e.ctx, seed))
+    hs, A = Int(e.cfg.hidden_state_size), Int(e.cfg.A)
+    representation = x -> (B = size(x)[end]; h = Matrix{Float32}(undef, hs, B);
+        check(e, ccall((:mz_representation, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}), e.ctx, B, x, h)); h)
+    prediction = h -> (B = size(h)[end]; v = Matrix{Float32}(undef, 1, B); p = Matrix{Float32}(undef, A, B);
+        check(e, ccall((:mz_prediction, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), e.ctx, B, h, v, p)); (v, p))
+    dynamics = sa -> (B = size(sa)[end]; h = Matrix{Float32}(undef, hs, B); r = Matrix{Float32}(undef, 1, B);
+        check(e, ccall((:mz_dynamics, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}), e.ctx, B, sa, h, r)); (h, r))
+    return (representation=representation, prediction=prediction, dynamics=dynamics)
+end
+
+# ---- run_mcts (src/SelfPlay.jl:230) ----------------------------------------------------------------------
+struct Node                    # what callers read from the returned root (SelfPlay.jl:62-70, 115-122, 293-306)
+    visit_counts::Vector{Int32}
+    priors::Vector{Float32}
+    value::Float32
+    legal_actions::Vector{Int}
+end
+legal_mask(actions) = UInt32(reduce(|, (1 << (a - 1) for a in actions)))
+function run_mcts(e::Engine, observation::Array{Float32,3}, legal_actions::Vector{Int}, to_play::Int, exploration::Bool; game_id=0, move_idx=1)::Node
+    @assert !isempty(legal_actions) "Legal actions should not be an empty array. Got $(legal_actions)"
+    A = Int(e.cfg.A); vc = zeros(Int32, A); rv = zeros(Float32, 1); pri = zeros(Float32, A)
+    check(e, ccall((:mz_run_mcts, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Float32}, Ptr{UInt32}, Ptr{Int32}, Cint, Ptr{UInt64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+        e.ctx, 1, observation, UInt32[legal_mask(legal_actions)], Int32[to_play], exploration, UInt64[game_id], Int32[move_idx], vc, rv, pri))
+    return Node(vc, pri, rv[1], legal_actions)
+end
+function select_action(e::Engine, node::Node, temperature::Float32; game_id=0, move_idx=1)::Int
+    act = zeros(Int32, 1)
+    check(e, ccall((:mz_select_action, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{UInt32}, Cfloat, Ptr{UInt64}, Ptr{Int32}, Ptr{Int32}),
+        e.ctx, 1, node.visit_counts, UInt32[legal_mask(node.legal_actions)], temperature, UInt64[game_id], Int32[move_idx], act))
+    return act[1]
+end
+
+# ---- self_play! / play_game / save_game (src/SelfPlay.jl:330-419, src/ReplayBuffer.jl:133-161) -----------------
+visit_softmax_temperature_fn(trained_steps::Int)::Float32 = trained_steps < 500e3 ? 1.0 : trained_steps < 750e3 ? 0.5 : 0.25
+"Plays `n_games` games on the GPU's game slots and save_game()s each into the device replay buffer."
+function self_play!(e::Engine, n_games::Integer; temperature=visit_softmax_temperature_fn(e.training_step))
+    sims = Ref{Int64}(0); moves = Ref{Int64}(0)
+    check(e, ccall((:mz_self_play, LIB), Cint, (Ptr{Cvoid}, UInt64, Int64, Cfloat, Ref{Int64}, Ref{Int64}), e.ctx, e.next_game, n_games, temperature, sims, moves))
+    e.next_game += n_games
+    return sims[], moves[]
+end
+"GameHistory for replay key `key` (fields and shapes of src/Constructors.jl:6-16)."
+function history(e::Engine, key::Integer, GameHistory)
+    Tm = Int(e.cfg.max_moves) + 1; A = Int(e.cfg.A); W, H, C = Int(e.cfg.W), Int(e.cfg.H), Int(e.cfg.C)
+    gid = zeros(Int64, 1); T = zeros(Int32, 1); obs = zeros(Float32, W, H, C, Tm); act = zeros(Int32, Tm); rew = zeros(Float32, Tm)
+    tp = zeros(Int32, Tm); cv = zeros(Float32, A, Tm); rv = zeros(Float32, Tm)
+    check(e, ccall((:mz_history_export, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+        e.ctx, key, 1, gid, T, obs, act, rew, tp, cv, rv))
+    t = T[1]
+    return GameHistory(obs[:, :, :, 1:t], Int.(act[1:t]), rew[1:t], Int.(tp[1:t]), cv[:, 1:t], rv[1:t], nothing, nothing, nothing)
+end
+function play_game(e::Engine, temperature, render::Bool, opponent::String, muzero_player::Int, GameHistory)
+    opponent == "self" || error("only opponent == \"self\" is on the accelerated path")
+    self_play!(e, 1; temperature=Float32(temperature))
+    n = Ref{Int64}(0); k = Ref{Int64}(0); s = Ref{Int64}(0)
+    check(e, ccall((:mz_replay_info, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}), e.ctx, n, k, s))
+    return history(e, k[] + n[] - 1, GameHistory)
+end
+
+# ---- get_batch (src/ReplayBuffer.jl:188-217) --------------------------------------------------------------------
+function get_batch(e::Engine; step=e.training_step + 1)
+    B = Int(e.cfg.batch_size); K1 = Int(e.cfg.num_unroll_steps) + 1; A = Int(e.cfg.A)
+    planes = Int(e.cfg.C) * (Int(e.cfg.stacked_observations) + 1) + Int(e.cfg.stacked_observations)
+    index = zeros(Int32, 2, B); obs = zeros(Float32, Int(e.cfg.W), Int(e.cfg.H), planes, B)
+    actions = zeros(Float32, K1, B); values = zeros(Float32, K1, B); rewards = zeros(Float32, K1, B)
+    policies = zeros(Float32, A, K1, B); gscale = zeros(Float32, B)
+    check(e, ccall((:mz_get_batch, LIB), Cint,
+        (Ptr{Cvoid}, UInt64, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+        e.ctx, step, index, obs, actions, values, rewards, policies, gscale))
+    index_batch = [(Int(index[1, b]), Float32(index[2, b])) for b in 1:B]
+    return index_batch, (obs, actions, values, rewards, policies, nothing, gscale)
+end
+
+# ---- learning! (src/Learning.jl:306-438) ------------------------------------------------------------------------
+"`steps` iterations of get_batch -> unroll -> loss -> gradients -> ADAM(Cos schedule); returns the last three losses."
+function learning!(e::Engine, steps::Integer; grad_mode::Integer=0)
+    losses = zeros(Float32, 3)
+    for _ in 1:steps
+        e.training_step += 1
+        check(e, ccall((:mz_learn_step, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Float32}), e.ctx, e.training_step, grad_mode, losses))
+    end
+    return (l_representation=losses[1], l_prediction=losses[2], l_dynamics=losses[3])
+end
+
+end # module
