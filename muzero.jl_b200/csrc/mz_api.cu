@@ -9,6 +9,7 @@
 #include <vector>
 #include "mz_host.h"
 #include "mz_learner.cuh"
+#include "mz_kernels_tc.cuh"
 
 namespace {
 
@@ -59,6 +60,7 @@ struct mz_ctx {
     std::string err;
     size_t smem_bytes = 0; int sm_count = 0;
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
+    unsigned char *d_w_tc = nullptr; float *d_bias_tc = nullptr; size_t smem_bytes_tc = 0;   // tensor-core weight image
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
     void *d_trees = nullptr;
     mz_slots slots{}; mz_ring ring{};
@@ -129,6 +131,13 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
     std::vector<float> dev((size_t)c->M.P.total_floats);
     mzh::pack_weights(c->M.P, src.data(), dev.data());
     MZ_CUDA(c, cudaMemcpyAsync(c->d_w, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (c->d_w_tc) {   // bf16 pre-swizzled A-operand image + fp32 biases for the tcgen05 path
+        std::vector<uint16_t> image; std::vector<float> bias;
+        mzh::pack_weights_tc(c->M.P, src.data(), image, bias);
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_w_tc, image.data(), image.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_tc, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
@@ -226,7 +235,8 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     c->cfg = *cfg; c->device = device;
     if (const char *e = mzh::build_model(*cfg, c->M)) { int r = fail(nullptr, MZ_E_ARG, "%s", e); delete c; return r; }
     if (cfg->replay_buffer_size < cfg->num_slots) { int r = fail(nullptr, MZ_E_ARG, "replay_buffer_size must be >= num_slots"); delete c; return r; }
-    if (cfg->nn_mode != MZ_NN_FP32_EXACT) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "nn_mode %d not available in this build", cfg->nn_mode); delete c; return r; }
+    if (cfg->nn_mode != MZ_NN_FP32_EXACT && cfg->nn_mode != MZ_NN_BF16_TC) { int r = fail(nullptr, MZ_E_ARG, "unknown nn_mode %d", cfg->nn_mode); delete c; return r; }
+    if (cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }
@@ -242,6 +252,19 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    if (c->M.P.tc_ok) {
+        c->smem_bytes_tc = mz_tc_smem_bytes(P.tc_net_off[3], P.tc_bias_floats, P.hidden_pad, P.S);
+        if (c->smem_bytes_tc <= (size_t)prop.sharedMemPerBlockOptin) {
+            MZ_CREATE(cudaFuncSetAttribute(mz_k_search_tc<MZ_MODE_API>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
+            MZ_CREATE(cudaFuncSetAttribute(mz_k_search_tc<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
+            MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
+            MZ_CREATE(cudaMalloc((void **)&c->d_w_tc, (size_t)P.tc_net_off[3] + 8192));
+            MZ_CREATE(dmalloc(&c->d_bias_tc, (size_t)P.tc_bias_floats));
+        } else if (cfg->nn_mode == MZ_NN_BF16_TC) {
+            int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes_tc, (size_t)prop.sharedMemPerBlockOptin);
+            mz_destroy(c); return r;
+        }
+    }
     MZ_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
     const size_t nf = (size_t)P.total_floats;
     MZ_CREATE(dmalloc(&c->d_w, nf)); MZ_CREATE(dmalloc(&c->d_m, nf)); MZ_CREATE(dmalloc(&c->d_v, nf)); MZ_CREATE(dmalloc(&c->d_grad, nf));
@@ -280,7 +303,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    void *ptrs[] = {c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -353,7 +376,10 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
     MZ_TRY(h2d<float>(c, c->scratch[1], nullptr, (size_t)B * n1, &d_o1));
     MZ_TRY(h2d<float>(c, c->scratch[2], nullptr, (size_t)B * (n2 ? n2 : 1), &d_o2));
     mz_nn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.net = net; a.in = d_in; a.out1 = d_o1; a.out2 = d_o2;
-    { launch_scope ls(c, 5); mz_k_nn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+        mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
+        launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
+    } else { launch_scope ls(c, 5); mz_k_nn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
     MZ_CUDA(c, cudaGetLastError());
     MZ_TRY(d2h(c, out1, d_o1, (size_t)B * n1));
     if (n2 && out2) MZ_TRY(d2h(c, out2, d_o2, (size_t)B * n2));
@@ -448,7 +474,10 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = m; a.max_dim = c->M.max_dim;
         a.max_layer_floats = c->M.max_layer_floats; a.exploration = exploration; a.stacked = d_st; a.legal = d_legal; a.to_play = d_tp; a.game_id = d_gid;
         a.move_idx = d_mv; a.visit_counts = d_vc; a.root_value = d_rv; a.root_priors = d_pri; a.stats = nullptr;
-        { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+            mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
+            launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
+        } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         MZ_CUDA(c, cudaGetLastError());
         MZ_TRY(d2h(c, visit_counts + (size_t)off * P.A, d_vc, (size_t)m * P.A)); MZ_TRY(d2h(c, root_value + off, d_rv, (size_t)m));
         if (root_priors) MZ_TRY(d2h(c, root_priors + (size_t)off * P.A, d_pri, (size_t)m * P.A));
@@ -498,7 +527,10 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         if (active == 0) break;
         if (guard > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         total_moves += active;
-        { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+            mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
+            launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
+        } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
     }
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

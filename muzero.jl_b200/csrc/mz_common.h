@@ -153,6 +153,13 @@ struct mz_params {
     int32_t n_layers, total_floats, n_params, pad2_;
     mz_net nets[3];
     mz_layer layers[MZ_MAX_LAYERS];
+    // tensor-core (MZ_NN_BF16_TC) weight image: per layer a [rows8(out) x 64] bf16 tile in the UMMA K-major
+    // SWIZZLE_128B shared-memory layout, pre-swizzled on the host so one bulk copy per network stages it
+    int32_t tc_a_off[MZ_MAX_LAYERS];   // byte offset of the layer's A tile inside the image (1024-aligned)
+    int32_t tc_ksteps[MZ_MAX_LAYERS];  // ceil(in / 16) tcgen05.mma instructions per layer
+    int32_t tc_net_off[4];             // byte offset of each network's block; [3] = total image bytes
+    int32_t tc_bias_off[MZ_MAX_LAYERS];// float offset of the layer's bias inside the bias block
+    int32_t tc_bias_floats, tc_ok, tc_pad_[2];
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -147,6 +147,22 @@ inline const char *build_model(const mz_config &c, model &M) {
     add_layer(P, w, 1, c.reward_activation_tanh ? MZ_ACT_TANH : MZ_ACT_ID, src, dev);
     P.nets[2].n_trunk = c.depth_dynamics + 1; P.nets[2].n_h1 = c.depth_state_head + 1; P.nets[2].n_h2 = c.depth_reward + 1;
     P.n_params = src; P.total_floats = dev;
+    // tensor-core image geometry: usable when every layer has in <= 64 and out <= 64 (one K block, one M=64 tile)
+    P.tc_ok = 1;
+    {
+        int off = 0, boff = 0;
+        for (int n = 0; n < 3; n++) {
+            P.tc_net_off[n] = off;
+            int first = P.nets[n].first, cnt = P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2;
+            for (int i = first; i < first + cnt; i++) {
+                const mz_layer &l = P.layers[i];
+                if (l.in > 64 || l.out > 64) P.tc_ok = 0;
+                P.tc_a_off[i] = off; P.tc_ksteps[i] = (l.in + 15) / 16; P.tc_bias_off[i] = boff;
+                off += ((l.out + 7) / 8) * 1024; boff += 64;
+            }
+        }
+        P.tc_net_off[3] = off; P.tc_bias_floats = boff;
+    }
     M.max_dim = 4; M.max_layer_floats = 0;
     for (int i = 0; i < P.n_layers; i++) {
         if (P.layers[i].in > M.max_dim) M.max_dim = P.layers[i].in;
@@ -185,6 +201,28 @@ inline void unpack_weights(const mz_params &P, const float *dev, float *src) {
         const mz_layer &l = P.layers[i];
         for (int k = 0; k < l.in; k++) for (int o = 0; o < l.out; o++) src[l.src_w_off + k * l.out + o] = dev[l.w_off + k * l.out_pad + o];
         for (int o = 0; o < l.out; o++) src[l.src_b_off + o] = dev[l.b_off + o];
+    }
+}
+
+// float -> bfloat16, round to nearest even (the same rounding as __float2bfloat16_rn on the device)
+inline uint16_t f2bf16(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+// Byte offset of element (row r, k) inside a K-major SWIZZLE_128B tile with 64 bf16 (128 B) per row: 8-row groups of
+// 1024 B, 16-byte chunk index XOR-ed with the row index inside the group (Swizzle<3,4,3>).
+inline int tc_tile_offset(int r, int k) { return (r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 3) ^ (r & 7)) & 7) << 4) + (k & 7) * 2; }
+// reference-order blob -> bf16 A-operand image (rows = output features, K = input features) + fp32 bias block
+inline void pack_weights_tc(const mz_params &P, const float *src, std::vector<uint16_t> &image, std::vector<float> &bias) {
+    image.assign((size_t)P.tc_net_off[3] / 2 + 4096, 0); bias.assign((size_t)P.tc_bias_floats, 0.0f);
+    for (int i = 0; i < P.n_layers; i++) {
+        const mz_layer &l = P.layers[i];
+        for (int o = 0; o < l.out; o++) {
+            for (int k = 0; k < l.in; k++) image[(size_t)(P.tc_a_off[i] + tc_tile_offset(o, k)) / 2] = f2bf16(src[l.src_w_off + k * l.out + o]);
+            bias[(size_t)P.tc_bias_off[i] + o] = src[l.src_b_off + o];
+        }
     }
 }
 

@@ -233,12 +233,30 @@ void mzo_init_weights(const mzo_config *c, uint64_t seed, float *blob) {
     }
 }
 
+/* bf16 emulation for checking the tensor-core path (MZ_NN_BF16_TC): when enabled, every Dense rounds its input
+ * vector and its weights to bfloat16 (round to nearest even) and accumulates in Float32; biases, activations and the
+ * final outputs stay Float32.  Off by default (the reference computes in Float32). */
+static int g_bf16 = 0;
+void mzo_set_bf16(int on) { g_bf16 = on; }
+static inline float bf16_round(float f) {
+    uint32_t u = f2bits(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return f;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return bits2f(u & 0xffff0000u);
+}
 /* Dense (Flux 0.12.4, un-vendored): y = act.(W*x .+ b).  Contract: sequential-k fmaf, then + b. */
 static void dense(const float *blob, const layer_t *l, const float *x, float *y) {
     float acc[256];
     const float *W = blob + l->w_off, *b = blob + l->b_off;
     int out = l->out;
     for (int o = 0; o < out; o++) acc[o] = 0.0f;
+    if (g_bf16) {
+        for (int k = 0; k < l->in; k++) {
+            float xk = bf16_round(x[k]);
+            const float *wk = W + (size_t)k * out;
+            for (int o = 0; o < out; o++) acc[o] = fmaf(bf16_round(wk[o]), xk, acc[o]);
+        }
+    } else
     for (int k = 0; k < l->in; k++) {
         float xk = x[k];
         const float *wk = W + (size_t)k * out;

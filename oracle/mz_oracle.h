@@ -72,6 +72,9 @@ int  mzo_num_params(const mzo_config *cfg, int net); /* net: 0 repr, 1 pred, 2 d
 void mzo_init_weights(const mzo_config *cfg, uint64_t seed, float *blob); /* glorot_uniform, bias 0 */
 void mzo_julia_dict_order(int A, int32_t *order);    /* Dict{Int,...} iteration order of 1..A */
 
+/* bf16-operand emulation of the networks (checks the tensor-core path); 0 = exact Float32 (default) */
+void mzo_set_bf16(int on);
+
 /* math contract (exported so tests can pin them) */
 float mzo_expf(float x);
 float mzo_logf(float x);

@@ -75,6 +75,7 @@ def lib():
     L.mzo_julia_dict_order.argtypes = [C.c_int, i32p]
     for name in ("mzo_expf", "mzo_logf", "mzo_tanhf"):
         getattr(L, name).argtypes = [C.c_float]; getattr(L, name).restype = C.c_float
+    L.mzo_set_bf16.argtypes = [C.c_int]
     L.mzo_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p]
     envp = C.POINTER(Env)
     L.mzo_env_reset.argtypes = [cfgp, envp]
@@ -100,6 +101,11 @@ def lib():
     L.mzo_learn_step.argtypes = [cfgp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int] + [f32p] * 7
     _lib = L
     return L
+
+
+def set_bf16(on):
+    """bf16-operand emulation of the networks (for checking the tensor-core path); off = the reference's Float32."""
+    lib().mzo_set_bf16(int(on))
 
 
 def _p(a, t=C.c_float):

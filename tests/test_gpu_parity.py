@@ -244,3 +244,73 @@ def test_learner_large_batch_properties(capi):
     opv, opr, opp, ol = O.learn_forward(common.oracle_config(ctx.cfg), blob, {k: v[:64] for k, v in b.items()})
     assert np.array_equal(opv, pv[:64]) and np.array_equal(opp, pp[:64])
     ctx.close()
+
+
+# ---- tensor-core network path (MZ_NN_BF16_TC): tolerance + agreement, not bit-exactness -----------------------------
+TC_ATOL = 5e-3          # bf16 operands: one bf16 ulp of an O(1) activation is 4e-3
+
+
+def test_tc_networks_within_bf16_tolerance(capi):
+    ctx, ocfg = make_ctx(capi, nn_mode=capi.NN_BF16_TC)
+    ctx.init_weights(1337); blob = ctx.get_weights()
+    rng = np.random.default_rng(2)
+    st, legal, tp = common.random_stacked(ocfg, 70, seed=9)
+    O.set_bf16(True)
+    try:
+        h = ctx.representation(st)
+        oh = np.stack([O.representation(ocfg, blob, x) for x in st])
+        assert np.allclose(h, oh, atol=TC_ATOL) and np.median(np.abs(h - oh)) < 1e-5
+        v, p = ctx.prediction(oh)
+        ov, op = zip(*[O.prediction(ocfg, blob, x) for x in oh])
+        assert np.allclose(v, np.array(ov), atol=TC_ATOL) and np.allclose(p, np.stack(op), atol=TC_ATOL)
+        assert np.median(np.abs(p - np.stack(op))) < 1e-5
+        sa = np.concatenate([oh * 2, np.full((70, 9), np.float32(5.0 / 9.0), np.float32)], axis=1)
+        nh, r = ctx.dynamics(sa)
+        onh, orr = zip(*[O.dynamics(ocfg, blob, x) for x in sa])
+        assert np.allclose(nh, np.stack(onh), atol=TC_ATOL) and np.allclose(r, np.array(orr), atol=TC_ATOL)
+        assert np.median(np.abs(nh - np.stack(onh))) < 1e-5
+    finally:
+        O.set_bf16(False)
+    # against the reference's Float32 arithmetic: bf16 tolerance
+    oh32 = np.stack([O.representation(ocfg, blob, x) for x in st])
+    assert np.allclose(h, oh32, atol=5e-2)
+    ctx.close()
+
+
+def test_tc_run_mcts_agreement(capi):
+    n, S = 256, 50
+    ctx, ocfg = make_ctx(capi, num_iters=S, exploration_eps=0.0, nn_mode=capi.NN_BF16_TC)
+    ctx.init_weights(7); blob = ctx.get_weights()
+    st, legal, tp = common.random_stacked(ocfg, n, seed=77)
+    game = np.arange(n, dtype=np.uint64) + 100; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    assert np.all(vc.sum(1) == S) and np.all((vc > 0) <= ((legal[:, None] >> np.arange(9)) & 1).astype(bool))
+    exact = [O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i])) for i in range(n)]
+    O.set_bf16(True)
+    try:
+        emu = [O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i])) for i in range(n)]
+    finally:
+        O.set_bf16(False)
+    same_emu = np.mean([vc[i].tolist() == emu[i][0].tolist() for i in range(n)])
+    same_exact = np.mean([vc[i].tolist() == exact[i][0].tolist() for i in range(n)])
+    best_exact = np.mean([int(np.argmax(vc[i])) == int(np.argmax(exact[i][0])) for i in range(n)])
+    print("TC visit counts identical to bf16-emulating oracle: %.3f, to the Float32 oracle: %.3f, same most-visited action: %.3f"
+          % (same_emu, same_exact, best_exact))
+    assert same_emu >= 0.95        # same arithmetic up to accumulation order
+    assert best_exact >= 0.85      # bf16 vs Float32 networks
+    assert np.allclose(pri, np.stack([e[2] for e in emu]), atol=TC_ATOL)
+    assert np.allclose(rv, np.array([e[1] for e in emu]), atol=5e-2)
+    ctx.close()
+
+
+def test_tc_self_play_is_well_formed(capi):
+    ctx, ocfg = make_ctx(capi, nn_mode=capi.NN_BF16_TC, num_slots=128, replay_buffer_size=512)
+    ctx.init_weights(3)
+    sims, moves = ctx.self_play(0, 300, 1.0)
+    h = ctx.history_export()
+    assert sims == moves * ctx.cfg.num_iters and sorted(h["game_id"].tolist()) == list(range(300))
+    assert h["T"].min() >= 6 and h["T"].max() <= 9
+    for j in range(300):
+        T = h["T"][j]
+        assert np.allclose(h["child_visits"][j, :T].sum(1), 1.0, atol=1e-6) and np.all(h["rewards"][j, :T - 1] == 0)
+    ctx.close()
