@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-learner", action="store_true")
+    ap.add_argument("--nn", default="fp32", choices=["fp32", "tc"],
+                    help="network arithmetic of the headline number: fp32 = exact (bit-identical to the oracle), tc = bf16 tcgen05")
+    ap.add_argument("--no-tc-extra", action="store_true", help="skip the additional tensor-core measurement in fp32 mode")
     return ap.parse_args()
 
 
@@ -150,7 +153,8 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     G, S = a.games, a.sims
-    cfg = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G))
+    nn_mode = capi.NN_BF16_TC if a.nn == "tc" else capi.NN_FP32_EXACT
+    cfg = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=nn_mode)
     stream = torch.cuda.Stream()
     ctx = capi.Context(cfg, device=local, stream=stream.cuda_stream)
     ctx.init_weights(1337)
@@ -199,6 +203,25 @@ def run_b200(a):
             e2e_ms += e0.elapsed_time(e1); e2e_sims += s
             d2h = sum(v.nbytes for v in hist.values())
         barrier()
+        # ---- the same waves with the networks on the tcgen05 tensor cores (bf16 operands): reported beside the headline ----
+        tc_extra = None
+        if a.nn == "fp32" and not a.no_tc_extra:
+            cfg_tc = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=capi.NN_BF16_TC)
+            ctx_tc = capi.Context(cfg_tc, device=local, stream=stream.cuda_stream)
+            ctx_tc.set_weights(blob)
+            for i in range(a.warmup):
+                ctx_tc.self_play(game_base + i * G, G, 1.0)
+            tms, tsims = 0.0, 0
+            for i in range(a.steps):
+                flush.zero_(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                s_, _ = ctx_tc.self_play(game_base + (a.warmup + i) * G, G, 1.0)
+                e1.record(stream); e1.synchronize()
+                tms += e0.elapsed_time(e1); tsims += s_
+            tc_extra = (tms, tsims)
+            ctx_tc.close()
+        barrier()
         # ---- learner: samples/s at the reference batch (32) ----
         learner = None
         if not a.no_learner:
@@ -217,12 +240,12 @@ def run_b200(a):
             learner = {"batch_per_gpu": cfg.batch_size, "grad_mode": "reference_l2", "ms_per_step": lms / a.learner_steps,
                        "losses": [float(x) for x in losses]}
 
-    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0)], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([sims_total, e2e_sims, launches], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, learn_ms_max = [float(x) for x in t.cpu()]
-    sims_all, e2e_sims_all, launches_all = [float(x) for x in cnt.cpu()]
+    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max = [float(x) for x in t.cpu()]
+    sims_all, e2e_sims_all, launches_all, tc_sims_all = [float(x) for x in cnt.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -238,19 +261,25 @@ def run_b200(a):
         achieved = bytes_per_sim * sims_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
         out = {
             "metric": METRIC, "value": sims_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "games_per_gpu": G, "simulations_per_move": S, "nn_mode": "fp32_exact", "parallelism": "dp%d" % world,
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if a.nn == "tc" else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "games_per_gpu": G, "simulations_per_move": S,
+                       "nn_mode": "bf16_tcgen05" if a.nn == "tc" else "fp32_exact", "parallelism": "dp%d" % world,
                        "l2": "L2 flushed (384 MiB memset) between timed iterations", "mean_legal_actions": Lm, "mean_select_depth": d,
                        "moves_per_step": moves_total / a.steps},
             "e2e": {"value": e2e_sims_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "mz_k_search_tc<MODE_SLOTS>" if a.nn == "tc" else "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_simulation": bytes_per_sim, "simulations_per_launch": sims_per_launch,
                          "avg_launch_ms": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms if ms > 0 else None,
                          "nn_flops_per_simulation": 111232, "nn_tflops_achieved": 111232 * sims_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0},
         }
+        if tc_extra:
+            out["tensor_core"] = {"value": tc_sims_all / (tc_ms_max * 1e-3), "unit": UNIT, "ms_per_step": tc_ms_max / a.steps, "dtype": "bf16",
+                                  "kernel": "mz_k_search_tc<MODE_SLOTS>",
+                                  "note": "same waves with the networks on tcgen05 (bf16 operands, fp32 accumulate); results agree with the "
+                                          "oracle to bf16 tolerance, not bit-exactly, so the headline value is the exact-fp32 path"}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
             out["learner"] = learner

@@ -65,6 +65,8 @@ __device__ __forceinline__ void mz_nn_issue(const mz_nn_pipe &s, const mz_params
     mz_bulk_g2s(s.wbuf[slot], s.wglob + L.w_off, bytes, &s.mbar[slot]);
 }
 
+__device__ __noinline__ float mz_tanhf_ni(float x) { return mz_tanhf(x); }   // keeps the (rare) tanh out of the hot epilogue code
+
 // y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row].
 // One copy of this code in the binary (noinline): every layer of every network goes through it.
 __device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
@@ -99,7 +101,7 @@ __device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_
             float4 r;
             r.x = acc[0][j] + bj[j]; r.y = acc[1][j] + bj[j]; r.z = acc[2][j] + bj[j]; r.w = acc[3][j] + bj[j];
             if (act == MZ_ACT_RELU) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
-            else if (act == MZ_ACT_TANH) { r.x = mz_tanhf(r.x); r.y = mz_tanhf(r.y); r.z = mz_tanhf(r.z); r.w = mz_tanhf(r.w); }
+            else if (act == MZ_ACT_TANH) { r.x = mz_tanhf_ni(r.x); r.y = mz_tanhf_ni(r.y); r.z = mz_tanhf_ni(r.z); r.w = mz_tanhf_ni(r.w); }
             mz_sts128(dst_smem + (uint32_t)((4 * g + j) * MZ_ROWS * 4) + (uint32_t)rg * 16u, r);
         }
     }

@@ -63,6 +63,8 @@ __device__ __forceinline__ void mz_tc_store_bf16(uint32_t tile, int n, int k, fl
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(tile + mz_tc_tile_offset(n, k)), "h"(b) : "memory");
 }
 
+__device__ __noinline__ float mz_tanhf_noinline(float x) { return mz_tanhf(x); }
+
 struct mz_tc_pipe {             // one per group
     uint32_t w_base;            // shared address of the weight image
     const float *bias;          // shared fp32 bias block
@@ -90,18 +92,27 @@ __device__ __noinline__ void mz_tc_layer(mz_tc_pipe &s, const mz_params &P, int 
     mz_tc_ld32(s.tmem_d + ((uint32_t)(32 * w) << 16), v);       // M = 64: rows 16w..16w+15 live in lanes 32w..32w+15
     const int m = 16 * w + t;
     if (t < 16 && m < L.out) {
+        // compact epilogue (one code path for relu / identity; tanh -- only the 1-wide value / reward outputs -- goes through a
+        // non-inlined call) so both groups' epilogues stay resident in the instruction cache
         const float b = s.bias[P.tc_bias_off[layer] + m];
-        if (dst_tile) {
+        const float lo = L.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
+        float x[32];
 #pragma unroll
-            for (int n = 0; n < 32; n++) mz_tc_store_bf16(dst_tile, n, m, mz_activate(__uint_as_float(v[n]) + b, L.act));
+        for (int n = 0; n < 32; n++) x[n] = fmaxf(__uint_as_float(v[n]) + b, lo);
+        if (L.act == MZ_ACT_TANH) {
+#pragma unroll
+            for (int n = 0; n < 32; n++) x[n] = mz_tanhf_noinline(x[n]);
+        }
+        if (dst_tile) {
+            const uint32_t colbase = dst_tile + (uint32_t)((m & 7) * 2), chunk = (uint32_t)(m >> 3);
+#pragma unroll
+            for (int n = 0; n < 32; n++) {
+                unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(x[n]));
+                asm volatile("st.shared.b16 [%0], %1;" ::"r"(colbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + ((chunk ^ (uint32_t)(n & 7)) << 4)), "h"(h) : "memory");
+            }
         } else {
 #pragma unroll
-            for (int n = 0; n < 32; n += 4) {
-                float4 r;
-                r.x = mz_activate(__uint_as_float(v[n]) + b, L.act); r.y = mz_activate(__uint_as_float(v[n + 1]) + b, L.act);
-                r.z = mz_activate(__uint_as_float(v[n + 2]) + b, L.act); r.w = mz_activate(__uint_as_float(v[n + 3]) + b, L.act);
-                *reinterpret_cast<float4 *>(dst_f32 + m * MZ_ROWS + n) = r;
-            }
+            for (int n = 0; n < 32; n += 4) *reinterpret_cast<float4 *>(dst_f32 + m * MZ_ROWS + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
         }
     }
     mz_fence_proxy_async();
