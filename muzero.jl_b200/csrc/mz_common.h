@@ -263,34 +263,35 @@ MZ_HD float mz_stacked_value(const mz_params &P, const uint64_t *h1, const uint6
 // ------------------------------------------------------------------------------------------------
 // Flat per-tree node pool.  Q7 (every expanded node gets children for the ROOT's legal set) makes the
 // pool regular: expansion e (0 = root, 1..S = simulations) owns the child block [1+e*A, 1+(e+1)*A) and
-// the hidden state slot e.
-//   nodeA[n] = {visit_count (int bits), value_sum, prior, reward}            (16 B)
-//   nodeB[n] = parent (16 bits) | (expansion id + 1) (10 bits) | doublings (6 bits)   (4 B)
-//   hidden[e][hidden_pad]
-// `doublings` implements make_state_action's in-place `state .*= 2` (Q6) as a scale on read.
+// the hidden state slot e.  One 16-byte record per node:
+//   node[n] = { x = visit_count (bits 0-11) | expansion id + 1 (bits 12-23) | doublings (bits 24-29),
+//               y = value_sum, z = prior, w = reward }
+// Everything the next selection level needs about a child (is it expanded, where are ITS children) travels with
+// the record that was loaded to score it, so a selection level costs one dependent memory round trip.
+// `doublings` implements make_state_action's in-place `state .*= 2` (Q6) as an exact power-of-two scale on read.
 // ------------------------------------------------------------------------------------------------
 struct alignas(16) mz_f4 { float x, y, z, w; };
 struct mz_tree {
     mz_f4 *A;
-    uint32_t *B;
     float *hidden;
 };
 MZ_HD mz_tree mz_tree_at(const mz_params &P, void *pool, int64_t tree) {
     char *base = (char *)pool + tree * (int64_t)P.tree_stride_bytes;
-    mz_tree t; t.A = (mz_f4 *)base; t.B = (uint32_t *)(base + P.nodeB_off_bytes); t.hidden = (float *)(base + P.hidden_off_bytes);
+    mz_tree t; t.A = (mz_f4 *)base; t.hidden = (float *)(base + P.hidden_off_bytes);
     return t;
 }
-MZ_HD uint32_t mz_nodeB_pack(int parent, int exp_id, int dbl) { return (uint32_t)parent | ((uint32_t)(exp_id + 1) << 16) | ((uint32_t)dbl << 26); }
-MZ_HD int mz_nodeB_parent(uint32_t b) { return (int)(b & 0xffffu); }
-MZ_HD int mz_nodeB_exp(uint32_t b) { return (int)((b >> 16) & 0x3ffu) - 1; }
-MZ_HD int mz_nodeB_dbl(uint32_t b) { return (int)(b >> 26); }
+MZ_HD uint32_t mz_nx_pack(int visit, int exp_id, int dbl) { return (uint32_t)visit | ((uint32_t)(exp_id + 1) << 12) | ((uint32_t)dbl << 24); }
+MZ_HD int mz_nx_visit(uint32_t x) { return (int)(x & 0xfffu); }
+MZ_HD int mz_nx_exp(uint32_t x) { return (int)((x >> 12) & 0xfffu) - 1; }
+MZ_HD int mz_nx_dbl(uint32_t x) { return (int)(x >> 24); }
+MZ_HD uint32_t mz_node_x(const mz_f4 &r) { return mz_f2bits(r.x); }
 
 struct mz_minmax { float mn, mx; };
 
 // ucb_score (src/SelfPlay.jl:171-184): Float64 exploration term from integer-only tables
 // (pbc0[N] = log2((N+base+1)/base) + init, sqrtN[N] = sqrt(N)), Float32 value term, Float32 result.
 MZ_HD float mz_ucb(const mz_params &P, const double *pbc0, const double *sqrtN, int N, mz_f4 child, mz_minmax mm) {
-    int n = (int)mz_f2bits(child.x);
+    int n = mz_nx_visit(mz_f2bits(child.x));
     double pb_c = pbc0[N] * (sqrtN[N] / (double)(n + 1));
     double prior_score = pb_c * (double)child.z;
     if (n > 0) {
@@ -302,17 +303,19 @@ MZ_HD float mz_ucb(const mz_params &P, const double *pbc0, const double *sqrtN, 
     return (float)(prior_score + 0.0);
 }
 
-struct mz_leaf { int node, parent, action, depth; };
+// leaf of a selection: node indices, the leaf's prior (its record is rebuilt by expand), the parent's packed x word
+struct mz_leaf { int node, parent, action, depth; float prior; uint32_t parent_x; };
 
-// select_child loop of run_mcts (src/SelfPlay.jl:157-166, 261-268).
+// select_child loop of run_mcts (src/SelfPlay.jl:157-166, 261-268); records the path (root .. leaf) for the backup.
 MZ_HD mz_leaf mz_tree_select(const mz_params &P, const mz_tree &t, const double *pbc0, const double *sqrtN, uint32_t legal,
-                             mz_minmax mm, uint32_t game, uint32_t move, uint32_t sim) {
-    mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0;
-    int e = mz_nodeB_exp(t.B[0]);
-    while (e >= 0) {
+                             mz_minmax mm, uint32_t game, uint32_t move, uint32_t sim, uint16_t *path) {
+    mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0; L.prior = 0.0f; L.parent_x = 0;
+    uint32_t x = mz_f2bits(t.A[0].x);
+    path[0] = 0;
+    while (mz_nx_exp(x) >= 0) {
         L.depth++;
-        int base = 1 + e * P.A;
-        int N = (int)mz_f2bits(t.A[L.node].x);
+        int base = 1 + mz_nx_exp(x) * P.A;
+        int N = mz_nx_visit(x);
         float best = 0.0f; uint32_t tied = 0;
         for (int j = 0; j < P.A; j++) {
             int a = P.order[j];
@@ -328,9 +331,11 @@ MZ_HD mz_leaf mz_tree_select(const mz_params &P, const mz_tree &t, const double 
         for (int i = 0; i < pick; i++) m &= m - 1;
         int j = 0; while (!((m >> j) & 1u)) j++;
         L.action = P.order[j];
-        L.parent = L.node;
+        L.parent = L.node; L.parent_x = x;
         L.node = base + L.action - 1;
-        e = mz_nodeB_exp(t.B[L.node]);
+        path[L.depth] = (uint16_t)L.node;
+        mz_f4 c = t.A[L.node];
+        x = mz_f2bits(c.x); L.prior = c.z;
     }
     return L;
 }
@@ -345,42 +350,39 @@ MZ_HD void mz_softmax(const float *x, int n, float *y) {
 }
 
 // expand_node! (src/SelfPlay.jl:88-96): second softmax over the legal subset (ascending actions, Q1) of the
-// already-softmaxed policy; children block e; node becomes expanded with reward r.
-MZ_HD void mz_tree_expand(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *policy, float reward) {
+// already-softmaxed policy; children block e; the node (unvisited until the backup, prior `prior`) becomes expanded
+// with reward r.
+MZ_HD void mz_tree_expand(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *policy, float reward, float prior) {
     float sub[MZ_MAX_A], pv[MZ_MAX_A]; int n = 0;
     for (int a = 1; a <= P.A; a++) if ((legal >> (a - 1)) & 1u) sub[n++] = policy[a - 1];
     mz_softmax(sub, n, pv);
     int base = 1 + e * P.A; n = 0;
     for (int a = 1; a <= P.A; a++) {
-        mz_f4 c; c.x = mz_bits2f(0u); c.y = 0.0f; c.w = 0.0f;
+        mz_f4 c; c.x = mz_bits2f(mz_nx_pack(0, -1, 0)); c.y = 0.0f; c.w = 0.0f;
         c.z = ((legal >> (a - 1)) & 1u) ? pv[n++] : 0.0f;
         t.A[base + a - 1] = c;
-        t.B[base + a - 1] = mz_nodeB_pack(node, -1, 0);
     }
-    uint32_t b = t.B[node];
-    t.B[node] = mz_nodeB_pack(mz_nodeB_parent(b), e, 0);
-    mz_f4 me = t.A[node]; me.w = reward; t.A[node] = me;
+    mz_f4 me; me.x = mz_bits2f(mz_nx_pack(0, e, 0)); me.y = 0.0f; me.z = prior; me.w = reward;
+    t.A[node] = me;
 }
 
-// backpropagate! (src/SelfPlay.jl:190-217) walking parent links leaf -> root.  Two players: a node j steps
+// backpropagate! (src/SelfPlay.jl:190-217) over the recorded path, leaf -> root.  Two players: a node j steps
 // above the leaf has node.to_play == to_play iff j is even; includes the dropped-bootstrap bug (Q8).
-MZ_HD void mz_tree_backup(const mz_params &P, const mz_tree &t, int leaf, float value, mz_minmax &mm) {
-    int node = leaf;
-    for (int j = 0;; j++) {
+MZ_HD void mz_tree_backup(const mz_params &P, const mz_tree &t, const uint16_t *path, int depth, float value, mz_minmax &mm) {
+    for (int j = 0; j <= depth; j++) {
+        int node = path[depth - j];
         mz_f4 a = t.A[node];
-        int vc = (int)mz_f2bits(a.x);
+        uint32_t x = mz_f2bits(a.x) + 1u;                                 // visit_count += 1 (low bits of the packed word)
+        int vc = mz_nx_visit(x);
         bool same = (P.P == 1) || ((j % P.P) == 0);
         a.y = same ? a.y + value : a.y - value;
-        vc += 1;
-        a.x = mz_bits2f((uint32_t)vc);
+        a.x = mz_bits2f(x);
         t.A[node] = a;
         float u = a.w + P.discount * (a.y / (float)vc);
         mm.mn = mm.mn < u ? mm.mn : u;                                   // update_tree! :27-31
         mm.mx = mm.mx > u ? mm.mx : u;
         if (P.P == 1) value = a.w + P.discount * value;
         else value = same ? -a.w : a.w + P.discount * value;
-        if (node == 0) break;
-        node = mz_nodeB_parent(t.B[node]);
     }
 }
 

@@ -75,11 +75,11 @@ __device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_
     const int opq = out_pad >> 2;
     const uint32_t wstride = (uint32_t)out_pad * 4u;
     for (int g = (warp << 2) | (lane >> 3); g < opq; g += 16) {
-        float acc[4][4];
+        // packed fp32 FMA (fma.rn.f32x2, sm_100+): two IEEE round-to-nearest FMAs per instruction, so the result is
+        // bit-identical to 16 scalar fmaf per k while the FMA pipe sees half the instructions
+        unsigned long long acc2[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+        for (int i = 0; i < 4; i++) { acc2[i][0] = 0ull; acc2[i][1] = 0ull; }
         uint32_t wa = w_smem + (uint32_t)g * 16u;
         uint32_t xa = src_smem + (uint32_t)rg * 16u;
 #pragma unroll 4
@@ -87,12 +87,23 @@ __device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_
             const float4 wv = mz_lds128(wa);
             const float4 xv = mz_lds128(xa);
             wa += wstride; xa += MZ_ROWS * 4;
-            const float wj[4] = {wv.x, wv.y, wv.z, wv.w};
+            unsigned long long w01, w23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(w01) : "f"(wv.x), "f"(wv.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(w23) : "f"(wv.z), "f"(wv.w));
             const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int i = 0; i < 4; i++) {
+                unsigned long long xx;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(xi[i]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][0]) : "l"(w01), "l"(xx));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][1]) : "l"(w23), "l"(xx));
+            }
+        }
+        float acc[4][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wj[j], xi[i], acc[i][j]);
+        for (int i = 0; i < 4; i++) {
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][0]), "=f"(acc[i][1]) : "l"(acc2[i][0]));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2]), "=f"(acc[i][3]) : "l"(acc2[i][1]));
         }
         const float4 bv = mz_lds128(w_smem + (uint32_t)in * wstride + (uint32_t)g * 16u);
         const float bj[4] = {bv.x, bv.y, bv.z, bv.w};

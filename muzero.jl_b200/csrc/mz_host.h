@@ -54,7 +54,7 @@ inline const char *validate(const mz_config &c) {
     if (c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
     if (c.num_players < 1 || c.num_players > 2) return "1 or 2 players";
     if (c.num_iters < 1 || c.num_iters > 1000) return "num_iters must be in 1..1000";
-    if (1 + (c.num_iters + 1) * c.A > 65535) return "tree too large for 16-bit parent links";
+    if (1 + (c.num_iters + 1) * c.A > 65535) return "tree too large for 16-bit path entries";
     if (c.max_moves < 1 || c.max_moves > 63) return "max_moves must be in 1..63";
     if (c.stacked_observations < 0 || c.stacked_observations > 8) return "stacked_observations out of range";
     if (c.num_unroll_steps < 0 || c.num_unroll_steps > 32 || c.td_steps < 0 || c.td_steps > 64) return "unroll/td steps out of range";
@@ -119,10 +119,10 @@ inline const char *build_model(const mz_config &c, model &M) {
     for (int i = 0; i < 72; i++) P.disc_pow[i] = discount_pow(c.discount, i);
     // tree pool geometry
     P.nodes_per_tree = 1 + (c.num_iters + 1) * c.A;
-    int a_bytes = P.nodes_per_tree * 16, b_bytes = ((P.nodes_per_tree * 4) + 15) & ~15;
+    int a_bytes = P.nodes_per_tree * 16;
     int h_bytes = (c.num_iters + 1) * P.hidden_pad * 4;
-    P.nodeB_off_bytes = a_bytes; P.hidden_off_bytes = a_bytes + b_bytes;
-    P.tree_stride_bytes = (a_bytes + b_bytes + h_bytes + 127) & ~127;
+    P.nodeB_off_bytes = 0; P.hidden_off_bytes = a_bytes;
+    P.tree_stride_bytes = (a_bytes + h_bytes + 127) & ~127;
     // networks (src/Learning.jl:87-142), Flux.params order
     int src = 0, dev = 0, w = c.width_hidden;
     P.nets[0].first = P.n_layers;

@@ -65,21 +65,26 @@ __device__ __forceinline__ int mz_seg_add(int v, uint32_t segmask) {
 }
 
 // select_child loop (src/SelfPlay.jl:157-166, 261-268): lane ln scores the children at Dict positions ln and ln+8.
+// One dependent memory round trip per level: the chosen child's packed word (expanded? where are its children?) and
+// prior come by shuffle from the lane that loaded its record to score it.
 __device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, const mz_tree &t, const double *pbc0, const double *sqrtN, uint32_t legal,
                                                         uint32_t posmask, mz_minmax mm, uint32_t game, uint32_t move, uint32_t sim, int ln,
                                                         uint32_t segmask, uint16_t *path) {
-    mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0;
-    const int a0 = ln < P.A ? P.order[ln] : 0, a1 = ln + 8 < P.A ? P.order[ln + 8] : 0;
+    mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0; L.prior = 0.0f; L.parent_x = 0;
+    const int a0 = ln < P.A ? P.order[ln] : 1, a1 = ln + 8 < P.A ? P.order[ln + 8] : 1;
     const bool ok0 = (posmask >> ln) & 1u, ok1 = (posmask >> (ln + 8)) & 1u;
-    int e = mz_nodeB_exp(t.B[0]);
+    uint32_t x = mz_f2bits(t.A[0].x);
     if (ln == 0) path[0] = 0;
-    while (e >= 0) {
+    while (mz_nx_exp(x) >= 0) {
         L.depth++;
-        const int base = 1 + e * P.A;
-        const int N = (int)mz_f2bits(t.A[L.node].x);
+        const int base = 1 + mz_nx_exp(x) * P.A;
+        const int N = mz_nx_visit(x);
+        mz_f4 c0, c1; c0.x = c0.y = c0.z = c0.w = 0.0f; c1 = c0;
+        if (ok0) c0 = t.A[base + a0 - 1];
+        if (ok1) c1 = t.A[base + a1 - 1];
         float s0 = 0.0f, s1 = 0.0f;
-        if (ok0) s0 = mz_ucb(P, pbc0, sqrtN, N, t.A[base + a0 - 1], mm);
-        if (ok1) s1 = mz_ucb(P, pbc0, sqrtN, N, t.A[base + a1 - 1], mm);
+        if (ok0) s0 = mz_ucb(P, pbc0, sqrtN, N, c0, mm);
+        if (ok1) s1 = mz_ucb(P, pbc0, sqrtN, N, c1, mm);
         float b = ok0 ? s0 : -INFINITY;
         if (ok1) b = s1 > b ? s1 : b;
         const float best = mz_seg_max(b, segmask);
@@ -93,18 +98,20 @@ __device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, cons
         for (int i = 0; i < pick; i++) m &= m - 1;
         const int j = __ffs((int)m) - 1;
         L.action = P.order[j];
-        L.parent = L.node;
+        L.parent = L.node; L.parent_x = x;
         L.node = base + L.action - 1;
+        x = __shfl_sync(segmask, j < 8 ? mz_f2bits(c0.x) : mz_f2bits(c1.x), j & 7, MZ_LANES);
+        L.prior = __shfl_sync(segmask, j < 8 ? c0.z : c1.z, j & 7, MZ_LANES);
         if (ln == 0) path[L.depth] = (uint16_t)L.node;
-        e = mz_nodeB_exp(t.B[L.node]);
     }
     return L;
 }
 
 // softmax(logits) (Learning.jl:114) then expand_node!'s second softmax over the legal subset (SelfPlay.jl:88-96, Q1);
-// exp() calls are spread over the lanes, both sums run in ascending action order like the scalar code.
+// exp() calls are spread over the lanes, both sums run in ascending action order like the scalar code.  The expanded
+// node's record is rebuilt from what is known (unvisited, prior, reward): no load.
 __device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *logits /* [a*MZ_ROWS] */,
-                                                     float reward, int ln, uint32_t segmask) {
+                                                     float reward, float prior, int ln, uint32_t segmask) {
     const bool v0 = ln < P.A, v1 = ln + 8 < P.A;
     const float l0 = v0 ? logits[ln * MZ_ROWS] : -INFINITY, l1 = v1 ? logits[(ln + 8) * MZ_ROWS] : -INFINITY;
     float m = mz_seg_max(l1 > l0 ? l1 : l0, segmask);
@@ -119,12 +126,10 @@ __device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const m
     float s2 = 0.0f;
     for (int a = 0; a < P.A; a++) { float v = __shfl_sync(segmask, a < 8 ? f0 : f1, a & 7, MZ_LANES); if ((legal >> a) & 1u) s2 = s2 + v; }
     const int base = 1 + e * P.A;
-    if (v0) { mz_f4 c; c.x = mz_bits2f(0u); c.y = 0.0f; c.w = 0.0f; c.z = g0 ? f0 / s2 : 0.0f; t.A[base + ln] = c; t.B[base + ln] = mz_nodeB_pack(node, -1, 0); }
-    if (v1) { mz_f4 c; c.x = mz_bits2f(0u); c.y = 0.0f; c.w = 0.0f; c.z = g1 ? f1 / s2 : 0.0f; t.A[base + ln + 8] = c; t.B[base + ln + 8] = mz_nodeB_pack(node, -1, 0); }
-    if (ln == 0) {
-        t.B[node] = mz_nodeB_pack(mz_nodeB_parent(t.B[node]), e, 0);
-        mz_f4 me = t.A[node]; me.w = reward; t.A[node] = me;
-    }
+    mz_f4 c; c.x = mz_bits2f(mz_nx_pack(0, -1, 0)); c.y = 0.0f; c.w = 0.0f;
+    if (v0) { c.z = g0 ? f0 / s2 : 0.0f; t.A[base + ln] = c; }
+    if (v1) { c.z = g1 ? f1 / s2 : 0.0f; t.A[base + ln + 8] = c; }
+    if (ln == 0) { mz_f4 me; me.x = mz_bits2f(mz_nx_pack(0, e, 0)); me.y = 0.0f; me.z = prior; me.w = reward; t.A[node] = me; }
     __syncwarp(segmask);
 }
 
@@ -138,17 +143,18 @@ __device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const m
         mz_f4 rec = t.A[nd];
         const int cnt = top + 1 < MZ_LANES ? top + 1 : MZ_LANES;
         for (int u = 0; u < cnt; u++) {
-            const float x = __shfl_sync(segmask, rec.x, u, MZ_LANES), y = __shfl_sync(segmask, rec.y, u, MZ_LANES), w = __shfl_sync(segmask, rec.w, u, MZ_LANES);
+            const uint32_t x = __shfl_sync(segmask, mz_f2bits(rec.x), u, MZ_LANES) + 1u;     // visit_count += 1
+            const float y = __shfl_sync(segmask, rec.y, u, MZ_LANES), w = __shfl_sync(segmask, rec.w, u, MZ_LANES);
             const int j = depth - (top - u);
             const bool same = (P.P == 1) || ((j % P.P) == 0);
             const float ny = same ? y + value : y - value;
-            const int vc = (int)mz_f2bits(x) + 1;
+            const int vc = mz_nx_visit(x);
             const float upd = w + P.discount * (ny / (float)vc);
             mm.mn = mm.mn < upd ? mm.mn : upd;
             mm.mx = mm.mx > upd ? mm.mx : upd;
             if (P.P == 1) value = w + P.discount * value;
             else value = same ? -w : w + P.discount * value;
-            if (ln == u) { rec.x = mz_bits2f((uint32_t)vc); rec.y = ny; t.A[nd] = rec; }
+            if (ln == u) { rec.x = mz_bits2f(x); rec.y = ny; t.A[nd] = rec; }
         }
     }
     __syncwarp(segmask);
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
     bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
-    mz_tree tree; tree.A = nullptr; tree.B = nullptr; tree.hidden = nullptr;
+    mz_tree tree; tree.A = nullptr; tree.hidden = nullptr;
     if (g < a.n) {
         tree = mz_tree_at(P, a.tree_pool, g);
         if (MODE == MZ_MODE_API) {
@@ -225,23 +231,22 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
     if (active) {
         for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_ROWS + r];
         if (ln == 0) {
-            mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;   // Node(prior=0), :232
-            tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
+            mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;   // Node(prior=0), :232
+            tree.A[0] = root;
         }
         __syncwarp(segmask);
-        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, ln, segmask);        // :245
+        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, 0.0f, ln, segmask);        // :245
         if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);   // :247-249 (eps = 0 is the identity)
         __syncwarp(segmask);
     }
 
     // ---- simulations (SelfPlay.jl:254-283) ----
     for (int sim = 1; sim <= P.S; sim++) {
-        mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0;
+        mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
         if (active) {
             leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
-            const uint32_t pb = tree.B[leaf.parent];
-            const int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+            const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
             const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);                       // 2^dbl: state after dbl in-place doublings (Q6)
             for (int k = ln; k < P.hidden; k += MZ_LANES) {
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
             const float plane = P.act_plane_play[leaf.action];                              // :8-9
             for (int k = P.obs_size + ln; k < P.sa_size; k += MZ_LANES) sp.in0[k * MZ_ROWS + r] = plane;
             __syncwarp(segmask);
-            if (ln == 0) tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+            if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
         __syncthreads();
         if (pipe.grp == 0) mz_nn_net(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
-            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], ln, segmask);   // :280 (root's legal set, Q7)
+            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], leaf.prior, ln, segmask);   // :280 (root's legal set, Q7)
             mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);                  // :281
         }
         // no CTA barrier needed here: the lanes that stage the next inputs are the ones that just read the outputs, and
@@ -272,11 +277,11 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
     if (active && ln == 0) {
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
         for (int i = 0; i < P.A; i++) {
-            vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
+            vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_nx_visit(mz_f2bits(tree.A[1 + i].x)) : 0;
             sum_visits += vc[i]; nlegal += (int)((legal >> i) & 1u);
         }
         mz_f4 root = tree.A[0];
-        int rvc = (int)mz_f2bits(root.x);
+        int rvc = mz_nx_visit(mz_f2bits(root.x));
         float rv = rvc == 0 ? 0.0f : root.y / (float)rvc;                                   // node_value(root)
         if (a.stats) {
             atomicAdd(&a.stats[0], depth_sum); atomicAdd(&a.stats[1], (unsigned long long)P.S);

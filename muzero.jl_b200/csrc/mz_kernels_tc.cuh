@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
     bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
-    mz_tree tree; tree.A = nullptr; tree.B = nullptr; tree.hidden = nullptr;
+    mz_tree tree; tree.A = nullptr; tree.hidden = nullptr;
     if (g < a.n) {
         tree = mz_tree_at(P, a.tree_pool, g);
         if (MODE == MZ_MODE_API) {
@@ -105,23 +105,22 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     if (active) {
         for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_ROWS + r];
         if (ln == 0) {
-            mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
-            tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
+            mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
+            tree.A[0] = root;
         }
         __syncwarp(segmask);
-        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, ln, segmask);
+        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, 0.0f, ln, segmask);
         if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);
         __syncwarp(segmask);
     }
 
     // ---- simulations ----
     for (int sim = 1; sim <= P.S; sim++) {
-        mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0;
+        mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
         if (active) {
             leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
-            const uint32_t pb = tree.B[leaf.parent];
-            const int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+            const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
             const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);
             for (int k = ln; k < P.hidden; k += MZ_LANES) {
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
             const float plane = P.act_plane_play[leaf.action];
             for (int k = P.obs_size + ln; k < P.sa_size; k += MZ_LANES) mz_tc_store_bf16(sp.in0, r, k, plane);
             __syncwarp(segmask);
-            if (ln == 0) tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+            if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
         mz_fence_proxy_async();
         __syncthreads();
@@ -142,7 +141,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
-            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], ln, segmask);
+            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], leaf.prior, ln, segmask);
             mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);
         }
     }
@@ -151,11 +150,11 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     if (active && ln == 0) {
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
         for (int i = 0; i < P.A; i++) {
-            vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
+            vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_nx_visit(mz_f2bits(tree.A[1 + i].x)) : 0;
             sum_visits += vc[i]; nlegal += (int)((legal >> i) & 1u);
         }
         mz_f4 root = tree.A[0];
-        int rvc = (int)mz_f2bits(root.x);
+        int rvc = mz_nx_visit(mz_f2bits(root.x));
         float rv = rvc == 0 ? 0.0f : root.y / (float)rvc;
         if (a.stats) {
             atomicAdd(&a.stats[0], depth_sum); atomicAdd(&a.stats[1], (unsigned long long)P.S);

@@ -49,36 +49,36 @@ void search_one(const mzh::model &M, const net_runner &nn, std::vector<char> &po
     for (int k = 0; k < P.hidden; k++) tree.hidden[k] = outH[(size_t)k];
     for (int i = 0; i < P.A; i++) logits[i] = outL[(size_t)i];
     mz_softmax(logits, P.A, policy);
-    mz_f4 root; root.x = mz_bits2f(0u); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
-    tree.A[0] = root; tree.B[0] = mz_nodeB_pack(0, -1, 0);
-    mz_tree_expand(P, tree, 0, 0, legal, policy, 0.0f);
+    mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
+    tree.A[0] = root;
+    mz_tree_expand(P, tree, 0, 0, legal, policy, 0.0f, 0.0f);
     if (exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);
     out.depth_sum = 0;
+    std::vector<uint16_t> path((size_t)P.S + 2);
     for (int sim = 1; sim <= P.S; sim++) {
-        mz_leaf leaf = mz_tree_select(P, tree, M.pbc0.data(), M.sqrtN.data(), legal, mm, game, move, (uint32_t)sim);
+        mz_leaf leaf = mz_tree_select(P, tree, M.pbc0.data(), M.sqrtN.data(), legal, mm, game, move, (uint32_t)sim, path.data());
         out.depth_sum += leaf.depth;
-        uint32_t pb = tree.B[leaf.parent];
-        int pe = mz_nodeB_exp(pb), dbl = mz_nodeB_dbl(pb);
+        int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
         const float *hp = tree.hidden + (size_t)pe * P.hidden_pad;
         float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);
         for (int k = 0; k < P.hidden; k++) { float v = hp[k] * sc; in1[(size_t)k] = v; in0[(size_t)k] = v * 2.0f; }
         float plane = P.act_plane_play[leaf.action];
         for (int k = P.obs_size; k < P.sa_size; k++) in0[(size_t)k] = plane;
-        tree.B[leaf.parent] = mz_nodeB_pack(mz_nodeB_parent(pb), pe, dbl + 1);
+        { mz_f4 pr = tree.A[leaf.parent]; pr.x = mz_bits2f(mz_f2bits(pr.x) + (1u << 24)); tree.A[leaf.parent] = pr; }   // one more in-place doubling
         nn.net(1, in1.data(), outV.data(), outL.data());
         nn.net(2, in0.data(), outH.data(), outR.data());
         float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
         for (int k = 0; k < P.hidden; k++) nh[k] = outH[(size_t)k];
         for (int i = 0; i < P.A; i++) logits[i] = outL[(size_t)i];
         mz_softmax(logits, P.A, policy);
-        mz_tree_expand(P, tree, leaf.node, sim, legal, policy, outR[0]);
-        mz_tree_backup(P, tree, leaf.node, outV[0], mm);
+        mz_tree_expand(P, tree, leaf.node, sim, legal, policy, outR[0], leaf.prior);
+        mz_tree_backup(P, tree, path.data(), leaf.depth, outV[0], mm);
     }
     for (int i = 0; i < P.A; i++) {
-        out.vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_f2bits(tree.A[1 + i].x) : 0;
+        out.vc[i] = ((legal >> i) & 1u) ? (int32_t)mz_nx_visit(mz_f2bits(tree.A[1 + i].x)) : 0;
         out.priors[i] = ((legal >> i) & 1u) ? tree.A[1 + i].z : 0.0f;
     }
-    mz_f4 r = tree.A[0]; int rvc = (int)mz_f2bits(r.x);
+    mz_f4 r = tree.A[0]; int rvc = mz_nx_visit(mz_f2bits(r.x));
     out.rv = rvc == 0 ? 0.0f : r.y / (float)rvc;
 }
 }  // namespace
