@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libmuzero_b200.so")
+_SO = os.environ.get("MUZERO_B200_LIB") or os.path.join(_HERE, "libmuzero_b200.so")
 MAX_A = 16
 
 OK, E_ARG, E_CUDA, E_STATE, E_NCCL, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
@@ -111,6 +111,7 @@ def lib():
         "mz_kernel_time": ([ctx, C.c_int, C.POINTER(C.c_double), i64p], C.c_int),
         "mz_kernel_time_reset": ([ctx, C.c_int], C.c_int),
         "mz_search_stats": ([ctx, C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
+        "mz_phase_cycles": ([ctx, u64p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)   # AttributeError here = the library does not export a declared symbol
@@ -365,6 +366,11 @@ class Context:
         ms, n = C.c_double(), C.c_int64()
         self._ck(self.L.mz_kernel_time(self._h, family, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def phase_cycles(self):
+        out = np.zeros(12, np.uint64)
+        self._ck(self.L.mz_phase_cycles(self._h, _p(out, C.c_uint64)))
+        return out.reshape(2, 6)
 
     def search_stats(self):
         a, b = C.c_double(), C.c_double()

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
 
     mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;
     unsigned long long depth_sum = 0;
+    MZ_TIMER_DECL;
     if (active) {
         for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_ROWS + r];
         if (ln == 0) {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     // ---- simulations ----
     for (int sim = 1; sim <= P.S; sim++) {
         mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
+        MZ_TIMER(0);
         if (active) {
             leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
@@ -134,18 +136,24 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
             if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
         mz_fence_proxy_async();
+        MZ_TIMER(1);
         __syncthreads();
+        MZ_TIMER(2);
         if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
         else               mz_tc_net(pipe, P, 2, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
+        MZ_TIMER(3);
         __syncthreads();
+        MZ_TIMER(4);
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
             mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], leaf.prior, ln, segmask);
             mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);
         }
+        MZ_TIMER(5);
     }
 
+    MZ_TIMER_FLUSH(a.stats);
     // ---- results (lane 0 of each tree), identical to mz_k_search ----
     if (active && ln == 0) {
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;

@@ -1,0 +1,22 @@
+"""Per-phase cycle breakdown of the simulation loop (needs a -DMZ_PHASE_TIMERS build: make -C muzero.jl_b200/csrc -B EXTRA=-DMZ_PHASE_TIMERS)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from muzero_jl_b200 import capi
+
+G, S = 4096, 50
+names = ["select+stage", "wait", "network", "wait", "expand+backup"]
+for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_tcgen05")):
+    ctx = capi.Context(capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=10000, nn_mode=mode))
+    ctx.init_weights(1337)
+    ctx.self_play(0, G, 1.0)
+    sims, moves = ctx.self_play(G, G, 1.0)
+    pc = ctx.phase_cycles().astype(float)
+    for g, who in ((0, "thread 0 (tree lane / prediction group)"), (1, "thread 128 (dynamics group)")):
+        n = pc[g, 5]; rounds = n * S
+        if n == 0:
+            print(label, who, "no timers in this build"); continue
+        tot = pc[g, :5].sum()
+        print("%s %s: %.0f cycles/round; " % (label, who, tot / rounds) + ", ".join("%s %.0f (%.0f%%)" % (names[i], pc[g, i] / rounds, 100 * pc[g, i] / tot) for i in range(5)))
+    ctx.close()
