@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     }
     mz_tc_pipe pipe;
     pipe.grp = tid >> 7; pipe.gtid = tid & (MZ_GROUP - 1); pipe.w_base = sp.w_base; pipe.bias = sp.bias; pipe.mbar = sp.mbar_mma[pipe.grp];
-    pipe.tmem_d = tmem_base + (uint32_t)(32 * pipe.grp); pipe.q = 0;
+    pipe.tmem_d = tmem_base + (uint32_t)(64 * pipe.grp); pipe.q = 0;
     uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     __syncthreads();
 
     // ---- root: representation -> h0 (fp32 in outH); prediction(h0) -> (v0, p0) ----
-    if (pipe.grp == 0) mz_tc_net(pipe, P, 0, sp.inS, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+    if (pipe.grp == 0) mz_tc_net(pipe, P, 0, sp.inS, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0], 0u);
     __syncthreads();
     for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_THREADS) { int k = i / MZ_ROWS, rr = i % MZ_ROWS; mz_tc_store_bf16(sp.in1, rr, k, sp.outH[k * MZ_ROWS + rr]); }
     mz_fence_proxy_async();
     __syncthreads();
-    if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+    if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0], sp.t1[0]);
     __syncthreads();
 
     mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         MZ_TIMER(1);
         __syncthreads();
         MZ_TIMER(2);
-        if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
-        else               mz_tc_net(pipe, P, 2, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
+        if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0], sp.t1[0]);
+        else               mz_tc_net(pipe, P, 2, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1], sp.inS);
         MZ_TIMER(3);
         __syncthreads();
         MZ_TIMER(4);
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward_tc(const __grid_co
     }
     mz_tc_pipe pipe;
     pipe.grp = tid >> 7; pipe.gtid = tid & (MZ_GROUP - 1); pipe.w_base = sp.w_base; pipe.bias = sp.bias; pipe.mbar = sp.mbar_mma[pipe.grp];
-    pipe.tmem_d = tmem_base + (uint32_t)(32 * pipe.grp); pipe.q = 0;
+    pipe.tmem_d = tmem_base + (uint32_t)(64 * pipe.grp); pipe.q = 0;
     const int in = P.layers[P.nets[a.net].first].in;
     for (int i = tid; i < MZ_ROWS * in; i += MZ_THREADS) {
         int rr = i / in, k = i % in;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward_tc(const __grid_co
     mz_mbar_wait(sp.mbar_w, 0);
     __syncthreads();
     float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
-    if (pipe.grp == 0) mz_tc_net(pipe, P, a.net, sp.inS, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0]);
+    if (pipe.grp == 0) mz_tc_net(pipe, P, a.net, sp.inS, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0], sp.in1);
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
     if (tid < MZ_ROWS && g < a.B) {

@@ -15,7 +15,7 @@
 #include "mz_device.cuh"
 
 #define MZ_TC_TILE_BYTES 4096          // [32 rows x 64 bf16]
-#define MZ_TC_TMEM_COLS 64             // two accumulators of 32 fp32 columns
+#define MZ_TC_TMEM_COLS 128            // two groups x two accumulators of 32 fp32 columns
 // instruction descriptor, kind::f16: D=F32 (bits 4-5 = 1), A=BF16 (bits 7-9 = 1), B=BF16 (bits 10-12 = 1), K-major A and B,
 // N>>3 at bits 17-22, M>>4 at bits 24-28  (cute::UMMA::InstrDescriptor)
 #define MZ_TC_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((64u >> 4) << 24))
@@ -74,75 +74,125 @@ struct mz_tc_pipe {             // one per group
     int grp, gtid;
 };
 
-// One Dense layer on the tensor core for one group.  src: bf16 B tile.  dst: bf16 tile (dst_tile != 0) or fp32 [m*32+n].
-__device__ __noinline__ void mz_tc_layer(mz_tc_pipe &s, const mz_params &P, int layer, uint32_t src_tile, uint32_t dst_tile, float *dst_f32) {
-    const mz_layer &L = P.layers[layer];
+// TMEM -> registers, shape 16x256b.x4: the warp reads 16 TMEM lanes x 32 columns; thread t receives, for column block
+// q = 0..3, v[4q+0..1] = (lane t/4,   columns 8q + 2(t%4) + {0,1}) and v[4q+2..3] = (lane t/4 + 8, same columns)
+// (cute::SM100_TMEM_LOAD_16dp256b4x).  With M = 64 accumulators only lanes 0..15 of each warp's TMEM partition hold
+// rows, so this shape keeps all 32 threads of every warp busy in the epilogue.
+__device__ __forceinline__ void mz_tc_ld16x256(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void mz_tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct mz_tc_job { int layer; uint32_t src, dst_tile; float *dst_f32; };   // layer < 0: no job
+
+// bias + activation + store of one job's accumulator fragment (16 values per thread)
+__device__ __forceinline__ void mz_tc_epilogue(const mz_tc_pipe &s, const mz_params &P, const mz_tc_job &j, const uint32_t (&v)[16]) {
+    const mz_layer &L = P.layers[j.layer];
+    const int w = s.gtid >> 5, t = s.gtid & 31, c = 2 * (t & 3);
+    const float lo = L.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int m = 16 * w + (t >> 2) + 8 * half;
+        if (m < L.out) {
+            const float b = s.bias[P.tc_bias_off[j.layer] + m];
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 4; q++) { x[2 * q] = fmaxf(__uint_as_float(v[4 * q + 2 * half]) + b, lo); x[2 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 2 * half + 1]) + b, lo); }
+            if (L.act == MZ_ACT_TANH) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = mz_tanhf_noinline(x[i]);
+            }
+            if (j.dst_tile) {
+                const uint32_t colbase = j.dst_tile + (uint32_t)((m & 7) * 2), chunk = (uint32_t)(m >> 3);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int n = 8 * (i >> 1) + c + (i & 1);
+                    unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(x[i]));
+                    asm volatile("st.shared.b16 [%0], %1;" ::"r"(colbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + ((chunk ^ (uint32_t)(n & 7)) << 4)), "h"(h) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) *reinterpret_cast<float2 *>(j.dst_f32 + m * MZ_ROWS + 8 * q + c) = make_float2(x[2 * q], x[2 * q + 1]);
+            }
+        }
+    }
+}
+
+// One round for one group: up to two independent Dense layers (e.g. the first layers of the two heads of a network,
+// which read the same trunk tile) are issued back to back on the tensor core into the group's two 32-column
+// accumulators, committed once, and their epilogues share one barrier round trip.
+__device__ __noinline__ void mz_tc_round(mz_tc_pipe &s, const mz_params &P, mz_tc_job j0, mz_tc_job j1) {
     if (s.gtid == 0) {
         mz_tc_fence_after();
-        const uint64_t adesc = mz_tc_desc(s.w_base + (uint32_t)P.tc_a_off[layer]), bdesc = mz_tc_desc(src_tile);
-        const int ks = P.tc_ksteps[layer];
-        for (int k = 0; k < ks; k++) mz_tc_mma(s.tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+        {
+            const uint64_t adesc = mz_tc_desc(s.w_base + (uint32_t)P.tc_a_off[j0.layer]), bdesc = mz_tc_desc(j0.src);
+            const int ks = P.tc_ksteps[j0.layer];
+            for (int k = 0; k < ks; k++) mz_tc_mma(s.tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+        }
+        if (j1.layer >= 0) {
+            const uint64_t adesc = mz_tc_desc(s.w_base + (uint32_t)P.tc_a_off[j1.layer]), bdesc = mz_tc_desc(j1.src);
+            const int ks = P.tc_ksteps[j1.layer];
+            for (int k = 0; k < ks; k++) mz_tc_mma(s.tmem_d + 32u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
+        }
         mz_tc_commit(s.mbar);
     }
     mz_mbar_wait(s.mbar, s.q & 1u);
     mz_tc_fence_after();
-    const int w = s.gtid >> 5, t = s.gtid & 31;
-    uint32_t v[32];
     __syncwarp();
-    mz_tc_ld32(s.tmem_d + ((uint32_t)(32 * w) << 16), v);       // M = 64: rows 16w..16w+15 live in lanes 32w..32w+15
-    const int m = 16 * w + t;
-    if (t < 16 && m < L.out) {
-        // compact epilogue (one code path for relu / identity; tanh -- only the 1-wide value / reward outputs -- goes through a
-        // non-inlined call) so both groups' epilogues stay resident in the instruction cache
-        const float b = s.bias[P.tc_bias_off[layer] + m];
-        const float lo = L.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
-        float x[32];
-#pragma unroll
-        for (int n = 0; n < 32; n++) x[n] = fmaxf(__uint_as_float(v[n]) + b, lo);
-        if (L.act == MZ_ACT_TANH) {
-#pragma unroll
-            for (int n = 0; n < 32; n++) x[n] = mz_tanhf_noinline(x[n]);
-        }
-        if (dst_tile) {
-            const uint32_t colbase = dst_tile + (uint32_t)((m & 7) * 2), chunk = (uint32_t)(m >> 3);
-#pragma unroll
-            for (int n = 0; n < 32; n++) {
-                unsigned short h = __bfloat16_as_ushort(__float2bfloat16_rn(x[n]));
-                asm volatile("st.shared.b16 [%0], %1;" ::"r"(colbase + (uint32_t)((n >> 3) * 1024 + (n & 7) * 128) + ((chunk ^ (uint32_t)(n & 7)) << 4)), "h"(h) : "memory");
-            }
-        } else {
-#pragma unroll
-            for (int n = 0; n < 32; n += 4) *reinterpret_cast<float4 *>(dst_f32 + m * MZ_ROWS + n) = make_float4(x[n], x[n + 1], x[n + 2], x[n + 3]);
-        }
-    }
+    const uint32_t lane_base = s.tmem_d + ((uint32_t)(32 * (s.gtid >> 5)) << 16);     // M = 64: rows 16w..16w+15 live in lanes 32w..32w+15
+    uint32_t v0[16], v1[16];
+    mz_tc_ld16x256(lane_base, v0);
+    if (j1.layer >= 0) mz_tc_ld16x256(lane_base + 32u, v1);
+    mz_tc_wait_ld();
+    mz_tc_epilogue(s, P, j0, v0);
+    if (j1.layer >= 0) mz_tc_epilogue(s, P, j1, v1);
     mz_fence_proxy_async();
     mz_tc_fence_before();
     mz_group_sync(s.grp);
     s.q++;
 }
+__device__ __forceinline__ mz_tc_job mz_tc_mkjob(int layer, uint32_t src, uint32_t dst_tile, float *dst_f32) { mz_tc_job j; j.layer = layer; j.src = src; j.dst_tile = dst_tile; j.dst_f32 = dst_f32; return j; }
 __device__ __forceinline__ void mz_tc_chain(mz_tc_pipe &s, const mz_params &P, int first, int n, uint32_t src, float *dst_f32, uint32_t t0, uint32_t t1) {
     uint32_t cur = src;
     for (int i = 0; i < n; i++) {
         const bool last = i == n - 1;
         uint32_t d = (i & 1) ? t1 : t0;
-        mz_tc_layer(s, P, first + i, cur, last ? 0u : d, last ? dst_f32 : nullptr);
+        mz_tc_round(s, P, mz_tc_mkjob(first + i, cur, last ? 0u : d, last ? dst_f32 : nullptr), mz_tc_mkjob(-1, 0u, 0u, nullptr));
         cur = d;
     }
 }
-// trunk -> bufT tile, heads -> fp32 outputs (representation: trunk's last layer -> h1dst)
-__device__ __forceinline__ void mz_tc_net(mz_tc_pipe &s, const mz_params &P, int net, uint32_t src, uint32_t bufT, float *h1dst, float *h2dst, uint32_t t0, uint32_t t1) {
+// trunk -> bufT tile, then the two heads advance in lockstep, one round per depth level (head 2 may be at most two layers
+// deep: it has the single scratch tile tx); representation: the trunk's last layer -> h1dst
+__device__ __forceinline__ void mz_tc_net(mz_tc_pipe &s, const mz_params &P, int net, uint32_t src, uint32_t bufT, float *h1dst, float *h2dst,
+                                          uint32_t t0, uint32_t t1, uint32_t tx) {
     const mz_net &N = P.nets[net];
     const int f = N.first;
     if (N.n_h1 == 0) { mz_tc_chain(s, P, f, N.n_trunk, src, h1dst, t0, t1); return; }
-    // trunk: every layer writes a tile; the last one goes to bufT
     uint32_t cur = src;
     for (int i = 0; i < N.n_trunk; i++) {
         uint32_t d = (i == N.n_trunk - 1) ? bufT : ((i & 1) ? t1 : t0);
-        mz_tc_layer(s, P, f + i, cur, d, nullptr);
+        mz_tc_round(s, P, mz_tc_mkjob(f + i, cur, d, nullptr), mz_tc_mkjob(-1, 0u, 0u, nullptr));
         cur = d;
     }
-    mz_tc_chain(s, P, f + N.n_trunk, N.n_h1, bufT, h1dst, t0, t1);
-    mz_tc_chain(s, P, f + N.n_trunk + N.n_h1, N.n_h2, bufT, h2dst, t0, t1);
+    const int f1 = f + N.n_trunk, f2 = f1 + N.n_h1;
+    if (N.n_h2 > 2 || N.n_h2 > N.n_h1) {   // general fallback: heads one after the other
+        mz_tc_chain(s, P, f1, N.n_h1, bufT, h1dst, t0, t1);
+        mz_tc_chain(s, P, f2, N.n_h2, bufT, h2dst, t0, t1);
+        return;
+    }
+    uint32_t cur1 = bufT, cur2 = bufT;
+    for (int i = 0; i < N.n_h1; i++) {
+        const bool last1 = i == N.n_h1 - 1, has2 = i < N.n_h2, last2 = i == N.n_h2 - 1;
+        // when head 1 ends here its output is fp32, so its ping-pong tile of this round is free for head 2
+        const uint32_t d1 = (i & 1) ? t1 : t0;
+        const uint32_t d2 = last1 ? d1 : tx;
+        mz_tc_round(s, P, mz_tc_mkjob(f1 + i, cur1, last1 ? 0u : d1, last1 ? h1dst : nullptr),
+                    has2 ? mz_tc_mkjob(f2 + i, cur2, last2 ? 0u : d2, last2 ? h2dst : nullptr) : mz_tc_mkjob(-1, 0u, 0u, nullptr));
+        cur1 = d1; cur2 = d2;
+    }
 }
 
 struct mz_tc_plan {
