@@ -368,9 +368,9 @@ class Context:
         return ms.value, n.value
 
     def phase_cycles(self):
-        out = np.zeros(12, np.uint64)
+        out = np.zeros(28, np.uint64)
         self._ck(self.L.mz_phase_cycles(self._h, _p(out, C.c_uint64)))
-        return out.reshape(2, 6)
+        return out
 
     def search_stats(self):
         a, b = C.c_double(), C.c_double()

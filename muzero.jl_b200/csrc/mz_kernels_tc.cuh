@@ -46,9 +46,22 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         }
         mz_bulk_g2s((void *)sp.bias, ta.bias, bbytes, sp.mbar_w);
     }
-    mz_tc_pipe pipe;
-    pipe.grp = tid >> 7; pipe.gtid = tid & (MZ_GROUP - 1); pipe.w_base = sp.w_base; pipe.bias = sp.bias; pipe.mbar = sp.mbar_mma[pipe.grp];
-    pipe.tmem_d = tmem_base + (uint32_t)(64 * pipe.grp); pipe.q = 0;
+    // compile the three networks into the round table (one thread, once per kernel)
+    int *rounds = reinterpret_cast<int *>(sp.tmem_slot) + 4;            // [0] representation, [1] prediction, [2] dynamics round counts
+    if (tid == 0) {
+        mz_tc_builder B; B.prog = sp.prog; B.n = 0; B.w_base = sp.w_base; B.bias_base = mz_smem_u32(sp.bias);
+        rounds[0] = mz_tc_build_net(B, P, 0, sp.inS, sp.bufT[0], mz_smem_u32(sp.outH), 0u, sp.t0[0], sp.t1[0], 0u);
+        rounds[1] = mz_tc_build_net(B, P, 1, sp.in1, sp.bufT[0], mz_smem_u32(sp.outV), mz_smem_u32(sp.outL), sp.t0[0], sp.t1[0], sp.t1[0]);
+        rounds[2] = mz_tc_build_net(B, P, 2, sp.in0, sp.bufT[1], mz_smem_u32(sp.outH), mz_smem_u32(sp.outR), sp.t0[1], sp.t1[1], sp.inS);
+    }
+    const int grp = tid >> 7, gtid = tid & (MZ_GROUP - 1);
+    const uint32_t tmem_d = tmem_base + (uint32_t)(64 * grp), mbar_mma = mz_smem_u32(sp.mbar_mma[grp]);
+    uint32_t q = 0;                                                     // rounds executed by this group (mbarrier parity)
+    long long *tk = nullptr;
+#ifdef MZ_PHASE_TIMERS
+    long long rt[6] = {0, 0, 0, 0, 0, 0};
+    if (tid == 0 || tid == MZ_GROUP + 32) tk = rt;                      // observers: the issuing thread of group 0, a plain epilogue thread of group 1
+#endif
     uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
@@ -92,12 +105,13 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     __syncthreads();
 
     // ---- root: representation -> h0 (fp32 in outH); prediction(h0) -> (v0, p0) ----
-    if (pipe.grp == 0) mz_tc_net(pipe, P, 0, sp.inS, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0], 0u);
+    const int n_repr = rounds[0], n_pred = rounds[1], n_dyn = rounds[2];
+    if (grp == 0) q = mz_tc_run(sp.prog, 0, n_repr, tmem_d, mbar_mma, q, grp, gtid, tk);
     __syncthreads();
     for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_THREADS) { int k = i / MZ_ROWS, rr = i % MZ_ROWS; mz_tc_store_bf16(sp.in1, rr, k, sp.outH[k * MZ_ROWS + rr]); }
     mz_fence_proxy_async();
     __syncthreads();
-    if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0], sp.t1[0]);
+    if (grp == 0) q = mz_tc_run(sp.prog, n_repr, n_pred, tmem_d, mbar_mma, q, grp, gtid, tk);
     __syncthreads();
 
     mz_minmax mm; mm.mn = INFINITY; mm.mx = -INFINITY;
@@ -139,8 +153,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         MZ_TIMER(1);
         __syncthreads();
         MZ_TIMER(2);
-        if (pipe.grp == 0) mz_tc_net(pipe, P, 1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0], sp.t1[0]);
-        else               mz_tc_net(pipe, P, 2, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1], sp.inS);
+        if (grp == 0) q = mz_tc_run(sp.prog, n_repr, n_pred, tmem_d, mbar_mma, q, grp, gtid, tk);
+        else          q = mz_tc_run(sp.prog, n_repr + n_pred, n_dyn, tmem_d, mbar_mma, q, grp, gtid, tk);
         MZ_TIMER(3);
         __syncthreads();
         MZ_TIMER(4);
@@ -154,6 +168,9 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
     }
 
     MZ_TIMER_FLUSH(a.stats);
+#ifdef MZ_PHASE_TIMERS
+    if (a.stats && tk) { int o_ = tid == 0 ? 16 : 24; for (int i_ = 0; i_ < 6; i_++) atomicAdd(&a.stats[o_ + i_], (unsigned long long)rt[i_]); atomicAdd(&a.stats[o_ + 6], (unsigned long long)q); }
+#endif
     // ---- results (lane 0 of each tree), identical to mz_k_search ----
     if (active && ln == 0) {
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
@@ -225,9 +242,13 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward_tc(const __grid_co
         }
         mz_bulk_g2s((void *)sp.bias, a.bias, bbytes, sp.mbar_w);
     }
-    mz_tc_pipe pipe;
-    pipe.grp = tid >> 7; pipe.gtid = tid & (MZ_GROUP - 1); pipe.w_base = sp.w_base; pipe.bias = sp.bias; pipe.mbar = sp.mbar_mma[pipe.grp];
-    pipe.tmem_d = tmem_base + (uint32_t)(64 * pipe.grp); pipe.q = 0;
+    float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
+    int *rounds = reinterpret_cast<int *>(sp.tmem_slot) + 4;
+    if (tid == 0) {
+        mz_tc_builder B; B.prog = sp.prog; B.n = 0; B.w_base = sp.w_base; B.bias_base = mz_smem_u32(sp.bias);
+        rounds[0] = mz_tc_build_net(B, P, a.net, sp.inS, sp.bufT[0], mz_smem_u32(h1), mz_smem_u32(h2), sp.t0[0], sp.t1[0], sp.in1);
+    }
+    const int grp = tid >> 7, gtid = tid & (MZ_GROUP - 1);
     const int in = P.layers[P.nets[a.net].first].in;
     for (int i = tid; i < MZ_ROWS * in; i += MZ_THREADS) {
         int rr = i / in, k = i % in;
@@ -237,8 +258,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward_tc(const __grid_co
     mz_fence_proxy_async();
     mz_mbar_wait(sp.mbar_w, 0);
     __syncthreads();
-    float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
-    if (pipe.grp == 0) mz_tc_net(pipe, P, a.net, sp.inS, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0], sp.in1);
+    if (grp == 0) mz_tc_run(sp.prog, 0, rounds[0], tmem_base, mz_smem_u32(sp.mbar_mma[0]), 0u, grp, gtid, nullptr);
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
     if (tid < MZ_ROWS && g < a.B) {

@@ -65,14 +65,27 @@ __device__ __forceinline__ void mz_tc_store_bf16(uint32_t tile, int n, int k, fl
 
 __device__ __noinline__ float mz_tanhf_noinline(float x) { return mz_tanhf(x); }
 
-struct mz_tc_pipe {             // one per group
-    uint32_t w_base;            // shared address of the weight image
-    const float *bias;          // shared fp32 bias block
-    uint64_t *mbar;             // MMA-done barrier of this group
-    uint32_t tmem_d;            // this group's 32 accumulator columns
-    uint32_t q;                 // layers executed by this group (barrier parity)
-    int grp, gtid;
+// ---- table-driven execution ------------------------------------------------------------------------------------
+// The three networks are compiled ONCE per kernel (by one thread) into a table of "rounds" in shared memory.  A round is
+// up to two independent Dense layers (e.g. the first layers of the two heads of a network, which read the same trunk
+// tile): they are issued back to back into the group's two 32-column accumulators, committed once, and their epilogues
+// share one barrier round trip.  Everything a round needs (UMMA descriptors, K steps, bias address, destination) is in
+// its 80-byte descriptor, so the per-round code is one compact, register-only loop body.
+struct __align__(16) mz_tc_rdesc {
+    unsigned long long adesc[2], bdesc[2];
+    uint32_t dst_tile[2];      // bf16 B tile of the next layer (shared address) or 0
+    uint32_t dst_f32[2];       // fp32 [m*32 + n] output (shared address) or 0
+    uint32_t bias[2];          // shared address of the layer's fp32 bias
+    int16_t ks[2], out[2], act[2], njobs, pad_;
 };
+#define MZ_TC_MAX_ROUNDS 40
+
+#ifdef MZ_PHASE_TIMERS
+#define MZ_RT(i) do { if (tk) { long long c_ = clock64(); if ((i) > 0) tk[(i) - 1] += c_ - tprev; tprev = c_; } } while (0)
+#else
+#define MZ_RT(i)
+#endif
+
 
 // TMEM -> registers, shape 16x256b.x4: the warp reads 16 TMEM lanes x 32 columns; thread t receives, for column block
 // q = 0..3, v[4q+0..1] = (lane t/4,   columns 8q + 2(t%4) + {0,1}) and v[4q+2..3] = (lane t/4 + 8, same columns)
@@ -85,28 +98,26 @@ __device__ __forceinline__ void mz_tc_ld16x256(uint32_t taddr, uint32_t (&v)[16]
                  : "r"(taddr));
 }
 __device__ __forceinline__ void mz_tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float mz_lds32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 
-struct mz_tc_job { int layer; uint32_t src, dst_tile; float *dst_f32; };   // layer < 0: no job
-
-// bias + activation + store of one job's accumulator fragment (16 values per thread)
-__device__ __forceinline__ void mz_tc_epilogue(const mz_tc_pipe &s, const mz_params &P, const mz_tc_job &j, const uint32_t (&v)[16]) {
-    const mz_layer &L = P.layers[j.layer];
-    const int w = s.gtid >> 5, t = s.gtid & 31, c = 2 * (t & 3);
-    const float lo = L.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
+// bias + activation + store of one job's accumulator fragment (16 values per thread, rows m0 = 16w + t/4 and m0 + 8)
+__device__ __forceinline__ void mz_tc_epilogue(const uint32_t (&v)[16], int out, int act, uint32_t bias, uint32_t dst_tile, uint32_t dst_f32, int w, int t) {
+    const int c = 2 * (t & 3);
+    const float lo = act == MZ_ACT_RELU ? 0.0f : -INFINITY;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int m = 16 * w + (t >> 2) + 8 * half;
-        if (m < L.out) {
-            const float b = s.bias[P.tc_bias_off[j.layer] + m];
+        if (m < out) {
+            const float b = mz_lds32(bias + (uint32_t)m * 4u);
             float x[8];
 #pragma unroll
             for (int q = 0; q < 4; q++) { x[2 * q] = fmaxf(__uint_as_float(v[4 * q + 2 * half]) + b, lo); x[2 * q + 1] = fmaxf(__uint_as_float(v[4 * q + 2 * half + 1]) + b, lo); }
-            if (L.act == MZ_ACT_TANH) {
+            if (act == MZ_ACT_TANH) {
 #pragma unroll
                 for (int i = 0; i < 8; i++) x[i] = mz_tanhf_noinline(x[i]);
             }
-            if (j.dst_tile) {
-                const uint32_t colbase = j.dst_tile + (uint32_t)((m & 7) * 2), chunk = (uint32_t)(m >> 3);
+            if (dst_tile) {
+                const uint32_t colbase = dst_tile + (uint32_t)((m & 7) * 2), chunk = (uint32_t)(m >> 3);
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int n = 8 * (i >> 1) + c + (i & 1);
@@ -115,91 +126,114 @@ __device__ __forceinline__ void mz_tc_epilogue(const mz_tc_pipe &s, const mz_par
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++) *reinterpret_cast<float2 *>(j.dst_f32 + m * MZ_ROWS + 8 * q + c) = make_float2(x[2 * q], x[2 * q + 1]);
+                for (int q = 0; q < 4; q++)
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst_f32 + (uint32_t)((m * MZ_ROWS + 8 * q + c) * 4)), "f"(x[2 * q]), "f"(x[2 * q + 1]) : "memory");
             }
         }
     }
 }
 
-// One round for one group: up to two independent Dense layers (e.g. the first layers of the two heads of a network,
-// which read the same trunk tile) are issued back to back on the tensor core into the group's two 32-column
-// accumulators, committed once, and their epilogues share one barrier round trip.
-__device__ __noinline__ void mz_tc_round(mz_tc_pipe &s, const mz_params &P, mz_tc_job j0, mz_tc_job j1) {
-    if (s.gtid == 0) {
-        mz_tc_fence_after();
+// Runs rounds [first, first+count) of the table for one 128-thread group.  All state is in registers.
+__device__ __noinline__ uint32_t mz_tc_run(const mz_tc_rdesc *prog, int first, int count, uint32_t tmem_d, uint32_t mbar, uint32_t q, int grp, int gtid,
+                                           long long *tk) {
+    long long tprev = 0; (void)tprev; (void)tk;
+    const int w = gtid >> 5, t = gtid & 31;
+    const uint32_t lane_base = tmem_d + ((uint32_t)(32 * w) << 16);     // M = 64: rows 16w..16w+15 live in lanes 32w..32w+15
+    for (int r = first; r < first + count; r++) {
+        const mz_tc_rdesc *R = prog + r;
+        const int njobs = R->njobs;
+        MZ_RT(0);
+        if (gtid == 0) {
+            mz_tc_fence_after();
+            for (int j = 0; j < njobs; j++) {
+                const uint64_t ad = R->adesc[j], bd = R->bdesc[j];
+                const int ks = R->ks[j];
+                for (int k = 0; k < ks; k++) mz_tc_mma(tmem_d + 32u * (uint32_t)j, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+        }
+        MZ_RT(1);
         {
-            const uint64_t adesc = mz_tc_desc(s.w_base + (uint32_t)P.tc_a_off[j0.layer]), bdesc = mz_tc_desc(j0.src);
-            const int ks = P.tc_ksteps[j0.layer];
-            for (int k = 0; k < ks; k++) mz_tc_mma(s.tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+            uint32_t ok = 0, spin = 0;
+            while (!ok) {
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(mbar), "r"(q & 1u) : "memory");
+                if (++spin > (1u << 24)) __trap();
+            }
         }
-        if (j1.layer >= 0) {
-            const uint64_t adesc = mz_tc_desc(s.w_base + (uint32_t)P.tc_a_off[j1.layer]), bdesc = mz_tc_desc(j1.src);
-            const int ks = P.tc_ksteps[j1.layer];
-            for (int k = 0; k < ks; k++) mz_tc_mma(s.tmem_d + 32u, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
-        }
-        mz_tc_commit(s.mbar);
+        MZ_RT(2);
+        mz_tc_fence_after();
+        __syncwarp();
+        uint32_t v0[16], v1[16];
+        mz_tc_ld16x256(lane_base, v0);
+        if (njobs > 1) mz_tc_ld16x256(lane_base + 32u, v1);
+        mz_tc_wait_ld();
+        MZ_RT(3);
+        mz_tc_epilogue(v0, R->out[0], R->act[0], R->bias[0], R->dst_tile[0], R->dst_f32[0], w, t);
+        if (njobs > 1) mz_tc_epilogue(v1, R->out[1], R->act[1], R->bias[1], R->dst_tile[1], R->dst_f32[1], w, t);
+        MZ_RT(4);
+        mz_fence_proxy_async();
+        MZ_RT(5);
+        mz_tc_fence_before();
+        mz_group_sync(grp);
+        MZ_RT(6);
+        q++;
     }
-    mz_mbar_wait(s.mbar, s.q & 1u);
-    mz_tc_fence_after();
-    __syncwarp();
-    const uint32_t lane_base = s.tmem_d + ((uint32_t)(32 * (s.gtid >> 5)) << 16);     // M = 64: rows 16w..16w+15 live in lanes 32w..32w+15
-    uint32_t v0[16], v1[16];
-    mz_tc_ld16x256(lane_base, v0);
-    if (j1.layer >= 0) mz_tc_ld16x256(lane_base + 32u, v1);
-    mz_tc_wait_ld();
-    mz_tc_epilogue(s, P, j0, v0);
-    if (j1.layer >= 0) mz_tc_epilogue(s, P, j1, v1);
-    mz_fence_proxy_async();
-    mz_tc_fence_before();
-    mz_group_sync(s.grp);
-    s.q++;
+    return q;
 }
-__device__ __forceinline__ mz_tc_job mz_tc_mkjob(int layer, uint32_t src, uint32_t dst_tile, float *dst_f32) { mz_tc_job j; j.layer = layer; j.src = src; j.dst_tile = dst_tile; j.dst_f32 = dst_f32; return j; }
-__device__ __forceinline__ void mz_tc_chain(mz_tc_pipe &s, const mz_params &P, int first, int n, uint32_t src, float *dst_f32, uint32_t t0, uint32_t t1) {
-    uint32_t cur = src;
-    for (int i = 0; i < n; i++) {
-        const bool last = i == n - 1;
-        uint32_t d = (i & 1) ? t1 : t0;
-        mz_tc_round(s, P, mz_tc_mkjob(first + i, cur, last ? 0u : d, last ? dst_f32 : nullptr), mz_tc_mkjob(-1, 0u, 0u, nullptr));
-        cur = d;
+
+// ---- table construction (one thread, once per kernel) ------------------------------------------------------------
+struct mz_tc_builder { mz_tc_rdesc *prog; int n; uint32_t w_base, bias_base; };
+__device__ __forceinline__ void mz_tc_emit(mz_tc_builder &B, const mz_params &P, int l0, uint32_t src0, uint32_t dt0, uint32_t df0,
+                                           int l1, uint32_t src1, uint32_t dt1, uint32_t df1) {
+    mz_tc_rdesc &R = B.prog[B.n++];
+    const int ls[2] = {l0, l1}; const uint32_t srcs[2] = {src0, src1}, dts[2] = {dt0, dt1}, dfs[2] = {df0, df1};
+    R.njobs = l1 >= 0 ? 2 : 1; R.pad_ = 0;
+    for (int j = 0; j < 2; j++) {
+        const int l = ls[j] >= 0 ? ls[j] : l0;
+        R.adesc[j] = mz_tc_desc(B.w_base + (uint32_t)P.tc_a_off[l]); R.bdesc[j] = mz_tc_desc(srcs[j] ? srcs[j] : src0);
+        R.ks[j] = (int16_t)P.tc_ksteps[l]; R.out[j] = (int16_t)P.layers[l].out; R.act[j] = (int16_t)P.layers[l].act;
+        R.bias[j] = B.bias_base + (uint32_t)P.tc_bias_off[l] * 4u; R.dst_tile[j] = dts[j]; R.dst_f32[j] = dfs[j];
     }
 }
-// trunk -> bufT tile, then the two heads advance in lockstep, one round per depth level (head 2 may be at most two layers
-// deep: it has the single scratch tile tx); representation: the trunk's last layer -> h1dst
-__device__ __forceinline__ void mz_tc_net(mz_tc_pipe &s, const mz_params &P, int net, uint32_t src, uint32_t bufT, float *h1dst, float *h2dst,
-                                          uint32_t t0, uint32_t t1, uint32_t tx) {
+// rounds of one network: trunk -> bufT tile, then the two heads in lockstep (head 2 at most two layers deep: it has the
+// single scratch tile tx); representation: the trunk's last layer -> h1 (fp32).  Returns the number of rounds emitted.
+__device__ __forceinline__ int mz_tc_build_net(mz_tc_builder &B, const mz_params &P, int net, uint32_t src, uint32_t bufT, uint32_t h1dst, uint32_t h2dst,
+                                               uint32_t t0, uint32_t t1, uint32_t tx) {
     const mz_net &N = P.nets[net];
-    const int f = N.first;
-    if (N.n_h1 == 0) { mz_tc_chain(s, P, f, N.n_trunk, src, h1dst, t0, t1); return; }
+    const int f = N.first, n0 = B.n;
     uint32_t cur = src;
     for (int i = 0; i < N.n_trunk; i++) {
-        uint32_t d = (i == N.n_trunk - 1) ? bufT : ((i & 1) ? t1 : t0);
-        mz_tc_round(s, P, mz_tc_mkjob(f + i, cur, d, nullptr), mz_tc_mkjob(-1, 0u, 0u, nullptr));
+        const bool last = i == N.n_trunk - 1;
+        const uint32_t d = last ? bufT : ((i & 1) ? t1 : t0);
+        if (last && N.n_h1 == 0) mz_tc_emit(B, P, f + i, cur, 0u, h1dst, -1, 0u, 0u, 0u);
+        else mz_tc_emit(B, P, f + i, cur, d, 0u, -1, 0u, 0u, 0u);
         cur = d;
     }
+    if (N.n_h1 == 0) return B.n - n0;
     const int f1 = f + N.n_trunk, f2 = f1 + N.n_h1;
     if (N.n_h2 > 2 || N.n_h2 > N.n_h1) {   // general fallback: heads one after the other
-        mz_tc_chain(s, P, f1, N.n_h1, bufT, h1dst, t0, t1);
-        mz_tc_chain(s, P, f2, N.n_h2, bufT, h2dst, t0, t1);
-        return;
+        uint32_t c1 = bufT;
+        for (int i = 0; i < N.n_h1; i++) { const bool last = i == N.n_h1 - 1; const uint32_t d = (i & 1) ? t1 : t0; mz_tc_emit(B, P, f1 + i, c1, last ? 0u : d, last ? h1dst : 0u, -1, 0u, 0u, 0u); c1 = d; }
+        uint32_t c2 = bufT;
+        for (int i = 0; i < N.n_h2; i++) { const bool last = i == N.n_h2 - 1; const uint32_t d = (i & 1) ? t1 : t0; mz_tc_emit(B, P, f2 + i, c2, last ? 0u : d, last ? h2dst : 0u, -1, 0u, 0u, 0u); c2 = d; }
+        return B.n - n0;
     }
     uint32_t cur1 = bufT, cur2 = bufT;
     for (int i = 0; i < N.n_h1; i++) {
         const bool last1 = i == N.n_h1 - 1, has2 = i < N.n_h2, last2 = i == N.n_h2 - 1;
-        // when head 1 ends here its output is fp32, so its ping-pong tile of this round is free for head 2
         const uint32_t d1 = (i & 1) ? t1 : t0;
-        const uint32_t d2 = last1 ? d1 : tx;
-        mz_tc_round(s, P, mz_tc_mkjob(f1 + i, cur1, last1 ? 0u : d1, last1 ? h1dst : nullptr),
-                    has2 ? mz_tc_mkjob(f2 + i, cur2, last2 ? 0u : d2, last2 ? h2dst : nullptr) : mz_tc_mkjob(-1, 0u, 0u, nullptr));
+        const uint32_t d2 = last1 ? d1 : tx;     // when head 1 ends here its output is fp32, so its ping-pong tile is free for head 2
+        mz_tc_emit(B, P, f1 + i, cur1, last1 ? 0u : d1, last1 ? h1dst : 0u, has2 ? f2 + i : -1, cur2, (has2 && !last2) ? d2 : 0u, (has2 && last2) ? h2dst : 0u);
         cur1 = d1; cur2 = d2;
     }
+    return B.n - n0;
 }
 
 struct mz_tc_plan {
     uint32_t w_base; float *bias; uint64_t *mbar_w; uint64_t *mbar_mma[2]; uint32_t *tmem_slot;
     uint32_t inS, in0, in1, bufT[2], t0[2], t1[2];     // bf16 tiles (shared addresses)
     unsigned char *tiles_ptr;                          // generic pointer to inS (all 9 tiles are contiguous)
-    float *outV, *outL, *outR, *outH; double *pbc0, *sqrtN; uint16_t *path;
+    float *outV, *outL, *outR, *outH; double *pbc0, *sqrtN; uint16_t *path; mz_tc_rdesc *prog;
 };
 __host__ __device__ inline size_t mz_tc_smem_bytes(int image_bytes, int bias_floats, int hidden_pad, int S) {
     size_t w = ((size_t)image_bytes + 1023) & ~(size_t)1023;
@@ -207,7 +241,7 @@ __host__ __device__ inline size_t mz_tc_smem_bytes(int image_bytes, int bias_flo
     size_t tab = (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
     size_t path = (((size_t)S + 2) * 2 * MZ_ROWS + 127) & ~(size_t)127;
     size_t bias = ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
-    return 1024 + w + 9 * MZ_TC_TILE_BYTES + bias + 128 + small + tab + path + 128;
+    return 1024 + w + 9 * MZ_TC_TILE_BYTES + bias + 128 + small + tab + path + MZ_TC_MAX_ROUNDS * sizeof(mz_tc_rdesc) + 128;
 }
 __device__ __forceinline__ mz_tc_plan mz_tc_carve(unsigned char *raw, int image_bytes, int bias_floats, int hidden_pad, int S) {
     mz_tc_plan p;
@@ -226,6 +260,7 @@ __device__ __forceinline__ mz_tc_plan mz_tc_carve(unsigned char *raw, int image_
     p.outR = (float *)c; c += 4 * MZ_ROWS * 4;
     p.outH = (float *)c; c += (size_t)hidden_pad * MZ_ROWS * 4;
     p.pbc0 = (double *)c; p.sqrtN = p.pbc0 + (S + 2); c += (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
-    p.path = (uint16_t *)c;
+    p.path = (uint16_t *)c; c += (((size_t)S + 2) * 2 * MZ_ROWS + 127) & ~(size_t)127;
+    p.prog = (mz_tc_rdesc *)c;
     return p;
 }

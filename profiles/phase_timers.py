@@ -12,11 +12,17 @@ for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_
     ctx.init_weights(1337)
     ctx.self_play(0, G, 1.0)
     sims, moves = ctx.self_play(G, G, 1.0)
-    pc = ctx.phase_cycles().astype(float)
+    raw = ctx.phase_cycles().astype(float)
+    pc = raw[:12].reshape(2, 6)
     for g, who in ((0, "thread 0 (tree lane / prediction group)"), (1, "thread 128 (dynamics group)")):
         n = pc[g, 5]; rounds = n * S
         if n == 0:
             print(label, who, "no timers in this build"); continue
         tot = pc[g, :5].sum()
         print("%s %s: %.0f cycles/round; " % (label, who, tot / rounds) + ", ".join("%s %.0f (%.0f%%)" % (names[i], pc[g, i] / rounds, 100 * pc[g, i] / tot) for i in range(5)))
+    for o, who in ((12, 'issuing thread, group 0'), (20, 'epilogue thread, group 1')):
+        q = raw[o + 6]
+        if q > 0:
+            lab = ['issue', 'mbarrier wait', 'tcgen05.ld', 'epilogue', 'fence.proxy.async', 'group barrier']
+            print('%s TC round (%s): %.0f cycles; ' % (label, who, raw[o:o + 6].sum() / q) + ', '.join('%s %.0f' % (lab[i], raw[o + i] / q) for i in range(6)))
     ctx.close()
