@@ -67,7 +67,7 @@ for r in rows[hi + 1:]:
         if s.startswith("stall_") and "Not Issued" not in s and r[col[s]] not in ("", "0"):
             stall[key][s[6:]] += int(r[col[s]]); st_tot[s[6:]] += int(r[col[s]])
 src = {}
-for f in os.listdir(os.path.join(ROOT, "muzero.jl_b200", "csrc")):
+for f in [x for x in os.listdir(os.path.join(ROOT, "muzero.jl_b200", "csrc")) if os.path.isfile(os.path.join(ROOT, "muzero.jl_b200", "csrc", x))]:
     src[f] = open(os.path.join(ROOT, "muzero.jl_b200", "csrc", f), errors="replace").read().split("\n")
 lines.append("")
 lines.append("warp-stall samples (total %d): %s" % (tot, ", ".join("%s %.1f%%" % (k, 100.0 * v / max(tot, 1)) for k, v in st_tot.most_common(8))))
