@@ -178,11 +178,17 @@ def run_b200(a):
     flush = torch.empty(384 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
     game_base = rank * (10 ** 7)
 
+    host_hist = ctx.history_buffers(G, pinned=True)                       # page-locked host buffers of the end-to-end leg
+    host_blob = torch.from_numpy(blob).pin_memory().numpy()
+
     def wave(i, e2e=False):
         if e2e:
-            ctx.set_weights(blob)
+            ctx.set_weights(host_blob)                                      # what self_play! receives through remote_NNs
         sims, moves = ctx.self_play(game_base + i * G, G, 1.0)
-        hist = ctx.history_export(n=G, key0=ctx.replay_info()["first_key"] + ctx.replay_info()["n_games"] - G) if e2e else None
+        hist = None
+        if e2e:                                                             # what save_game ships: every GameHistory of the wave
+            info = ctx.replay_info()
+            hist = ctx.history_export(key0=info["first_key"] + info["n_games"] - G, n=G, out=host_hist)
         return sims, moves, hist
 
     with torch.cuda.stream(stream):

@@ -282,15 +282,24 @@ class Context:
     def replay_clear(self):
         self._ck(self.L.mz_replay_clear(self._h))
 
-    def history_export(self, key0=None, n=None):
-        info = self.replay_info()
-        key0 = info["first_key"] if key0 is None else key0
-        n = info["n_games"] - (key0 - info["first_key"]) if n is None else n
+    def history_buffers(self, n, pinned=False):
+        """Caller-owned output arrays for history_export (optionally page-locked through torch, for repeated exports)."""
         s = self.s
-        out = dict(game_id=np.zeros(n, np.int64), T=np.zeros(n, np.int32), obs=np.zeros((n, s["Tmax"], s["obs"]), np.float32),
-                   actions=np.zeros((n, s["Tmax"]), np.int32), rewards=np.zeros((n, s["Tmax"]), np.float32),
-                   to_play=np.zeros((n, s["Tmax"]), np.int32), child_visits=np.zeros((n, s["Tmax"], s["A"]), np.float32),
-                   root_values=np.zeros((n, s["Tmax"]), np.float32))
+        shapes = dict(game_id=((n,), np.int64), T=((n,), np.int32), obs=((n, s["Tmax"], s["obs"]), np.float32),
+                      actions=((n, s["Tmax"]), np.int32), rewards=((n, s["Tmax"]), np.float32), to_play=((n, s["Tmax"]), np.int32),
+                      child_visits=((n, s["Tmax"], s["A"]), np.float32), root_values=((n, s["Tmax"]), np.float32))
+        if pinned:
+            import torch
+            return {k: torch.zeros(shp, dtype=getattr(torch, np.dtype(dt).name), pin_memory=True).numpy() for k, (shp, dt) in shapes.items()}
+        return {k: np.zeros(shp, dt) for k, (shp, dt) in shapes.items()}
+
+    def history_export(self, key0=None, n=None, out=None):
+        if key0 is None or n is None:
+            info = self.replay_info()
+            key0 = info["first_key"] if key0 is None else key0
+            n = info["n_games"] - (key0 - info["first_key"]) if n is None else n
+        if out is None:
+            out = self.history_buffers(n)
         self._ck(self.L.mz_history_export(self._h, key0, n, _p(out["game_id"], C.c_int64), _p(out["T"], C.c_int32), _p(out["obs"], C.c_float),
                                           _p(out["actions"], C.c_int32), _p(out["rewards"], C.c_float), _p(out["to_play"], C.c_int32),
                                           _p(out["child_visits"], C.c_float), _p(out["root_values"], C.c_float)))

@@ -131,7 +131,7 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
     std::vector<float> dev((size_t)c->M.P.total_floats);
     mzh::pack_weights(c->M.P, src.data(), dev.data());
     MZ_CUDA(c, cudaMemcpyAsync(c->d_w, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (c->d_w_tc) {   // bf16 pre-swizzled A-operand image + fp32 biases for the tcgen05 path
+    if (c->d_w_tc && c->cfg.nn_mode == MZ_NN_BF16_TC) {   // bf16 pre-swizzled A-operand image + fp32 biases for the tcgen05 path
         std::vector<uint16_t> image; std::vector<float> bias;
         mzh::pack_weights_tc(c->M.P, src.data(), image, bias);
         MZ_CUDA(c, cudaMemcpyAsync(c->d_w_tc, image.data(), image.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
@@ -350,8 +350,8 @@ int mz_set_weights(mz_ctx *c, int net, const float *blob, int64_t n) {
     if (net < 0 || net > 3 || !blob) return fail(c, MZ_E_ARG, "bad net id or NULL blob");
     if (n != mzh::net_params(c->M.P, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, mzh::net_params(c->M.P, net));
     std::vector<float> src;
-    MZ_TRY(download_weights(c, src));
-    memcpy(src.data() + mzh::net_src_offset(c->M.P, net), blob, (size_t)n * sizeof(float));
+    if (net == MZ_NET_ALL) src.assign(blob, blob + n);                    // whole model: nothing to merge with
+    else { MZ_TRY(download_weights(c, src)); memcpy(src.data() + mzh::net_src_offset(c->M.P, net), blob, (size_t)n * sizeof(float)); }
     return upload_weights(c, src);
 }
 int mz_get_weights(mz_ctx *c, int net, float *blob, int64_t n) {
