@@ -1,0 +1,94 @@
+"""GPU tests of the reference-facing Python mirror (muzero.jl_b200/api.py): the call sequence a user of the reference
+would write -- Config / FeedForwardHP -> init networks -> run_mcts / play_game / self_play! -> get_batch -> learning! --
+checked against the oracle.  Also error behaviour of the C ABI."""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mz():
+    import muzero_jl_b200 as mz
+    return mz
+
+
+def test_reference_call_sequence(mz):
+    conf = mz.Config(num_iters=10, exploration_ϵ=0.0)
+    hyper = mz.FeedForwardHP()
+    eng = mz.Engine(conf, hyper, num_slots=64)
+    NNs = mz.init_networks(eng, seed=1337)
+    ocfg = common.oracle_config(eng.ctx.cfg)
+    blob = eng.ctx.get_weights()
+    # environment verbs (games/tictactoe/game.jl) and KAT-env-1
+    env = mz.TicTacToe(eng)
+    obs = env.reset()
+    assert obs.shape == (3, 3, 3) and obs[2].all() and not obs[:2].any() and env.current_player() == 1
+    for a in (1, 2, 4, 5, 7):
+        env(a)
+    assert env.legal_action_space() == [3, 6, 8, 9] and not env.is_terminated()
+    env(3)
+    assert env.is_terminated() and env.legal_action_space() == []
+    # NNs callables: shapes of the Flux chains
+    st = np.zeros((1, 63), np.float32); st[0, 18:27] = 1
+    h = NNs["representation"](st); v, p = NNs["prediction"](h)
+    assert h.shape == (1, 27) and p.shape == (1, 9) and abs(p.sum() - 1) < 1e-6
+    # run_mcts + select_action
+    root = mz.run_mcts(eng, st[0], list(range(1, 10)), 1, True, game_id=5, move_idx=1)
+    ovc, orv, opri = O.run_mcts(ocfg, blob, st[0], 0x1ff, 1, True, 5, 1)
+    assert root.visit_counts.tolist() == ovc.tolist() and root.value == orv and np.array_equal(root.priors, opri)
+    assert mz.select_action(eng, root, 0.0, 5, 1) == O.select_action(ocfg, ovc, 0x1ff, 0.0, 5, 1)
+    with pytest.raises(AssertionError):
+        mz.run_mcts(eng, st[0], [], 1)                        # SelfPlay.jl:243
+    # play_game / self_play! / save_game / get_batch / learning!
+    hist = mz.play_game(eng, 1.0, False, "self", 1)
+    o = O.self_play(ocfg, blob, 0, 1, 1.0, 1)
+    T = int(o["T"][0])
+    assert hist.action_history.tolist() == o["actions"][0, :T].tolist() and np.array_equal(hist.child_visits, o["child_visits"][0, :T])
+    assert hist.observation_history.shape == (T, 3, 3, 3)
+    sims, moves = mz.self_play(eng, 40, temperature=1.0)
+    assert sims == moves * 10 and len(mz.ReplayBuffer(eng)) == 41
+    mz.save_game(eng, hist, game_id=999)                       # a host-built history goes through the same ring
+    assert len(mz.ReplayBuffer(eng)) == 42 and mz.ReplayBuffer(eng)[42].action_history.tolist() == hist.action_history.tolist()
+    index_batch, (obs_b, act_b, val_b, rew_b, pol_b, w_b, gs_b) = mz.get_batch(eng)
+    assert len(index_batch) == 32 and obs_b.shape == (32, 63) and pol_b.shape == (32, 6, 9) and w_b is None
+    losses = mz.learning(eng, 3)
+    assert eng.training_step == 3 and np.all(np.isfinite(losses))
+    eng.close()
+
+
+def test_error_behaviour(mz):
+    capi = mz.capi
+    ctx = capi.Context(capi.default_config(num_slots=32, replay_buffer_size=64))
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.learn_step(1)                                      # empty buffer (Learning.jl:311 waits; the ABI reports)
+    assert e.value.code == capi.E_STATE
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.set_weights(np.zeros(10, np.float32))
+    assert e.value.code == capi.E_ARG
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.env_step(*ctx.env_reset(2), [0, 10])               # actions out of range
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.learn_step(1, grad_mode=capi.GRAD_BPTT, batch=None)
+    with pytest.raises(capi.MuZeroB200Error):
+        capi.Context(capi.default_config(num_slots=64, replay_buffer_size=32))   # ring smaller than the slot count
+    ctx.close()
+
+
+def test_two_contexts_are_independent(mz):
+    capi = mz.capi
+    a = capi.Context(capi.default_config(num_slots=32, replay_buffer_size=64, num_iters=8))
+    b = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=64, num_iters=20, exploration_eps=0.0))
+    a.init_weights(1); b.init_weights(2)
+    a.self_play(0, 40, 1.0); b.self_play(0, 40, 1.0)
+    ha, hb = a.history_export(), b.history_export()
+    oa = O.self_play(common.oracle_config(a.cfg), a.get_weights(), 0, 40, 1.0, 2)
+    ob = O.self_play(common.oracle_config(b.cfg), b.get_weights(), 0, 40, 1.0, 2)
+    for h, o in ((ha, oa), (hb, ob)):
+        order = np.argsort(h["game_id"])
+        assert np.array_equal(h["actions"][order], o["actions"]) and np.array_equal(h["root_values"][order], o["root_values"])
+    assert a.launch_count() > 0 and a.kernel_time(0)[1] == 0   # timers are off by default
+    a.close(); b.close()
