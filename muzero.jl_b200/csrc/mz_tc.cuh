@@ -33,6 +33,11 @@ __device__ __forceinline__ void mz_tc_mma(uint32_t tmem_d, uint64_t adesc, uint6
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(MZ_TC_IDESC), "r"(accumulate), "r"(0u) : "memory");
 }
+__device__ __forceinline__ bool mz_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mz_tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(bar)) : "memory");
 }
@@ -143,14 +148,20 @@ __device__ __noinline__ uint32_t mz_tc_run(const mz_tc_rdesc *prog, int first, i
         const mz_tc_rdesc *R = prog + r;
         const int njobs = R->njobs;
         MZ_RT(0);
-        if (gtid == 0) {
+        if (w == 0) {   // warp-uniform branch + elect.sync: the MMA operands stay in uniform registers (no per-lane waterfall loop)
             mz_tc_fence_after();
-            for (int j = 0; j < njobs; j++) {
-                const uint64_t ad = R->adesc[j], bd = R->bdesc[j];
-                const int ks = R->ks[j];
-                for (int k = 0; k < ks; k++) mz_tc_mma(tmem_d + 32u * (uint32_t)j, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+            const uint64_t ad0 = R->adesc[0], bd0 = R->bdesc[0], ad1 = R->adesc[1], bd1 = R->bdesc[1];
+            if (mz_elect_one()) {
+                // always 4 K-steps: operand tiles are zero-filled beyond a layer's real K, so the extra steps add exact zeros
+#pragma unroll
+                for (int k = 0; k < 4; k++) mz_tc_mma(tmem_d, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), k > 0 ? 1u : 0u);   // +32 B per K=16 step
+                if (njobs > 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) mz_tc_mma(tmem_d + 32u, ad1 + (uint64_t)(2 * k), bd1 + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+            __syncwarp();
         }
         MZ_RT(1);
         {
