@@ -159,7 +159,7 @@ int mz_kernel_time_reset(mz_ctx *ctx, int enable);
 /* phase timers of the last mz_self_play call (profiling builds with -DMZ_PHASE_TIMERS, zeros otherwise):
  * out[6*g + p] = clock cycles summed over CTAs, g = 0 prediction group / tree lane 0, g = 1 dynamics group,
  * p = 0 select+stage, 1 wait, 2 network, 3 wait, 4 expand+backup, 5 = number of CTAs that reported */
-int mz_phase_cycles(mz_ctx *ctx, uint64_t out[28]);   /* [12..27]: per-round timers of the tensor-core layer routine */
+int mz_phase_cycles(mz_ctx *ctx, uint64_t out[60]);   /* raw profiling counters, see profiles/phase_timers.py */
 /* tree statistics of the last mz_self_play call: mean legal actions L and mean selection depth d */
 int mz_search_stats(mz_ctx *ctx, double *mean_legal, double *mean_depth);
 

@@ -377,7 +377,7 @@ class Context:
         return ms.value, n.value
 
     def phase_cycles(self):
-        out = np.zeros(28, np.uint64)
+        out = np.zeros(60, np.uint64)
         self._ck(self.L.mz_phase_cycles(self._h, _p(out, C.c_uint64)))
         return out
 

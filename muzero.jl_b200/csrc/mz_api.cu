@@ -286,11 +286,11 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(dmalloc(&r.h_reward, R * Tm)); MZ_CREATE(dmalloc(&r.h_to_play, R * Tm)); MZ_CREATE(dmalloc(&r.h_cv, R * Tm * P.A)); MZ_CREATE(dmalloc(&r.h_rv, R * Tm));
     MZ_CREATE(dmalloc(&r.counters, 8)); MZ_CREATE(cudaMemset(r.counters, 0, 8 * sizeof(int64_t)));
     MZ_CREATE(cudaMemset(r.T, 0, R * sizeof(int32_t)));
-    MZ_CREATE(dmalloc(&c->d_stats, 32)); MZ_CREATE(cudaMemset(c->d_stats, 0, 32 * sizeof(unsigned long long)));
+    MZ_CREATE(dmalloc(&c->d_stats, 64)); MZ_CREATE(cudaMemset(c->d_stats, 0, 64 * sizeof(unsigned long long)));
     MZ_CREATE(dmalloc(&c->d_lossout, 8));
     MZ_CREATE(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(int64_t)));
     MZ_CREATE(cudaMallocHost((void **)&c->h_lossout, 8 * sizeof(double)));
-    MZ_CREATE(cudaMallocHost((void **)&c->h_stats, 32 * sizeof(unsigned long long)));
+    MZ_CREATE(cudaMallocHost((void **)&c->h_stats, 64 * sizeof(unsigned long long)));
     MZ_CREATE(cudaDeviceSynchronize());
 #undef MZ_CREATE
     *out = c;
@@ -514,7 +514,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
     if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "previous self-play did not finish");
     c->h_counters[3] = (int64_t)first_game; c->h_counters[4] = (int64_t)first_game + n_games; c->h_counters[5] = 0;
     MZ_TRY(write_counters(c));
-    MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 32 * sizeof(unsigned long long), c->stream));
+    MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 64 * sizeof(unsigned long long), c->stream));
     mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = G; a.max_dim = c->M.max_dim;
     a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
     a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;
@@ -533,7 +533,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
     }
-    MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     if (simulations) *simulations = (int64_t)c->h_stats[1];
     if (moves) *moves = total_moves;
@@ -730,9 +730,9 @@ int mz_kernel_time(mz_ctx *c, int family, double *ms, int64_t *launches) {
     if (launches) *launches = c->fam_n[family];
     return MZ_OK;
 }
-int mz_phase_cycles(mz_ctx *c, uint64_t out[28]) {   // only meaningful in a -DMZ_PHASE_TIMERS build
+int mz_phase_cycles(mz_ctx *c, uint64_t out[60]) {   // only meaningful in a -DMZ_PHASE_TIMERS build
     if (!c || !out) return fail(c, MZ_E_ARG, "NULL");
-    for (int i = 0; i < 28; i++) out[i] = (uint64_t)c->h_stats[4 + i];
+    for (int i = 0; i < 60; i++) out[i] = (uint64_t)c->h_stats[4 + i];
     return MZ_OK;
 }
 int mz_search_stats(mz_ctx *c, double *mean_legal, double *mean_depth) {

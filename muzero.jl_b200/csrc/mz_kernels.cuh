@@ -19,10 +19,10 @@ enum { MZ_MODE_API = 0, MZ_MODE_SLOTS = 1 };
 // group) of every CTA accumulate clock64() deltas of the simulation loop into stats[4 + 6*g + phase]:
 // 0->1 select+stage, 1->2 wait, 2->3 network, 3->4 wait, 4->5 expand+backup.  Compiled out of the product build.
 #ifdef MZ_PHASE_TIMERS
-#define MZ_TIMER_DECL long long mz_tk[6] = {0, 0, 0, 0, 0, 0}; long long mz_acc[5] = {0, 0, 0, 0, 0}
-#define MZ_TIMER(i) do { mz_tk[i] = clock64(); if ((i) > 0) mz_acc[(i) - 1] += mz_tk[i] - mz_tk[(i) - 1]; } while (0)
+#define MZ_TIMER_DECL long long mz_tk[1] = {0}; long long mz_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define MZ_TIMER(i) do { long long c_ = clock64(); if ((i) > 0) mz_acc[(i) - 1] += c_ - mz_tk[0]; mz_tk[0] = c_; } while (0)
 #define MZ_TIMER_FLUSH(stats) do { if ((stats) && (threadIdx.x == 0 || threadIdx.x == MZ_GROUP)) { int g_ = threadIdx.x ? 1 : 0; \
-    for (int i_ = 0; i_ < 5; i_++) atomicAdd(&(stats)[4 + 6 * g_ + i_], (unsigned long long)mz_acc[i_]); atomicAdd(&(stats)[4 + 6 * g_ + 5], 1ull); } } while (0)
+    for (int i_ = 0; i_ < 8; i_++) atomicAdd(&(stats)[32 + 9 * g_ + i_], (unsigned long long)mz_acc[i_]); atomicAdd(&(stats)[32 + 9 * g_ + 8], 1ull); } } while (0)
 #else
 #define MZ_TIMER_DECL
 #define MZ_TIMER(i)
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
         if (active) {
             leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
+            MZ_TIMER(1);
             const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
             const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);                       // 2^dbl: state after dbl in-place doublings (Q6)
@@ -275,21 +276,23 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
             __syncwarp(segmask);
             if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
-        MZ_TIMER(1);
-        __syncthreads();
         MZ_TIMER(2);
+        __syncthreads();
+        MZ_TIMER(3);
         if (pipe.grp == 0) mz_nn_net(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
         else               mz_nn_net(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
-        MZ_TIMER(3);
-        __syncthreads();
         MZ_TIMER(4);
+        __syncthreads();
+        MZ_TIMER(5);
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
+            MZ_TIMER(6);
             mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], leaf.prior, ln, segmask);   // :280 (root's legal set, Q7)
+            MZ_TIMER(7);
             mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);                  // :281
         }
-        MZ_TIMER(5);
+        MZ_TIMER(8);
         // no CTA barrier needed here: the lanes that stage the next inputs are the ones that just read the outputs, and
         // every network read of in0/in1 finished before the barrier above
     }

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         if (active) {
             leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
+            MZ_TIMER(1);
             const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
             const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);
@@ -150,21 +151,23 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
             if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
         mz_fence_proxy_async();
-        MZ_TIMER(1);
-        __syncthreads();
         MZ_TIMER(2);
+        __syncthreads();
+        MZ_TIMER(3);
         if (grp == 0) q = mz_tc_run(sp.prog, n_repr, n_pred, tmem_d, mbar_mma, q, grp, gtid, tk);
         else          q = mz_tc_run(sp.prog, n_repr + n_pred, n_dyn, tmem_d, mbar_mma, q, grp, gtid, tk);
-        MZ_TIMER(3);
-        __syncthreads();
         MZ_TIMER(4);
+        __syncthreads();
+        MZ_TIMER(5);
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
+            MZ_TIMER(6);
             mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, sp.outR[r], leaf.prior, ln, segmask);
+            MZ_TIMER(7);
             mz_tree_backup_lanes(P, tree, path, leaf.depth, sp.outV[r], mm, ln, segmask);
         }
-        MZ_TIMER(5);
+        MZ_TIMER(8);
     }
 
     MZ_TIMER_FLUSH(a.stats);

@@ -6,20 +6,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from muzero_jl_b200 import capi
 
 G, S = 4096, 50
-names = ["select+stage", "wait", "network", "wait", "expand+backup"]
+names = ["select", "stage", "-", "network(+wait)", "-", "hidden write(+wait)", "expand", "backup"]
 for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_tcgen05")):
     ctx = capi.Context(capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=10000, nn_mode=mode))
     ctx.init_weights(1337)
     ctx.self_play(0, G, 1.0)
     sims, moves = ctx.self_play(G, G, 1.0)
     raw = ctx.phase_cycles().astype(float)
-    pc = raw[:12].reshape(2, 6)
+    pc = raw[28:46].reshape(2, 9)
     for g, who in ((0, "thread 0 (tree lane / prediction group)"), (1, "thread 128 (dynamics group)")):
-        n = pc[g, 5]; rounds = n * S
+        n = pc[g, 8]; rounds = n * S
         if n == 0:
             print(label, who, "no timers in this build"); continue
-        tot = pc[g, :5].sum()
-        print("%s %s: %.0f cycles/round; " % (label, who, tot / rounds) + ", ".join("%s %.0f (%.0f%%)" % (names[i], pc[g, i] / rounds, 100 * pc[g, i] / tot) for i in range(5)))
+        tot = pc[g, :8].sum()
+        print("%s %s: %.0f cycles/round; " % (label, who, tot / rounds) + ", ".join("%s %.0f" % (names[i], pc[g, i] / rounds) for i in range(8) if names[i] != "-"))
     for o, who in ((12, 'issuing thread, group 0'), (20, 'epilogue thread, group 1')):
         q = raw[o + 6]
         if q > 0:
