@@ -256,12 +256,28 @@ def run_b200(a):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for t in range(4, 4 + a.learner_steps):
-                losses = ctx.learn_step(t)
+            losses = ctx.learn_steps(4, a.learner_steps)                    # get_batch gather + unroll + loss + grads (+ allreduce) + ADAM, per step
             e1.record(stream); e1.synchronize()
             lms = e0.elapsed_time(e1)
             learner = {"batch_per_gpu": cfg.batch_size, "grad_mode": "reference_l2", "ms_per_step": lms / a.learner_steps,
                        "losses": [float(x) for x in losses]}
+            # the same learner at a throughput-sized batch (the reference's batch_size is 32, params.jl:14)
+            big = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=max(10000, G), batch_size=4096), device=local, stream=stream.cuda_stream)
+            big.set_weights(blob)
+            info = ctx.replay_info()
+            n_imp = min(info["n_games"], 4096)
+            big.history_import(ctx.history_export(key0=info["first_key"] + info["n_games"] - n_imp, n=n_imp))
+            if world > 1:
+                from muzero_jl_b200 import dist as mzdist
+                mzdist.attach_communicator(big, rank, world, device="cuda")
+            big.learn_steps(1, 3)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            big.learn_steps(4, a.learner_steps)
+            e1.record(stream); e1.synchronize()
+            learner["large_batch"] = {"batch_per_gpu": 4096, "ms_per_step": e0.elapsed_time(e1) / a.learner_steps}
+            big.close()
 
     t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0], dtype=torch.float64, device="cuda")
     cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0], dtype=torch.float64, device="cuda")
@@ -314,6 +330,7 @@ def run_b200(a):
                                           "oracle to bf16 tolerance, not bit-exactly, so the headline value is the exact-fp32 path"}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
+            learner["large_batch"]["samples_per_s"] = 4096 * world / (learner["large_batch"]["ms_per_step"] * 1e-3)
             out["learner"] = learner
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(ocfg, blob, a.cpu_seconds)

@@ -137,6 +137,8 @@ int mz_learn_forward(mz_ctx *ctx, int B, const float *obs_batch, const float *ac
 /* one training step t (1-based): get_batch(step=t) on the device ring, unroll, loss, gradients (grad_mode),
  * gradient allreduce when a communicator is attached, ADAM with the Cos schedule (Learning.jl:382-397) */
 int mz_learn_step(mz_ctx *ctx, int64_t t, int grad_mode, float *losses /* [3] */);
+/* n consecutive iterations t0 .. t0+n-1 queued back to back (no host round trip in between); losses of the last one */
+int mz_learn_steps(mz_ctx *ctx, int64_t t0, int n, int grad_mode, float *losses /* [3] */);
 /* same update on a caller-supplied batch (parity entry point) */
 int mz_learn_step_batch(mz_ctx *ctx, int64_t t, int grad_mode, int B, const float *obs_batch, const float *action_batch,
                         const float *value_batch, const float *reward_batch, const float *policy_batch,

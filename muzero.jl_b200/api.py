@@ -282,9 +282,12 @@ def learning(engine: Engine, steps: int, grad_mode=capi.GRAD_REFERENCE_L2, log_e
     if len(ReplayBuffer(engine)) < 1:
         raise RuntimeError("replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)")
     losses = None
-    for _ in range(steps):
-        engine.training_step += 1
-        losses = engine.ctx.learn_step(engine.training_step, grad_mode)
-        if log_every and engine.training_step % log_every == 0:
+    chunk = log_every if log_every else steps          # losses are only read back when they are reported (Learning.jl:416-424)
+    done = 0
+    while done < steps:
+        n = min(chunk, steps - done)
+        losses = engine.ctx.learn_steps(engine.training_step + 1, n, grad_mode)
+        engine.training_step += n; done += n
+        if log_every:
             print("Training Progress", engine.training_step, losses)
     return losses

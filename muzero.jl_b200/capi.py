@@ -102,6 +102,7 @@ def lib():
         "mz_get_batch": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
         "mz_learn_forward": ([ctx, C.c_int] + [f32p] * 10, C.c_int),
         "mz_learn_step": ([ctx, C.c_int64, C.c_int, f32p], C.c_int),
+        "mz_learn_steps": ([ctx, C.c_int64, C.c_int, C.c_int, f32p], C.c_int),
         "mz_learn_step_batch": ([ctx, C.c_int64, C.c_int, C.c_int] + [f32p] * 7, C.c_int),
         "mz_optimizer_reset": ([ctx], C.c_int),
         "mz_comm_unique_id": ([u8p], C.c_int),
@@ -343,6 +344,11 @@ class Context:
         else:
             arrs, ptrs = self._batch_ptrs(batch)
             self._ck(self.L.mz_learn_step_batch(self._h, t, grad_mode, arrs[0].shape[0], *ptrs, _p(losses, C.c_float)))
+        return losses
+
+    def learn_steps(self, t0, n, grad_mode=GRAD_REFERENCE_L2):
+        losses = np.zeros(3, np.float32)
+        self._ck(self.L.mz_learn_steps(self._h, t0, n, grad_mode, _p(losses, C.c_float)))
         return losses
 
     def optimizer_reset(self):

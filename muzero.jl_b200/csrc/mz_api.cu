@@ -677,6 +677,23 @@ int mz_learn_step(mz_ctx *c, int64_t t, int grad_mode, float *losses) {
     MZ_TRY(launch_update(c, t, grad_mode));
     return finish_losses(c, c->cfg.batch_size, losses);
 }
+// n consecutive learning! iterations (steps t0 .. t0+n-1) without a host round trip in between: the replay gather of
+// step t+1 is queued behind the ADAM update of step t on the same stream; only the last step's losses are read back
+// (the reference logs them every checkpoint_interval steps, Learning.jl:416-424).
+int mz_learn_steps(mz_ctx *c, int64_t t0, int n, int grad_mode, float *losses) {
+    MZ_CHECK_CTX(c);
+    if (!losses || t0 < 1 || n < 1) return fail(c, MZ_E_ARG, "bad arguments");
+    const int B = c->cfg.batch_size;
+    MZ_TRY(alloc_batch(c, B));
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[0] < 1) return fail(c, MZ_E_STATE, "replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)");
+    for (int i = 0; i < n; i++) {
+        { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, (uint64_t)(t0 + i), B, c->batch); }
+        MZ_TRY(launch_learn_forward(c, B));
+        MZ_TRY(launch_update(c, t0 + i, grad_mode));
+    }
+    return finish_losses(c, B, losses);
+}
 int mz_optimizer_reset(mz_ctx *c) {
     MZ_CHECK_CTX(c);
     MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)c->M.P.total_floats * 4, c->stream));

@@ -160,10 +160,8 @@ end
 "`steps` iterations of get_batch -> unroll -> loss -> gradients -> ADAM(Cos schedule); returns the last three losses."
 function learning!(e::Engine, steps::Integer; grad_mode::Integer=0)
     losses = zeros(Float32, 3)
-    for _ in 1:steps
-        e.training_step += 1
-        check(e, ccall((:mz_learn_step, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Float32}), e.ctx, e.training_step, grad_mode, losses))
-    end
+    check(e, ccall((:mz_learn_steps, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float32}), e.ctx, e.training_step + 1, steps, grad_mode, losses))
+    e.training_step += steps
     return (l_representation=losses[1], l_prediction=losses[2], l_dynamics=losses[3])
 end
 

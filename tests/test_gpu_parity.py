@@ -314,3 +314,17 @@ def test_tc_self_play_is_well_formed(capi):
         T = h["T"][j]
         assert np.allclose(h["child_visits"][j, :T].sum(1), 1.0, atol=1e-6) and np.all(h["rewards"][j, :T - 1] == 0)
     ctx.close()
+
+
+def test_learn_steps_equals_repeated_learn_step(capi):
+    ws = []
+    for fused in (False, True):
+        ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=128)
+        ctx.init_weights(21); ctx.self_play(0, 64, 1.0)
+        if fused:
+            losses = ctx.learn_steps(1, 7)
+        else:
+            for t in range(1, 8):
+                losses = ctx.learn_step(t)
+        ws.append((ctx.get_weights(), losses)); ctx.close()
+    assert np.array_equal(ws[0][0], ws[1][0]) and np.allclose(ws[0][1], ws[1][1], rtol=LOSS_RTOL)
