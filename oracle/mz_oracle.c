@@ -881,6 +881,173 @@ static void adam_update(float *theta, float *m, float *v, const float *grad, int
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * grad_mode = MZO_GRAD_BPTT: the gradient of the reference's OWN loss value (Learning.jl:261-288, with
+ * Q19's unroll order and Q21's policy-term broadcast) taken through the reference's own forward unroll
+ * (:347-374) -- what Zygote.pullback would return had the predictions been computed inside the closure
+ * (Q20 explains why the reference's actual gradient degenerates to 2*theta).  Every parameter array gets
+ * d(data loss)/d(theta) + 2*theta (each net's loss adds its own sum(abs2, theta), :287).
+ *
+ * The backward arithmetic is Float64.  The forward activations it linearises around are either the
+ * Float32 contract's (fwd64 = 0: identical relu masks to the CUDA path) or an all-Float64 forward
+ * (fwd64 = 1: used by the finite-difference check of the formulae, tests/test_oracle_kat.py).
+ * ------------------------------------------------------------------------------------------ */
+#define BP_MAXW 256
+typedef struct { double in[BP_MAXW]; double out[24][BP_MAXW]; } chain_act_t;
+typedef struct { chain_act_t trunk, h1, h2; } net_act_t;
+
+static void dense_fwd(const float *blob, const double *wd, const layer_t *l, const double *x, double *y, int fwd64) {
+    if (fwd64) {
+        for (int o = 0; o < l->out; o++) {
+            double acc = 0.0;
+            for (int k = 0; k < l->in; k++) acc += wd[l->w_off + o + (size_t)l->out * k] * x[k];
+            acc += wd[l->b_off + o];
+            y[o] = l->act == ACT_RELU ? (acc > 0.0 ? acc : 0.0) : l->act == ACT_TANH ? tanh(acc) : acc;
+        }
+    } else {
+        float xf[BP_MAXW], yf[BP_MAXW];
+        for (int k = 0; k < l->in; k++) xf[k] = (float)x[k];
+        dense(blob, l, xf, yf);
+        for (int o = 0; o < l->out; o++) y[o] = (double)yf[o];
+    }
+}
+static void chain_fwd(const float *blob, const double *wd, const layer_t *ls, int n, const double *x, chain_act_t *a, int fwd64) {
+    for (int k = 0; k < ls[0].in; k++) a->in[k] = x[k];
+    const double *cur = a->in;
+    for (int l = 0; l < n; l++) { dense_fwd(blob, wd, &ls[l], cur, a->out[l], fwd64); cur = a->out[l]; }
+}
+/* dy = gradient w.r.t. the post-activation output of the chain's last layer; G accumulates dW (blob order) and db;
+ * dx (may be NULL) receives the gradient w.r.t. the chain input. */
+static void chain_bwd(const double *wd, double *G, const layer_t *ls, int n, const chain_act_t *a, const double *dy, double *dx) {
+    double cur[BP_MAXW], nxt[BP_MAXW];
+    for (int o = 0; o < ls[n - 1].out; o++) cur[o] = dy[o];
+    for (int l = n - 1; l >= 0; l--) {
+        const layer_t *L = &ls[l];
+        const double *y = a->out[l], *x = l ? a->out[l - 1] : a->in;
+        for (int o = 0; o < L->out; o++) {
+            double d = L->act == ACT_RELU ? (y[o] > 0.0 ? 1.0 : 0.0) : L->act == ACT_TANH ? 1.0 - y[o] * y[o] : 1.0;
+            cur[o] *= d;
+            G[L->b_off + o] += cur[o];
+        }
+        for (int k = 0; k < L->in; k++) {
+            double s = 0.0;
+            for (int o = 0; o < L->out; o++) { G[L->w_off + o + (size_t)L->out * k] += cur[o] * x[k]; s += wd[L->w_off + o + (size_t)L->out * k] * cur[o]; }
+            nxt[k] = s;
+        }
+        for (int k = 0; k < L->in; k++) cur[k] = nxt[k];
+    }
+    if (dx) for (int k = 0; k < ls[0].in; k++) dx[k] = cur[k];
+}
+static void net_fwd(const float *blob, const double *wd, const net_t *n, const double *x, net_act_t *a, int fwd64) {
+    chain_fwd(blob, wd, n->trunk, n->n_trunk, x, &a->trunk, fwd64);
+    if (n->n_h1) chain_fwd(blob, wd, n->h1, n->n_h1, a->trunk.out[n->n_trunk - 1], &a->h1, fwd64);
+    if (n->n_h2) chain_fwd(blob, wd, n->h2, n->n_h2, a->trunk.out[n->n_trunk - 1], &a->h2, fwd64);
+}
+/* d1 / d2: gradients w.r.t. the two heads' outputs (NULL = zero); dx: gradient w.r.t. the net input */
+static void net_bwd(const double *wd, double *G, const net_t *n, const net_act_t *a, const double *d1, const double *d2, double *dx) {
+    double dt[BP_MAXW], tmp[BP_MAXW];
+    int w = n->trunk[n->n_trunk - 1].out;
+    if (n->n_h1 == 0) { chain_bwd(wd, G, n->trunk, n->n_trunk, &a->trunk, d1, dx); return; }
+    for (int k = 0; k < w; k++) dt[k] = 0.0;
+    if (d1) { chain_bwd(wd, G, n->h1, n->n_h1, &a->h1, d1, tmp); for (int k = 0; k < w; k++) dt[k] += tmp[k]; }
+    if (d2) { chain_bwd(wd, G, n->h2, n->n_h2, &a->h2, d2, tmp); for (int k = 0; k < w; k++) dt[k] += tmp[k]; }
+    chain_bwd(wd, G, n->trunk, n->n_trunk, &a->trunk, dt, dx);
+}
+
+/* grad[n_params] (blob order, Float64) and the Float64 data loss.  perturb_index >= 0 adds perturb_delta to that
+ * parameter of the Float64 weight copy first (finite differences; only meaningful with fwd64 = 1). */
+double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                           const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                           int fwd64, int perturb_index, double perturb_delta, double *grad) {
+    model_t m; model_init(&m, c, blob);
+    int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), on = obs_size(c), plane = c->W * c->H, hs = c->hidden_state_size;
+    int np = mzo_num_params(c, 3);
+    double *wd = (double *)malloc(sizeof(double) * (size_t)np);
+    for (int i = 0; i < np; i++) wd[i] = (double)blob[i];
+    if (perturb_index >= 0) wd[perturb_index] += perturb_delta;
+    if (grad) for (int i = 0; i < np; i++) grad[i] = 0.0;
+    net_act_t *ar = (net_act_t *)malloc(sizeof(net_act_t)), *ap = (net_act_t *)malloc(sizeof(net_act_t) * (size_t)K1), *ad = (net_act_t *)malloc(sizeof(net_act_t) * (size_t)(K ? K : 1));
+    double G = 0.0;                                   /* mean_i(1/g_i): Q21's (1,B,B) broadcast factorises */
+    for (int b = 0; b < B; b++) G += 1.0 / (double)gscale[b];
+    G /= (double)B;
+    double vsum = 0.0, rsum = 0.0, ssum = 0.0;
+    for (int b = 0; b < B; b++) {
+        double x[BP_MAXW], sa[BP_MAXW], pol[MZO_MAX_A * 40], q[MZO_MAX_A];
+        for (int k = 0; k < ss; k++) x[k] = (double)obs_batch[(size_t)b * ss + k];
+        net_fwd(blob, wd, &m.nets[0], x, ar, fwd64);                                        /* :347 */
+        const double *h = ar->trunk.out[m.nets[0].n_trunk - 1];
+        double g = (double)gscale[b];
+        /* rows: row 0 = prediction(h0) (:351); row i = prediction(h_{i-1}) BEFORE dynamics step i (:356-362, Q19) */
+        for (int i = 0; i <= K; i++) {
+            net_fwd(blob, wd, &m.nets[1], h, &ap[i], fwd64);
+            if (i >= 1) {
+                double av = fwd64 ? (double)action_batch[(size_t)b * K1 + (i - 1)] / (double)A
+                                  : (double)(action_batch[(size_t)b * K1 + (i - 1)] / (float)A);
+                for (int j = 0; j < on; j++) sa[j] = h[j] * 2.0;
+                for (int j = 0; j < plane; j++) sa[on + j] = av;
+                net_fwd(blob, wd, &m.nets[2], sa, &ad[i - 1], fwd64);
+                h = ad[i - 1].h1.out[m.nets[2].n_h1 - 1];
+            }
+        }
+        /* loss terms of this sample + gradients w.r.t. the predictions */
+        double dv[40], dr[40], dz[40][MZO_MAX_A];
+        for (int i = 0; i <= K; i++) {
+            const net_act_t *pa = &ap[i];
+            double v = pa->h1.out[m.nets[1].n_h1 - 1][0];
+            const double *z = pa->h2.out[m.nets[1].n_h2 - 1];
+            double tv = (double)value_batch[(size_t)b * K1 + i];
+            vsum += (v - tv) * (v - tv) / g;
+            dv[i] = 2.0 * (v - tv) / (g * (double)B);
+            double r = i == 0 ? 0.0 : ad[i - 1].h2.out[m.nets[2].n_h2 - 1][0], tr = (double)reward_batch[(size_t)b * K1 + i];
+            rsum += (r - tr) * (r - tr) / g;
+            dr[i] = (c->intermediate_rewards && i >= 1) ? 2.0 * (r - tr) / (g * (double)B) : 0.0;
+            /* policy: p = softmax(z) (:114); logitcrossentropy(p, y) = -sum(y .* logsoftmax(p)) (Q21: softmax twice) */
+            double *p = pol + (size_t)i * A;
+            if (fwd64) {
+                double mx = z[0]; for (int a = 1; a < A; a++) mx = z[a] > mx ? z[a] : mx;
+                double s = 0.0; for (int a = 0; a < A; a++) { p[a] = exp(z[a] - mx); s += p[a]; }
+                for (int a = 0; a < A; a++) p[a] /= s;
+            } else {
+                float zf[MZO_MAX_A], pf[MZO_MAX_A];
+                for (int a = 0; a < A; a++) zf[a] = (float)z[a];
+                softmax(zf, A, pf);
+                for (int a = 0; a < A; a++) p[a] = (double)pf[a];
+            }
+            const float *y = policy_batch + ((size_t)b * K1 + i) * A;
+            double mx = p[0]; for (int a = 1; a < A; a++) mx = p[a] > mx ? p[a] : mx;
+            double s = 0.0; for (int a = 0; a < A; a++) { q[a] = exp(p[a] - mx); s += q[a]; }
+            double lse = log(s), ysum = 0.0, ce = 0.0;
+            for (int a = 0; a < A; a++) { q[a] /= s; ysum += (double)y[a]; ce -= (double)y[a] * ((p[a] - mx) - lse); }
+            ssum += ce;
+            double dp[MZO_MAX_A], dot = 0.0, up = G / (double)B;                         /* d(policy_loss)/d(S_b) = G / B */
+            for (int a = 0; a < A; a++) { dp[a] = up * (-(double)y[a] + q[a] * ysum); dot += p[a] * dp[a]; }
+            for (int a = 0; a < A; a++) dz[i][a] = p[a] * (dp[a] - dot);
+        }
+        if (grad) {
+            double dh[BP_MAXW], dsa[BP_MAXW], dhp[BP_MAXW];
+            for (int k = 0; k < hs; k++) dh[k] = 0.0;                                       /* h_K feeds nothing */
+            for (int i = K; i >= 1; i--) {
+                net_bwd(wd, grad, &m.nets[2], &ad[i - 1], dh, &dr[i], dsa);                  /* dynamics step i produced h_i, r_i */
+                net_bwd(wd, grad, &m.nets[1], &ap[i], &dv[i], dz[i], dhp);                   /* row i consumed h_{i-1} */
+                for (int k = 0; k < hs; k++) dh[k] = 2.0 * dsa[k] + dhp[k];                  /* state * 2.0f0 (:299) */
+            }
+            net_bwd(wd, grad, &m.nets[1], &ap[0], &dv[0], dz[0], dhp);                       /* row 0 consumed h_0 */
+            for (int k = 0; k < hs; k++) dh[k] += dhp[k];
+            net_bwd(wd, grad, &m.nets[0], ar, dh, NULL, NULL);
+        }
+    }
+    if (grad) for (int i = 0; i < np; i++) grad[i] += 2.0 * wd[i];                          /* sum(sqnorm, params), :287 */
+    double value_loss = vsum / (double)B, policy_loss = (ssum / (double)B) * G;
+    double data = value_loss + (c->intermediate_rewards ? rsum / (double)B : 0.0) + policy_loss;
+    free(wd); free(ar); free(ap); free(ad);
+    return data;
+}
+
+/* Flux.ADAM on a caller-supplied gradient (lets the tests check the CUDA update bit-for-bit given the CUDA gradient) */
+void mzo_adam_apply(float *blob, float *adam_m, float *adam_v, const float *grad, int n, int t) {
+    adam_update(blob, adam_m, adam_v, grad, n, mzo_cos_schedule(t), t);
+}
+
 void mzo_learn_step(const mzo_config *c, float *blob, float *adam_m, float *adam_v, int t, int grad_mode, int B,
                     const float *obs_batch, const float *action_batch, const float *value_batch, const float *reward_batch,
                     const float *policy_batch, const float *gscale, float *losses) {
@@ -888,10 +1055,16 @@ void mzo_learn_step(const mzo_config *c, float *blob, float *adam_m, float *adam
     float *pv = (float *)malloc(sizeof(float) * (size_t)B * K1), *pr = (float *)malloc(sizeof(float) * (size_t)B * K1);
     float *pp = (float *)malloc(sizeof(float) * (size_t)B * K1 * A), *grad = (float *)malloc(sizeof(float) * (size_t)np);
     mzo_learn_forward(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, pv, pr, pp, losses);
-    /* Q20: predictions are computed OUTSIDE Zygote.pullback (Learning.jl:347-374 vs 385-393), so the only
-     * parameter-dependent term is sum(sqnorm, params): grad = 2*theta for every array. */
-    (void)grad_mode;
-    for (int i = 0; i < np; i++) grad[i] = blob[i] + blob[i];
+    if (grad_mode == MZO_GRAD_BPTT) {
+        double *gd = (double *)malloc(sizeof(double) * (size_t)np);
+        mzo_learn_gradients(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, 0, -1, 0.0, gd);
+        for (int i = 0; i < np; i++) grad[i] = (float)gd[i];
+        free(gd);
+    } else {
+        /* Q20: predictions are computed OUTSIDE Zygote.pullback (Learning.jl:347-374 vs 385-393), so the only
+         * parameter-dependent term is sum(sqnorm, params): grad = 2*theta for every array. */
+        for (int i = 0; i < np; i++) grad[i] = blob[i] + blob[i];
+    }
     adam_update(blob, adam_m, adam_v, grad, np, mzo_cos_schedule(t), t);
     free(pv); free(pr); free(pp); free(grad);
 }

@@ -146,6 +146,15 @@ void mzo_learn_step(const mzo_config *cfg, float *blob, float *adam_m, float *ad
                     const float *obs_batch, const float *action_batch, const float *value_batch,
                     const float *reward_batch, const float *policy_batch, const float *gscale, float *losses);
 
+/* grad_mode = MZO_GRAD_BPTT: d(loss)/d(theta) through the unroll (Float64 backward; see mz_oracle.c).  Returns the
+ * Float64 data loss; grad (may be NULL) = d(data loss)/d(theta) + 2*theta in blob order.  fwd64 = 0 linearises around
+ * the Float32-contract forward, 1 around an all-Float64 forward; perturb_index >= 0 adds perturb_delta to that
+ * parameter first (finite-difference checks). */
+double mzo_learn_gradients(const mzo_config *cfg, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                           const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                           int fwd64, int perturb_index, double perturb_delta, double *grad);
+void mzo_adam_apply(float *blob, float *adam_m, float *adam_v, const float *grad, int n, int t);
+
 #ifdef __cplusplus
 }
 #endif

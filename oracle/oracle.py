@@ -99,6 +99,9 @@ def lib():
     L.mzo_learn_forward.argtypes = [cfgp, f32p, C.c_int] + [f32p] * 10
     L.mzo_cos_schedule.argtypes = [C.c_int]; L.mzo_cos_schedule.restype = C.c_double
     L.mzo_learn_step.argtypes = [cfgp, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int] + [f32p] * 7
+    L.mzo_learn_gradients.argtypes = [cfgp, f32p, C.c_int] + [f32p] * 6 + [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    L.mzo_learn_gradients.restype = C.c_double
+    L.mzo_adam_apply.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -222,3 +225,18 @@ def learn_step(cfg, blob, adam_m, adam_v, t, batch, grad_mode=GRAD_REFERENCE_L2)
                          _p(batch["actions"]), _p(batch["values"]), _p(batch["rewards"]), _p(batch["policies"]),
                          _p(batch["gscale"]), _p(losses))
     return losses
+
+
+def learn_gradients(cfg, blob, batch, fwd64=False, perturb=None, want_grad=True):
+    """grad_mode = BPTT: (Float64 data loss, Float64 gradient of data loss + sum(theta^2) in blob order)."""
+    B = batch["obs"].shape[0]
+    grad = np.zeros(blob.shape[0], np.float64) if want_grad else None
+    idx, delta = perturb if perturb is not None else (-1, 0.0)
+    loss = lib().mzo_learn_gradients(C.byref(cfg), _p(blob), B, _p(batch["obs"]), _p(batch["actions"]), _p(batch["values"]),
+                                     _p(batch["rewards"]), _p(batch["policies"]), _p(batch["gscale"]), int(fwd64), int(idx),
+                                     float(delta), grad.ctypes.data_as(C.POINTER(C.c_double)) if want_grad else None)
+    return loss, grad
+
+
+def adam_apply(blob, adam_m, adam_v, grad, t):
+    lib().mzo_adam_apply(_p(blob), _p(adam_m), _p(adam_v), _p(grad), blob.shape[0], t)

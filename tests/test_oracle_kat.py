@@ -258,3 +258,62 @@ def test_self_play_shapes_and_invariants(cfg):
         assert np.allclose(h["child_visits"][g, :T].sum(1), 1.0, atol=1e-6)
         assert np.all(h["rewards"][g, :T - 1] == 0)
         assert list(h["to_play"][g, :T]) == [1 + (i % 2) for i in range(T)]
+
+
+# ---- grad_mode = BPTT: the Float64 backward of the oracle is pinned by finite differences of its own Float64 loss ----
+def _bptt_case(intermediate_rewards, B=4, seed=3):
+    c = O.default_config(batch_size=B, intermediate_rewards=int(intermediate_rewards), exploration_eps=0.0)
+    blob = O.init_weights(c, seed)
+    rng = np.random.default_rng(seed)
+    blob = blob + (rng.standard_normal(blob.shape[0]) * 0.02).astype(f32)      # non-zero biases
+    hist = O.self_play(c, blob, 0, 8, 1.0, 1)
+    batch = O.get_batch(c, hist, step=seed)
+    batch["rewards"] = batch["rewards"] + (rng.standard_normal(batch["rewards"].shape) * 0.3).astype(f32)   # exercise the reward head
+    return c, blob, batch
+
+
+@pytest.mark.parametrize("ir", [0, 1])
+def test_bptt_gradient_matches_finite_differences(ir):
+    c, blob, batch = _bptt_case(ir)
+    loss, grad = O.learn_gradients(c, blob, batch, fwd64=True)
+    assert np.isfinite(loss) and np.all(np.isfinite(grad))
+    rng = np.random.default_rng(11)
+    n = blob.shape[0]
+    nr, npred = O.num_params(c, 0), O.num_params(c, 1)
+    picks = list(rng.integers(0, nr, 12)) + list(nr + rng.integers(0, npred, 12)) + list(nr + npred + rng.integers(0, n - nr - npred, 16))
+    h = 1e-6
+    worst = 0.0
+    for i in picks:
+        lp, _ = O.learn_gradients(c, blob, batch, fwd64=True, perturb=(int(i), +h), want_grad=False)
+        lm, _ = O.learn_gradients(c, blob, batch, fwd64=True, perturb=(int(i), -h), want_grad=False)
+        fd = (lp - lm) / (2 * h) + 2.0 * float(blob[i])          # the returned loss is the data loss; grad adds 2*theta
+        worst = max(worst, abs(fd - grad[i]) / (abs(grad[i]) + 1e-6))
+    assert worst < 2e-4, worst
+    if not ir:   # without intermediate rewards the reward head only sees the L2 term (Learning.jl:277-279)
+        net = O.lib().mzo_num_params
+        nd = O.num_params(c, 2)
+        # reward head = last (depth_reward + 1) layers of the dynamics net: 64*64+64 + 64*1+1 parameters
+        tail = 64 * 64 + 64 + 64 + 1
+        assert np.allclose(grad[n - tail:], 2.0 * blob[n - tail:].astype(np.float64), rtol=0, atol=1e-12)
+
+
+def test_bptt_float32_forward_is_close_to_float64_forward():
+    c, blob, batch = _bptt_case(1)
+    l64, g64 = O.learn_gradients(c, blob, batch, fwd64=True)
+    l32, g32 = O.learn_gradients(c, blob, batch, fwd64=False)
+    _, _, _, losses = O.learn_forward(c, blob, batch)
+    assert abs(l64 - l32) < 1e-5 * abs(l64)
+    assert np.max(np.abs(g64 - g32)) < 1e-4 * np.max(np.abs(g64))
+    # the Float32 loss scalar of learn_forward = data loss + that net's own sum(theta^2)
+    nr = O.num_params(c, 0)
+    assert abs(float(losses[0]) - (l32 + float(np.sum(blob[:nr].astype(np.float64) ** 2)))) < 1e-4 * float(losses[0])
+
+
+def test_bptt_learn_step_uses_the_gradient():
+    c, blob, batch = _bptt_case(0)
+    _, g = O.learn_gradients(c, blob, batch, fwd64=False)
+    b1 = blob.copy(); m1 = np.zeros_like(blob); v1 = np.zeros_like(blob)
+    O.learn_step(c, b1, m1, v1, 1, batch, grad_mode=O.GRAD_BPTT)
+    b2 = blob.copy(); m2 = np.zeros_like(blob); v2 = np.zeros_like(blob)
+    O.adam_apply(b2, m2, v2, g.astype(f32), 1)
+    assert np.array_equal(b1, b2) and np.array_equal(m1, m2) and np.array_equal(v1, v2)
