@@ -139,6 +139,12 @@ int mz_learn_forward(mz_ctx *ctx, int B, const float *obs_batch, const float *ac
 int mz_learn_step(mz_ctx *ctx, int64_t t, int grad_mode, float *losses /* [3] */);
 /* n consecutive iterations t0 .. t0+n-1 queued back to back (no host round trip in between); losses of the last one */
 int mz_learn_steps(mz_ctx *ctx, int64_t t0, int n, int grad_mode, float *losses /* [3] */);
+/* gradients of one caller-supplied batch without an update (parity entry point): grad[n_params] in the reference blob
+ * order.  MZ_GRAD_REFERENCE_L2: what the reference's three Zygote pullbacks actually return, 2*theta (Learning.jl:385-393
+ * differentiate a closure whose predictions were computed outside of it).  MZ_GRAD_BPTT: the gradient of the same loss
+ * value (Learning.jl:261-288) through the unroll (Learning.jl:347-370), plus 2*theta. */
+int mz_learn_gradients(mz_ctx *ctx, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                       const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses /* [3] */);
 /* same update on a caller-supplied batch (parity entry point) */
 int mz_learn_step_batch(mz_ctx *ctx, int64_t t, int grad_mode, int B, const float *obs_batch, const float *action_batch,
                         const float *value_batch, const float *reward_batch, const float *policy_batch,

@@ -104,6 +104,7 @@ def lib():
         "mz_learn_step": ([ctx, C.c_int64, C.c_int, f32p], C.c_int),
         "mz_learn_steps": ([ctx, C.c_int64, C.c_int, C.c_int, f32p], C.c_int),
         "mz_learn_step_batch": ([ctx, C.c_int64, C.c_int, C.c_int] + [f32p] * 7, C.c_int),
+        "mz_learn_gradients": ([ctx, C.c_int, C.c_int] + [f32p] * 8, C.c_int),
         "mz_optimizer_reset": ([ctx], C.c_int),
         "mz_comm_unique_id": ([u8p], C.c_int),
         "mz_comm_init": ([ctx, C.c_int, C.c_int, u8p], C.c_int),
@@ -345,6 +346,13 @@ class Context:
             arrs, ptrs = self._batch_ptrs(batch)
             self._ck(self.L.mz_learn_step_batch(self._h, t, grad_mode, arrs[0].shape[0], *ptrs, _p(losses, C.c_float)))
         return losses
+
+    def learn_gradients(self, batch, grad_mode=GRAD_REFERENCE_L2):
+        """(gradient in the reference blob order, losses) of one batch; no update."""
+        arrs, ptrs = self._batch_ptrs(batch)
+        grad = np.zeros(self.num_params(), np.float32); losses = np.zeros(3, np.float32)
+        self._ck(self.L.mz_learn_gradients(self._h, grad_mode, arrs[0].shape[0], *ptrs, _p(grad, C.c_float), _p(losses, C.c_float)))
+        return grad, losses
 
     def learn_steps(self, t0, n, grad_mode=GRAD_REFERENCE_L2):
         losses = np.zeros(3, np.float32)

@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 #include "mz_host.h"
-#include "mz_learner.cuh"
+#include "mz_learner_bptt.cuh"
 #include "mz_kernels_tc.cuh"
 
 namespace {
@@ -72,6 +72,9 @@ struct mz_ctx {
     dev_buf scratch[12];
     int64_t adam_t = 0; double bp1 = 0.9, bp2 = 0.999;
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // grad_mode = MZ_GRAD_BPTT
+    mzh::bptt_program bptt; mz_bstage *d_bstages[2] = {nullptr, nullptr}; size_t smem_bytes_bptt = 0;
+    float *d_act = nullptr, *d_gpart = nullptr; int bptt_tiles_cap = 0;
     int64_t launches = 0; bool timing = false; std::vector<timed_launch> timed; double fam_ms[8] = {0}; int64_t fam_n[8] = {0};
     double last_mean_legal = 0, last_mean_depth = 0;
 };
@@ -173,11 +176,27 @@ template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
 }
 #define MZ_TRY(x) do { int r_ = (x); if (r_ != MZ_OK) return r_; } while (0)
 
-int launch_learn_forward(mz_ctx *c, int B) {
+int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2) {
     const mz_params &P = c->M.P;
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
-    { launch_scope ls(c, 3); mz_k_learn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
+    if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
+        if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT needs more shared memory per CTA than the device allows for this network");
+        if (tiles > c->bptt_tiles_cap) {
+            if (c->d_act) cudaFree(c->d_act);
+            if (c->d_gpart) cudaFree(c->d_gpart);
+            c->d_act = nullptr; c->d_gpart = nullptr; c->bptt_tiles_cap = 0;
+            MZ_CUDA(c, dmalloc(&c->d_act, (size_t)tiles * c->bptt.plan.tile_floats));
+            MZ_CUDA(c, dmalloc(&c->d_gpart, (size_t)tiles * P.total_floats));
+            c->bptt_tiles_cap = tiles;
+        }
+        mz_bptt_args b{}; b.f = a; b.act = c->d_act; b.gpart = c->d_gpart; b.stages[0] = c->d_bstages[0]; b.stages[1] = c->d_bstages[1];
+        { launch_scope ls(c, 3); mz_k_learn_bptt<<<tiles, MZ_THREADS, c->smem_bytes_bptt, c->stream>>>(P, c->bptt.plan, b); }
+        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, c->d_grad); }
+    } else if (grad_mode == MZ_GRAD_REFERENCE_L2) {
+        launch_scope ls(c, 3); mz_k_learn_forward<<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
+    } else return fail(c, MZ_E_ARG, "unknown grad_mode %d", grad_mode);
     { launch_scope ls(c, 3); mz_k_loss_rows<<<(B + 127) / 128, 128, 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
     { launch_scope ls(c, 3); mz_k_loss_reduce<<<1, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
     MZ_CUDA(c, cudaGetLastError());
@@ -197,10 +216,10 @@ int finish_losses(mz_ctx *c, int B, float *losses) {
     return MZ_OK;
 }
 int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
-    if (grad_mode != MZ_GRAD_REFERENCE_L2) return fail(c, MZ_E_UNSUPPORTED, "grad_mode %d is not implemented yet (only MZ_GRAD_REFERENCE_L2)", grad_mode);
     const int n = c->M.P.total_floats;
     if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
-    { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
+    // MZ_GRAD_BPTT: d_grad was produced by launch_learn_forward (mz_k_learn_bptt + mz_k_grad_reduce)
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
     float scale = 1.0f;
     if (c->comm) {   // data-parallel: sum gradients over ranks, average in the update
         ncclResult_t r = g_nccl.AllReduce(c->d_grad, c->d_grad, (size_t)n, ncclFloat, ncclSum, c->comm, c->stream);
@@ -252,6 +271,15 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
     MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; }
+    c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
+    if (c->smem_bytes_bptt <= (size_t)prop.sharedMemPerBlockOptin) {
+        MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_bptt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_bptt));
+        for (int g = 0; g < 2; g++) {
+            MZ_CREATE(dmalloc(&c->d_bstages[g], c->bptt.stages[g].size() + 1));
+            if (!c->bptt.stages[g].empty()) MZ_CREATE(cudaMemcpy(c->d_bstages[g], c->bptt.stages[g].data(), c->bptt.stages[g].size() * sizeof(mz_bstage), cudaMemcpyHostToDevice));
+        }
+    } else c->smem_bytes_bptt = 0;   // MZ_GRAD_BPTT reports MZ_E_UNSUPPORTED for this configuration
     if (c->M.P.tc_ok) {
         c->smem_bytes_tc = mz_tc_smem_bytes(P.tc_net_off[3], P.tc_bias_floats, P.hidden_pad, P.S);
         if (c->smem_bytes_tc <= (size_t)prop.sharedMemPerBlockOptin) {
@@ -303,7 +331,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    void *ptrs[] = {c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -665,15 +693,31 @@ int mz_learn_step_batch(mz_ctx *c, int64_t t, int grad_mode, int B, const float 
     MZ_CHECK_CTX(c);
     if (!losses || t < 1) return fail(c, MZ_E_ARG, "bad arguments");
     MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
-    MZ_TRY(launch_learn_forward(c, B));
+    MZ_TRY(launch_learn_forward(c, B, grad_mode));
     MZ_TRY(launch_update(c, t, grad_mode));
     return finish_losses(c, B, losses);
+}
+// gradients of one batch without an update (parity entry point): grad in the reference blob order
+int mz_learn_gradients(mz_ctx *c, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                       const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses) {
+    MZ_CHECK_CTX(c);
+    if (!losses || !grad) return fail(c, MZ_E_ARG, "bad arguments");
+    MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
+    MZ_TRY(launch_learn_forward(c, B, grad_mode));
+    const int n = c->M.P.total_floats;
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
+    std::vector<float> dev((size_t)n), src((size_t)c->M.P.n_params);
+    MZ_CUDA(c, cudaMemcpyAsync(dev.data(), c->d_grad, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    MZ_TRY(finish_losses(c, B, losses));
+    mzh::unpack_weights(c->M.P, dev.data(), src.data());
+    memcpy(grad, src.data(), src.size() * sizeof(float));
+    return MZ_OK;
 }
 int mz_learn_step(mz_ctx *c, int64_t t, int grad_mode, float *losses) {
     MZ_CHECK_CTX(c);
     if (!losses || t < 1) return fail(c, MZ_E_ARG, "bad arguments");
     MZ_TRY(gather_batch(c, (uint64_t)t));
-    MZ_TRY(launch_learn_forward(c, c->cfg.batch_size));
+    MZ_TRY(launch_learn_forward(c, c->cfg.batch_size, grad_mode));
     MZ_TRY(launch_update(c, t, grad_mode));
     return finish_losses(c, c->cfg.batch_size, losses);
 }
@@ -689,7 +733,7 @@ int mz_learn_steps(mz_ctx *c, int64_t t0, int n, int grad_mode, float *losses) {
     if (c->h_counters[0] < 1) return fail(c, MZ_E_STATE, "replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)");
     for (int i = 0; i < n; i++) {
         { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, (uint64_t)(t0 + i), B, c->batch); }
-        MZ_TRY(launch_learn_forward(c, B));
+        MZ_TRY(launch_learn_forward(c, B, grad_mode));
         MZ_TRY(launch_update(c, t0 + i, grad_mode));
     }
     return finish_losses(c, B, losses);

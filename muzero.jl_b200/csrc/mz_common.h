@@ -163,6 +163,34 @@ struct mz_params {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Learner backward pass (grad_mode = MZ_GRAD_BPTT): host-built program of backward layer applications.
+// One CTA = 32 samples; group 0 walks the prediction rows (and finally the representation), group 1 the
+// dynamics steps, in lock-step "steps" separated by CTA barriers (see mz_learner_bptt.cuh).
+// ------------------------------------------------------------------------------------------------
+enum { MZ_BUF_Z0 = 0, MZ_BUF_Z1 = 1, MZ_BUF_TA = 2, MZ_BUF_DH = 3, MZ_BUF_DHP = 4, MZ_BUF_DHD = 5 };
+enum { MZ_PRE_NONE = 0, MZ_PRE_VALUE = 1, MZ_PRE_POLICY = 2, MZ_PRE_REWARD = 3 };
+enum { MZ_DX_NONE = 0, MZ_DX_STORE = 1, MZ_DX_ACCUM = 2 };
+#define MZ_MAX_BSTEPS 40
+struct mz_bstage {
+    int16_t layer;        // index into mz_params::layers
+    int16_t row;          // prediction row / dynamics step (1-based) the loss terms of `pre` belong to
+    int32_t x_off;        // float offset of the layer's input activations inside the tile's activation block
+    uint8_t dz_buf, dx_buf, dx_mode, prev_act;   // prev_act: activation of the layer that produced the input (applied to dX)
+    uint8_t first, pre, merge0, pad_;            // first: this is the tile's first gradient contribution to the layer (store, not add)
+    float dx_scale;
+};
+struct mz_bptt_plan {
+    int32_t y_off[MZ_MAX_LAYERS];     // float offset of each layer's output inside its network's evaluation block
+    int32_t x_off[MZ_MAX_LAYERS];     // float offset of each layer's input inside the block
+    int32_t net_base[3], net_block[3];// activation block = [repr | pred evals | dyn evals]
+    int32_t tile_floats, n_pred_evals, n_steps, rewards;
+    int32_t n_stages[2];
+    int32_t step_end[2][MZ_MAX_BSTEPS];   // exclusive end of each step's stages in the group's program
+    uint8_t dhd_valid[MZ_MAX_BSTEPS];     // group 1 produced a dynamics-input gradient in this step
+    uint64_t dead_layers;                 // layers that receive no data gradient at all (their partial sums are zero-filled)
+};
+
+// ------------------------------------------------------------------------------------------------
 // Games.  TicTacToe follows games/tictactoe/game.jl including its quirks; boards are
 // two bit masks (bit a-1 = cell of action a, column-major like CartesianIndices((3,3))[a]).
 // MZ_GAME_CONNECT is the synthetic larger-board game of BASELINE.json config 4 (no reference code):

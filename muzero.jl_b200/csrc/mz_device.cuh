@@ -90,8 +90,10 @@ __device__ __forceinline__ void mz_fma_step(unsigned long long (&acc2)[4][2], co
 }   // keeps the (rare) tanh out of the hot epilogue code
 
 // y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row].
-// One copy of this code in the binary (noinline): every layer of every network goes through it.
-__device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
+// SAVE also streams the outputs to global memory in the same k-major [o][32] layout (the learner's backward pass reads
+// them back as the next layer's input activations).
+template <bool SAVE>
+__device__ __forceinline__ void mz_dense_tile_body(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid, float *gsave) {
     const int lane = gtid & 31, warp = gtid >> 5;
     const int rg = lane & 7;
     const int opq = out_pad >> 2;
@@ -124,8 +126,17 @@ MZ_UNROLL_K
             if (act == MZ_ACT_RELU) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
             else if (act == MZ_ACT_TANH) { r.x = mz_tanhf_ni(r.x); r.y = mz_tanhf_ni(r.y); r.z = mz_tanhf_ni(r.z); r.w = mz_tanhf_ni(r.w); }
             mz_sts128(dst_smem + (uint32_t)((4 * g + j) * MZ_ROWS * 4) + (uint32_t)rg * 16u, r);
+            if (SAVE) *reinterpret_cast<float4 *>(gsave + (4 * g + j) * MZ_ROWS + rg * 4) = r;
         }
     }
+}
+
+// One copy of each in the binary (noinline): every layer of every network goes through them.
+__device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
+    mz_dense_tile_body<false>(in, out_pad, act, w_smem, src_smem, dst_smem, gtid, nullptr);
+}
+__device__ __noinline__ void mz_dense_tile_save(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid, float *gsave) {
+    mz_dense_tile_body<true>(in, out_pad, act, w_smem, src_smem, dst_smem, gtid, gsave);
 }
 
 // One layer for one group: prefetch `next` (or nothing when next < 0) into the other buffer, wait for this layer's

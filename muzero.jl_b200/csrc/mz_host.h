@@ -245,6 +245,99 @@ inline void init_weights(const mz_params &P, uint64_t seed, float *src) {
     }
 }
 
+// Backward program of one 32-sample tile for grad_mode = MZ_GRAD_BPTT (kernel: mz_k_learn_bptt).  Follows the unroll
+// of Learning.jl:347-370 backwards: rows K..1 of the prediction net on group 0, dynamics steps K..1 on group 1, one
+// lock-step per unroll step (the gradient w.r.t. h_{i-1} needs both), then the representation net.  Rows 0 and 1 of the
+// predictions are the same forward evaluation prediction(h_0) (Q19), so their loss gradients are summed before one
+// backward walk (the backward pass is linear in the upstream gradient).
+struct bptt_program { mz_bptt_plan plan; std::vector<mz_bstage> stages[2]; };
+
+inline void bptt_chain(const mz_params &P, const mz_bptt_plan &pl, std::vector<mz_bstage> &out, int eval_base, int first_layer, int n,
+                       int in_prev_act, int dz_first, int pre, int row, int merge0, int dx_last_buf, int dx_last_mode, float dx_last_scale,
+                       uint64_t &used) {
+    int cur = dz_first;
+    for (int j = n - 1; j >= 0; j--) {
+        mz_bstage s; memset(&s, 0, sizeof(s));
+        s.layer = (int16_t)(first_layer + j); s.row = (int16_t)row;
+        s.x_off = eval_base + pl.x_off[first_layer + j];
+        s.dz_buf = (uint8_t)cur;
+        s.pre = (uint8_t)(j == n - 1 ? pre : MZ_PRE_NONE); s.merge0 = (uint8_t)(j == n - 1 ? merge0 : 0);
+        if (j > 0) { s.dx_buf = (uint8_t)(cur == MZ_BUF_Z0 ? MZ_BUF_Z1 : MZ_BUF_Z0); s.dx_mode = MZ_DX_STORE; s.prev_act = (uint8_t)P.layers[first_layer + j - 1].act; s.dx_scale = 1.0f; }
+        else { s.dx_buf = (uint8_t)dx_last_buf; s.dx_mode = (uint8_t)dx_last_mode; s.prev_act = (uint8_t)in_prev_act; s.dx_scale = dx_last_scale; }
+        s.first = (uint8_t)(((used >> (first_layer + j)) & 1ull) ? 0 : 1);
+        used |= 1ull << (first_layer + j);
+        out.push_back(s);
+        cur = s.dx_buf;
+    }
+}
+
+inline const char *build_bptt(const mz_params &P, bptt_program &bp) {
+    mz_bptt_plan &pl = bp.plan; memset(&pl, 0, sizeof(pl));
+    bp.stages[0].clear(); bp.stages[1].clear();
+    if (P.K + 2 > MZ_MAX_BSTEPS) return "too many unroll steps for the backward program";
+    for (int n = 0; n < 3; n++) {
+        const mz_net &N = P.nets[n];
+        int off = ((P.layers[N.first].in + 3) & ~3) * 32;
+        int cnt = N.n_trunk + N.n_h1 + N.n_h2;
+        for (int i = 0; i < cnt; i++) {
+            int l = N.first + i;
+            pl.y_off[l] = off; off += P.layers[l].out_pad * 32;
+            if (i == 0) pl.x_off[l] = 0;
+            else if (i == N.n_trunk || i == N.n_trunk + N.n_h1) pl.x_off[l] = pl.y_off[N.first + N.n_trunk - 1];
+            else pl.x_off[l] = pl.y_off[l - 1];
+        }
+        pl.net_block[n] = off;
+    }
+    pl.n_pred_evals = P.K > 0 ? P.K : 1;
+    pl.net_base[0] = 0; pl.net_base[1] = pl.net_block[0]; pl.net_base[2] = pl.net_base[1] + pl.n_pred_evals * pl.net_block[1];
+    pl.tile_floats = pl.net_base[2] + P.K * pl.net_block[2];
+    pl.rewards = P.intermediate_rewards ? 1 : 0;
+    const mz_net &NR = P.nets[0], &NP = P.nets[1], &ND = P.nets[2];
+    const int trunk_act_p = P.layers[NP.first + NP.n_trunk - 1].act, trunk_act_d = P.layers[ND.first + ND.n_trunk - 1].act;
+    uint64_t used = 0;
+    int step = 0;
+    const int nrows = P.K > 0 ? P.K : 1;
+    for (int s = 0; s < nrows; s++, step++) {
+        // group 0: prediction row i (evaluation e = prediction(h_e), e = i - 1; row 0 shares evaluation 0)
+        const int i = P.K > 0 ? P.K - s : 0, e = i > 0 ? i - 1 : 0, merge0 = (P.K > 0 && i == 1) ? 1 : 0;
+        const int pbase = pl.net_base[1] + e * pl.net_block[1];
+        bptt_chain(P, pl, bp.stages[0], pbase, NP.first + NP.n_trunk, NP.n_h1, trunk_act_p, MZ_BUF_Z0, MZ_PRE_VALUE, i, merge0, MZ_BUF_TA, MZ_DX_STORE, 1.0f, used);
+        bptt_chain(P, pl, bp.stages[0], pbase, NP.first + NP.n_trunk + NP.n_h1, NP.n_h2, trunk_act_p, MZ_BUF_Z0, MZ_PRE_POLICY, i, merge0, MZ_BUF_TA, MZ_DX_ACCUM, 1.0f, used);
+        bptt_chain(P, pl, bp.stages[0], pbase, NP.first, NP.n_trunk, MZ_ACT_ID, MZ_BUF_TA, MZ_PRE_NONE, i, 0, MZ_BUF_DHP, MZ_DX_STORE, 1.0f, used);
+        pl.step_end[0][step] = (int32_t)bp.stages[0].size();
+        // group 1: dynamics step i (produced h_i and r_i from h_{i-1}); h_K feeds nothing, so step K has no state-head gradient
+        if (P.K > 0) {
+            const int dbase = pl.net_base[2] + (i - 1) * pl.net_block[2];
+            const bool state = i < P.K, reward = P.intermediate_rewards != 0;
+            if (state) bptt_chain(P, pl, bp.stages[1], dbase, ND.first + ND.n_trunk, ND.n_h1, trunk_act_d, MZ_BUF_DH, MZ_PRE_NONE, i, 0, MZ_BUF_TA, MZ_DX_STORE, 1.0f, used);
+            if (reward) bptt_chain(P, pl, bp.stages[1], dbase, ND.first + ND.n_trunk + ND.n_h1, ND.n_h2, trunk_act_d, MZ_BUF_Z0, MZ_PRE_REWARD, i, 0, MZ_BUF_TA, state ? MZ_DX_ACCUM : MZ_DX_STORE, 1.0f, used);
+            if (state || reward) {   // make_dynamics_input: state * 2.0f0 (Learning.jl:299)
+                bptt_chain(P, pl, bp.stages[1], dbase, ND.first, ND.n_trunk, MZ_ACT_ID, MZ_BUF_TA, MZ_PRE_NONE, i, 0, MZ_BUF_DHD, MZ_DX_STORE, 2.0f, used);
+                pl.dhd_valid[step] = 1;
+            }
+        }
+        pl.step_end[1][step] = (int32_t)bp.stages[1].size();
+    }
+    // representation (group 0): upstream = d loss / d h_0 in DH
+    {
+        int cur = MZ_BUF_DH;
+        for (int j = NR.n_trunk - 1; j >= 0; j--) {
+            mz_bstage s; memset(&s, 0, sizeof(s));
+            s.layer = (int16_t)(NR.first + j); s.x_off = pl.net_base[0] + pl.x_off[NR.first + j]; s.dz_buf = (uint8_t)cur;
+            if (j > 0) { s.dx_buf = (uint8_t)(cur == MZ_BUF_Z0 ? MZ_BUF_Z1 : MZ_BUF_Z0); s.dx_mode = MZ_DX_STORE; s.prev_act = (uint8_t)P.layers[NR.first + j - 1].act; s.dx_scale = 1.0f; }
+            s.first = 1; used |= 1ull << (NR.first + j);
+            bp.stages[0].push_back(s);
+            cur = s.dx_buf;
+        }
+        pl.step_end[0][step] = (int32_t)bp.stages[0].size(); pl.step_end[1][step] = (int32_t)bp.stages[1].size();
+        step++;
+    }
+    pl.n_steps = step;
+    pl.n_stages[0] = (int32_t)bp.stages[0].size(); pl.n_stages[1] = (int32_t)bp.stages[1].size();
+    pl.dead_layers = ~used & ((P.n_layers >= 64 ? 0ull : (1ull << P.n_layers)) - 1ull);
+    return nullptr;
+}
+
 // ParameterSchedulers.Cos(l0=1e-4, l1=1e-1, period=10) (Learning.jl:319), 1-based step.
 inline double cos_schedule(int64_t t) {
     double l0 = 1e-4, l1 = 1e-1, period = 10.0;

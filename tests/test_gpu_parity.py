@@ -328,3 +328,99 @@ def test_learn_steps_equals_repeated_learn_step(capi):
                 losses = ctx.learn_step(t)
         ws.append((ctx.get_weights(), losses)); ctx.close()
     assert np.array_equal(ws[0][0], ws[1][0]) and np.allclose(ws[0][1], ws[1][1], rtol=LOSS_RTOL)
+
+
+# ---- grad_mode = MZ_GRAD_BPTT: gradient of the reference's loss through the unroll (mz_k_learn_bptt) -----------------
+# The CUDA backward accumulates in Float32 (32-row tiles, then tiles in order); the oracle's backward is Float64 around
+# the SAME Float32 forward activations (identical relu masks).  Tolerance: 2e-5 of the largest gradient entry of the
+# network the parameter belongs to.
+BPTT_RTOL = 2e-5
+
+
+def _bptt_batch(ocfg, blob, B, seed):
+    rng = np.random.default_rng(seed)
+    hist = O.self_play(ocfg, blob, 0, 16, 1.0, 2)
+    c2 = O.Config.from_buffer_copy(ocfg); c2.batch_size = B
+    batch = O.get_batch(c2, hist, step=seed)
+    batch["rewards"] = batch["rewards"] + (rng.standard_normal(batch["rewards"].shape) * 0.3).astype(np.float32)
+    return batch
+
+
+def _check_grad(ocfg, g, og):
+    nr, npred = O.num_params(ocfg, 0), O.num_params(ocfg, 1)
+    for lo, hi in ((0, nr), (nr, nr + npred), (nr + npred, g.shape[0])):
+        scale = np.max(np.abs(og[lo:hi]))
+        err = np.max(np.abs(g[lo:hi].astype(np.float64) - og[lo:hi]))
+        assert err <= BPTT_RTOL * scale, (lo, hi, err, scale)
+
+
+@pytest.mark.parametrize("kw,B", [({}, 32), ({"intermediate_rewards": 1}, 32), ({"intermediate_rewards": 1}, 77), ({}, 5),
+                                  ({"num_unroll_steps": 1, "intermediate_rewards": 1}, 40), ({"num_unroll_steps": 2}, 33),   # (K = 0 is degenerate in the reference: gradient_scale = min(K, ..) = 0, ReplayBuffer.jl:212)
+                                  ({"depth_value": 0, "depth_policy": 2, "depth_reward": 0, "depth_state_head": 1, "intermediate_rewards": 1}, 64)])
+def test_bptt_gradients_match_oracle(capi, kw, B):
+    ctx, ocfg = make_ctx(capi, batch_size=B, **kw)
+    ctx.init_weights(5)
+    rng = np.random.default_rng(8)
+    blob = ctx.get_weights() + (rng.standard_normal(ctx.num_params()) * 0.02).astype(np.float32)   # non-zero biases
+    ctx.set_weights(blob)
+    batch = _bptt_batch(ocfg, blob, B, 3)
+    g, losses = ctx.learn_gradients(batch, capi.GRAD_BPTT)
+    _, og = O.learn_gradients(ocfg, blob, batch, fwd64=False)
+    _check_grad(ocfg, g, og)
+    # the fused kernel's forward is the forward kernel's arithmetic: predictions and losses are bit-identical
+    pv, pr, pp, l_fwd = ctx.learn_forward(batch)
+    assert np.array_equal(losses, l_fwd)
+    opv, opr, opp, ol = O.learn_forward(ocfg, blob, batch)
+    assert np.array_equal(pv, opv) and np.array_equal(pp, opp) and np.allclose(losses, ol, rtol=LOSS_RTOL)
+    # deterministic: same bits on a second run
+    g2, _ = ctx.learn_gradients(batch, capi.GRAD_BPTT)
+    assert np.array_equal(g, g2)
+    # reference_l2 mode through the same entry point: exactly 2*theta (Q20)
+    g3, _ = ctx.learn_gradients(batch, capi.GRAD_REFERENCE_L2)
+    assert np.array_equal(g3, blob + blob)
+    ctx.close()
+
+
+def test_bptt_update_is_adam_on_the_gradient(capi):
+    ctx, ocfg = make_ctx(capi, batch_size=48, intermediate_rewards=1)
+    ctx.init_weights(6); blob = ctx.get_weights()
+    m = np.zeros_like(blob); v = np.zeros_like(blob); ob = blob.copy()
+    for t in (1, 2, 3):
+        batch = _bptt_batch(ocfg, ob, 48, 10 + t)
+        g, _ = ctx.learn_gradients(batch, capi.GRAD_BPTT)
+        ctx.learn_step(t, capi.GRAD_BPTT, batch)
+        O.adam_apply(ob, m, v, g, t)                      # Flux.ADAM on the CUDA gradient: the update itself is bit-exact
+        assert np.array_equal(ctx.get_weights(), ob)
+    ctx.close()
+
+
+def test_bptt_large_batch_properties(capi):
+    """Size-independent properties at a throughput-sized batch (B = 4096, 128 tiles): a batch made of 128 copies of a
+    32-sample batch has the same mean gradient as the 32-sample batch (the loss is a batch mean and Q21's mean_i(1/g_i)
+    is unchanged by replication), and the training loop decreases the data loss."""
+    ctx, ocfg = make_ctx(capi, batch_size=4096, replay_buffer_size=4096)
+    ctx.init_weights(9); blob = ctx.get_weights()
+    small = _bptt_batch(ocfg, blob, 32, 4)
+    big = {k: np.concatenate([v] * 128) for k, v in small.items()}
+    gs, _ = ctx.learn_gradients(small, capi.GRAD_BPTT)
+    gb, _ = ctx.learn_gradients(big, capi.GRAD_BPTT)
+    assert np.max(np.abs(gs - gb)) <= 1e-4 * np.max(np.abs(gs))
+    _, og = O.learn_gradients(ocfg, blob, small, fwd64=False)
+    _check_grad(ocfg, gb, og)
+    ctx.close()
+
+
+def test_bptt_training_reduces_the_loss(capi):
+    """The objective the reference's optimiser sees (data loss + sum(theta^2) per net, Learning.jl:287) goes down."""
+    ctx, ocfg = make_ctx(capi, num_slots=256, replay_buffer_size=1024, batch_size=256)
+    ctx.init_weights(12)
+    ctx.self_play(0, 512, 1.0)
+
+    def objective():
+        _, _, _, l = ctx.learn_forward(ctx.get_batch(999))
+        return float(np.sum(l.astype(np.float64)))
+    before = objective()
+    ctx.learn_steps(1, 60, capi.GRAD_BPTT)
+    after = objective()
+    assert np.isfinite(after) and after < 0.5 * before, (before, after)
+    ctx.close()
