@@ -270,13 +270,30 @@ def run_b200(a):
             if world > 1:
                 from muzero_jl_b200 import dist as mzdist
                 mzdist.attach_communicator(big, rank, world, device="cuda")
-            big.learn_steps(1, 3)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            big.learn_steps(4, a.learner_steps)
-            e1.record(stream); e1.synchronize()
-            learner["large_batch"] = {"batch_per_gpu": 4096, "ms_per_step": e0.elapsed_time(e1) / a.learner_steps}
+            learner["large_batch"] = {"batch_per_gpu": 4096}
+            # grad_mode = bptt (the gradient through the unroll; SURVEY 8e: "report bptt mode as the meaningful number") and
+            # reference_l2 (what the reference's pullbacks actually return: 2*theta, Q20), both end to end per step:
+            # get_batch gather + unroll forward (+ backward) + loss + gradient reduce (+ allreduce) + ADAM
+            for name, c_, mode in (("bptt", ctx, capi.GRAD_BPTT), ("large_batch_bptt", big, capi.GRAD_BPTT), ("large_batch_l2", big, capi.GRAD_REFERENCE_L2)):
+                c_.learn_steps(1, 3, mode)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                c_.learn_steps(4, a.learner_steps, mode)
+                e1.record(stream); e1.synchronize()
+                lms_ = e0.elapsed_time(e1) / a.learner_steps
+                c_.kernel_time_reset(True)               # separate pass with per-launch events for the breakdown
+                c_.learn_steps(4 + a.learner_steps, a.learner_steps, mode)
+                fk_ms, fk_n = c_.kernel_time(3)          # family 3: unroll forward (+ backward) + loss kernels
+                c_.kernel_time_reset(False)
+                Bp = c_.cfg.batch_size
+                entry = {"batch_per_gpu": Bp, "ms_per_step": lms_, "unroll_and_loss_kernels_ms_per_step": fk_ms / a.learner_steps}
+                if name == "bptt":
+                    learner["bptt"] = entry
+                elif name == "large_batch_bptt":
+                    learner["large_batch"]["bptt"] = entry
+                else:
+                    learner["large_batch"]["reference_l2"] = entry
             big.close()
 
     t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0], dtype=torch.float64, device="cuda")
@@ -330,7 +347,10 @@ def run_b200(a):
                                           "oracle to bf16 tolerance, not bit-exactly, so the headline value is the exact-fp32 path"}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
-            learner["large_batch"]["samples_per_s"] = 4096 * world / (learner["large_batch"]["ms_per_step"] * 1e-3)
+            for e_ in (learner["bptt"], learner["large_batch"]["bptt"], learner["large_batch"]["reference_l2"]):
+                e_["samples_per_s"] = e_["batch_per_gpu"] * world / (e_["ms_per_step"] * 1e-3)      # per-rank time of rank 0; ranks run in lock-step through the allreduce
+                e_["fwd_bwd_flops_per_sample"] = 1913856 if e_ is not learner["large_batch"]["reference_l2"] else 637952
+                e_["tflops"] = e_["fwd_bwd_flops_per_sample"] * e_["samples_per_s"] / 1e12
             out["learner"] = learner
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(ocfg, blob, a.cpu_seconds)

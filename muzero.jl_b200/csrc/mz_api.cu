@@ -111,6 +111,14 @@ void collect_timings(mz_ctx *c) {
     c->timed.clear();
 }
 
+// The dynamic shared memory limit of a kernel is a per-function (process-wide) attribute: contexts with different network /
+// tree sizes share it, so it is always raised to everything the device allows (the launch itself asks for what it needs).
+template <typename F> cudaError_t allow_max_smem(F *func, const cudaDeviceProp &prop) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, func);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(prop.sharedMemPerBlockOptin - fa.sharedSizeBytes));
+}
 template <typename T> cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
 
 int alloc_batch(mz_ctx *c, int B) {
@@ -267,14 +275,14 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     const mz_params &P = c->M.P;
     c->smem_bytes = mz_smem_bytes(c->M.max_dim, c->M.max_layer_floats, P.hidden_pad, P.S);
     if (c->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
-    MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_API>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    MZ_CREATE(cudaFuncSetAttribute(mz_k_search<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
-    MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes));
+    MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
+    MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
     if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; }
     c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
-    if (c->smem_bytes_bptt <= (size_t)prop.sharedMemPerBlockOptin) {
-        MZ_CREATE(cudaFuncSetAttribute(mz_k_learn_bptt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_bptt));
+    if (c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {   // 4 KB head-room for the kernel's static shared memory
+        MZ_CREATE(allow_max_smem(mz_k_learn_bptt, prop));
         for (int g = 0; g < 2; g++) {
             MZ_CREATE(dmalloc(&c->d_bstages[g], c->bptt.stages[g].size() + 1));
             if (!c->bptt.stages[g].empty()) MZ_CREATE(cudaMemcpy(c->d_bstages[g], c->bptt.stages[g].data(), c->bptt.stages[g].size() * sizeof(mz_bstage), cudaMemcpyHostToDevice));
@@ -283,9 +291,9 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (c->M.P.tc_ok) {
         c->smem_bytes_tc = mz_tc_smem_bytes(P.tc_net_off[3], P.tc_bias_floats, P.hidden_pad, P.S);
         if (c->smem_bytes_tc <= (size_t)prop.sharedMemPerBlockOptin) {
-            MZ_CREATE(cudaFuncSetAttribute(mz_k_search_tc<MZ_MODE_API>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
-            MZ_CREATE(cudaFuncSetAttribute(mz_k_search_tc<MZ_MODE_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
-            MZ_CREATE(cudaFuncSetAttribute(mz_k_nn_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes_tc));
+            MZ_CREATE(allow_max_smem(mz_k_search_tc<MZ_MODE_API>, prop));
+            MZ_CREATE(allow_max_smem(mz_k_search_tc<MZ_MODE_SLOTS>, prop));
+            MZ_CREATE(allow_max_smem(mz_k_nn_forward_tc, prop));
             MZ_CREATE(cudaMalloc((void **)&c->d_w_tc, (size_t)P.tc_net_off[3] + 8192));
             MZ_CREATE(dmalloc(&c->d_bias_tc, (size_t)P.tc_bias_floats));
         } else if (cfg->nn_mode == MZ_NN_BF16_TC) {

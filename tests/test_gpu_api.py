@@ -92,3 +92,19 @@ def test_two_contexts_are_independent(mz):
         assert np.array_equal(h["actions"][order], o["actions"]) and np.array_equal(h["root_values"][order], o["root_values"])
     assert a.launch_count() > 0 and a.kernel_time(0)[1] == 0   # timers are off by default
     a.close(); b.close()
+
+
+def test_contexts_with_different_sizes_coexist(mz):
+    capi = mz.capi
+    """The shared-memory limit of a kernel is a process-wide attribute: creating a context with a smaller tree / network
+    must not break an existing larger one (regression: the second mz_create used to lower the limit)."""
+    import numpy as np
+    big = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=64, num_iters=50))
+    small = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=64, num_iters=5))
+    big.init_weights(1); small.init_weights(1)
+    s1, _ = big.self_play(0, 64, 1.0)
+    s2, _ = small.self_play(0, 64, 1.0)
+    assert s1 > 0 and s2 > 0
+    l = big.learn_steps(1, 2, capi.GRAD_BPTT)
+    assert np.all(np.isfinite(l))
+    big.close(); small.close()
