@@ -69,6 +69,13 @@ __device__ __forceinline__ void mz_bwd_dw(const mz_layer &L, bool first, uint32_
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) acc2[i][j] = 0ull;
+        // earlier contributions of this tile to the layer (read-modify-write): fetched now, needed after the reduction
+        float4 old[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = 4 * kg + i;
+            old[i] = (!first && k < L.in) ? *reinterpret_cast<const float4 *>(gpart + L.w_off + k * L.out_pad + 4 * og) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
         const uint32_t xa = x_smem + (uint32_t)kg * (4u * MZ_ROWS * 4u), za = dz_smem + (uint32_t)og * (4u * MZ_ROWS * 4u);
 #pragma unroll 2
         for (int c = 0; c < 8; c++) {
@@ -99,19 +106,26 @@ __device__ __forceinline__ void mz_bwd_dw(const mz_layer &L, bool first, uint32_
 #pragma unroll
             for (int j = 0; j < 4; j++) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(acc2[i][j])); v[j] = a + b; }
             float4 *dst = reinterpret_cast<float4 *>(gpart + L.w_off + k * L.out_pad + 4 * og);
-            float4 r; r.x = v[0]; r.y = v[1]; r.z = v[2]; r.w = v[3];
-            if (!first) { float4 o = *dst; r.x = o.x + r.x; r.y = o.y + r.y; r.z = o.z + r.z; r.w = o.w + r.w; }
+            float4 r; r.x = old[i].x + v[0]; r.y = old[i].y + v[1]; r.z = old[i].z + v[2]; r.w = old[i].w + v[3];
             *dst = r;
         }
     }
-    // bias gradient: warp w owns outputs 16w .. 16w+15, lanes = rows, butterfly sum
-    for (int j = 0; j < 16; j++) {
-        const int o = warp * 16 + j;
-        if (o >= L.out_pad) break;
-        float v = dz[o * MZ_ROWS + lane];
+    // bias gradient: warp w owns outputs 16w .. 16w+15, lanes = rows, butterfly sum; lane j keeps output 16w+j and the
+    // 16 sums go out in one coalesced read-modify-write
+    {
+        float *dst = gpart + L.b_off + warp * 16 + lane;
+        const bool mine_ok = lane < 16 && warp * 16 + lane < L.out_pad;
+        const float oldb = (mine_ok && !first) ? *dst : 0.0f;
+        float mine = 0.0f;
+        for (int j = 0; j < 16; j++) {
+            const int o = warp * 16 + j;
+            if (o >= L.out_pad) break;
+            float v = dz[o * MZ_ROWS + lane];
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, m);
-        if (lane == 0) { float *dst = gpart + L.b_off + o; *dst = first ? v : *dst + v; }
+            for (int m = 16; m > 0; m >>= 1) v = v + __shfl_xor_sync(0xffffffffu, v, m);
+            if (lane == j) mine = v;
+        }
+        if (mine_ok) *dst = oldb + mine;
     }
 }
 // dX[k][row] = act'(X[k][row]) * scale * sum_o W[k][o] * dZ[o][row]   (rows k >= in are written as zeros: they are the

@@ -155,6 +155,7 @@ void mzo_default_config(mzo_config *c) { /* games/tictactoe/params.jl:2-29; src/
     c->width_hidden = 64; c->depth_representation = 3; c->depth_prediction = 3; c->depth_dynamics = 3;
     c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
+    c->net_type = 0; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -205,7 +206,10 @@ static void build_nets(const mzo_config *c, net_t nets[3]) {
     build_net(c, 1, &nets[1], nets[0].n_params);
     build_net(c, 2, &nets[2], nets[0].n_params + nets[1].n_params);
 }
+static int rn_num_params(const mzo_config *c, int net);
+static void rn_init_weights(const mzo_config *c, uint64_t seed, float *blob);
 int mzo_num_params(const mzo_config *c, int net) {
+    if (c->net_type == 1) return rn_num_params(c, net);
     net_t n[3]; build_nets(c, n);
     return net < 3 ? n[net].n_params : n[0].n_params + n[1].n_params + n[2].n_params;
 }
@@ -214,6 +218,7 @@ int mzo_num_params(const mzo_config *c, int net) {
  * The reference draws from the unseeded global RNG (conf.seed is never read, Constructors.jl:19);
  * contract: element i of layer l of net n = Philox(seed, INIT, n, l, i/4)[i%4]. */
 void mzo_init_weights(const mzo_config *c, uint64_t seed, float *blob) {
+    if (c->net_type == 1) { rn_init_weights(c, seed, blob); return; }
     net_t nets[3]; build_nets(c, nets);
     for (int n = 0; n < 3; n++) {
         int li = 0;
@@ -287,13 +292,203 @@ static void softmax(const float *x, int n, float *y) {
     for (int i = 0; i < n; i++) y[i] = y[i] / s;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * ResNet networks (net_type = 1): the REPAIRED spec of src/Learning.jl:148-255.
+ *
+ * The reference's ResNet constructors never ran: they read undefined names (`downsampling`, `size`,
+ * `hyper.width_hidden`, `hyper.stacked_actions`; Learning.jl:175,177,203,237) and no ResNetHP exists.
+ * Repairs (and nothing else): downsampling = hyper.downsample = false; width_hidden = the Config-level
+ * width (64); stacked_actions = 1 (one action plane, as make_state_action builds, SelfPlay.jl:7-14);
+ * hlayers(depth, hs, ...) = depth x Dense(hs, hs, relu) (make_dense without batch norm, :70-80).
+ *   unit ConvBN(k, cin => cout, act) = Conv((k,k), cin => cout, pad = k / 2) ; BatchNorm(cout, act)
+ *   block(k, n) = relu.(x + BN(Conv(relu(BN(Conv(x))))))                                   (:148-158)
+ *   representation: ConvBN(K, planes => nf, relu); num_blocks x block(K, nf)               (:160-171) -> (W,H,nf)
+ *   prediction: ConvBN(1, nf => nf, relu); blocks(1);                                       (:193-206)
+ *       value : ConvBN(1, nf => nvf, relu); flatten; Dense(W*H*nvf => hs, relu); hlayers(depth_value); Dense(hs => 1, tanh)
+ *       policy: ConvBN(1, nf => npf, relu); flatten; Dense(W*H*npf => hs) [no activation]; hlayers(depth_value) [sic, :222];
+ *               Dense(hs => A); softmax                                                      (:208-226)
+ *   dynamics: ConvBN(1, nf + 1 => nf, relu); blocks(1);                                     (:228-241)
+ *       state : ConvBN(1, nf => nf, relu); blocks(1)                                         (:243-246)
+ *       reward: like the value head                                                           (:248-254)
+ * Un-vendored library semantics restated here: NNlib.conv is a TRUE convolution (kernel flipped):
+ *   y[x,y,co] = b[co] + sum_{ci,b,a} w[a,b,ci,co] * in[x + pad - a, y + pad - b, ci]   (0-based, zero padding);
+ * Flux.BatchNorm outside a gradient context (the reference never differentiates its forward passes, Q20) uses the
+ * stored statistics:  act.(gamma .* (x .- mu) ./ sqrt.(var .+ 1f-5) .+ beta);  flatten is column-major (cell fastest).
+ * Blob: units in construction order; ConvBN = W (k,k,cin,cout) column-major, b[cout], beta, gamma, mu, var [cout each];
+ * Dense = W (out,in) column-major, b.  Init: glorot_uniform with nfan = (k*k*cin, k*k*cout), b = 0, beta = 0, gamma = 1,
+ * mu = 0, var = 1 (Flux defaults).
+ *
+ * bf16 emulation (mzo_set_bf16(1)) mirrors the tensor-core kernel: every stored activation is rounded to bfloat16,
+ * weights are rounded to bfloat16, sums accumulate in Float32, BatchNorm is folded into a Float32 per-channel affine;
+ * the action plane of the dynamics input and the final value / logits / reward stay Float32.
+ * ------------------------------------------------------------------------------------------ */
+enum { RN_CONV = 0, RN_DENSE = 1 };
+typedef struct { int kind, k, cin, cout, act; int w_off, b_off, beta_off, gamma_off, mu_off, var_off; } rn_unit_t;
+typedef struct { int n; rn_unit_t u[64]; int base, n_params; } rn_net_t;
+typedef struct { rn_net_t net[3]; int trunk[3], blocks; int head1_first[3], head2_first[3]; } rn_model_t;
+
+static void rn_add_conv(rn_net_t *n, int k, int cin, int cout, int act, int *off) {
+    rn_unit_t *u = &n->u[n->n++]; memset(u, 0, sizeof(*u));
+    u->kind = RN_CONV; u->k = k; u->cin = cin; u->cout = cout; u->act = act;
+    u->w_off = *off; *off += k * k * cin * cout; u->b_off = *off; *off += cout;
+    u->beta_off = *off; *off += cout; u->gamma_off = *off; *off += cout; u->mu_off = *off; *off += cout; u->var_off = *off; *off += cout;
+}
+static void rn_add_dense(rn_net_t *n, int in, int out, int act, int *off) {
+    rn_unit_t *u = &n->u[n->n++]; memset(u, 0, sizeof(*u));
+    u->kind = RN_DENSE; u->k = 1; u->cin = in; u->cout = out; u->act = act;
+    u->w_off = *off; *off += in * out; u->b_off = *off; *off += out;
+}
+static void rn_add_blocks(rn_net_t *n, int k, int nf, int nb, int *off) {
+    for (int i = 0; i < nb; i++) { rn_add_conv(n, k, nf, nf, ACT_RELU, off); rn_add_conv(n, k, nf, nf, ACT_ID, off); }
+}
+static void rn_add_scalar_head(rn_net_t *n, const mzo_config *c, int f, int first_act, int out, int out_act, int *off) {
+    rn_add_conv(n, 1, c->rn_num_filters, f, ACT_RELU, off);
+    rn_add_dense(n, c->W * c->H * f, c->width_hidden, first_act, off);
+    for (int i = 0; i < c->depth_value; i++) rn_add_dense(n, c->width_hidden, c->width_hidden, ACT_RELU, off);
+    rn_add_dense(n, c->width_hidden, out, out_act, off);
+}
+static void rn_build(const mzo_config *c, rn_model_t *m) {
+    int off = 0, nf = c->rn_num_filters, nb = c->rn_num_blocks;
+    memset(m, 0, sizeof(*m)); m->blocks = nb;
+    rn_net_t *r = &m->net[0]; r->base = off;
+    rn_add_conv(r, c->rn_kernel, obs_planes(c), nf, ACT_RELU, &off); rn_add_blocks(r, c->rn_kernel, nf, nb, &off);
+    r->n_params = off - r->base; m->trunk[0] = r->n;
+    rn_net_t *p = &m->net[1]; p->base = off;
+    rn_add_conv(p, 1, nf, nf, ACT_RELU, &off); rn_add_blocks(p, 1, nf, nb, &off); m->trunk[1] = p->n;
+    m->head1_first[1] = p->n; rn_add_scalar_head(p, c, c->rn_first_head_filters, ACT_RELU, 1, ACT_TANH, &off);
+    m->head2_first[1] = p->n; rn_add_scalar_head(p, c, c->rn_second_head_filters, ACT_ID, c->A, ACT_ID, &off);
+    p->n_params = off - p->base;
+    rn_net_t *d = &m->net[2]; d->base = off;
+    rn_add_conv(d, 1, nf + 1, nf, ACT_RELU, &off); rn_add_blocks(d, 1, nf, nb, &off); m->trunk[2] = d->n;
+    m->head1_first[2] = d->n; rn_add_conv(d, 1, nf, nf, ACT_RELU, &off); rn_add_blocks(d, 1, nf, nb, &off);
+    m->head2_first[2] = d->n; rn_add_scalar_head(d, c, c->rn_first_head_filters, ACT_RELU, 1, ACT_TANH, &off);
+    d->n_params = off - d->base;
+}
+static int rn_num_params(const mzo_config *c, int net) {
+    rn_model_t m; rn_build(c, &m);
+    return net < 3 ? m.net[net].n_params : m.net[0].n_params + m.net[1].n_params + m.net[2].n_params;
+}
+static void rn_init_weights(const mzo_config *c, uint64_t seed, float *blob) {
+    rn_model_t m; rn_build(c, &m);
+    for (int n = 0; n < 3; n++) for (int ui = 0; ui < m.net[n].n; ui++) {
+        const rn_unit_t *u = &m.net[n].u[ui];
+        int nw = u->k * u->k * u->cin * u->cout;
+        float scale = sqrtf(24.0f / (float)(u->k * u->k * (u->cin + u->cout)));
+        for (int i = 0; i < nw; i += 4) {
+            uint32_t r[4]; mzo_philox(seed, STREAM_INIT, (uint32_t)n, (uint32_t)ui, (uint32_t)(i / 4), 0, r);
+            for (int j = 0; j < 4 && i + j < nw; j++) blob[u->w_off + i + j] = (u32_to_unit(r[j]) - 0.5f) * scale;
+        }
+        for (int o = 0; o < u->cout; o++) {
+            blob[u->b_off + o] = 0.0f;
+            if (u->kind == RN_CONV) { blob[u->beta_off + o] = 0.0f; blob[u->gamma_off + o] = 1.0f; blob[u->mu_off + o] = 0.0f; blob[u->var_off + o] = 1.0f; }
+        }
+    }
+}
+static inline float rn_store(float v) { return g_bf16 ? bf16_round(v) : v; }   /* a stored activation */
+static inline float rn_act(float v, int act) { return act == ACT_RELU ? (v > 0.0f ? v : 0.0f) : act == ACT_TANH ? mzo_tanhf(v) : v; }
+/* ConvBN on a (W,H,cin) array (cell fastest).  skip (may be NULL) is added after the BatchNorm, before `act`
+ * (SkipConnection(layers, +) then relu, :157-158).  extra_plane >= 0: the LAST input channel is a constant plane whose
+ * value is rowval (the dynamics action plane) and `in` holds only cin-1 channels, scaled by in_mul (state * 2). */
+static void rn_conv(const mzo_config *c, const float *blob, const rn_unit_t *u, const float *in, float in_mul, int has_plane, float plane,
+                    const float *skip, int act, float *out) {
+    int W = c->W, H = c->H, cells = W * H, k = u->k, pad = k / 2, cin = u->cin, cout = u->cout;
+    const float *w = blob + u->w_off;
+    for (int co = 0; co < cout; co++) {
+        float den = sqrtf(blob[u->var_off + co] + 1e-5f), gamma = blob[u->gamma_off + co], beta = blob[u->beta_off + co], mu = blob[u->mu_off + co], b = blob[u->b_off + co];
+        for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
+            float acc = 0.0f, v;
+            int cmain = has_plane ? cin - 1 : cin;
+            for (int ci = 0; ci < cmain; ci++) for (int kb = 0; kb < k; kb++) for (int ka = 0; ka < k; ka++) {
+                int sx = x + pad - ka, sy = y + pad - kb;
+                if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
+                float wv = w[ka + k * (kb + k * (ci + cin * co))], xv = in[sx + W * sy + cells * ci];
+                if (g_bf16) acc = fmaf(bf16_round(wv), xv, acc);           /* operands already stored as bf16; in_mul applied below (power of two) */
+                else acc = fmaf(wv, xv * in_mul, acc);
+            }
+            if (g_bf16) {   /* the kernel's folded Float32 epilogue: acc * (mul * s) + plane * (w_plane * s) + ((b - mu) * s + beta) */
+                float s = gamma / den, S = in_mul * s, T = fmaf(b - mu, s, beta), E = has_plane ? w[0 + k * (0 + k * ((cin - 1) + cin * co))] * s : 0.0f;
+                v = fmaf(acc, S, fmaf(plane, E, T));
+            } else {
+                if (has_plane) acc = fmaf(w[0 + k * (0 + k * ((cin - 1) + cin * co))], plane, acc);
+                v = acc + b;
+                v = ((gamma * (v - mu)) / den) + beta;                       /* Flux BatchNorm, test mode */
+            }
+            if (skip) v = v + skip[x + W * y + cells * co];
+            out[x + W * y + cells * co] = rn_store(rn_act(v, act));
+        }
+    }
+}
+static void rn_dense(const float *blob, const rn_unit_t *u, const float *x, int final, float *y) {
+    const float *W = blob + u->w_off, *b = blob + u->b_off;
+    for (int o = 0; o < u->cout; o++) {
+        float acc = 0.0f;
+        for (int k = 0; k < u->cin; k++) acc = fmaf(g_bf16 ? bf16_round(W[o + (size_t)u->cout * k]) : W[o + (size_t)u->cout * k], x[k], acc);
+        float v = rn_act(acc + b[o], u->act);
+        y[o] = final ? v : rn_store(v);
+    }
+}
+/* ConvBN(relu) + num_blocks blocks starting at unit `first`; returns the index after the tower; result in out (may alias in) */
+static int rn_tower(const mzo_config *c, const float *blob, const rn_net_t *n, int first, int nb, const float *in, float in_mul, int has_plane, float plane, float *out) {
+    static __thread float t1[MZO_MAX_HIDDEN + 64], t2[MZO_MAX_HIDDEN + 64];
+    rn_conv(c, blob, &n->u[first], in, in_mul, has_plane, plane, NULL, ACT_RELU, t1);
+    int ui = first + 1;
+    for (int b = 0; b < nb; b++, ui += 2) {
+        rn_conv(c, blob, &n->u[ui], t1, 1.0f, 0, 0.0f, NULL, ACT_RELU, t2);
+        rn_conv(c, blob, &n->u[ui + 1], t2, 1.0f, 0, 0.0f, t1, ACT_RELU, out);       /* relu.(x + layers(x)) */
+        memcpy(t1, out, sizeof(float) * (size_t)c->W * c->H * n->u[ui + 1].cout);
+    }
+    if (nb == 0) memcpy(out, t1, sizeof(float) * (size_t)c->W * c->H * n->u[first].cout);
+    return ui;
+}
+static void rn_scalar_head(const mzo_config *c, const float *blob, const rn_net_t *n, int first, const float *trunk, float *out) {
+    float f[MZO_MAX_OBS * 2], a[256], b[256];
+    rn_conv(c, blob, &n->u[first], trunk, 1.0f, 0, 0.0f, NULL, ACT_RELU, f);   /* flatten: cell fastest, then filter */
+    const float *cur = f; int ui = first + 1, nd = c->depth_value + 2;
+    for (int i = 0; i < nd; i++, ui++) {
+        float *dst = (i == nd - 1) ? out : ((i & 1) ? b : a);
+        rn_dense(blob, &n->u[ui], cur, i == nd - 1, dst);
+        cur = dst;
+    }
+}
+static void rn_representation(const mzo_config *c, const float *blob, const float *stacked, float *hidden) {
+    rn_model_t m; rn_build(c, &m);
+    static __thread float in[MZO_MAX_OBS * 4];
+    for (int i = 0; i < stack_size(c); i++) in[i] = rn_store(stacked[i]);
+    rn_tower(c, blob, &m.net[0], 0, m.blocks, in, 1.0f, 0, 0.0f, hidden);
+}
+static void softmax(const float *x, int n, float *y);
+static void rn_prediction(const mzo_config *c, const float *blob, const float *hidden, float *value, float *policy) {
+    rn_model_t m; rn_build(c, &m);
+    static __thread float in[MZO_MAX_HIDDEN], t[MZO_MAX_HIDDEN];
+    float logits[MZO_MAX_A];
+    for (int i = 0; i < c->hidden_state_size; i++) in[i] = rn_store(hidden[i]);
+    rn_tower(c, blob, &m.net[1], 0, m.blocks, in, 1.0f, 0, 0.0f, t);
+    rn_scalar_head(c, blob, &m.net[1], m.head1_first[1], t, value);
+    rn_scalar_head(c, blob, &m.net[1], m.head2_first[1], t, logits);
+    softmax(logits, c->A, policy);
+}
+/* sa = (W,H,nf+1): nf state channels (already doubled by make_state_action) and the constant action plane */
+static void rn_dynamics(const mzo_config *c, const float *blob, const float *sa, float *next_hidden, float *reward) {
+    rn_model_t m; rn_build(c, &m);
+    static __thread float in[MZO_MAX_HIDDEN], t[MZO_MAX_HIDDEN];
+    int hs = c->hidden_state_size;
+    float plane = sa[hs];
+    if (g_bf16) { for (int i = 0; i < hs; i++) in[i] = bf16_round(sa[i] * 0.5f); }   /* the kernel stages h and multiplies the accumulator by 2 */
+    else for (int i = 0; i < hs; i++) in[i] = sa[i];
+    rn_tower(c, blob, &m.net[2], 0, m.blocks, in, g_bf16 ? 2.0f : 1.0f, 1, plane, t);
+    rn_tower(c, blob, &m.net[2], m.head1_first[2], m.blocks, t, 1.0f, 0, 0.0f, next_hidden);
+    rn_scalar_head(c, blob, &m.net[2], m.head2_first[2], t, reward);
+}
+
 typedef struct { mzo_config cfg; net_t nets[3]; const float *blob; } model_t;
 static void model_init(model_t *m, const mzo_config *c, const float *blob) { m->cfg = *c; build_nets(c, m->nets); m->blob = blob; }
 
 static void representation(const model_t *m, const float *stacked, float *hidden) {
+    if (m->cfg.net_type == 1) { rn_representation(&m->cfg, m->blob, stacked, hidden); return; }
     run_layers(m->blob, m->nets[0].trunk, m->nets[0].n_trunk, stacked, hidden);
 }
 static void prediction(const model_t *m, const float *hidden, float *value, float *policy) {
+    if (m->cfg.net_type == 1) { rn_prediction(&m->cfg, m->blob, hidden, value, policy); return; }
     float t[256], logits[MZO_MAX_A];
     const net_t *n = &m->nets[1];
     run_layers(m->blob, n->trunk, n->n_trunk, hidden, t);
@@ -302,6 +497,7 @@ static void prediction(const model_t *m, const float *hidden, float *value, floa
     softmax(logits, m->cfg.A, policy); /* Learning.jl:114: the policy head ENDS in softmax (Q1) */
 }
 static void dynamics(const model_t *m, const float *sa, float *next_hidden, float *reward) {
+    if (m->cfg.net_type == 1) { rn_dynamics(&m->cfg, m->blob, sa, next_hidden, reward); return; }
     float t[256];
     const net_t *n = &m->nets[2];
     run_layers(m->blob, n->trunk, n->n_trunk, sa, t);
@@ -558,7 +754,7 @@ static void backpropagate(const mzo_config *c, node_t **path, int n, float value
 /* make_state_action (SelfPlay.jl:7-14): doubles the CALLER's state in place (Q6); action plane =
  * Float32(Float64(a) / length(action_space)). */
 static void make_state_action(const mzo_config *c, float *state, int action, float *sa) {
-    int on = obs_size(c), plane = c->W * c->H;
+    int on = c->hidden_state_size, plane = c->W * c->H;   /* the state is the (W,H,channels) hidden state */
     float av = (float)((double)action / (double)c->A);
     for (int i = 0; i < on; i++) { state[i] = state[i] * 2.0f; sa[i] = state[i]; }
     for (int i = 0; i < plane; i++) sa[on + i] = av;
@@ -587,7 +783,7 @@ static void run_mcts(tree_t *t, const float *stacked, uint32_t legal, int to_pla
             vtp = vtp % c->num_players + 1;                              /* mod1(vtp+1, nplayers) */
         }
         node_t *parent = path[np - 2];                                   /* :270 */
-        float value, policy[MZO_MAX_A], sa[MZO_MAX_OBS + 64], reward;
+        float value, policy[MZO_MAX_A], sa[MZO_MAX_HIDDEN + 64], reward;
         prediction(m, parent->hidden_state, &value, policy);             /* :271 -- PARENT state (Q5) */
         make_state_action(c, parent->hidden_state, action, sa);          /* :273 */
         float *nh = t->hiddens + (size_t)(t->n_hiddens++) * hs;

@@ -32,6 +32,7 @@ extern "C" {
 
 #define MZO_MAX_A 16      /* max action-space size */
 #define MZO_MAX_OBS 192   /* max W*H*C of one observation */
+#define MZO_MAX_HIDDEN 4096 /* max hidden_state_size (ResNet: W*H*num_filters) */
 #define MZO_MAX_T 64      /* max moves stored per game (max_moves+1) */
 
 enum { MZO_GAME_TICTACTOE = 0, MZO_GAME_CONNECT = 1 };
@@ -65,6 +66,14 @@ typedef struct mzo_config {
     int32_t depth_policy, depth_value, depth_reward, depth_state_head;
     int32_t hidden_state_size;
     int32_t reward_activation_tanh; /* 1 = tanh (params.jl:28), 0 = identity */
+    /* ResNetHP (src/Constructors.jl:77-90) -- the REPAIRED spec of the residual networks (Learning.jl:148-255 as
+     * written reference undefined names and never ran; see the ResNet section of mz_oracle.c) */
+    int32_t net_type;               /* 0 = FeedForwardHP networks, 1 = ResNetHP networks */
+    int32_t rn_num_blocks;          /* num_blocks */
+    int32_t rn_num_filters;         /* num_filters: the hidden state is (W,H,num_filters) */
+    int32_t rn_kernel;              /* conv_kernel_size = (k,k), odd; representation only (Learning.jl:195,230 fix (1,1) elsewhere) */
+    int32_t rn_first_head_filters;  /* num_first_head_filters = 1 (value and reward heads) */
+    int32_t rn_second_head_filters; /* num_second_head_filters = 2 (policy head) */
 } mzo_config;
 
 void mzo_default_config(mzo_config *cfg);            /* params.jl:2-29 defaults */

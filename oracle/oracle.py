@@ -31,6 +31,8 @@ class Config(C.Structure):
         ("depth_dynamics", C.c_int32), ("depth_policy", C.c_int32), ("depth_value", C.c_int32),
         ("depth_reward", C.c_int32), ("depth_state_head", C.c_int32), ("hidden_state_size", C.c_int32),
         ("reward_activation_tanh", C.c_int32),
+        ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
+        ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
     ]
 
 
@@ -129,8 +131,17 @@ def default_config(**kw):
 
 def sizes(cfg):
     planes = cfg.C * (cfg.stacked_observations + 1) + cfg.stacked_observations
-    return dict(obs=cfg.W * cfg.H * cfg.C, stack=cfg.W * cfg.H * planes, sa=cfg.W * cfg.H * (cfg.C + 1),
+    return dict(obs=cfg.W * cfg.H * cfg.C, stack=cfg.W * cfg.H * planes, sa=cfg.hidden_state_size + cfg.W * cfg.H,
                 Tmax=cfg.max_moves + 1, K1=cfg.num_unroll_steps + 1, A=cfg.A, hidden=cfg.hidden_state_size)
+
+
+def resnet_config(**kw):
+    """TicTacToe with the repaired ResNetHP networks (hidden state (W,H,num_filters))."""
+    base = dict(net_type=1, rn_num_blocks=2, rn_num_filters=64, rn_kernel=3, rn_first_head_filters=1, rn_second_head_filters=2)
+    base.update(kw)
+    cfg = default_config(**base)
+    cfg.hidden_state_size = cfg.W * cfg.H * cfg.rn_num_filters
+    return cfg
 
 
 def num_params(cfg, net=3):
