@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 1
+#define MZ_ABI_VERSION 2
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
@@ -34,6 +34,7 @@ enum { MZ_TIE_PHILOX = 0, MZ_TIE_FIRST = 1 };
 enum { MZ_GRAD_REFERENCE_L2 = 0, MZ_GRAD_BPTT = 1 };
 /* network arithmetic: exact fp32 (bit-identical to the oracle contract) or bf16 tcgen05 tensor cores */
 enum { MZ_NN_FP32_EXACT = 0, MZ_NN_BF16_TC = 1 };
+enum { MZ_NET_FEEDFORWARD = 0, MZ_NET_RESNET = 1 };
 enum { MZ_NET_REPRESENTATION = 0, MZ_NET_PREDICTION = 1, MZ_NET_DYNAMICS = 2, MZ_NET_ALL = 3 };
 
 /* POD mirror of Config (src/Constructors.jl:18-52, games/tictactoe/params.jl:2-16) and FeedForwardHP
@@ -66,6 +67,15 @@ typedef struct mz_config {
     /* B200 execution parameters (no reference counterpart) */
     int32_t num_slots;            /* concurrent self-play games resident on this GPU (e.g. 4096) */
     int32_t nn_mode;              /* MZ_NN_* */
+    /* ResNetHP (src/Constructors.jl:77-90): the residual networks of src/Learning.jl:148-255 in their repaired form
+     * (the reference's constructors read undefined names and never ran; DESIGN.md "ResNet").  net_type = MZ_NET_RESNET
+     * needs nn_mode = MZ_NN_BF16_TC and hidden_state_size = W*H*rn_num_filters; width_hidden / depth_value are shared. */
+    int32_t net_type;               /* MZ_NET_FEEDFORWARD | MZ_NET_RESNET */
+    int32_t rn_num_blocks;          /* num_blocks */
+    int32_t rn_num_filters;         /* num_filters (64) */
+    int32_t rn_kernel;              /* conv_kernel_size = (k,k) of the representation network, 1 or 3 */
+    int32_t rn_first_head_filters;  /* num_first_head_filters = 1 */
+    int32_t rn_second_head_filters; /* num_second_head_filters = 2 */
 } mz_config;
 
 typedef struct mz_ctx mz_ctx;

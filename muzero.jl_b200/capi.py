@@ -17,6 +17,7 @@ OK, E_ARG, E_CUDA, E_STATE, E_NCCL, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 GAME_TICTACTOE, GAME_CONNECT = 0, 1
 TIE_PHILOX, TIE_FIRST = 0, 1
 GRAD_REFERENCE_L2, GRAD_BPTT = 0, 1
+NET_FEEDFORWARD, NET_RESNET = 0, 1
 NN_FP32_EXACT, NN_BF16_TC = 0, 1
 NET_REPRESENTATION, NET_PREDICTION, NET_DYNAMICS, NET_ALL = 0, 1, 2, 3
 KERNEL_FAMILIES = ("selfplay_move", "save_refill", "replay_gather", "learn_forward_loss", "adam", "nn_batch", "env")
@@ -42,6 +43,8 @@ class MzConfig(C.Structure):
         ("depth_dynamics", C.c_int32), ("depth_policy", C.c_int32), ("depth_value", C.c_int32),
         ("depth_reward", C.c_int32), ("depth_state_head", C.c_int32), ("hidden_state_size", C.c_int32),
         ("reward_activation_tanh", C.c_int32), ("num_slots", C.c_int32), ("nn_mode", C.c_int32),
+        ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
+        ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
     ]
 
     def copy(self):
@@ -135,9 +138,19 @@ def default_config(**kw):
     return cfg
 
 
+def resnet_config(**kw):
+    """Default Config with the (repaired) ResNetHP networks on the tensor cores: hidden state (W,H,num_filters)."""
+    base = dict(net_type=NET_RESNET, nn_mode=NN_BF16_TC, rn_num_blocks=2, rn_num_filters=64, rn_kernel=3, rn_first_head_filters=1,
+                rn_second_head_filters=2)
+    base.update(kw)
+    cfg = default_config(**base)
+    cfg.hidden_state_size = cfg.W * cfg.H * cfg.rn_num_filters
+    return cfg
+
+
 def sizes(cfg):
     planes = cfg.C * (cfg.stacked_observations + 1) + cfg.stacked_observations
-    return dict(obs=cfg.W * cfg.H * cfg.C, stack=cfg.W * cfg.H * planes, sa=cfg.W * cfg.H * (cfg.C + 1),
+    return dict(obs=cfg.W * cfg.H * cfg.C, stack=cfg.W * cfg.H * planes, sa=cfg.hidden_state_size + cfg.W * cfg.H,
                 Tmax=cfg.max_moves + 1, K1=cfg.num_unroll_steps + 1, A=cfg.A, hidden=cfg.hidden_state_size)
 
 

@@ -9,7 +9,8 @@
 #include <vector>
 #include "mz_host.h"
 #include "mz_learner_bptt.cuh"
-#include "mz_kernels_tc.cuh"
+#include "mz_rn_host.h"
+#include "mz_kernels_rn.cuh"
 
 namespace {
 
@@ -72,6 +73,8 @@ struct mz_ctx {
     dev_buf scratch[12];
     int64_t adam_t = 0; double bp1 = 0.9, bp2 = 0.999;
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    // net_type = MZ_NET_RESNET
+    mzh::rn_model rn; unsigned char *d_rn_image = nullptr; mz_rn_step *d_rn_steps = nullptr; size_t smem_bytes_rn = 0; std::vector<float> rn_blob;
     // grad_mode = MZ_GRAD_BPTT
     mzh::bptt_program bptt; mz_bstage *d_bstages[2] = {nullptr, nullptr}; size_t smem_bytes_bptt = 0;
     float *d_act = nullptr, *d_gpart = nullptr; int bptt_tiles_cap = 0;
@@ -139,6 +142,14 @@ int alloc_batch(mz_ctx *c, int B) {
 }
 
 int upload_weights(mz_ctx *c, const std::vector<float> &src) {
+    if (c->cfg.net_type == MZ_NET_RESNET) {   // blob -> bf16 B-operand images + folded BatchNorm parameters, one block per program step
+        c->rn_blob = src;
+        std::vector<unsigned char> image;
+        mzh::rn_pack(c->rn, src.data(), image);
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_image, image.data(), (size_t)c->rn.image_bytes, cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        return MZ_OK;
+    }
     std::vector<float> dev((size_t)c->M.P.total_floats);
     mzh::pack_weights(c->M.P, src.data(), dev.data());
     MZ_CUDA(c, cudaMemcpyAsync(c->d_w, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -153,6 +164,7 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
     return MZ_OK;
 }
 int download_weights(mz_ctx *c, std::vector<float> &src) {
+    if (c->cfg.net_type == MZ_NET_RESNET) { src = c->rn_blob; return MZ_OK; }   // inference-only networks: the blob is kept on the host
     std::vector<float> dev((size_t)c->M.P.total_floats);
     MZ_CUDA(c, cudaMemcpyAsync(dev.data(), c->d_w, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -172,6 +184,14 @@ int write_counters(mz_ctx *c) {
     return MZ_OK;
 }
 
+int ctx_net_params(const mz_ctx *c, int net) {
+    if (c->cfg.net_type == MZ_NET_RESNET) return net == MZ_NET_ALL ? mzh::rn_total_params(c->rn) : c->rn.n_params[net];
+    return ctx_net_params(c, net);
+}
+int ctx_net_offset(const mz_ctx *c, int net) {
+    if (c->cfg.net_type == MZ_NET_RESNET) return net == MZ_NET_ALL ? 0 : c->rn.base[net];
+    return ctx_net_offset(c, net);
+}
 template <typename T> int h2d(mz_ctx *c, dev_buf &b, const T *host, size_t n, T **out) {
     MZ_CUDA(c, b.ensure(n * sizeof(T) + 16));
     if (host && n) MZ_CUDA(c, cudaMemcpyAsync(b.p, host, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
@@ -186,6 +206,7 @@ template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
 
 int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2) {
     const mz_params &P = c->M.P;
+    if (c->cfg.net_type == MZ_NET_RESNET) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only (the ResNet path is self-play inference)");
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
@@ -252,6 +273,10 @@ const char *mz_last_error(mz_ctx *ctx) { return ctx ? ctx->err.c_str() : tl_erro
 int mz_num_params(const mz_config *cfg, int net) {
     if (!cfg || net < 0 || net > 3) return fail(nullptr, MZ_E_ARG, "bad arguments");
     mzh::model M; if (const char *e = mzh::build_model(*cfg, M)) return fail(nullptr, MZ_E_ARG, "%s", e);
+    if (cfg->net_type == MZ_NET_RESNET) {
+        mzh::rn_model R; mzh::rn_units_build(*cfg, R);
+        return net == MZ_NET_ALL ? mzh::rn_total_params(R) : R.n_params[net];
+    }
     return mzh::net_params(M.P, net);
 }
 
@@ -263,7 +288,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (const char *e = mzh::build_model(*cfg, c->M)) { int r = fail(nullptr, MZ_E_ARG, "%s", e); delete c; return r; }
     if (cfg->replay_buffer_size < cfg->num_slots) { int r = fail(nullptr, MZ_E_ARG, "replay_buffer_size must be >= num_slots"); delete c; return r; }
     if (cfg->nn_mode != MZ_NN_FP32_EXACT && cfg->nn_mode != MZ_NN_BF16_TC) { int r = fail(nullptr, MZ_E_ARG, "unknown nn_mode %d", cfg->nn_mode); delete c; return r; }
-    if (cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
+    if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }
@@ -272,16 +297,29 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     cudaDeviceProp prop; MZ_CREATE(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); mz_destroy(c); return r; }
     c->sm_count = prop.multiProcessorCount;
+    const bool resnet = cfg->net_type == MZ_NET_RESNET;
+    if (resnet) {
+        if (const char *er = mzh::rn_build(*cfg, c->M.P, c->rn)) { int r = fail(nullptr, MZ_E_ARG, "%s", er); mz_destroy(c); return r; }
+        c->M.P.tree_stride_bytes = c->rn.R.tree_stride_bytes; c->M.P.hidden_off_bytes = c->rn.R.hidden_off_bytes;
+        c->M.P.n_params = mzh::rn_total_params(c->rn); c->M.P.total_floats = 4;
+        c->smem_bytes_rn = mz_rn_smem_bytes(c->rn.R.slot_bytes, c->M.P.S, c->rn.R.ntrees);
+        if (c->smem_bytes_rn + 1024 > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "the ResNet search kernel needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes_rn, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
+        MZ_CREATE(allow_max_smem(mz_k_search_rn<MZ_MODE_API>, prop)); MZ_CREATE(allow_max_smem(mz_k_search_rn<MZ_MODE_SLOTS>, prop)); MZ_CREATE(allow_max_smem(mz_k_rn_forward, prop));
+        MZ_CREATE(cudaMalloc((void **)&c->d_rn_image, (size_t)c->rn.image_bytes + 4096));
+        MZ_CREATE(dmalloc(&c->d_rn_steps, c->rn.steps.size() + 1));
+        MZ_CREATE(cudaMemcpy(c->d_rn_steps, c->rn.steps.data(), c->rn.steps.size() * sizeof(mz_rn_step), cudaMemcpyHostToDevice));
+        c->rn_blob.assign((size_t)c->M.P.n_params, 0.0f);
+    }
     const mz_params &P = c->M.P;
-    c->smem_bytes = mz_smem_bytes(c->M.max_dim, c->M.max_layer_floats, P.hidden_pad, P.S);
+    c->smem_bytes = resnet ? 0 : mz_smem_bytes(c->M.max_dim, c->M.max_layer_floats, P.hidden_pad, P.S);
     if (c->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API>, prop));
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS>, prop));
     MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
     MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
-    if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; }
+    if (!resnet) { if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; } }
     c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
-    if (c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {   // 4 KB head-room for the kernel's static shared memory
+    if (!resnet && c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {   // 4 KB head-room for the kernel's static shared memory
         MZ_CREATE(allow_max_smem(mz_k_learn_bptt, prop));
         for (int g = 0; g < 2; g++) {
             MZ_CREATE(dmalloc(&c->d_bstages[g], c->bptt.stages[g].size() + 1));
@@ -339,7 +377,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    void *ptrs[] = {c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -378,25 +416,26 @@ int mz_device_info(mz_ctx *c, int32_t *sm_count, int32_t *cc_major, int32_t *cc_
 int mz_init_weights(mz_ctx *c, uint64_t seed) {
     MZ_CHECK_CTX(c);
     std::vector<float> src((size_t)c->M.P.n_params);
-    mzh::init_weights(c->M.P, seed, src.data());
+    if (c->cfg.net_type == MZ_NET_RESNET) mzh::rn_init_weights(c->rn, seed, src.data());
+    else mzh::init_weights(c->M.P, seed, src.data());
     return upload_weights(c, src);
 }
 int mz_set_weights(mz_ctx *c, int net, const float *blob, int64_t n) {
     MZ_CHECK_CTX(c);
     if (net < 0 || net > 3 || !blob) return fail(c, MZ_E_ARG, "bad net id or NULL blob");
-    if (n != mzh::net_params(c->M.P, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, mzh::net_params(c->M.P, net));
+    if (n != ctx_net_params(c, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, ctx_net_params(c, net));
     std::vector<float> src;
     if (net == MZ_NET_ALL) src.assign(blob, blob + n);                    // whole model: nothing to merge with
-    else { MZ_TRY(download_weights(c, src)); memcpy(src.data() + mzh::net_src_offset(c->M.P, net), blob, (size_t)n * sizeof(float)); }
+    else { MZ_TRY(download_weights(c, src)); memcpy(src.data() + ctx_net_offset(c, net), blob, (size_t)n * sizeof(float)); }
     return upload_weights(c, src);
 }
 int mz_get_weights(mz_ctx *c, int net, float *blob, int64_t n) {
     MZ_CHECK_CTX(c);
     if (net < 0 || net > 3 || !blob) return fail(c, MZ_E_ARG, "bad net id or NULL blob");
-    if (n != mzh::net_params(c->M.P, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, mzh::net_params(c->M.P, net));
+    if (n != ctx_net_params(c, net)) return fail(c, MZ_E_ARG, "weight blob has %lld floats, net %d needs %d", (long long)n, net, ctx_net_params(c, net));
     std::vector<float> src;
     MZ_TRY(download_weights(c, src));
-    memcpy(blob, src.data() + mzh::net_src_offset(c->M.P, net), (size_t)n * sizeof(float));
+    memcpy(blob, src.data() + ctx_net_offset(c, net), (size_t)n * sizeof(float));
     return MZ_OK;
 }
 
@@ -406,13 +445,20 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
     if (B < 0 || (B > 0 && (!in || !out1))) return fail(c, MZ_E_ARG, "NULL buffer");
     if (B == 0) return MZ_OK;
     const mz_params &P = c->M.P;
-    const int in_dim = P.layers[P.nets[net].first].in;
+    const bool resnet = c->cfg.net_type == MZ_NET_RESNET;
+    const int in_dim = resnet ? (net == 0 ? P.stack_size : net == 1 ? P.hidden : P.sa_size) : P.layers[P.nets[net].first].in;
     float *d_in, *d_o1, *d_o2;
     MZ_TRY(h2d(c, c->scratch[0], in, (size_t)B * in_dim, &d_in));
     MZ_TRY(h2d<float>(c, c->scratch[1], nullptr, (size_t)B * n1, &d_o1));
     MZ_TRY(h2d<float>(c, c->scratch[2], nullptr, (size_t)B * (n2 ? n2 : 1), &d_o2));
     mz_nn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.net = net; a.in = d_in; a.out1 = d_o1; a.out2 = d_o2;
-    if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+    if (resnet) {
+        unsigned char *d_pool;
+        MZ_TRY(h2d<unsigned char>(c, c->scratch[3], nullptr, (size_t)B * c->rn.R.node_bytes, &d_pool));
+        mz_search_rn_args t{}; t.image = c->d_rn_image; t.steps = c->d_rn_steps; t.net = net; t.B = B; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2; t.scratch_pool = d_pool;
+        const int nt = c->rn.R.ntrees;
+        launch_scope ls(c, 5); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+    } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
         mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
         launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
     } else { launch_scope ls(c, 5); mz_k_nn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
@@ -510,7 +556,11 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = m; a.max_dim = c->M.max_dim;
         a.max_layer_floats = c->M.max_layer_floats; a.exploration = exploration; a.stacked = d_st; a.legal = d_legal; a.to_play = d_tp; a.game_id = d_gid;
         a.move_idx = d_mv; a.visit_counts = d_vc; a.root_value = d_rv; a.root_priors = d_pri; a.stats = nullptr;
-        if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+        if (c->cfg.net_type == MZ_NET_RESNET) {
+            mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
+            const int nt = c->rn.R.ntrees;
+            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_API><<<(m + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+        } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
         } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
@@ -563,7 +613,11 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         if (active == 0) break;
         if (guard > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         total_moves += active;
-        if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
+        if (c->cfg.net_type == MZ_NET_RESNET) {
+            mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
+            const int nt = c->rn.R.ntrees;
+            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+        } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
         } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }

@@ -191,6 +191,38 @@ struct mz_bptt_plan {
 };
 
 // ------------------------------------------------------------------------------------------------
+// ResNet networks on the tensor cores (net_type = MZ_NET_RESNET): host-built step program (mz_rn_host.h) executed by
+// mz_kernels_rn.cuh.  Activations are bf16 tiles of 128 rows x 64 channels (rows = (tree, cell) pairs for the
+// convolution towers, rows = trees for the dense heads), UMMA K-major SWIZZLE_128B; a step = up to 4 jobs (one MMA
+// chain + epilogue each) sharing one staged weight block.
+// ------------------------------------------------------------------------------------------------
+#define MZ_RN_TILES 4
+enum { MZ_RN_BUF_X0 = 0, MZ_RN_BUF_T0 = 4, MZ_RN_BUF_HV = 8, MZ_RN_BUF_HP = 9, MZ_RN_BUF_S0 = 10, MZ_RN_BUF_S1 = 11 };
+enum { MZ_RN_EPI_TILE = 0, MZ_RN_EPI_HEAD = 1, MZ_RN_EPI_F32 = 2 };
+enum { MZ_RN_F_PLANE = 1, MZ_RN_F_POOL = 2, MZ_RN_F_TREES = 4 };
+enum { MZ_RN_OUT_V = 0, MZ_RN_OUT_L = 1, MZ_RN_OUT_R = 2 };
+struct mz_rn_job {
+    uint8_t a_buf, dst_buf, dst2_buf, skip_buf;   // buffer ids (0xff = none)
+    uint8_t epi, n16, kblocks, act;
+    uint8_t wg, acc, flags, nfa;                  // wg: warpgroup running the epilogue; acc: TMEM accumulator slot (64 columns each)
+    uint8_t nfb, out, out_id, pad_;
+    int32_t w_sub, p_sub;                         // byte offsets inside the step's staged block: B image; {S[64], T[64], E[64]} floats
+    int32_t wref;                                 // host-side bookkeeping
+};
+struct mz_rn_step {
+    int32_t w_off, w_bytes;                       // the step's block inside the global weight image
+    uint8_t njobs, ntaps, tap, last;              // k x k convolutions: one step per tap, epilogue after the last
+    int8_t dx, dy; uint8_t accumulate, pad_;      // tap: A = copy of a_buf shifted by (dx, dy) cells
+    mz_rn_job jobs[MZ_RN_TILES];
+};
+struct mz_rn_params {
+    int32_t cells, nf, tpt, ntrees, rows_valid, node_bytes;
+    int32_t planes, ksize, nvf, npf;
+    int32_t prog_repr[2], prog_pred[2], prog_dyn[2], n_steps;
+    int32_t image_bytes, slot_bytes, hidden_off_bytes, tree_stride_bytes;
+};
+
+// ------------------------------------------------------------------------------------------------
 // Games.  TicTacToe follows games/tictactoe/game.jl including its quirks; boards are
 // two bit masks (bit a-1 = cell of action a, column-major like CartesianIndices((3,3))[a]).
 // MZ_GAME_CONNECT is the synthetic larger-board game of BASELINE.json config 4 (no reference code):

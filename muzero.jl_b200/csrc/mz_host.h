@@ -43,6 +43,7 @@ inline void default_config(mz_config *c) {   // games/tictactoe/params.jl:2-29, 
     c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
     c->num_slots = 4096; c->nn_mode = MZ_NN_FP32_EXACT;
+    c->net_type = MZ_NET_FEEDFORWARD; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
 inline const char *validate(const mz_config &c) {
@@ -51,7 +52,8 @@ inline const char *validate(const mz_config &c) {
     if (c.W < 1 || c.H < 1 || c.C != 3) return "observation_shape must be (W,H,3)";
     if (c.game == MZ_GAME_TICTACTOE && (c.W != 3 || c.H != 3 || c.A != 9)) return "TicTacToe needs observation_shape (3,3,3) and 9 actions";
     if (c.game == MZ_GAME_CONNECT && (c.A != c.H || (c.W + 1) * c.H > 64)) return "Connect needs A == H columns and (W+1)*H <= 64";
-    if (c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
+    if (c.net_type != MZ_NET_FEEDFORWARD && c.net_type != MZ_NET_RESNET) return "unknown net_type";
+    if (c.net_type == MZ_NET_FEEDFORWARD && c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
     if (c.num_players < 1 || c.num_players > 2) return "1 or 2 players";
     if (c.num_iters < 1 || c.num_iters > 1000) return "num_iters must be in 1..1000";
     if (1 + (c.num_iters + 1) * c.A > 65535) return "tree too large for 16-bit path entries";
@@ -97,7 +99,7 @@ inline float discount_pow(float g, int i) {
 
 inline const char *build_model(const mz_config &c, model &M) {
     if (const char *e = validate(c)) return e;
-    if (count_layers(c) > MZ_MAX_LAYERS) return "too many layers";
+    if (c.net_type == MZ_NET_FEEDFORWARD && count_layers(c) > MZ_MAX_LAYERS) return "too many layers";
     mz_params &P = M.P;
     memset(&P, 0, sizeof(P));
     P.game = c.game; P.W = c.W; P.H = c.H; P.C = c.C; P.A = c.A; P.P = c.num_players;
@@ -123,6 +125,16 @@ inline const char *build_model(const mz_config &c, model &M) {
     int h_bytes = (c.num_iters + 1) * P.hidden_pad * 4;
     P.nodeB_off_bytes = 0; P.hidden_off_bytes = a_bytes;
     P.tree_stride_bytes = (a_bytes + h_bytes + 127) & ~127;
+    // ucb_score (SelfPlay.jl:172-174): pb_c = log2((N + base + 1) / base) + init, then * sqrt(N)/(n+1); all Float64
+    M.pbc0.resize((size_t)c.num_iters + 2); M.sqrtN.resize((size_t)c.num_iters + 2);
+    for (int N = 0; N <= c.num_iters + 1; N++) {
+        M.pbc0[(size_t)N] = log2((double)(N + c.pb_c_base + 1) / (double)c.pb_c_base) + (double)c.pb_c_init;
+        M.sqrtN[(size_t)N] = sqrt((double)N);
+    }
+    if (c.net_type == MZ_NET_RESNET) {   // the residual networks have their own description (mz_rn_host.h); the state is (W,H,nf)
+        P.sa_size = P.hidden + P.cells; P.tc_ok = 0; M.max_dim = 4; M.max_layer_floats = 0;
+        return nullptr;
+    }
     // networks (src/Learning.jl:87-142), Flux.params order
     int src = 0, dev = 0, w = c.width_hidden;
     P.nets[0].first = P.n_layers;
@@ -170,12 +182,6 @@ inline const char *build_model(const mz_config &c, model &M) {
         if (P.layers[i].floats > M.max_layer_floats) M.max_layer_floats = P.layers[i].floats;
     }
     M.max_dim = (M.max_dim + 3) & ~3;
-    // ucb_score (SelfPlay.jl:172-174): pb_c = log2((N + base + 1) / base) + init, then * sqrt(N)/(n+1); all Float64
-    M.pbc0.resize((size_t)c.num_iters + 2); M.sqrtN.resize((size_t)c.num_iters + 2);
-    for (int N = 0; N <= c.num_iters + 1; N++) {
-        M.pbc0[(size_t)N] = log2((double)(N + c.pb_c_base + 1) / (double)c.pb_c_base) + (double)c.pb_c_init;
-        M.sqrtN[(size_t)N] = sqrt((double)N);
-    }
     return nullptr;
 }
 

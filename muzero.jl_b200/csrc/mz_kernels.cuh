@@ -124,10 +124,10 @@ __device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, cons
 // softmax(logits) (Learning.jl:114) then expand_node!'s second softmax over the legal subset (SelfPlay.jl:88-96, Q1);
 // exp() calls are spread over the lanes, both sums run in ascending action order like the scalar code.  The expanded
 // node's record is rebuilt from what is known (unvisited, prior, reward): no load.
-__device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *logits /* [a*MZ_ROWS] */,
-                                                     float reward, float prior, int ln, uint32_t segmask) {
+__device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const mz_tree &t, int node, int e, uint32_t legal, const float *logits /* [a*ls] */,
+                                                     float reward, float prior, int ln, uint32_t segmask, int ls = MZ_ROWS /* stride between logits */) {
     const bool v0 = ln < P.A, v1 = ln + 8 < P.A;
-    const float l0 = v0 ? logits[ln * MZ_ROWS] : -INFINITY, l1 = v1 ? logits[(ln + 8) * MZ_ROWS] : -INFINITY;
+    const float l0 = v0 ? logits[ln * ls] : -INFINITY, l1 = v1 ? logits[(ln + 8) * ls] : -INFINITY;
     float m = mz_seg_max(l1 > l0 ? l1 : l0, segmask);
     float e0 = v0 ? mz_expf(l0 - m) : 0.0f, e1 = v1 ? mz_expf(l1 - m) : 0.0f;
     float s = 0.0f;

@@ -1,0 +1,582 @@
+// mz_kernels_rn.cuh -- the ResNet networks (net_type = MZ_NET_RESNET, repaired src/Learning.jl:148-255) on the tcgen05
+// tensor cores, and the fused search kernel that uses them.
+//
+// Orientation (the opposite of the feed-forward tensor path): the ACTIVATIONS are the A operand.  A 1x1 convolution
+// does not mix board cells, so every (tree, cell) pair is an independent row of a [rows x 64 channels] x [64 x 64] GEMM:
+//   D[row = (tree, cell)][co] = sum_ci X[row][ci] * W[co][ci]         M = 128 rows per tile, N = 64, K = 64
+// One CTA owns 4 tiles (TicTacToe: 14 trees x 9 cells = 126 rows per tile, 56 trees per CTA; a 6x7 board: 3 trees per
+// tile).  Accumulators live in TMEM (lane = row, 64 fp32 columns per tile), so an epilogue thread owns one row: it reads
+// its 64 channels with tcgen05.ld, applies the folded BatchNorm affine (+ action-plane term, + residual), relu, and
+// writes the bf16 row of the next layer's A tile with eight 16-byte swizzled stores (and, for the last layer of the
+// dynamics state head / the representation, the same row to the tree's hidden-state slot in HBM).  Weights stream
+// through a two-slot shared-memory ring by TMA bulk copies, one block per step, prefetched one step ahead.
+// The k x k convolutions of the representation network (root only) run as k*k accumulating tap-steps over shifted
+// copies of the source tile; its first convolution is a single im2col tile built from the boards.
+// The dense heads run on the same machinery with rows = trees.
+// Execution is lock-step: all 256 threads walk the host-built step program; thread 0 issues the MMAs of a step's jobs
+// back to back (each committed to its own mbarrier), warpgroup w runs the epilogues of jobs w and w + 2, so the tensor
+// core works on the later jobs while the earlier ones are in their epilogue.
+#pragma once
+#include "mz_kernels_tc.cuh"
+
+#define MZ_RN_TMEM_COLS 256
+#define MZ_RN_TILE_BYTES 16384
+#define MZ_RN_AUX_BYTES 32768
+#define MZ_RN_OUT_ROWS 64          // trees per CTA in the fp32 head outputs / per-tree tables
+
+struct mz_rn_plan {
+    uint32_t tiles;                // X0..X3, T0..T3 (shared address)
+    uint32_t aux;                  // HV | HP (two K blocks) ; or the two scratch tiles of the tap-steps
+    uint32_t wring;                // two weight slots
+    unsigned char *tiles_ptr, *wring_ptr;
+    uint64_t *w_bar, *mma_bar, *scr_bar; uint32_t *tmem_slot;
+    float *out;                    // fp32 head outputs: V [4][64] | L [16][64] | R [4][64]
+    float *plane; int32_t *pe, *dbl, *active; unsigned long long *tree_base;
+    double *pbc0, *sqrtN; uint16_t *path;
+};
+__host__ __device__ inline size_t mz_rn_smem_bytes(int slot_bytes, int S, int ntrees) {
+    size_t tab = (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
+    size_t path = (((size_t)S + 2) * 2 * ntrees + 127) & ~(size_t)127;
+    return 1024 + 8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES + 2 * (size_t)slot_bytes + 256 + 24 * MZ_RN_OUT_ROWS * 4 + 5 * MZ_RN_OUT_ROWS * 8 + tab + path + 128;
+}
+__device__ __forceinline__ mz_rn_plan mz_rn_carve(unsigned char *raw, int slot_bytes, int S, int ntrees) {
+    mz_rn_plan p;
+    uint32_t a = mz_smem_u32(raw);
+    unsigned char *c = raw + (((a + 1023u) & ~1023u) - a);
+    p.tiles_ptr = c; p.tiles = mz_smem_u32(c); c += 8 * MZ_RN_TILE_BYTES;
+    p.aux = mz_smem_u32(c); c += MZ_RN_AUX_BYTES;
+    p.wring_ptr = c; p.wring = mz_smem_u32(c); c += 2 * (size_t)slot_bytes;
+    p.w_bar = (uint64_t *)c; p.mma_bar = p.w_bar + 2; p.scr_bar = p.w_bar + 6; p.tmem_slot = (uint32_t *)(c + 128); c += 256;
+    p.out = (float *)c; c += 24 * MZ_RN_OUT_ROWS * 4;
+    p.tree_base = (unsigned long long *)c; c += MZ_RN_OUT_ROWS * 8;
+    p.plane = (float *)c; c += MZ_RN_OUT_ROWS * 4; p.pe = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4; p.dbl = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4;
+    p.active = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4; c += MZ_RN_OUT_ROWS * 16;   // (spare)
+    p.pbc0 = (double *)c; p.sqrtN = p.pbc0 + (S + 2); c += (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
+    p.path = (uint16_t *)c;
+    return p;
+}
+__device__ __forceinline__ uint32_t mz_rn_buf(const mz_rn_plan &sp, int id) {
+    if (id < 8) return sp.tiles + (uint32_t)id * MZ_RN_TILE_BYTES;
+    if (id == MZ_RN_BUF_HV) return sp.aux;
+    if (id == MZ_RN_BUF_HP) return sp.aux + 8192u;
+    return sp.aux + (uint32_t)(id - MZ_RN_BUF_S0) * MZ_RN_TILE_BYTES;
+}
+__device__ __forceinline__ int mz_rn_out_base(int out_id) { return out_id == MZ_RN_OUT_V ? 0 : out_id == MZ_RN_OUT_L ? 4 * MZ_RN_OUT_ROWS : 20 * MZ_RN_OUT_ROWS; }
+
+__device__ __forceinline__ void mz_rn_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// kind::f16, D = F32, A = B = BF16, K-major, M = 128, N = 16 * n16
+__device__ __forceinline__ uint32_t mz_rn_idesc(int n16) { return (1u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)(n16 * 16) >> 3) << 17) | ((128u >> 4) << 24); }
+__device__ __forceinline__ void mz_rn_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mz_rn_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 mz_lds128u(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
+__device__ __forceinline__ void mz_sts128u(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+__device__ __forceinline__ float mz_bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float mz_bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t mz_pack_bf16(float lo, float hi) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+}
+__device__ __forceinline__ void mz_mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spin = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (++spin > (1u << 24)) __trap();
+    }
+}
+
+// ---- executor state (uniform across the CTA) ----------------------------------------------------------------------
+struct mz_rn_exec {
+    mz_rn_plan sp; const mz_rn_step *steps; const unsigned char *image;
+    uint32_t tmem; int slot_bytes;
+    uint32_t wq;            // weight blocks consumed
+    int pf;                 // step whose block is in (or on its way to) slot wq & 1, or -1
+    uint32_t mq[4];         // commits seen per job barrier
+    uint32_t sq[2];         // commits seen per scratch barrier
+    int pool_slot;          // hidden-state slot written by MZ_RN_F_POOL epilogues
+    int W, H;
+};
+__device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, int s, uint32_t slot) {
+    const int off = X.steps[s].w_off, bytes = X.steps[s].w_bytes;
+    const uint32_t bar = mz_smem_u32(&X.sp.w_bar[slot]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(X.sp.wring + slot * (uint32_t)X.slot_bytes), "l"(X.image + off), "r"((uint32_t)bytes), "r"(bar) : "memory");
+}
+
+// epilogue of one job for one warpgroup thread (row = TMEM lane)
+__device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_params &R, const mz_rn_job &J, uint32_t wslot, int wgt) {
+    const int warp4 = wgt >> 5, lane = wgt & 31, row = 32 * warp4 + lane;
+    const uint32_t taddr = X.tmem + ((uint32_t)(32 * warp4) << 16) + 64u * J.acc;
+    const uint32_t pS = wslot + (uint32_t)J.p_sub, pT = pS + 256u, pE = pS + 512u;
+    const bool trees = (J.flags & MZ_RN_F_TREES) != 0;
+    int tree, cell;
+    if (trees) { tree = row; cell = 0; } else { tree = (J.acc) * R.tpt + row / R.cells; cell = row % R.cells; }
+    const bool valid = (trees ? row < R.ntrees : row < R.rows_valid) && X.sp.active[tree < MZ_RN_OUT_ROWS ? tree : 0] != 0;
+    if (J.epi == MZ_RN_EPI_TILE) {
+        const uint32_t rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t dst = mz_rn_buf(X.sp, J.dst_buf) + rowoff;
+        const uint32_t skp = J.skip_buf != 0xff ? mz_rn_buf(X.sp, J.skip_buf) + rowoff : 0u;
+        const float rowval = (J.flags & MZ_RN_F_PLANE) ? X.sp.plane[tree < MZ_RN_OUT_ROWS ? tree : 0] : 0.0f;
+        unsigned char *pool = nullptr;
+        if ((J.flags & MZ_RN_F_POOL) && valid)
+            pool = reinterpret_cast<unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.pool_slot * R.node_bytes + (size_t)cell * 128;
+        const float lo = J.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            uint32_t v[32];
+            mz_rn_ld32(taddr + 32u * half, v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int c8 = 4 * half + q;
+                const float4 s0 = mz_lds128(pS + c8 * 32), s1 = mz_lds128(pS + c8 * 32 + 16), t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
+                float y[8];
+                const float S[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, T[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+                if (J.flags & MZ_RN_F_PLANE) {
+                    const float4 e0 = mz_lds128(pE + c8 * 32), e1 = mz_lds128(pE + c8 * 32 + 16);
+                    const float E[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] = fmaf(__uint_as_float(v[8 * q + i]), S[i], fmaf(rowval, E[i], T[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] = fmaf(__uint_as_float(v[8 * q + i]), S[i], T[i]);
+                }
+                const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) << 4);
+                if (skp) {
+                    const uint4 k = mz_lds128u(skp + chunk);
+                    y[0] = y[0] + mz_bf16lo(k.x); y[1] = y[1] + mz_bf16hi(k.x); y[2] = y[2] + mz_bf16lo(k.y); y[3] = y[3] + mz_bf16hi(k.y);
+                    y[4] = y[4] + mz_bf16lo(k.z); y[5] = y[5] + mz_bf16hi(k.z); y[6] = y[6] + mz_bf16lo(k.w); y[7] = y[7] + mz_bf16hi(k.w);
+                }
+                uint4 o;
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] = fmaxf(y[i], lo);
+                    o.x = mz_pack_bf16(y[0], y[1]); o.y = mz_pack_bf16(y[2], y[3]); o.z = mz_pack_bf16(y[4], y[5]); o.w = mz_pack_bf16(y[6], y[7]);
+                } else { o.x = o.y = o.z = o.w = 0u; }
+                if (!trees || row < MZ_RN_OUT_ROWS) mz_sts128u(dst + chunk, o);
+                if (pool) *reinterpret_cast<uint4 *>(pool + c8 * 16) = o;
+            }
+        }
+    } else if (J.epi == MZ_RN_EPI_HEAD) {
+        uint32_t v[16];
+        mz_rn_ld16(taddr, v);
+        if (valid) {
+            const int nf = J.nfa + J.nfb;
+            for (int f = 0; f < nf; f++) {
+                const float y = fmaxf(fmaf(__uint_as_float(v[f]), mz_lds32(pS + f * 4), mz_lds32(pT + f * 4)), 0.0f);
+                const bool second = f >= J.nfa;
+                const int k = cell + R.cells * (second ? f - J.nfa : f);
+                const uint32_t tile = mz_rn_buf(X.sp, second ? J.dst2_buf : J.dst_buf) + (uint32_t)(k >> 6) * 8192u;
+                mz_tc_store_bf16(tile, tree, k & 63, y);
+            }
+        }
+    } else {
+        uint32_t v[16];
+        mz_rn_ld16(taddr, v);
+        if (row < R.ntrees) {
+            float *o = X.sp.out + mz_rn_out_base(J.out_id);
+            for (int k = 0; k < J.out; k++) {
+                float y = __uint_as_float(v[k]) + mz_lds32(pT + k * 4);
+                if (J.act == MZ_ACT_TANH) y = mz_tanhf_noinline(y); else if (J.act == MZ_ACT_RELU) y = fmaxf(y, 0.0f);
+                o[k * MZ_RN_OUT_ROWS + row] = y;
+            }
+        }
+    }
+}
+
+// Runs steps [first, last) of the program; next_first = the step that will run after this range (its weights are
+// prefetched during the last step), or -1.
+__device__ __noinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int first, int last, int next_first) {
+    const int tid = threadIdx.x, wg = tid >> 7, wgt = tid & 127;
+    for (int s = first; s < last; s++) {
+        const mz_rn_step *st = X.steps + s;
+        const uint32_t slot = X.wq & 1u;
+        const int next = s + 1 < last ? s + 1 : next_first;
+        if (tid == 0) {
+            if (X.pf != s) mz_rn_issue_weights(X, s, slot);
+            if (next >= 0) mz_rn_issue_weights(X, next, slot ^ 1u);
+        }
+        mz_mbar_wait_u32(mz_smem_u32(&X.sp.w_bar[slot]), (X.wq >> 1) & 1u);
+        const uint32_t wslot = X.sp.wring + slot * (uint32_t)X.slot_bytes;
+        const int njobs = st->njobs, ntaps = st->ntaps;
+        if (ntaps > 1) {
+            // tap-step: per tile, A = copy of the source tile shifted by (dx, dy) cells, built in one of two scratch tiles
+            const int dx = st->dx, dy = st->dy;
+            for (int j = 0; j < njobs; j++) {
+                const mz_rn_job &J = st->jobs[j];
+                const uint32_t sl = (uint32_t)(j & 1);
+                if (j >= 2) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);   // the MMA that read this scratch tile is done
+                const uint32_t src = mz_rn_buf(X.sp, J.a_buf), dst = mz_rn_buf(X.sp, MZ_RN_BUF_S0 + (int)sl);
+                for (int i = tid; i < 128 * 8; i += MZ_THREADS) {
+                    const int row = i >> 3, ch = i & 7;
+                    uint4 v; v.x = v.y = v.z = v.w = 0u;
+                    if (row < R.rows_valid) {
+                        const int t = row / R.cells, cell = row % R.cells, x = cell % X.W + dx, y = cell / X.W + dy;
+                        if (x >= 0 && x < X.W && y >= 0 && y < X.H) {
+                            const int sr = t * R.cells + x + X.W * y;
+                            v = mz_lds128u(src + (uint32_t)((sr >> 3) * 1024 + (sr & 7) * 128 + ((ch ^ (sr & 7)) << 4)));
+                        }
+                    }
+                    mz_sts128u(dst + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4)), v);
+                }
+                mz_fence_proxy_async();
+                mz_tc_fence_before();
+                __syncthreads();
+                if (tid < 32) {
+                    mz_tc_fence_after();
+                    if (mz_elect_one()) {
+                        const uint64_t ad = mz_tc_desc(dst), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub);
+                        const uint32_t idesc = mz_rn_idesc(J.n16);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (st->accumulate || k > 0) ? 1u : 0u);
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.scr_bar[sl])) : "memory");
+                        if (st->last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
+                    }
+                    __syncwarp();
+                }
+                X.sq[sl]++;
+            }
+            // every MMA of the step is complete before its weight slot / scratch tiles are reused
+            for (uint32_t sl = 0; sl < 2; sl++) if (X.sq[sl] > 0) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);
+        } else {
+            if (tid < 32) {
+                mz_tc_fence_after();
+                if (mz_elect_one()) {
+                    for (int j = 0; j < njobs; j++) {
+                        const mz_rn_job &J = st->jobs[j];
+                        const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
+                        for (int kb = 0; kb < J.kblocks; kb++) {
+                            const uint64_t ad = mz_tc_desc(a + (uint32_t)kb * 8192u), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub + (uint32_t)(kb * J.n16 * 2048));
+#pragma unroll
+                            for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (st->last) {
+            for (int j = 0; j < njobs; j++) {
+                const mz_rn_job &J = st->jobs[j];
+                if ((int)J.wg != wg) continue;
+                mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[j]), X.mq[j] & 1u);
+                mz_tc_fence_after();
+                __syncwarp();
+                mz_rn_epilogue(X, R, J, wslot, wgt);
+            }
+            for (int j = 0; j < njobs; j++) X.mq[j]++;
+        }
+        mz_fence_proxy_async();
+        mz_tc_fence_before();
+        __syncthreads();
+        mz_tc_fence_after();
+        X.wq++; X.pf = next;
+    }
+}
+
+// parent hidden states (bf16 rows in the tree pools) -> X tiles, scaled by 2^doublings (Q6); rows of idle trees are zero
+__device__ __forceinline__ void mz_rn_stage_hidden(const mz_rn_exec &X, const mz_rn_params &R) {
+    for (int i = threadIdx.x; i < MZ_RN_TILES * 128 * 8; i += MZ_THREADS) {
+        const int ch = i & 7, row = (i >> 3) & 127, tile = i >> 10;
+        uint4 v; v.x = v.y = v.z = v.w = 0u;
+        if (row < R.rows_valid) {
+            const int tree = tile * R.tpt + row / R.cells, cell = row % R.cells;
+            if (X.sp.active[tree]) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.sp.pe[tree] * R.node_bytes + (size_t)cell * 128 + ch * 16;
+                v = *reinterpret_cast<const uint4 *>(src);
+                const int dbl = X.sp.dbl[tree];
+                if (dbl > 0) {
+                    const float sc = __uint_as_float((uint32_t)(127 + dbl) << 23);
+                    v.x = mz_pack_bf16(mz_bf16lo(v.x) * sc, mz_bf16hi(v.x) * sc); v.y = mz_pack_bf16(mz_bf16lo(v.y) * sc, mz_bf16hi(v.y) * sc);
+                    v.z = mz_pack_bf16(mz_bf16lo(v.z) * sc, mz_bf16hi(v.z) * sc); v.w = mz_pack_bf16(mz_bf16lo(v.w) * sc, mz_bf16hi(v.w) * sc);
+                }
+            }
+        }
+        mz_sts128u(X.sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4)), v);
+    }
+    mz_fence_proxy_async();
+    __syncthreads();
+}
+
+struct mz_search_rn_args {
+    mz_search_args base;
+    const unsigned char *image; const mz_rn_step *steps;
+    // mz_k_rn_forward only
+    int32_t net, B; const float *in; float *out1, *out2; unsigned char *scratch_pool;
+};
+
+// common prologue: barriers, TMEM, zeroed tiles, executor state
+__device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, const mz_rn_params &R, const mz_search_rn_args &ta, unsigned char *smem) {
+    X.sp = mz_rn_carve(smem, R.slot_bytes, P.S, R.ntrees);
+    X.steps = ta.steps; X.image = ta.image; X.slot_bytes = R.slot_bytes; X.wq = 0; X.pf = -1; X.pool_slot = 0; X.W = P.W; X.H = P.H;
+    for (int j = 0; j < 4; j++) X.mq[j] = 0;
+    X.sq[0] = X.sq[1] = 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.w_bar[i], 1);
+        for (int i = 0; i < 4; i++) mz_mbar_init(&X.sp.mma_bar[i], 1);
+        for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.scr_bar[i], 1);
+        mz_fence_mbar_init();
+    }
+    __syncwarp();
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mz_smem_u32(X.sp.tmem_slot)), "r"((uint32_t)MZ_RN_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < (8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES) / 16; i += MZ_THREADS) reinterpret_cast<uint4 *>(X.sp.tiles_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 24 * MZ_RN_OUT_ROWS; i += MZ_THREADS) X.sp.out[i] = 0.0f;
+    for (int i = tid; i < MZ_RN_OUT_ROWS; i += MZ_THREADS) { X.sp.active[i] = 0; X.sp.pe[i] = 0; X.sp.dbl[i] = 0; X.sp.plane[i] = 0.0f; X.sp.tree_base[i] = 0ull; }
+    mz_fence_proxy_async();
+    mz_tc_fence_before();
+    __syncthreads();
+    mz_tc_fence_after();
+    X.tmem = *X.sp.tmem_slot;
+}
+__device__ __forceinline__ void mz_rn_teardown(const mz_rn_exec &X) {
+    mz_tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(X.tmem), "r"((uint32_t)MZ_RN_TMEM_COLS) : "memory");
+}
+// im2col tiles of the first representation convolution: element (row = (tree, cell), kk = tap * planes + plane)
+template <typename F>
+__device__ __forceinline__ void mz_rn_im2col(const mz_rn_exec &X, const mz_params &P, const mz_rn_params &R, F &&stacked /* (tree, plane, cell) -> float */) {
+    const int k = R.ksize, pad = k / 2, kk_n = k * k * R.planes;
+    for (int i = threadIdx.x; i < MZ_RN_TILES * 128 * kk_n; i += MZ_THREADS) {
+        const int kk = i % kk_n, row = (i / kk_n) & 127, tile = i / (kk_n * 128);
+        float v = 0.0f;
+        if (row < R.rows_valid) {
+            const int tree = tile * R.tpt + row / R.cells, cell = row % R.cells;
+            const int t = kk / R.planes, pl = kk % R.planes, x = cell % P.W + pad - (t % k), y = cell / P.W + pad - (t / k);
+            if (X.sp.active[tree] && x >= 0 && x < P.W && y >= 0 && y < P.H) v = stacked(tree, pl, x + P.W * y);
+        }
+        mz_tc_store_bf16(X.sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES), row, kk, v);
+    }
+    mz_fence_proxy_async();
+    __syncthreads();
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
+    extern __shared__ __align__(1024) unsigned char mz_smem_rn[];
+    const mz_search_args &a = ta.base;
+    mz_rn_exec X;
+    mz_rn_setup(X, P, R, ta, mz_smem_rn);
+    const mz_rn_plan &sp = X.sp;
+    const int tid = threadIdx.x, ln = tid & (MZ_LANES - 1);
+    const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
+    for (int i = tid; i <= P.S + 1; i += MZ_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
+
+    // ---- per-tree state: two passes of 32 trees, replicated in the 8 lanes of each tree ----
+    bool active[2]; uint32_t legal[2], game[2], move[2], posmask[2]; mz_tree tree[2]; mz_minmax mm[2]; int ts[2]; int64_t gidx[2];
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        ts[p] = 32 * p + (tid >> 3); gidx[p] = (int64_t)blockIdx.x * R.ntrees + ts[p];
+        active[p] = false; legal[p] = 0; game[p] = 0; move[p] = 0; tree[p].A = nullptr; tree[p].hidden = nullptr;
+        if (ts[p] < R.ntrees && gidx[p] < a.n) {
+            const int64_t g = gidx[p];
+            tree[p] = mz_tree_at(P, a.tree_pool, g);
+            if (MODE == MZ_MODE_API) { active[p] = true; legal[p] = a.legal[g]; game[p] = (uint32_t)a.game_id[g]; move[p] = (uint32_t)a.move_idx[g]; }
+            else {
+                active[p] = a.slots.status[g] == MZ_SLOT_ACTIVE;
+                if (active[p]) {
+                    mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
+                    legal[p] = mz_env_legal_b(P, b); game[p] = (uint32_t)a.slots.game_id[g]; move[p] = (uint32_t)a.slots.T[g] + 1u;
+                }
+            }
+            if (legal[p] == 0) active[p] = false;
+            if (ln == 0) { sp.active[ts[p]] = active[p] ? 1 : 0; sp.tree_base[ts[p]] = (unsigned long long)(uintptr_t)tree[p].A; }
+        }
+        posmask[p] = 0;
+        for (int j = 0; j < P.A; j++) if ((legal[p] >> (P.order[j] - 1)) & 1u) posmask[p] |= 1u << j;
+        mm[p].mn = INFINITY; mm[p].mx = -INFINITY;
+    }
+    __syncthreads();
+
+    // ---- root: representation (im2col of the stacked observation) -> h0 in the pool; prediction(h0) ----
+    if (MODE == MZ_MODE_API) {
+        mz_rn_im2col(X, P, R, [&](int t, int pl, int cell) { return a.stacked[((int64_t)blockIdx.x * R.ntrees + t) * P.stack_size + cell + P.cells * pl]; });
+    } else {
+        mz_rn_im2col(X, P, R, [&](int t, int pl, int cell) {
+            const int64_t gg = (int64_t)blockIdx.x * R.ntrees + t;
+            return mz_stacked_value(P, a.slots.h_p1 + gg * P.Tmax, a.slots.h_p2 + gg * P.Tmax, a.slots.h_action + gg * P.Tmax, a.slots.T[gg] + 1, cell + P.cells * pl);
+        });
+    }
+    X.pool_slot = 0;
+    mz_rn_run(X, R, R.prog_repr[0], R.prog_repr[1], R.prog_pred[0]);
+    __threadfence_block();
+    __syncthreads();
+    mz_rn_stage_hidden(X, R);                      // pe = 0, dbl = 0: h0
+    mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], R.prog_pred[0]);
+    const float *outV = sp.out, *outL = sp.out + 4 * MZ_RN_OUT_ROWS, *outR = sp.out + 20 * MZ_RN_OUT_ROWS;
+    unsigned long long depth_sum = 0;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (active[p]) {
+            if (ln == 0) { mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f; tree[p].A[0] = root; }
+            __syncwarp(segmask);
+            mz_tree_expand_lanes(P, tree[p], 0, 0, legal[p], outL + ts[p], 0.0f, 0.0f, ln, segmask, MZ_RN_OUT_ROWS);
+            if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree[p], legal[p], game[p], move[p]);
+            __syncwarp(segmask);
+        }
+    }
+
+    // ---- simulations (SelfPlay.jl:254-283) ----
+    for (int sim = 1; sim <= P.S; sim++) {
+        mz_leaf leaf[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            leaf[p].node = 0; leaf[p].parent = 0; leaf[p].action = 1; leaf[p].depth = 0; leaf[p].prior = 0.0f; leaf[p].parent_x = 0;
+            if (active[p]) {
+                uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
+                leaf[p] = mz_tree_select_lanes(P, tree[p], sp.pbc0, sp.sqrtN, legal[p], posmask[p], mm[p], game[p], move[p], (uint32_t)sim, ln, segmask, path);
+                depth_sum += (unsigned long long)leaf[p].depth;
+                if (ln == 0) {
+                    sp.pe[ts[p]] = mz_nx_exp(leaf[p].parent_x); sp.dbl[ts[p]] = mz_nx_dbl(leaf[p].parent_x);
+                    sp.plane[ts[p]] = P.act_plane_play[leaf[p].action];
+                    reinterpret_cast<uint32_t *>(&tree[p].A[leaf[p].parent])[0] = leaf[p].parent_x + (1u << 24);   // one more doubling (Q6)
+                }
+            }
+        }
+        __syncthreads();
+        mz_rn_stage_hidden(X, R);                                                   // prediction(parent.hidden_state) (Q5)
+        mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], R.prog_dyn[0]);
+        mz_rn_stage_hidden(X, R);                                                   // dynamics(state * 2, action plane)
+        X.pool_slot = sim;
+        mz_rn_run(X, R, R.prog_dyn[0], R.prog_dyn[1], sim < P.S ? R.prog_pred[0] : -1);
+        __threadfence_block();
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            if (active[p]) {
+                const uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
+                mz_tree_expand_lanes(P, tree[p], leaf[p].node, sim, legal[p], outL + ts[p], outR[ts[p]], leaf[p].prior, ln, segmask, MZ_RN_OUT_ROWS);
+                mz_tree_backup_lanes(P, tree[p], path, leaf[p].depth, outV[ts[p]], mm[p], ln, segmask);
+            }
+        }
+    }
+
+    // ---- results (lane 0 of each tree), as in mz_k_search ----
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        if (!(active[p] && ln == 0)) continue;
+        const int64_t g = gidx[p];
+        int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
+        for (int i = 0; i < P.A; i++) {
+            vc[i] = ((legal[p] >> i) & 1u) ? (int32_t)mz_nx_visit(mz_f2bits(tree[p].A[1 + i].x)) : 0;
+            sum_visits += vc[i]; nlegal += (int)((legal[p] >> i) & 1u);
+        }
+        mz_f4 root = tree[p].A[0];
+        int rvc = mz_nx_visit(mz_f2bits(root.x));
+        float rv = rvc == 0 ? 0.0f : root.y / (float)rvc;
+        if (a.stats) {
+            atomicAdd(&a.stats[0], depth_sum); atomicAdd(&a.stats[1], (unsigned long long)P.S);
+            atomicAdd(&a.stats[2], (unsigned long long)nlegal); atomicAdd(&a.stats[3], 1ull);
+            depth_sum = 0;
+        }
+        if (MODE == MZ_MODE_API) {
+            for (int i = 0; i < P.A; i++) {
+                a.visit_counts[g * P.A + i] = vc[i];
+                if (a.root_priors) a.root_priors[g * P.A + i] = ((legal[p] >> i) & 1u) ? tree[p].A[1 + i].z : 0.0f;
+            }
+            a.root_value[g] = rv;
+        } else {
+            int T = a.slots.T[g];
+            int action = mz_select_action_counts(P, vc, legal[p], a.temperature, game[p], move[p]);
+            mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
+            int pl = b.player;
+            mz_env_step_b(P, b, action);
+            float reward = (float)mz_env_reward_b(P, b, pl);
+            bool done = mz_env_terminated_b(P, b);
+            float *cv = a.slots.h_cv + ((size_t)g * P.Tmax + T) * P.A;
+            for (int i = 0; i < P.A; i++) cv[i] = ((legal[p] >> i) & 1u) ? (float)((double)vc[i] / (double)sum_visits) : 0.0f;
+            a.slots.h_rv[(size_t)g * P.Tmax + T] = rv;
+            a.slots.h_action[(size_t)g * P.Tmax + T] = action;
+            a.slots.h_reward[(size_t)g * P.Tmax + T] = reward;
+            a.slots.h_to_play[(size_t)g * P.Tmax + T] = (uint8_t)pl;
+            T += 1;
+            a.slots.p1[g] = b.p1; a.slots.p2[g] = b.p2; a.slots.player[g] = b.player; a.slots.T[g] = T;
+            if (T < P.Tmax) { a.slots.h_p1[(size_t)g * P.Tmax + T] = b.p1; a.slots.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
+            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED;
+        }
+    }
+    mz_rn_teardown(X);
+}
+
+// batched network callables (init_*(hyper::ResNetHP) callables): net 0 representation(stacked), 1 prediction(hidden),
+// 2 dynamics(state_action).  Hidden states go through a scratch pool of one slot per tree (bf16, like the real pool).
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
+    extern __shared__ __align__(1024) unsigned char mz_smem_rn[];
+    mz_rn_exec X;
+    mz_rn_setup(X, P, R, ta, mz_smem_rn);
+    const mz_rn_plan &sp = X.sp;
+    const int tid = threadIdx.x;
+    const int64_t g0 = (int64_t)blockIdx.x * R.ntrees;
+    // scratch pool: per tree one hidden slot, addressed as tree_base + hidden_off + 0 * node_bytes
+    for (int t = tid; t < R.ntrees; t += MZ_THREADS) {
+        sp.active[t] = g0 + t < ta.B ? 1 : 0;
+        sp.tree_base[t] = (unsigned long long)(uintptr_t)(ta.scratch_pool + (size_t)(g0 + t) * R.node_bytes) - (unsigned long long)R.hidden_off_bytes;
+    }
+    __syncthreads();
+    if (ta.net == 0) {
+        mz_rn_im2col(X, P, R, [&](int t, int pl, int cell) { return ta.in[(g0 + t) * P.stack_size + cell + P.cells * pl]; });
+        mz_rn_run(X, R, R.prog_repr[0], R.prog_repr[1], -1);
+    } else {
+        // stage the fp32 input states as bf16 rows (dynamics: the caller's state is already doubled; the kernel multiplies the accumulator by 2)
+        const float mul = ta.net == 2 ? 0.5f : 1.0f;
+        const int in_dim = ta.net == 2 ? P.sa_size : P.hidden;
+        for (int i = tid; i < MZ_RN_TILES * 128 * 64; i += MZ_THREADS) {
+            const int c = i & 63, row = (i >> 6) & 127, tile = i >> 13;
+            float v = 0.0f;
+            if (row < R.rows_valid && c < R.nf) {
+                const int t = tile * R.tpt + row / R.cells, cell = row % R.cells;
+                if (sp.active[t]) v = ta.in[(g0 + t) * in_dim + cell + P.cells * c] * mul;
+            }
+            mz_tc_store_bf16(sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES), row, c, v);
+        }
+        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_THREADS) sp.plane[t] = sp.active[t] ? ta.in[(g0 + t) * in_dim + P.hidden] : 0.0f;
+        mz_fence_proxy_async();
+        __syncthreads();
+        if (ta.net == 1) mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], -1);
+        else mz_rn_run(X, R, R.prog_dyn[0], R.prog_dyn[1], -1);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (ta.net != 1) {   // hidden state out: Julia (W,H,nf) order, from the bf16 scratch pool
+        for (int i = tid; i < R.ntrees * P.hidden; i += MZ_THREADS) {
+            const int t = i / P.hidden, k = i % P.hidden, cell = k % P.cells, c = k / P.cells;
+            if (g0 + t < ta.B) {
+                const unsigned short h = *reinterpret_cast<const unsigned short *>(ta.scratch_pool + (size_t)(g0 + t) * R.node_bytes + (size_t)cell * 128 + c * 2);
+                ta.out1[(g0 + t) * P.hidden + k] = __uint_as_float((uint32_t)h << 16);
+            }
+        }
+        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_THREADS) if (g0 + t < ta.B) ta.out2[g0 + t] = sp.out[20 * MZ_RN_OUT_ROWS + t];
+    } else {
+        for (int t = tid; t < R.ntrees; t += MZ_THREADS) if (g0 + t < ta.B) {
+            float logits[MZ_MAX_A], policy[MZ_MAX_A];
+            for (int i = 0; i < P.A; i++) logits[i] = sp.out[4 * MZ_RN_OUT_ROWS + i * MZ_RN_OUT_ROWS + t];
+            mz_softmax(logits, P.A, policy);
+            ta.out1[g0 + t] = sp.out[t];
+            for (int i = 0; i < P.A; i++) ta.out2[(g0 + t) * P.A + i] = policy[i];
+        }
+    }
+    mz_rn_teardown(X);
+}

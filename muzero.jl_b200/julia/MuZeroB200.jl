@@ -22,6 +22,7 @@ mutable struct MzConfig
     depth_policy::Int32; depth_value::Int32; depth_reward::Int32; depth_state_head::Int32
     hidden_state_size::Int32; reward_activation_tanh::Int32
     num_slots::Int32; nn_mode::Int32
+    net_type::Int32; rn_num_blocks::Int32; rn_num_filters::Int32; rn_kernel::Int32; rn_first_head_filters::Int32; rn_second_head_filters::Int32
     MzConfig() = new()
 end
 
