@@ -302,7 +302,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
         if (const char *er = mzh::rn_build(*cfg, c->M.P, c->rn)) { int r = fail(nullptr, MZ_E_ARG, "%s", er); mz_destroy(c); return r; }
         c->M.P.tree_stride_bytes = c->rn.R.tree_stride_bytes; c->M.P.hidden_off_bytes = c->rn.R.hidden_off_bytes;
         c->M.P.n_params = mzh::rn_total_params(c->rn); c->M.P.total_floats = 4;
-        c->smem_bytes_rn = mz_rn_smem_bytes(c->rn.R.slot_bytes, c->M.P.S, c->rn.R.ntrees);
+        c->smem_bytes_rn = mz_rn_smem_bytes(c->rn.R.slot_bytes, c->M.P.S, c->rn.R.ntrees, c->rn.R.n_steps - c->rn.R.smem_first);
         if (c->smem_bytes_rn + 1024 > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "the ResNet search kernel needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes_rn, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
         MZ_CREATE(allow_max_smem(mz_k_search_rn<MZ_MODE_API>, prop)); MZ_CREATE(allow_max_smem(mz_k_search_rn<MZ_MODE_SLOTS>, prop)); MZ_CREATE(allow_max_smem(mz_k_rn_forward, prop));
         MZ_CREATE(cudaMalloc((void **)&c->d_rn_image, (size_t)c->rn.image_bytes + 4096));

@@ -218,7 +218,7 @@ struct mz_rn_step {
 struct mz_rn_params {
     int32_t cells, nf, tpt, ntrees, rows_valid, node_bytes;
     int32_t planes, ksize, nvf, npf;
-    int32_t prog_repr[2], prog_pred[2], prog_dyn[2], n_steps;
+    int32_t prog_repr[2], prog_pred[2], prog_dyn[2], n_steps, smem_first;   // steps >= smem_first are copied to shared memory
     int32_t image_bytes, slot_bytes, hidden_off_bytes, tree_stride_bytes;
 };
 

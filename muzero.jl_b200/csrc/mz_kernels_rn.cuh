@@ -33,13 +33,14 @@ struct mz_rn_plan {
     float *out;                    // fp32 head outputs: V [4][64] | L [16][64] | R [4][64]
     float *plane; int32_t *pe, *dbl, *active; unsigned long long *tree_base;
     double *pbc0, *sqrtN; uint16_t *path;
+    mz_rn_step *prog;              // steps [smem_first, n_steps) of the program (the simulation loop's)
 };
-__host__ __device__ inline size_t mz_rn_smem_bytes(int slot_bytes, int S, int ntrees) {
+__host__ __device__ inline size_t mz_rn_smem_bytes(int slot_bytes, int S, int ntrees, int smem_steps) {
     size_t tab = (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
     size_t path = (((size_t)S + 2) * 2 * ntrees + 127) & ~(size_t)127;
-    return 1024 + 8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES + 2 * (size_t)slot_bytes + 256 + 24 * MZ_RN_OUT_ROWS * 4 + 5 * MZ_RN_OUT_ROWS * 8 + tab + path + 128;
+    return 1024 + 8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES + 2 * (size_t)slot_bytes + 256 + 24 * MZ_RN_OUT_ROWS * 4 + 5 * MZ_RN_OUT_ROWS * 8 + tab + path + (size_t)smem_steps * sizeof(mz_rn_step) + 128;
 }
-__device__ __forceinline__ mz_rn_plan mz_rn_carve(unsigned char *raw, int slot_bytes, int S, int ntrees) {
+__device__ __forceinline__ mz_rn_plan mz_rn_carve(unsigned char *raw, int slot_bytes, int S, int ntrees, int smem_steps) {
     mz_rn_plan p;
     uint32_t a = mz_smem_u32(raw);
     unsigned char *c = raw + (((a + 1023u) & ~1023u) - a);
@@ -52,7 +53,8 @@ __device__ __forceinline__ mz_rn_plan mz_rn_carve(unsigned char *raw, int slot_b
     p.plane = (float *)c; c += MZ_RN_OUT_ROWS * 4; p.pe = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4; p.dbl = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4;
     p.active = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4; c += MZ_RN_OUT_ROWS * 16;   // (spare)
     p.pbc0 = (double *)c; p.sqrtN = p.pbc0 + (S + 2); c += (((size_t)S + 2) * 8 * 2 + 127) & ~(size_t)127;
-    p.path = (uint16_t *)c;
+    p.path = (uint16_t *)c; c += (((size_t)S + 2) * 2 * ntrees + 127) & ~(size_t)127;
+    p.prog = (mz_rn_step *)c;
     return p;
 }
 __device__ __forceinline__ uint32_t mz_rn_buf(const mz_rn_plan &sp, int id) {
@@ -92,8 +94,10 @@ __device__ __forceinline__ uint4 mz_lds128u(uint32_t addr) { uint4 v; asm volati
 __device__ __forceinline__ void mz_sts128u(uint32_t addr, uint4 v) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 __device__ __forceinline__ float mz_bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float mz_bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t mz_pack_bf16(float lo, float hi) {
-    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(lo)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(hi)) << 16);
+__device__ __forceinline__ uint32_t mz_pack_bf16(float lo, float hi) {   // round to nearest even, two values per instruction
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ void mz_mbar_wait_u32(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0, spin = 0;
@@ -123,7 +127,7 @@ __device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, int s, 
 }
 
 // epilogue of one job for one warpgroup thread (row = TMEM lane)
-__device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_params &R, const mz_rn_job &J, uint32_t wslot, int wgt) {
+__device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_params &R, const mz_rn_job J, uint32_t wslot, int wgt) {
     const int warp4 = wgt >> 5, lane = wgt & 31, row = 32 * warp4 + lane;
     const uint32_t taddr = X.tmem + ((uint32_t)(32 * warp4) << 16) + 64u * J.acc;
     const uint32_t pS = wslot + (uint32_t)J.p_sub, pT = pS + 256u, pE = pS + 512u;
@@ -131,6 +135,7 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
     int tree, cell;
     if (trees) { tree = row; cell = 0; } else { tree = (J.acc) * R.tpt + row / R.cells; cell = row % R.cells; }
     const bool valid = (trees ? row < R.ntrees : row < R.rows_valid) && X.sp.active[tree < MZ_RN_OUT_ROWS ? tree : 0] != 0;
+    const int jflags = J.flags, jact = J.act;
     if (J.epi == MZ_RN_EPI_TILE) {
         const uint32_t rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
         const uint32_t dst = mz_rn_buf(X.sp, J.dst_buf) + rowoff;
@@ -139,7 +144,7 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
         unsigned char *pool = nullptr;
         if ((J.flags & MZ_RN_F_POOL) && valid)
             pool = reinterpret_cast<unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.pool_slot * R.node_bytes + (size_t)cell * 128;
-        const float lo = J.act == MZ_ACT_RELU ? 0.0f : -INFINITY;
+        const float lo = jact == MZ_ACT_RELU ? 0.0f : -INFINITY;
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             uint32_t v[32];
@@ -150,7 +155,7 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
                 const float4 s0 = mz_lds128(pS + c8 * 32), s1 = mz_lds128(pS + c8 * 32 + 16), t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
                 float y[8];
                 const float S[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, T[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                if (J.flags & MZ_RN_F_PLANE) {
+                if (jflags & MZ_RN_F_PLANE) {
                     const float4 e0 = mz_lds128(pE + c8 * 32), e1 = mz_lds128(pE + c8 * 32 + 16);
                     const float E[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
@@ -203,28 +208,30 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
 }
 
 // Runs steps [first, last) of the program; next_first = the step that will run after this range (its weights are
-// prefetched during the last step), or -1.
-__device__ __noinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int first, int last, int next_first) {
+// prefetched during the last step), or -1.  Inlined at its (single) call site per kernel so that the executor state
+// stays in registers; the steps of the simulation loop are read from shared memory.
+__device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int first, int last, int next_first) {
     const int tid = threadIdx.x, wg = tid >> 7, wgt = tid & 127;
     for (int s = first; s < last; s++) {
-        const mz_rn_step *st = X.steps + s;
+        const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
         const uint32_t slot = X.wq & 1u;
         const int next = s + 1 < last ? s + 1 : next_first;
         if (tid == 0) {
             if (X.pf != s) mz_rn_issue_weights(X, s, slot);
             if (next >= 0) mz_rn_issue_weights(X, next, slot ^ 1u);
         }
+        const int njobs = st->njobs, ntaps = st->ntaps, is_last = st->last;
         mz_mbar_wait_u32(mz_smem_u32(&X.sp.w_bar[slot]), (X.wq >> 1) & 1u);
         const uint32_t wslot = X.sp.wring + slot * (uint32_t)X.slot_bytes;
-        const int njobs = st->njobs, ntaps = st->ntaps;
         if (ntaps > 1) {
             // tap-step: per tile, A = copy of the source tile shifted by (dx, dy) cells, built in one of two scratch tiles
-            const int dx = st->dx, dy = st->dy;
-            for (int j = 0; j < njobs; j++) {
-                const mz_rn_job &J = st->jobs[j];
+            const int dx = st->dx, dy = st->dy, accumulate = st->accumulate;
+#pragma unroll
+            for (int j = 0; j < MZ_RN_TILES; j++) {
+                if (j >= njobs) break;
                 const uint32_t sl = (uint32_t)(j & 1);
                 if (j >= 2) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);   // the MMA that read this scratch tile is done
-                const uint32_t src = mz_rn_buf(X.sp, J.a_buf), dst = mz_rn_buf(X.sp, MZ_RN_BUF_S0 + (int)sl);
+                const uint32_t src = mz_rn_buf(X.sp, st->jobs[j].a_buf), dst = mz_rn_buf(X.sp, MZ_RN_BUF_S0 + (int)sl);
                 for (int i = tid; i < 128 * 8; i += MZ_THREADS) {
                     const int row = i >> 3, ch = i & 7;
                     uint4 v; v.x = v.y = v.z = v.w = 0u;
@@ -243,25 +250,26 @@ __device__ __noinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int
                 if (tid < 32) {
                     mz_tc_fence_after();
                     if (mz_elect_one()) {
-                        const uint64_t ad = mz_tc_desc(dst), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub);
-                        const uint32_t idesc = mz_rn_idesc(J.n16);
+                        const uint64_t ad = mz_tc_desc(dst), bd = mz_tc_desc(wslot + (uint32_t)st->jobs[j].w_sub);
+                        const uint32_t idesc = mz_rn_idesc(st->jobs[j].n16), acc = st->jobs[j].acc;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (st->accumulate || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (accumulate || k > 0) ? 1u : 0u);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.scr_bar[sl])) : "memory");
-                        if (st->last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
+                        if (is_last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
                     }
                     __syncwarp();
                 }
                 X.sq[sl]++;
             }
             // every MMA of the step is complete before its weight slot / scratch tiles are reused
+#pragma unroll
             for (uint32_t sl = 0; sl < 2; sl++) if (X.sq[sl] > 0) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);
         } else {
             if (tid < 32) {
                 mz_tc_fence_after();
                 if (mz_elect_one()) {
                     for (int j = 0; j < njobs; j++) {
-                        const mz_rn_job &J = st->jobs[j];
+                        const mz_rn_job J = st->jobs[j];
                         const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
                         for (int kb = 0; kb < J.kblocks; kb++) {
                             const uint64_t ad = mz_tc_desc(a + (uint32_t)kb * 8192u), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub + (uint32_t)(kb * J.n16 * 2048));
@@ -274,16 +282,19 @@ __device__ __noinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int
                 __syncwarp();
             }
         }
-        if (st->last) {
-            for (int j = 0; j < njobs; j++) {
-                const mz_rn_job &J = st->jobs[j];
-                if ((int)J.wg != wg) continue;
-                mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[j]), X.mq[j] & 1u);
-                mz_tc_fence_after();
-                __syncwarp();
-                mz_rn_epilogue(X, R, J, wslot, wgt);
+        if (is_last) {
+#pragma unroll
+            for (int j = 0; j < MZ_RN_TILES; j++) {
+                if (j >= njobs) break;
+                if ((int)st->jobs[j].wg == wg) {
+                    const mz_rn_job J = st->jobs[j];
+                    mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[j]), X.mq[j] & 1u);
+                    mz_tc_fence_after();
+                    __syncwarp();
+                    mz_rn_epilogue(X, R, J, wslot, wgt);
+                }
+                X.mq[j]++;
             }
-            for (int j = 0; j < njobs; j++) X.mq[j]++;
         }
         mz_fence_proxy_async();
         mz_tc_fence_before();
@@ -326,7 +337,7 @@ struct mz_search_rn_args {
 
 // common prologue: barriers, TMEM, zeroed tiles, executor state
 __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, const mz_rn_params &R, const mz_search_rn_args &ta, unsigned char *smem) {
-    X.sp = mz_rn_carve(smem, R.slot_bytes, P.S, R.ntrees);
+    X.sp = mz_rn_carve(smem, R.slot_bytes, P.S, R.ntrees, R.n_steps - R.smem_first);
     X.steps = ta.steps; X.image = ta.image; X.slot_bytes = R.slot_bytes; X.wq = 0; X.pf = -1; X.pool_slot = 0; X.W = P.W; X.H = P.H;
     for (int j = 0; j < 4; j++) X.mq[j] = 0;
     X.sq[0] = X.sq[1] = 0;
@@ -344,6 +355,8 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
     }
     for (int i = tid; i < (8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES) / 16; i += MZ_THREADS) reinterpret_cast<uint4 *>(X.sp.tiles_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < 24 * MZ_RN_OUT_ROWS; i += MZ_THREADS) X.sp.out[i] = 0.0f;
+    for (int i = tid; i < (R.n_steps - R.smem_first) * (int)(sizeof(mz_rn_step) / 4); i += MZ_THREADS)
+        reinterpret_cast<uint32_t *>(X.sp.prog)[i] = reinterpret_cast<const uint32_t *>(ta.steps + R.smem_first)[i];
     for (int i = tid; i < MZ_RN_OUT_ROWS; i += MZ_THREADS) { X.sp.active[i] = 0; X.sp.pe[i] = 0; X.sp.dbl[i] = 0; X.sp.plane[i] = 0.0f; X.sp.tree_base[i] = 0ull; }
     mz_fence_proxy_async();
     mz_tc_fence_before();
@@ -420,56 +433,59 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
             return mz_stacked_value(P, a.slots.h_p1 + gg * P.Tmax, a.slots.h_p2 + gg * P.Tmax, a.slots.h_action + gg * P.Tmax, a.slots.T[gg] + 1, cell + P.cells * pl);
         });
     }
-    X.pool_slot = 0;
-    mz_rn_run(X, R, R.prog_repr[0], R.prog_repr[1], R.prog_pred[0]);
-    __threadfence_block();
-    __syncthreads();
-    mz_rn_stage_hidden(X, R);                      // pe = 0, dbl = 0: h0
-    mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], R.prog_pred[0]);
+    // ---- phases: 0 = representation (root), 1 = prediction(h0), then per simulation 2 = prediction(parent), 3 = dynamics.
+    //      One loop so that the step executor is inlined exactly once. ----
     const float *outV = sp.out, *outL = sp.out + 4 * MZ_RN_OUT_ROWS, *outR = sp.out + 20 * MZ_RN_OUT_ROWS;
     unsigned long long depth_sum = 0;
+    mz_leaf leaf[2];
+    int sim = 0;
+    for (int phase = 0; ; phase = phase == 3 ? 2 : phase + 1) {
+        if (phase == 2) {
+            if (++sim > P.S) break;
+            // select (SelfPlay.jl:261-268); the parent's hidden state will be staged for both networks
 #pragma unroll
-    for (int p = 0; p < 2; p++) {
-        if (active[p]) {
-            if (ln == 0) { mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f; tree[p].A[0] = root; }
-            __syncwarp(segmask);
-            mz_tree_expand_lanes(P, tree[p], 0, 0, legal[p], outL + ts[p], 0.0f, 0.0f, ln, segmask, MZ_RN_OUT_ROWS);
-            if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree[p], legal[p], game[p], move[p]);
-            __syncwarp(segmask);
-        }
-    }
-
-    // ---- simulations (SelfPlay.jl:254-283) ----
-    for (int sim = 1; sim <= P.S; sim++) {
-        mz_leaf leaf[2];
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            leaf[p].node = 0; leaf[p].parent = 0; leaf[p].action = 1; leaf[p].depth = 0; leaf[p].prior = 0.0f; leaf[p].parent_x = 0;
-            if (active[p]) {
-                uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
-                leaf[p] = mz_tree_select_lanes(P, tree[p], sp.pbc0, sp.sqrtN, legal[p], posmask[p], mm[p], game[p], move[p], (uint32_t)sim, ln, segmask, path);
-                depth_sum += (unsigned long long)leaf[p].depth;
-                if (ln == 0) {
-                    sp.pe[ts[p]] = mz_nx_exp(leaf[p].parent_x); sp.dbl[ts[p]] = mz_nx_dbl(leaf[p].parent_x);
-                    sp.plane[ts[p]] = P.act_plane_play[leaf[p].action];
-                    reinterpret_cast<uint32_t *>(&tree[p].A[leaf[p].parent])[0] = leaf[p].parent_x + (1u << 24);   // one more doubling (Q6)
+            for (int p = 0; p < 2; p++) {
+                leaf[p].node = 0; leaf[p].parent = 0; leaf[p].action = 1; leaf[p].depth = 0; leaf[p].prior = 0.0f; leaf[p].parent_x = 0;
+                if (active[p]) {
+                    uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
+                    leaf[p] = mz_tree_select_lanes(P, tree[p], sp.pbc0, sp.sqrtN, legal[p], posmask[p], mm[p], game[p], move[p], (uint32_t)sim, ln, segmask, path);
+                    depth_sum += (unsigned long long)leaf[p].depth;
+                    if (ln == 0) {
+                        sp.pe[ts[p]] = mz_nx_exp(leaf[p].parent_x); sp.dbl[ts[p]] = mz_nx_dbl(leaf[p].parent_x);
+                        sp.plane[ts[p]] = P.act_plane_play[leaf[p].action];
+                        reinterpret_cast<uint32_t *>(&tree[p].A[leaf[p].parent])[0] = leaf[p].parent_x + (1u << 24);   // one more doubling (Q6)
+                    }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        mz_rn_stage_hidden(X, R);                                                   // prediction(parent.hidden_state) (Q5)
-        mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], R.prog_dyn[0]);
-        mz_rn_stage_hidden(X, R);                                                   // dynamics(state * 2, action plane)
-        X.pool_slot = sim;
-        mz_rn_run(X, R, R.prog_dyn[0], R.prog_dyn[1], sim < P.S ? R.prog_pred[0] : -1);
-        __threadfence_block();
-        __syncthreads();
+        if (phase >= 1) mz_rn_stage_hidden(X, R);      // root: h0 (pe = 0, dbl = 0); simulations: the parent's state (Q5), for prediction and again for dynamics
+        int first, last, next;
+        if (phase == 0) { first = R.prog_repr[0]; last = R.prog_repr[1]; next = R.prog_pred[0]; X.pool_slot = 0; }
+        else if (phase == 1) { first = R.prog_pred[0]; last = R.prog_pred[1]; next = R.prog_pred[0]; }
+        else if (phase == 2) { first = R.prog_pred[0]; last = R.prog_pred[1]; next = R.prog_dyn[0]; }
+        else { first = R.prog_dyn[0]; last = R.prog_dyn[1]; next = sim < P.S ? R.prog_pred[0] : -1; X.pool_slot = sim; }
+        mz_rn_run(X, R, first, last, next);
+        if (phase == 0 || phase == 3) { __threadfence_block(); __syncthreads(); }   // hidden states written to the pool are read back by the next staging
+        if (phase == 1) {
 #pragma unroll
-        for (int p = 0; p < 2; p++) {
-            if (active[p]) {
-                const uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
-                mz_tree_expand_lanes(P, tree[p], leaf[p].node, sim, legal[p], outL + ts[p], outR[ts[p]], leaf[p].prior, ln, segmask, MZ_RN_OUT_ROWS);
-                mz_tree_backup_lanes(P, tree[p], path, leaf[p].depth, outV[ts[p]], mm[p], ln, segmask);
+            for (int p = 0; p < 2; p++) {
+                if (active[p]) {
+                    if (ln == 0) { mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f; tree[p].A[0] = root; }
+                    __syncwarp(segmask);
+                    mz_tree_expand_lanes(P, tree[p], 0, 0, legal[p], outL + ts[p], 0.0f, 0.0f, ln, segmask, MZ_RN_OUT_ROWS);
+                    if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree[p], legal[p], game[p], move[p]);
+                    __syncwarp(segmask);
+                }
+            }
+        } else if (phase == 3) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                if (active[p]) {
+                    const uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
+                    mz_tree_expand_lanes(P, tree[p], leaf[p].node, sim, legal[p], outL + ts[p], outR[ts[p]], leaf[p].prior, ln, segmask, MZ_RN_OUT_ROWS);
+                    mz_tree_backup_lanes(P, tree[p], path, leaf[p].depth, outV[ts[p]], mm[p], ln, segmask);
+                }
             }
         }
     }
@@ -538,7 +554,6 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
     __syncthreads();
     if (ta.net == 0) {
         mz_rn_im2col(X, P, R, [&](int t, int pl, int cell) { return ta.in[(g0 + t) * P.stack_size + cell + P.cells * pl]; });
-        mz_rn_run(X, R, R.prog_repr[0], R.prog_repr[1], -1);
     } else {
         // stage the fp32 input states as bf16 rows (dynamics: the caller's state is already doubled; the kernel multiplies the accumulator by 2)
         const float mul = ta.net == 2 ? 0.5f : 1.0f;
@@ -555,9 +570,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
         if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_THREADS) sp.plane[t] = sp.active[t] ? ta.in[(g0 + t) * in_dim + P.hidden] : 0.0f;
         mz_fence_proxy_async();
         __syncthreads();
-        if (ta.net == 1) mz_rn_run(X, R, R.prog_pred[0], R.prog_pred[1], -1);
-        else mz_rn_run(X, R, R.prog_dyn[0], R.prog_dyn[1], -1);
     }
+    mz_rn_run(X, R, ta.net == 0 ? R.prog_repr[0] : ta.net == 1 ? R.prog_pred[0] : R.prog_dyn[0], ta.net == 0 ? R.prog_repr[1] : ta.net == 1 ? R.prog_pred[1] : R.prog_dyn[1], -1);
     __threadfence_block();
     __syncthreads();
     if (ta.net != 1) {   // hidden state out: Julia (W,H,nf) order, from the bf16 scratch pool

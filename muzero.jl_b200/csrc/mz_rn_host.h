@@ -199,7 +199,7 @@ inline const char *rn_build(const mz_config &c, const mz_params &P, rn_model &M)
     B.tower(2, nt, 1 /* trunk in T */, 0 /* next state ends in X */, true, 1.0f, 0);
     { const int fu[1] = {2 * nt + 1}, ib[1] = {MZ_RN_BUF_HV}, oi[1] = {MZ_RN_OUT_R}; B.dense_chains(2, 1, fu, ib, oi); }
     R.prog_dyn[1] = (int)M.steps.size();
-    R.n_steps = (int)M.steps.size();
+    R.n_steps = (int)M.steps.size(); R.smem_first = R.prog_pred[0];
     M.image_bytes = B.image_off;
     R.image_bytes = B.image_off;
     int slot = 0;
