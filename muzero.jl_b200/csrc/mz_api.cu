@@ -457,7 +457,7 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
         MZ_TRY(h2d<unsigned char>(c, c->scratch[3], nullptr, (size_t)B * c->rn.R.node_bytes, &d_pool));
         mz_search_rn_args t{}; t.image = c->d_rn_image; t.steps = c->d_rn_steps; t.net = net; t.B = B; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2; t.scratch_pool = d_pool;
         const int nt = c->rn.R.ntrees;
-        launch_scope ls(c, 5); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+        launch_scope ls(c, 5); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
     } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
         mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
         launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -559,7 +559,7 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
             const int nt = c->rn.R.ntrees;
-            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_API><<<(m + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_API><<<(m + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -616,7 +616,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
             const int nt = c->rn.R.ntrees;
-            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
+            launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);

@@ -23,6 +23,8 @@
 #define MZ_RN_TILE_BYTES 16384
 #define MZ_RN_AUX_BYTES 32768
 #define MZ_RN_OUT_ROWS 64          // trees per CTA in the fp32 head outputs / per-tree tables
+#define MZ_RN_THREADS 512         // 16 warps: one warpgroup per tile job in the epilogues, 8 lanes per tree for 64 trees in the tree phases
+#define MZ_RN_NPASS 1
 
 struct mz_rn_plan {
     uint32_t tiles;                // X0..X3, T0..T3 (shared address)
@@ -99,6 +101,19 @@ __device__ __forceinline__ uint32_t mz_pack_bf16(float lo, float hi) {   // roun
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+__device__ __forceinline__ uint32_t mz_pack_bf16_relu(float lo, float hi) {   // max(x, 0) fused into the conversion
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mz_f2pack(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void mz_f2unpack(unsigned long long p, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ unsigned long long mz_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {   // two IEEE fmaf per instruction
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long mz_add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
 __device__ __forceinline__ void mz_mbar_wait_u32(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0, spin = 0;
     while (!ok) {
@@ -117,9 +132,15 @@ struct mz_rn_exec {
     uint32_t sq[2];         // commits seen per scratch barrier
     int pool_slot;          // hidden-state slot written by MZ_RN_F_POOL epilogues
     int W, H;
+    int my_tree, my_cell;   // (tree, cell) of this thread's TMEM lane in its warpgroup's convolution tile
+    int st_tl[2], st_cell[2]; // hidden staging: this thread copies one 16-byte chunk of rows (tid >> 3) and (tid >> 3) + 64 of every tile
+#ifdef MZ_PHASE_TIMERS
+    long long st_t[6]; long long st_c;
+#endif
 };
-__device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, int s, uint32_t slot) {
-    const int off = X.steps[s].w_off, bytes = X.steps[s].w_bytes;
+__device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, const mz_rn_params &R, int s, uint32_t slot) {
+    const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
+    const int off = st->w_off, bytes = st->w_bytes;
     const uint32_t bar = mz_smem_u32(&X.sp.w_bar[slot]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -133,7 +154,7 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
     const uint32_t pS = wslot + (uint32_t)J.p_sub, pT = pS + 256u, pE = pS + 512u;
     const bool trees = (J.flags & MZ_RN_F_TREES) != 0;
     int tree, cell;
-    if (trees) { tree = row; cell = 0; } else { tree = (J.acc) * R.tpt + row / R.cells; cell = row % R.cells; }
+    if (trees) { tree = row; cell = 0; } else { tree = X.my_tree; cell = X.my_cell; }   // convolution job j is always run by warpgroup j
     const bool valid = (trees ? row < R.ntrees : row < R.rows_valid) && X.sp.active[tree < MZ_RN_OUT_ROWS ? tree : 0] != 0;
     const int jflags = J.flags, jact = J.act;
     if (J.epi == MZ_RN_EPI_TILE) {
@@ -144,7 +165,8 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
         unsigned char *pool = nullptr;
         if ((J.flags & MZ_RN_F_POOL) && valid)
             pool = reinterpret_cast<unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.pool_slot * R.node_bytes + (size_t)cell * 128;
-        const float lo = jact == MZ_ACT_RELU ? 0.0f : -INFINITY;
+        const bool relu = jact == MZ_ACT_RELU, plane = (jflags & MZ_RN_F_PLANE) != 0;
+        const unsigned long long rv2 = mz_f2pack(rowval, rowval);
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             uint32_t v[32];
@@ -153,31 +175,31 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
             for (int q = 0; q < 4; q++) {
                 const int c8 = 4 * half + q;
                 const float4 s0 = mz_lds128(pS + c8 * 32), s1 = mz_lds128(pS + c8 * 32 + 16), t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
-                float y[8];
-                const float S[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, T[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-                if (jflags & MZ_RN_F_PLANE) {
+                unsigned long long S[4] = {mz_f2pack(s0.x, s0.y), mz_f2pack(s0.z, s0.w), mz_f2pack(s1.x, s1.y), mz_f2pack(s1.z, s1.w)};
+                unsigned long long T[4] = {mz_f2pack(t0.x, t0.y), mz_f2pack(t0.z, t0.w), mz_f2pack(t1.x, t1.y), mz_f2pack(t1.z, t1.w)};
+                if (plane) {   // + action plane * (w_plane * s): y = fmaf(acc, S, fmaf(plane, E, T))
                     const float4 e0 = mz_lds128(pE + c8 * 32), e1 = mz_lds128(pE + c8 * 32 + 16);
-                    const float E[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-                    for (int i = 0; i < 8; i++) y[i] = fmaf(__uint_as_float(v[8 * q + i]), S[i], fmaf(rowval, E[i], T[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) y[i] = fmaf(__uint_as_float(v[8 * q + i]), S[i], T[i]);
+                    T[0] = mz_fma2(rv2, mz_f2pack(e0.x, e0.y), T[0]); T[1] = mz_fma2(rv2, mz_f2pack(e0.z, e0.w), T[1]);
+                    T[2] = mz_fma2(rv2, mz_f2pack(e1.x, e1.y), T[2]); T[3] = mz_fma2(rv2, mz_f2pack(e1.z, e1.w), T[3]);
                 }
+                unsigned long long y[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) y[i] = mz_fma2(mz_f2pack(__uint_as_float(v[8 * q + 2 * i]), __uint_as_float(v[8 * q + 2 * i + 1])), S[i], T[i]);
                 const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) << 4);
                 if (skp) {
                     const uint4 k = mz_lds128u(skp + chunk);
-                    y[0] = y[0] + mz_bf16lo(k.x); y[1] = y[1] + mz_bf16hi(k.x); y[2] = y[2] + mz_bf16lo(k.y); y[3] = y[3] + mz_bf16hi(k.y);
-                    y[4] = y[4] + mz_bf16lo(k.z); y[5] = y[5] + mz_bf16hi(k.z); y[6] = y[6] + mz_bf16lo(k.w); y[7] = y[7] + mz_bf16hi(k.w);
+                    y[0] = mz_add2(y[0], mz_f2pack(mz_bf16lo(k.x), mz_bf16hi(k.x))); y[1] = mz_add2(y[1], mz_f2pack(mz_bf16lo(k.y), mz_bf16hi(k.y)));
+                    y[2] = mz_add2(y[2], mz_f2pack(mz_bf16lo(k.z), mz_bf16hi(k.z))); y[3] = mz_add2(y[3], mz_f2pack(mz_bf16lo(k.w), mz_bf16hi(k.w)));
                 }
-                uint4 o;
-                if (valid) {
+                uint32_t o[4];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) y[i] = fmaxf(y[i], lo);
-                    o.x = mz_pack_bf16(y[0], y[1]); o.y = mz_pack_bf16(y[2], y[3]); o.z = mz_pack_bf16(y[4], y[5]); o.w = mz_pack_bf16(y[6], y[7]);
-                } else { o.x = o.y = o.z = o.w = 0u; }
-                if (!trees || row < MZ_RN_OUT_ROWS) mz_sts128u(dst + chunk, o);
-                if (pool) *reinterpret_cast<uint4 *>(pool + c8 * 16) = o;
+                for (int i = 0; i < 4; i++) {
+                    float a0, a1; mz_f2unpack(y[i], a0, a1);
+                    o[i] = !valid ? 0u : relu ? mz_pack_bf16_relu(a0, a1) : mz_pack_bf16(a0, a1);
+                }
+                const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+                if (!trees || row < MZ_RN_OUT_ROWS) mz_sts128u(dst + chunk, ov);
+                if (pool) *reinterpret_cast<uint4 *>(pool + c8 * 16) = ov;
             }
         }
     } else if (J.epi == MZ_RN_EPI_HEAD) {
@@ -210,19 +232,26 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
 // Runs steps [first, last) of the program; next_first = the step that will run after this range (its weights are
 // prefetched during the last step), or -1.  Inlined at its (single) call site per kernel so that the executor state
 // stays in registers; the steps of the simulation loop are read from shared memory.
+#ifdef MZ_PHASE_TIMERS
+#define MZ_RN_ST(i) do { long long c_ = clock64(); X.st_t[i] += c_ - X.st_c; X.st_c = c_; } while (0)
+#else
+#define MZ_RN_ST(i)
+#endif
 __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int first, int last, int next_first) {
     const int tid = threadIdx.x, wg = tid >> 7, wgt = tid & 127;
     for (int s = first; s < last; s++) {
+        MZ_RN_ST(5);
         const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
         const uint32_t slot = X.wq & 1u;
         const int next = s + 1 < last ? s + 1 : next_first;
         if (tid == 0) {
-            if (X.pf != s) mz_rn_issue_weights(X, s, slot);
-            if (next >= 0) mz_rn_issue_weights(X, next, slot ^ 1u);
+            if (X.pf != s) mz_rn_issue_weights(X, R, s, slot);
+            if (next >= 0) mz_rn_issue_weights(X, R, next, slot ^ 1u);
         }
         const int njobs = st->njobs, ntaps = st->ntaps, is_last = st->last;
         mz_mbar_wait_u32(mz_smem_u32(&X.sp.w_bar[slot]), (X.wq >> 1) & 1u);
         const uint32_t wslot = X.sp.wring + slot * (uint32_t)X.slot_bytes;
+        MZ_RN_ST(0);
         if (ntaps > 1) {
             // tap-step: per tile, A = copy of the source tile shifted by (dx, dy) cells, built in one of two scratch tiles
             const int dx = st->dx, dy = st->dy, accumulate = st->accumulate;
@@ -232,7 +261,7 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
                 const uint32_t sl = (uint32_t)(j & 1);
                 if (j >= 2) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);   // the MMA that read this scratch tile is done
                 const uint32_t src = mz_rn_buf(X.sp, st->jobs[j].a_buf), dst = mz_rn_buf(X.sp, MZ_RN_BUF_S0 + (int)sl);
-                for (int i = tid; i < 128 * 8; i += MZ_THREADS) {
+                for (int i = tid; i < 128 * 8; i += MZ_RN_THREADS) {
                     const int row = i >> 3, ch = i & 7;
                     uint4 v; v.x = v.y = v.z = v.w = 0u;
                     if (row < R.rows_valid) {
@@ -282,47 +311,63 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
                 __syncwarp();
             }
         }
+        MZ_RN_ST(1);
         if (is_last) {
+            // a warpgroup runs at most one epilogue per step (convolution job j <-> warpgroup j; dense heads: one job per warpgroup),
+            // so the epilogue code exists once
+            int mine = -1; uint32_t par = 0;
 #pragma unroll
             for (int j = 0; j < MZ_RN_TILES; j++) {
-                if (j >= njobs) break;
-                if ((int)st->jobs[j].wg == wg) {
-                    const mz_rn_job J = st->jobs[j];
-                    mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[j]), X.mq[j] & 1u);
-                    mz_tc_fence_after();
-                    __syncwarp();
-                    mz_rn_epilogue(X, R, J, wslot, wgt);
-                }
-                X.mq[j]++;
+                if (j < njobs) { if ((int)st->jobs[j].wg == wg) { mine = j; par = X.mq[j] & 1u; } X.mq[j]++; }
+            }
+            if (mine >= 0) {
+                const mz_rn_job J = st->jobs[mine];
+                mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[mine]), par);
+                mz_tc_fence_after();
+                __syncwarp();
+                MZ_RN_ST(2);
+                mz_rn_epilogue(X, R, J, wslot, wgt);
+                MZ_RN_ST(3);
             }
         }
         mz_fence_proxy_async();
         mz_tc_fence_before();
         __syncthreads();
         mz_tc_fence_after();
+        MZ_RN_ST(4);
         X.wq++; X.pf = next;
     }
 }
 
 // parent hidden states (bf16 rows in the tree pools) -> X tiles, scaled by 2^doublings (Q6); rows of idle trees are zero
 __device__ __forceinline__ void mz_rn_stage_hidden(const mz_rn_exec &X, const mz_rn_params &R) {
-    for (int i = threadIdx.x; i < MZ_RN_TILES * 128 * 8; i += MZ_THREADS) {
-        const int ch = i & 7, row = (i >> 3) & 127, tile = i >> 10;
-        uint4 v; v.x = v.y = v.z = v.w = 0u;
-        if (row < R.rows_valid) {
-            const int tree = tile * R.tpt + row / R.cells, cell = row % R.cells;
+    constexpr int NIT = MZ_RN_TILES * 128 * 8 / MZ_RN_THREADS;   // 16-byte chunks per thread; all loads are issued before the first store
+    static_assert(NIT == 2 * MZ_RN_TILES, "staging layout assumes 512 threads");
+    const int ch = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+    uint4 v[NIT]; float sc[NIT];
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int h = it & 1, tile = it >> 1;
+        v[it] = make_uint4(0u, 0u, 0u, 0u); sc[it] = 1.0f;
+        if (X.st_tl[h] >= 0) {
+            const int tree = tile * R.tpt + X.st_tl[h];
             if (X.sp.active[tree]) {
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.sp.pe[tree] * R.node_bytes + (size_t)cell * 128 + ch * 16;
-                v = *reinterpret_cast<const uint4 *>(src);
-                const int dbl = X.sp.dbl[tree];
-                if (dbl > 0) {
-                    const float sc = __uint_as_float((uint32_t)(127 + dbl) << 23);
-                    v.x = mz_pack_bf16(mz_bf16lo(v.x) * sc, mz_bf16hi(v.x) * sc); v.y = mz_pack_bf16(mz_bf16lo(v.y) * sc, mz_bf16hi(v.y) * sc);
-                    v.z = mz_pack_bf16(mz_bf16lo(v.z) * sc, mz_bf16hi(v.z) * sc); v.w = mz_pack_bf16(mz_bf16lo(v.w) * sc, mz_bf16hi(v.w) * sc);
-                }
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.sp.pe[tree] * R.node_bytes + (size_t)(X.st_cell[h] * 128 + ch * 16);
+                v[it] = *reinterpret_cast<const uint4 *>(src);
+                sc[it] = __uint_as_float((uint32_t)(127 + X.sp.dbl[tree]) << 23);
             }
         }
-        mz_sts128u(X.sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4)), v);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int row = r0 + 64 * (it & 1), tile = it >> 1;
+        uint4 o = v[it];
+        if (sc[it] != 1.0f) {
+            const float f = sc[it];
+            o.x = mz_pack_bf16(mz_bf16lo(o.x) * f, mz_bf16hi(o.x) * f); o.y = mz_pack_bf16(mz_bf16lo(o.y) * f, mz_bf16hi(o.y) * f);
+            o.z = mz_pack_bf16(mz_bf16lo(o.z) * f, mz_bf16hi(o.z) * f); o.w = mz_pack_bf16(mz_bf16lo(o.w) * f, mz_bf16hi(o.w) * f);
+        }
+        mz_sts128u(X.sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4)), o);
     }
     mz_fence_proxy_async();
     __syncthreads();
@@ -341,6 +386,12 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
     X.steps = ta.steps; X.image = ta.image; X.slot_bytes = R.slot_bytes; X.wq = 0; X.pf = -1; X.pool_slot = 0; X.W = P.W; X.H = P.H;
     for (int j = 0; j < 4; j++) X.mq[j] = 0;
     X.sq[0] = X.sq[1] = 0;
+    for (int h = 0; h < 2; h++) { const int row = (int)(threadIdx.x >> 3) + 64 * h; X.st_tl[h] = row < R.rows_valid ? row / R.cells : -1; X.st_cell[h] = row % R.cells; }
+    { const int row = (int)(threadIdx.x & 127); X.my_tree = (int)(threadIdx.x >> 7) * R.tpt + row / R.cells; X.my_cell = row % R.cells; }
+#ifdef MZ_PHASE_TIMERS
+    for (int i = 0; i < 6; i++) X.st_t[i] = 0;
+    X.st_c = clock64();
+#endif
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.w_bar[i], 1);
@@ -353,11 +404,11 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mz_smem_u32(X.sp.tmem_slot)), "r"((uint32_t)MZ_RN_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = tid; i < (8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES) / 16; i += MZ_THREADS) reinterpret_cast<uint4 *>(X.sp.tiles_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < 24 * MZ_RN_OUT_ROWS; i += MZ_THREADS) X.sp.out[i] = 0.0f;
-    for (int i = tid; i < (R.n_steps - R.smem_first) * (int)(sizeof(mz_rn_step) / 4); i += MZ_THREADS)
+    for (int i = tid; i < (8 * MZ_RN_TILE_BYTES + MZ_RN_AUX_BYTES) / 16; i += MZ_RN_THREADS) reinterpret_cast<uint4 *>(X.sp.tiles_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < 24 * MZ_RN_OUT_ROWS; i += MZ_RN_THREADS) X.sp.out[i] = 0.0f;
+    for (int i = tid; i < (R.n_steps - R.smem_first) * (int)(sizeof(mz_rn_step) / 4); i += MZ_RN_THREADS)
         reinterpret_cast<uint32_t *>(X.sp.prog)[i] = reinterpret_cast<const uint32_t *>(ta.steps + R.smem_first)[i];
-    for (int i = tid; i < MZ_RN_OUT_ROWS; i += MZ_THREADS) { X.sp.active[i] = 0; X.sp.pe[i] = 0; X.sp.dbl[i] = 0; X.sp.plane[i] = 0.0f; X.sp.tree_base[i] = 0ull; }
+    for (int i = tid; i < MZ_RN_OUT_ROWS; i += MZ_RN_THREADS) { X.sp.active[i] = 0; X.sp.pe[i] = 0; X.sp.dbl[i] = 0; X.sp.plane[i] = 0.0f; X.sp.tree_base[i] = 0ull; }
     mz_fence_proxy_async();
     mz_tc_fence_before();
     __syncthreads();
@@ -373,7 +424,7 @@ __device__ __forceinline__ void mz_rn_teardown(const mz_rn_exec &X) {
 template <typename F>
 __device__ __forceinline__ void mz_rn_im2col(const mz_rn_exec &X, const mz_params &P, const mz_rn_params &R, F &&stacked /* (tree, plane, cell) -> float */) {
     const int k = R.ksize, pad = k / 2, kk_n = k * k * R.planes;
-    for (int i = threadIdx.x; i < MZ_RN_TILES * 128 * kk_n; i += MZ_THREADS) {
+    for (int i = threadIdx.x; i < MZ_RN_TILES * 128 * kk_n; i += MZ_RN_THREADS) {
         const int kk = i % kk_n, row = (i / kk_n) & 127, tile = i / (kk_n * 128);
         float v = 0.0f;
         if (row < R.rows_valid) {
@@ -388,7 +439,7 @@ __device__ __forceinline__ void mz_rn_im2col(const mz_rn_exec &X, const mz_param
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
+__global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
     extern __shared__ __align__(1024) unsigned char mz_smem_rn[];
     const mz_search_args &a = ta.base;
     mz_rn_exec X;
@@ -396,13 +447,13 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
     const mz_rn_plan &sp = X.sp;
     const int tid = threadIdx.x, ln = tid & (MZ_LANES - 1);
     const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
-    for (int i = tid; i <= P.S + 1; i += MZ_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
+    for (int i = tid; i <= P.S + 1; i += MZ_RN_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
 
-    // ---- per-tree state: two passes of 32 trees, replicated in the 8 lanes of each tree ----
-    bool active[2]; uint32_t legal[2], game[2], move[2], posmask[2]; mz_tree tree[2]; mz_minmax mm[2]; int ts[2]; int64_t gidx[2];
+    // ---- per-tree state: 64 trees x 8 lanes, replicated in the lanes of each tree ----
+    bool active[MZ_RN_NPASS]; uint32_t legal[MZ_RN_NPASS], game[MZ_RN_NPASS], move[MZ_RN_NPASS], posmask[MZ_RN_NPASS]; mz_tree tree[MZ_RN_NPASS]; mz_minmax mm[MZ_RN_NPASS]; int ts[MZ_RN_NPASS]; int64_t gidx[MZ_RN_NPASS];
 #pragma unroll
-    for (int p = 0; p < 2; p++) {
-        ts[p] = 32 * p + (tid >> 3); gidx[p] = (int64_t)blockIdx.x * R.ntrees + ts[p];
+    for (int p = 0; p < MZ_RN_NPASS; p++) {
+        ts[p] = 64 * p + (tid >> 3); gidx[p] = (int64_t)blockIdx.x * R.ntrees + ts[p];
         active[p] = false; legal[p] = 0; game[p] = 0; move[p] = 0; tree[p].A = nullptr; tree[p].hidden = nullptr;
         if (ts[p] < R.ntrees && gidx[p] < a.n) {
             const int64_t g = gidx[p];
@@ -437,14 +488,21 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
     //      One loop so that the step executor is inlined exactly once. ----
     const float *outV = sp.out, *outL = sp.out + 4 * MZ_RN_OUT_ROWS, *outR = sp.out + 20 * MZ_RN_OUT_ROWS;
     unsigned long long depth_sum = 0;
-    mz_leaf leaf[2];
+    mz_leaf leaf[MZ_RN_NPASS];
     int sim = 0;
+#ifdef MZ_PHASE_TIMERS
+    long long rn_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rn_c = clock64();
+#define MZ_RN_T(i) do { long long c_ = clock64(); rn_t[i] += c_ - rn_c; rn_c = c_; } while (0)
+#else
+#define MZ_RN_T(i)
+#endif
     for (int phase = 0; ; phase = phase == 3 ? 2 : phase + 1) {
+        MZ_RN_T(7);
         if (phase == 2) {
             if (++sim > P.S) break;
             // select (SelfPlay.jl:261-268); the parent's hidden state will be staged for both networks
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
+            for (int p = 0; p < MZ_RN_NPASS; p++) {
                 leaf[p].node = 0; leaf[p].parent = 0; leaf[p].action = 1; leaf[p].depth = 0; leaf[p].prior = 0.0f; leaf[p].parent_x = 0;
                 if (active[p]) {
                     uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
@@ -458,18 +516,21 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
                 }
             }
             __syncthreads();
+            MZ_RN_T(0);
         }
-        if (phase >= 1) mz_rn_stage_hidden(X, R);      // root: h0 (pe = 0, dbl = 0); simulations: the parent's state (Q5), for prediction and again for dynamics
+        if (phase >= 1) mz_rn_stage_hidden(X, R);
+        MZ_RN_T(1);      // root: h0 (pe = 0, dbl = 0); simulations: the parent's state (Q5), for prediction and again for dynamics
         int first, last, next;
         if (phase == 0) { first = R.prog_repr[0]; last = R.prog_repr[1]; next = R.prog_pred[0]; X.pool_slot = 0; }
         else if (phase == 1) { first = R.prog_pred[0]; last = R.prog_pred[1]; next = R.prog_pred[0]; }
         else if (phase == 2) { first = R.prog_pred[0]; last = R.prog_pred[1]; next = R.prog_dyn[0]; }
         else { first = R.prog_dyn[0]; last = R.prog_dyn[1]; next = sim < P.S ? R.prog_pred[0] : -1; X.pool_slot = sim; }
         mz_rn_run(X, R, first, last, next);
+        MZ_RN_T(phase == 0 ? 2 : phase == 3 ? 4 : 3);
         if (phase == 0 || phase == 3) { __threadfence_block(); __syncthreads(); }   // hidden states written to the pool are read back by the next staging
         if (phase == 1) {
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
+            for (int p = 0; p < MZ_RN_NPASS; p++) {
                 if (active[p]) {
                     if (ln == 0) { mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f; tree[p].A[0] = root; }
                     __syncwarp(segmask);
@@ -480,19 +541,24 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
             }
         } else if (phase == 3) {
 #pragma unroll
-            for (int p = 0; p < 2; p++) {
+            for (int p = 0; p < MZ_RN_NPASS; p++) {
                 if (active[p]) {
                     const uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
                     mz_tree_expand_lanes(P, tree[p], leaf[p].node, sim, legal[p], outL + ts[p], outR[ts[p]], leaf[p].prior, ln, segmask, MZ_RN_OUT_ROWS);
                     mz_tree_backup_lanes(P, tree[p], path, leaf[p].depth, outV[ts[p]], mm[p], ln, segmask);
                 }
             }
+            MZ_RN_T(5);
         }
     }
+#ifdef MZ_PHASE_TIMERS
+    if (a.stats && tid == 0) { for (int i = 0; i < 8; i++) atomicAdd(&a.stats[32 + i], (unsigned long long)rn_t[i]); atomicAdd(&a.stats[40], 1ull); }
+    if (a.stats && (tid == 0 || tid == 128)) { for (int i = 0; i < 6; i++) atomicAdd(&a.stats[41 + 7 * (tid >> 7) + i], (unsigned long long)X.st_t[i]); atomicAdd(&a.stats[47 + 7 * (tid >> 7)], (unsigned long long)X.wq); }
+#endif
 
     // ---- results (lane 0 of each tree), as in mz_k_search ----
 #pragma unroll
-    for (int p = 0; p < 2; p++) {
+    for (int p = 0; p < MZ_RN_NPASS; p++) {
         if (!(active[p] && ln == 0)) continue;
         const int64_t g = gidx[p];
         int32_t vc[MZ_MAX_A]; int sum_visits = 0, nlegal = 0;
@@ -539,7 +605,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_rn(const __grid_consta
 
 // batched network callables (init_*(hyper::ResNetHP) callables): net 0 representation(stacked), 1 prediction(hidden),
 // 2 dynamics(state_action).  Hidden states go through a scratch pool of one slot per tree (bf16, like the real pool).
-__global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
+__global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_rn_forward(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
     extern __shared__ __align__(1024) unsigned char mz_smem_rn[];
     mz_rn_exec X;
     mz_rn_setup(X, P, R, ta, mz_smem_rn);
@@ -547,7 +613,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
     const int tid = threadIdx.x;
     const int64_t g0 = (int64_t)blockIdx.x * R.ntrees;
     // scratch pool: per tree one hidden slot, addressed as tree_base + hidden_off + 0 * node_bytes
-    for (int t = tid; t < R.ntrees; t += MZ_THREADS) {
+    for (int t = tid; t < R.ntrees; t += MZ_RN_THREADS) {
         sp.active[t] = g0 + t < ta.B ? 1 : 0;
         sp.tree_base[t] = (unsigned long long)(uintptr_t)(ta.scratch_pool + (size_t)(g0 + t) * R.node_bytes) - (unsigned long long)R.hidden_off_bytes;
     }
@@ -558,7 +624,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
         // stage the fp32 input states as bf16 rows (dynamics: the caller's state is already doubled; the kernel multiplies the accumulator by 2)
         const float mul = ta.net == 2 ? 0.5f : 1.0f;
         const int in_dim = ta.net == 2 ? P.sa_size : P.hidden;
-        for (int i = tid; i < MZ_RN_TILES * 128 * 64; i += MZ_THREADS) {
+        for (int i = tid; i < MZ_RN_TILES * 128 * 64; i += MZ_RN_THREADS) {
             const int c = i & 63, row = (i >> 6) & 127, tile = i >> 13;
             float v = 0.0f;
             if (row < R.rows_valid && c < R.nf) {
@@ -567,7 +633,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
             }
             mz_tc_store_bf16(sp.tiles + (uint32_t)(tile * MZ_RN_TILE_BYTES), row, c, v);
         }
-        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_THREADS) sp.plane[t] = sp.active[t] ? ta.in[(g0 + t) * in_dim + P.hidden] : 0.0f;
+        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_RN_THREADS) sp.plane[t] = sp.active[t] ? ta.in[(g0 + t) * in_dim + P.hidden] : 0.0f;
         mz_fence_proxy_async();
         __syncthreads();
     }
@@ -575,16 +641,16 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_rn_forward(const __grid_const
     __threadfence_block();
     __syncthreads();
     if (ta.net != 1) {   // hidden state out: Julia (W,H,nf) order, from the bf16 scratch pool
-        for (int i = tid; i < R.ntrees * P.hidden; i += MZ_THREADS) {
+        for (int i = tid; i < R.ntrees * P.hidden; i += MZ_RN_THREADS) {
             const int t = i / P.hidden, k = i % P.hidden, cell = k % P.cells, c = k / P.cells;
             if (g0 + t < ta.B) {
                 const unsigned short h = *reinterpret_cast<const unsigned short *>(ta.scratch_pool + (size_t)(g0 + t) * R.node_bytes + (size_t)cell * 128 + c * 2);
                 ta.out1[(g0 + t) * P.hidden + k] = __uint_as_float((uint32_t)h << 16);
             }
         }
-        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_THREADS) if (g0 + t < ta.B) ta.out2[g0 + t] = sp.out[20 * MZ_RN_OUT_ROWS + t];
+        if (ta.net == 2) for (int t = tid; t < R.ntrees; t += MZ_RN_THREADS) if (g0 + t < ta.B) ta.out2[g0 + t] = sp.out[20 * MZ_RN_OUT_ROWS + t];
     } else {
-        for (int t = tid; t < R.ntrees; t += MZ_THREADS) if (g0 + t < ta.B) {
+        for (int t = tid; t < R.ntrees; t += MZ_RN_THREADS) if (g0 + t < ta.B) {
             float logits[MZ_MAX_A], policy[MZ_MAX_A];
             for (int i = 0; i < P.A; i++) logits[i] = sp.out[4 * MZ_RN_OUT_ROWS + i * MZ_RN_OUT_ROWS + t];
             mz_softmax(logits, P.A, policy);

@@ -117,7 +117,7 @@ struct rn_builder {
             for (int j = 0; j < MZ_RN_TILES; j++) {
                 mz_rn_job &J = st.jobs[j];
                 J.a_buf = (uint8_t)(src * MZ_RN_TILES + j); J.dst_buf = (uint8_t)(dst * MZ_RN_TILES + j); J.skip_buf = skip >= 0 ? (uint8_t)(skip * MZ_RN_TILES + j) : 0xff;
-                J.epi = MZ_RN_EPI_TILE; J.n16 = 4; J.kblocks = 1; J.act = (uint8_t)act; J.wg = (uint8_t)(j & 1); J.acc = (uint8_t)j;
+                J.epi = MZ_RN_EPI_TILE; J.n16 = 4; J.kblocks = 1; J.act = (uint8_t)act; J.wg = (uint8_t)j; J.acc = (uint8_t)j;
                 J.flags = (uint8_t)((plane ? MZ_RN_F_PLANE : 0) | (to_pool ? MZ_RN_F_POOL : 0)); J.wref = wi;
             }
             finish(st, v, blk);
@@ -139,7 +139,7 @@ struct rn_builder {
         for (int j = 0; j < MZ_RN_TILES; j++) {
             mz_rn_job &J = st.jobs[j];
             J.a_buf = (uint8_t)(src * MZ_RN_TILES + j); J.dst_buf = (uint8_t)ha; J.dst2_buf = (uint8_t)(ub >= 0 ? hb : 0xff); J.skip_buf = 0xff;
-            J.epi = MZ_RN_EPI_HEAD; J.n16 = 1; J.kblocks = 1; J.act = MZ_ACT_RELU; J.wg = (uint8_t)(j & 1); J.acc = (uint8_t)j;
+            J.epi = MZ_RN_EPI_HEAD; J.n16 = 1; J.kblocks = 1; J.act = MZ_ACT_RELU; J.wg = (uint8_t)j; J.acc = (uint8_t)j;
             J.nfa = (uint8_t)M.units[net][ua].cout; J.nfb = (uint8_t)(ub >= 0 ? M.units[net][ub].cout : 0); J.wref = wi;
         }
         finish(st, v, blk);
