@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--nn", default="fp32", choices=["fp32", "tc"],
                     help="network arithmetic of the headline number: fp32 = exact (bit-identical to the oracle), tc = bf16 tcgen05")
     ap.add_argument("--no-tc-extra", action="store_true", help="skip the additional tensor-core measurement in fp32 mode")
+    ap.add_argument("--no-resnet-extra", action="store_true", help="skip the additional ResNet measurement (BASELINE.json configs[2]: 16384 games, bf16)")
+    ap.add_argument("--resnet-games", type=int, default=16384)
     return ap.parse_args()
 
 
@@ -245,6 +247,27 @@ def run_b200(a):
             tc_extra = (tms, tsims, tk_ms, tk_n)
             ctx_tc.close()
         barrier()
+        # ---- BASELINE.json configs[2]: TicTacToe ResNet, 16384 concurrent games, bf16 inference on tcgen05 (reported beside the headline) ----
+        rn_extra = None
+        if not a.no_resnet_extra:
+            Gr = a.resnet_games
+            ctx_rn = capi.Context(capi.resnet_config(num_slots=Gr, num_iters=S, replay_buffer_size=max(10000, Gr)), device=local, stream=stream.cuda_stream)
+            ctx_rn.init_weights(1337)
+            for i in range(a.warmup):
+                ctx_rn.self_play(game_base + i * Gr, Gr, 1.0)
+            rms, rsims = 0.0, 0
+            ctx_rn.kernel_time_reset(True)
+            for i in range(a.steps):
+                flush.zero_(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                s_, _ = ctx_rn.self_play(game_base + (a.warmup + i) * Gr, Gr, 1.0)
+                e1.record(stream); e1.synchronize()
+                rms += e0.elapsed_time(e1); rsims += s_
+            rk_ms, rk_n = ctx_rn.kernel_time(0)
+            rn_extra = (rms, rsims, rk_ms, rk_n, Gr)
+            ctx_rn.close()
+        barrier()
         # ---- learner: samples/s at the reference batch (32) ----
         learner = None
         if not a.no_learner:
@@ -296,12 +319,12 @@ def run_b200(a):
                     learner["large_batch"]["reference_l2"] = entry
             big.close()
 
-    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0, rn_extra[0] if rn_extra else 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0, rn_extra[1] if rn_extra else 0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max = [float(x) for x in t.cpu()]
-    sims_all, e2e_sims_all, launches_all, tc_sims_all = [float(x) for x in cnt.cpu()]
+    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max, rn_ms_max = [float(x) for x in t.cpu()]
+    sims_all, e2e_sims_all, launches_all, tc_sims_all, rn_sims_all = [float(x) for x in cnt.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -345,6 +368,20 @@ def run_b200(a):
                                                "note": "useful (unpadded) network FLOPs only; M=64 x N=32 x K<=64 MMAs in a 8-round dependent chain are latency-bound"},
                                   "note": "same waves with the networks on tcgen05 (bf16 operands, fp32 accumulate); results agree with the "
                                           "oracle to bf16 tolerance, not bit-exactly, so the headline value is the exact-fp32 path"}
+        if rn_extra:
+            # useful network MACs per simulation, nf = 64, 2 blocks, hs = 64, depth_value = 1 (DESIGN.md "ResNet"): prediction 196,608 + dynamics 374,528;
+            # + per move (1/S of it per simulation): representation 3x3 tower (in-bounds taps only) 824,768 + prediction 196,608
+            bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            flops_per_sim = 2 * (196608 + 374528) + 2 * (824768 + 196608) / S
+            rn_launch_s = (rn_extra[2] / max(rn_extra[3], 1)) * 1e-3
+            rn_tflops = flops_per_sim * (rn_extra[1] / max(rn_extra[3], 1)) / rn_launch_s / 1e12 if rn_launch_s > 0 else 0.0
+            out["resnet"] = {"value": rn_sims_all / (rn_ms_max * 1e-3), "unit": UNIT, "ms_per_step": rn_ms_max / a.steps, "dtype": "bf16",
+                             "config": {"workload": "TicTacToe ResNet (repaired ResNetHP: 64 filters, 2 blocks, 3x3 representation, 1x1 elsewhere), %d concurrent games x %d simulations/move per GPU, bf16 inference" % (rn_extra[4], S)},
+                             "kernel": "mz_k_search_rn<MODE_SLOTS>", "avg_launch_ms": rn_extra[2] / max(rn_extra[3], 1),
+                             "roofline": {"bound": "tensor", "achieved": rn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": rn_tflops / bf16_peak,
+                                          "flops_per_simulation": flops_per_sim,
+                                          "note": "useful FLOPs only; K = 64 per layer, so every output element is read from TMEM (64 B/clk/SM) for 64 MACs: the "
+                                                  "epilogue's TMEM reads bound the tensor pipe at ~25 % busy; see DESIGN.md"}}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
             for e_ in (learner["bptt"], learner["large_batch"]["bptt"], learner["large_batch"]["reference_l2"]):

@@ -186,11 +186,11 @@ int write_counters(mz_ctx *c) {
 
 int ctx_net_params(const mz_ctx *c, int net) {
     if (c->cfg.net_type == MZ_NET_RESNET) return net == MZ_NET_ALL ? mzh::rn_total_params(c->rn) : c->rn.n_params[net];
-    return ctx_net_params(c, net);
+    return mzh::net_params(c->M.P, net);
 }
 int ctx_net_offset(const mz_ctx *c, int net) {
     if (c->cfg.net_type == MZ_NET_RESNET) return net == MZ_NET_ALL ? 0 : c->rn.base[net];
-    return ctx_net_offset(c, net);
+    return mzh::net_src_offset(c->M.P, net);
 }
 template <typename T> int h2d(mz_ctx *c, dev_buf &b, const T *host, size_t n, T **out) {
     MZ_CUDA(c, b.ensure(n * sizeof(T) + 16));
