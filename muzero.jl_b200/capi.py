@@ -148,6 +148,18 @@ def resnet_config(**kw):
     return cfg
 
 
+def connect_config(**kw):
+    """The synthetic 6x7, 7-action Connect game (BASELINE.json configs[3]) with the ResNet networks."""
+    base = dict(game=GAME_CONNECT, W=6, H=7, A=7, max_moves=42)
+    base.update(kw)
+    cfg = resnet_config(**base)
+    order = (C.c_int32 * MAX_A)()
+    lib().mz_julia_dict_order(cfg.A, order)
+    for i in range(MAX_A):
+        cfg.child_order[i] = order[i] if i < cfg.A else 0
+    return cfg
+
+
 def sizes(cfg):
     planes = cfg.C * (cfg.stacked_observations + 1) + cfg.stacked_observations
     return dict(obs=cfg.W * cfg.H * cfg.C, stack=cfg.W * cfg.H * planes, sa=cfg.hidden_state_size + cfg.W * cfg.H,

@@ -528,13 +528,38 @@ static int ttt_is_win_side_to_move(const mzo_env *e) {
 }
 static uint64_t cells_mask(const mzo_config *c) { return (c->W * c->H >= 64) ? ~0ull : ((1ull << (c->W * c->H)) - 1ull); }
 
+/* ---- MZO_GAME_CONNECT: the synthetic larger-board game of BASELINE.json configs[3] (no reference code; SURVEY 8d:
+ * "column drop, 4-in-row, clean termination, reward to last mover").  The observation is (W,H,3) with W rows and H columns,
+ * cell = row + W*column, row 0 is the bottom; action a in 1..H drops a mark into column a.  The game ends when the LAST MOVER
+ * has four in a row (horizontal, vertical or diagonal) or the board is full; reward(env, p) = +1 / -1 for the last mover /
+ * the other player after a win, 0 otherwise.  None of TicTacToe's quirks (Q14-Q16) apply. ---- */
+static int cn_at(const mzo_config *c, uint64_t b, int r, int col) { return (r >= 0 && r < c->W && col >= 0 && col < c->H) ? (int)((b >> (r + c->W * col)) & 1ull) : 0; }
+static int cn_height(const mzo_config *c, const mzo_env *e, int col) { int h = 0; while (h < c->W && cn_at(c, e->p1 | e->p2, h, col)) h++; return h; }
+static int cn_has4(const mzo_config *c, uint64_t b) {
+    static const int dr[4] = {1, 0, 1, 1}, dc[4] = {0, 1, 1, -1};
+    for (int col = 0; col < c->H; col++) for (int r = 0; r < c->W; r++) for (int d = 0; d < 4; d++) {
+        int n = 0;
+        while (n < 4 && cn_at(c, b, r + n * dr[d], col + n * dc[d])) n++;
+        if (n == 4) return 1;
+    }
+    return 0;
+}
+static int cn_last_mover_won(const mzo_config *c, const mzo_env *e) { return cn_has4(c, e->player == 1 ? e->p2 : e->p1); }
+static int cn_full(const mzo_config *c, const mzo_env *e) { for (int col = 0; col < c->H; col++) if (cn_height(c, e, col) < c->W) return 0; return 1; }
+
 uint32_t mzo_env_legal_mask(const mzo_config *c, const mzo_env *e) { /* game.jl:35-43 */
+    if (c->game == MZO_GAME_CONNECT) {
+        uint32_t m = 0;
+        if (cn_last_mover_won(c, e)) return 0;
+        for (int col = 0; col < c->H; col++) if (cn_height(c, e, col) < c->W) m |= 1u << col;
+        return m;
+    }
     if (ttt_is_win_side_to_move(e)) return 0; /* is_win(env,1) || is_win(env,2): both test env.player */
     return (uint32_t)(~(e->p1 | e->p2) & cells_mask(c));
 }
 void mzo_env_step(const mzo_config *c, mzo_env *e, int action) { /* game.jl:45-52 */
-    (void)c;
     uint64_t bit = 1ull << (action - 1);
+    if (c->game == MZO_GAME_CONNECT) bit = 1ull << (cn_height(c, e, action - 1) + c->W * (action - 1));
     if (e->player == 1) e->p1 |= bit; else e->p2 |= bit; /* board[a,3]=false; board[a,player]=true */
     e->moves += 1;
     e->player = e->player == 1 ? 2 : 1;                  /* mod1(player+1, 2) */
@@ -542,10 +567,12 @@ void mzo_env_step(const mzo_config *c, mzo_env *e, int action) { /* game.jl:45-5
 /* State table (game.jl:117-147): is_terminated = !(has_empty_pos && isnothing(w)), w = 1 when
  * is_win (of the side to move, Q14-Q15) else nothing; winner is never 2. */
 int mzo_env_is_terminated(const mzo_config *c, const mzo_env *e) { /* game.jl:85 */
+    if (c->game == MZO_GAME_CONNECT) return cn_full(c, e) || cn_last_mover_won(c, e);
     int has_empty = (~(e->p1 | e->p2) & cells_mask(c)) != 0;
     return !(has_empty && !ttt_is_win_side_to_move(e));
 }
 int mzo_env_reward(const mzo_config *c, const mzo_env *e, int player) { /* game.jl:87-100 */
+    if (c->game == MZO_GAME_CONNECT) return !cn_last_mover_won(c, e) ? 0 : (player == (e->player == 1 ? 2 : 1) ? 1 : -1);
     if (!mzo_env_is_terminated(c, e)) return 0;
     if (!ttt_is_win_side_to_move(e)) return 0; /* winner === nothing */
     return player == 1 ? 1 : -1;               /* winner is always 1 (Q15) */

@@ -144,6 +144,18 @@ def resnet_config(**kw):
     return cfg
 
 
+def connect_config(**kw):
+    """The synthetic 6x7, 7-action Connect game of BASELINE.json configs[3] with the ResNet networks."""
+    base = dict(game=1, W=6, H=7, A=7, max_moves=42)
+    base.update(kw)
+    cfg = resnet_config(**base)
+    order = (C.c_int32 * MAX_A)()
+    lib().mzo_julia_dict_order(cfg.A, order)
+    for i in range(MAX_A):
+        cfg.child_order[i] = order[i] if i < cfg.A else 0
+    return cfg
+
+
 def num_params(cfg, net=3):
     return lib().mzo_num_params(C.byref(cfg), net)
 
