@@ -196,7 +196,7 @@ class Context:
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self.L.mz_destroy(self._h)
-            self._h = C.c_void_p()
+            self._h = None          # (at interpreter shutdown the ctypes module may already be gone: no C.c_void_p() here)
 
     __del__ = close
 
