@@ -60,6 +60,7 @@ struct mz_ctx {
     cudaStream_t stream = nullptr; bool own_stream = false;
     std::string err;
     size_t smem_bytes = 0; int sm_count = 0;
+    int exact_gt = 128;   // threads per network group of the exact search kernel: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps; measured no faster: the layer is bound by shared-memory wavefronts)
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     unsigned char *d_w_tc = nullptr; float *d_bias_tc = nullptr; size_t smem_bytes_tc = 0;   // tensor-core weight image
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
@@ -315,6 +316,9 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (c->smem_bytes > (size_t)prop.sharedMemPerBlockOptin) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "network needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes, (size_t)prop.sharedMemPerBlockOptin); mz_destroy(c); return r; }
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API>, prop));
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API, 256>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS, 256>, prop));
+    if (const char *eg = getenv("MZ_EXACT_GROUP")) c->exact_gt = atoi(eg) == 256 ? 256 : 128;   // measurement switch
     MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
     MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
     if (!resnet) { if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; } }
@@ -563,7 +567,8 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
-        } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API, 256><<<(m + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
+        else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         MZ_CUDA(c, cudaGetLastError());
         MZ_TRY(d2h(c, visit_counts + (size_t)off * P.A, d_vc, (size_t)m * P.A)); MZ_TRY(d2h(c, root_value + off, d_rv, (size_t)m));
         if (root_priors) MZ_TRY(d2h(c, root_priors + (size_t)off * P.A, d_pri, (size_t)m * P.A));
@@ -620,7 +625,8 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
-        } else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
+        else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
     }
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));

@@ -174,24 +174,27 @@ __device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const m
     __syncwarp(segmask);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
+// GT = threads per network group: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps for the same work; the tree
+// phases still use 8 lanes x 32 trees = the first 256 threads).
+template <int MODE, int GT = MZ_GROUP>
+__global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
+    constexpr int NT = 2 * GT;
     const int tid = threadIdx.x;
     const int r = tid >> 3, ln = tid & (MZ_LANES - 1);              // tree (row) of this thread and its lane within the tree
     const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + r;
     mz_nn_pipe pipe;
-    mz_pipe_init(pipe, sp, a.wglob);
-    mz_zero_activations(sp, a.max_dim);
-    for (int i = tid; i <= P.S + 1; i += MZ_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
+    mz_pipe_init<GT>(pipe, sp, a.wglob);
+    mz_zero_activations<NT>(sp, a.max_dim);
+    for (int i = tid; i <= P.S + 1; i += NT) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
     uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
     bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
     mz_tree tree; tree.A = nullptr; tree.hidden = nullptr;
-    if (g < a.n) {
+    if (r < MZ_ROWS && g < a.n) {
         tree = mz_tree_at(P, a.tree_pool, g);
         if (MODE == MZ_MODE_API) {
             active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
@@ -210,17 +213,17 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
     __syncthreads();   // mbarrier init + zeroed buffers visible
     const int pred_first = P.nets[1].first, dyn_first = P.nets[2].first;
     if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);            // group 0: representation, then prediction
-    if (tid == MZ_GROUP) mz_nn_issue(pipe, P, dyn_first, 0);           // group 1: dynamics (first used in simulation 1)
+    if (tid == GT) mz_nn_issue(pipe, P, dyn_first, 0);           // group 1: dynamics (first used in simulation 1)
 
     // ---- stage the stacked observations, k-major (get_stacked_observations, SelfPlay.jl:128-149) ----
     if (MODE == MZ_MODE_API) {
-        for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+        for (int i = tid; i < MZ_ROWS * P.stack_size; i += NT) {
             int rr = i / P.stack_size, k = i % P.stack_size;
             int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + rr;
             sp.in0[k * MZ_ROWS + rr] = gg < a.n ? a.stacked[gg * P.stack_size + k] : 0.0f;
         }
     } else {
-        for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+        for (int i = tid; i < MZ_ROWS * P.stack_size; i += NT) {
             int k = i / MZ_ROWS, rr = i % MZ_ROWS;
             int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + rr;
             float v = 0.0f;
@@ -235,8 +238,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
 
     // ---- root: representation -> h0; prediction(h0) -> (v0, p0)  (SelfPlay.jl:233-245), group 0 only ----
     if (pipe.grp == 0) {
-        mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
-        mz_nn_net(pipe, P, 1, pred_first, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // prefetches simulation 1's first layer
+        mz_nn_net<GT>(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net<GT>(pipe, P, 1, pred_first, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // prefetches simulation 1's first layer
     }
     __syncthreads();
 
@@ -279,8 +282,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search(const __grid_constant_
         MZ_TIMER(2);
         __syncthreads();
         MZ_TIMER(3);
-        if (pipe.grp == 0) mz_nn_net(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
-        else               mz_nn_net(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
+        if (pipe.grp == 0) mz_nn_net<GT>(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+        else               mz_nn_net<GT>(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
         MZ_TIMER(4);
         __syncthreads();
         MZ_TIMER(5);
