@@ -294,19 +294,22 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
 #pragma unroll
             for (uint32_t sl = 0; sl < 2; sl++) if (X.sq[sl] > 0) mz_mbar_wait_u32(mz_smem_u32(&X.sp.scr_bar[sl]), (X.sq[sl] - 1u) & 1u);
         } else {
-            if (tid < 32) {
+            // every warpgroup's first warp issues the MMAs of the job that warpgroup will run the epilogue of (tcgen05.mma may be issued
+            // from any warp): the four issues run in parallel instead of one thread issuing 16 MMAs ahead of its own epilogue
+            if ((tid & 127) < 32) {
                 mz_tc_fence_after();
-                if (mz_elect_one()) {
-                    for (int j = 0; j < njobs; j++) {
-                        const mz_rn_job J = st->jobs[j];
-                        const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
-                        for (int kb = 0; kb < J.kblocks; kb++) {
-                            const uint64_t ad = mz_tc_desc(a + (uint32_t)kb * 8192u), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub + (uint32_t)(kb * J.n16 * 2048));
+                int mine = -1;
 #pragma unroll
-                            for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
+                for (int j = 0; j < MZ_RN_TILES; j++) if (j < njobs && (int)st->jobs[j].wg == wg) mine = j;
+                if (mine >= 0 && mz_elect_one()) {
+                    const mz_rn_job J = st->jobs[mine];
+                    const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
+                    for (int kb = 0; kb < J.kblocks; kb++) {
+                        const uint64_t ad = mz_tc_desc(a + (uint32_t)kb * 8192u), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub + (uint32_t)(kb * J.n16 * 2048));
+#pragma unroll
+                        for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[mine])) : "memory");
                 }
                 __syncwarp();
             }
