@@ -134,6 +134,12 @@ int mz_history_export(mz_ctx *ctx, int64_t key0, int n, int64_t *game_id, int32_
 int mz_history_import(mz_ctx *ctx, int n, const int64_t *game_id, const int32_t *T, const float *obs, const int32_t *actions,
                       const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values);
 int mz_replay_clear(mz_ctx *ctx);
+/* reanalyse: fills GameHistory.reanalysed_predicted_root_values (src/Constructors.jl:13) of games key0 .. key0+n-1 with the value
+ * head of the CURRENT networks at every stored position, prediction(representation(get_stacked_observations(history, i))).
+ * The reference consumes the field in compute_target_value (src/ReplayBuffer.jl:8) but has no producer (main.jl:18 keeps only a
+ * counter); from then on get_batch / mz_learn_step bootstrap those games' value targets from the reanalysed values. */
+int mz_reanalyse(mz_ctx *ctx, int64_t key0, int n);
+int mz_reanalysed_export(mz_ctx *ctx, int64_t key0, int n, float *values /* [n][Tmax] */, int32_t *is_set /* [n]: 0 = nothing */);
 
 /* ---- replay sampling + targets: get_batch (src/ReplayBuffer.jl:188-217) ---------------------- */
 int mz_get_batch(mz_ctx *ctx, uint64_t step, int32_t *index_batch /* [B][2] (game key, position) */, float *obs_batch,

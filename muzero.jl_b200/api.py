@@ -276,6 +276,12 @@ def get_batch(engine: Engine, step=None):
     return index_batch, (b["obs"], b["actions"], b["values"], b["rewards"], b["policies"], None, b["gscale"])
 
 
+def reanalyse(engine: Engine, key0=None, n=None):
+    """Producer of `GameHistory.reanalysed_predicted_root_values` (Constructors.jl:13; consumed by compute_target_value,
+    ReplayBuffer.jl:8; the reference has no producer): the current networks' root value at every stored position."""
+    engine.ctx.reanalyse(key0, n)
+
+
 def learning(engine: Engine, steps: int, grad_mode=capi.GRAD_REFERENCE_L2, log_every=0):
     """learning! (Learning.jl:306-438): `steps` iterations of get_batch -> unroll -> loss -> gradients -> ADAM(Cos schedule).
     Returns the three losses (representation, prediction, dynamics) of the last step."""

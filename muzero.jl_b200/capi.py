@@ -102,6 +102,8 @@ def lib():
         "mz_history_export": ([ctx, C.c_int64, C.c_int, i64p, i32p, f32p, i32p, f32p, i32p, f32p, f32p], C.c_int),
         "mz_history_import": ([ctx, C.c_int, i64p, i32p, f32p, i32p, f32p, i32p, f32p, f32p], C.c_int),
         "mz_replay_clear": ([ctx], C.c_int),
+        "mz_reanalyse": ([ctx, C.c_int64, C.c_int], C.c_int),
+        "mz_reanalysed_export": ([ctx, C.c_int64, C.c_int, f32p, i32p], C.c_int),
         "mz_get_batch": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
         "mz_learn_forward": ([ctx, C.c_int] + [f32p] * 10, C.c_int),
         "mz_learn_step": ([ctx, C.c_int64, C.c_int, f32p], C.c_int),
@@ -350,6 +352,21 @@ class Context:
                                      _p(out["values"], C.c_float), _p(out["rewards"], C.c_float), _p(out["policies"], C.c_float),
                                      _p(out["gscale"], C.c_float)))
         return out
+
+    def reanalyse(self, key0=None, n=None):
+        """reanalysed_predicted_root_values of games key0 .. key0+n-1 (default: the whole buffer) from the current networks."""
+        info = self.replay_info()
+        key0 = info["first_key"] if key0 is None else key0
+        n = info["n_games"] - (key0 - info["first_key"]) if n is None else n
+        self._ck(self.L.mz_reanalyse(self._h, key0, n))
+
+    def reanalysed_export(self, key0=None, n=None):
+        info = self.replay_info()
+        key0 = info["first_key"] if key0 is None else key0
+        n = info["n_games"] - (key0 - info["first_key"]) if n is None else n
+        values = np.zeros((n, self.s["Tmax"]), np.float32); flags = np.zeros(n, np.int32)
+        self._ck(self.L.mz_reanalysed_export(self._h, key0, n, _p(values, C.c_float), _p(flags, C.c_int32)))
+        return values, flags
 
     # ---- learner ----
     def _batch_ptrs(self, batch):

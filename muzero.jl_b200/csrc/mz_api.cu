@@ -320,6 +320,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS, 256>, prop));
     if (const char *eg = getenv("MZ_EXACT_GROUP")) c->exact_gt = atoi(eg) == 256 ? 256 : 128;   // measurement switch
     MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
+    MZ_CREATE(allow_max_smem(mz_k_reanalyse, prop));
     MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
     if (!resnet) { if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; } }
     c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
@@ -362,6 +363,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(dmalloc(&r.game_id, R)); MZ_CREATE(dmalloc(&r.T, R));
     MZ_CREATE(dmalloc(&r.h_p1, R * Tm)); MZ_CREATE(dmalloc(&r.h_p2, R * Tm)); MZ_CREATE(dmalloc(&r.h_action, R * Tm));
     MZ_CREATE(dmalloc(&r.h_reward, R * Tm)); MZ_CREATE(dmalloc(&r.h_to_play, R * Tm)); MZ_CREATE(dmalloc(&r.h_cv, R * Tm * P.A)); MZ_CREATE(dmalloc(&r.h_rv, R * Tm));
+    MZ_CREATE(dmalloc(&r.h_rrv, R * Tm)); MZ_CREATE(dmalloc(&r.reanalysed, R)); MZ_CREATE(cudaMemset(r.reanalysed, 0, R)); MZ_CREATE(cudaMemset(r.h_rrv, 0, R * Tm * sizeof(float)));
     MZ_CREATE(dmalloc(&r.counters, 8)); MZ_CREATE(cudaMemset(r.counters, 0, 8 * sizeof(int64_t)));
     MZ_CREATE(cudaMemset(r.T, 0, R * sizeof(int32_t)));
     MZ_CREATE(dmalloc(&c->d_stats, 64)); MZ_CREATE(cudaMemset(c->d_stats, 0, 64 * sizeof(unsigned long long)));
@@ -384,7 +386,7 @@ int mz_destroy(mz_ctx *c) {
     void *ptrs[] = {c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
-                    c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
+                    c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
                     c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale, c->d_pv, c->d_pr, c->d_pp,
                     c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -654,6 +656,7 @@ int mz_replay_clear(mz_ctx *c) {
     for (int i = 0; i < 8; i++) c->h_counters[i] = 0;
     MZ_TRY(write_counters(c));
     MZ_CUDA(c, cudaMemsetAsync(c->ring.T, 0, (size_t)c->ring.capacity * sizeof(int32_t), c->stream));
+    MZ_CUDA(c, cudaMemsetAsync(c->ring.reanalysed, 0, (size_t)c->ring.capacity, c->stream));
     return MZ_OK;
 }
 
@@ -709,6 +712,42 @@ int mz_history_import(mz_ctx *c, int n, const int64_t *game_id, const int32_t *T
     { launch_scope ls(c, 2); mz_k_history_import<<<(unsigned)((N * Tm + 127) / 128), 128, 0, c->stream>>>(P, c->ring, key0, n, d_gid, d_T, d_obs, d_act, d_rew, d_tp, d_cv, d_rv); }
     MZ_CUDA(c, cudaGetLastError());
     return write_counters(c);
+}
+
+// ---- reanalyse (GameHistory.reanalysed_predicted_root_values, consumed by compute_target_value, ReplayBuffer.jl:8) ----
+int mz_reanalyse(mz_ctx *c, int64_t key0, int n) {
+    MZ_CHECK_CTX(c);
+    if (c->cfg.net_type != MZ_NET_FEEDFORWARD) return fail(c, MZ_E_UNSUPPORTED, "reanalyse runs the exact feed-forward networks");
+    if (n < 0) return fail(c, MZ_E_ARG, "n < 0");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    int64_t played = c->h_counters[0], have = played < c->ring.capacity ? played : c->ring.capacity, first = played - have + 1;
+    if (key0 < first || key0 + n - 1 > played) return fail(c, MZ_E_ARG, "keys %lld..%lld not in the buffer (holds %lld..%lld)", (long long)key0, (long long)(key0 + n - 1), (long long)first, (long long)played);
+    const mz_params &P = c->M.P;
+    mz_reanalyse_args a{}; a.wglob = c->d_w; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.n = n; a.key0 = key0; a.ring = c->ring;
+    const int64_t total = (int64_t)n * P.Tmax;
+    { launch_scope ls(c, 5); mz_k_reanalyse<<<(unsigned)((total + MZ_ROWS - 1) / MZ_ROWS), MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
+int mz_reanalysed_export(mz_ctx *c, int64_t key0, int n, float *values, int32_t *flags) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!values || !flags))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(read_counters(c));
+    int64_t played = c->h_counters[0], have = played < c->ring.capacity ? played : c->ring.capacity, first = played - have + 1;
+    if (key0 < first || key0 + n - 1 > played) return fail(c, MZ_E_ARG, "keys not in the buffer");
+    const size_t Tm = (size_t)c->M.P.Tmax;
+    std::vector<uint8_t> fl((size_t)c->ring.capacity);
+    MZ_CUDA(c, cudaMemcpyAsync(fl.data(), c->ring.reanalysed, fl.size(), cudaMemcpyDeviceToHost, c->stream));
+    for (int j = 0; j < n; j++) {
+        const int64_t pos = (key0 + j - 1) % c->ring.capacity;
+        MZ_CUDA(c, cudaMemcpyAsync(values + (size_t)j * Tm, c->ring.h_rrv + (size_t)pos * Tm, Tm * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < n; j++) flags[j] = fl[(size_t)((key0 + j - 1) % c->ring.capacity)];
+    return MZ_OK;
 }
 
 // ---- replay sampling / learner -----------------------------------------------------------------------------

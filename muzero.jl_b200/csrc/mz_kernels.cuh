@@ -44,6 +44,7 @@ struct mz_ring {           // device replay buffer: key k lives at (k-1) % capac
     int64_t capacity;
     int64_t *game_id; int32_t *T;
     uint64_t *h_p1, *h_p2; int32_t *h_action; float *h_reward; uint8_t *h_to_play; float *h_cv; float *h_rv;
+    float *h_rrv; uint8_t *reanalysed;   // GameHistory.reanalysed_predicted_root_values (Constructors.jl:13): [R][Tmax] + "is not nothing" flag per game
     // counters (device): [0] num_played_games, [1] num_played_steps, [2] total_samples, [3] next game id to hand out,
     // [4] end game id (exclusive), [5] active slots after the last refill
     int64_t *counters;
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
             int64_t pos = (key - 1) % r.capacity;
             int T = s.T[g];
             if (key > r.capacity) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)(-(long long)r.T[pos]));   // evicted history (:156-160)
-            r.game_id[pos] = s.game_id[g]; r.T[pos] = T;
+            r.game_id[pos] = s.game_id[g]; r.T[pos] = T; r.reanalysed[pos] = 0;
             for (int i = 0; i < P.Tmax; i++) {
                 size_t so = (size_t)g * P.Tmax + i, ro = (size_t)pos * P.Tmax + i;
                 r.h_p1[ro] = s.h_p1[so]; r.h_p2[ro] = s.h_p2[so]; r.h_action[ro] = s.h_action[so]; r.h_reward[ro] = s.h_reward[so];
@@ -438,6 +439,45 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_const
             for (int k = 0; k < P.hidden; k++) a.out1[g * P.hidden + k] = sp.outH[k * MZ_ROWS + tid];
             if (a.net == 2) a.out2[g] = sp.outR[tid];
         }
+    }
+}
+
+// ---- reanalyse: fills GameHistory.reanalysed_predicted_root_values (Constructors.jl:13) -------------------------------
+// The reference consumes the field (compute_target_value, ReplayBuffer.jl:8) but nothing produces it (main.jl:18 only keeps a
+// counter).  Producer, as in MuZero Reanalyze: for every stored position of games key0 .. key0+n-1 the value head of the CURRENT
+// networks on the stacked observation, prediction(representation(get_stacked_observations(history, i))).  32 positions per CTA.
+struct mz_reanalyse_args { const float *wglob; int32_t max_dim, max_layer_floats, n; int64_t key0; mz_ring ring; };
+__global__ void __launch_bounds__(MZ_THREADS) mz_k_reanalyse(const __grid_constant__ mz_params P, const mz_reanalyse_args a) {
+    extern __shared__ __align__(128) unsigned char mz_smem[];
+    const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
+    const int tid = threadIdx.x;
+    mz_nn_pipe pipe;
+    mz_pipe_init(pipe, sp, a.wglob);
+    mz_zero_activations(sp, a.max_dim);
+    __syncthreads();
+    if (tid == 0) mz_nn_issue(pipe, P, P.nets[0].first, 0);
+    const int64_t total = (int64_t)a.n * P.Tmax;
+    for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_THREADS) {
+        const int k = i / MZ_ROWS, rr = i % MZ_ROWS;
+        const int64_t item = (int64_t)blockIdx.x * MZ_ROWS + rr;
+        float v = 0.0f;
+        if (item < total) {
+            const int64_t pos = (a.key0 + item / P.Tmax - 1) % a.ring.capacity; const int t = (int)(item % P.Tmax);
+            if (t < a.ring.T[pos]) v = mz_stacked_value(P, a.ring.h_p1 + pos * P.Tmax, a.ring.h_p2 + pos * P.Tmax, a.ring.h_action + pos * P.Tmax, t + 1, k);
+        }
+        sp.in0[k * MZ_ROWS + rr] = v;
+    }
+    __syncthreads();
+    if (pipe.grp == 0) {
+        mz_nn_net(pipe, P, 0, P.nets[1].first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net(pipe, P, 1, -1, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+    }
+    __syncthreads();
+    const int64_t item = (int64_t)blockIdx.x * MZ_ROWS + tid;
+    if (tid < MZ_ROWS && item < total) {
+        const int64_t pos = (a.key0 + item / P.Tmax - 1) % a.ring.capacity; const int t = (int)(item % P.Tmax);
+        a.ring.h_rrv[pos * P.Tmax + t] = t < a.ring.T[pos] ? sp.outV[tid] : 0.0f;
+        if (t == 0) a.ring.reanalysed[pos] = 1;
     }
 }
 
@@ -513,5 +553,5 @@ __global__ void mz_k_history_import(const __grid_constant__ mz_params P, mz_ring
     r.h_p1[ro] = b1; r.h_p2[ro] = b2; r.h_action[ro] = actions[oo]; r.h_reward[ro] = rewards[oo]; r.h_to_play[ro] = (uint8_t)to_play[oo];
     r.h_rv[ro] = rv[oo];
     for (int a = 0; a < P.A; a++) r.h_cv[ro * P.A + a] = cv[oo * P.A + a];
-    if (t == 0) { r.game_id[pos] = game_id[j]; r.T[pos] = T[j]; }
+    if (t == 0) { r.game_id[pos] = game_id[j]; r.T[pos] = T[j]; r.reanalysed[pos] = 0; }
 }

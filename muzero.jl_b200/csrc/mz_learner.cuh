@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(64) mz_k_replay_gather(const __grid_constant__
         s_pos = pos; s_T = T; s_ring = ring;
         out.index[2 * b] = (int32_t)key; out.index[2 * b + 1] = pos;
         const float *rew = r.h_reward + (size_t)ring * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)ring * P.Tmax;
-        const float *rv = r.h_rv + (size_t)ring * P.Tmax; const int32_t *act = r.h_action + (size_t)ring * P.Tmax;
+        const float *rv = (r.reanalysed[ring] ? r.h_rrv : r.h_rv) + (size_t)ring * P.Tmax;   // ReplayBuffer.jl:8
+        const int32_t *act = r.h_action + (size_t)ring * P.Tmax;
         for (int k = 0; k < K1; k++) {
             int ci = pos + k; float tv, tr; int a;
             if (ci < T) { tv = mz_target_value(P, T, rew, tp, rv, ci); tr = rew[ci - 1]; a = act[ci - 1]; }

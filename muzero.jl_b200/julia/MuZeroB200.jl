@@ -158,6 +158,9 @@ function get_batch(e::Engine; step=e.training_step + 1)
 end
 
 # ---- learning! (src/Learning.jl:306-438) ------------------------------------------------------------------------
+"Fill `reanalysed_predicted_root_values` (Constructors.jl:13) of games `key0 .. key0+n-1` from the current networks; `get_batch` then bootstraps from them (ReplayBuffer.jl:8)."
+reanalyse!(e::Engine, key0::Integer, n::Integer) = check(e, ccall((:mz_reanalyse, LIB), Cint, (Ptr{Cvoid}, Int64, Cint), e.ctx, key0, n))
+
 "`steps` iterations of get_batch -> unroll -> loss -> gradients -> ADAM(Cos schedule); returns the last three losses."
 function learning!(e::Engine, steps::Integer; grad_mode::Integer=0)
     losses = zeros(Float32, 3)

@@ -424,3 +424,41 @@ def test_bptt_training_reduces_the_loss(capi):
     after = objective()
     assert np.isfinite(after) and after < 0.5 * before, (before, after)
     ctx.close()
+
+
+def test_reanalyse_bit_exact_and_used_by_targets(capi):
+    """reanalysed_predicted_root_values (Constructors.jl:13): produced on the device for a range of games, bit-exact vs
+    prediction(representation(stacked observation)) of the oracle, and consumed by compute_target_value (ReplayBuffer.jl:8)."""
+    ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=128, batch_size=64)
+    ctx.init_weights(31); blob = ctx.get_weights()
+    ctx.self_play(0, 96, 1.0)
+    h = ctx.history_export()
+    n = len(h["T"])
+    v0, f0 = ctx.reanalysed_export()
+    assert not f0.any()
+    b_before = ctx.get_batch(5)
+    ctx.reanalyse(key0=17, n=40)                                # a sub-range: keys 17..56
+    vals, flags = ctx.reanalysed_export()
+    assert flags.sum() == 40 and flags[16:56].all()
+    L = O.lib()
+    s = O.sizes(ocfg)
+    hist2 = {k: v.copy() for k, v in h.items()}
+    for j in range(16, 56):
+        T = h["T"][j]
+        for t in range(T):
+            st = np.zeros(s["stack"], np.float32)
+            L.mzo_stack_observations(C.byref(ocfg), O._p(np.ascontiguousarray(h["obs"][j])), O._p(np.ascontiguousarray(h["actions"][j]), C.c_int32), t + 1, O._p(st))
+            v, _ = O.prediction(ocfg, blob, O.representation(ocfg, blob, st))
+            assert vals[j, t] == v, (j, t)
+            hist2["root_values"][j, t] = v
+        assert not vals[j, T:].any()
+    b_after = ctx.get_batch(5)
+    ob = O.get_batch(ocfg, hist2, step=5)
+    for k in common.BATCH_KEYS:
+        assert np.array_equal(b_after[k], ob[k]), k
+    assert not np.array_equal(b_after["values"], b_before["values"])     # the bootstrap values changed for the reanalysed games
+    # a newly saved game clears the flag of the ring slot it takes
+    ctx.self_play(96, 64, 1.0)
+    _, f2 = ctx.reanalysed_export()
+    assert f2.sum() < 40
+    ctx.close()
