@@ -42,7 +42,7 @@ def harness():
     from muzero_jl_b200 import capi
     src = os.path.join(ROOT, "tests", "host_harness.cpp")
     so = os.path.join(ROOT, "tests", "libhost_harness.so")
-    deps = [src] + [os.path.join(ROOT, "muzero.jl_b200", "csrc", f) for f in ("mz_common.h", "mz_host.h")]
+    deps = [src] + [os.path.join(ROOT, "muzero.jl_b200", "csrc", f) for f in ("mz_common.h", "mz_host.h", "mz_rn_host.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         flags = ["-mavx2", "-mfma"] if (O._cpu_has("avx2") and O._cpu_has("fma")) else []
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-math-errno", "-fPIC", "-shared"] + flags + ["-o", so, src, "-lm"])
@@ -56,6 +56,9 @@ def harness():
     L.hh_self_play.argtypes = [cfgp, f32p, C.c_uint64, C.c_int, C.c_float, i32p, f32p, i32p, f32p, i32p, f32p, f32p]
     L.hh_self_play.restype = C.c_int64
     L.hh_get_batch.argtypes = [cfgp, C.c_int, C.c_int64, i32p, f32p, i32p, f32p, i32p, f32p, f32p, C.c_uint64, i32p] + [f32p] * 6
+    L.hh_rn_num_params.argtypes = [cfgp]
+    L.hh_rn_program_info.argtypes = [cfgp, i32p]
+    L.hh_rn_forward.argtypes = [cfgp, f32p, C.c_int, C.c_int, f32p, f32p, f32p]
     _hh = L
     return L
 

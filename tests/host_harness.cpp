@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <vector>
 #include "../muzero.jl_b200/csrc/mz_host.h"
+#include "../muzero.jl_b200/csrc/mz_rn_host.h"
 
 namespace {
 struct net_runner {
@@ -181,6 +182,143 @@ int hh_get_batch(const mz_config *c, int n_games, int64_t first_key, const int32
         int gs = Tg + 1 - pos; if (P.K < gs) gs = P.K;
         gscale[b] = (float)gs;
         for (int k = 0; k < P.stack_size; k++) obs_batch[(size_t)b * P.stack_size + k] = mz_stacked_value(P, h1.data(), h2.data(), act, pos, k);
+    }
+    return 0;
+}
+
+
+}  // extern "C"
+
+// ---- ResNet step program replayed on the CPU ------------------------------------------------------------------------
+// A scalar interpreter of the host-built program (mzh::rn_build) and weight image (mzh::rn_pack): exactly the data flow of
+// mz_k_search_rn / mz_k_rn_forward -- bf16 activation tiles [128 rows][64 channels], B images read back through the swizzle,
+// fp32 accumulation, folded affine epilogue, residual, head scatter, dense heads -- so that the program builder and the packer
+// are validated against the oracle without a GPU.  net: 0 representation(stacked), 1 prediction(hidden), 2 dynamics(sa).
+namespace {
+inline float bf16f(float v) { uint16_t h = mzh::f2bf16(v); uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+inline float img_bf16(const unsigned char *img, int row, int k) { uint16_t h; memcpy(&h, img + mzh::tc_tile_offset(row, k), 2); uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+struct rn_cpu {
+    const mzh::rn_model &M; const mz_params &P; const std::vector<unsigned char> &image;
+    std::vector<float> tile[8];               // X0..3, T0..3: [128][64]
+    std::vector<float> hv, hp;                // head tiles [64 trees][64], [64][128]
+    std::vector<float> out, plane; std::vector<float> pool;   // out: V[4][64] | L[16][64] | R[4][64]; pool: [ntrees][cells][64]
+    std::vector<double> acc[4];
+    rn_cpu(const mzh::rn_model &M_, const mz_params &P_, const std::vector<unsigned char> &img) : M(M_), P(P_), image(img) {
+        for (auto &t : tile) t.assign(128 * 64, 0.0f);
+        hv.assign(64 * 64, 0.0f); hp.assign(64 * 128, 0.0f); out.assign(24 * 64, 0.0f); plane.assign(64, 0.0f);
+        pool.assign((size_t)64 * M.R.cells * 64, 0.0f);
+        for (auto &a : acc) a.assign(128 * 64, 0.0);
+    }
+    float *buf(int id, int kb, int row) { if (id < 8) return &tile[id][(size_t)row * 64]; if (id == MZ_RN_BUF_HV) return &hv[(size_t)row * 64]; return &hp[(size_t)row * 128 + 64 * kb]; }
+    void run(int first, int last, int ntrees) {
+        const mz_rn_params &R = M.R;
+        for (int si = first; si < last; si++) {
+            const mz_rn_step &st = M.steps[(size_t)si];
+            const unsigned char *blk = image.data() + st.w_off;
+            for (int j = 0; j < st.njobs; j++) {
+                const mz_rn_job &J = st.jobs[j];
+                const int N = 16 * J.n16;
+                const bool trees = (J.flags & MZ_RN_F_TREES) != 0;
+                std::vector<double> &A = acc[J.acc];
+                if (!st.accumulate) std::fill(A.begin(), A.end(), 0.0);
+                for (int row = 0; row < 128; row++) {
+                    if (trees ? row >= 64 : row >= R.rows_valid) continue;
+                    for (int kb = 0; kb < J.kblocks; kb++) {
+                        const float *a;
+                        std::vector<float> shifted(64, 0.0f);
+                        if (st.ntaps > 1) {   // tap-step: source row shifted by (dx, dy) cells
+                            const int t = row / R.cells, cell = row % R.cells, x = cell % P.W + st.dx, y = cell / P.W + st.dy;
+                            if (x >= 0 && x < P.W && y >= 0 && y < P.H) { const float *src = buf(J.a_buf, 0, t * R.cells + x + P.W * y); for (int k = 0; k < 64; k++) shifted[(size_t)k] = src[k]; }
+                            a = shifted.data();
+                        } else a = buf(J.a_buf, kb, row);
+                        const unsigned char *img = blk + J.w_sub + kb * (J.n16 * 2048);
+                        for (int n = 0; n < N; n++) { double s = 0.0; for (int k = 0; k < 64; k++) s += (double)a[k] * (double)img_bf16(img, n, k); A[(size_t)row * 64 + n] += s; }
+                    }
+                }
+                if (!st.last) continue;
+                const float *S = reinterpret_cast<const float *>(blk + J.p_sub), *T = S + 64, *E = S + 128;
+                for (int row = 0; row < 128; row++) {
+                    int tree, cell;
+                    if (trees) { tree = row; cell = 0; if (row >= 64) continue; } else { if (row >= R.rows_valid) continue; tree = J.acc * R.tpt + row / R.cells; cell = row % R.cells; }
+                    const bool valid = tree < ntrees;
+                    if (J.epi == MZ_RN_EPI_TILE) {
+                        float *dst = buf(J.dst_buf, 0, row); const float *skp = J.skip_buf != 0xff ? buf(J.skip_buf, 0, row) : nullptr;
+                        float y[64];
+                        for (int c = 0; c < 64; c++) {
+                            float v = fmaf((float)A[(size_t)row * 64 + c], S[c], (J.flags & MZ_RN_F_PLANE) ? fmaf(plane[(size_t)tree], E[c], T[c]) : T[c]);
+                            if (skp) v = v + skp[c];
+                            if (J.act == MZ_ACT_RELU) v = v > 0.0f ? v : 0.0f;
+                            y[c] = valid ? bf16f(v) : 0.0f;
+                        }
+                        for (int c = 0; c < 64; c++) dst[c] = y[c];
+                        if ((J.flags & MZ_RN_F_POOL) && valid) for (int c = 0; c < 64; c++) pool[((size_t)tree * R.cells + cell) * 64 + c] = y[c];
+                    } else if (J.epi == MZ_RN_EPI_HEAD) {
+                        if (!valid) continue;
+                        for (int f = 0; f < J.nfa + J.nfb; f++) {
+                            float v = fmaf((float)A[(size_t)row * 64 + f], S[f], T[f]); v = v > 0.0f ? v : 0.0f;
+                            const bool second = f >= J.nfa; const int k = cell + R.cells * (second ? f - J.nfa : f);
+                            buf(second ? J.dst2_buf : J.dst_buf, k >> 6, tree)[k & 63] = bf16f(v);
+                        }
+                    } else {
+                        if (row >= R.ntrees) continue;
+                        const int base = J.out_id == MZ_RN_OUT_V ? 0 : J.out_id == MZ_RN_OUT_L ? 4 * 64 : 20 * 64;
+                        for (int k = 0; k < J.out; k++) { float v = (float)A[(size_t)row * 64 + k] + T[k]; out[(size_t)base + k * 64 + row] = mz_activate(v, J.act); }
+                    }
+                }
+            }
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+int hh_rn_num_params(const mz_config *c) { mzh::rn_model M; mzh::rn_units_build(*c, M); return mzh::rn_total_params(M); }
+int hh_rn_program_info(const mz_config *c, int32_t *out /* [8]: n_steps, repr steps, pred steps, dyn steps, image bytes, slot bytes, ntrees, tree stride */) {
+    mzh::model Mm; if (const char *e = mzh::build_model(*c, Mm)) { fprintf(stderr, "%s\n", e); return -1; }
+    mzh::rn_model M; if (const char *e = mzh::rn_build(*c, Mm.P, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    const mz_rn_params &R = M.R;
+    out[0] = R.n_steps; out[1] = R.prog_repr[1] - R.prog_repr[0]; out[2] = R.prog_pred[1] - R.prog_pred[0]; out[3] = R.prog_dyn[1] - R.prog_dyn[0];
+    out[4] = R.image_bytes; out[5] = R.slot_bytes; out[6] = R.ntrees; out[7] = R.tree_stride_bytes;
+    for (const auto &s : M.steps) if (s.w_bytes > R.slot_bytes || s.w_off + s.w_bytes > R.image_bytes || s.njobs < 1 || s.njobs > MZ_RN_TILES) return -2;
+    return 0;
+}
+// n <= ntrees inputs through one network; out1 / out2 like the C ABI callables (hidden in Julia (W,H,nf) order)
+int hh_rn_forward(const mz_config *c, const float *blob, int net, int n, const float *in, float *out1, float *out2) {
+    mzh::model Mm; if (const char *e = mzh::build_model(*c, Mm)) { fprintf(stderr, "%s\n", e); return -1; }
+    mzh::rn_model M; if (const char *e = mzh::rn_build(*c, Mm.P, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    const mz_params &P = Mm.P; const mz_rn_params &R = M.R;
+    if (n > R.ntrees) return -3;
+    std::vector<unsigned char> image; mzh::rn_pack(M, blob, image);
+    rn_cpu X(M, P, image);
+    if (net == 0) {   // im2col tiles of the first convolution
+        const int k = R.ksize, pad = k / 2;
+        for (int t = 0; t < n; t++) for (int cell = 0; cell < R.cells; cell++) for (int tap = 0; tap < k * k; tap++) for (int pl = 0; pl < R.planes; pl++) {
+            const int x = cell % P.W + pad - (tap % k), y = cell / P.W + pad - (tap / k);
+            float v = 0.0f;
+            if (x >= 0 && x < P.W && y >= 0 && y < P.H) v = in[(size_t)t * P.stack_size + (x + P.W * y) + P.cells * pl];
+            X.tile[t / R.tpt][(size_t)((t % R.tpt) * R.cells + cell) * 64 + tap * R.planes + pl] = bf16f(v);
+        }
+        X.run(R.prog_repr[0], R.prog_repr[1], n);
+    } else {
+        const int in_dim = net == 2 ? P.sa_size : P.hidden; const float mul = net == 2 ? 0.5f : 1.0f;
+        for (int t = 0; t < n; t++) {
+            for (int cell = 0; cell < R.cells; cell++) for (int ch = 0; ch < R.nf; ch++)
+                X.tile[t / R.tpt][(size_t)((t % R.tpt) * R.cells + cell) * 64 + ch] = bf16f(in[(size_t)t * in_dim + cell + P.cells * ch] * mul);
+            if (net == 2) X.plane[(size_t)t] = in[(size_t)t * in_dim + P.hidden];
+        }
+        if (net == 1) X.run(R.prog_pred[0], R.prog_pred[1], n); else X.run(R.prog_dyn[0], R.prog_dyn[1], n);
+    }
+    if (net != 1) {
+        for (int t = 0; t < n; t++) for (int k = 0; k < P.hidden; k++) out1[(size_t)t * P.hidden + k] = X.pool[((size_t)t * R.cells + k % P.cells) * 64 + k / P.cells];
+        if (net == 2) for (int t = 0; t < n; t++) out2[t] = X.out[20 * 64 + t];
+    } else {
+        for (int t = 0; t < n; t++) {
+            float logits[MZ_MAX_A], policy[MZ_MAX_A];
+            for (int i = 0; i < P.A; i++) logits[i] = X.out[4 * 64 + i * 64 + t];
+            mz_softmax(logits, P.A, policy);
+            out1[t] = X.out[t];
+            for (int i = 0; i < P.A; i++) out2[(size_t)t * P.A + i] = policy[i];
+        }
     }
     return 0;
 }

@@ -97,3 +97,41 @@ def test_get_batch_bit_exact(hh):
         got = dict(index=idx, obs=obs, actions=act, values=val, rewards=rew, policies=pol, gscale=gs)
         for k in common.BATCH_KEYS:
             assert np.array_equal(got[k], ob[k]), k
+
+
+# ---- ResNet: the host-built step program + weight image, replayed by a scalar interpreter, vs the bf16-emulating oracle ----
+@pytest.mark.parametrize("kw", [dict(), dict(rn_kernel=1, rn_num_blocks=1, rn_num_filters=32), dict(game=1, W=6, H=7, A=7, max_moves=42, rn_num_blocks=1)])
+def test_resnet_program_replay_matches_bf16_oracle(hh, kw):
+    from muzero_jl_b200 import capi
+    from test_oracle_resnet import _randomised_blob
+    cfg = capi.resnet_config(**kw)
+    if kw.get("game") == 1:
+        cfg = capi.connect_config(**{k: v for k, v in kw.items() if k not in ("game", "W", "H", "A", "max_moves")})
+    ocfg = common.oracle_config(cfg)
+    info = np.zeros(8, np.int32)
+    assert hh.hh_rn_program_info(C.byref(cfg), _p(info, C.c_int32)) == 0
+    assert info[0] == info[1] + info[2] + info[3] and info[6] == 4 * (128 // (cfg.W * cfg.H)) and info[5] >= 8192 + 768
+    assert hh.hh_rn_num_params(C.byref(cfg)) == O.num_params(ocfg)
+    blob = _randomised_blob(ocfg, 17)
+    s = O.sizes(ocfg); n = 5
+    rng = np.random.default_rng(3)
+    st = rng.integers(0, 2, (n, s["stack"])).astype(np.float32)
+    O.set_bf16(True)
+    try:
+        oh = np.stack([O.representation(ocfg, blob, x) for x in st])
+        ov, op = zip(*[O.prediction(ocfg, blob, x) for x in oh])
+        sa = np.concatenate([2 * oh, np.repeat(((np.arange(n) % cfg.A + 1) / np.float32(cfg.A)).astype(np.float32)[:, None], cfg.W * cfg.H, 1)], 1).astype(np.float32)
+        onh, orr = zip(*[O.dynamics(ocfg, blob, x) for x in sa])
+    finally:
+        O.set_bf16(False)
+    h = np.zeros((n, s["hidden"]), np.float32); dummy = np.zeros(n, np.float32)
+    assert hh.hh_rn_forward(C.byref(cfg), _p(blob), 0, n, _p(st), _p(h), _p(dummy)) == 0
+    scale = max(1.0, float(np.max(np.abs(oh))))
+    assert np.max(np.abs(h - oh)) < 2e-2 * scale and np.median(np.abs(h - oh)) < 1e-3
+    v = np.zeros(n, np.float32); p = np.zeros((n, cfg.A), np.float32)
+    assert hh.hh_rn_forward(C.byref(cfg), _p(blob), 1, n, _p(np.ascontiguousarray(oh)), _p(v), _p(p)) == 0
+    assert np.max(np.abs(v - np.array(ov))) < 2e-2 and np.max(np.abs(p - np.stack(op))) < 2e-2
+    nh = np.zeros((n, s["hidden"]), np.float32); r = np.zeros(n, np.float32)
+    assert hh.hh_rn_forward(C.byref(cfg), _p(blob), 2, n, _p(sa), _p(nh), _p(r)) == 0
+    onh = np.stack(onh)
+    assert np.max(np.abs(nh - onh)) < 2e-2 * max(1.0, float(np.max(np.abs(onh)))) and np.max(np.abs(r - np.array(orr))) < 2e-2
