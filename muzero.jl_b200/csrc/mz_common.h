@@ -350,9 +350,12 @@ struct mz_minmax { float mn, mx; };
 
 // ucb_score (src/SelfPlay.jl:171-184): Float64 exploration term from integer-only tables
 // (pbc0[N] = log2((N+base+1)/base) + init, sqrtN[N] = sqrt(N)), Float32 value term, Float32 result.
-MZ_HD float mz_ucb(const mz_params &P, const double *pbc0, const double *sqrtN, int N, mz_f4 child, mz_minmax mm) {
+// `pbc` is the host-built table pbc[N * (S + 2) + n] = pbc0[N] * (sqrtN[N] / (double)(n + 1)): the same IEEE double operations in
+// the same order, evaluated once on the host -- the device does no Float64 division (slow on this part) in the selection loop.
+MZ_HD float mz_ucb(const mz_params &P, const double *pbc, const double *unused_, int N, mz_f4 child, mz_minmax mm) {
+    (void)unused_;
     int n = mz_nx_visit(mz_f2bits(child.x));
-    double pb_c = pbc0[N] * (sqrtN[N] / (double)(n + 1));
+    double pb_c = pbc[N * (P.S + 2) + n];
     double prior_score = pb_c * (double)child.z;
     if (n > 0) {
         float nv = child.y / (float)n;                                    // node_value :76-82

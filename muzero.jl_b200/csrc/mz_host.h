@@ -126,10 +126,15 @@ inline const char *build_model(const mz_config &c, model &M) {
     P.nodeB_off_bytes = 0; P.hidden_off_bytes = a_bytes;
     P.tree_stride_bytes = (a_bytes + h_bytes + 127) & ~127;
     // ucb_score (SelfPlay.jl:172-174): pb_c = log2((N + base + 1) / base) + init, then * sqrt(N)/(n+1); all Float64
-    M.pbc0.resize((size_t)c.num_iters + 2); M.sqrtN.resize((size_t)c.num_iters + 2);
-    for (int N = 0; N <= c.num_iters + 1; N++) {
-        M.pbc0[(size_t)N] = log2((double)(N + c.pb_c_base + 1) / (double)c.pb_c_base) + (double)c.pb_c_init;
-        M.sqrtN[(size_t)N] = sqrt((double)N);
+    // evaluated for every (parent visits N, child visits n) pair on the host: pbc0[N * (S + 2) + n] = pbc0(N) * (sqrt(N) / (n + 1))
+    {
+        const size_t W = (size_t)c.num_iters + 2;
+        M.pbc0.resize(W * W); M.sqrtN.resize(W);
+        for (size_t N = 0; N < W; N++) {
+            const double p0 = log2((double)((int)N + c.pb_c_base + 1) / (double)c.pb_c_base) + (double)c.pb_c_init;
+            M.sqrtN[N] = sqrt((double)N);
+            for (size_t n = 0; n < W; n++) M.pbc0[N * W + n] = p0 * (M.sqrtN[N] / (double)(n + 1));
+        }
     }
     if (c.net_type == MZ_NET_RESNET) {   // the residual networks have their own description (mz_rn_host.h); the state is (W,H,nf)
         P.sa_size = P.hidden + P.cells; P.tc_ok = 0; M.max_dim = 4; M.max_layer_floats = 0;

@@ -189,7 +189,6 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
     mz_nn_pipe pipe;
     mz_pipe_init<GT>(pipe, sp, a.wglob);
     mz_zero_activations<NT>(sp, a.max_dim);
-    for (int i = tid; i <= P.S + 1; i += NT) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
     uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
@@ -264,7 +263,7 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
         mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
         MZ_TIMER(0);
         if (active) {
-            leaf = mz_tree_select_lanes(P, tree, sp.pbc0, sp.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
+            leaf = mz_tree_select_lanes(P, tree, a.pbc0, a.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
             depth_sum += (unsigned long long)leaf.depth;
             MZ_TIMER(1);
             const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);

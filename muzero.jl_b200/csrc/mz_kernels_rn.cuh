@@ -450,7 +450,6 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
     const mz_rn_plan &sp = X.sp;
     const int tid = threadIdx.x, ln = tid & (MZ_LANES - 1);
     const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
-    for (int i = tid; i <= P.S + 1; i += MZ_RN_THREADS) { sp.pbc0[i] = a.pbc0[i]; sp.sqrtN[i] = a.sqrtN[i]; }
 
     // ---- per-tree state: 64 trees x 8 lanes, replicated in the lanes of each tree ----
     bool active[MZ_RN_NPASS]; uint32_t legal[MZ_RN_NPASS], game[MZ_RN_NPASS], move[MZ_RN_NPASS], posmask[MZ_RN_NPASS]; mz_tree tree[MZ_RN_NPASS]; mz_minmax mm[MZ_RN_NPASS]; int ts[MZ_RN_NPASS]; int64_t gidx[MZ_RN_NPASS];
@@ -509,7 +508,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
                 leaf[p].node = 0; leaf[p].parent = 0; leaf[p].action = 1; leaf[p].depth = 0; leaf[p].prior = 0.0f; leaf[p].parent_x = 0;
                 if (active[p]) {
                     uint16_t *path = sp.path + (size_t)ts[p] * (P.S + 2);
-                    leaf[p] = mz_tree_select_lanes(P, tree[p], sp.pbc0, sp.sqrtN, legal[p], posmask[p], mm[p], game[p], move[p], (uint32_t)sim, ln, segmask, path);
+                    leaf[p] = mz_tree_select_lanes(P, tree[p], a.pbc0, a.sqrtN, legal[p], posmask[p], mm[p], game[p], move[p], (uint32_t)sim, ln, segmask, path);
                     depth_sum += (unsigned long long)leaf[p].depth;
                     if (ln == 0) {
                         sp.pe[ts[p]] = mz_nx_exp(leaf[p].parent_x); sp.dbl[ts[p]] = mz_nx_dbl(leaf[p].parent_x);
