@@ -381,6 +381,9 @@ def run_b200(a):
                              "kernel": "mz_k_search_rn<MODE_SLOTS>", "avg_launch_ms": rn_extra[2] / max(rn_extra[3], 1),
                              "roofline": {"bound": "tensor", "achieved": rn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": rn_tflops / bf16_peak,
                                           "flops_per_simulation": flops_per_sim,
+                                          "traffic": (lambda t: t["bytes"] * rn_extra[4] / 8288.0 if t else None)(profiled_traffic("mz_k_search_rn")),
+                                          "traffic_note": "DRAM bytes per launch from the committed ncu capture (8288 games), scaled to this launch's games: bf16 hidden states written once "
+                                                          "per simulation (1152 B) and mostly re-read from L2",
                                           "note": "useful FLOPs only; K = 64 per layer, so every output element is read from TMEM (64 B/clk/SM) for 64 MACs: the "
                                                   "epilogue's TMEM reads bound the tensor pipe at ~25 % busy; see DESIGN.md"}}
         if learner:
