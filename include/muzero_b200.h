@@ -166,6 +166,10 @@ int mz_learn_step_batch(mz_ctx *ctx, int64_t t, int grad_mode, int B, const floa
                         const float *value_batch, const float *reward_batch, const float *policy_batch,
                         const float *gscale, float *losses);
 int mz_optimizer_reset(mz_ctx *ctx);
+/* checkpoint / resume (Learning.jl:416-435 serialises the networks only; resuming ADAM needs its moments): m, v in the blob order,
+ * steps_done = number of updates applied so far (the next step must be called with t = steps_done + 1) */
+int mz_get_optimizer_state(mz_ctx *ctx, float *m, float *v, int64_t n, int64_t *steps_done);
+int mz_set_optimizer_state(mz_ctx *ctx, const float *m, const float *v, int64_t n, int64_t steps_done);
 
 /* ---- multi-GPU: data-parallel learner, one process per GPU (no reference counterpart; the reference's
  * only transport is Julia Distributed, games/tictactoe/main.jl:1-2,15-21) ------------------------- */

@@ -276,6 +276,21 @@ def get_batch(engine: Engine, step=None):
     return index_batch, (b["obs"], b["actions"], b["values"], b["rewards"], b["policies"], None, b["gscale"])
 
 
+def save_checkpoint(engine: Engine, path: str):
+    """Learning.jl:426-434 serialises the three networks in the last 10 % of training; this also keeps ADAM's moments, the step
+    counter and the replay buffer so that a run can be resumed bit-identically (numpy .npz, documented flat arrays)."""
+    ck = engine.ctx.checkpoint()
+    ck["training_step"] = np.int64(engine.training_step)
+    np.savez(path, **ck)
+
+
+def load_checkpoint(engine: Engine, path: str):
+    with np.load(path) as z:
+        ck = {k: z[k] for k in z.files}
+    engine.ctx.restore(ck)
+    engine.training_step = int(ck.get("training_step", ck["steps_done"]))
+
+
 def reanalyse(engine: Engine, key0=None, n=None):
     """Producer of `GameHistory.reanalysed_predicted_root_values` (Constructors.jl:13; consumed by compute_target_value,
     ReplayBuffer.jl:8; the reference has no producer): the current networks' root value at every stored position."""

@@ -111,6 +111,8 @@ def lib():
         "mz_learn_step_batch": ([ctx, C.c_int64, C.c_int, C.c_int] + [f32p] * 7, C.c_int),
         "mz_learn_gradients": ([ctx, C.c_int, C.c_int] + [f32p] * 8, C.c_int),
         "mz_optimizer_reset": ([ctx], C.c_int),
+        "mz_get_optimizer_state": ([ctx, f32p, f32p, C.c_int64, C.POINTER(C.c_int64)], C.c_int),
+        "mz_set_optimizer_state": ([ctx, f32p, f32p, C.c_int64, C.c_int64], C.c_int),
         "mz_comm_unique_id": ([u8p], C.c_int),
         "mz_comm_init": ([ctx, C.c_int, C.c_int, u8p], C.c_int),
         "mz_comm_destroy": ([ctx], C.c_int),
@@ -400,6 +402,24 @@ class Context:
         losses = np.zeros(3, np.float32)
         self._ck(self.L.mz_learn_steps(self._h, t0, n, grad_mode, _p(losses, C.c_float)))
         return losses
+
+    def checkpoint(self):
+        """Everything needed to resume: weights, ADAM moments + step count, and the replay buffer's histories."""
+        n = self.num_params()
+        m = np.zeros(n, np.float32); v = np.zeros(n, np.float32); t = C.c_int64(0)
+        self._ck(self.L.mz_get_optimizer_state(self._h, _p(m, C.c_float), _p(v, C.c_float), n, C.byref(t)))
+        ck = dict(weights=self.get_weights(), adam_m=m, adam_v=v, steps_done=np.int64(t.value))
+        if self.replay_info()["n_games"] > 0:
+            ck.update({"hist_" + k: a for k, a in self.history_export().items()})
+        return ck
+
+    def restore(self, ck):
+        self.set_weights(np.ascontiguousarray(ck["weights"], np.float32))
+        m = np.ascontiguousarray(ck["adam_m"], np.float32); v = np.ascontiguousarray(ck["adam_v"], np.float32)
+        self._ck(self.L.mz_set_optimizer_state(self._h, _p(m, C.c_float), _p(v, C.c_float), m.size, int(ck["steps_done"])))
+        if "hist_T" in ck:
+            self.replay_clear()
+            self.history_import({k[5:]: ck[k] for k in ck if k.startswith("hist_")})
 
     def optimizer_reset(self):
         self._ck(self.L.mz_optimizer_reset(self._h))

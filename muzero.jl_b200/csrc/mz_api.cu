@@ -845,6 +845,36 @@ int mz_learn_steps(mz_ctx *c, int64_t t0, int n, int grad_mode, float *losses) {
     }
     return finish_losses(c, B, losses);
 }
+// ---- checkpoint / resume of the optimiser (weights: mz_get_weights / mz_set_weights; histories: mz_history_export / import) ----
+// Flux.ADAM keeps (mt, vt, beta powers) per parameter array (Learning.jl:318, 395-397); m and v cross the ABI in the blob order.
+int mz_get_optimizer_state(mz_ctx *c, float *m, float *v, int64_t n, int64_t *steps_done) {
+    MZ_CHECK_CTX(c);
+    if (c->cfg.net_type != MZ_NET_FEEDFORWARD) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only");
+    if (!m || !v || !steps_done || n != c->M.P.n_params) return fail(c, MZ_E_ARG, "bad arguments (need %d floats per moment)", c->M.P.n_params);
+    std::vector<float> dev((size_t)c->M.P.total_floats);
+    for (int which = 0; which < 2; which++) {
+        MZ_CUDA(c, cudaMemcpyAsync(dev.data(), which ? c->d_v : c->d_m, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        mzh::unpack_weights(c->M.P, dev.data(), which ? v : m);
+    }
+    *steps_done = c->adam_t > 0 ? c->adam_t - 1 : 0;
+    return MZ_OK;
+}
+int mz_set_optimizer_state(mz_ctx *c, const float *m, const float *v, int64_t n, int64_t steps_done) {
+    MZ_CHECK_CTX(c);
+    if (c->cfg.net_type != MZ_NET_FEEDFORWARD) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only");
+    if (!m || !v || steps_done < 0 || n != c->M.P.n_params) return fail(c, MZ_E_ARG, "bad arguments (need %d floats per moment)", c->M.P.n_params);
+    std::vector<float> dev((size_t)c->M.P.total_floats);
+    for (int which = 0; which < 2; which++) {
+        mzh::pack_weights(c->M.P, which ? v : m, dev.data());
+        MZ_CUDA(c, cudaMemcpyAsync(which ? c->d_v : c->d_m, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    c->adam_t = steps_done + 1; c->bp1 = 0.9; c->bp2 = 0.999;           // beta^t by repeated product, as the running state builds it
+    for (int64_t i = 0; i < steps_done; i++) { c->bp1 *= 0.9; c->bp2 *= 0.999; }
+    if (steps_done == 0) c->adam_t = 0;
+    return MZ_OK;
+}
 int mz_optimizer_reset(mz_ctx *c) {
     MZ_CHECK_CTX(c);
     MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)c->M.P.total_floats * 4, c->stream));

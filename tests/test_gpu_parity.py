@@ -462,3 +462,24 @@ def test_reanalyse_bit_exact_and_used_by_targets(capi):
     _, f2 = ctx.reanalysed_export()
     assert f2.sum() < 40
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["l2", "bptt"])
+def test_checkpoint_resume_is_bit_identical(capi, mode, tmp_path):
+    """weights + ADAM moments + step count + replay histories: a restored context continues exactly like the original."""
+    gm = capi.GRAD_BPTT if mode == "bptt" else capi.GRAD_REFERENCE_L2
+    ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=128, batch_size=48)
+    ctx.init_weights(41); ctx.self_play(0, 96, 1.0)
+    ctx.learn_steps(1, 4, gm)
+    ck = ctx.checkpoint()
+    assert ck["steps_done"] == 4 and ck["adam_m"].any() and ck["adam_v"].any()
+    np.savez(tmp_path / "ck.npz", **ck)
+    la = ctx.learn_steps(5, 3, gm); wa = ctx.get_weights(); ctx.close()
+    ctx2, _ = make_ctx(capi, num_slots=64, replay_buffer_size=128, batch_size=48)
+    with np.load(tmp_path / "ck.npz") as z:
+        ctx2.restore({k: z[k] for k in z.files})
+    lb = ctx2.learn_steps(5, 3, gm); wb = ctx2.get_weights()
+    assert np.array_equal(wa, wb) and np.array_equal(la, lb)
+    ck2 = ctx2.checkpoint()
+    assert ck2["steps_done"] == 7
+    ctx2.close()
