@@ -6,7 +6,7 @@
 //   D[row = (tree, cell)][co] = sum_ci X[row][ci] * W[co][ci]         M = 128 rows per tile, N = 64, K = 64
 // One CTA owns 4 tiles (TicTacToe: 14 trees x 9 cells = 126 rows per tile, 56 trees per CTA; a 6x7 board: 3 trees per
 // tile).  Accumulators live in TMEM (lane = row, 64 fp32 columns per tile), so an epilogue thread owns one row: it reads
-// its 64 channels with tcgen05.ld, applies the folded BatchNorm affine (+ action-plane term, + residual), relu, and
+// its 64 channels with tcgen05.ld, applies the BatchNorm shift (its scale is folded into the bf16 weights; + action-plane term, + residual), relu, and
 // writes the bf16 row of the next layer's A tile with eight 16-byte swizzled stores (and, for the last layer of the
 // dynamics state head / the representation, the same row to the tree's hidden-state slot in HBM).  Weights stream
 // through a two-slot shared-memory ring by TMA bulk copies, one block per step, prefetched one step ahead.
@@ -174,17 +174,16 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int c8 = 4 * half + q;
-                const float4 s0 = mz_lds128(pS + c8 * 32), s1 = mz_lds128(pS + c8 * 32 + 16), t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
-                unsigned long long S[4] = {mz_f2pack(s0.x, s0.y), mz_f2pack(s0.z, s0.w), mz_f2pack(s1.x, s1.y), mz_f2pack(s1.z, s1.w)};
+                const float4 t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
                 unsigned long long T[4] = {mz_f2pack(t0.x, t0.y), mz_f2pack(t0.z, t0.w), mz_f2pack(t1.x, t1.y), mz_f2pack(t1.z, t1.w)};
-                if (plane) {   // + action plane * (w_plane * s): y = fmaf(acc, S, fmaf(plane, E, T))
+                if (plane) {   // + action plane * (w_plane * s): y = acc + fmaf(plane, E, T)   (the BatchNorm scale is folded into the weights)
                     const float4 e0 = mz_lds128(pE + c8 * 32), e1 = mz_lds128(pE + c8 * 32 + 16);
                     T[0] = mz_fma2(rv2, mz_f2pack(e0.x, e0.y), T[0]); T[1] = mz_fma2(rv2, mz_f2pack(e0.z, e0.w), T[1]);
                     T[2] = mz_fma2(rv2, mz_f2pack(e1.x, e1.y), T[2]); T[3] = mz_fma2(rv2, mz_f2pack(e1.z, e1.w), T[3]);
                 }
                 unsigned long long y[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) y[i] = mz_fma2(mz_f2pack(__uint_as_float(v[8 * q + 2 * i]), __uint_as_float(v[8 * q + 2 * i + 1])), S[i], T[i]);
+                for (int i = 0; i < 4; i++) y[i] = mz_add2(mz_f2pack(__uint_as_float(v[8 * q + 2 * i]), __uint_as_float(v[8 * q + 2 * i + 1])), T[i]);
                 const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) << 4);
                 if (skp) {
                     const uint4 k = mz_lds128u(skp + chunk);
@@ -208,7 +207,7 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
         if (valid) {
             const int nf = J.nfa + J.nfb;
             for (int f = 0; f < nf; f++) {
-                const float y = fmaxf(fmaf(__uint_as_float(v[f]), mz_lds32(pS + f * 4), mz_lds32(pT + f * 4)), 0.0f);
+                const float y = fmaxf(__uint_as_float(v[f]) + mz_lds32(pT + f * 4), 0.0f);
                 const bool second = f >= J.nfa;
                 const int k = cell + R.cells * (second ? f - J.nfa : f);
                 const uint32_t tile = mz_rn_buf(X.sp, second ? J.dst2_buf : J.dst_buf) + (uint32_t)(k >> 6) * 8192u;

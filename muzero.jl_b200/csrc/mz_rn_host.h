@@ -227,6 +227,8 @@ inline void rn_pack(const rn_model &M, const float *blob, std::vector<unsigned c
                 const rn_unit &u = rn_unit_of(M, pu);
                 const int kin = u.kind == 0 ? (w.plane ? u.cin - 1 : u.cin) : u.cin;
                 for (int o = 0; o < u.cout; o++) {
+                    // BatchNorm scale (and the x2 of the dynamics input) folded into the weight before the bf16 rounding
+                    const float fold = u.kind == 0 ? w.mul * (blob[u.gamma_off + o] / sqrtf(blob[u.var_off + o] + 1e-5f)) : 1.0f;
                     if (u.kind == 1) {
                         for (int k = 0; k < kin; k++) {
                             uint16_t h = f2bf16(blob[u.w_off + o + u.cout * k]);
@@ -234,10 +236,10 @@ inline void rn_pack(const rn_model &M, const float *blob, std::vector<unsigned c
                         }
                     } else if (w.tap >= 0) {
                         const int ka = w.tap % u.k, kb = w.tap / u.k;
-                        for (int ci = 0; ci < kin; ci++) { uint16_t h = f2bf16(blob[u.w_off + ka + u.k * (kb + u.k * (ci + u.cin * o))]); memcpy(base + tc_tile_offset(row0 + o, ci), &h, 2); }
+                        for (int ci = 0; ci < kin; ci++) { uint16_t h = f2bf16(blob[u.w_off + ka + u.k * (kb + u.k * (ci + u.cin * o))] * fold); memcpy(base + tc_tile_offset(row0 + o, ci), &h, 2); }
                     } else {   // all taps in one image: k index = tap * cin + ci (im2col); 1x1: tap = 0
                         for (int t = 0; t < u.k * u.k; t++) for (int ci = 0; ci < kin; ci++) {
-                            uint16_t h = f2bf16(blob[u.w_off + (t % u.k) + u.k * ((t / u.k) + u.k * (ci + u.cin * o))]);
+                            uint16_t h = f2bf16(blob[u.w_off + (t % u.k) + u.k * ((t / u.k) + u.k * (ci + u.cin * o))] * fold);
                             memcpy(base + tc_tile_offset(row0 + o, t * kin + ci), &h, 2);
                         }
                     }
@@ -253,7 +255,7 @@ inline void rn_pack(const rn_model &M, const float *blob, std::vector<unsigned c
                     const rn_unit &u = rn_unit_of(M, pu);
                     for (int o = 0; o < u.cout; o++) {
                         if (u.kind == 1) { S[c0 + o] = 1.0f; T[c0 + o] = blob[u.b_off + o]; E[c0 + o] = 0.0f; continue; }
-                        // BatchNorm (test mode) folded with the convolution bias: y = acc * (mul * s) + plane * (w_plane * s) + ((b - mu) * s + beta)
+                        // BatchNorm (test mode): the scale s = gamma / sqrt(var + eps) lives in the weights; y = acc + plane * (w_plane * s) + ((b - mu) * s + beta)
                         const float den = sqrtf(blob[u.var_off + o] + 1e-5f), s = blob[u.gamma_off + o] / den;
                         S[c0 + o] = w.mul * s;
                         T[c0 + o] = fmaf(blob[u.b_off + o] - blob[u.mu_off + o], s, blob[u.beta_off + o]);

@@ -319,7 +319,8 @@ static void softmax(const float *x, int n, float *y) {
  * mu = 0, var = 1 (Flux defaults).
  *
  * bf16 emulation (mzo_set_bf16(1)) mirrors the tensor-core kernel: every stored activation is rounded to bfloat16,
- * weights are rounded to bfloat16, sums accumulate in Float32, BatchNorm is folded into a Float32 per-channel affine;
+ * weights are rounded to bfloat16 AFTER the BatchNorm scale gamma/sqrt(var+eps) (and the x2 of make_state_action) is folded into them,
+ * sums accumulate in Float32, the rest of BatchNorm is a Float32 per-channel shift;
  * the action plane of the dynamics input and the final value / logits / reward stay Float32.
  * ------------------------------------------------------------------------------------------ */
 enum { RN_CONV = 0, RN_DENSE = 1 };
@@ -402,12 +403,12 @@ static void rn_conv(const mzo_config *c, const float *blob, const rn_unit_t *u, 
                 int sx = x + pad - ka, sy = y + pad - kb;
                 if (sx < 0 || sx >= W || sy < 0 || sy >= H) continue;
                 float wv = w[ka + k * (kb + k * (ci + cin * co))], xv = in[sx + W * sy + cells * ci];
-                if (g_bf16) acc = fmaf(bf16_round(wv), xv, acc);           /* operands already stored as bf16; in_mul applied below (power of two) */
+                if (g_bf16) acc = fmaf(bf16_round(wv * (in_mul * (gamma / den))), xv, acc);   /* BatchNorm scale (and the x2 of the dynamics input) folded into the bf16 weight */
                 else acc = fmaf(wv, xv * in_mul, acc);
             }
-            if (g_bf16) {   /* the kernel's folded Float32 epilogue: acc * (mul * s) + plane * (w_plane * s) + ((b - mu) * s + beta) */
-                float s = gamma / den, S = in_mul * s, T = fmaf(b - mu, s, beta), E = has_plane ? w[0 + k * (0 + k * ((cin - 1) + cin * co))] * s : 0.0f;
-                v = fmaf(acc, S, fmaf(plane, E, T));
+            if (g_bf16) {   /* the kernel's Float32 epilogue: acc + plane * (w_plane * s) + ((b - mu) * s + beta), s = gamma / sqrt(var + eps) */
+                float s = gamma / den, T = fmaf(b - mu, s, beta), E = has_plane ? w[0 + k * (0 + k * ((cin - 1) + cin * co))] * s : 0.0f;
+                v = acc + fmaf(plane, E, T);
             } else {
                 if (has_plane) acc = fmaf(w[0 + k * (0 + k * ((cin - 1) + cin * co))], plane, acc);
                 v = acc + b;

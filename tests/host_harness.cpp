@@ -245,7 +245,7 @@ struct rn_cpu {
                         float *dst = buf(J.dst_buf, 0, row); const float *skp = J.skip_buf != 0xff ? buf(J.skip_buf, 0, row) : nullptr;
                         float y[64];
                         for (int c = 0; c < 64; c++) {
-                            float v = fmaf((float)A[(size_t)row * 64 + c], S[c], (J.flags & MZ_RN_F_PLANE) ? fmaf(plane[(size_t)tree], E[c], T[c]) : T[c]);
+                            float v = (float)A[(size_t)row * 64 + c] + ((J.flags & MZ_RN_F_PLANE) ? fmaf(plane[(size_t)tree], E[c], T[c]) : T[c]);
                             if (skp) v = v + skp[c];
                             if (J.act == MZ_ACT_RELU) v = v > 0.0f ? v : 0.0f;
                             y[c] = valid ? bf16f(v) : 0.0f;
@@ -255,7 +255,7 @@ struct rn_cpu {
                     } else if (J.epi == MZ_RN_EPI_HEAD) {
                         if (!valid) continue;
                         for (int f = 0; f < J.nfa + J.nfb; f++) {
-                            float v = fmaf((float)A[(size_t)row * 64 + f], S[f], T[f]); v = v > 0.0f ? v : 0.0f;
+                            float v = (float)A[(size_t)row * 64 + f] + T[f]; v = v > 0.0f ? v : 0.0f;
                             const bool second = f >= J.nfa; const int k = cell + R.cells * (second ? f - J.nfa : f);
                             buf(second ? J.dst2_buf : J.dst_buf, k >> 6, tree)[k & 63] = bf16f(v);
                         }
