@@ -40,7 +40,7 @@ end
 
 check(e::Engine, rc) = rc == 0 ? nothing : throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx))))
 
-"Build the engine from the reference's `conf::Config` and `hyper::FeedForwardHP` (src/Constructors.jl:18-75)."
+"Build the engine from the reference's `conf::Config` and `hyper::FeedForwardHP` or `hyper::ResNetHP` (src/Constructors.jl:18-90)."
 function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
     c = MzConfig()
     ccall((:mz_default_config, LIB), Cint, (Ref{MzConfig},), c)
@@ -54,10 +54,18 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
     order = zeros(Int32, MZ_MAX_A)
     ccall((:mz_julia_dict_order, LIB), Cint, (Cint, Ptr{Int32}), c.A, order)   # or: collect(keys(Dict(a => 0 for a in conf.action_space)))
     c.child_order = Tuple(order)
-    c.width_hidden = hyper.width_hidden; c.depth_representation = hyper.depth_representation
-    c.depth_prediction = hyper.depth_prediction; c.depth_dynamics = hyper.depth_dynamics; c.depth_policy = hyper.depth_policy
-    c.depth_value = hyper.depth_value; c.depth_reward = hyper.depth_reward; c.depth_state_head = hyper.depth_state_head
-    c.hidden_state_size = hyper.hidden_state_size; c.reward_activation_tanh = hyper.reward_activation === tanh
+    if hasproperty(hyper, :num_blocks)      # ResNetHP (src/Constructors.jl:77-90): the repaired residual networks, bf16 on the tensor cores
+        c.net_type = 1; c.nn_mode = 1
+        c.rn_num_blocks = hyper.num_blocks; c.rn_num_filters = hyper.num_filters; c.rn_kernel = hyper.conv_kernel_size[1]
+        c.rn_first_head_filters = hyper.num_first_head_filters; c.rn_second_head_filters = hyper.num_second_head_filters
+        c.depth_value = hyper.depth_value; c.width_hidden = 64
+        c.hidden_state_size = c.W * c.H * c.rn_num_filters
+    else                                    # FeedForwardHP (src/Constructors.jl:62-75)
+        c.width_hidden = hyper.width_hidden; c.depth_representation = hyper.depth_representation
+        c.depth_prediction = hyper.depth_prediction; c.depth_dynamics = hyper.depth_dynamics; c.depth_policy = hyper.depth_policy
+        c.depth_value = hyper.depth_value; c.depth_reward = hyper.depth_reward; c.depth_state_head = hyper.depth_state_head
+        c.hidden_state_size = hyper.hidden_state_size; c.reward_activation_tanh = hyper.reward_activation === tanh
+    end
     c.num_slots = num_slots
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:mz_create, LIB), Cint, (Ref{MzConfig}, Cint, Ref{Ptr{Cvoid}}), c, device, ctx)
