@@ -155,6 +155,7 @@ void mzo_default_config(mzo_config *c) { /* games/tictactoe/params.jl:2-29; src/
     c->width_hidden = 64; c->depth_representation = 3; c->depth_prediction = 3; c->depth_dynamics = 3;
     c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
+    c->per = 0; c->per_alpha = 1;
     c->net_type = 0; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
@@ -971,16 +972,83 @@ float mzo_compute_target_value(const mzo_config *c, int T, const float *rewards,
 /* get_batch (ReplayBuffer.jl:188-217) with sample_n_games/sample_position uniform branches (:102-104, :80)
  * and make_target (:25-50, Q18).  RNG contract: Philox(seed, REPLAY, step, b) -> [0]: game, [1]: position;
  * absorbing-state actions Philox(seed, ABSORB, step, b, unroll offset). */
-void mzo_get_batch(const mzo_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
+/* ------------------------------------------------------------------------------------------
+ * Prioritised replay (conf.PER = true): REPAIRED specification of ReplayBuffer.jl:73-100, 136-145, 168-183, 213-215 and
+ * Learning.jl:400-404.  As written the reference cannot run with PER: update_priorities! indexes priority[1:end_index -
+ * start_index + 1] with up to K+2 elements of a K+1 vector (ReplayBuffer.jl:176-178, BoundsError), and the normalisations sum
+ * Float32 vectors in Dict iteration order.  Contract here:
+ *   - priority p = |root_value - compute_target_value|^PER_alpha (Float32, Julia's Float32^Int), quantised to fixed point
+ *     q = max(1, round(p * 2^16)) so that sums and prefix sums are exact integers (order independent, scan friendly) and every
+ *     stored position stays sampleable; game priority = max over its positions (:145);
+ *   - games in ascending key order; game ~ q_game / Q, position ~ q_pos / Q_game, by inverse CDF with 64-bit draws
+ *     mulhi(u64(philox.x, philox.z), Q) and mulhi(u64(philox.y, philox.w), Q_game) of Philox(seed, REPLAY, step, b);
+ *   - weight = 1 / (total_samples * game_prob * pos_prob), probabilities as Float32(q / Q), then ./= maximum (:213-215);
+ *   - update_priorities!: rows k = 0 .. min(K, T - pos) of |predicted_values - target_values|^alpha are written to positions
+ *     pos + k, batch elements in order (last write wins), then the game priority is recomputed.
+ * ------------------------------------------------------------------------------------------ */
+static float pow_int_f32(float x, int i) { /* Float32 ^ Int as Julia evaluates it: products for i <= 3, llvm.pow.f32 beyond */
+    if (i == 0) return 1.0f;
+    if (i == 1) return x;
+    if (i == 2) return x * x;
+    if (i == 3) return x * x * x;
+    return powf(x, (float)i);
+}
+uint32_t mzo_per_quantise(float p) {
+    float s = p * 65536.0f;
+    if (!(s >= 1.0f)) return 1u;
+    if (s > 4.0e9f) return 4000000000u;
+    return (uint32_t)llrintf(s);
+}
+void mzo_per_priorities(const mzo_config *c, int T, const float *rewards, const int32_t *to_play, const float *root_values,
+                        uint32_t *q_pos, uint32_t *q_game) { /* save_game, ReplayBuffer.jl:136-145 */
+    uint32_t mx = 0;
+    for (int i = 1; i <= T; i++) {
+        float p = pow_int_f32(fabsf(root_values[i - 1] - mzo_compute_target_value(c, T, rewards, to_play, root_values, i)), c->per_alpha);
+        q_pos[i - 1] = mzo_per_quantise(p);
+        if (q_pos[i - 1] > mx) mx = q_pos[i - 1];
+    }
+    *q_game = mx;
+}
+static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+void mzo_per_update(const mzo_config *c, int B, const int32_t *index_batch, const float *pred_values, const float *target_values,
+                    int n_games, int64_t first_key, const int32_t *T, uint32_t *q_pos, uint32_t *q_game) {
+    int Tmax = c->max_moves + 1, K1 = c->num_unroll_steps + 1;
+    for (int b = 0; b < B; b++) {
+        int64_t gi = (int64_t)index_batch[2 * b] - first_key; int pos = index_batch[2 * b + 1];
+        if (gi < 0 || gi >= n_games) continue;                             /* the game has left the buffer (:172) */
+        int Tg = T[gi];
+        for (int k = 0; k < K1 && pos + k <= Tg; k++)
+            q_pos[(size_t)gi * Tmax + pos + k - 1] = mzo_per_quantise(pow_int_f32(fabsf(pred_values[(size_t)b * K1 + k] - target_values[(size_t)b * K1 + k]), c->per_alpha));
+        uint32_t mx = 0;
+        for (int i = 0; i < Tg; i++) if (q_pos[(size_t)gi * Tmax + i] > mx) mx = q_pos[(size_t)gi * Tmax + i];
+        q_game[gi] = mx;
+    }
+}
+
+static void get_batch_impl(const mzo_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
                    const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values, uint64_t step,
                    int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
-                   float *policy_batch, float *gscale) {
+                   float *policy_batch, float *gscale, const uint32_t *q_pos, const uint32_t *q_game, float *weights) {
     int Tmax = c->max_moves + 1, on = obs_size(c), ss = stack_size(c), K1 = c->num_unroll_steps + 1, A = c->A;
+    uint64_t Q = 0; int64_t total_samples = 0;
+    if (q_game) for (int g = 0; g < n_games; g++) { Q += q_game[g]; total_samples += T[g]; }
     for (int b = 0; b < c->batch_size; b++) {
         uint32_t r[4]; mzo_philox(c->seed, STREAM_REPLAY, (uint32_t)step, (uint32_t)b, 0, 0, r);
-        int gi = (int)u32_below(r[0], (uint32_t)n_games);
+        int gi, pos;
+        if (q_game) {   /* prioritised: sample_n_games :90-100, sample_position :75-79 */
+            uint64_t t = mulhi64(((uint64_t)r[0] << 32) | r[2], Q), acc = 0;
+            for (gi = 0; gi < n_games - 1; gi++) { acc += q_game[gi]; if (acc > t) break; }
+            const uint32_t *qp = q_pos + (size_t)gi * Tmax;
+            uint64_t Qg = 0; for (int i = 0; i < T[gi]; i++) Qg += qp[i];
+            uint64_t t2 = mulhi64(((uint64_t)r[1] << 32) | r[3], Qg), a2 = 0;
+            for (pos = 1; pos < T[gi]; pos++) { a2 += qp[pos - 1]; if (a2 > t2) break; }
+            float game_prob = (float)((double)q_game[gi] / (double)Q), pos_prob = (float)((double)qp[pos - 1] / (double)Qg);
+            weights[b] = 1.0f / (((float)total_samples * game_prob) * pos_prob);             /* :213 */
+        } else {
+            gi = (int)u32_below(r[0], (uint32_t)n_games);
+            pos = 1 + (int)u32_below(r[1], (uint32_t)T[gi]);              /* rand(1:length(root_values)) */
+        }
         int Tg = T[gi];
-        int pos = 1 + (int)u32_below(r[1], (uint32_t)Tg);                 /* rand(1:length(root_values)) */
         const float *g_obs = obs + (size_t)gi * Tmax * on; const int32_t *g_act = actions + (size_t)gi * Tmax;
         const float *g_rew = rewards + (size_t)gi * Tmax; const int32_t *g_tp = to_play + (size_t)gi * Tmax;
         const float *g_cv = child_visits + (size_t)gi * Tmax * A; const float *g_rv = root_values + (size_t)gi * Tmax;
@@ -1008,6 +1076,25 @@ void mzo_get_batch(const mzo_config *c, int n_games, int64_t first_key, const in
         int gs = Tg + 1 - pos; if (c->num_unroll_steps < gs) gs = c->num_unroll_steps; /* :212 */
         gscale[b] = (float)gs;
     }
+    if (q_game) {   /* weight_batch ./= maximum(weight_batch), :215 */
+        float mx = weights[0];
+        for (int b = 1; b < c->batch_size; b++) mx = weights[b] > mx ? weights[b] : mx;
+        for (int b = 0; b < c->batch_size; b++) weights[b] = weights[b] / mx;
+    }
+}
+void mzo_get_batch(const mzo_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
+                   const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values, uint64_t step,
+                   int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
+                   float *policy_batch, float *gscale) {
+    get_batch_impl(c, n_games, first_key, T, obs, actions, rewards, to_play, child_visits, root_values, step, index_batch, obs_batch,
+                   action_batch, value_batch, reward_batch, policy_batch, gscale, NULL, NULL, NULL);
+}
+void mzo_get_batch_per(const mzo_config *c, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
+                       const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values,
+                       const uint32_t *q_pos, const uint32_t *q_game, uint64_t step, int32_t *index_batch, float *obs_batch,
+                       float *action_batch, float *value_batch, float *reward_batch, float *policy_batch, float *gscale, float *weights) {
+    get_batch_impl(c, n_games, first_key, T, obs, actions, rewards, to_play, child_visits, root_values, step, index_batch, obs_batch,
+                   action_batch, value_batch, reward_batch, policy_batch, gscale, q_pos, q_game, weights);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -1029,8 +1116,9 @@ static float sqnorm_net(const float *blob, const net_t *n) { /* sum(sqnorm, para
     return total;
 }
 
-void mzo_learn_forward(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+static void learn_forward_impl(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
                        const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                       const float *weights /* PER importance weights (1,B), or NULL: weight_batch = 1.0f0 (:266-268) */,
                        float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
     model_t m; model_init(&m, c, blob);
     int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), on = obs_size(c), plane = c->W * c->H;
@@ -1069,20 +1157,31 @@ void mzo_learn_forward(const mzo_config *c, const float *blob, int B, const floa
             for (int a = 0; a < A; a++) acc = acc + y[a] * ((p[a] - mx) - lse);
             sp = sp + (-acc);
         }
-        vsum = vsum + sv / gscale[b];
-        rsum = rsum + sr / (double)gscale[b];
+        vsum = vsum + (weights ? (sv / gscale[b]) * weights[b] : sv / gscale[b]);
+        rsum = rsum + (weights ? (sr / (double)gscale[b]) * (double)weights[b] : sr / (double)gscale[b]);
         S[b] = sp;
     }
     float value_loss = vsum / (float)B;
     /* sum(x,dims=2) is (1,1,B), gscale is (1,B): the broadcast is (1,B,B); mean over all B*B entries */
     float psum = 0.0f;
-    for (int j = 0; j < B; j++) for (int i = 0; i < B; i++) psum = psum + S[j] / gscale[i];
+    for (int j = 0; j < B; j++) for (int i = 0; i < B; i++) psum = psum + (weights ? (S[j] / gscale[i]) * weights[i] : S[j] / gscale[i]);
     float policy_loss = psum / (float)(B * B);
     free(S);
     float data_loss;
     if (c->intermediate_rewards) data_loss = (float)(((double)value_loss + rsum / (double)B) + (double)policy_loss);
     else data_loss = (value_loss + 0.0f) + policy_loss;
     for (int n = 0; n < 3; n++) losses[n] = data_loss + sqnorm_net(blob, &m.nets[n]);
+}
+
+void mzo_learn_forward(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                       const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                       float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
+    learn_forward_impl(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, NULL, pred_values, pred_rewards, pred_policies, losses);
+}
+void mzo_learn_forward_w(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                         const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale, const float *weights,
+                         float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
+    learn_forward_impl(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, weights, pred_values, pred_rewards, pred_policies, losses);
 }
 
 double mzo_cos_schedule(int t) { /* ParameterSchedulers.Cos(l0=1e-4, l1=1e-1, period=10), Learning.jl:319 (Q22) */
@@ -1180,8 +1279,8 @@ static void net_bwd(const double *wd, double *G, const net_t *n, const net_act_t
 
 /* grad[n_params] (blob order, Float64) and the Float64 data loss.  perturb_index >= 0 adds perturb_delta to that
  * parameter of the Float64 weight copy first (finite differences; only meaningful with fwd64 = 1). */
-double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
-                           const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+static double learn_gradients_impl(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                           const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale, const float *weights,
                            int fwd64, int perturb_index, double perturb_delta, double *grad) {
     model_t m; model_init(&m, c, blob);
     int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), on = obs_size(c), plane = c->W * c->H, hs = c->hidden_state_size;
@@ -1192,7 +1291,7 @@ double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const 
     if (grad) for (int i = 0; i < np; i++) grad[i] = 0.0;
     net_act_t *ar = (net_act_t *)malloc(sizeof(net_act_t)), *ap = (net_act_t *)malloc(sizeof(net_act_t) * (size_t)K1), *ad = (net_act_t *)malloc(sizeof(net_act_t) * (size_t)(K ? K : 1));
     double G = 0.0;                                   /* mean_i(1/g_i): Q21's (1,B,B) broadcast factorises */
-    for (int b = 0; b < B; b++) G += 1.0 / (double)gscale[b];
+    for (int b = 0; b < B; b++) G += (weights ? (double)weights[b] : 1.0) / (double)gscale[b];
     G /= (double)B;
     double vsum = 0.0, rsum = 0.0, ssum = 0.0;
     for (int b = 0; b < B; b++) {
@@ -1200,7 +1299,7 @@ double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const 
         for (int k = 0; k < ss; k++) x[k] = (double)obs_batch[(size_t)b * ss + k];
         net_fwd(blob, wd, &m.nets[0], x, ar, fwd64);                                        /* :347 */
         const double *h = ar->trunk.out[m.nets[0].n_trunk - 1];
-        double g = (double)gscale[b];
+        double g = (double)gscale[b] / (weights ? (double)weights[b] : 1.0);   /* value / reward terms: (sum / g) * w */
         /* rows: row 0 = prediction(h0) (:351); row i = prediction(h_{i-1}) BEFORE dynamics step i (:356-362, Q19) */
         for (int i = 0; i <= K; i++) {
             net_fwd(blob, wd, &m.nets[1], h, &ap[i], fwd64);
@@ -1265,6 +1364,17 @@ double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const 
     double data = value_loss + (c->intermediate_rewards ? rsum / (double)B : 0.0) + policy_loss;
     free(wd); free(ar); free(ap); free(ad);
     return data;
+}
+
+double mzo_learn_gradients(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                           const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                           int fwd64, int perturb_index, double perturb_delta, double *grad) {
+    return learn_gradients_impl(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, NULL, fwd64, perturb_index, perturb_delta, grad);
+}
+double mzo_learn_gradients_w(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                             const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale, const float *weights,
+                             int fwd64, int perturb_index, double perturb_delta, double *grad) {
+    return learn_gradients_impl(c, blob, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, weights, fwd64, perturb_index, perturb_delta, grad);
 }
 
 /* Flux.ADAM on a caller-supplied gradient (lets the tests check the CUDA update bit-for-bit given the CUDA gradient) */

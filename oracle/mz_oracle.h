@@ -74,6 +74,8 @@ typedef struct mzo_config {
     int32_t rn_kernel;              /* conv_kernel_size = (k,k), odd; representation only (Learning.jl:195,230 fix (1,1) elsewhere) */
     int32_t rn_first_head_filters;  /* num_first_head_filters = 1 (value and reward heads) */
     int32_t rn_second_head_filters; /* num_second_head_filters = 2 (policy head) */
+    int32_t per;                    /* conf.PER (params.jl:11: false) */
+    int32_t per_alpha;              /* conf.PER_alpha (Constructors.jl:44: 1) */
 } mzo_config;
 
 void mzo_default_config(mzo_config *cfg);            /* params.jl:2-29 defaults */
@@ -154,6 +156,24 @@ double mzo_cos_schedule(int t);
 void mzo_learn_step(const mzo_config *cfg, float *blob, float *adam_m, float *adam_v, int t, int grad_mode, int B,
                     const float *obs_batch, const float *action_batch, const float *value_batch,
                     const float *reward_batch, const float *policy_batch, const float *gscale, float *losses);
+
+/* ---- prioritised replay (conf.PER = true), repaired specification: see the PER section of mz_oracle.c ---- */
+uint32_t mzo_per_quantise(float p);
+void mzo_per_priorities(const mzo_config *cfg, int T, const float *rewards, const int32_t *to_play, const float *root_values,
+                        uint32_t *q_pos /* [T] */, uint32_t *q_game);
+void mzo_get_batch_per(const mzo_config *cfg, int n_games, int64_t first_key, const int32_t *T, const float *obs, const int32_t *actions,
+                       const float *rewards, const int32_t *to_play, const float *child_visits, const float *root_values,
+                       const uint32_t *q_pos /* [n][Tmax] */, const uint32_t *q_game /* [n] */, uint64_t step, int32_t *index_batch,
+                       float *obs_batch, float *action_batch, float *value_batch, float *reward_batch, float *policy_batch, float *gscale,
+                       float *weights /* [B] */);
+void mzo_per_update(const mzo_config *cfg, int B, const int32_t *index_batch, const float *pred_values, const float *target_values,
+                    int n_games, int64_t first_key, const int32_t *T, uint32_t *q_pos, uint32_t *q_game);
+void mzo_learn_forward_w(const mzo_config *cfg, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                         const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                         const float *weights, float *pred_values, float *pred_rewards, float *pred_policies, float *losses);
+double mzo_learn_gradients_w(const mzo_config *cfg, const float *blob, int B, const float *obs_batch, const float *action_batch,
+                             const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
+                             const float *weights, int fwd64, int perturb_index, double perturb_delta, double *grad);
 
 /* grad_mode = MZO_GRAD_BPTT: d(loss)/d(theta) through the unroll (Float64 backward; see mz_oracle.c).  Returns the
  * Float64 data loss; grad (may be NULL) = d(data loss)/d(theta) + 2*theta in blob order.  fwd64 = 0 linearises around

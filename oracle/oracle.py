@@ -33,6 +33,7 @@ class Config(C.Structure):
         ("reward_activation_tanh", C.c_int32),
         ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
         ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
+        ("per", C.c_int32), ("per_alpha", C.c_int32),
     ]
 
 
@@ -104,6 +105,14 @@ def lib():
     L.mzo_learn_gradients.argtypes = [cfgp, f32p, C.c_int] + [f32p] * 6 + [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
     L.mzo_learn_gradients.restype = C.c_double
     L.mzo_adam_apply.argtypes = [f32p, f32p, f32p, f32p, C.c_int, C.c_int]
+    L.mzo_per_quantise.argtypes = [C.c_float]; L.mzo_per_quantise.restype = C.c_uint32
+    L.mzo_per_priorities.argtypes = [cfgp, C.c_int, f32p, i32p, f32p, u32p, u32p]
+    L.mzo_get_batch_per.argtypes = [cfgp, C.c_int, C.c_int64, i32p, f32p, i32p, f32p, i32p, f32p, f32p, u32p, u32p, C.c_uint64,
+                                    i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
+    L.mzo_per_update.argtypes = [cfgp, C.c_int, i32p, f32p, f32p, C.c_int, C.c_int64, i32p, u32p, u32p]
+    L.mzo_learn_forward_w.argtypes = [cfgp, f32p, C.c_int] + [f32p] * 11
+    L.mzo_learn_gradients_w.argtypes = [cfgp, f32p, C.c_int] + [f32p] * 7 + [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    L.mzo_learn_gradients_w.restype = C.c_double
     _lib = L
     return L
 
@@ -263,3 +272,56 @@ def learn_gradients(cfg, blob, batch, fwd64=False, perturb=None, want_grad=True)
 
 def adam_apply(blob, adam_m, adam_v, grad, t):
     lib().mzo_adam_apply(_p(blob), _p(adam_m), _p(adam_v), _p(grad), blob.shape[0], t)
+
+
+# ---- prioritised replay (conf.PER = true; repaired specification, see mz_oracle.c) ----
+def per_priorities(cfg, hist):
+    """save_game's initial priorities (ReplayBuffer.jl:136-145) for every history: (q_pos [n][Tmax], q_game [n]) fixed point."""
+    n = len(hist["T"]); Tmax = cfg.max_moves + 1
+    q_pos = np.zeros((n, Tmax), np.uint32); q_game = np.zeros(n, np.uint32)
+    for g in range(n):
+        lib().mzo_per_priorities(C.byref(cfg), int(hist["T"][g]), _p(np.ascontiguousarray(hist["rewards"][g])),
+                                 _p(np.ascontiguousarray(hist["to_play"][g], np.int32), C.c_int32), _p(np.ascontiguousarray(hist["root_values"][g])),
+                                 q_pos[g].ctypes.data_as(C.POINTER(C.c_uint32)), q_game[g:].ctypes.data_as(C.POINTER(C.c_uint32)))
+    return q_pos, q_game
+
+
+def get_batch_per(cfg, hist, q_pos, q_game, step, first_key=1):
+    s = sizes(cfg); B = cfg.batch_size
+    out = dict(index=np.zeros((B, 2), np.int32), obs=np.zeros((B, s["stack"]), np.float32),
+               actions=np.zeros((B, s["K1"]), np.float32), values=np.zeros((B, s["K1"]), np.float32),
+               rewards=np.zeros((B, s["K1"]), np.float32), policies=np.zeros((B, s["K1"], s["A"]), np.float32),
+               gscale=np.zeros(B, np.float32), weights=np.zeros(B, np.float32))
+    lib().mzo_get_batch_per(C.byref(cfg), len(hist["T"]), first_key, _p(hist["T"], C.c_int32), _p(hist["obs"]),
+                            _p(hist["actions"], C.c_int32), _p(hist["rewards"]), _p(hist["to_play"], C.c_int32),
+                            _p(hist["child_visits"]), _p(hist["root_values"]), _p(q_pos, C.c_uint32), _p(q_game, C.c_uint32), step,
+                            _p(out["index"], C.c_int32), _p(out["obs"]), _p(out["actions"]), _p(out["values"]), _p(out["rewards"]),
+                            _p(out["policies"]), _p(out["gscale"]), _p(out["weights"]))
+    return out
+
+
+def per_update(cfg, hist, q_pos, q_game, index_batch, pred_values, target_values, first_key=1):
+    """update_priorities! (ReplayBuffer.jl:168-183, repaired bounds), in place."""
+    lib().mzo_per_update(C.byref(cfg), index_batch.shape[0], _p(np.ascontiguousarray(index_batch, np.int32), C.c_int32),
+                         _p(np.ascontiguousarray(pred_values, np.float32)), _p(np.ascontiguousarray(target_values, np.float32)),
+                         len(hist["T"]), first_key, _p(hist["T"], C.c_int32), _p(q_pos, C.c_uint32), _p(q_game, C.c_uint32))
+
+
+def learn_forward_w(cfg, blob, batch):
+    B = batch["obs"].shape[0]; s = sizes(cfg)
+    pv = np.zeros((B, s["K1"]), np.float32); pr = np.zeros((B, s["K1"]), np.float32)
+    pp = np.zeros((B, s["K1"], s["A"]), np.float32); losses = np.zeros(3, np.float32)
+    lib().mzo_learn_forward_w(C.byref(cfg), _p(blob), B, _p(batch["obs"]), _p(batch["actions"]), _p(batch["values"]),
+                              _p(batch["rewards"]), _p(batch["policies"]), _p(batch["gscale"]), _p(batch["weights"]), _p(pv), _p(pr), _p(pp),
+                              _p(losses))
+    return pv, pr, pp, losses
+
+
+def learn_gradients_w(cfg, blob, batch, fwd64=False, perturb=None, want_grad=True):
+    B = batch["obs"].shape[0]
+    grad = np.zeros(blob.shape[0], np.float64) if want_grad else None
+    idx, delta = perturb if perturb is not None else (-1, 0.0)
+    loss = lib().mzo_learn_gradients_w(C.byref(cfg), _p(blob), B, _p(batch["obs"]), _p(batch["actions"]), _p(batch["values"]),
+                                       _p(batch["rewards"]), _p(batch["policies"]), _p(batch["gscale"]), _p(batch["weights"]), int(fwd64),
+                                       int(idx), float(delta), grad.ctypes.data_as(C.POINTER(C.c_double)) if want_grad else None)
+    return loss, grad
