@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 2
+#define MZ_ABI_VERSION 3
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
@@ -76,6 +76,9 @@ typedef struct mz_config {
     int32_t rn_kernel;              /* conv_kernel_size = (k,k) of the representation network, 1 or 3 */
     int32_t rn_first_head_filters;  /* num_first_head_filters = 1 */
     int32_t rn_second_head_filters; /* num_second_head_filters = 2 */
+    /* prioritised replay (src/Constructors.jl:43-44): repaired specification, DESIGN.md "PER" */
+    int32_t per;                    /* conf.PER */
+    int32_t per_alpha;              /* conf.PER_alpha, 0..3 */
 } mz_config;
 
 typedef struct mz_ctx mz_ctx;
@@ -145,6 +148,12 @@ int mz_reanalysed_export(mz_ctx *ctx, int64_t key0, int n, float *values /* [n][
 int mz_get_batch(mz_ctx *ctx, uint64_t step, int32_t *index_batch /* [B][2] (game key, position) */, float *obs_batch,
                  float *action_batch, float *value_batch, float *reward_batch, float *policy_batch, float *gscale);
 
+/* conf.PER = true: the same batch + the importance-sampling weights (ReplayBuffer.jl:213-215), games / positions drawn by priority */
+int mz_get_batch_per(mz_ctx *ctx, uint64_t step, int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch,
+                     float *reward_batch, float *policy_batch, float *gscale, float *weight_batch /* [B] */);
+/* fixed-point priorities of games key0 .. key0+n-1: q_pos [n][Tmax], q_game [n] (history.priorities, history.game_priority) */
+int mz_replay_priorities(mz_ctx *ctx, int64_t key0, int n, uint32_t *q_pos, uint32_t *q_game);
+
 /* ---- learner: learning! (src/Learning.jl:306-438) --------------------------------------------- */
 /* forward unroll + loss on a caller-supplied batch (parity entry point; Learning.jl:347-374, 261-288) */
 int mz_learn_forward(mz_ctx *ctx, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
@@ -161,6 +170,10 @@ int mz_learn_steps(mz_ctx *ctx, int64_t t0, int n, int grad_mode, float *losses 
  * value (Learning.jl:261-288) through the unroll (Learning.jl:347-370), plus 2*theta. */
 int mz_learn_gradients(mz_ctx *ctx, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
                        const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses /* [3] */);
+/* the same with importance-sampling weights weight_batch [B] (conf.PER; NULL = 1) */
+int mz_learn_gradients_w(mz_ctx *ctx, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                         const float *reward_batch, const float *policy_batch, const float *gscale, const float *weight_batch, float *grad,
+                         float *losses /* [3] */);
 /* same update on a caller-supplied batch (parity entry point) */
 int mz_learn_step_batch(mz_ctx *ctx, int64_t t, int grad_mode, int B, const float *obs_batch, const float *action_batch,
                         const float *value_batch, const float *reward_batch, const float *policy_batch,

@@ -86,8 +86,6 @@ class GameHistory:
 
 def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.GAME_TICTACTOE, tie_mode=capi.TIE_PHILOX,
                  child_order=None, nn_mode=capi.NN_FP32_EXACT):
-    if conf.PER:
-        raise NotImplementedError("PER=true is outside the accelerated path (SURVEY.md section 8f)")
     if hyper.use_batch_norm:
         raise NotImplementedError("use_batch_norm=true is not supported (default false, Constructors.jl:71)")
     if list(conf.action_space) != list(range(1, len(conf.action_space) + 1)):
@@ -122,6 +120,8 @@ def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.G
               "depth_reward", "depth_state_head", "hidden_state_size"):
         setattr(c, k, getattr(hyper, k))
     c.reward_activation_tanh = 1 if hyper.reward_activation in ("tanh", np.tanh) else 0
+    c.per = 1 if conf.PER else 0          # repaired specification of the prioritised replay
+    c.per_alpha = int(conf.PER_alpha)
     c.num_slots = num_slots
     c.nn_mode = nn_mode
     return c
@@ -270,10 +270,11 @@ def save_game(engine: Engine, history: GameHistory, game_id=None):
 
 def get_batch(engine: Engine, step=None):
     """get_batch(buffer) (ReplayBuffer.jl:188-217): (index_batch, (observation_batch, action_batch, value_batch,
-    reward_batch, policy_batch, weight_batch, gradient_scale_batch)); weight_batch is None (PER=false)."""
-    b = engine.ctx.get_batch(engine.training_step + 1 if step is None else step)
+    reward_batch, policy_batch, weight_batch, gradient_scale_batch)); weight_batch is None when PER = false."""
+    t = engine.training_step + 1 if step is None else step
+    b = engine.ctx.get_batch_per(t) if engine.ctx.cfg.per else engine.ctx.get_batch(t)
     index_batch = [(int(k), int(p)) for k, p in b["index"]]
-    return index_batch, (b["obs"], b["actions"], b["values"], b["rewards"], b["policies"], None, b["gscale"])
+    return index_batch, (b["obs"], b["actions"], b["values"], b["rewards"], b["policies"], b.get("weights"), b["gscale"])
 
 
 def save_checkpoint(engine: Engine, path: str):

@@ -45,6 +45,7 @@ class MzConfig(C.Structure):
         ("reward_activation_tanh", C.c_int32), ("num_slots", C.c_int32), ("nn_mode", C.c_int32),
         ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
         ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
+        ("per", C.c_int32), ("per_alpha", C.c_int32),
     ]
 
     def copy(self):
@@ -105,6 +106,9 @@ def lib():
         "mz_reanalyse": ([ctx, C.c_int64, C.c_int], C.c_int),
         "mz_reanalysed_export": ([ctx, C.c_int64, C.c_int, f32p, i32p], C.c_int),
         "mz_get_batch": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
+        "mz_get_batch_per": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
+        "mz_replay_priorities": ([ctx, C.c_int64, C.c_int, u32p, u32p], C.c_int),
+        "mz_learn_gradients_w": ([ctx, C.c_int, C.c_int] + [f32p] * 9, C.c_int),
         "mz_learn_forward": ([ctx, C.c_int] + [f32p] * 10, C.c_int),
         "mz_learn_step": ([ctx, C.c_int64, C.c_int, f32p], C.c_int),
         "mz_learn_steps": ([ctx, C.c_int64, C.c_int, C.c_int, f32p], C.c_int),
@@ -355,6 +359,25 @@ class Context:
                                      _p(out["gscale"], C.c_float)))
         return out
 
+    def get_batch_per(self, step):
+        """conf.PER = true: get_batch with prioritised sampling + importance weights (ReplayBuffer.jl:188-217)."""
+        s = self.s; B = self.cfg.batch_size
+        out = dict(index=np.zeros((B, 2), np.int32), obs=np.zeros((B, s["stack"]), np.float32), actions=np.zeros((B, s["K1"]), np.float32),
+                   values=np.zeros((B, s["K1"]), np.float32), rewards=np.zeros((B, s["K1"]), np.float32),
+                   policies=np.zeros((B, s["K1"], s["A"]), np.float32), gscale=np.zeros(B, np.float32), weights=np.zeros(B, np.float32))
+        self._ck(self.L.mz_get_batch_per(self._h, step, _p(out["index"], C.c_int32), _p(out["obs"], C.c_float), _p(out["actions"], C.c_float),
+                                         _p(out["values"], C.c_float), _p(out["rewards"], C.c_float), _p(out["policies"], C.c_float),
+                                         _p(out["gscale"], C.c_float), _p(out["weights"], C.c_float)))
+        return out
+
+    def replay_priorities(self, key0=None, n=None):
+        info = self.replay_info()
+        key0 = info["first_key"] if key0 is None else key0
+        n = info["n_games"] - (key0 - info["first_key"]) if n is None else n
+        q_pos = np.zeros((n, self.s["Tmax"]), np.uint32); q_game = np.zeros(n, np.uint32)
+        self._ck(self.L.mz_replay_priorities(self._h, key0, n, _p(q_pos, C.c_uint32), _p(q_game, C.c_uint32)))
+        return q_pos, q_game
+
     def reanalyse(self, key0=None, n=None):
         """reanalysed_predicted_root_values of games key0 .. key0+n-1 (default: the whole buffer) from the current networks."""
         info = self.replay_info()
@@ -395,6 +418,10 @@ class Context:
         """(gradient in the reference blob order, losses) of one batch; no update."""
         arrs, ptrs = self._batch_ptrs(batch)
         grad = np.zeros(self.num_params(), np.float32); losses = np.zeros(3, np.float32)
+        if "weights" in batch and self.cfg.per:
+            w = _f32(batch["weights"])
+            self._ck(self.L.mz_learn_gradients_w(self._h, grad_mode, arrs[0].shape[0], *ptrs, _p(w, C.c_float), _p(grad, C.c_float), _p(losses, C.c_float)))
+            return grad, losses
         self._ck(self.L.mz_learn_gradients(self._h, grad_mode, arrs[0].shape[0], *ptrs, _p(grad, C.c_float), _p(losses, C.c_float)))
         return grad, losses
 

@@ -128,13 +128,13 @@ template <typename T> cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((
 int alloc_batch(mz_ctx *c, int B) {
     if (B <= c->batch_cap) return MZ_OK;
     const mz_params &P = c->M.P; int K1 = P.K + 1;
-    void *ptrs[] = {c->batch.index, c->batch.obs, c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale,
+    void *ptrs[] = {c->batch.weights, c->batch.index, c->batch.obs, c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale,
                     c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
     for (void *p : ptrs) if (p) cudaFree(p);
     MZ_CUDA(c, dmalloc(&c->batch.index, (size_t)B * 2)); MZ_CUDA(c, dmalloc(&c->batch.obs, (size_t)B * P.stack_size));
     MZ_CUDA(c, dmalloc(&c->batch.actions, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.values, (size_t)B * K1));
     MZ_CUDA(c, dmalloc(&c->batch.rewards, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.policies, (size_t)B * K1 * P.A));
-    MZ_CUDA(c, dmalloc(&c->batch.gscale, (size_t)B));
+    MZ_CUDA(c, dmalloc(&c->batch.gscale, (size_t)B)); MZ_CUDA(c, dmalloc(&c->batch.weights, (size_t)B));
     MZ_CUDA(c, dmalloc(&c->d_pv, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->d_pr, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->d_pp, (size_t)B * K1 * P.A));
     MZ_CUDA(c, dmalloc(&c->d_rowv, (size_t)B)); MZ_CUDA(c, dmalloc(&c->d_rowp, (size_t)B)); MZ_CUDA(c, dmalloc(&c->d_rowinvg, (size_t)B));
     MZ_CUDA(c, dmalloc(&c->d_rowr, (size_t)B));
@@ -363,6 +363,8 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(dmalloc(&r.game_id, R)); MZ_CREATE(dmalloc(&r.T, R));
     MZ_CREATE(dmalloc(&r.h_p1, R * Tm)); MZ_CREATE(dmalloc(&r.h_p2, R * Tm)); MZ_CREATE(dmalloc(&r.h_action, R * Tm));
     MZ_CREATE(dmalloc(&r.h_reward, R * Tm)); MZ_CREATE(dmalloc(&r.h_to_play, R * Tm)); MZ_CREATE(dmalloc(&r.h_cv, R * Tm * P.A)); MZ_CREATE(dmalloc(&r.h_rv, R * Tm));
+    MZ_CREATE(dmalloc(&r.q_pos, R * Tm)); MZ_CREATE(dmalloc(&r.q_game, R)); MZ_CREATE(dmalloc(&r.prefix, R)); MZ_CREATE(dmalloc(&r.upd, R * Tm));
+    MZ_CREATE(cudaMemset(r.q_pos, 0, R * Tm * 4)); MZ_CREATE(cudaMemset(r.q_game, 0, R * 4)); MZ_CREATE(cudaMemset(r.upd, 0, R * Tm * 8));
     MZ_CREATE(dmalloc(&r.h_rrv, R * Tm)); MZ_CREATE(dmalloc(&r.reanalysed, R)); MZ_CREATE(cudaMemset(r.reanalysed, 0, R)); MZ_CREATE(cudaMemset(r.h_rrv, 0, R * Tm * sizeof(float)));
     MZ_CREATE(dmalloc(&r.counters, 8)); MZ_CREATE(cudaMemset(r.counters, 0, 8 * sizeof(int64_t)));
     MZ_CREATE(cudaMemset(r.T, 0, R * sizeof(int32_t)));
@@ -386,8 +388,8 @@ int mz_destroy(mz_ctx *c) {
     void *ptrs[] = {c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
-                    c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
-                    c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale, c->d_pv, c->d_pr, c->d_pp,
+                    c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
+                    c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale, c->batch.weights, c->d_pv, c->d_pr, c->d_pp,
                     c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &b : c->scratch) b.release();
@@ -710,6 +712,7 @@ int mz_history_import(mz_ctx *c, int n, const int64_t *game_id, const int32_t *T
     MZ_TRY(h2d(c, c->scratch[4], rewards, N * Tm, &d_rew)); MZ_TRY(h2d(c, c->scratch[5], to_play, N * Tm, &d_tp));
     MZ_TRY(h2d(c, c->scratch[6], child_visits, N * Tm * P.A, &d_cv)); MZ_TRY(h2d(c, c->scratch[7], root_values, N * Tm, &d_rv));
     { launch_scope ls(c, 2); mz_k_history_import<<<(unsigned)((N * Tm + 127) / 128), 128, 0, c->stream>>>(P, c->ring, key0, n, d_gid, d_T, d_obs, d_act, d_rew, d_tp, d_cv, d_rv); }
+    if (c->cfg.per) { launch_scope ls(c, 2); mz_k_per_init<<<(n + 127) / 128, 128, 0, c->stream>>>(P, c->ring, key0, n); }   // save_game's initial priorities
     MZ_CUDA(c, cudaGetLastError());
     return write_counters(c);
 }
@@ -751,14 +754,28 @@ int mz_reanalysed_export(mz_ctx *c, int64_t key0, int n, float *values, int32_t 
 }
 
 // ---- replay sampling / learner -----------------------------------------------------------------------------
+// get_batch on the device ring; conf.PER: prefix scan of the game priorities first, weight normalisation after
+static int launch_gather(mz_ctx *c, uint64_t step, int B) {
+    if (c->cfg.per) { launch_scope ls(c, 2); mz_k_per_scan<<<1, 1024, 0, c->stream>>>(c->M.P, c->ring); }
+    { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, step, B, c->batch); }
+    if (c->cfg.per) { launch_scope ls(c, 2); mz_k_per_normalise<<<1, 1024, 0, c->stream>>>(B, c->batch.weights); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
+// update_priorities! after the optimiser step (Learning.jl:400-404)
+static int launch_per_update(mz_ctx *c, int B) {
+    if (!c->cfg.per) return MZ_OK;
+    const int n = B * (c->M.P.K + 1);
+    for (int phase = 0; phase < 3; phase++) { launch_scope ls(c, 2); mz_k_per_update<<<(n + 127) / 128, 128, 0, c->stream>>>(c->M.P, c->ring, B, c->batch.index, c->d_pv, c->batch.values, phase); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
 static int gather_batch(mz_ctx *c, uint64_t step) {
     const int B = c->cfg.batch_size;
     MZ_TRY(alloc_batch(c, B));
     MZ_TRY(read_counters(c));
     if (c->h_counters[0] < 1) return fail(c, MZ_E_STATE, "replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)");
-    { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, step, B, c->batch); }
-    MZ_CUDA(c, cudaGetLastError());
-    return MZ_OK;
+    return launch_gather(c, step, B);
 }
 int mz_get_batch(mz_ctx *c, uint64_t step, int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
                  float *policy_batch, float *gscale) {
@@ -773,6 +790,33 @@ int mz_get_batch(mz_ctx *c, uint64_t step, int32_t *index_batch, float *obs_batc
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
+int mz_get_batch_per(mz_ctx *c, uint64_t step, int32_t *index_batch, float *obs_batch, float *action_batch, float *value_batch, float *reward_batch,
+                     float *policy_batch, float *gscale, float *weight_batch) {
+    MZ_CHECK_CTX(c);
+    if (!c->cfg.per) return fail(c, MZ_E_STATE, "conf.PER is false: use mz_get_batch");
+    if (!weight_batch) return fail(c, MZ_E_ARG, "NULL buffer");
+    int rc = mz_get_batch(c, step, index_batch, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale);
+    if (rc != MZ_OK) return rc;
+    MZ_TRY(d2h(c, weight_batch, c->batch.weights, (size_t)c->cfg.batch_size));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int mz_replay_priorities(mz_ctx *c, int64_t key0, int n, uint32_t *q_pos, uint32_t *q_game) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!q_pos || !q_game))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(read_counters(c));
+    int64_t played = c->h_counters[0], have = played < c->ring.capacity ? played : c->ring.capacity, first = played - have + 1;
+    if (key0 < first || key0 + n - 1 > played) return fail(c, MZ_E_ARG, "keys not in the buffer");
+    const size_t Tm = (size_t)c->M.P.Tmax;
+    for (int j = 0; j < n; j++) {
+        const int64_t pos = (key0 + j - 1) % c->ring.capacity;
+        MZ_CUDA(c, cudaMemcpyAsync(q_pos + (size_t)j * Tm, c->ring.q_pos + (size_t)pos * Tm, Tm * 4, cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaMemcpyAsync(q_game + j, c->ring.q_game + pos, 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
 static int upload_batch(mz_ctx *c, int B, const float *obs, const float *act, const float *val, const float *rew, const float *pol, const float *gs) {
     if (B < 1 || !obs || !act || !val || !rew || !pol || !gs) return fail(c, MZ_E_ARG, "bad batch");
     MZ_TRY(alloc_batch(c, B));
@@ -783,6 +827,11 @@ static int upload_batch(mz_ctx *c, int B, const float *obs, const float *act, co
     MZ_CUDA(c, cudaMemcpyAsync(c->batch.rewards, rew, b * K1 * 4, cudaMemcpyHostToDevice, c->stream));
     MZ_CUDA(c, cudaMemcpyAsync(c->batch.policies, pol, b * K1 * P.A * 4, cudaMemcpyHostToDevice, c->stream));
     MZ_CUDA(c, cudaMemcpyAsync(c->batch.gscale, gs, b * 4, cudaMemcpyHostToDevice, c->stream));
+    if (c->cfg.per) {   // caller-supplied batches carry no importance weights unless mz_learn_gradients_w provides them: weight_batch = 1
+        std::vector<float> ones(b, 1.0f);
+        MZ_CUDA(c, cudaMemcpyAsync(c->batch.weights, ones.data(), b * 4, cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     return MZ_OK;
 }
 int mz_learn_forward(mz_ctx *c, int B, const float *obs_batch, const float *action_batch, const float *value_batch, const float *reward_batch,
@@ -807,9 +856,15 @@ int mz_learn_step_batch(mz_ctx *c, int64_t t, int grad_mode, int B, const float 
 // gradients of one batch without an update (parity entry point): grad in the reference blob order
 int mz_learn_gradients(mz_ctx *c, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
                        const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses) {
+    return mz_learn_gradients_w(c, grad_mode, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale, nullptr, grad, losses);
+}
+int mz_learn_gradients_w(mz_ctx *c, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
+                         const float *reward_batch, const float *policy_batch, const float *gscale, const float *weight_batch, float *grad, float *losses) {
     MZ_CHECK_CTX(c);
     if (!losses || !grad) return fail(c, MZ_E_ARG, "bad arguments");
+    if (weight_batch && !c->cfg.per) return fail(c, MZ_E_STATE, "importance weights need conf.PER = true");
     MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
+    if (weight_batch) MZ_CUDA(c, cudaMemcpyAsync(c->batch.weights, weight_batch, (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
     MZ_TRY(launch_learn_forward(c, B, grad_mode));
     const int n = c->M.P.total_floats;
     if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
@@ -826,6 +881,7 @@ int mz_learn_step(mz_ctx *c, int64_t t, int grad_mode, float *losses) {
     MZ_TRY(gather_batch(c, (uint64_t)t));
     MZ_TRY(launch_learn_forward(c, c->cfg.batch_size, grad_mode));
     MZ_TRY(launch_update(c, t, grad_mode));
+    MZ_TRY(launch_per_update(c, c->cfg.batch_size));
     return finish_losses(c, c->cfg.batch_size, losses);
 }
 // n consecutive learning! iterations (steps t0 .. t0+n-1) without a host round trip in between: the replay gather of
@@ -839,9 +895,10 @@ int mz_learn_steps(mz_ctx *c, int64_t t0, int n, int grad_mode, float *losses) {
     MZ_TRY(read_counters(c));
     if (c->h_counters[0] < 1) return fail(c, MZ_E_STATE, "replay buffer is empty (learning! waits for num_played_games >= 1, Learning.jl:311)");
     for (int i = 0; i < n; i++) {
-        { launch_scope ls(c, 2); mz_k_replay_gather<<<B, 64, 0, c->stream>>>(c->M.P, c->ring, (uint64_t)(t0 + i), B, c->batch); }
+        MZ_TRY(launch_gather(c, (uint64_t)(t0 + i), B));
         MZ_TRY(launch_learn_forward(c, B, grad_mode));
         MZ_TRY(launch_update(c, t0 + i, grad_mode));
+        MZ_TRY(launch_per_update(c, B));
     }
     return finish_losses(c, B, losses);
 }

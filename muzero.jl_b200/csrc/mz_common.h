@@ -150,7 +150,8 @@ struct mz_params {
     float act_plane_play[MZ_MAX_A + 1];        // Float32(Float64(a)/A)      (src/SelfPlay.jl:8-9)
     float act_plane_learn[MZ_MAX_A + 1];       // Float32(a) / Float32(A)    (src/Learning.jl:294)
     float disc_pow[72];                        // conf.discount^i as Julia computes Float32^Int
-    int32_t n_layers, total_floats, n_params, pad2_;
+    int32_t n_layers, total_floats, n_params, per;   // per: conf.PER
+    int32_t per_alpha, pad3_[3];
     mz_net nets[3];
     mz_layer layers[MZ_MAX_LAYERS];
     // tensor-core (MZ_NN_BF16_TC) weight image: per layer a [rows8(out) x 64] bf16 tile in the UMMA K-major
@@ -517,6 +518,17 @@ MZ_HD int mz_select_action_counts(const mz_params &P, const int32_t *visit_count
     float draw = mz_u32_to_unit(r.x), cp = d[0]; int i = 0;
     while (cp <= draw && i < n - 1) { i++; cp = cp + d[i]; }
     return acts[i];
+}
+
+// Prioritised replay (conf.PER, repaired specification: DESIGN.md / oracle/mz_oracle.c): priority |root value - target value|^alpha
+// (Float32 ^ Int as Julia evaluates it for alpha <= 3) in fixed point, q = max(1, round(p * 2^16)): integer sums are exact, so the
+// device prefix scan and the oracle's sequential sums agree bit for bit.
+MZ_HD float mz_pow_int(float x, int i) { return i == 0 ? 1.0f : i == 1 ? x : i == 2 ? x * x : x * x * x; }
+MZ_HD uint32_t mz_per_quantise(float p) {
+    float s = p * 65536.0f;
+    if (!(s >= 1.0f)) return 1u;
+    if (s > 4.0e9f) return 4000000000u;
+    return (uint32_t)llrintf(s);
 }
 
 // compute_target_value (src/ReplayBuffer.jl:5-20), Q17; 1-based index.

@@ -43,6 +43,7 @@ inline void default_config(mz_config *c) {   // games/tictactoe/params.jl:2-29, 
     c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
     c->num_slots = 4096; c->nn_mode = MZ_NN_FP32_EXACT;
+    c->per = 0; c->per_alpha = 1;
     c->net_type = MZ_NET_FEEDFORWARD; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
@@ -53,6 +54,8 @@ inline const char *validate(const mz_config &c) {
     if (c.game == MZ_GAME_TICTACTOE && (c.W != 3 || c.H != 3 || c.A != 9)) return "TicTacToe needs observation_shape (3,3,3) and 9 actions";
     if (c.game == MZ_GAME_CONNECT && (c.A != c.H || (c.W + 1) * c.H > 64)) return "Connect needs A == H columns and (W+1)*H <= 64";
     if (c.net_type != MZ_NET_FEEDFORWARD && c.net_type != MZ_NET_RESNET) return "unknown net_type";
+    if (c.per && (c.per_alpha < 0 || c.per_alpha > 3)) return "PER_alpha must be in 0..3";
+    if (c.per && c.net_type != MZ_NET_FEEDFORWARD) return "PER belongs to the learner, which is implemented for the FeedForwardHP networks";
     if (c.net_type == MZ_NET_FEEDFORWARD && c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
     if (c.num_players < 1 || c.num_players > 2) return "1 or 2 players";
     if (c.num_iters < 1 || c.num_iters > 1000) return "num_iters must be in 1..1000";
@@ -112,7 +115,7 @@ inline const char *build_model(const mz_config &c, model &M) {
     P.tie_mode = c.tie_mode; P.pb_c_base = c.pb_c_base; P.intermediate_rewards = c.intermediate_rewards;
     P.batch_size = c.batch_size;
     P.pb_c_init = c.pb_c_init; P.discount = c.discount; P.dirichlet_alpha = c.dirichlet_alpha; P.exploration_eps = c.exploration_eps;
-    P.seed = c.seed;
+    P.seed = c.seed; P.per = c.per ? 1 : 0; P.per_alpha = c.per_alpha;
     for (int i = 0; i < MZ_MAX_A; i++) P.order[i] = c.child_order[i];
     for (int a = 0; a <= c.A; a++) {
         P.act_plane_play[a] = (float)((double)a / (double)c.A);   // SelfPlay.jl:8-9: Int/Int -> Float64, stored Float32

@@ -44,6 +44,8 @@ struct mz_ring {           // device replay buffer: key k lives at (k-1) % capac
     int64_t capacity;
     int64_t *game_id; int32_t *T;
     uint64_t *h_p1, *h_p2; int32_t *h_action; float *h_reward; uint8_t *h_to_play; float *h_cv; float *h_rv;
+    uint32_t *q_pos, *q_game;             // conf.PER: history.priorities [R][Tmax], history.game_priority [R] (fixed point)
+    unsigned long long *prefix, *upd;     // inclusive prefix sums of q_game in key order [R]; update_priorities! scratch [R][Tmax]
     float *h_rrv; uint8_t *reanalysed;   // GameHistory.reanalysed_predicted_root_values (Constructors.jl:13): [R][Tmax] + "is not nothing" flag per game
     // counters (device): [0] num_played_games, [1] num_played_steps, [2] total_samples, [3] next game id to hand out,
     // [4] end game id (exclusive), [5] active slots after the last refill
@@ -344,6 +346,62 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
     }
 }
 
+// Initial priorities of one stored game (save_game, ReplayBuffer.jl:136-145): |root_value - compute_target_value|^alpha per
+// position, game priority = their maximum.
+__device__ __forceinline__ void mz_per_init_game(const mz_params &P, const mz_ring &r, int64_t pos) {
+    const int T = r.T[pos];
+    const float *rew = r.h_reward + (size_t)pos * P.Tmax, *rv = r.h_rv + (size_t)pos * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)pos * P.Tmax;
+    uint32_t mx = 0;
+    for (int i = 1; i <= P.Tmax; i++) {
+        uint32_t q = 0;
+        if (i <= T) { q = mz_per_quantise(mz_pow_int(fabsf(rv[i - 1] - mz_target_value(P, T, rew, tp, rv, i)), P.per_alpha)); mx = q > mx ? q : mx; }
+        r.q_pos[(size_t)pos * P.Tmax + i - 1] = q;
+    }
+    r.q_game[pos] = mx;
+}
+__global__ void mz_k_per_init(const __grid_constant__ mz_params P, mz_ring r, int64_t key0, int n) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) mz_per_init_game(P, r, (key0 + j - 1) % r.capacity);
+}
+// Inclusive prefix sums of the game priorities in ascending key order (single CTA; integer sums: exact and order independent).
+// counters[6] = their total.
+__global__ void __launch_bounds__(1024) mz_k_per_scan(const __grid_constant__ mz_params P, mz_ring r) {
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    const int64_t played = r.counters[0], n = played < r.capacity ? played : r.capacity, first_key = played - n + 1;
+    const int64_t per = (n + 1023) / 1024, lo = (int64_t)tid * per, hi = lo + per < n ? lo + per : n;
+    unsigned long long s = 0;
+    for (int64_t i = lo; i < hi; i++) s += r.q_game[(first_key + i - 1) % r.capacity];
+    part[tid] = s; __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) { unsigned long long t = tid >= off ? part[tid - off] : 0ull; __syncthreads(); part[tid] += t; __syncthreads(); }
+    unsigned long long run = tid ? part[tid - 1] : 0ull;
+    for (int64_t i = lo; i < hi; i++) { run += r.q_game[(first_key + i - 1) % r.capacity]; r.prefix[i] = run; }
+    if (tid == 1023) r.counters[6] = (int64_t)part[1023];
+}
+// update_priorities! (ReplayBuffer.jl:168-183, repaired bounds; Learning.jl:400-404): rows k = 0 .. min(K, T - pos) of
+// |predicted_values - target_values|^alpha go to positions pos + k.  Batch elements apply in order (the last one wins where they
+// overlap): phase 1 marks every slot with the largest (b + 1, q) by a 64-bit atomicMax, phase 2 lets the winner write, phase 3
+// recomputes the game priorities.
+__global__ void mz_k_per_update(const __grid_constant__ mz_params P, mz_ring r, int B, const int32_t *index, const float *pv, const float *tv, int phase) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, K1 = P.K + 1;
+    if (i >= B * K1) return;
+    const int b = i / K1, k = i % K1;
+    const int64_t key = index[2 * b], played = r.counters[0], n = played < r.capacity ? played : r.capacity;
+    if (key < played - n + 1 || key > played) return;                       // the game has left the buffer (:172)
+    const int64_t pos = (key - 1) % r.capacity;
+    const int T = r.T[pos], p = index[2 * b + 1];
+    if (phase == 2) {
+        if (k == 0) { uint32_t mx = 0; for (int t = 0; t < T; t++) { uint32_t q = r.q_pos[(size_t)pos * P.Tmax + t]; mx = q > mx ? q : mx; } r.q_game[pos] = mx; }
+        return;
+    }
+    if (p + k > T) return;
+    const size_t slot = (size_t)pos * P.Tmax + p + k - 1;
+    const uint32_t q = mz_per_quantise(mz_pow_int(fabsf(pv[(size_t)b * K1 + k] - tv[(size_t)b * K1 + k]), P.per_alpha));
+    const unsigned long long mine = ((unsigned long long)(b + 1) << 32) | q;
+    if (phase == 0) atomicMax(&r.upd[slot], mine);
+    else if (r.upd[slot] == mine) { r.q_pos[slot] = q; r.upd[slot] = 0ull; }
+}
+
 // save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
 __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
@@ -381,6 +439,7 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
             }
             atomicAdd((unsigned long long *)&add_steps, (unsigned long long)T);
             atomicAdd((unsigned long long *)&add_samples, (unsigned long long)T);
+            if (P.per) mz_per_init_game(P, r, pos);                         // initial priorities (:136-145)
         }
         if (fre) {
             int64_t id = next_game + free_rank;

@@ -11,6 +11,7 @@ struct mz_batch {   // get_batch's tuple (ReplayBuffer.jl:216), device arrays
     float *rewards;   // [B][K+1]
     float *policies;  // [B][K+1][A]
     float *gscale;    // [B]
+    float *weights;   // [B] importance-sampling weights (conf.PER; ReplayBuffer.jl:213-215), else unused
 };
 
 // One CTA per batch element.  Thread 0 draws (game, position) (sample_n_games :102-104, sample_position :80;
@@ -25,10 +26,25 @@ __global__ void __launch_bounds__(64) mz_k_replay_gather(const __grid_constant__
         int64_t n_games = played < r.capacity ? played : r.capacity;
         int64_t first_key = played - n_games + 1;
         mz_u4 q = mz_philox(P.seed, MZ_STREAM_REPLAY, (uint32_t)step, (uint32_t)b, 0, 0);
-        int64_t gi = (int64_t)mz_u32_below(q.x, (uint32_t)n_games);
-        int64_t key = first_key + gi, ring = (key - 1) % r.capacity;
-        int T = r.T[ring];
-        int pos = 1 + (int)mz_u32_below(q.y, (uint32_t)T);
+        int64_t gi; int pos, T; int64_t key, ring;
+        if (P.per) {   // sample_n_games :90-100 / sample_position :75-79 by priority: inverse CDF over the exact integer prefix sums
+            const unsigned long long Q = (unsigned long long)r.counters[6];
+            const unsigned long long t = __umul64hi(((unsigned long long)q.x << 32) | q.z, Q);
+            int64_t lo = 0, hi = n_games - 1;
+            while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (r.prefix[mid] > t) hi = mid; else lo = mid + 1; }
+            gi = lo; key = first_key + gi; ring = (key - 1) % r.capacity; T = r.T[ring];
+            const uint32_t *qp = r.q_pos + (size_t)ring * P.Tmax;
+            unsigned long long Qg = 0; for (int i = 0; i < T; i++) Qg += qp[i];
+            const unsigned long long t2 = __umul64hi(((unsigned long long)q.y << 32) | q.w, Qg);
+            unsigned long long a2 = 0;
+            for (pos = 1; pos < T; pos++) { a2 += qp[pos - 1]; if (a2 > t2) break; }
+            const float game_prob = (float)((double)r.q_game[ring] / (double)Q), pos_prob = (float)((double)qp[pos - 1] / (double)Qg);
+            out.weights[b] = 1.0f / (((float)r.counters[2] * game_prob) * pos_prob);      // :213 (total_samples)
+        } else {
+            gi = (int64_t)mz_u32_below(q.x, (uint32_t)n_games);
+            key = first_key + gi; ring = (key - 1) % r.capacity; T = r.T[ring];
+            pos = 1 + (int)mz_u32_below(q.y, (uint32_t)T);
+        }
         s_pos = pos; s_T = T; s_ring = ring;
         out.index[2 * b] = (int32_t)key; out.index[2 * b + 1] = pos;
         const float *rew = r.h_reward + (size_t)ring * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)ring * P.Tmax;
@@ -53,6 +69,18 @@ __global__ void __launch_bounds__(64) mz_k_replay_gather(const __grid_constant__
         int k = i / P.A, a = i % P.A, ci = pos + k;
         out.policies[((size_t)b * K1 + k) * P.A + a] = ci < T ? r.h_cv[((size_t)ring * P.Tmax + ci - 1) * P.A + a] : 1.0f / (float)P.A;
     }
+}
+
+// weight_batch ./= maximum(weight_batch) (ReplayBuffer.jl:215); the maximum is order independent
+__global__ void __launch_bounds__(1024) mz_k_per_normalise(int B, float *w) {
+    __shared__ float red[1024];
+    const int tid = threadIdx.x;
+    float m = 0.0f;
+    for (int i = tid; i < B; i += 1024) m = fmaxf(m, w[i]);
+    red[tid] = m; __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) { if (tid < s) red[tid] = fmaxf(red[tid], red[tid + s]); __syncthreads(); }
+    const float mx = red[0];
+    for (int i = tid; i < B; i += 1024) w[i] = w[i] / mx;
 }
 
 // K-step unroll forward for 32 samples per CTA (src/Learning.jl:347-370, Q19): row 0 = prediction(h0); for
@@ -133,7 +161,10 @@ __global__ void mz_k_loss_rows(const __grid_constant__ mz_params P, int B, mz_ba
         spol = spol + (-acc);
     }
     float gs = batch.gscale[b];
-    row_v[b] = sv / gs; row_r[b] = sr / (double)gs; row_p[b] = spol; row_invg[b] = 1.0f / gs;
+    if (P.per && batch.weights) {   // (sum ./ gradient_scale) .* weight_batch (Learning.jl:272-281)
+        const float w = batch.weights[b];
+        row_v[b] = (sv / gs) * w; row_r[b] = (sr / (double)gs) * (double)w; row_p[b] = spol; row_invg[b] = (1.0f / gs) * w;
+    } else { row_v[b] = sv / gs; row_r[b] = sr / (double)gs; row_p[b] = spol; row_invg[b] = 1.0f / gs; }
 }
 // deterministic single-CTA tree reductions: out[0] = sum row_v, out[1] = sum row_p, out[2] = sum row_invg, out[3] = sum row_r,
 // out[4..6] = sum(theta^2) per net (double accumulation; compared against the oracle with a stated tolerance)

@@ -207,7 +207,7 @@ __device__ __forceinline__ void mz_bwd_loss_grad(const mz_params &P, const mz_bp
     } else {
         float d = 0.0f;
         if (ok) {
-            const float gs = a.f.batch.gscale[g];
+            const float gs = (P.per && a.f.batch.weights) ? a.f.batch.gscale[g] / a.f.batch.weights[g] : a.f.batch.gscale[g];   // (sum / g) * w
             for (int rr = merge0 ? 0 : row_idx; rr <= row_idx; rr++) {
                 const float y = pre == MZ_PRE_VALUE ? a.f.pred_values[g * K1 + rr] : a.f.pred_rewards[g * K1 + rr];
                 const float t = pre == MZ_PRE_VALUE ? a.f.batch.values[g * K1 + rr] : a.f.batch.rewards[g * K1 + rr];
@@ -242,7 +242,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_bptt(const __grid_const
     // mean_i(1/g_i) over the whole batch (Q21's broadcast couples every sample's policy term to it): same fixed-order sum in every CTA
     {
         double s = 0.0;
-        for (int i = tid; i < a.f.B; i += MZ_THREADS) s += 1.0 / (double)a.f.batch.gscale[i];
+        const bool per = P.per && a.f.batch.weights;
+        for (int i = tid; i < a.f.B; i += MZ_THREADS) s += (per ? (double)a.f.batch.weights[i] : 1.0) / (double)a.f.batch.gscale[i];
         s_red[tid] = s;
     }
     // layers without any data gradient: their partial sums are zero

@@ -23,6 +23,7 @@ mutable struct MzConfig
     hidden_state_size::Int32; reward_activation_tanh::Int32
     num_slots::Int32; nn_mode::Int32
     net_type::Int32; rn_num_blocks::Int32; rn_num_filters::Int32; rn_kernel::Int32; rn_first_head_filters::Int32; rn_second_head_filters::Int32
+    per::Int32; per_alpha::Int32
     MzConfig() = new()
 end
 
@@ -51,6 +52,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
     c.replay_buffer_size = max(conf.replay_buffer_size, num_slots); c.pb_c_base = conf.pb_c_base
     c.intermediate_rewards = conf.intermediate_rewards; c.pb_c_init = conf.pb_c_init; c.discount = conf.discount
     c.dirichlet_alpha = conf.dirichlet_α; c.exploration_eps = conf.exploration_ϵ; c.seed = conf.seed
+    c.per = conf.PER; c.per_alpha = conf.PER_alpha
     order = zeros(Int32, MZ_MAX_A)
     ccall((:mz_julia_dict_order, LIB), Cint, (Cint, Ptr{Int32}), c.A, order)   # or: collect(keys(Dict(a => 0 for a in conf.action_space)))
     c.child_order = Tuple(order)
