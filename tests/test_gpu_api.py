@@ -108,3 +108,40 @@ def test_contexts_with_different_sizes_coexist(mz):
     l = big.learn_steps(1, 2, capi.GRAD_BPTT)
     assert np.all(np.isfinite(l))
     big.close(); small.close()
+
+
+def test_new_entry_points_error_behaviour(mz):
+    """ABI error classes of the ResNet / PER / reanalyse / checkpoint entry points: bad configurations are refused at mz_create
+    with a message, misuse returns MZ_E_* and never aborts."""
+    import numpy as np
+    capi = mz.capi
+    for bad, frag in ((capi.resnet_config(nn_mode=capi.NN_FP32_EXACT), "tensor cores"), (capi.resnet_config(rn_num_filters=20), "rn_num_filters"),
+                      (capi.resnet_config(rn_kernel=5), "rn_kernel"), (capi.default_config(per=1, per_alpha=7), "PER_alpha"),
+                      (capi.resnet_config(per=1), "PER"), (capi.default_config(net_type=9), "net_type")):
+        with pytest.raises(capi.MuZeroB200Error) as e:
+            capi.Context(bad)
+        assert frag in str(e.value), str(e.value)
+    ctx = capi.Context(capi.default_config(num_slots=32, replay_buffer_size=64))
+    ctx.init_weights(1)
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.reanalyse(key0=1, n=4)                    # empty buffer
+    ctx.self_play(0, 40, 1.0)
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.reanalyse(key0=30, n=40)                  # keys 30..69 but only 1..40 exist
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.get_batch_per(1)                          # conf.PER is false
+    ck = ctx.checkpoint()
+    ck["adam_m"] = ck["adam_m"][:-1]
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.restore(ck)
+    vc, rv = ctx.run_mcts(np.zeros((0, 63), np.float32), np.zeros(0, np.uint32), np.zeros(0, np.int32), False, np.zeros(0, np.uint64), np.zeros(0, np.int32))
+    assert vc.shape == (0, 9)
+    ctx.close()
+    rn = capi.Context(capi.resnet_config(num_slots=8, replay_buffer_size=8, num_iters=4))
+    rn.init_weights(1)
+    assert rn.representation(np.zeros((0, 63), np.float32)).shape == (0, 576)
+    with pytest.raises(capi.MuZeroB200Error):
+        rn.reanalyse(key0=1, n=1)
+    with pytest.raises(capi.MuZeroB200Error):
+        rn.checkpoint()
+    rn.close()
