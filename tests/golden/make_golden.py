@@ -45,6 +45,31 @@ def main():
     np.savez_compressed(os.path.join(HERE, "selfplay_learn.npz"), **{"hist_" + k: hist[k] for k in common.HIST_KEYS},
                         **{"batch_" + k: batch[k] for k in common.BATCH_KEYS}, pred_values=pv, pred_rewards=pr, pred_policies=pp,
                         losses=losses, losses_step1=l1, losses_step2=l2, weights_after_2=w, sims=np.int64(hist["sims"]))
+    # 3. paths added later: BPTT gradient, prioritised replay, ResNet networks (Float32 and bf16 emulation) and a ResNet search
+    cfg = O.default_config(batch_size=24, per=1, intermediate_rewards=1)
+    blob = O.init_weights(cfg, 77)
+    hist = O.self_play(cfg, blob, 0, 40, 1.0, 2)
+    q_pos, q_game = O.per_priorities(cfg, hist)
+    pb = O.get_batch_per(cfg, hist, q_pos, q_game, 3)
+    _, grad = O.learn_gradients_w(cfg, blob, pb, fwd64=False)
+    pv, _, _, pl = O.learn_forward_w(cfg, blob, pb)
+    q2, g2 = q_pos.copy(), q_game.copy()
+    O.per_update(cfg, hist, q2, g2, pb["index"], pv, pb["values"])
+    rcfg = O.resnet_config(num_iters=20, exploration_eps=0.0)
+    rblob = O.init_weights(rcfg, 5)
+    st, legal, tp = common.random_stacked(rcfg, 12, seed=31)
+    rh = np.stack([O.representation(rcfg, rblob, x) for x in st])
+    O.set_bf16(True)
+    try:
+        rh16 = np.stack([O.representation(rcfg, rblob, x) for x in st])
+        rv16, rp16 = zip(*[O.prediction(rcfg, rblob, x) for x in rh16])
+        rvc = np.stack([O.run_mcts(rcfg, rblob, st[i], int(legal[i]), int(tp[i]), False, 500 + i, 1)[0] for i in range(12)])
+    finally:
+        O.set_bf16(False)
+    np.savez_compressed(os.path.join(HERE, "bptt_per_resnet.npz"), **{"hist_" + k: hist[k] for k in common.HIST_KEYS}, q_pos=q_pos, q_game=q_game,
+                        **{"pb_" + k: pb[k] for k in common.BATCH_KEYS + ("weights",)}, grad=grad.astype(np.float32), losses=pl, q_pos_after=q2,
+                        q_game_after=g2, rn_stacked=st, rn_legal=legal, rn_to_play=tp, rn_hidden_f32=rh, rn_hidden_bf16=rh16,
+                        rn_value_bf16=np.array(rv16, np.float32), rn_policy_bf16=np.stack(rp16), rn_visit_counts_bf16=rvc)
     print("golden fixtures written")
 
 

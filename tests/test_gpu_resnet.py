@@ -106,3 +106,33 @@ def test_resnet_learner_is_refused(capi):
     with pytest.raises(capi.MuZeroB200Error):
         ctx.learn_step(1)
     ctx.close()
+
+
+def test_golden_resnet_and_per_fixture(capi):
+    """The committed fixture tests/golden/bptt_per_resnet.npz against the CUDA path: prioritised batch and priority update bit-exact,
+    BPTT gradient and ResNet outputs within their tolerances, ResNet visit counts."""
+    import os
+    g = np.load(os.path.join(common.ROOT, "tests", "golden", "bptt_per_resnet.npz"))
+    ctx = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=64, batch_size=24, per=1, intermediate_rewards=1))
+    ctx.init_weights(77)
+    ctx.history_import({k: g["hist_" + k] for k in common.HIST_KEYS})
+    q_pos, q_game = ctx.replay_priorities()
+    assert np.array_equal(q_pos, g["q_pos"]) and np.array_equal(q_game, g["q_game"])
+    pb = ctx.get_batch_per(3)
+    for k in common.BATCH_KEYS + ("weights",):
+        assert np.array_equal(pb[k], g["pb_" + k]), k
+    grad, losses = ctx.learn_gradients(pb, capi.GRAD_BPTT)
+    assert np.max(np.abs(grad - g["grad"])) <= 2e-5 * np.max(np.abs(g["grad"])) and np.allclose(losses, g["losses"], rtol=2e-6)
+    ctx.learn_step(3, capi.GRAD_REFERENCE_L2)
+    q2, g2 = ctx.replay_priorities()
+    assert np.array_equal(q2, g["q_pos_after"]) and np.array_equal(g2, g["q_game_after"])
+    ctx.close()
+    rctx, ocfg = make(capi, num_iters=20, exploration_eps=0.0)
+    rctx.init_weights(5)
+    h = rctx.representation(g["rn_stacked"])
+    assert np.max(np.abs(h - g["rn_hidden_bf16"])) < RN_ATOL * max(1.0, float(np.max(np.abs(g["rn_hidden_bf16"]))))
+    v, p = rctx.prediction(g["rn_hidden_bf16"])
+    assert np.max(np.abs(v - g["rn_value_bf16"])) < RN_ATOL and np.max(np.abs(p - g["rn_policy_bf16"])) < RN_ATOL
+    vc, rv = rctx.run_mcts(g["rn_stacked"], g["rn_legal"], g["rn_to_play"], False, np.arange(12, dtype=np.uint64) + 500, np.ones(12, np.int32))
+    assert (vc == g["rn_visit_counts_bf16"]).all(1).sum() >= 10
+    rctx.close()

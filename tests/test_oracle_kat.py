@@ -317,3 +317,29 @@ def test_bptt_learn_step_uses_the_gradient():
     b2 = blob.copy(); m2 = np.zeros_like(blob); v2 = np.zeros_like(blob)
     O.adam_apply(b2, m2, v2, g.astype(f32), 1)
     assert np.array_equal(b1, b2) and np.array_equal(m1, m2) and np.array_equal(v1, v2)
+
+
+def test_golden_bptt_per_resnet_fixture_is_reproduced():
+    """tests/golden/bptt_per_resnet.npz (generator committed) freezes the oracle's BPTT gradient, prioritised batch, priority update
+    and ResNet outputs: any drift of the oracle shows up here, on the CPU."""
+    import os
+    import common
+    g = np.load(os.path.join(common.ROOT, "tests", "golden", "bptt_per_resnet.npz"))
+    cfg = O.default_config(batch_size=24, per=1, intermediate_rewards=1)
+    blob = O.init_weights(cfg, 77)
+    hist = {k: g["hist_" + k] for k in common.HIST_KEYS}
+    q_pos, q_game = O.per_priorities(cfg, hist)
+    assert np.array_equal(q_pos, g["q_pos"]) and np.array_equal(q_game, g["q_game"])
+    pb = O.get_batch_per(cfg, hist, q_pos, q_game, 3)
+    for k in common.BATCH_KEYS + ("weights",):
+        assert np.array_equal(pb[k], g["pb_" + k]), k
+    _, grad = O.learn_gradients_w(cfg, blob, pb, fwd64=False)
+    assert np.array_equal(grad.astype(np.float32), g["grad"])
+    rcfg = O.resnet_config(num_iters=20, exploration_eps=0.0)
+    rblob = O.init_weights(rcfg, 5)
+    assert np.array_equal(np.stack([O.representation(rcfg, rblob, x) for x in g["rn_stacked"]]), g["rn_hidden_f32"])
+    O.set_bf16(True)
+    try:
+        assert np.array_equal(np.stack([O.representation(rcfg, rblob, x) for x in g["rn_stacked"][:4]]), g["rn_hidden_bf16"][:4])
+    finally:
+        O.set_bf16(False)
