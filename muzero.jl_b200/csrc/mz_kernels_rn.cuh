@@ -147,6 +147,45 @@ __device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, const m
                  ::"r"(X.sp.wring + slot * (uint32_t)X.slot_bytes), "l"(X.image + off), "r"((uint32_t)bytes), "r"(bar) : "memory");
 }
 
+struct mz_rn_tile_ctx { uint32_t taddr, pT, pE, dst, skp, r7x; unsigned char *pool; unsigned long long rv2; bool store; };
+template <bool RELU, bool SKIP, bool PLANE>
+__device__ __forceinline__ void mz_rn_tile_rows(const mz_rn_tile_ctx &c) {
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        uint32_t v[32];
+        mz_rn_ld32(c.taddr + 32u * half, v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int c8 = 4 * half + q;
+            const float4 t0 = mz_lds128(c.pT + c8 * 32), t1 = mz_lds128(c.pT + c8 * 32 + 16);
+            unsigned long long T[4] = {mz_f2pack(t0.x, t0.y), mz_f2pack(t0.z, t0.w), mz_f2pack(t1.x, t1.y), mz_f2pack(t1.z, t1.w)};
+            if (PLANE) {   // + action plane * (w_plane * s): y = acc + fmaf(plane, E, T)   (the BatchNorm scale is folded into the weights)
+                const float4 e0 = mz_lds128(c.pE + c8 * 32), e1 = mz_lds128(c.pE + c8 * 32 + 16);
+                T[0] = mz_fma2(c.rv2, mz_f2pack(e0.x, e0.y), T[0]); T[1] = mz_fma2(c.rv2, mz_f2pack(e0.z, e0.w), T[1]);
+                T[2] = mz_fma2(c.rv2, mz_f2pack(e1.x, e1.y), T[2]); T[3] = mz_fma2(c.rv2, mz_f2pack(e1.z, e1.w), T[3]);
+            }
+            unsigned long long y[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) y[i] = mz_add2(mz_f2pack(__uint_as_float(v[8 * q + 2 * i]), __uint_as_float(v[8 * q + 2 * i + 1])), T[i]);
+            const uint32_t chunk = (uint32_t)(c8 << 4) ^ c.r7x;
+            if (SKIP) {
+                const uint4 k = mz_lds128u(c.skp + chunk);
+                y[0] = mz_add2(y[0], mz_f2pack(mz_bf16lo(k.x), mz_bf16hi(k.x))); y[1] = mz_add2(y[1], mz_f2pack(mz_bf16lo(k.y), mz_bf16hi(k.y)));
+                y[2] = mz_add2(y[2], mz_f2pack(mz_bf16lo(k.z), mz_bf16hi(k.z))); y[3] = mz_add2(y[3], mz_f2pack(mz_bf16lo(k.w), mz_bf16hi(k.w)));
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                float a0, a1; mz_f2unpack(y[i], a0, a1);
+                o[i] = RELU ? mz_pack_bf16_relu(a0, a1) : mz_pack_bf16(a0, a1);
+            }
+            const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
+            if (c.store) mz_sts128u(c.dst + chunk, ov);
+            if (c.pool) *reinterpret_cast<uint4 *>(c.pool + c8 * 16) = ov;
+        }
+    }
+}
+
 // epilogue of one job for one warpgroup thread (row = TMEM lane)
 __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_params &R, const mz_rn_job J, uint32_t wslot, int wgt) {
     const int warp4 = wgt >> 5, lane = wgt & 31, row = 32 * warp4 + lane;
@@ -165,41 +204,23 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
         unsigned char *pool = nullptr;
         if ((J.flags & MZ_RN_F_POOL) && valid)
             pool = reinterpret_cast<unsigned char *>(X.sp.tree_base[tree]) + R.hidden_off_bytes + (size_t)X.pool_slot * R.node_bytes + (size_t)cell * 128;
-        const bool relu = jact == MZ_ACT_RELU, plane = (jflags & MZ_RN_F_PLANE) != 0;
-        const unsigned long long rv2 = mz_f2pack(rowval, rowval);
-#pragma unroll 1
-        for (int half = 0; half < 2; half++) {
-            uint32_t v[32];
-            mz_rn_ld32(taddr + 32u * half, v);
+        // the inner loop is compiled per (relu, skip, plane) combination: no uniform branches or per-element selects inside it; rows
+        // that are not valid (the two pad rows of a tile, idle trees) are computed like the others and zeroed afterwards
+        const mz_rn_tile_ctx tc{taddr, pT, pE, dst, skp, (uint32_t)((row & 7) << 4), pool, mz_f2pack(rowval, rowval), !trees || row < MZ_RN_OUT_ROWS};
+        const int combo = (jact == MZ_ACT_RELU ? 4 : 0) | (skp ? 2 : 0) | ((jflags & MZ_RN_F_PLANE) ? 1 : 0);
+        switch (combo) {
+            case 4: mz_rn_tile_rows<true, false, false>(tc); break;      // ConvBN + relu, dense + relu
+            case 6: mz_rn_tile_rows<true, true, false>(tc); break;       // second convolution of a residual block
+            case 5: mz_rn_tile_rows<true, false, true>(tc); break;       // first dynamics convolution (action plane)
+            case 0: mz_rn_tile_rows<false, false, false>(tc); break;     // first dense layer of the policy head (no activation)
+            case 2: mz_rn_tile_rows<false, true, false>(tc); break;
+            case 1: mz_rn_tile_rows<false, false, true>(tc); break;
+            case 3: mz_rn_tile_rows<false, true, true>(tc); break;
+            default: mz_rn_tile_rows<true, true, true>(tc); break;
+        }
+        if (!valid && tc.store) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int c8 = 4 * half + q;
-                const float4 t0 = mz_lds128(pT + c8 * 32), t1 = mz_lds128(pT + c8 * 32 + 16);
-                unsigned long long T[4] = {mz_f2pack(t0.x, t0.y), mz_f2pack(t0.z, t0.w), mz_f2pack(t1.x, t1.y), mz_f2pack(t1.z, t1.w)};
-                if (plane) {   // + action plane * (w_plane * s): y = acc + fmaf(plane, E, T)   (the BatchNorm scale is folded into the weights)
-                    const float4 e0 = mz_lds128(pE + c8 * 32), e1 = mz_lds128(pE + c8 * 32 + 16);
-                    T[0] = mz_fma2(rv2, mz_f2pack(e0.x, e0.y), T[0]); T[1] = mz_fma2(rv2, mz_f2pack(e0.z, e0.w), T[1]);
-                    T[2] = mz_fma2(rv2, mz_f2pack(e1.x, e1.y), T[2]); T[3] = mz_fma2(rv2, mz_f2pack(e1.z, e1.w), T[3]);
-                }
-                unsigned long long y[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) y[i] = mz_add2(mz_f2pack(__uint_as_float(v[8 * q + 2 * i]), __uint_as_float(v[8 * q + 2 * i + 1])), T[i]);
-                const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) << 4);
-                if (skp) {
-                    const uint4 k = mz_lds128u(skp + chunk);
-                    y[0] = mz_add2(y[0], mz_f2pack(mz_bf16lo(k.x), mz_bf16hi(k.x))); y[1] = mz_add2(y[1], mz_f2pack(mz_bf16lo(k.y), mz_bf16hi(k.y)));
-                    y[2] = mz_add2(y[2], mz_f2pack(mz_bf16lo(k.z), mz_bf16hi(k.z))); y[3] = mz_add2(y[3], mz_f2pack(mz_bf16lo(k.w), mz_bf16hi(k.w)));
-                }
-                uint32_t o[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    float a0, a1; mz_f2unpack(y[i], a0, a1);
-                    o[i] = !valid ? 0u : relu ? mz_pack_bf16_relu(a0, a1) : mz_pack_bf16(a0, a1);
-                }
-                const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
-                if (!trees || row < MZ_RN_OUT_ROWS) mz_sts128u(dst + chunk, ov);
-                if (pool) *reinterpret_cast<uint4 *>(pool + c8 * 16) = ov;
-            }
+            for (int c8 = 0; c8 < 8; c8++) mz_sts128u(dst + (uint32_t)(c8 << 4), make_uint4(0u, 0u, 0u, 0u));
         }
     } else if (J.epi == MZ_RN_EPI_HEAD) {
         uint32_t v[16];
