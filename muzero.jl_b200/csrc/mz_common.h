@@ -213,7 +213,9 @@ struct mz_rn_job {
 struct mz_rn_step {
     int32_t w_off, w_bytes;                       // the step's block inside the global weight image
     uint8_t njobs, ntaps, tap, last;              // k x k convolutions: one step per tap, epilogue after the last
-    int8_t dx, dy; uint8_t accumulate, pad_;      // tap: A = copy of a_buf shifted by (dx, dy) cells
+    int8_t dx, dy; uint8_t accumulate;            // tap: A = copy of a_buf shifted by (dx, dy) cells
+    uint8_t rowlocal;                             // 1/2: every job is a (tree,cell)-tile job of warpgroup j on its own tile, so the warpgroups need not
+                                                  // meet after the step (1), except before a step that is not row-local / the end of a range (2)
     mz_rn_job jobs[MZ_RN_TILES];
 };
 struct mz_rn_params {

@@ -31,7 +31,7 @@ struct mz_rn_plan {
     uint32_t aux;                  // HV | HP (two K blocks) ; or the two scratch tiles of the tap-steps
     uint32_t wring;                // two weight slots
     unsigned char *tiles_ptr, *wring_ptr;
-    uint64_t *w_bar, *mma_bar, *scr_bar; uint32_t *tmem_slot;
+    uint64_t *w_bar, *mma_bar, *scr_bar, *e_bar; uint32_t *tmem_slot;
     float *out;                    // fp32 head outputs: V [4][64] | L [16][64] | R [4][64]
     float *plane; int32_t *pe, *dbl, *active; unsigned long long *tree_base;
     double *pbc0, *sqrtN; uint16_t *path;
@@ -49,7 +49,7 @@ __device__ __forceinline__ mz_rn_plan mz_rn_carve(unsigned char *raw, int slot_b
     p.tiles_ptr = c; p.tiles = mz_smem_u32(c); c += 8 * MZ_RN_TILE_BYTES;
     p.aux = mz_smem_u32(c); c += MZ_RN_AUX_BYTES;
     p.wring_ptr = c; p.wring = mz_smem_u32(c); c += 2 * (size_t)slot_bytes;
-    p.w_bar = (uint64_t *)c; p.mma_bar = p.w_bar + 2; p.scr_bar = p.w_bar + 6; p.tmem_slot = (uint32_t *)(c + 128); c += 256;
+    p.w_bar = (uint64_t *)c; p.mma_bar = p.w_bar + 2; p.scr_bar = p.w_bar + 6; p.e_bar = p.w_bar + 8; p.tmem_slot = (uint32_t *)(c + 128); c += 256;
     p.out = (float *)c; c += 24 * MZ_RN_OUT_ROWS * 4;
     p.tree_base = (unsigned long long *)c; c += MZ_RN_OUT_ROWS * 8;
     p.plane = (float *)c; c += MZ_RN_OUT_ROWS * 4; p.pe = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4; p.dbl = (int32_t *)c; c += MZ_RN_OUT_ROWS * 4;
@@ -130,6 +130,7 @@ struct mz_rn_exec {
     int pf;                 // step whose block is in (or on its way to) slot wq & 1, or -1
     uint32_t mq[4];         // commits seen per job barrier
     uint32_t sq[2];         // commits seen per scratch barrier
+    uint32_t eq0, eq1, ew0, ew1;  // per weight slot: row-local steps that released it through e_bar / releases thread 0 has waited for
     int pool_slot;          // hidden-state slot written by MZ_RN_F_POOL epilogues
     int W, H;
     int my_tree, my_cell;   // (tree, cell) of this thread's TMEM lane in its warpgroup's convolution tile
@@ -145,6 +146,11 @@ __device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, const m
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(X.sp.wring + slot * (uint32_t)X.slot_bytes), "l"(X.image + off), "r"((uint32_t)bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mz_rn_slot_free(mz_rn_exec &X, uint32_t sl) {
+    if (sl == 0) { while (X.ew0 < X.eq0) { mz_mbar_wait_u32(mz_smem_u32(&X.sp.e_bar[0]), X.ew0 & 1u); X.ew0++; } }
+    else { while (X.ew1 < X.eq1) { mz_mbar_wait_u32(mz_smem_u32(&X.sp.e_bar[1]), X.ew1 & 1u); X.ew1++; } }
 }
 
 struct mz_rn_tile_ctx { uint32_t taddr, pT, pE, dst, skp, r7x; unsigned char *pool; unsigned long long rv2; bool store; };
@@ -264,11 +270,13 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
         const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
         const uint32_t slot = X.wq & 1u;
         const int next = s + 1 < last ? s + 1 : next_first;
+        const int njobs = st->njobs, ntaps = st->ntaps, is_last = st->last, st_rowlocal = st->rowlocal;
         if (tid == 0) {
-            if (X.pf != s) mz_rn_issue_weights(X, R, s, slot);
-            if (next >= 0) mz_rn_issue_weights(X, R, next, slot ^ 1u);
+            // a slot last used by a row-local step is free once all four warpgroups have finished that step's epilogue (it reads the
+            // BatchNorm shifts from the slot): each of them arrives on e_bar[slot] after its own barrier
+            if (X.pf != s) { mz_rn_slot_free(X, slot); mz_rn_issue_weights(X, R, s, slot); }
+            if (next >= 0) { mz_rn_slot_free(X, slot ^ 1u); mz_rn_issue_weights(X, R, next, slot ^ 1u); }
         }
-        const int njobs = st->njobs, ntaps = st->ntaps, is_last = st->last;
         mz_mbar_wait_u32(mz_smem_u32(&X.sp.w_bar[slot]), (X.wq >> 1) & 1u);
         const uint32_t wslot = X.sp.wring + slot * (uint32_t)X.slot_bytes;
         MZ_RN_ST(0);
@@ -355,7 +363,14 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
         }
         mz_fence_proxy_async();
         mz_tc_fence_before();
-        __syncthreads();
+        if (st_rowlocal == 1 && s + 1 < last) {
+            // the next step reads only what this warpgroup wrote: meet inside the warpgroup, release the weight slot, run on
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+            if (wgt == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mz_smem_u32(&X.sp.e_bar[slot])) : "memory");
+            if (slot == 0) X.eq0++; else X.eq1++;
+        } else {
+            __syncthreads();
+        }
         mz_tc_fence_after();
         MZ_RN_ST(4);
         X.wq++; X.pf = next;
@@ -408,7 +423,7 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
     X.sp = mz_rn_carve(smem, R.slot_bytes, P.S, R.ntrees, R.n_steps - R.smem_first);
     X.steps = ta.steps; X.image = ta.image; X.slot_bytes = R.slot_bytes; X.wq = 0; X.pf = -1; X.pool_slot = 0; X.W = P.W; X.H = P.H;
     for (int j = 0; j < 4; j++) X.mq[j] = 0;
-    X.sq[0] = X.sq[1] = 0;
+    X.sq[0] = X.sq[1] = 0; X.eq0 = X.eq1 = X.ew0 = X.ew1 = 0;
     for (int h = 0; h < 2; h++) { const int row = (int)(threadIdx.x >> 3) + 64 * h; X.st_tl[h] = row < R.rows_valid ? row / R.cells : -1; X.st_cell[h] = row % R.cells; }
     { const int row = (int)(threadIdx.x & 127); X.my_tree = (int)(threadIdx.x >> 7) * R.tpt + row / R.cells; X.my_cell = row % R.cells; }
 #ifdef MZ_PHASE_TIMERS
@@ -420,6 +435,7 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
         for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.w_bar[i], 1);
         for (int i = 0; i < 4; i++) mz_mbar_init(&X.sp.mma_bar[i], 1);
         for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.scr_bar[i], 1);
+        for (int i = 0; i < 2; i++) mz_mbar_init(&X.sp.e_bar[i], MZ_RN_TILES);
         mz_fence_mbar_init();
     }
     __syncwarp();

@@ -200,6 +200,22 @@ inline const char *rn_build(const mz_config &c, const mz_params &P, rn_model &M)
     { const int fu[1] = {2 * nt + 1}, ib[1] = {MZ_RN_BUF_HV}, oi[1] = {MZ_RN_OUT_R}; B.dense_chains(2, 1, fu, ib, oi); }
     R.prog_dyn[1] = (int)M.steps.size();
     R.n_steps = (int)M.steps.size(); R.smem_first = R.prog_pred[0];
+    // row-local steps: single-tap convolutions whose job j is warpgroup j's own tile; inside a run of them the warpgroups run unsynchronised
+    {
+        auto rl = [&](int i) {
+            const mz_rn_step &s = M.steps[(size_t)i];
+            if (s.ntaps != 1 || s.njobs != MZ_RN_TILES || !s.last) return false;
+            for (int j = 0; j < s.njobs; j++) if (s.jobs[j].epi != MZ_RN_EPI_TILE || (s.jobs[j].flags & MZ_RN_F_TREES) || s.jobs[j].wg != j || s.jobs[j].acc != j) return false;
+            return true;
+        };
+        const int ends[3] = {R.prog_repr[1], R.prog_pred[1], R.prog_dyn[1]};
+        for (int i = 0; i < R.n_steps; i++) {
+            M.steps[(size_t)i].rowlocal = 0;
+            if (!rl(i)) continue;
+            const bool range_end = i + 1 == ends[0] || i + 1 == ends[1] || i + 1 == ends[2];
+            M.steps[(size_t)i].rowlocal = (!range_end && rl(i + 1)) ? 1 : 2;
+        }
+    }
     M.image_bytes = B.image_off;
     R.image_bytes = B.image_off;
     int slot = 0;

@@ -282,6 +282,20 @@ int hh_rn_program_info(const mz_config *c, int32_t *out /* [8]: n_steps, repr st
     for (const auto &s : M.steps) if (s.w_bytes > R.slot_bytes || s.w_off + s.w_bytes > R.image_bytes || s.njobs < 1 || s.njobs > MZ_RN_TILES) return -2;
     return 0;
 }
+// one line per step of the program (debugging aid; also pins the step count the kernels are timed with)
+int hh_rn_program_dump(const mz_config *c) {
+    mzh::model Mm; if (const char *e = mzh::build_model(*c, Mm)) { fprintf(stderr, "%s\n", e); return -1; }
+    mzh::rn_model M; if (const char *e = mzh::rn_build(*c, Mm.P, M)) { fprintf(stderr, "%s\n", e); return -1; }
+    const mz_rn_params &R = M.R;
+    printf("repr [%d,%d) pred [%d,%d) dyn [%d,%d) smem_first %d slot %d B\n", R.prog_repr[0], R.prog_repr[1], R.prog_pred[0], R.prog_pred[1], R.prog_dyn[0], R.prog_dyn[1], R.smem_first, R.slot_bytes);
+    for (size_t i = 0; i < M.steps.size(); i++) {
+        const mz_rn_step &s = M.steps[i];
+        printf("step %2zu w %6d B njobs %d taps %d/%d last %d :", i, s.w_bytes, s.njobs, s.tap, s.ntaps, s.last);
+        for (int j = 0; j < s.njobs; j++) { const mz_rn_job &J = s.jobs[j]; printf(" [a%d->d%d/%d skip %d epi %d n16 %d kb %d act %d wg %d acc %d fl %d]", J.a_buf, J.dst_buf, J.dst2_buf, J.skip_buf, J.epi, J.n16, J.kblocks, J.act, J.wg, J.acc, J.flags); }
+        printf("\n");
+    }
+    return 0;
+}
 // n <= ntrees inputs through one network; out1 / out2 like the C ABI callables (hidden in Julia (W,H,nf) order)
 int hh_rn_forward(const mz_config *c, const float *blob, int net, int n, const float *in, float *out1, float *out2) {
     mzh::model Mm; if (const char *e = mzh::build_model(*c, Mm)) { fprintf(stderr, "%s\n", e); return -1; }
