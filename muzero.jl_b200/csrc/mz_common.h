@@ -217,6 +217,7 @@ struct mz_rn_step {
     uint8_t rowlocal;                             // 1/2: every job is a (tree,cell)-tile job of warpgroup j on its own tile, so the warpgroups need not
                                                   // meet after the step (1), except before a step that is not row-local / the end of a range (2)
     mz_rn_job jobs[MZ_RN_TILES];
+    int8_t wgjob[4];                              // the job warpgroup w runs the epilogue of (at most one per step), or -1
 };
 struct mz_rn_params {
     int32_t cells, nf, tpt, ntrees, rows_valid, node_bytes;

@@ -128,12 +128,14 @@ struct mz_rn_exec {
     uint32_t tmem; int slot_bytes;
     uint32_t wq;            // weight blocks consumed
     int pf;                 // step whose block is in (or on its way to) slot wq & 1, or -1
-    uint32_t mq[4];         // commits seen per job barrier
+    uint32_t mqw;           // commits this thread's warpgroup has waited for on its barrier mma_bar[wg]
     uint32_t sq[2];         // commits seen per scratch barrier
     uint32_t eq0, eq1, ew0, ew1;  // per weight slot: row-local steps that released it through e_bar / releases thread 0 has waited for
     int pool_slot;          // hidden-state slot written by MZ_RN_F_POOL epilogues
     int W, H;
     int my_tree, my_cell;   // (tree, cell) of this thread's TMEM lane in its warpgroup's convolution tile
+    uint32_t rowoff;        // byte offset of this thread's row inside a swizzled tile
+    bool row_valid, tree_valid;   // this thread's row holds a (tree, cell) of an active tree / (rows = trees jobs) an active tree; set by mz_rn_bind_rows
     int st_tl[2], st_cell[2]; // hidden staging: this thread copies one 16-byte chunk of rows (tid >> 3) and (tid >> 3) + 64 of every tile
 #ifdef MZ_PHASE_TIMERS
     long long st_t[6]; long long st_c;
@@ -154,7 +156,7 @@ __device__ __forceinline__ void mz_rn_slot_free(mz_rn_exec &X, uint32_t sl) {
 }
 
 struct mz_rn_tile_ctx { uint32_t taddr, pT, pE, dst, skp, r7x; unsigned char *pool; unsigned long long rv2; bool store; };
-template <bool RELU, bool SKIP, bool PLANE>
+template <bool RELU, bool SKIP, bool PLANE, bool POOL>
 __device__ __forceinline__ void mz_rn_tile_rows(const mz_rn_tile_ctx &c) {
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
@@ -187,7 +189,7 @@ __device__ __forceinline__ void mz_rn_tile_rows(const mz_rn_tile_ctx &c) {
             }
             const uint4 ov = make_uint4(o[0], o[1], o[2], o[3]);
             if (c.store) mz_sts128u(c.dst + chunk, ov);
-            if (c.pool) *reinterpret_cast<uint4 *>(c.pool + c8 * 16) = ov;
+            if (POOL) { if (c.pool) *reinterpret_cast<uint4 *>(c.pool + c8 * 16) = ov; }
         }
     }
 }
@@ -200,10 +202,10 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
     const bool trees = (J.flags & MZ_RN_F_TREES) != 0;
     int tree, cell;
     if (trees) { tree = row; cell = 0; } else { tree = X.my_tree; cell = X.my_cell; }   // convolution job j is always run by warpgroup j
-    const bool valid = (trees ? row < R.ntrees : row < R.rows_valid) && X.sp.active[tree < MZ_RN_OUT_ROWS ? tree : 0] != 0;
+    const bool valid = trees ? X.tree_valid : X.row_valid;
     const int jflags = J.flags, jact = J.act;
     if (J.epi == MZ_RN_EPI_TILE) {
-        const uint32_t rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+        const uint32_t rowoff = X.rowoff;
         const uint32_t dst = mz_rn_buf(X.sp, J.dst_buf) + rowoff;
         const uint32_t skp = J.skip_buf != 0xff ? mz_rn_buf(X.sp, J.skip_buf) + rowoff : 0u;
         const float rowval = (J.flags & MZ_RN_F_PLANE) ? X.sp.plane[tree < MZ_RN_OUT_ROWS ? tree : 0] : 0.0f;
@@ -214,16 +216,19 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
         // that are not valid (the two pad rows of a tile, idle trees) are computed like the others and zeroed afterwards
         const mz_rn_tile_ctx tc{taddr, pT, pE, dst, skp, (uint32_t)((row & 7) << 4), pool, mz_f2pack(rowval, rowval), !trees || row < MZ_RN_OUT_ROWS};
         const int combo = (jact == MZ_ACT_RELU ? 4 : 0) | (skp ? 2 : 0) | ((jflags & MZ_RN_F_PLANE) ? 1 : 0);
-        switch (combo) {
-            case 4: mz_rn_tile_rows<true, false, false>(tc); break;      // ConvBN + relu, dense + relu
-            case 6: mz_rn_tile_rows<true, true, false>(tc); break;       // second convolution of a residual block
-            case 5: mz_rn_tile_rows<true, false, true>(tc); break;       // first dynamics convolution (action plane)
-            case 0: mz_rn_tile_rows<false, false, false>(tc); break;     // first dense layer of the policy head (no activation)
-            case 2: mz_rn_tile_rows<false, true, false>(tc); break;
-            case 1: mz_rn_tile_rows<false, false, true>(tc); break;
-            case 3: mz_rn_tile_rows<false, true, true>(tc); break;
-            default: mz_rn_tile_rows<true, true, true>(tc); break;
+#define MZ_RN_TILE_DISPATCH(POOL_) \
+        switch (combo) { \
+            case 4: mz_rn_tile_rows<true, false, false, POOL_>(tc); break;      /* ConvBN + relu, dense + relu */ \
+            case 6: mz_rn_tile_rows<true, true, false, POOL_>(tc); break;       /* second convolution of a residual block */ \
+            case 5: mz_rn_tile_rows<true, false, true, POOL_>(tc); break;       /* first dynamics convolution (action plane) */ \
+            case 0: mz_rn_tile_rows<false, false, false, POOL_>(tc); break;     /* first dense layer of the policy head (no activation) */ \
+            case 2: mz_rn_tile_rows<false, true, false, POOL_>(tc); break; \
+            case 1: mz_rn_tile_rows<false, false, true, POOL_>(tc); break; \
+            case 3: mz_rn_tile_rows<false, true, true, POOL_>(tc); break; \
+            default: mz_rn_tile_rows<true, true, true, POOL_>(tc); break; \
         }
+        if (jflags & MZ_RN_F_POOL) { MZ_RN_TILE_DISPATCH(true) } else { MZ_RN_TILE_DISPATCH(false) }
+#undef MZ_RN_TILE_DISPATCH
         if (!valid && tc.store) {
 #pragma unroll
             for (int c8 = 0; c8 < 8; c8++) mz_sts128u(dst + (uint32_t)(c8 << 4), make_uint4(0u, 0u, 0u, 0u));
@@ -270,7 +275,9 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
         const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
         const uint32_t slot = X.wq & 1u;
         const int next = s + 1 < last ? s + 1 : next_first;
-        const int njobs = st->njobs, ntaps = st->ntaps, is_last = st->last, st_rowlocal = st->rowlocal;
+        const uint32_t hdr = reinterpret_cast<const uint32_t *>(st)[2], hdr2 = reinterpret_cast<const uint32_t *>(st)[3];   // njobs, ntaps, tap, last | dx, dy, accumulate, rowlocal
+        const int njobs = (int)(hdr & 0xffu), ntaps = (int)((hdr >> 8) & 0xffu), is_last = (int)(hdr >> 24), st_rowlocal = (int)(hdr2 >> 24);
+        const int mine = (int)(int8_t)((reinterpret_cast<const uint32_t *>(st->wgjob)[0] >> (8 * wg)) & 0xffu);   // this warpgroup's job in the step, or -1
         if (tid == 0) {
             // a slot last used by a row-local step is free once all four warpgroups have finished that step's epilogue (it reads the
             // BatchNorm shifts from the slot): each of them arrives on e_bar[slot] after its own barrier
@@ -312,7 +319,7 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
 #pragma unroll
                         for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (accumulate || k > 0) ? 1u : 0u);
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.scr_bar[sl])) : "memory");
-                        if (is_last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[j])) : "memory");
+                        if (is_last) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[st->jobs[j].wg])) : "memory");
                     }
                     __syncwarp();
                 }
@@ -326,9 +333,6 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
             // from any warp): the four issues run in parallel instead of one thread issuing 16 MMAs ahead of its own epilogue
             if ((tid & 127) < 32) {
                 mz_tc_fence_after();
-                int mine = -1;
-#pragma unroll
-                for (int j = 0; j < MZ_RN_TILES; j++) if (j < njobs && (int)st->jobs[j].wg == wg) mine = j;
                 if (mine >= 0 && mz_elect_one()) {
                     const mz_rn_job J = st->jobs[mine];
                     const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
@@ -337,7 +341,7 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
 #pragma unroll
                         for (int k = 0; k < 4; k++) mz_rn_mma(X.tmem + 64u * J.acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[mine])) : "memory");
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&X.sp.mma_bar[wg])) : "memory");
                 }
                 __syncwarp();
             }
@@ -346,14 +350,10 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
         if (is_last) {
             // a warpgroup runs at most one epilogue per step (convolution job j <-> warpgroup j; dense heads: one job per warpgroup),
             // so the epilogue code exists once
-            int mine = -1; uint32_t par = 0;
-#pragma unroll
-            for (int j = 0; j < MZ_RN_TILES; j++) {
-                if (j < njobs) { if ((int)st->jobs[j].wg == wg) { mine = j; par = X.mq[j] & 1u; } X.mq[j]++; }
-            }
             if (mine >= 0) {
                 const mz_rn_job J = st->jobs[mine];
-                mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[mine]), par);
+                mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[wg]), X.mqw & 1u);
+                X.mqw++;
                 mz_tc_fence_after();
                 __syncwarp();
                 MZ_RN_ST(2);
@@ -422,7 +422,7 @@ struct mz_search_rn_args {
 __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, const mz_rn_params &R, const mz_search_rn_args &ta, unsigned char *smem) {
     X.sp = mz_rn_carve(smem, R.slot_bytes, P.S, R.ntrees, R.n_steps - R.smem_first);
     X.steps = ta.steps; X.image = ta.image; X.slot_bytes = R.slot_bytes; X.wq = 0; X.pf = -1; X.pool_slot = 0; X.W = P.W; X.H = P.H;
-    for (int j = 0; j < 4; j++) X.mq[j] = 0;
+    X.mqw = 0;
     X.sq[0] = X.sq[1] = 0; X.eq0 = X.eq1 = X.ew0 = X.ew1 = 0;
     for (int h = 0; h < 2; h++) { const int row = (int)(threadIdx.x >> 3) + 64 * h; X.st_tl[h] = row < R.rows_valid ? row / R.cells : -1; X.st_cell[h] = row % R.cells; }
     { const int row = (int)(threadIdx.x & 127); X.my_tree = (int)(threadIdx.x >> 7) * R.tpt + row / R.cells; X.my_cell = row % R.cells; }
@@ -453,6 +453,13 @@ __device__ __forceinline__ void mz_rn_setup(mz_rn_exec &X, const mz_params &P, c
     __syncthreads();
     mz_tc_fence_after();
     X.tmem = *X.sp.tmem_slot;
+}
+// binds this thread's row: call once the active flags of the launch are in shared memory
+__device__ __forceinline__ void mz_rn_bind_rows(mz_rn_exec &X, const mz_rn_params &R) {
+    const int row = (int)(threadIdx.x & 127);
+    X.rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    X.row_valid = row < R.rows_valid && X.sp.active[X.my_tree < MZ_RN_OUT_ROWS ? X.my_tree : 0] != 0;
+    X.tree_valid = row < R.ntrees && X.sp.active[row < MZ_RN_OUT_ROWS ? row : 0] != 0;
 }
 __device__ __forceinline__ void mz_rn_teardown(const mz_rn_exec &X) {
     mz_tc_fence_before();
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
         mm[p].mn = INFINITY; mm[p].mx = -INFINITY;
     }
     __syncthreads();
+    mz_rn_bind_rows(X, R);
 
     // ---- root: representation (im2col of the stacked observation) -> h0 in the pool; prediction(h0) ----
     if (MODE == MZ_MODE_API) {
@@ -656,6 +664,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_rn_forward(const __grid_co
         sp.tree_base[t] = (unsigned long long)(uintptr_t)(ta.scratch_pool + (size_t)(g0 + t) * R.node_bytes) - (unsigned long long)R.hidden_off_bytes;
     }
     __syncthreads();
+    mz_rn_bind_rows(X, R);
     if (ta.net == 0) {
         mz_rn_im2col(X, P, R, [&](int t, int pl, int cell) { return ta.in[(g0 + t) * P.stack_size + cell + P.cells * pl]; });
     } else {

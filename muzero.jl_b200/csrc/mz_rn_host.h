@@ -209,6 +209,13 @@ inline const char *rn_build(const mz_config &c, const mz_params &P, rn_model &M)
             return true;
         };
         const int ends[3] = {R.prog_repr[1], R.prog_pred[1], R.prog_dyn[1]};
+        for (auto &st : M.steps) {
+            for (int w = 0; w < 4; w++) st.wgjob[w] = -1;
+            for (int j = 0; j < st.njobs; j++) {
+                if (st.jobs[j].wg >= 4 || st.wgjob[st.jobs[j].wg] >= 0) return "internal: two jobs of one step on the same warpgroup";
+                st.wgjob[st.jobs[j].wg] = (int8_t)j;
+            }
+        }
         for (int i = 0; i < R.n_steps; i++) {
             M.steps[(size_t)i].rowlocal = 0;
             if (!rl(i)) continue;
