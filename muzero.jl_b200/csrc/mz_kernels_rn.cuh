@@ -150,6 +150,14 @@ __device__ __forceinline__ void mz_rn_issue_weights(const mz_rn_exec &X, const m
                  ::"r"(X.sp.wring + slot * (uint32_t)X.slot_bytes), "l"(X.image + off), "r"((uint32_t)bytes), "r"(bar) : "memory");
 }
 
+// a job descriptor as seven 32-bit loads (its fields are bytes: a member-wise copy would load them one by one)
+__device__ __forceinline__ mz_rn_job mz_rn_load_job(const mz_rn_job *p) {
+    static_assert(sizeof(mz_rn_job) == 28, "mz_rn_job layout");
+    union { mz_rn_job j; uint32_t w[7]; } u;
+#pragma unroll
+    for (int i = 0; i < 7; i++) u.w[i] = reinterpret_cast<const uint32_t *>(p)[i];
+    return u.j;
+}
 __device__ __forceinline__ void mz_rn_slot_free(mz_rn_exec &X, uint32_t sl) {
     if (sl == 0) { while (X.ew0 < X.eq0) { mz_mbar_wait_u32(mz_smem_u32(&X.sp.e_bar[0]), X.ew0 & 1u); X.ew0++; } }
     else { while (X.ew1 < X.eq1) { mz_mbar_wait_u32(mz_smem_u32(&X.sp.e_bar[1]), X.ew1 & 1u); X.ew1++; } }
@@ -206,8 +214,9 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
     const int jflags = J.flags, jact = J.act;
     if (J.epi == MZ_RN_EPI_TILE) {
         const uint32_t rowoff = X.rowoff;
-        const uint32_t dst = mz_rn_buf(X.sp, J.dst_buf) + rowoff;
-        const uint32_t skp = J.skip_buf != 0xff ? mz_rn_buf(X.sp, J.skip_buf) + rowoff : 0u;
+        // destination and residual source of a tile epilogue are always X/T tiles (buffer ids < 8; checked by the host builder)
+        const uint32_t dst = X.sp.tiles + (uint32_t)J.dst_buf * MZ_RN_TILE_BYTES + rowoff;
+        const uint32_t skp = J.skip_buf != 0xff ? X.sp.tiles + (uint32_t)J.skip_buf * MZ_RN_TILE_BYTES + rowoff : 0u;
         const float rowval = (J.flags & MZ_RN_F_PLANE) ? X.sp.plane[tree < MZ_RN_OUT_ROWS ? tree : 0] : 0.0f;
         unsigned char *pool = nullptr;
         if ((J.flags & MZ_RN_F_POOL) && valid)
@@ -270,9 +279,11 @@ __device__ __forceinline__ void mz_rn_epilogue(const mz_rn_exec &X, const mz_rn_
 #endif
 __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, int first, int last, int next_first) {
     const int tid = threadIdx.x, wg = tid >> 7, wgt = tid & 127;
+    // a range lies entirely in the shared-memory copy of the program (the simulation loop's) or entirely in global memory (the root's)
+    const mz_rn_step *const prog = first >= R.smem_first ? X.sp.prog - R.smem_first : X.steps;
     for (int s = first; s < last; s++) {
         MZ_RN_ST(5);
-        const mz_rn_step *st = s >= R.smem_first ? X.sp.prog + (s - R.smem_first) : X.steps + s;
+        const mz_rn_step *st = prog + s;
         const uint32_t slot = X.wq & 1u;
         const int next = s + 1 < last ? s + 1 : next_first;
         const uint32_t hdr = reinterpret_cast<const uint32_t *>(st)[2], hdr2 = reinterpret_cast<const uint32_t *>(st)[3];   // njobs, ntaps, tap, last | dx, dy, accumulate, rowlocal
@@ -334,7 +345,7 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
             if ((tid & 127) < 32) {
                 mz_tc_fence_after();
                 if (mine >= 0 && mz_elect_one()) {
-                    const mz_rn_job J = st->jobs[mine];
+                    const mz_rn_job J = mz_rn_load_job(&st->jobs[mine]);
                     const uint32_t a = mz_rn_buf(X.sp, J.a_buf), idesc = mz_rn_idesc(J.n16);
                     for (int kb = 0; kb < J.kblocks; kb++) {
                         const uint64_t ad = mz_tc_desc(a + (uint32_t)kb * 8192u), bd = mz_tc_desc(wslot + (uint32_t)J.w_sub + (uint32_t)(kb * J.n16 * 2048));
@@ -351,7 +362,7 @@ __device__ __forceinline__ void mz_rn_run(mz_rn_exec &X, const mz_rn_params &R, 
             // a warpgroup runs at most one epilogue per step (convolution job j <-> warpgroup j; dense heads: one job per warpgroup),
             // so the epilogue code exists once
             if (mine >= 0) {
-                const mz_rn_job J = st->jobs[mine];
+                const mz_rn_job J = mz_rn_load_job(&st->jobs[mine]);
                 mz_mbar_wait_u32(mz_smem_u32(&X.sp.mma_bar[wg]), X.mqw & 1u);
                 X.mqw++;
                 mz_tc_fence_after();

@@ -214,6 +214,7 @@ inline const char *rn_build(const mz_config &c, const mz_params &P, rn_model &M)
             for (int j = 0; j < st.njobs; j++) {
                 if (st.jobs[j].wg >= 4 || st.wgjob[st.jobs[j].wg] >= 0) return "internal: two jobs of one step on the same warpgroup";
                 st.wgjob[st.jobs[j].wg] = (int8_t)j;
+                if (st.jobs[j].epi == MZ_RN_EPI_TILE && (st.jobs[j].dst_buf >= 8 || (st.jobs[j].skip_buf != 0xff && st.jobs[j].skip_buf >= 8))) return "internal: tile epilogue outside the X/T tiles";
             }
         }
         for (int i = 0; i < R.n_steps; i++) {
