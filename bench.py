@@ -384,8 +384,8 @@ def run_b200(a):
                                           "traffic": (lambda t: t["bytes"] * rn_extra[4] / 8288.0 if t else None)(profiled_traffic("mz_k_search_rn")),
                                           "traffic_note": "DRAM bytes per launch from the committed ncu capture (8288 games), scaled to this launch's games: bf16 hidden states written once "
                                                           "per simulation (1152 B) and mostly re-read from L2",
-                                          "note": "useful FLOPs only; K = 64 per layer, so every output element is read from TMEM (64 B/clk/SM) for 64 MACs: the "
-                                                  "epilogue's TMEM reads bound the tensor pipe at ~25 % busy; see DESIGN.md"}}
+                                          "note": "useful FLOPs only; K = 64 per layer: each warpgroup's step is a dependent chain (MMA issue -> commit -> tcgen05.ld -> "
+                                                  "epilogue -> barrier, ~4 k cycles) and shared memory allows four chains per SM; see DESIGN.md 2.4"}}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
             for e_ in (learner["bptt"], learner["large_batch"]["bptt"], learner["large_batch"]["reference_l2"]):
