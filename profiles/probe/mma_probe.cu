@@ -20,7 +20,7 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__global__ void __launch_bounds__(512, 1) probe(int N, int nm, int issuers, long long *out) {
+__global__ void __launch_bounds__(512, 1) probe(int N, int nm, int issuers, long long *out, int stagger = 0) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bar[4];
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(512, 1) probe(int N, int nm, int issuers, long
     for (int rep = 0; rep < 3; rep++) {
         __syncthreads();
         if ((tid & 127) < 32 && wg < issuers) {
+            { const long long until = clock64() + (long long)stagger * wg; while (clock64() < until) { } }
             t0 = clock64();
             if (elect_one()) {
                 const uint64_t ad = desc(smem_u32(smem)), bd = desc(smem_u32(smem + 16384));
@@ -75,6 +76,15 @@ int main() {
         long long a = 0, b = 0;
         for (int w = 0; w < is; w++) { if (out[2 * w] > a) a = out[2 * w]; if (out[2 * w + 1] > b) b = out[2 * w + 1]; }
         printf("%4d %4d %8d | %6lld %6lld   (%.1f cycles per MMA over all issuers)\n", N, nm, is, a, b, (double)b / (nm * is));
+    }
+    printf("4 issuers x 4 MMAs (N=64) started `stagger` cycles apart: cycles until issued / until commit observed, per issuer\n");
+    for (int st : {0, 150, 300, 600}) {
+        for (int i = 0; i < 8; i++) out[i] = 0;
+        probe<<<148, 512, 16384 + 32768 + 1024>>>(64, 4, 4, out, st);
+        cudaDeviceSynchronize();
+        printf("stagger %4d |", st);
+        for (int w = 0; w < 4; w++) printf(" %5lld/%5lld", out[2 * w], out[2 * w + 1]);
+        printf("\n");
     }
     return 0;
 }
