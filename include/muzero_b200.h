@@ -26,12 +26,14 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 3
+#define MZ_ABI_VERSION 4
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
 enum { MZ_TIE_PHILOX = 0, MZ_TIE_FIRST = 1 };
 enum { MZ_GRAD_REFERENCE_L2 = 0, MZ_GRAD_BPTT = 1 };
+/* conf.opponent (src/Constructors.jl:27; select_opponent_action, src/SelfPlay.jl:311-325) */
+enum { MZ_OPP_SELF = 0, MZ_OPP_RANDOM = 1, MZ_OPP_EXPERT = 2 };
 /* network arithmetic: exact fp32 (bit-identical to the oracle contract) or bf16 tcgen05 tensor cores */
 enum { MZ_NN_FP32_EXACT = 0, MZ_NN_BF16_TC = 1 };
 enum { MZ_NET_FEEDFORWARD = 0, MZ_NET_RESNET = 1 };
@@ -126,6 +128,17 @@ int mz_select_action(mz_ctx *ctx, int n, const int32_t *visit_counts, const uint
  * Plays games first_game .. first_game+n_games-1 on the ctx's num_slots device-resident game slots and
  * appends every finished GameHistory to the device replay ring under the next game number. */
 int mz_self_play(mz_ctx *ctx, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves);
+/* competitive_play! (src/SelfPlay.jl:421-435) for n_games games at once: play_game with `opponent` (MZ_OPP_RANDOM: rand over the
+ * legal actions, :320; MZ_OPP_EXPERT: the reference's expert_agent() is undefined -- one-ply lookahead: win, else block, else random)
+ * moving for the side that is not muzero_player (1 or 2).  The reference passes temperature 0 and, through play_game, still searches
+ * with exploration noise (:359).  Finished games go to the replay ring like self-play games (opponent plies repeat the statistics of
+ * the previous search, :374; zeros before the first one), so use a context of its own for evaluation.  wins / draws / losses count
+ * games for MuZero: the side that completes a line first wins (TicTacToe runs one ply past a win). */
+int mz_arena(mz_ctx *ctx, uint64_t first_game, int64_t n_games, int opponent, int muzero_player, float temperature,
+             int64_t *wins, int64_t *draws, int64_t *losses, int64_t *simulations);
+/* select_opponent_action for n boards (bit masks as in mz_env_step); action[n] 1-based */
+int mz_opponent_action(mz_ctx *ctx, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, int opponent,
+                       const uint64_t *game_id, const int32_t *move_idx, int32_t *action);
 /* replay ring state: number of stored games, key (game number) of the oldest one, total stored positions */
 int mz_replay_info(mz_ctx *ctx, int64_t *n_games, int64_t *first_key, int64_t *total_samples);
 /* GameHistory export (src/Constructors.jl:6-16) for keys key0 .. key0+n-1, padded to Tmax = max_moves+1:

@@ -250,11 +250,34 @@ def self_play(engine: Engine, n_games: int, temperature: Optional[float] = None)
 
 def play_game(engine: Engine, temperature, render=False, opponent="self", muzero_player=1) -> GameHistory:
     """play_game(env, temperature, render, opponent, muzero_player, NNs)::GameHistory (SelfPlay.jl:330)."""
-    if opponent != "self":
-        raise NotImplementedError("only opponent == \"self\" is on the accelerated path (SelfPlay.jl:358)")
-    self_play(engine, 1, temperature)
+    if opponent == "human":
+        raise NotImplementedError("a human opponent has no batched meaning; use the reference's own loop (SelfPlay.jl:312-316)")
+    if opponent == "self":
+        self_play(engine, 1, temperature)
+    else:
+        engine.ctx.arena(engine.next_game, 1, _OPPONENTS[opponent], muzero_player, temperature)
+        engine.next_game += 1
     info = engine.ctx.replay_info()
     return ReplayBuffer(engine)[info["first_key"] + info["n_games"] - 1]
+
+
+_OPPONENTS = {"self": capi.OPP_SELF, "random": capi.OPP_RANDOM, "expert": capi.OPP_EXPERT}
+
+
+def competitive_play(engine: Engine, n_games: int = 1, opponent: Optional[str] = None, muzero_player: Optional[int] = None, temperature=0.0):
+    """competitive_play!(; NNs) (SelfPlay.jl:421-435), batched: n_games games of play_game(env, 0.0, ..., conf.opponent, conf.muzero_player, NNs).
+    The reference renders the game and returns nothing; this returns dict(wins, draws, losses, simulations) for MuZero.  The games are
+    saved to the engine's replay buffer like self-play games: evaluate on an Engine of its own (`Engine(conf, hyper)` + `set_weights`)."""
+    conf = engine.conf
+    opponent = (conf.opponent if len(conf.players) > 1 else "self") if opponent is None else opponent     # :428
+    muzero_player = conf.muzero_player if muzero_player is None else muzero_player
+    if opponent == "human":
+        raise NotImplementedError("a human opponent has no batched meaning; use the reference's own loop (SelfPlay.jl:312-316)")
+    if opponent not in _OPPONENTS:
+        raise ValueError("Wrong argument: opponent argument should be self, human, expert or random")     # :323
+    r = engine.ctx.arena(engine.next_game, n_games, _OPPONENTS[opponent], muzero_player, temperature)
+    engine.next_game += n_games
+    return r
 
 
 def save_game(engine: Engine, history: GameHistory, game_id=None):

@@ -18,6 +18,7 @@ GAME_TICTACTOE, GAME_CONNECT = 0, 1
 TIE_PHILOX, TIE_FIRST = 0, 1
 GRAD_REFERENCE_L2, GRAD_BPTT = 0, 1
 NET_FEEDFORWARD, NET_RESNET = 0, 1
+OPP_SELF, OPP_RANDOM, OPP_EXPERT = 0, 1, 2
 NN_FP32_EXACT, NN_BF16_TC = 0, 1
 NET_REPRESENTATION, NET_PREDICTION, NET_DYNAMICS, NET_ALL = 0, 1, 2, 3
 KERNEL_FAMILIES = ("selfplay_move", "save_refill", "replay_gather", "learn_forward_loss", "adam", "nn_batch", "env")
@@ -99,6 +100,8 @@ def lib():
         "mz_run_mcts": ([ctx, C.c_int, f32p, u32p, i32p, C.c_int, u64p, i32p, i32p, f32p, f32p], C.c_int),
         "mz_select_action": ([ctx, C.c_int, i32p, u32p, C.c_float, u64p, i32p, i32p], C.c_int),
         "mz_self_play": ([ctx, C.c_uint64, C.c_int64, C.c_float, i64p, i64p], C.c_int),
+        "mz_arena": ([ctx, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, i64p, i64p, i64p, i64p], C.c_int),
+        "mz_opponent_action": ([ctx, C.c_int, u64p, u64p, i32p, C.c_int, u64p, i32p, i32p], C.c_int),
         "mz_replay_info": ([ctx, i64p, i64p, i64p], C.c_int),
         "mz_history_export": ([ctx, C.c_int64, C.c_int, i64p, i32p, f32p, i32p, f32p, i32p, f32p, f32p], C.c_int),
         "mz_history_import": ([ctx, C.c_int, i64p, i32p, f32p, i32p, f32p, i32p, f32p, f32p], C.c_int),
@@ -308,6 +311,20 @@ class Context:
         sims, moves = C.c_int64(), C.c_int64()
         self._ck(self.L.mz_self_play(self._h, first_game, n_games, temperature, C.byref(sims), C.byref(moves)))
         return sims.value, moves.value
+
+    def arena(self, first_game, n_games, opponent=OPP_RANDOM, muzero_player=1, temperature=0.0):
+        """competitive_play! (SelfPlay.jl:421-435) for n_games games: dict(wins, draws, losses, simulations) for MuZero."""
+        w, d, l, sims = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.L.mz_arena(self._h, first_game, n_games, opponent, muzero_player, temperature, C.byref(w), C.byref(d), C.byref(l), C.byref(sims)))
+        return dict(wins=w.value, draws=d.value, losses=l.value, simulations=sims.value)
+
+    def opponent_action(self, p1, p2, player, opponent, game_id, move_idx):
+        p1 = np.ascontiguousarray(p1, np.uint64); p2 = np.ascontiguousarray(p2, np.uint64); player = np.ascontiguousarray(player, np.int32)
+        game_id = np.ascontiguousarray(game_id, np.uint64); move_idx = np.ascontiguousarray(move_idx, np.int32)
+        out = np.zeros(len(p1), np.int32)
+        self._ck(self.L.mz_opponent_action(self._h, len(p1), _p(p1, C.c_uint64), _p(p2, C.c_uint64), _p(player, C.c_int32), opponent,
+                                           _p(game_id, C.c_uint64), _p(move_idx, C.c_int32), _p(out, C.c_int32)))
+        return out
 
     def replay_info(self):
         n, k, t = C.c_int64(), C.c_int64(), C.c_int64()

@@ -599,11 +599,13 @@ int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32
 }
 
 // ---- self-play ---------------------------------------------------------------------------------------------
-int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves) {
-    MZ_CHECK_CTX(c);
+// one wave of games on the slots; arena_player != 0: competitive play, `arena_opponent` moves for the other side
+static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
     if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
     if (first_game + (uint64_t)n_games > 0xffffffffull) return fail(c, MZ_E_ARG, "game ids must fit in 32 bits (Philox counter)");
-    const mz_params &P = c->M.P;
+    mz_params P = c->M.P;
+    P.arena_player = arena_player; P.arena_opponent = arena_opponent; P.arena_tally = tally_player;
+    unsigned long long *tally = c->d_stats + 61;   // wins, draws, losses (the last three of the 64 counters)
     const int G = c->cfg.num_slots;
     MZ_TRY(read_counters(c));
     if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "previous self-play did not finish");
@@ -614,7 +616,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
     a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
     a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;
     int64_t total_moves = 0;
-    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
+    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
     for (int64_t guard = 0;; guard++) {
         MZ_CUDA(c, cudaGetLastError());
         MZ_TRY(read_counters(c));
@@ -622,6 +624,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
         if (active == 0) break;
         if (guard > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         total_moves += active;
+        if (arena_player != 0) { launch_scope ls(c, 6); mz_k_opponent_move<<<(G + 127) / 128, 128, 0, c->stream>>>(P, c->slots, G); }
         if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
             const int nt = c->rn.R.ntrees;
@@ -631,7 +634,7 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
         } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
-        { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G); }
+        { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
     }
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -639,6 +642,43 @@ int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperat
     if (moves) *moves = total_moves;
     c->last_mean_depth = c->h_stats[1] ? (double)c->h_stats[0] / (double)c->h_stats[1] : 0.0;
     c->last_mean_legal = c->h_stats[3] ? (double)c->h_stats[2] / (double)c->h_stats[3] : 0.0;
+    return MZ_OK;
+}
+
+int mz_self_play(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves) {
+    MZ_CHECK_CTX(c);
+    return run_wave(c, first_game, n_games, temperature, 0, MZ_OPP_SELF, 0, simulations, moves);
+}
+// competitive_play! (src/SelfPlay.jl:421-435) for n_games games at once
+int mz_arena(mz_ctx *c, uint64_t first_game, int64_t n_games, int opponent, int muzero_player, float temperature, int64_t *wins, int64_t *draws,
+             int64_t *losses, int64_t *simulations) {
+    MZ_CHECK_CTX(c);
+    if (opponent != MZ_OPP_SELF && opponent != MZ_OPP_RANDOM && opponent != MZ_OPP_EXPERT)
+        return fail(c, MZ_E_ARG, "opponent must be MZ_OPP_SELF, MZ_OPP_RANDOM or MZ_OPP_EXPERT (\"human\" has no batched meaning)");
+    if (c->M.P.P != 2 && opponent != MZ_OPP_SELF) return fail(c, MZ_E_ARG, "an opponent needs a two-player game");
+    if (muzero_player < 1 || muzero_player > c->M.P.P) return fail(c, MZ_E_ARG, "muzero_player %d out of range 1..%d", muzero_player, c->M.P.P);
+    // length(conf.players) == 1 ? "self" : conf.opponent (:428); "self": every ply is searched, outcomes still tallied for muzero_player
+    MZ_TRY(run_wave(c, first_game, n_games, temperature, opponent == MZ_OPP_SELF ? 0 : muzero_player, opponent, muzero_player, simulations, nullptr));
+    if (wins) *wins = (int64_t)c->h_stats[61];
+    if (draws) *draws = (int64_t)c->h_stats[62];
+    if (losses) *losses = (int64_t)c->h_stats[63];
+    return MZ_OK;
+}
+int mz_opponent_action(mz_ctx *c, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, int opponent, const uint64_t *game_id,
+                       const int32_t *move_idx, int32_t *action) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!p1 || !p2 || !player || !game_id || !move_idx || !action))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (opponent != MZ_OPP_RANDOM && opponent != MZ_OPP_EXPERT) return fail(c, MZ_E_ARG, "opponent must be MZ_OPP_RANDOM or MZ_OPP_EXPERT");
+    if (n == 0) return MZ_OK;
+    const mz_params &P = c->M.P;
+    uint64_t *d_p1, *d_p2, *d_gid; int32_t *d_pl, *d_mv, *d_act;
+    MZ_TRY(h2d(c, c->scratch[0], p1, (size_t)n, &d_p1)); MZ_TRY(h2d(c, c->scratch[1], p2, (size_t)n, &d_p2));
+    MZ_TRY(h2d(c, c->scratch[2], player, (size_t)n, &d_pl)); MZ_TRY(h2d(c, c->scratch[3], game_id, (size_t)n, &d_gid));
+    MZ_TRY(h2d(c, c->scratch[4], move_idx, (size_t)n, &d_mv)); MZ_TRY(h2d<int32_t>(c, c->scratch[5], nullptr, (size_t)n, &d_act));
+    { launch_scope ls(c, 6); mz_k_opponent_action<<<(n + 127) / 128, 128, 0, c->stream>>>(P, n, d_p1, d_p2, d_pl, opponent, d_gid, d_mv, d_act); }
+    MZ_CUDA(c, cudaGetLastError());
+    MZ_TRY(d2h(c, action, d_act, (size_t)n));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
 

@@ -22,7 +22,7 @@
 #define MZ_MAX_LAYERS 40
 #define MZ_MAX_WIDTH 64   /* width_hidden of the fp32 SIMT path (reference: 64) */
 
-enum { MZ_STREAM_TIE = 1, MZ_STREAM_ACTION = 2, MZ_STREAM_DIRICHLET = 3, MZ_STREAM_REPLAY = 4, MZ_STREAM_ABSORB = 5, MZ_STREAM_INIT = 7 };
+enum { MZ_STREAM_TIE = 1, MZ_STREAM_ACTION = 2, MZ_STREAM_DIRICHLET = 3, MZ_STREAM_REPLAY = 4, MZ_STREAM_ABSORB = 5, MZ_STREAM_INIT = 7, MZ_STREAM_OPPONENT = 8 };
 enum { MZ_ACT_ID = 0, MZ_ACT_RELU = 1, MZ_ACT_TANH = 2 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,7 +151,9 @@ struct mz_params {
     float act_plane_learn[MZ_MAX_A + 1];       // Float32(a) / Float32(A)    (src/Learning.jl:294)
     float disc_pow[72];                        // conf.discount^i as Julia computes Float32^Int
     int32_t n_layers, total_floats, n_params, per;   // per: conf.PER
-    int32_t per_alpha, pad3_[3];
+    int32_t per_alpha;
+    int32_t arena_player, arena_opponent;      // competitive play (SelfPlay.jl:421-435): the side MuZero plays (0 = self-play) and who moves for the other
+    int32_t arena_tally;                       // the side whose wins / draws / losses mz_k_save_refill counts (0 = none)
     mz_net nets[3];
     mz_layer layers[MZ_MAX_LAYERS];
     // tensor-core (MZ_NN_BF16_TC) weight image: per layer a [rows8(out) x 64] bf16 tile in the UMMA K-major
@@ -501,6 +503,40 @@ MZ_HD void mz_tree_add_noise(const mz_params &P, const mz_tree &t, uint32_t lega
         c.z = c.z * (1.0f - P.exploration_eps) + nz * P.exploration_eps;
         t.A[1 + a - 1] = c;
     }
+}
+
+// ---- competitive play: select_opponent_action (src/SelfPlay.jl:311-325) ------------------------------------------
+// a completed line of one side's marks (the real rule, not is_win's side-to-move test)
+MZ_HD bool mz_env_has_line(const mz_params &P, uint64_t b) { return P.game == MZ_GAME_TICTACTOE ? mz_ttt_line((uint32_t)b) : mz_connect_has4(b, P.W); }
+// "random": rand(rng, las), uniform over the ascending legal actions from the Philox stream (seed, OPPONENT, game, move) -- as written
+// the branch reads `las` before defining it.  "expert": expert_agent() is not defined in the reference; repaired as one-ply
+// lookahead: the first legal action that completes a line for the mover, else the first that would complete one for the other
+// side, else the random action.
+MZ_HD int mz_opponent_action(const mz_params &P, const mz_board &b, int opponent, uint32_t game, uint32_t move) {
+    const uint32_t legal = mz_env_legal_b(P, b);
+    int las[MZ_MAX_A], n = 0;
+    for (int a = 1; a <= P.A; a++) if ((legal >> (a - 1)) & 1u) las[n++] = a;
+    if (n == 0) return 1;
+    if (opponent == MZ_OPP_EXPERT) {
+        for (int pass = 0; pass < 2; pass++) for (int i = 0; i < n; i++) {
+            mz_board t = b;
+            if (pass == 1) t.player = t.player % P.P + 1;
+            const int who = t.player;
+            mz_env_step_b(P, t, las[i]);
+            if (mz_env_has_line(P, who == 1 ? t.p1 : t.p2)) return las[i];
+        }
+    }
+    return las[mz_u32_below(mz_philox(P.seed, MZ_STREAM_OPPONENT, game, move, 0, 0).x, (uint32_t)n)];
+}
+// +1 / 0 / -1 for MuZero: the side that completes a line first wins (TicTacToe runs one ply past a win, Q14)
+MZ_HD int mz_arena_outcome(const mz_params &P, int T, const int32_t *actions, int muzero_player) {
+    mz_board b; mz_env_reset_b(P, b);
+    for (int i = 0; i < T; i++) {
+        const int who = b.player;
+        mz_env_step_b(P, b, actions[i]);
+        if (mz_env_has_line(P, who == 1 ? b.p1 : b.p2)) return who == muzero_player ? 1 : -1;
+    }
+    return 0;
 }
 
 // select_action (src/SelfPlay.jl:293-306) over the root's children in Dict order (Q9-Q10).

@@ -116,6 +116,7 @@ inline const char *build_model(const mz_config &c, model &M) {
     P.batch_size = c.batch_size;
     P.pb_c_init = c.pb_c_init; P.discount = c.discount; P.dirichlet_alpha = c.dirichlet_alpha; P.exploration_eps = c.exploration_eps;
     P.seed = c.seed; P.per = c.per ? 1 : 0; P.per_alpha = c.per_alpha;
+    P.arena_player = 0; P.arena_opponent = MZ_OPP_SELF; P.arena_tally = 0;
     for (int i = 0; i < MZ_MAX_A; i++) P.order[i] = c.child_order[i];
     for (int a = 0; a <= c.A; a++) {
         P.act_plane_play[a] = (float)((double)a / (double)c.A);   // SelfPlay.jl:8-9: Int/Int -> Float64, stored Float32

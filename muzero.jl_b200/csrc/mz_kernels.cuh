@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
         if (MODE == MZ_MODE_API) {
             active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
         } else {
-            active = a.slots.status[g] == MZ_SLOT_ACTIVE;
+            active = a.slots.status[g] == MZ_SLOT_ACTIVE && (P.arena_player == 0 || a.slots.player[g] == P.arena_player);   // competitive play: MuZero's plies only
             if (active) {
                 mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
                 legal = mz_env_legal_b(P, b); to_play = b.player;                       // SelfPlay.jl:351,359
@@ -402,9 +402,39 @@ __global__ void mz_k_per_update(const __grid_constant__ mz_params P, mz_ring r, 
     else if (r.upd[slot] == mine) { r.q_pos[slot] = q; r.upd[slot] = 0ull; }
 }
 
+// competitive play (play_game with an opponent, src/SelfPlay.jl:358-363): the opponent's ply for every active slot whose side to move
+// is not MuZero's.  The history entry repeats the statistics of the previous search (store_search_stats! is called with the stale
+// root, :374); before the first search the reference's `root` is the Int 0 and it would throw: zeros.
+__global__ void mz_k_opponent_move(const __grid_constant__ mz_params P, mz_slots s, int n_slots) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_slots || s.status[g] != MZ_SLOT_ACTIVE || s.player[g] == P.arena_player) return;
+    mz_board b; b.p1 = s.p1[g]; b.p2 = s.p2[g]; b.player = s.player[g];
+    int T = s.T[g];
+    const int p = b.player;
+    const int action = mz_opponent_action(P, b, P.arena_opponent, (uint32_t)s.game_id[g], (uint32_t)T + 1u);
+    mz_env_step_b(P, b, action);
+    const float reward = (float)mz_env_reward_b(P, b, p);
+    const bool done = mz_env_terminated_b(P, b);
+    const size_t o = (size_t)g * P.Tmax + T;
+    for (int i = 0; i < P.A; i++) s.h_cv[o * P.A + i] = T > 0 ? s.h_cv[(o - 1) * P.A + i] : 0.0f;
+    s.h_rv[o] = T > 0 ? s.h_rv[o - 1] : 0.0f;
+    s.h_action[o] = action; s.h_reward[o] = reward; s.h_to_play[o] = (uint8_t)p;
+    T += 1;
+    s.p1[g] = b.p1; s.p2[g] = b.p2; s.player[g] = b.player; s.T[g] = T;
+    if (T < P.Tmax) { s.h_p1[(size_t)g * P.Tmax + T] = b.p1; s.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
+    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED;
+}
+__global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, int opponent,
+                                     const uint64_t *game_id, const int32_t *move_idx, int32_t *action) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    mz_board b; b.p1 = p1[g]; b.p2 = p2[g]; b.player = player[g];
+    action[g] = mz_opponent_action(P, b, opponent, (uint32_t)game_id[g], (uint32_t)move_idx[g]);
+}
+
 // save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
-__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
+__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr) {
     __shared__ int scan[1024];
     __shared__ int64_t base_key, next_game, end_game;
     __shared__ int carry_fin, carry_free, active_count;
@@ -440,6 +470,8 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
             atomicAdd((unsigned long long *)&add_steps, (unsigned long long)T);
             atomicAdd((unsigned long long *)&add_samples, (unsigned long long)T);
             if (P.per) mz_per_init_game(P, r, pos);                         // initial priorities (:136-145)
+            if (arena_tally && P.arena_tally != 0)                           // competitive play: wins / draws / losses for MuZero
+                atomicAdd(&arena_tally[1 - mz_arena_outcome(P, T, s.h_action + (size_t)g * P.Tmax, P.arena_tally)], 1ull);
         }
         if (fre) {
             int64_t id = next_game + free_rank;

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
             tree[p] = mz_tree_at(P, a.tree_pool, g);
             if (MODE == MZ_MODE_API) { active[p] = true; legal[p] = a.legal[g]; game[p] = (uint32_t)a.game_id[g]; move[p] = (uint32_t)a.move_idx[g]; }
             else {
-                active[p] = a.slots.status[g] == MZ_SLOT_ACTIVE;
+                active[p] = a.slots.status[g] == MZ_SLOT_ACTIVE && (P.arena_player == 0 || a.slots.player[g] == P.arena_player);   // competitive play: MuZero's plies only
                 if (active[p]) {
                     mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
                     legal[p] = mz_env_legal_b(P, b); game[p] = (uint32_t)a.slots.game_id[g]; move[p] = (uint32_t)a.slots.T[g] + 1u;

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
         if (MODE == MZ_MODE_API) {
             active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
         } else {
-            active = a.slots.status[g] == MZ_SLOT_ACTIVE;
+            active = a.slots.status[g] == MZ_SLOT_ACTIVE && (P.arena_player == 0 || a.slots.player[g] == P.arena_player);   // competitive play: MuZero's plies only
             if (active) {
                 mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
                 legal = mz_env_legal_b(P, b); to_play = b.player;

@@ -134,6 +134,22 @@ function self_play!(e::Engine, n_games::Integer; temperature=visit_softmax_tempe
     e.next_game += n_games
     return sims[], moves[]
 end
+# ---- competitive_play! (src/SelfPlay.jl:421-435), batched ------------------------------------------------------
+const OPPONENTS = Dict("self" => 0, "random" => 1, "expert" => 2)
+"""
+`n_games` games of `play_game(env, 0.0f0, render, conf.opponent, conf.muzero_player, NNs)` at once. The reference renders one game and
+returns nothing; this returns `(wins, draws, losses, simulations)` for MuZero. "expert" is a one-ply lookahead (the reference's
+`expert_agent()` is undefined); "human" stays with the reference's own loop. The games are saved to the engine's replay buffer like
+self-play games: evaluate on an `Engine` of its own.
+"""
+function competitive_play!(e::Engine, n_games::Integer=1; opponent::String="random", muzero_player::Integer=1, temperature=0.0f0)
+    haskey(OPPONENTS, opponent) || error("Wrong argument: opponent argument should be self, human, expert or random")
+    w = Ref{Int64}(0); d = Ref{Int64}(0); l = Ref{Int64}(0); sims = Ref{Int64}(0)
+    check(e, ccall((:mz_arena, LIB), Cint, (Ptr{Cvoid}, UInt64, Int64, Cint, Cint, Cfloat, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+                   e.ctx, e.next_game, n_games, OPPONENTS[opponent], muzero_player, temperature, w, d, l, sims))
+    e.next_game += n_games
+    return (wins=w[], draws=d[], losses=l[], simulations=sims[])
+end
 "GameHistory for replay key `key` (fields and shapes of src/Constructors.jl:6-16)."
 function history(e::Engine, key::Integer, GameHistory)
     Tm = Int(e.cfg.max_moves) + 1; A = Int(e.cfg.A); W, H, C = Int(e.cfg.W), Int(e.cfg.H), Int(e.cfg.C)

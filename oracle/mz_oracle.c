@@ -17,7 +17,7 @@
  * Philox4x32-10 (Salmon et al. 2011).  Replaces the reference's unseeded global RNG / the
  * MersenneTwister(1234) at src/SelfPlay.jl:152, which cannot be reproduced in a batched setting.
  * ------------------------------------------------------------------------------------------ */
-enum { STREAM_TIE = 1, STREAM_ACTION = 2, STREAM_DIRICHLET = 3, STREAM_REPLAY = 4, STREAM_ABSORB = 5, STREAM_INIT = 7 };
+enum { STREAM_TIE = 1, STREAM_ACTION = 2, STREAM_DIRICHLET = 3, STREAM_REPLAY = 4, STREAM_ABSORB = 5, STREAM_INIT = 7, STREAM_OPPONENT = 8 };
 
 void mzo_philox(uint64_t seed, uint32_t stream, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ stream;
@@ -879,10 +879,49 @@ typedef struct {
     const model_t *m; uint64_t first_game; int lo, hi; float temperature;
     int32_t *T; float *obs; int32_t *actions; float *rewards; int32_t *to_play; float *child_visits; float *root_values;
     int64_t sims;
+    int opponent, muzero_player; int32_t *outcome;     /* competitive play (SelfPlay.jl:421-435); opponent 0 = "self" */
 } sp_job_t;
 
+/* a completed line of one side's marks (the real rule, not is_win's side-to-move test) */
+static int side_has_line(const mzo_config *c, uint64_t b) {
+    if (c->game == MZO_GAME_CONNECT) return cn_has4(c, b);
+    for (int i = 0; i < 8; i++) if (((uint32_t)b & TTT_LINES[i]) == TTT_LINES[i]) return 1;
+    return 0;
+}
+/* select_opponent_action (SelfPlay.jl:311-325).  "random": rand(rng, las) -- uniform over the ascending legal actions, here from
+ * the Philox stream (seed, STREAM_OPPONENT, game, move); as written the branch reads `las` before defining it and never ran.
+ * "expert": expert_agent() is not defined anywhere in the reference; repaired as one-ply lookahead: the first (ascending) legal
+ * action that completes a line for the mover, else the first that would complete one for the other side, else the random action. */
+int mzo_opponent_action(const mzo_config *c, const mzo_env *e, int opponent, uint64_t game_id, int move_idx) {
+    uint32_t legal = mzo_env_legal_mask(c, e);
+    int las[MZO_MAX_A], n = 0;
+    for (int a = 1; a <= c->A; a++) if ((legal >> (a - 1)) & 1u) las[n++] = a;
+    if (n == 0) return 1;
+    if (opponent == MZO_OPP_EXPERT) {
+        for (int pass = 0; pass < 2; pass++) for (int i = 0; i < n; i++) {
+            mzo_env t = *e;
+            if (pass == 1) t.player = t.player == 1 ? 2 : 1;
+            int who = t.player;
+            mzo_env_step(c, &t, las[i]);
+            if (side_has_line(c, who == 1 ? t.p1 : t.p2)) return las[i];
+        }
+    }
+    uint32_t r[4]; mzo_philox(c->seed, STREAM_OPPONENT, (uint32_t)game_id, (uint32_t)move_idx, 0, 0, r);
+    return las[u32_below(r[0], (uint32_t)n)];
+}
+/* +1 / 0 / -1: the side that completed a line first (TicTacToe lets the game run one ply past a win, Q14) is the winner */
+int mzo_arena_outcome(const mzo_config *c, int T, const int32_t *actions, int muzero_player) {
+    mzo_env e; mzo_env_reset(c, &e);
+    for (int i = 0; i < T; i++) {
+        int who = e.player;
+        mzo_env_step(c, &e, actions[i]);
+        if (side_has_line(c, who == 1 ? e.p1 : e.p2)) return who == muzero_player ? 1 : -1;
+    }
+    return 0;
+}
+
 static void play_game(const model_t *m, tree_t *t, uint64_t game_id, float temperature, int32_t *T_out, float *obs_h,
-                      int32_t *act_h, float *rew_h, int32_t *tp_h, float *cv_h, float *rv_h, int64_t *sims) {
+                      int32_t *act_h, float *rew_h, int32_t *tp_h, float *cv_h, float *rv_h, int64_t *sims, int opponent, int muzero_player) {
     const mzo_config *c = &m->cfg;
     int on = obs_size(c), T = 0, done = 0;
     mzo_env env; float stacked[MZO_MAX_OBS * 3];
@@ -893,6 +932,19 @@ static void play_game(const model_t *m, tree_t *t, uint64_t game_id, float tempe
         mzo_stack_observations(c, obs_h, act_h, T + 1, stacked);          /* :355 */
         uint32_t legal = mzo_env_legal_mask(c, &env);
         t->game_id = game_id; t->move_idx = T + 1;
+        if (opponent != MZO_OPP_SELF && p != muzero_player) {             /* :358-363 */
+            int action = mzo_opponent_action(c, &env, opponent, game_id, T + 1);
+            mzo_env_step(c, &env, action);
+            float reward = (float)mzo_env_reward(c, &env, p);
+            done = mzo_env_is_terminated(c, &env);
+            /* store_search_stats!(history, root, ...) with the root of the previous search (:374); before the first search `root`
+             * is the Int 0 and the reference would throw: zeros */
+            for (int a = 0; a < c->A; a++) cv_h[(size_t)T * c->A + a] = T > 0 ? cv_h[(size_t)(T - 1) * c->A + a] : 0.0f;
+            rv_h[T] = T > 0 ? rv_h[T - 1] : 0.0f;
+            act_h[T] = action; rew_h[T] = reward; tp_h[T] = p;
+            T++;
+            continue;
+        }
         node_t *root;
         run_mcts(t, stacked, legal, p, 1, &root, NULL);                   /* :359 exploration hard-coded true (Q11) */
         *sims += c->num_iters;
@@ -917,14 +969,22 @@ static void *sp_worker(void *arg) {
     int Tmax = c->max_moves + 1, on = obs_size(c);
     tree_t *t = tree_alloc(j->m);
     for (int g = j->lo; g < j->hi; g++)
+    {
         play_game(j->m, t, j->first_game + (uint64_t)g, j->temperature, &j->T[g], j->obs + (size_t)g * Tmax * on,
                   j->actions + (size_t)g * Tmax, j->rewards + (size_t)g * Tmax, j->to_play + (size_t)g * Tmax,
-                  j->child_visits + (size_t)g * Tmax * c->A, j->root_values + (size_t)g * Tmax, &j->sims);
+                  j->child_visits + (size_t)g * Tmax * c->A, j->root_values + (size_t)g * Tmax, &j->sims, j->opponent, j->muzero_player);
+        if (j->outcome) j->outcome[g] = mzo_arena_outcome(c, j->T[g], j->actions + (size_t)g * Tmax, j->muzero_player);
+    }
     tree_free(t);
     return NULL;
 }
 int64_t mzo_self_play(const mzo_config *cfg, const float *blob, uint64_t first_game, int n_games, float temperature, int nthreads,
                       int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values) {
+    return mzo_arena(cfg, blob, first_game, n_games, MZO_OPP_SELF, 1, temperature, nthreads, T, obs, actions, rewards, to_play, child_visits, root_values, NULL);
+}
+/* competitive_play! (SelfPlay.jl:421-435) over many games: play_game with an opponent on the other side */
+int64_t mzo_arena(const mzo_config *cfg, const float *blob, uint64_t first_game, int n_games, int opponent, int muzero_player, float temperature, int nthreads,
+                  int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values, int32_t *outcome) {
     model_t m; model_init(&m, cfg, blob);
     if (nthreads < 1) nthreads = 1;
     if (nthreads > n_games) nthreads = n_games > 0 ? n_games : 1;
@@ -932,7 +992,7 @@ int64_t mzo_self_play(const mzo_config *cfg, const float *blob, uint64_t first_g
     sp_job_t *jobs = (sp_job_t *)calloc((size_t)nthreads, sizeof(sp_job_t));
     for (int i = 0; i < nthreads; i++) {
         sp_job_t *j = &jobs[i];
-        j->m = &m; j->first_game = first_game; j->temperature = temperature;
+        j->m = &m; j->first_game = first_game; j->temperature = temperature; j->opponent = opponent; j->muzero_player = muzero_player; j->outcome = outcome;
         j->lo = (int)((int64_t)n_games * i / nthreads); j->hi = (int)((int64_t)n_games * (i + 1) / nthreads);
         j->T = T; j->obs = obs; j->actions = actions; j->rewards = rewards; j->to_play = to_play; j->child_visits = child_visits; j->root_values = root_values;
         if (nthreads == 1) sp_worker(j); else pthread_create(&th[i], NULL, sp_worker, j);

@@ -131,6 +131,16 @@ int64_t mzo_self_play(const mzo_config *cfg, const float *blob, uint64_t first_g
                       int nthreads, int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play,
                       float *child_visits, float *root_values);
 
+/* ---- competitive play (src/SelfPlay.jl:421-435, select_opponent_action :311-325) ----
+ * play_game with `opponent` moving for the side that is not muzero_player; outcome[n] = +1 / 0 / -1 for MuZero (the side that
+ * completed a line first wins).  Histories as in mzo_self_play; opponent plies repeat the previous search statistics. */
+enum { MZO_OPP_SELF = 0, MZO_OPP_RANDOM = 1, MZO_OPP_EXPERT = 2 };
+int mzo_opponent_action(const mzo_config *cfg, const mzo_env *e, int opponent, uint64_t game_id, int move_idx);
+int mzo_arena_outcome(const mzo_config *cfg, int T, const int32_t *actions, int muzero_player);
+int64_t mzo_arena(const mzo_config *cfg, const float *blob, uint64_t first_game, int n_games, int opponent, int muzero_player,
+                  float temperature, int nthreads, int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play,
+                  float *child_visits, float *root_values, int32_t *outcome);
+
 /* ---- replay / targets (src/ReplayBuffer.jl:5-50,188-217) ----
  * The buffer is the same padded layout holding n_games games whose keys (game numbers) are
  * first_key .. first_key+n_games-1.  Outputs follow get_batch's tuple (ReplayBuffer.jl:216):

@@ -227,6 +227,31 @@ def self_play(cfg, blob, first_game, n_games, temperature=1.0, nthreads=1):
     return out
 
 
+OPP_SELF, OPP_RANDOM, OPP_EXPERT = 0, 1, 2
+
+
+def arena(cfg, blob, first_game, n_games, opponent=OPP_RANDOM, muzero_player=1, temperature=0.0, nthreads=1):
+    """competitive_play! (SelfPlay.jl:421-435) over n games: histories as in self_play plus outcome[n] (+1 / 0 / -1 for MuZero)."""
+    s = sizes(cfg)
+    out = dict(T=np.zeros(n_games, np.int32), obs=np.zeros((n_games, s["Tmax"], s["obs"]), np.float32),
+               actions=np.zeros((n_games, s["Tmax"]), np.int32), rewards=np.zeros((n_games, s["Tmax"]), np.float32),
+               to_play=np.zeros((n_games, s["Tmax"]), np.int32),
+               child_visits=np.zeros((n_games, s["Tmax"], s["A"]), np.float32),
+               root_values=np.zeros((n_games, s["Tmax"]), np.float32), outcome=np.zeros(n_games, np.int32))
+    L = lib()
+    L.mzo_arena.restype = C.c_int64
+    out["sims"] = L.mzo_arena(C.byref(cfg), _p(blob), C.c_uint64(first_game), C.c_int(n_games), C.c_int(opponent), C.c_int(muzero_player),
+                              C.c_float(temperature), C.c_int(nthreads), _p(out["T"], C.c_int32), _p(out["obs"]), _p(out["actions"], C.c_int32),
+                              _p(out["rewards"]), _p(out["to_play"], C.c_int32), _p(out["child_visits"]), _p(out["root_values"]),
+                              _p(out["outcome"], C.c_int32))
+    return out
+
+
+def opponent_action(cfg, p1, p2, player, opponent, game_id, move_idx):
+    e = Env(); e.p1, e.p2, e.player, e.moves = p1, p2, player, bin(p1 | p2).count("1")
+    return lib().mzo_opponent_action(C.byref(cfg), C.byref(e), opponent, C.c_uint64(game_id), move_idx)
+
+
 def get_batch(cfg, hist, step, first_key=1):
     s = sizes(cfg); B = cfg.batch_size
     out = dict(index=np.zeros((B, 2), np.int32), obs=np.zeros((B, s["stack"]), np.float32),

@@ -58,9 +58,20 @@ def harness():
     L.hh_get_batch.argtypes = [cfgp, C.c_int, C.c_int64, i32p, f32p, i32p, f32p, i32p, f32p, f32p, C.c_uint64, i32p] + [f32p] * 6
     L.hh_rn_num_params.argtypes = [cfgp]
     L.hh_rn_program_info.argtypes = [cfgp, i32p]
+    L.hh_opponent_action.argtypes = [cfgp, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int]
+    L.hh_arena_outcome.argtypes = [cfgp, C.c_int, i32p, C.c_int]
+    L.hh_rn_program_dump.argtypes = [cfgp]
     L.hh_rn_forward.argtypes = [cfgp, f32p, C.c_int, C.c_int, f32p, f32p, f32p]
     _hh = L
     return L
+
+
+def product_board(pcfg, actions):
+    """(p1, p2, player) of the product's board encoding after `actions` from the empty board (host harness)."""
+    hh = harness()
+    a = np.asarray(actions, np.int32); p1, p2, pl = C.c_uint64(), C.c_uint64(), C.c_int32()
+    assert hh.hh_board_after(C.byref(pcfg), len(a), a.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(p1), C.byref(p2), C.byref(pl)) == 0
+    return p1.value, p2.value, pl.value
 
 
 def random_stacked(cfg, n, seed=0):

@@ -282,6 +282,23 @@ int hh_rn_program_info(const mz_config *c, int32_t *out /* [8]: n_steps, repr st
     for (const auto &s : M.steps) if (s.w_bytes > R.slot_bytes || s.w_off + s.w_bytes > R.image_bytes || s.njobs < 1 || s.njobs > MZ_RN_TILES) return -2;
     return 0;
 }
+// select_opponent_action / arena outcome: the product's scalar code (the kernels call the same functions)
+int hh_opponent_action(const mz_config *c, uint64_t p1, uint64_t p2, int player, int opponent, uint64_t game, int move) {
+    mzh::model M; if (mzh::build_model(*c, M)) return -1;
+    mz_board b; b.p1 = p1; b.p2 = p2; b.player = player;
+    return mz_opponent_action(M.P, b, opponent, (uint32_t)game, (uint32_t)move);
+}
+int hh_board_after(const mz_config *c, int n, const int32_t *actions, uint64_t *p1, uint64_t *p2, int32_t *player) {
+    mzh::model M; if (mzh::build_model(*c, M)) return -1;
+    mz_board b; mz_env_reset_b(M.P, b);
+    for (int i = 0; i < n; i++) mz_env_step_b(M.P, b, actions[i]);
+    *p1 = b.p1; *p2 = b.p2; *player = b.player;
+    return 0;
+}
+int hh_arena_outcome(const mz_config *c, int T, const int32_t *actions, int muzero_player) {
+    mzh::model M; if (mzh::build_model(*c, M)) return -99;
+    return mz_arena_outcome(M.P, T, actions, muzero_player);
+}
 // one line per step of the program (debugging aid; also pins the step count the kernels are timed with)
 int hh_rn_program_dump(const mz_config *c) {
     mzh::model Mm; if (const char *e = mzh::build_model(*c, Mm)) { fprintf(stderr, "%s\n", e); return -1; }
