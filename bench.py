@@ -59,16 +59,49 @@ def workload_name(a):
 
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region.  NVML in-process (every 2 ms: the timed region of the
+    default run is ~0.1 s, shorter than one nvidia-smi start-up); falls back to the `nvidia-smi -lms` loop of the B200_PROFILING.md
+    recipe when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.halt, self.source = index, [], None, threading.Event(), None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(ids[index]) if index < len(ids) else index)
+            self.nvml = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml; self.source = "nvml"
+            bits = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown, n.nvmlClocksEventReasonSwThermalSlowdown,
+                    n.nvmlClocksEventReasonSwPowerCap]
+            while not self.halt.is_set():
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    self.rows.append([str(sm), str(self.mx)] + ["Active" if r & b else "Not Active" for b in bits])
+                except Exception:
+                    pass
+                self.halt.wait(0.002)
+            return
         try:
+            self.source = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
@@ -77,14 +110,15 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self.halt.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "source": self.source}
 
 
 def cpu_self_play_rate(ocfg, blob, games, threads, first_game=10 ** 6):
