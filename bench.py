@@ -393,6 +393,16 @@ def run_b200(a):
                          "avg_launch_ms": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms if ms > 0 else None,
                          "nn_flops_per_simulation": 111232, "nn_tflops_achieved": 111232 * sims_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0},
         }
+        if a.nn != "tc" and avg_launch_s > 0 and clocks.get("sm_mhz"):
+            # the resource the exact network phase actually saturates: shared-memory wavefronts (one per clock per SM).  A 4x4 register tile
+            # issues two 128-bit shared loads (4 wavefronts each) per 8 packed FMAs: 64 wavefront-cycles against 32 FMA-pipe cycles per k step
+            # for the 8 warps of a CTA; ncu counts 830 wavefronts per simulation over the whole kernel.
+            ctas = (G + 31) // 32
+            wf_rate = 830.0 * sims_per_launch / (avg_launch_s * clocks["sm_mhz"] * 1e6 * ctas)
+            out["roofline"]["shared_memory"] = {"wavefronts_per_simulation": 830, "source": "profiles/r1j_search_exact_final_ncu.txt (l1tex__data_pipe_lsu_wavefronts_mem_shared)",
+                                                "achieved_per_clk_per_sm": wf_rate, "peak_per_clk_per_sm": 1.0, "frac": wf_rate, "sms_with_a_cta": ctas,
+                                                "note": "whole-launch average incl. the tree phases; inside the network phase the wavefront pipe is the bound "
+                                                        "(64 wavefront-cycles vs 32 FMA-cycles per k step), which caps the FMA pipe at 50 %"}
         if tc_extra:
             bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             tc_launch_s = (tc_extra[2] / max(tc_extra[3], 1)) * 1e-3

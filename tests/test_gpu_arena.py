@@ -84,6 +84,8 @@ def test_opponent_action_matches_oracle(capi):
 def test_arena_argument_errors(capi):
     ctx, _ = make_ctx(capi)
     ctx.init_weights(1)
+    assert ctx.arena(0, 0, capi.OPP_RANDOM, 1, 0.0) == dict(wins=0, draws=0, losses=0, simulations=0)      # empty input
+    assert ctx.opponent_action([], [], [], capi.OPP_RANDOM, [], []).size == 0
     for args in ((0, 4, 7, 1, 0.0), (0, 4, capi.OPP_RANDOM, 3, 0.0), (0, 4, capi.OPP_RANDOM, 0, 0.0)):
         with pytest.raises(capi.MuZeroB200Error) as e:
             ctx.arena(*args)
