@@ -71,6 +71,7 @@ struct mz_ctx {
     float *d_pv = nullptr, *d_pr = nullptr, *d_pp = nullptr, *d_rowv = nullptr, *d_rowp = nullptr, *d_rowinvg = nullptr;
     double *d_rowr = nullptr, *d_lossout = nullptr;
     int64_t *h_counters = nullptr; double *h_lossout = nullptr; unsigned long long *h_stats = nullptr;   // pinned
+    int64_t *h_wave = nullptr; cudaEvent_t ev_wave[2] = {nullptr, nullptr};   // pinned: two snapshots of the counters, self-play runs one iteration ahead of the host
     dev_buf scratch[12];
     int64_t adam_t = 0; double bp1 = 0.9, bp2 = 0.999;
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
@@ -356,9 +357,11 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     mz_slots &s = c->slots;
     MZ_CREATE(dmalloc(&s.p1, G)); MZ_CREATE(dmalloc(&s.p2, G)); MZ_CREATE(dmalloc(&s.player, G)); MZ_CREATE(dmalloc(&s.T, G));
     MZ_CREATE(dmalloc(&s.status, G)); MZ_CREATE(dmalloc(&s.game_id, G));
+    MZ_CREATE(dmalloc(&s.fin_list, G));
     MZ_CREATE(dmalloc(&s.h_p1, G * Tm)); MZ_CREATE(dmalloc(&s.h_p2, G * Tm)); MZ_CREATE(dmalloc(&s.h_action, G * Tm));
     MZ_CREATE(dmalloc(&s.h_reward, G * Tm)); MZ_CREATE(dmalloc(&s.h_to_play, G * Tm)); MZ_CREATE(dmalloc(&s.h_cv, G * Tm * P.A)); MZ_CREATE(dmalloc(&s.h_rv, G * Tm));
     MZ_CREATE(cudaMemset(s.status, 0, G * sizeof(int32_t)));
+    MZ_CREATE(cudaMemset(s.h_p1, 0, G * Tm * sizeof(uint64_t))); MZ_CREATE(cudaMemset(s.h_p2, 0, G * Tm * sizeof(uint64_t)));   // the board before move 0 is empty
     mz_ring &r = c->ring; r.capacity = (int64_t)R;
     MZ_CREATE(dmalloc(&r.game_id, R)); MZ_CREATE(dmalloc(&r.T, R));
     MZ_CREATE(dmalloc(&r.h_p1, R * Tm)); MZ_CREATE(dmalloc(&r.h_p2, R * Tm)); MZ_CREATE(dmalloc(&r.h_action, R * Tm));
@@ -371,6 +374,8 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(dmalloc(&c->d_stats, 64)); MZ_CREATE(cudaMemset(c->d_stats, 0, 64 * sizeof(unsigned long long)));
     MZ_CREATE(dmalloc(&c->d_lossout, 8));
     MZ_CREATE(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(int64_t)));
+    MZ_CREATE(cudaMallocHost((void **)&c->h_wave, 16 * sizeof(int64_t)));
+    for (int i = 0; i < 2; i++) MZ_CREATE(cudaEventCreateWithFlags(&c->ev_wave[i], cudaEventDisableTiming));
     MZ_CREATE(cudaMallocHost((void **)&c->h_lossout, 8 * sizeof(double)));
     MZ_CREATE(cudaMallocHost((void **)&c->h_stats, 64 * sizeof(unsigned long long)));
     MZ_CREATE(cudaDeviceSynchronize());
@@ -386,7 +391,7 @@ int mz_destroy(mz_ctx *c) {
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
-                    c->slots.status, c->slots.game_id, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
+                    c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
                     c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale, c->batch.weights, c->d_pv, c->d_pr, c->d_pp,
@@ -394,6 +399,8 @@ int mz_destroy(mz_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &b : c->scratch) b.release();
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_wave) cudaFreeHost(c->h_wave);
+    for (int i = 0; i < 2; i++) if (c->ev_wave[i]) cudaEventDestroy(c->ev_wave[i]);
     if (c->h_lossout) cudaFreeHost(c->h_lossout);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -616,14 +623,18 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
     a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
     a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;
     int64_t total_moves = 0;
+    // The host runs one iteration behind the device: iteration k (opponent plies, search, save/refill, counter snapshot) is queued before
+    // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,
+    // the iteration already queued finds every slot idle: each search CTA returns at its first instruction.
+    auto snapshot = [&](int i) -> int {
+        MZ_CUDA(c, cudaMemcpyAsync(c->h_wave + 8 * i, c->ring.counters, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaEventRecord(c->ev_wave[i], c->stream));
+        return MZ_OK;
+    };
     { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
-    for (int64_t guard = 0;; guard++) {
-        MZ_CUDA(c, cudaGetLastError());
-        MZ_TRY(read_counters(c));
-        int64_t active = c->h_counters[5];
-        if (active == 0) break;
-        if (guard > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
-        total_moves += active;
+    MZ_TRY(snapshot(0));
+    for (int64_t k = 0;; k++) {
+        if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         if (arena_player != 0) { launch_scope ls(c, 6); mz_k_opponent_move<<<(G + 127) / 128, 128, 0, c->stream>>>(P, c->slots, G); }
         if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
@@ -634,7 +645,19 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
         } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        const size_t search_entry = c->timed.size();                       // (timing builds) index just past this iteration's search launch
         { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
+        MZ_TRY(snapshot((int)((k + 1) & 1)));
+        MZ_CUDA(c, cudaGetLastError());
+        MZ_CUDA(c, cudaEventSynchronize(c->ev_wave[k & 1]));
+        const int64_t active = c->h_wave[8 * (k & 1) + 5];                 // games active when iteration k started
+        if (active == 0) {
+            // the iteration just queued is the idle one: keep it out of the per-family kernel statistics (family 7 = idle)
+            for (size_t i = search_entry; i-- > 0;) if (c->timed[i].family == 0) { c->timed[i].family = 7; break; }
+            if (c->timed.size() > search_entry) c->timed[search_entry].family = 7;
+            break;
+        }
+        total_moves += active;
     }
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));

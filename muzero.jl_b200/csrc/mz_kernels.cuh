@@ -32,6 +32,7 @@ enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 };
 
 struct mz_slots {          // device-resident concurrent games, SoA
     uint64_t *p1, *p2; int32_t *player, *T, *status; int64_t *game_id;
+    int32_t *fin_list;       // [G] scratch of mz_k_save_refill: the finished slots in slot order
     // per-slot GameHistory under construction (src/Constructors.jl:6-16); boards are kept as bit masks
     uint64_t *h_p1, *h_p2;   // [G][Tmax] board before move i
     int32_t *h_action;       // [G][Tmax]
@@ -179,9 +180,21 @@ __device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const m
 
 // GT = threads per network group: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps for the same work; the tree
 // phases still use 8 lanes x 32 trees = the first 256 threads).
+// Self-play launches run one iteration ahead of the host (run_wave, mz_api.cu): a CTA none of whose slots has a ply to search -- every
+// CTA of the iteration queued past the end of a wave -- returns at its first instruction, before any barrier, TMA or TMEM state exists.
+template <int MODE>
+__device__ __forceinline__ bool mz_cta_idle(const mz_params &P, const mz_search_args &a, int rows_per_cta) {
+    if (MODE != MZ_MODE_SLOTS) return false;
+    int any = 0;
+    const int64_t g = (int64_t)blockIdx.x * rows_per_cta + threadIdx.x;
+    if ((int)threadIdx.x < rows_per_cta && g < a.n) any = a.slots.status[g] == MZ_SLOT_ACTIVE && (P.arena_player == 0 || a.slots.player[g] == P.arena_player);
+    return __syncthreads_or(any) == 0;
+}
+
 template <int MODE, int GT = MZ_GROUP>
 __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
+    if (mz_cta_idle<MODE>(P, a, MZ_ROWS)) return;
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
     constexpr int NT = 2 * GT;
     const int tid = threadIdx.x;
@@ -435,59 +448,74 @@ __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n,
 // save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
 __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr) {
-    __shared__ int scan[1024];
-    __shared__ int64_t base_key, next_game, end_game;
-    __shared__ int carry_fin, carry_free, active_count;
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ int active_count;
     __shared__ long long add_steps, add_samples;
-    const int tid = threadIdx.x;
-    if (tid == 0) { base_key = r.counters[0]; next_game = r.counters[3]; end_game = r.counters[4]; carry_fin = 0; carry_free = 0; active_count = 0; add_steps = 0; add_samples = 0; }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base_key = r.counters[0], next_game = r.counters[3], end_game = r.counters[4];
+    if (tid == 0) { active_count = 0; add_steps = 0; add_samples = 0; }
+    // thread t owns the contiguous slots [t*K, (t+1)*K): one exclusive scan over the CTA gives every finished slot its rank in slot
+    // order (= the order game numbers are handed out in) and every free slot its rank among the free ones
+    const int K = (n_slots + 1023) / 1024, lo = tid * K, hi = lo + K < n_slots ? lo + K : n_slots;
+    unsigned long long mine = 0;                                           // finished count << 32 | free count
+    for (int g = lo; g < hi; g++) { const int st = s.status[g]; mine += ((unsigned long long)(st == MZ_SLOT_FINISHED) << 32) | (unsigned long long)(st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE); }
+    unsigned long long inc = mine;
+    for (int off = 1; off < 32; off <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
+    if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
-    for (int start = 0; start < n_slots; start += 1024) {
-        int g = start + tid;
-        int st = g < n_slots ? s.status[g] : MZ_SLOT_ACTIVE;
-        int fin = st == MZ_SLOT_FINISHED ? 1 : 0;
-        int fre = (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) ? 1 : 0;
-        // inclusive scans of fin and fre (packed: fin in the high half)
-        int v = (fin << 16) | fre;
-        scan[tid] = v; __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) { int t = tid >= off ? scan[tid - off] : 0; __syncthreads(); scan[tid] += t; __syncthreads(); }
-        int inc = scan[tid];
-        int fin_rank = carry_fin + (inc >> 16) - fin, free_rank = carry_free + (inc & 0xffff) - fre;
-        int tot = scan[1023];
-        __syncthreads();
-        if (fin) {   // copy this GameHistory into the ring under key = num_played_games + rank + 1 (:149-154)
-            int64_t key = base_key + fin_rank + 1;
-            int64_t pos = (key - 1) % r.capacity;
-            int T = s.T[g];
-            if (key > r.capacity) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)(-(long long)r.T[pos]));   // evicted history (:156-160)
+    unsigned long long before = 0, total = 0;
+    for (int w = 0; w < 32; w++) { const unsigned long long t = warp_tot[w]; if (w < warp) before += t; total += t; }
+    const unsigned long long excl = before + inc - mine;
+    int fin_rank = (int)(excl >> 32), free_rank = (int)(excl & 0xffffffffu);
+    const int total_fin = (int)(total >> 32), total_free = (int)(total & 0xffffffffu);
+    int nact = 0; long long steps = 0, samples = 0;
+    for (int g = lo; g < hi; g++) {
+        const int st = s.status[g];
+        if (st == MZ_SLOT_FINISHED) {   // this GameHistory goes into the ring under key = num_played_games + rank + 1 (:149-154)
+            const int64_t key = base_key + fin_rank + 1, pos = (key - 1) % r.capacity;
+            const int T = s.T[g];
+            if (key > r.capacity) samples -= (long long)r.T[pos];          // evicted history (:156-160)
             r.game_id[pos] = s.game_id[g]; r.T[pos] = T; r.reanalysed[pos] = 0;
-            for (int i = 0; i < P.Tmax; i++) {
-                size_t so = (size_t)g * P.Tmax + i, ro = (size_t)pos * P.Tmax + i;
-                r.h_p1[ro] = s.h_p1[so]; r.h_p2[ro] = s.h_p2[so]; r.h_action[ro] = s.h_action[so]; r.h_reward[ro] = s.h_reward[so];
-                r.h_to_play[ro] = s.h_to_play[so]; r.h_rv[ro] = s.h_rv[so];
-                for (int a = 0; a < P.A; a++) r.h_cv[ro * P.A + a] = s.h_cv[so * P.A + a];
-            }
-            atomicAdd((unsigned long long *)&add_steps, (unsigned long long)T);
-            atomicAdd((unsigned long long *)&add_samples, (unsigned long long)T);
-            if (P.per) mz_per_init_game(P, r, pos);                         // initial priorities (:136-145)
+            s.fin_list[fin_rank] = g;
+            steps += T; samples += T;
             if (arena_tally && P.arena_tally != 0)                           // competitive play: wins / draws / losses for MuZero
                 atomicAdd(&arena_tally[1 - mz_arena_outcome(P, T, s.h_action + (size_t)g * P.Tmax, P.arena_tally)], 1ull);
+            fin_rank++;
         }
-        if (fre) {
-            int64_t id = next_game + free_rank;
+        if (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) {
+            const int64_t id = next_game + free_rank;
             if (id < end_game) {
                 s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1;   // reset! (game.jl:15-20)
-                s.h_p1[(size_t)g * P.Tmax] = 0; s.h_p2[(size_t)g * P.Tmax] = 0;
-                atomicAdd(&active_count, 1);
+                nact++;                                                   // (the board before move 0 is empty in every history: h_p1/h_p2[g][0] stay 0)
             } else s.status[g] = MZ_SLOT_IDLE;
-        } else if (g < n_slots && st == MZ_SLOT_ACTIVE) atomicAdd(&active_count, 1);
-        __syncthreads();
-        if (tid == 0) { carry_fin += tot >> 16; carry_free += tot & 0xffff; }
-        __syncthreads();
+            free_rank++;
+        } else if (st == MZ_SLOT_ACTIVE) nact++;
     }
+    if (nact) atomicAdd(&active_count, nact);
+    if (steps) atomicAdd((unsigned long long *)&add_steps, (unsigned long long)steps);
+    if (samples) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)samples);
+    __syncthreads();
+    // the copies, spread over the whole CTA, one loop per array: a warp never diverges and the loads of several iterations are in
+    // flight together (one thread copying its own game is a chain of ~250 dependent load -> store round trips)
+    const int rows = total_fin * P.Tmax;
+#define MZ_COPY_ROWS(FIELD) _Pragma("unroll 4") for (int idx = tid; idx < rows; idx += 1024) { const int j = idx / P.Tmax, i = idx - j * P.Tmax; \
+        r.FIELD[(size_t)((base_key + j) % r.capacity) * P.Tmax + i] = s.FIELD[(size_t)s.fin_list[j] * P.Tmax + i]; }
+    MZ_COPY_ROWS(h_p1) MZ_COPY_ROWS(h_p2) MZ_COPY_ROWS(h_action) MZ_COPY_ROWS(h_reward) MZ_COPY_ROWS(h_to_play) MZ_COPY_ROWS(h_rv)
+#undef MZ_COPY_ROWS
+    const int row_cv = P.Tmax * P.A;
+#pragma unroll 4
+    for (int idx = tid; idx < total_fin * row_cv; idx += 1024) {
+        const int j = idx / row_cv, e = idx - j * row_cv;
+        r.h_cv[(size_t)((base_key + j) % r.capacity) * row_cv + e] = s.h_cv[(size_t)s.fin_list[j] * row_cv + e];
+    }
+    if (P.per) {                                                            // initial priorities (:136-145), from the stored histories
+        __syncthreads();
+        for (int j = tid; j < total_fin; j += 1024) mz_per_init_game(P, r, (base_key + j) % r.capacity);
+    }
+    __syncthreads();
     if (tid == 0) {
-        int64_t handed = next_game + carry_free < end_game ? carry_free : (end_game - next_game > 0 ? end_game - next_game : 0);
-        r.counters[0] = base_key + carry_fin;
+        const int64_t handed = next_game + total_free < end_game ? total_free : (end_game - next_game > 0 ? end_game - next_game : 0);
+        r.counters[0] = base_key + total_fin;
         r.counters[1] += add_steps;
         r.counters[2] += add_samples;
         r.counters[3] = next_game + handed;

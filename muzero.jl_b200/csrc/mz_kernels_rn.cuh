@@ -499,6 +499,7 @@ template <int MODE>
 __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_constant__ mz_params P, const __grid_constant__ mz_rn_params R, const mz_search_rn_args ta) {
     extern __shared__ __align__(1024) unsigned char mz_smem_rn[];
     const mz_search_args &a = ta.base;
+    if (mz_cta_idle<MODE>(P, a, R.ntrees)) return;
     mz_rn_exec X;
     mz_rn_setup(X, P, R, ta, mz_smem_rn);
     const mz_rn_plan &sp = X.sp;

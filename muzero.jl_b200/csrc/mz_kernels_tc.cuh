@@ -16,6 +16,7 @@ template <int MODE>
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_constant__ mz_params P, const mz_search_tc_args ta) {
     extern __shared__ __align__(1024) unsigned char mz_smem_tc[];
     const mz_search_args &a = ta.base;
+    if (mz_cta_idle<MODE>(P, a, MZ_ROWS)) return;
     const mz_tc_plan sp = mz_tc_carve(mz_smem_tc, P.tc_net_off[3], P.tc_bias_floats, P.hidden_pad, P.S);
     const int tid = threadIdx.x;
     const int r = tid >> 3, ln = tid & (MZ_LANES - 1);
