@@ -357,7 +357,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     mz_slots &s = c->slots;
     MZ_CREATE(dmalloc(&s.p1, G)); MZ_CREATE(dmalloc(&s.p2, G)); MZ_CREATE(dmalloc(&s.player, G)); MZ_CREATE(dmalloc(&s.T, G));
     MZ_CREATE(dmalloc(&s.status, G)); MZ_CREATE(dmalloc(&s.game_id, G));
-    MZ_CREATE(dmalloc(&s.fin_list, G));
+    MZ_CREATE(dmalloc(&s.fin_list, G + 4));
     MZ_CREATE(dmalloc(&s.h_p1, G * Tm)); MZ_CREATE(dmalloc(&s.h_p2, G * Tm)); MZ_CREATE(dmalloc(&s.h_action, G * Tm));
     MZ_CREATE(dmalloc(&s.h_reward, G * Tm)); MZ_CREATE(dmalloc(&s.h_to_play, G * Tm)); MZ_CREATE(dmalloc(&s.h_cv, G * Tm * P.A)); MZ_CREATE(dmalloc(&s.h_rv, G * Tm));
     MZ_CREATE(cudaMemset(s.status, 0, G * sizeof(int32_t)));
@@ -606,6 +606,13 @@ int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32
 }
 
 // ---- self-play ---------------------------------------------------------------------------------------------
+// save_game + refill: number the finished games and hand out new ones (one CTA, ordered), copy their histories (many CTAs), priorities
+static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally) {
+    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
+    { launch_scope ls(c, 1); mz_k_save_copy<<<c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
+    if (P.per) { launch_scope ls(c, 1); mz_k_save_per<<<(G + 255) / 256 < c->sm_count ? (G + 255) / 256 : c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
+    return MZ_OK;
+}
 // one wave of games on the slots; arena_player != 0: competitive play, `arena_opponent` moves for the other side
 static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
     if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
@@ -631,7 +638,7 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
         MZ_CUDA(c, cudaEventRecord(c->ev_wave[i], c->stream));
         return MZ_OK;
     };
-    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
+    MZ_TRY(launch_save_refill(c, P, G, tally));
     MZ_TRY(snapshot(0));
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
@@ -646,7 +653,7 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
         } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         const size_t search_entry = c->timed.size();                       // (timing builds) index just past this iteration's search launch
-        { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
+        MZ_TRY(launch_save_refill(c, P, G, tally));
         MZ_TRY(snapshot((int)((k + 1) & 1)));
         MZ_CUDA(c, cudaGetLastError());
         MZ_CUDA(c, cudaEventSynchronize(c->ev_wave[k & 1]));

@@ -65,6 +65,7 @@ inline const char *validate(const mz_config &c) {
     if (c.num_unroll_steps < 0 || c.num_unroll_steps > 32 || c.td_steps < 0 || c.td_steps > 64) return "unroll/td steps out of range";
     if (c.width_hidden < 4 || c.width_hidden % 4) return "width_hidden must be a positive multiple of 4";
     if (c.batch_size < 1 || c.replay_buffer_size < 1 || c.num_slots < 1) return "batch_size, replay_buffer_size, num_slots must be positive";
+    if (c.num_slots > 65536) return "num_slots must be <= 65536 (mz_k_save_refill keeps a 64-bit mask of the slots each of its 1024 threads owns)";
     int order_seen = 0;
     for (int i = 0; i < c.A; i++) { if (c.child_order[i] < 1 || c.child_order[i] > c.A) return "child_order must be a permutation of 1..A"; order_seen |= 1 << (c.child_order[i] - 1); }
     if (order_seen != (1 << c.A) - 1) return "child_order must be a permutation of 1..A";

@@ -32,7 +32,7 @@ enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 };
 
 struct mz_slots {          // device-resident concurrent games, SoA
     uint64_t *p1, *p2; int32_t *player, *T, *status; int64_t *game_id;
-    int32_t *fin_list;       // [G] scratch of mz_k_save_refill: the finished slots in slot order
+    int32_t *fin_list;       // [G + 4] scratch of mz_k_save_refill: the finished slots in slot order, their number, the first key - 1
     // per-slot GameHistory under construction (src/Constructors.jl:6-16); boards are kept as bit masks
     uint64_t *h_p1, *h_p2;   // [G][Tmax] board before move i
     int32_t *h_action;       // [G][Tmax]
@@ -447,6 +447,7 @@ __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n,
 
 // save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
+#define MZ_SAVE_MAX_K 64   // slots per thread of mz_k_save_refill: num_slots <= 65536
 __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ int active_count;
@@ -454,11 +455,16 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t base_key = r.counters[0], next_game = r.counters[3], end_game = r.counters[4];
     if (tid == 0) { active_count = 0; add_steps = 0; add_samples = 0; }
-    // thread t owns the contiguous slots [t*K, (t+1)*K): one exclusive scan over the CTA gives every finished slot its rank in slot
-    // order (= the order game numbers are handed out in) and every free slot its rank among the free ones
+    // (1) thread t owns the contiguous slots [t*K, (t+1)*K): one exclusive scan over the CTA gives every finished slot its rank in slot
+    //     order (= the order game numbers are handed out in) and every free slot its rank among the free ones
     const int K = (n_slots + 1023) / 1024, lo = tid * K, hi = lo + K < n_slots ? lo + K : n_slots;
-    unsigned long long mine = 0;                                           // finished count << 32 | free count
-    for (int g = lo; g < hi; g++) { const int st = s.status[g]; mine += ((unsigned long long)(st == MZ_SLOT_FINISHED) << 32) | (unsigned long long)(st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE); }
+    unsigned long long fin_bits = 0, free_bits = 0;                        // per owned slot (K <= 64)
+    for (int i = 0; lo + i < hi; i++) {
+        const int st = s.status[lo + i];
+        if (st == MZ_SLOT_FINISHED) fin_bits |= 1ull << i;
+        if (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) free_bits |= 1ull << i;
+    }
+    const unsigned long long mine = ((unsigned long long)__popcll(fin_bits) << 32) | (unsigned long long)__popcll(free_bits);
     unsigned long long inc = mine;
     for (int off = 1; off < 32; off <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += t; }
     if (lane == 31) warp_tot[warp] = inc;
@@ -466,52 +472,40 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
     unsigned long long before = 0, total = 0;
     for (int w = 0; w < 32; w++) { const unsigned long long t = warp_tot[w]; if (w < warp) before += t; total += t; }
     const unsigned long long excl = before + inc - mine;
-    int fin_rank = (int)(excl >> 32), free_rank = (int)(excl & 0xffffffffu);
+    const int fin_rank0 = (int)(excl >> 32), free_rank0 = (int)(excl & 0xffffffffu);
     const int total_fin = (int)(total >> 32), total_free = (int)(total & 0xffffffffu);
-    int nact = 0; long long steps = 0, samples = 0;
-    for (int g = lo; g < hi; g++) {
-        const int st = s.status[g];
-        if (st == MZ_SLOT_FINISHED) {   // this GameHistory goes into the ring under key = num_played_games + rank + 1 (:149-154)
-            const int64_t key = base_key + fin_rank + 1, pos = (key - 1) % r.capacity;
-            const int T = s.T[g];
-            if (key > r.capacity) samples -= (long long)r.T[pos];          // evicted history (:156-160)
-            r.game_id[pos] = s.game_id[g]; r.T[pos] = T; r.reanalysed[pos] = 0;
-            s.fin_list[fin_rank] = g;
-            steps += T; samples += T;
-            if (arena_tally && P.arena_tally != 0)                           // competitive play: wins / draws / losses for MuZero
-                atomicAdd(&arena_tally[1 - mz_arena_outcome(P, T, s.h_action + (size_t)g * P.Tmax, P.arena_tally)], 1ull);
-            fin_rank++;
-        }
-        if (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) {
-            const int64_t id = next_game + free_rank;
-            if (id < end_game) {
-                s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1;   // reset! (game.jl:15-20)
-                nact++;                                                   // (the board before move 0 is empty in every history: h_p1/h_p2[g][0] stay 0)
-            } else s.status[g] = MZ_SLOT_IDLE;
-            free_rank++;
-        } else if (st == MZ_SLOT_ACTIVE) nact++;
+    for (unsigned long long m = fin_bits; m; m &= m - 1) s.fin_list[fin_rank0 + __popcll(fin_bits & ((m & (0ull - m)) - 1ull))] = lo + __ffsll((long long)m) - 1;
+    __syncthreads();
+    // (2) save_game for finished game j (slot fin_list[j]) under key = num_played_games + j + 1 (:149-154); all games in parallel
+    long long steps = 0, samples = 0;
+    for (int j = tid; j < total_fin; j += 1024) {
+        const int g = s.fin_list[j];
+        const int64_t key = base_key + j + 1, pos = (key - 1) % r.capacity;
+        const int T = s.T[g];
+        if (key > r.capacity) samples -= (long long)r.T[pos];              // evicted history (:156-160)
+        r.game_id[pos] = s.game_id[g]; r.T[pos] = T; r.reanalysed[pos] = 0;
+        steps += T; samples += T;
+        if (arena_tally && P.arena_tally != 0)                               // competitive play: wins / draws / losses for MuZero
+            atomicAdd(&arena_tally[1 - mz_arena_outcome(P, T, s.h_action + (size_t)g * P.Tmax, P.arena_tally)], 1ull);
     }
-    if (nact) atomicAdd(&active_count, nact);
     if (steps) atomicAdd((unsigned long long *)&add_steps, (unsigned long long)steps);
     if (samples) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)samples);
+    //     the histories themselves are copied by mz_k_save_copy (many CTAs: one CTA moves ~1 MB far too slowly), which reads
+    //     {first key - 1, number of games} from the two words after the list
+    if (tid == 0) { s.fin_list[n_slots] = total_fin; reinterpret_cast<int64_t *>(s.fin_list + n_slots + 2)[0] = base_key; }
     __syncthreads();
-    // the copies, spread over the whole CTA, one loop per array: a warp never diverges and the loads of several iterations are in
-    // flight together (one thread copying its own game is a chain of ~250 dependent load -> store round trips)
-    const int rows = total_fin * P.Tmax;
-#define MZ_COPY_ROWS(FIELD) _Pragma("unroll 4") for (int idx = tid; idx < rows; idx += 1024) { const int j = idx / P.Tmax, i = idx - j * P.Tmax; \
-        r.FIELD[(size_t)((base_key + j) % r.capacity) * P.Tmax + i] = s.FIELD[(size_t)s.fin_list[j] * P.Tmax + i]; }
-    MZ_COPY_ROWS(h_p1) MZ_COPY_ROWS(h_p2) MZ_COPY_ROWS(h_action) MZ_COPY_ROWS(h_reward) MZ_COPY_ROWS(h_to_play) MZ_COPY_ROWS(h_rv)
-#undef MZ_COPY_ROWS
-    const int row_cv = P.Tmax * P.A;
-#pragma unroll 4
-    for (int idx = tid; idx < total_fin * row_cv; idx += 1024) {
-        const int j = idx / row_cv, e = idx - j * row_cv;
-        r.h_cv[(size_t)((base_key + j) % r.capacity) * row_cv + e] = s.h_cv[(size_t)s.fin_list[j] * row_cv + e];
+    // (3) hand the next game ids to the free slots, in slot order; reset! (game.jl:15-20).  The board before move 0 is empty in every
+    //     history, so h_p1 / h_p2 [g][0] stay zero.
+    int nact = 0, free_rank = free_rank0;
+    for (int i = 0; lo + i < hi; i++) {
+        const int g = lo + i;
+        if ((free_bits >> i) & 1ull) {
+            const int64_t id = next_game + free_rank++;
+            if (id < end_game) { s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1; nact++; }
+            else s.status[g] = MZ_SLOT_IDLE;
+        } else nact++;                                                     // neither finished nor idle: active
     }
-    if (P.per) {                                                            // initial priorities (:136-145), from the stored histories
-        __syncthreads();
-        for (int j = tid; j < total_fin; j += 1024) mz_per_init_game(P, r, (base_key + j) % r.capacity);
-    }
+    if (nact) atomicAdd(&active_count, nact);
     __syncthreads();
     if (tid == 0) {
         const int64_t handed = next_game + total_free < end_game ? total_free : (end_game - next_game > 0 ? end_game - next_game : 0);
@@ -521,6 +515,33 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
         r.counters[3] = next_game + handed;
         r.counters[5] = active_count;
     }
+}
+
+// The GameHistory arrays of the games mz_k_save_refill has just numbered: slot fin_list[j] -> ring position of key base_key + j + 1.
+// Reads nothing that the refill resets (the per-slot history arrays are overwritten only by the next game's plies, after this kernel).
+__global__ void __launch_bounds__(256) mz_k_save_copy(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
+    const int total_fin = s.fin_list[n_slots];
+    if (total_fin == 0) return;
+    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + n_slots + 2)[0];
+    const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rows = total_fin * P.Tmax;
+    for (int idx = t0; idx < rows; idx += nthreads) {
+        const int j = idx / P.Tmax, i = idx - j * P.Tmax;
+        const size_t so = (size_t)s.fin_list[j] * P.Tmax + i, ro = (size_t)((base_key + j) % r.capacity) * P.Tmax + i;
+        r.h_p1[ro] = s.h_p1[so]; r.h_p2[ro] = s.h_p2[so]; r.h_action[ro] = s.h_action[so]; r.h_reward[ro] = s.h_reward[so];
+        r.h_to_play[ro] = s.h_to_play[so]; r.h_rv[ro] = s.h_rv[so];
+    }
+    const int row_cv = P.Tmax * P.A;
+    for (int idx = t0; idx < total_fin * row_cv; idx += nthreads) {
+        const int j = idx / row_cv, e = idx - j * row_cv;
+        r.h_cv[(size_t)((base_key + j) % r.capacity) * row_cv + e] = s.h_cv[(size_t)s.fin_list[j] * row_cv + e];
+    }
+}
+// initial priorities of the games just saved (save_game, ReplayBuffer.jl:136-145), from the stored histories
+__global__ void mz_k_save_per(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
+    const int total_fin = s.fin_list[n_slots];
+    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + n_slots + 2)[0];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total_fin; j += gridDim.x * blockDim.x) mz_per_init_game(P, r, (base_key + j) % r.capacity);
 }
 
 // ---- batched network callables (init_*(hyper) callables, src/Learning.jl:87-142) -------------------
