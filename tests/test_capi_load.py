@@ -47,6 +47,14 @@ def test_invalid_config_is_rejected_with_message():
     assert b"hidden_state_size" in capi.lib().mz_last_error(None)
 
 
+def test_slot_count_limit_is_reported():
+    from muzero_jl_b200 import capi
+    c = capi.default_config(num_slots=65537)
+    assert capi.lib().mz_num_params(C.byref(c), 3) == capi.E_ARG
+    assert b"num_slots" in capi.lib().mz_last_error(None)
+    assert capi.lib().mz_num_params(C.byref(capi.default_config(num_slots=65536)), 3) == 74881
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
