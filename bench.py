@@ -150,9 +150,14 @@ def cpu_baseline(ocfg, blob, target_s):
     per_game = 8.3 * ocfg.num_iters
     games = int(max(threads, min(200000, rate * target_s / per_game)))
     rate, sims, dt = cpu_self_play_rate(ocfg, blob, games, threads)
+    # the reference's own topology runs ONE self-play actor (games/tictactoe/main.jl:30): the same port on one thread, ~2 s
+    g1 = int(max(4, rate / threads * 2.0 / per_game))
+    rate1, sims1, dt1 = cpu_self_play_rate(ocfg, blob, g1, 1, first_game=2 * 10 ** 6)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d self-play games (%d simulations) on %d host threads, %.1f s; C restatement of the reference "
-                      "(oracle/mz_oracle.c), the Julia reference cannot run in this image" % (games, sims, threads, dt)}
+                      "(oracle/mz_oracle.c), the Julia reference cannot run in this image" % (games, sims, threads, dt),
+            "single_actor": {"value": rate1, "unit": UNIT, "cores": 1,
+                             "sample": "%d games (%d simulations) on one thread, %.1f s: the reference's process topology has one self-play actor" % (g1, sims1, dt1)}}
 
 
 # ------------------------------------------------------------------------------------------------------------
