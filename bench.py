@@ -308,6 +308,25 @@ def run_b200(a):
             rn_extra = (rms, rsims, rk_ms, rk_n, Gr)
             ctx_rn.close()
         barrier()
+        # ---- strong scaling ("also report fixed total G"): the 4096 games of the 1-GPU workload split over the ranks ----
+        strong = None
+        if world > 1:
+            Gs = max(32, G // world)
+            ctx_s = capi.Context(capi.default_config(num_slots=Gs, num_iters=S, replay_buffer_size=max(10000, Gs)), device=local, stream=stream.cuda_stream)
+            ctx_s.set_weights(blob)
+            for i in range(a.warmup):
+                ctx_s.self_play(game_base + i * Gs, Gs, 1.0)
+            sms, ssims = 0.0, 0
+            for i in range(a.steps):
+                flush.zero_(); torch.cuda.synchronize(); barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                s_, _ = ctx_s.self_play(game_base + (a.warmup + i) * Gs, Gs, 1.0)
+                e1.record(stream); e1.synchronize()
+                sms += e0.elapsed_time(e1); ssims += s_
+            strong = (sms, ssims, Gs)
+            ctx_s.close()
+        barrier()
         # ---- learner: samples/s at the reference batch (32) ----
         learner = None
         if not a.no_learner:
@@ -359,12 +378,12 @@ def run_b200(a):
                     learner["large_batch"]["reference_l2"] = entry
             big.close()
 
-    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0, rn_extra[0] if rn_extra else 0.0], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0, rn_extra[1] if rn_extra else 0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0, rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0, rn_extra[1] if rn_extra else 0, strong[1] if strong else 0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max, rn_ms_max = [float(x) for x in t.cpu()]
-    sims_all, e2e_sims_all, launches_all, tc_sims_all, rn_sims_all = [float(x) for x in cnt.cpu()]
+    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max, rn_ms_max, strong_ms_max = [float(x) for x in t.cpu()]
+    sims_all, e2e_sims_all, launches_all, tc_sims_all, rn_sims_all, strong_sims_all = [float(x) for x in cnt.cpu()]
 
     if rank == 0:
         peaks = {}
@@ -408,6 +427,11 @@ def run_b200(a):
                                                 "achieved_per_clk_per_sm": wf_rate, "peak_per_clk_per_sm": 1.0, "frac": wf_rate, "sms_with_a_cta": ctas,
                                                 "note": "whole-launch average incl. the tree phases; inside the network phase the wavefront pipe is the bound "
                                                         "(64 wavefront-cycles vs 32 FMA-cycles per k step), which caps the FMA pipe at 50 %"}
+        if strong and strong_ms_max > 0:
+            out["strong_scaling"] = {"value": strong_sims_all / (strong_ms_max * 1e-3), "unit": UNIT, "ms_per_step": strong_ms_max / a.steps,
+                                     "games_total": strong[2] * world, "games_per_gpu": strong[2],
+                                     "note": "the 1-GPU workload split over the ranks (fixed total games); a move of the exact path is a latency chain "
+                                             "whose length does not depend on the number of trees per SM, so strong scaling is flat by construction"}
         if tc_extra:
             bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             tc_launch_s = (tc_extra[2] / max(tc_extra[3], 1)) * 1e-3
