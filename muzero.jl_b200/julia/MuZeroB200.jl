@@ -7,6 +7,8 @@
 # identical call sequence is exercised through the Python mirror (muzero.jl_b200/api.py) by the test-suite.
 module MuZeroB200
 
+import Serialization   # stdlib: checkpoint files of the reference (src/Learning.jl:431-433)
+
 const LIB = get(ENV, "MUZERO_B200_LIB", joinpath(@__DIR__, "..", "libmuzero_b200.so"))
 const MZ_MAX_A = 16
 
@@ -78,8 +80,11 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
 end
 
 # ---- networks: init_representation / init_prediction / init_dynamics (src/Learning.jl:87,100,118) ----------------
+# Flux is the reference's dependency, not this module's: its scripts load it into Main (src/Learning.jl:1-20), and it is looked up there
+# only when a Flux model is actually converted.
+_flux() = getfield(Main, :Flux)
 "Flatten a Flux Chain of Dense layers into the blob order of the ABI: per Dense `vec(W)` (column-major (out,in)) then `b`."
-flux_blob(model) = reduce(vcat, [vec(Float32.(p)) for p in Flux.params(model)])
+flux_blob(model) = reduce(vcat, [vec(Float32.(p)) for p in _flux().params(model)])
 """
 Blob of a (repaired) `ResNetHP` network (DESIGN.md §2.4): walks the Flux model in construction order; `Conv` -> `vec(weight)` (Flux's
 `(k,k,cin,cout)` column-major, flipped-kernel convention), `bias`; `BatchNorm` -> `β, γ, μ, σ²` (the running statistics are not in
@@ -87,20 +92,29 @@ Blob of a (repaired) `ResNetHP` network (DESIGN.md §2.4): walks the Flux model 
 field by field.
 """
 function flux_blob_resnet(model)
-    out = Float32[]
-    walk(l::Flux.Conv) = (append!(out, vec(Float32.(l.weight))); append!(out, Float32.(l.bias)))
-    walk(l::Flux.BatchNorm) = (append!(out, Float32.(l.β)); append!(out, Float32.(l.γ)); append!(out, Float32.(l.μ)); append!(out, Float32.(l.σ²)))
-    walk(l::Flux.Dense) = (append!(out, vec(Float32.(l.weight))); append!(out, Float32.(l.bias)))
-    walk(l::Union{Tuple,AbstractVector}) = foreach(walk, l)
-    walk(l::Function) = nothing
-    walk(l) = foreach(f -> walk(getfield(l, f)), fieldnames(typeof(l)))
+    F = _flux(); out = Float32[]
+    function walk(l)
+        if l isa F.Conv
+            append!(out, vec(Float32.(l.weight))); append!(out, Float32.(l.bias))
+        elseif l isa F.BatchNorm
+            append!(out, Float32.(l.β)); append!(out, Float32.(l.γ)); append!(out, Float32.(l.μ)); append!(out, Float32.(l.σ²))
+        elseif l isa F.Dense
+            append!(out, vec(Float32.(l.weight))); append!(out, Float32.(l.bias))
+        elseif l isa Function || l isa Number || l isa AbstractArray{<:Number} || l isa Nothing
+            nothing
+        elseif l isa Tuple || l isa AbstractVector
+            foreach(walk, l)
+        else
+            foreach(f -> walk(getfield(l, f)), fieldnames(typeof(l)))
+        end
+    end
     walk(model)
     return out
 end
 "Inverse of `flux_blob` for Dense chains: copies a blob into the parameters of a Flux model of the same architecture."
 function load_blob!(model, blob::Vector{Float32})
     off = 0
-    for p in Flux.params(model)
+    for p in _flux().params(model)
         n = length(p); copyto!(p, reshape(view(blob, off+1:off+n), size(p))); off += n
     end
     off == length(blob) || error("blob has $(length(blob)) floats, the model takes $off")
@@ -109,11 +123,11 @@ end
 """
 Checkpoint I/O in the reference's own format (src/Learning.jl:426-434 writes `\$(step)_representation.bin` etc. with `Serialization`;
 games/tictactoe/play.jl:12-14 reads them): `load_networks!` feeds Julia-trained Flux chains to the kernels, `save_networks` writes the
-engine's weights as Flux chains built by the reference's `init_*(hyper)` so that play.jl can `deserialize` them. Needs `Serialization`.
+engine's weights as Flux chains built by the reference's `init_*(hyper)` so that play.jl can `deserialize` them.
 """
 function load_networks!(e::Engine, networks_path::String, step::Integer; blob=flux_blob)
     for (net, name) in enumerate(("representation", "prediction", "dynamics"))
-        model = Main.Serialization.deserialize(joinpath(networks_path, "$(step)_$(name).bin"))
+        model = Serialization.deserialize(joinpath(networks_path, "$(step)_$(name).bin"))
         set_weights!(e, net - 1, blob(model))
     end
     return e
@@ -121,7 +135,7 @@ end
 function save_networks(e::Engine, networks_path::String, step::Integer, inits::NamedTuple, hyper)
     for (net, name) in enumerate((:representation, :prediction, :dynamics))
         model = load_blob!(getfield(inits, name)(hyper), get_weights(e, net - 1))
-        Main.Serialization.serialize(joinpath(networks_path, "$(step)_$(name).bin"), model)
+        Serialization.serialize(joinpath(networks_path, "$(step)_$(name).bin"), model)
     end
 end
 set_weights!(e::Engine, net::Integer, blob::Vector{Float32}) =
