@@ -357,7 +357,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     mz_slots &s = c->slots;
     MZ_CREATE(dmalloc(&s.p1, G)); MZ_CREATE(dmalloc(&s.p2, G)); MZ_CREATE(dmalloc(&s.player, G)); MZ_CREATE(dmalloc(&s.T, G));
     MZ_CREATE(dmalloc(&s.status, G)); MZ_CREATE(dmalloc(&s.game_id, G));
-    MZ_CREATE(dmalloc(&s.fin_list, G + 4));
+    MZ_CREATE(dmalloc(&s.fin_list, G + 6));
     MZ_CREATE(dmalloc(&s.h_p1, G * Tm)); MZ_CREATE(dmalloc(&s.h_p2, G * Tm)); MZ_CREATE(dmalloc(&s.h_action, G * Tm));
     MZ_CREATE(dmalloc(&s.h_reward, G * Tm)); MZ_CREATE(dmalloc(&s.h_to_play, G * Tm)); MZ_CREATE(dmalloc(&s.h_cv, G * Tm * P.A)); MZ_CREATE(dmalloc(&s.h_rv, G * Tm));
     MZ_CREATE(cudaMemset(s.status, 0, G * sizeof(int32_t)));

@@ -32,7 +32,7 @@ enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 };
 
 struct mz_slots {          // device-resident concurrent games, SoA
     uint64_t *p1, *p2; int32_t *player, *T, *status; int64_t *game_id;
-    int32_t *fin_list;       // [G + 4] scratch of mz_k_save_refill: the finished slots in slot order, their number, the first key - 1
+    int32_t *fin_list;       // [G + 6] scratch of mz_k_save_refill: the finished slots in slot order, their number, the first key - 1
     // per-slot GameHistory under construction (src/Constructors.jl:6-16); boards are kept as bit masks
     uint64_t *h_p1, *h_p2;   // [G][Tmax] board before move i
     int32_t *h_action;       // [G][Tmax]
@@ -448,6 +448,7 @@ __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n,
 // save_game (src/ReplayBuffer.jl:133-161) for every finished slot in slot order, then hand the next game ids to
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
 #define MZ_SAVE_MAX_K 64   // slots per thread of mz_k_save_refill: num_slots <= 65536
+#define MZ_FIN_KEY(n) (((n) + 3) & ~1)   // fin_list[n] = number of games; the 64-bit first key - 1 sits at the next 8-byte aligned pair (fin_list has n + 6 entries)
 __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ int active_count;
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
     if (samples) atomicAdd((unsigned long long *)&add_samples, (unsigned long long)samples);
     //     the histories themselves are copied by mz_k_save_copy (many CTAs: one CTA moves ~1 MB far too slowly), which reads
     //     {first key - 1, number of games} from the two words after the list
-    if (tid == 0) { s.fin_list[n_slots] = total_fin; reinterpret_cast<int64_t *>(s.fin_list + n_slots + 2)[0] = base_key; }
+    if (tid == 0) { s.fin_list[n_slots] = total_fin; reinterpret_cast<int64_t *>(s.fin_list + MZ_FIN_KEY(n_slots))[0] = base_key; }
     __syncthreads();
     // (3) hand the next game ids to the free slots, in slot order; reset! (game.jl:15-20).  The board before move 0 is empty in every
     //     history, so h_p1 / h_p2 [g][0] stay zero.
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
 __global__ void __launch_bounds__(256) mz_k_save_copy(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
     const int total_fin = s.fin_list[n_slots];
     if (total_fin == 0) return;
-    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + n_slots + 2)[0];
+    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + MZ_FIN_KEY(n_slots))[0];
     const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int rows = total_fin * P.Tmax;
     for (int idx = t0; idx < rows; idx += nthreads) {
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(256) mz_k_save_copy(const __grid_constant__ mz
 // initial priorities of the games just saved (save_game, ReplayBuffer.jl:136-145), from the stored histories
 __global__ void mz_k_save_per(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots) {
     const int total_fin = s.fin_list[n_slots];
-    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + n_slots + 2)[0];
+    const int64_t base_key = reinterpret_cast<const int64_t *>(s.fin_list + MZ_FIN_KEY(n_slots))[0];
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < total_fin; j += gridDim.x * blockDim.x) mz_per_init_game(P, r, (base_key + j) % r.capacity);
 }
 

@@ -81,6 +81,20 @@ def test_opponent_action_matches_oracle(capi):
     ctx.close()
 
 
+def test_odd_slot_count(capi):
+    """an odd number of slots (the save/refill scratch keeps a 64-bit key behind the slot list)"""
+    ctx, ocfg = make_ctx(capi, num_slots=37)
+    ctx.init_weights(8); blob = ctx.get_weights()
+    sims, _ = ctx.self_play(0, 90, 1.0)
+    o = O.self_play(ocfg, blob, 0, 90, 1.0, 4)
+    h = ctx.history_export()
+    assert sims == o["sims"]
+    for j in range(90):
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][int(h["game_id"][j])]), k
+    ctx.close()
+
+
 def test_arena_argument_errors(capi):
     ctx, _ = make_ctx(capi)
     ctx.init_weights(1)
