@@ -71,6 +71,24 @@ class FeedForwardHP:
 
 
 @dataclass
+class ResNetHP:
+    """src/Constructors.jl:77-90 (field names and defaults of the reference; the networks it describes are the repaired ones of
+    DESIGN.md 2.4: bf16 inference on the tensor cores, no learner)."""
+    num_blocks: int = 2
+    depth_representation: int = 1
+    num_filters: int = 64
+    conv_kernel_size: Tuple[int, int] = (3, 3)
+    num_second_head_filters: int = 2
+    num_first_head_filters: int = 1
+    batch_norm_momentum: float = 0.6
+    downsample: bool = False
+    hidden_state_size: int = 64          # width of the dense layers of the heads (the hidden STATE is (W, H, num_filters))
+    representation_output_size: Optional[int] = None
+    depth_policy: int = 1
+    depth_value: int = 1
+
+
+@dataclass
 class GameHistory:
     """src/Constructors.jl:6-16.  Arrays are in Julia memory order: observation_history[T][C][H][W]."""
     observation_history: np.ndarray
@@ -86,7 +104,8 @@ class GameHistory:
 
 def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.GAME_TICTACTOE, tie_mode=capi.TIE_PHILOX,
                  child_order=None, nn_mode=capi.NN_FP32_EXACT):
-    if hyper.use_batch_norm:
+    resnet = isinstance(hyper, ResNetHP)
+    if not resnet and hyper.use_batch_norm:
         raise NotImplementedError("use_batch_norm=true is not supported (default false, Constructors.jl:71)")
     if list(conf.action_space) != list(range(1, len(conf.action_space) + 1)):
         raise ValueError("action_space must be 1:A")
@@ -116,10 +135,21 @@ def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.G
         child_order = list(order)[:c.A]
     for i, a in enumerate(child_order):
         c.child_order[i] = a
-    for k in ("width_hidden", "depth_representation", "depth_prediction", "depth_dynamics", "depth_policy", "depth_value",
-              "depth_reward", "depth_state_head", "hidden_state_size"):
-        setattr(c, k, getattr(hyper, k))
-    c.reward_activation_tanh = 1 if hyper.reward_activation in ("tanh", np.tanh) else 0
+    if resnet:
+        if hyper.downsample:
+            raise NotImplementedError("downsample=true is not supported (default false, Constructors.jl:85)")
+        if hyper.conv_kernel_size[0] != hyper.conv_kernel_size[1] or hyper.depth_policy != hyper.depth_value:
+            raise NotImplementedError("square kernels and depth_policy == depth_value only (DESIGN.md 2.4)")
+        c.net_type = capi.NET_RESNET; nn_mode = capi.NN_BF16_TC
+        c.rn_num_blocks, c.rn_num_filters, c.rn_kernel = hyper.num_blocks, hyper.num_filters, hyper.conv_kernel_size[0]
+        c.rn_first_head_filters, c.rn_second_head_filters = hyper.num_first_head_filters, hyper.num_second_head_filters
+        c.depth_value = hyper.depth_value; c.width_hidden = hyper.hidden_state_size
+        c.hidden_state_size = c.W * c.H * hyper.num_filters
+    else:
+        for k in ("width_hidden", "depth_representation", "depth_prediction", "depth_dynamics", "depth_policy", "depth_value",
+                  "depth_reward", "depth_state_head", "hidden_state_size"):
+            setattr(c, k, getattr(hyper, k))
+        c.reward_activation_tanh = 1 if hyper.reward_activation in ("tanh", np.tanh) else 0
     c.per = 1 if conf.PER else 0          # repaired specification of the prioritised replay
     c.per_alpha = int(conf.PER_alpha)
     c.num_slots = num_slots

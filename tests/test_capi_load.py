@@ -79,8 +79,17 @@ def test_python_interface_mirrors_reference_names():
     for f in ("width_hidden", "depth_representation", "depth_prediction", "depth_dynamics", "depth_policy", "depth_value",
               "depth_reward", "depth_state_head", "use_batch_norm", "batch_norm_momentum", "hidden_state_size", "reward_activation"):
         assert hasattr(hp, f), f        # src/Constructors.jl:62-75
+    rhp = mz.ResNetHP()
+    for f in ("num_blocks", "depth_representation", "num_filters", "conv_kernel_size", "num_second_head_filters", "num_first_head_filters",
+              "batch_norm_momentum", "downsample", "hidden_state_size", "representation_output_size", "depth_policy", "depth_value"):
+        assert hasattr(rhp, f), f       # src/Constructors.jl:77-90
     from muzero_jl_b200.api import to_mz_config
     c = to_mz_config(conf, hp, num_slots=64)
+    from muzero_jl_b200 import capi
+    rc = to_mz_config(conf, rhp, num_slots=64); want = capi.resnet_config(num_slots=64, replay_buffer_size=rc.replay_buffer_size)
+    for name, _ in capi.MzConfig._fields_:
+        a_, b_ = getattr(rc, name), getattr(want, name)
+        assert (list(a_) == list(b_)) if hasattr(a_, "__len__") else (a_ == b_), name
     ref = O.default_config()
     o = common.oracle_config(c)
     for name, _ in O.Config._fields_:

@@ -118,6 +118,12 @@ def test_competitive_play_mirror_and_networks(capi):
     assert len(g.action_history) >= 5 and g.to_play_history[0] == 1
     with pytest.raises(ValueError):
         mz.competitive_play(eng, 1, opponent="nobody")
+    reng = mz.Engine(mz.Config(num_iters=6), mz.ResNetHP(), num_slots=28)                 # the reference's ResNetHP through the mirror
+    mz.init_networks(reng)
+    sims, moves = mz.self_play(reng, 40, 1.0)
+    assert sims == 6 * moves
+    rr = mz.competitive_play(reng, 20, opponent="expert", muzero_player=2)
+    assert rr["wins"] + rr["draws"] + rr["losses"] == 20
     res = []
     for slots in (32, 96):
         ctx = capi.Context(capi.default_config(num_slots=slots, num_iters=10, nn_mode=capi.NN_BF16_TC)); ctx.init_weights(2)
