@@ -205,6 +205,34 @@ class TicTacToe:
         full = ((int(p1[0]) | int(p2[0])) & 0x1ff) == 0x1ff
         return bool(full or legal[0] == 0)
 
+    # ---- the names of games/AbstractGame.jl (the interface a new game implements), as aliases of the verbs above ----
+    def execute_step(self, action: int):               # AbstractGame.jl:20: (observation, reward, done); reward for the mover (SelfPlay.jl:367)
+        obs = self(action)
+        return obs, float(self._last_reward[0]), bool(self._done[0])
+
+    def to_play(self):                                 # :30
+        return self.current_player()
+
+    def legal_actions(self):                           # :45
+        return self.legal_action_space()
+
+    def reset_game(self):                              # :56
+        return self.reset()
+
+    def close_game(self):                              # :63
+        return None
+
+    def expert_agent(self, game_id=0, move_idx=None):  # :91 raises "unimplemented" in the reference; here the one-ply expert of mz_arena
+        mv = bin(int(self.p1[0]) | int(self.p2[0])).count("1") + 1 if move_idx is None else move_idx
+        return int(self.engine.ctx.opponent_action(self.p1, self.p2, self.player, capi.OPP_EXPERT, [game_id], [mv])[0])
+
+    def action_to_string(self, action_number: int):    # :104
+        W, H, _ = self.engine.conf.observation_shape
+        return "cell (%d, %d)" % ((action_number - 1) % W + 1, (action_number - 1) // W + 1)
+
+    def get_observation(self):                         # :110
+        return self.observation()
+
 
 @dataclass
 class Node:

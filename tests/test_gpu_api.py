@@ -32,6 +32,17 @@ def test_reference_call_sequence(mz):
     assert env.legal_action_space() == [3, 6, 8, 9] and not env.is_terminated()
     env(3)
     assert env.is_terminated() and env.legal_action_space() == []
+    # the same through the names of games/AbstractGame.jl (:20-123): KAT-env-2, the mislabelled winner (Q15)
+    g = mz.TicTacToe(eng)
+    assert g.reset_game().shape == (3, 3, 3) and g.to_play() == 1 and g.legal_actions() == list(range(1, 10))
+    for a_ in (1, 2, 3, 5, 4, 8):
+        ob, rew, done = g.execute_step(a_)
+        assert rew == 0.0 and not done
+    assert g.expert_agent() in g.legal_actions()
+    ob, rew, done = g.execute_step(6)
+    assert done and rew == 1.0 and ob.shape == (3, 3, 3) and g.action_to_string(6) == "cell (3, 2)" and g.close_game() is None
+    g.reset_game(); g.execute_step(1); g.execute_step(4); g.execute_step(2); g.execute_step(5)
+    assert g.expert_agent() == 3                              # player 1 completes 1, 2, 3
     # NNs callables: shapes of the Flux chains
     st = np.zeros((1, 63), np.float32); st[0, 18:27] = 1
     h = NNs["representation"](st); v, p = NNs["prediction"](h)
