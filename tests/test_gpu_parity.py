@@ -483,3 +483,50 @@ def test_checkpoint_resume_is_bit_identical(capi, mode, tmp_path):
     ck2 = ctx2.checkpoint()
     assert ck2["steps_done"] == 7
     ctx2.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_randomised_configurations_bit_exact(capi, seed):
+    """self-play -> get_batch -> one learner step under randomly drawn hyper-parameters (network depths and widths of the state,
+    stacking depth, unroll / td steps, PUCT constants, discount, noise, temperature): every GameHistory, the batch and the updated
+    weights are bit-identical to the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    kw = dict(num_iters=int(rng.integers(3, 41)), stacked_observations=int(rng.integers(0, 3)), num_unroll_steps=int(rng.integers(1, 6)),
+              td_steps=int(rng.integers(1, 8)), batch_size=int(rng.integers(1, 70)), pb_c_base=int(rng.integers(50, 30000)),
+              pb_c_init=float(np.float32(rng.uniform(0.5, 2.5))), discount=float(np.float32(rng.uniform(0.8, 1.0))),
+              dirichlet_alpha=float(np.float32(rng.uniform(0.1, 1.0))), exploration_eps=float(np.float32(rng.choice([0.0, 0.25, 0.5]))),
+              depth_representation=int(rng.integers(0, 4)), depth_prediction=int(rng.integers(0, 4)), depth_dynamics=int(rng.integers(0, 4)),
+              depth_policy=int(rng.integers(0, 3)), depth_value=int(rng.integers(0, 3)), depth_reward=int(rng.integers(0, 3)),
+              depth_state_head=int(rng.integers(0, 4)), width_hidden=int(rng.choice([32, 48, 64])),
+              intermediate_rewards=int(rng.integers(0, 2)), seed=int(rng.integers(1, 1 << 30)), num_slots=int(rng.integers(8, 100)))
+    temperature = float(rng.choice([0.0, 0.5, 1.0]))
+    games = int(rng.integers(20, 120))
+    ctx, ocfg = make_ctx(capi, replay_buffer_size=512, **kw)
+    ctx.init_weights(seed + 40); blob = ctx.get_weights()
+    sims, moves = ctx.self_play(10, games, temperature)
+    o = O.self_play(ocfg, blob, 10, games, temperature, 4)
+    assert sims == o["sims"] and moves == int(o["T"].sum()), kw
+    h = ctx.history_export()
+    for j in range(games):
+        i = int(h["game_id"][j]) - 10
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][i]), (k, i, kw)
+    # rebuild the buffer in game-id order (the ring's key order is the save order) and compare batch + learner step
+    ctx.replay_clear()
+    hist = {k: o[k] for k in common.HIST_KEYS}
+    ctx.history_import(hist, game_id=np.arange(10, 10 + games))
+    b = ctx.get_batch(3); ob = O.get_batch(ocfg, hist, 3, first_key=1)
+    for k in ("index", "obs", "actions", "values", "rewards", "policies", "gscale"):
+        assert np.array_equal(b[k], ob[k]), (k, kw)
+    pv, pr, pp, losses = ctx.learn_forward(b)                      # unroll forward + loss (Learning.jl:347-374, 261-288)
+    opv, opr, opp, ol = O.learn_forward(ocfg, blob, ob)
+    assert np.array_equal(pv, opv) and np.array_equal(pr, opr) and np.array_equal(pp, opp), kw
+    assert np.allclose(losses, ol, rtol=LOSS_RTOL, atol=0), kw
+    try:                                                           # gradient through the unroll vs the oracle's Float64 backward
+        g, _ = ctx.learn_gradients(b, capi.GRAD_BPTT)
+    except capi.MuZeroB200Error as e:                              # the saved activations of very deep / wide draws exceed one CTA's shared memory
+        assert e.code == capi.E_UNSUPPORTED and "shared memory" in str(e), kw
+    else:
+        _, og = O.learn_gradients(ocfg, blob, ob, fwd64=False)
+        assert np.max(np.abs(g - og)) <= 2e-5 * max(np.max(np.abs(og)), 1e-30), kw
+    ctx.close()
