@@ -423,7 +423,7 @@ def run_b200(a):
             # for the 8 warps of a CTA; ncu counts 830 wavefronts per simulation over the whole kernel.
             ctas = (G + 31) // 32
             wf_rate = 830.0 * sims_per_launch / (avg_launch_s * clocks["sm_mhz"] * 1e6 * ctas)
-            out["roofline"]["shared_memory"] = {"wavefronts_per_simulation": 830, "source": "profiles/r1j_search_exact_final_ncu.txt (l1tex__data_pipe_lsu_wavefronts_mem_shared)",
+            out["roofline"]["shared_memory"] = {"wavefronts_per_simulation": 830, "source": "profiles/r1n_search_exact_final_ncu.txt (l1tex__data_pipe_lsu_wavefronts_mem_shared)",
                                                 "achieved_per_clk_per_sm": wf_rate, "peak_per_clk_per_sm": 1.0, "frac": wf_rate, "sms_with_a_cta": ctas,
                                                 "note": "whole-launch average incl. the tree phases; inside the network phase the wavefront pipe is the bound "
                                                         "(64 wavefront-cycles vs 32 FMA-cycles per k step), which caps the FMA pipe at 50 %"}
