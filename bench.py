@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--no-tc-extra", action="store_true", help="skip the additional tensor-core measurement in fp32 mode")
     ap.add_argument("--no-resnet-extra", action="store_true", help="skip the additional ResNet measurement (BASELINE.json configs[2]: 16384 games, bf16)")
     ap.add_argument("--resnet-games", type=int, default=16384)
+    ap.add_argument("--no-connect-extra", action="store_true", help="skip the additional Connect measurement (BASELINE.json configs[3]: 6x7 board, 7 actions, ResNet, 200 simulations/move)")
+    ap.add_argument("--connect-games", type=int, default=1776)
+    ap.add_argument("--connect-sims", type=int, default=200)
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the comparison of the last timed wave with the oracle")
     return ap.parse_args()
 
 
@@ -144,6 +148,25 @@ def profiled_traffic(kernel_tag):
     return best
 
 
+def cpu_learner_baseline(ocfg, blob):
+    """learning! (Learning.jl:327-397) on the host: get_batch + unroll + loss + gradients + ADAM per step, one thread (the reference's
+    learner is one process).  reference_l2 = what the reference's pullbacks return (2*theta); bptt = the gradient through the unroll."""
+    from oracle import oracle as O
+    import copy
+    hist = O.self_play(ocfg, blob, 3 * 10 ** 6, 256, 1.0, os.cpu_count() or 1)
+    out = {"unit": "samples/s", "cores": 1, "kind": "port"}
+    for name, B, mode, steps in (("reference_l2_B32", 32, O.GRAD_REFERENCE_L2, 200), ("bptt_B32", 32, O.GRAD_BPTT, 60), ("bptt_B4096", 4096, O.GRAD_BPTT, 1)):
+        c = copy.copy(ocfg); c.batch_size = B
+        w = blob.copy(); m = np.zeros_like(w); v = np.zeros_like(w)
+        t0 = time.perf_counter()
+        for t in range(1, steps + 1):
+            O.learn_step(c, w, m, v, t, O.get_batch(c, hist, t, first_key=1), mode)
+        dt = time.perf_counter() - t0
+        out[name] = {"samples_per_s": B * steps / dt, "ms_per_step": 1e3 * dt / steps, "batch": B,
+                     "sample": "%d steps of get_batch + learn_step (oracle/mz_oracle.c) on one host thread, %.2f s" % (steps, dt)}
+    return out
+
+
 def cpu_baseline(ocfg, blob, target_s):
     threads = os.cpu_count() or 1
     rate, _, _ = cpu_self_play_rate(ocfg, blob, 32 * threads, threads)            # calibration
@@ -153,7 +176,8 @@ def cpu_baseline(ocfg, blob, target_s):
     # the reference's own topology runs ONE self-play actor (games/tictactoe/main.jl:30): the same port on one thread, ~2 s
     g1 = int(max(4, rate / threads * 2.0 / per_game))
     rate1, sims1, dt1 = cpu_self_play_rate(ocfg, blob, g1, 1, first_game=2 * 10 ** 6)
-    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+    learner = cpu_learner_baseline(ocfg, blob)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "learner": learner,
             "sample": "%d self-play games (%d simulations) on %d host threads, %.1f s; C restatement of the reference "
                       "(oracle/mz_oracle.c), the Julia reference cannot run in this image" % (games, sims, threads, dt),
             "single_actor": {"value": rate1, "unit": UNIT, "cores": 1,
@@ -254,6 +278,20 @@ def run_b200(a):
         ctx.kernel_time_reset(False)
         clocks = sampler.stop()
         stats = ctx.search_stats()
+        # ---- parity of what was just timed: every GameHistory of the last timed wave against the oracle (outside the timed region) ----
+        parity = None
+        if not a.no_parity_check:
+            from oracle import oracle as O
+            info = ctx.replay_info()
+            h = ctx.history_export(key0=info["first_key"] + info["n_games"] - G, n=G)
+            fg = game_base + (a.warmup + a.steps - 1) * G
+            o = O.self_play(ocfg, blob, fg, G, 1.0, max(1, (os.cpu_count() or 1) // max(1, world)))
+            bad = 0
+            for j in range(G):
+                i = int(h["game_id"][j]) - fg
+                if not (0 <= i < G) or not all(np.array_equal(h[k][j], o[k][i]) for k in common.HIST_KEYS):
+                    bad += 1
+            parity = (G, bad, int(s == o["sims"]))
         # ---- end-to-end region: host weights in, GameHistory out, every step ----
         e2e_ms, e2e_sims, d2h = 0.0, 0, 0
         wave(a.warmup + 2 * a.steps, e2e=True)                              # untimed: first use of the export path allocates its device staging buffers
@@ -284,7 +322,20 @@ def run_b200(a):
                 e1.record(stream); e1.synchronize()
                 tms += e0.elapsed_time(e1); tsims += s_
             tk_ms, tk_n = ctx_tc.kernel_time(0)
-            tc_extra = (tms, tsims, tk_ms, tk_n)
+            tc_agree = None
+            if not a.no_parity_check:                                       # agreement of the tensor-core games with the Float32 oracle
+                from oracle import oracle as O
+                info = ctx_tc.replay_info()
+                h = ctx_tc.history_export(key0=info["first_key"] + info["n_games"] - G, n=G)
+                fg = game_base + (a.warmup + a.steps - 1) * G
+                o = O.self_play(ocfg, blob, fg, G, 1.0, max(1, (os.cpu_count() or 1) // max(1, world)))
+                same_game = same_first = 0
+                for j in range(G):
+                    i = int(h["game_id"][j]) - fg
+                    same_first += int(np.array_equal(h["child_visits"][j, 0], o["child_visits"][i, 0]))
+                    same_game += int(all(np.array_equal(h[k][j], o[k][i]) for k in ("T", "actions", "child_visits")))
+                tc_agree = (same_first / G, same_game / G)
+            tc_extra = (tms, tsims, tk_ms, tk_n, tc_agree)
             ctx_tc.close()
         barrier()
         # ---- BASELINE.json configs[2]: TicTacToe ResNet, 16384 concurrent games, bf16 inference on tcgen05 (reported beside the headline) ----
@@ -307,6 +358,32 @@ def run_b200(a):
             rk_ms, rk_n = ctx_rn.kernel_time(0)
             rn_extra = (rms, rsims, rk_ms, rk_n, Gr)
             ctx_rn.close()
+        barrier()
+        # ---- BASELINE.json configs[3]: synthetic 6x7 Connect board, 7 actions, ResNet, 200 simulations/move ----
+        cn_extra = None
+        if not a.no_connect_extra:
+            Gc, Sc = a.connect_games, a.connect_sims
+            ctx_cn = capi.Context(capi.connect_config(num_slots=Gc, num_iters=Sc, replay_buffer_size=max(4096, Gc)), device=local, stream=stream.cuda_stream)
+            ctx_cn.init_weights(1337)
+            ctx_cn.self_play(game_base, Gc, 1.0)                             # one untimed wave (a wave is ~40 plies x 200 simulations)
+            ctx_cn.kernel_time_reset(True)
+            flush.zero_(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            cs_, cm_ = ctx_cn.self_play(game_base + Gc, Gc, 1.0)
+            e1.record(stream); e1.synchronize()
+            ck_ms, ck_n = ctx_cn.kernel_time(0)
+            cn_extra = (e0.elapsed_time(e1), cs_, ck_ms, ck_n, Gc, Sc, cm_)
+            ctx_cn.close()
+        barrier()
+        # ---- latency of ONE run_mcts call with one root through the host API (what the reference's play_game calls per move) ----
+        st1 = np.zeros((1, 63), np.float32); st1[:, 18:27] = 1
+        one = (st1, np.full(1, 0x1ff, np.uint32), np.ones(1, np.int32), True, np.arange(1, dtype=np.uint64), np.ones(1, np.int32))
+        ctx.run_mcts(*one)
+        t0_ = time.perf_counter()
+        for _ in range(20):
+            ctx.run_mcts(*one)
+        single_root_ms = (time.perf_counter() - t0_) / 20 * 1e3
         barrier()
         # ---- strong scaling ("also report fixed total G"): the 4096 games of the 1-GPU workload split over the ranks ----
         strong = None
@@ -408,7 +485,11 @@ def run_b200(a):
             "e2e": {"value": e2e_sims_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "mz_k_search_tc<MODE_SLOTS>" if a.nn == "tc" else "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "parity_checked": ({"games": parity[0], "mismatches": parity[1], "simulation_count_equal": bool(parity[2]),
+                                "what": "every GameHistory of the last timed wave (rank 0) vs the CPU oracle (oracle/mz_oracle.c, a restatement of the reference: parity unpinned against Julia)"}
+                               if parity else None),
+            "single_root_latency_ms": single_root_ms,
+            "roofline": {"bound": "latency (L2-resident)" if a.nn != "tc" else "tensor", "hbm_bound_formula": "SURVEY 8d", "kernel": "mz_k_search_tc<MODE_SLOTS>" if a.nn == "tc" else "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic["bytes"] if traffic else None,
                          "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_per_sim * sims_per_launch,
@@ -440,8 +521,10 @@ def run_b200(a):
                                   "kernel": "mz_k_search_tc<MODE_SLOTS>", "avg_launch_ms": tc_extra[2] / max(tc_extra[3], 1),
                                   "roofline": {"bound": "tensor", "achieved": tc_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tc_tflops / bf16_peak,
                                                "note": "useful (unpadded) network FLOPs only; M=64 x N=32 x K<=64 MMAs in a 8-round dependent chain are latency-bound"},
-                                  "note": "same waves with the networks on tcgen05 (bf16 operands, fp32 accumulate); results agree with the "
-                                          "oracle to bf16 tolerance, not bit-exactly, so the headline value is the exact-fp32 path"}
+                                  "agreement_with_float32_oracle": ({"first_ply_visit_counts_identical": tc_extra[4][0], "whole_game_identical": tc_extra[4][1], "games": G}
+                                                                    if tc_extra[4] else None),
+                                  "note": "same waves with the networks on tcgen05 (fp32 accumulate); results agree with the Float32 "
+                                          "oracle at the stated rate, not bit-exactly, so the headline value is the exact-fp32 path"}
         if rn_extra:
             # useful network MACs per simulation, nf = 64, 2 blocks, hs = 64, depth_value = 1 (DESIGN.md "ResNet"): prediction 196,608 + dynamics 374,528;
             # + per move (1/S of it per simulation): representation 3x3 tower (in-bounds taps only) 824,768 + prediction 196,608
@@ -459,6 +542,23 @@ def run_b200(a):
                                                           "per simulation (1152 B) and mostly re-read from L2",
                                           "note": "useful FLOPs only; K = 64 per layer: each warpgroup's step is a dependent chain (MMA issue -> commit -> tcgen05.ld -> "
                                                   "epilogue -> barrier, ~4 k cycles) and shared memory allows four chains per SM; see DESIGN.md 2.4"}}
+        if cn_extra:
+            bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            # useful network MACs per simulation on the 6x7 board (42 cells): the 1x1 towers scale with the cells, the dense heads do not
+            cells = 42
+            tower = lambda cin, cout: cells * cin * cout
+            pred = tower(64, 64) * 5 + (tower(64, 1) + cells * 64 + 64 * 64 + 64) + (tower(64, 2) + 2 * cells * 64 + 64 * 64 + 64 * 7)
+            dyn = tower(65, 64) + tower(64, 64) * 4 + tower(64, 64) * 5 + (tower(64, 1) + cells * 64 + 64 * 64 + 64)
+            flops_per_sim = 2.0 * (pred + dyn)
+            cn_launch_s = (cn_extra[2] / max(cn_extra[3], 1)) * 1e-3
+            cn_tflops = flops_per_sim * (cn_extra[1] / max(cn_extra[3], 1)) / cn_launch_s / 1e12 if cn_launch_s > 0 else 0.0
+            out["connect"] = {"value": cn_extra[1] / (cn_extra[0] * 1e-3) * world, "unit": UNIT, "ms_per_step": cn_extra[0], "dtype": "bf16",
+                              "config": {"workload": "synthetic 6x7 Connect board, 7 actions, ResNet (64 filters, 2 blocks), %d concurrent games x %d simulations/move per GPU, bf16 inference" % (cn_extra[4], cn_extra[5]),
+                                         "moves_per_step": cn_extra[6]},
+                              "kernel": "mz_k_search_rn<MODE_SLOTS>", "avg_launch_ms": cn_extra[2] / max(cn_extra[3], 1),
+                              "roofline": {"bound": "tensor", "achieved": cn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": cn_tflops / bf16_peak,
+                                           "flops_per_simulation": flops_per_sim, "traffic": None,
+                                           "note": "useful FLOPs of prediction + dynamics per simulation (root inference excluded); per-rank value x ranks"}}
         if learner:
             learner["samples_per_s"] = cfg.batch_size * world / (learn_ms_max * 1e-3)
             for e_ in (learner["bptt"], learner["large_batch"]["bptt"], learner["large_batch"]["reference_l2"]):

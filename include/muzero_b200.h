@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 4
+#define MZ_ABI_VERSION 5
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
@@ -81,6 +81,9 @@ typedef struct mz_config {
     /* prioritised replay (src/Constructors.jl:43-44): repaired specification, DESIGN.md "PER" */
     int32_t per;                    /* conf.PER */
     int32_t per_alpha;              /* conf.PER_alpha, 0..3 */
+    /* conf.temperature_threshold (src/Constructors.jl:31): play_game switches to temperature 0 once
+     * length(history.action_history) >= threshold (src/SelfPlay.jl:344-346); -1 = nothing (the default) */
+    int32_t temperature_threshold;
 } mz_config;
 
 typedef struct mz_ctx mz_ctx;
@@ -128,6 +131,13 @@ int mz_select_action(mz_ctx *ctx, int n, const int32_t *visit_counts, const uint
  * Plays games first_game .. first_game+n_games-1 on the ctx's num_slots device-resident game slots and
  * appends every finished GameHistory to the device replay ring under the next game number. */
 int mz_self_play(mz_ctx *ctx, uint64_t first_game, int64_t n_games, float temperature, int64_t *simulations, int64_t *moves);
+/* play_game(env, temperature, render, opponent, muzero_player, NNs)::GameHistory (src/SelfPlay.jl:330-382) for n_games games at once:
+ * the histories come back to the caller (layout of mz_history_export; order = the order the games finished, game_id[] names them) and are
+ * NOT saved -- the reference's self_play! passes them to save_game itself (:414), here mz_history_import.  opponent MZ_OPP_SELF: every
+ * ply is searched; otherwise `opponent` moves for the side that is not muzero_player. */
+int mz_play_games(mz_ctx *ctx, uint64_t first_game, int n_games, float temperature, int opponent, int muzero_player, int64_t *game_id,
+                  int32_t *T, float *obs, int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values,
+                  int64_t *simulations /* may be NULL */);
 /* competitive_play! (src/SelfPlay.jl:421-435) for n_games games at once: play_game with `opponent` (MZ_OPP_RANDOM: rand over the
  * legal actions, :320; MZ_OPP_EXPERT: the reference's expert_agent() is undefined -- one-ply lookahead: win, else block, else random)
  * moving for the side that is not muzero_player (1 or 2).  The reference passes temperature 0 and, through play_game, still searches
@@ -156,6 +166,14 @@ int mz_replay_clear(mz_ctx *ctx);
  * counter); from then on get_batch / mz_learn_step bootstrap those games' value targets from the reanalysed values. */
 int mz_reanalyse(mz_ctx *ctx, int64_t key0, int n);
 int mz_reanalysed_export(mz_ctx *ctx, int64_t key0, int n, float *values /* [n][Tmax] */, int32_t *is_set /* [n]: 0 = nothing */);
+/* checkpoint / resume of the replay state (the reference never persists its buffer, main.jl:21 TODO): the three save_game counters
+ * (num_played_games, num_played_steps, total_samples; ReplayBuffer.jl:147-152) and, per stored game, what mz_history_import does not carry:
+ * history.priorities / game_priority as updated by update_priorities! and reanalysed_predicted_root_values.  Resume = mz_replay_clear,
+ * mz_replay_set_counters(first_key - 1, 0, 0), mz_history_import(the stored games), mz_replay_set_counters(saved), then the two setters. */
+int mz_replay_counters(mz_ctx *ctx, int64_t out[3]);
+int mz_replay_set_counters(mz_ctx *ctx, int64_t num_played_games, int64_t num_played_steps, int64_t total_samples);
+int mz_replay_set_priorities(mz_ctx *ctx, int64_t key0, int n, const uint32_t *q_pos /* [n][Tmax] */, const uint32_t *q_game /* [n] */);
+int mz_reanalysed_import(mz_ctx *ctx, int64_t key0, int n, const float *values /* [n][Tmax] */, const int32_t *is_set /* [n] */);
 
 /* ---- replay sampling + targets: get_batch (src/ReplayBuffer.jl:188-217) ---------------------- */
 int mz_get_batch(mz_ctx *ctx, uint64_t step, int32_t *index_batch /* [B][2] (game key, position) */, float *obs_batch,

@@ -11,3 +11,4 @@ from . import capi  # noqa: F401
 from .capi import Context, MzConfig, MuZeroB200Error, default_config, build_library  # noqa: F401
 from .api import (Config, FeedForwardHP, ResNetHP, GameHistory, TicTacToe, init_networks, run_mcts, select_action, play_game,  # noqa: F401
                   self_play, competitive_play, save_game, get_batch, learning, ReplayBuffer, Engine)
+from . import dropin  # noqa: F401  (the reference's entry points with the reference's own signatures)

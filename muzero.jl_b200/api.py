@@ -150,6 +150,7 @@ def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.G
                   "depth_reward", "depth_state_head", "hidden_state_size"):
             setattr(c, k, getattr(hyper, k))
         c.reward_activation_tanh = 1 if hyper.reward_activation in ("tanh", np.tanh) else 0
+    c.temperature_threshold = -1 if conf.temperature_threshold is None else int(conf.temperature_threshold)   # SelfPlay.jl:344-346
     c.per = 1 if conf.PER else 0          # repaired specification of the prioritised replay
     c.per_alpha = int(conf.PER_alpha)
     c.num_slots = num_slots
@@ -185,6 +186,7 @@ class TicTacToe:
         return self.observation()
 
     def __call__(self, action: int):                   # env(action), game.jl:45-52
+        self._last_mover = int(self.player[0])
         self._last_reward, self._done, self._legal = self.engine.ctx.env_step(self.p1, self.p2, self.player, [action])
         return self.observation()
 

@@ -46,7 +46,7 @@ class MzConfig(C.Structure):
         ("reward_activation_tanh", C.c_int32), ("num_slots", C.c_int32), ("nn_mode", C.c_int32),
         ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
         ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
-        ("per", C.c_int32), ("per_alpha", C.c_int32),
+        ("per", C.c_int32), ("per_alpha", C.c_int32), ("temperature_threshold", C.c_int32),
     ]
 
     def copy(self):
@@ -100,6 +100,7 @@ def lib():
         "mz_run_mcts": ([ctx, C.c_int, f32p, u32p, i32p, C.c_int, u64p, i32p, i32p, f32p, f32p], C.c_int),
         "mz_select_action": ([ctx, C.c_int, i32p, u32p, C.c_float, u64p, i32p, i32p], C.c_int),
         "mz_self_play": ([ctx, C.c_uint64, C.c_int64, C.c_float, i64p, i64p], C.c_int),
+        "mz_play_games": ([ctx, C.c_uint64, C.c_int, C.c_float, C.c_int, C.c_int, i64p, i32p, f32p, i32p, f32p, i32p, f32p, f32p, i64p], C.c_int),
         "mz_arena": ([ctx, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_float, i64p, i64p, i64p, i64p], C.c_int),
         "mz_opponent_action": ([ctx, C.c_int, u64p, u64p, i32p, C.c_int, u64p, i32p, i32p], C.c_int),
         "mz_replay_info": ([ctx, i64p, i64p, i64p], C.c_int),
@@ -108,6 +109,10 @@ def lib():
         "mz_replay_clear": ([ctx], C.c_int),
         "mz_reanalyse": ([ctx, C.c_int64, C.c_int], C.c_int),
         "mz_reanalysed_export": ([ctx, C.c_int64, C.c_int, f32p, i32p], C.c_int),
+        "mz_replay_counters": ([ctx, i64p], C.c_int),
+        "mz_replay_set_counters": ([ctx, C.c_int64, C.c_int64, C.c_int64], C.c_int),
+        "mz_replay_set_priorities": ([ctx, C.c_int64, C.c_int, u32p, u32p], C.c_int),
+        "mz_reanalysed_import": ([ctx, C.c_int64, C.c_int, f32p, i32p], C.c_int),
         "mz_get_batch": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
         "mz_get_batch_per": ([ctx, C.c_uint64, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p], C.c_int),
         "mz_replay_priorities": ([ctx, C.c_int64, C.c_int, u32p, u32p], C.c_int),
@@ -312,6 +317,17 @@ class Context:
         self._ck(self.L.mz_self_play(self._h, first_game, n_games, temperature, C.byref(sims), C.byref(moves)))
         return sims.value, moves.value
 
+    def play_games(self, first_game, n_games, temperature=1.0, opponent=OPP_SELF, muzero_player=1):
+        """play_game (SelfPlay.jl:330-382) for n_games games: their GameHistory arrays in game-id order (+ "sims"); nothing is saved."""
+        out = self.history_buffers(n_games); sims = C.c_int64()
+        self._ck(self.L.mz_play_games(self._h, first_game, n_games, temperature, opponent, muzero_player, _p(out["game_id"], C.c_int64), _p(out["T"], C.c_int32),
+                                      _p(out["obs"], C.c_float), _p(out["actions"], C.c_int32), _p(out["rewards"], C.c_float), _p(out["to_play"], C.c_int32),
+                                      _p(out["child_visits"], C.c_float), _p(out["root_values"], C.c_float), C.byref(sims)))
+        order = np.argsort(out["game_id"], kind="stable")
+        out = {k: v[order] for k, v in out.items()}
+        out["sims"] = sims.value
+        return out
+
     def arena(self, first_game, n_games, opponent=OPP_RANDOM, muzero_player=1, temperature=0.0):
         """competitive_play! (SelfPlay.jl:421-435) for n_games games: dict(wins, draws, losses, simulations) for MuZero."""
         w, d, l, sims = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
@@ -333,6 +349,15 @@ class Context:
 
     def replay_clear(self):
         self._ck(self.L.mz_replay_clear(self._h))
+
+    def replay_counters(self):
+        """(num_played_games, num_played_steps, total_samples) of save_game (ReplayBuffer.jl:147-152)."""
+        out = np.zeros(3, np.int64)
+        self._ck(self.L.mz_replay_counters(self._h, _p(out, C.c_int64)))
+        return out
+
+    def replay_set_counters(self, num_played_games, num_played_steps, total_samples):
+        self._ck(self.L.mz_replay_set_counters(self._h, num_played_games, num_played_steps, total_samples))
 
     def history_buffers(self, n, pinned=False):
         """Caller-owned output arrays for history_export (optionally page-locked through torch, for repeated exports)."""
@@ -453,17 +478,37 @@ class Context:
         m = np.zeros(n, np.float32); v = np.zeros(n, np.float32); t = C.c_int64(0)
         self._ck(self.L.mz_get_optimizer_state(self._h, _p(m, C.c_float), _p(v, C.c_float), n, C.byref(t)))
         ck = dict(weights=self.get_weights(), adam_m=m, adam_v=v, steps_done=np.int64(t.value))
-        if self.replay_info()["n_games"] > 0:
+        info = self.replay_info()
+        ck["replay_counters"] = self.replay_counters()
+        ck["replay_first_key"] = np.int64(info["first_key"])
+        if info["n_games"] > 0:
             ck.update({"hist_" + k: a for k, a in self.history_export().items()})
+            if self.cfg.per:                                 # priorities as update_priorities! left them
+                ck["per_q_pos"], ck["per_q_game"] = self.replay_priorities()
+            if self.cfg.net_type == NET_FEEDFORWARD:
+                ck["reanalysed_values"], ck["reanalysed_set"] = self.reanalysed_export()
         return ck
 
     def restore(self, ck):
         self.set_weights(np.ascontiguousarray(ck["weights"], np.float32))
         m = np.ascontiguousarray(ck["adam_m"], np.float32); v = np.ascontiguousarray(ck["adam_v"], np.float32)
         self._ck(self.L.mz_set_optimizer_state(self._h, _p(m, C.c_float), _p(v, C.c_float), m.size, int(ck["steps_done"])))
+        self.replay_clear()
         if "hist_T" in ck:
-            self.replay_clear()
+            # keys (game numbers) decide ring positions and eviction order: the import must start at the saved first key
+            first = int(ck.get("replay_first_key", 1)); n = len(ck["hist_T"])
+            self.replay_set_counters(first - 1, 0, 0)
             self.history_import({k[5:]: ck[k] for k in ck if k.startswith("hist_")})
+            if "replay_counters" in ck:
+                self.replay_set_counters(*[int(x) for x in ck["replay_counters"]])
+            if "per_q_pos" in ck and self.cfg.per:
+                q_pos = np.ascontiguousarray(ck["per_q_pos"], np.uint32); q_game = np.ascontiguousarray(ck["per_q_game"], np.uint32)
+                self._ck(self.L.mz_replay_set_priorities(self._h, first, n, _p(q_pos, C.c_uint32), _p(q_game, C.c_uint32)))
+            if "reanalysed_values" in ck:
+                vals = _f32(ck["reanalysed_values"]); flags = np.ascontiguousarray(ck["reanalysed_set"], np.int32)
+                self._ck(self.L.mz_reanalysed_import(self._h, first, n, _p(vals, C.c_float), _p(flags, C.c_int32)))
+        elif "replay_counters" in ck:
+            self.replay_set_counters(*[int(x) for x in ck["replay_counters"]])
 
     def optimizer_reset(self):
         self._ck(self.L.mz_optimizer_reset(self._h))

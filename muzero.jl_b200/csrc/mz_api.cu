@@ -66,6 +66,7 @@ struct mz_ctx {
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
     void *d_trees = nullptr;
     mz_slots slots{}; mz_ring ring{};
+    mz_ring play_ring{};   // mz_play_games: a ring of its own, so that play_game's histories go to the caller and not into the replay buffer
     unsigned long long *d_stats = nullptr;
     mz_batch batch{}; int batch_cap = 0;
     float *d_pv = nullptr, *d_pr = nullptr, *d_pp = nullptr, *d_rowv = nullptr, *d_rowp = nullptr, *d_rowinvg = nullptr;
@@ -126,12 +127,35 @@ template <typename F> cudaError_t allow_max_smem(F *func, const cudaDeviceProp &
 }
 template <typename T> cudaError_t dmalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
 
+void free_ring(mz_ring &r) {
+    void *ptrs[] = {r.game_id, r.T, r.h_p1, r.h_p2, r.h_action, r.h_reward, r.h_to_play, r.h_cv, r.h_rv, r.h_rrv, r.reanalysed, r.q_pos, r.q_game, r.prefix, r.upd, r.counters};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    r = mz_ring{};
+}
+int alloc_ring(mz_ctx *c, mz_ring &r, size_t R) {
+    const mz_params &P = c->M.P; const size_t Tm = (size_t)P.Tmax;
+    free_ring(r);
+    r.capacity = (int64_t)R;
+    MZ_CUDA(c, dmalloc(&r.game_id, R)); MZ_CUDA(c, dmalloc(&r.T, R));
+    MZ_CUDA(c, dmalloc(&r.h_p1, R * Tm)); MZ_CUDA(c, dmalloc(&r.h_p2, R * Tm)); MZ_CUDA(c, dmalloc(&r.h_action, R * Tm));
+    MZ_CUDA(c, dmalloc(&r.h_reward, R * Tm)); MZ_CUDA(c, dmalloc(&r.h_to_play, R * Tm)); MZ_CUDA(c, dmalloc(&r.h_cv, R * Tm * P.A)); MZ_CUDA(c, dmalloc(&r.h_rv, R * Tm));
+    MZ_CUDA(c, dmalloc(&r.q_pos, R * Tm)); MZ_CUDA(c, dmalloc(&r.q_game, R)); MZ_CUDA(c, dmalloc(&r.prefix, R)); MZ_CUDA(c, dmalloc(&r.upd, R * Tm));
+    MZ_CUDA(c, cudaMemset(r.q_pos, 0, R * Tm * 4)); MZ_CUDA(c, cudaMemset(r.q_game, 0, R * 4)); MZ_CUDA(c, cudaMemset(r.upd, 0, R * Tm * 8));
+    MZ_CUDA(c, dmalloc(&r.h_rrv, R * Tm)); MZ_CUDA(c, dmalloc(&r.reanalysed, R)); MZ_CUDA(c, cudaMemset(r.reanalysed, 0, R)); MZ_CUDA(c, cudaMemset(r.h_rrv, 0, R * Tm * sizeof(float)));
+    MZ_CUDA(c, dmalloc(&r.counters, 8)); MZ_CUDA(c, cudaMemset(r.counters, 0, 8 * sizeof(int64_t)));
+    MZ_CUDA(c, cudaMemset(r.T, 0, R * sizeof(int32_t)));
+    return MZ_OK;
+}
+
 int alloc_batch(mz_ctx *c, int B) {
     if (B <= c->batch_cap) return MZ_OK;
     const mz_params &P = c->M.P; int K1 = P.K + 1;
-    void *ptrs[] = {c->batch.weights, c->batch.index, c->batch.obs, c->batch.actions, c->batch.values, c->batch.rewards, c->batch.policies, c->batch.gscale,
-                    c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    // free + null first: if a later allocation fails the ctx holds no dangling pointer (batch_cap = 0 forces a clean retry)
+    void **ptrs[] = {(void **)&c->batch.weights, (void **)&c->batch.index, (void **)&c->batch.obs, (void **)&c->batch.actions, (void **)&c->batch.values,
+                     (void **)&c->batch.rewards, (void **)&c->batch.policies, (void **)&c->batch.gscale, (void **)&c->d_pv, (void **)&c->d_pr, (void **)&c->d_pp,
+                     (void **)&c->d_rowv, (void **)&c->d_rowp, (void **)&c->d_rowinvg, (void **)&c->d_rowr};
+    for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    c->batch_cap = 0;
     MZ_CUDA(c, dmalloc(&c->batch.index, (size_t)B * 2)); MZ_CUDA(c, dmalloc(&c->batch.obs, (size_t)B * P.stack_size));
     MZ_CUDA(c, dmalloc(&c->batch.actions, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.values, (size_t)B * K1));
     MZ_CUDA(c, dmalloc(&c->batch.rewards, (size_t)B * K1)); MZ_CUDA(c, dmalloc(&c->batch.policies, (size_t)B * K1 * P.A));
@@ -248,6 +272,9 @@ int finish_losses(mz_ctx *c, int B, float *losses) {
 }
 int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
     const int n = c->M.P.total_floats;
+    if (t == 1 && c->adam_t > 1) {   // learning! builds a fresh optimiser (Learning.jl:318): restarting at step 1 clears the moments too
+        MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)n * 4, c->stream)); MZ_CUDA(c, cudaMemsetAsync(c->d_v, 0, (size_t)n * 4, c->stream));
+    }
     if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
     // MZ_GRAD_BPTT: d_grad was produced by launch_learn_forward (mz_k_learn_bptt + mz_k_grad_reduce)
     if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
@@ -398,6 +425,7 @@ int mz_destroy(mz_ctx *c) {
                     c->d_rowv, c->d_rowp, c->d_rowinvg, c->d_rowr};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &b : c->scratch) b.release();
+    free_ring(c->play_ring);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_wave) cudaFreeHost(c->h_wave);
     for (int i = 0; i < 2; i++) if (c->ev_wave[i]) cudaEventDestroy(c->ev_wave[i]);
@@ -614,7 +642,24 @@ static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned lon
     return MZ_OK;
 }
 // one wave of games on the slots; arena_player != 0: competitive play, `arena_opponent` moves for the other side
+// every slot idle, no game in flight: the state a wave starts from (also the recovery after a wave that ended with an error)
+static int slots_reset(mz_ctx *c) {
+    MZ_CUDA(c, cudaMemsetAsync(c->slots.status, 0, (size_t)c->cfg.num_slots * sizeof(int32_t), c->stream));
+    MZ_CUDA(c, cudaMemsetAsync(c->ring.counters + 5, 0, sizeof(int64_t), c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves);
 static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
+    const int rc = run_wave_body(c, first_game, n_games, temperature, arena_player, arena_opponent, tally_player, simulations, moves);
+    if (rc != MZ_OK && rc != MZ_E_ARG) {   // a wave that failed half-way must not leave games in flight: later calls would answer MZ_E_STATE for ever
+        const std::string keep = c->err;
+        slots_reset(c);
+        c->err = keep; tl_error = keep;
+    }
+    return rc;
+}
+static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
     if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
     if (first_game + (uint64_t)n_games > 0xffffffffull) return fail(c, MZ_E_ARG, "game ids must fit in 32 bits (Philox counter)");
     mz_params P = c->M.P;
@@ -622,7 +667,7 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
     unsigned long long *tally = c->d_stats + 61;   // wins, draws, losses (the last three of the 64 counters)
     const int G = c->cfg.num_slots;
     MZ_TRY(read_counters(c));
-    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "previous self-play did not finish");
+    if (c->h_counters[5] != 0) { MZ_TRY(slots_reset(c)); MZ_TRY(read_counters(c)); }   // left over from a wave that ended with an error
     c->h_counters[3] = (int64_t)first_game; c->h_counters[4] = (int64_t)first_game + n_games; c->h_counters[5] = 0;
     MZ_TRY(write_counters(c));
     MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 64 * sizeof(unsigned long long), c->stream));
@@ -712,6 +757,30 @@ int mz_opponent_action(mz_ctx *c, int n, const uint64_t *p1, const uint64_t *p2,
     return MZ_OK;
 }
 
+// play_game (src/SelfPlay.jl:330-382) for n_games games at once, histories returned to the caller (in the order the games finished; game_id
+// says which is which) and NOT saved: the reference's self_play! calls save_game itself (:414).  The wave runs on a ring of its own.
+int mz_play_games(mz_ctx *c, uint64_t first_game, int n_games, float temperature, int opponent, int muzero_player, int64_t *game_id, int32_t *T, float *obs,
+                  int32_t *actions, float *rewards, int32_t *to_play, float *child_visits, float *root_values, int64_t *simulations) {
+    MZ_CHECK_CTX(c);
+    if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
+    if (opponent != MZ_OPP_SELF && opponent != MZ_OPP_RANDOM && opponent != MZ_OPP_EXPERT)
+        return fail(c, MZ_E_ARG, "opponent must be MZ_OPP_SELF, MZ_OPP_RANDOM or MZ_OPP_EXPERT (\"human\" has no batched meaning)");
+    if (opponent != MZ_OPP_SELF && (c->M.P.P != 2 || muzero_player < 1 || muzero_player > 2)) return fail(c, MZ_E_ARG, "an opponent needs a two-player game and muzero_player in 1..2");
+    if (simulations) *simulations = 0;
+    if (n_games == 0) return MZ_OK;
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) MZ_TRY(slots_reset(c));
+    if (c->play_ring.capacity < n_games) MZ_TRY(alloc_ring(c, c->play_ring, (size_t)(n_games < c->cfg.num_slots ? c->cfg.num_slots : n_games)));
+    MZ_CUDA(c, cudaMemsetAsync(c->play_ring.counters, 0, 8 * sizeof(int64_t), c->stream));
+    const int per = c->M.P.per; c->M.P.per = 0;                  // priorities belong to save_game
+    std::swap(c->ring, c->play_ring);
+    int rc = run_wave(c, first_game, n_games, temperature, opponent == MZ_OPP_SELF ? 0 : muzero_player, opponent, 0, simulations, nullptr);
+    if (rc == MZ_OK) rc = mz_history_export(c, 1, n_games, game_id, T, obs, actions, rewards, to_play, child_visits, root_values);
+    std::swap(c->ring, c->play_ring);
+    c->M.P.per = per;
+    return rc;
+}
+
 int mz_replay_info(mz_ctx *c, int64_t *n_games, int64_t *first_key, int64_t *total_samples) {
     MZ_CHECK_CTX(c);
     MZ_TRY(read_counters(c));
@@ -723,8 +792,7 @@ int mz_replay_info(mz_ctx *c, int64_t *n_games, int64_t *first_key, int64_t *tot
 }
 int mz_replay_clear(mz_ctx *c) {
     MZ_CHECK_CTX(c);
-    MZ_TRY(read_counters(c));
-    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    MZ_TRY(slots_reset(c));
     for (int i = 0; i < 8; i++) c->h_counters[i] = 0;
     MZ_TRY(write_counters(c));
     MZ_CUDA(c, cudaMemsetAsync(c->ring.T, 0, (size_t)c->ring.capacity * sizeof(int32_t), c->stream));
@@ -820,6 +888,59 @@ int mz_reanalysed_export(mz_ctx *c, int64_t key0, int n, float *values, int32_t 
     }
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int j = 0; j < n; j++) flags[j] = fl[(size_t)((key0 + j - 1) % c->ring.capacity)];
+    return MZ_OK;
+}
+
+// ---- replay state for checkpoint / resume: counters, priorities, reanalysed values ---------------------------
+int mz_replay_counters(mz_ctx *c, int64_t out[3]) {
+    MZ_CHECK_CTX(c);
+    if (!out) return fail(c, MZ_E_ARG, "NULL buffer");
+    MZ_TRY(read_counters(c));
+    for (int i = 0; i < 3; i++) out[i] = c->h_counters[i];
+    return MZ_OK;
+}
+int mz_replay_set_counters(mz_ctx *c, int64_t num_played_games, int64_t num_played_steps, int64_t total_samples) {
+    MZ_CHECK_CTX(c);
+    if (num_played_games < 0 || num_played_steps < 0 || total_samples < 0) return fail(c, MZ_E_ARG, "counters must be >= 0");
+    MZ_TRY(read_counters(c));
+    if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
+    c->h_counters[0] = num_played_games; c->h_counters[1] = num_played_steps; c->h_counters[2] = total_samples;
+    return write_counters(c);
+}
+static int keys_in_buffer(mz_ctx *c, int64_t key0, int n) {
+    MZ_TRY(read_counters(c));
+    const int64_t played = c->h_counters[0], have = played < c->ring.capacity ? played : c->ring.capacity, first = played - have + 1;
+    if (key0 < first || key0 + n - 1 > played) return fail(c, MZ_E_ARG, "keys %lld..%lld not in the buffer (holds %lld..%lld)", (long long)key0, (long long)(key0 + n - 1), (long long)first, (long long)played);
+    return MZ_OK;
+}
+int mz_replay_set_priorities(mz_ctx *c, int64_t key0, int n, const uint32_t *q_pos, const uint32_t *q_game) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!q_pos || !q_game))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(keys_in_buffer(c, key0, n));
+    const size_t Tm = (size_t)c->M.P.Tmax;
+    for (int j = 0; j < n; j++) {
+        const int64_t pos = (key0 + j - 1) % c->ring.capacity;
+        MZ_CUDA(c, cudaMemcpyAsync(c->ring.q_pos + (size_t)pos * Tm, q_pos + (size_t)j * Tm, Tm * 4, cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaMemcpyAsync(c->ring.q_game + pos, q_game + j, 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MZ_OK;
+}
+int mz_reanalysed_import(mz_ctx *c, int64_t key0, int n, const float *values, const int32_t *flags) {
+    MZ_CHECK_CTX(c);
+    if (n < 0 || (n > 0 && (!values || !flags))) return fail(c, MZ_E_ARG, "NULL buffer");
+    if (n == 0) return MZ_OK;
+    MZ_TRY(keys_in_buffer(c, key0, n));
+    const size_t Tm = (size_t)c->M.P.Tmax;
+    std::vector<uint8_t> fl((size_t)n);
+    for (int j = 0; j < n; j++) fl[(size_t)j] = flags[j] ? 1 : 0;
+    for (int j = 0; j < n; j++) {
+        const int64_t pos = (key0 + j - 1) % c->ring.capacity;
+        MZ_CUDA(c, cudaMemcpyAsync(c->ring.h_rrv + (size_t)pos * Tm, values + (size_t)j * Tm, Tm * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaMemcpyAsync(c->ring.reanalysed + pos, fl.data() + j, 1, cudaMemcpyHostToDevice, c->stream));
+    }
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
 

@@ -152,6 +152,7 @@ struct mz_params {
     float disc_pow[72];                        // conf.discount^i as Julia computes Float32^Int
     int32_t n_layers, total_floats, n_params, per;   // per: conf.PER
     int32_t per_alpha;
+    int32_t temp_threshold;                    // conf.temperature_threshold (SelfPlay.jl:344-346), -1 = nothing
     int32_t arena_player, arena_opponent;      // competitive play (SelfPlay.jl:421-435): the side MuZero plays (0 = self-play) and who moves for the other
     int32_t arena_tally;                       // the side whose wins / draws / losses mz_k_save_refill counts (0 = none)
     mz_net nets[3];
@@ -537,6 +538,11 @@ MZ_HD int mz_arena_outcome(const mz_params &P, int T, const int32_t *actions, in
         if (mz_env_has_line(P, who == 1 ? b.p1 : b.p2)) return who == muzero_player ? 1 : -1;
     }
     return 0;
+}
+
+// play_game's temperature for the ply searched after T plies (src/SelfPlay.jl:344-346): 0 from conf.temperature_threshold plies on
+MZ_HD float mz_play_temperature(const mz_params &P, int T, float temperature) {
+    return (P.temp_threshold >= 0 && T >= P.temp_threshold) ? 0.0f : temperature;
 }
 
 // select_action (src/SelfPlay.jl:293-306) over the root's children in Dict order (Q9-Q10).

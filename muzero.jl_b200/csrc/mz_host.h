@@ -44,6 +44,7 @@ inline void default_config(mz_config *c) {   // games/tictactoe/params.jl:2-29, 
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
     c->num_slots = 4096; c->nn_mode = MZ_NN_FP32_EXACT;
     c->per = 0; c->per_alpha = 1;
+    c->temperature_threshold = -1;
     c->net_type = MZ_NET_FEEDFORWARD; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
@@ -54,6 +55,7 @@ inline const char *validate(const mz_config &c) {
     if (c.game == MZ_GAME_TICTACTOE && (c.W != 3 || c.H != 3 || c.A != 9)) return "TicTacToe needs observation_shape (3,3,3) and 9 actions";
     if (c.game == MZ_GAME_CONNECT && (c.A != c.H || (c.W + 1) * c.H > 64)) return "Connect needs A == H columns and (W+1)*H <= 64";
     if (c.net_type != MZ_NET_FEEDFORWARD && c.net_type != MZ_NET_RESNET) return "unknown net_type";
+    if (c.temperature_threshold < -1) return "temperature_threshold must be >= 0, or -1 for nothing";
     if (c.per && (c.per_alpha < 0 || c.per_alpha > 3)) return "PER_alpha must be in 0..3";
     if (c.per && c.net_type != MZ_NET_FEEDFORWARD) return "PER belongs to the learner, which is implemented for the FeedForwardHP networks";
     if (c.net_type == MZ_NET_FEEDFORWARD && c.hidden_state_size != c.W * c.H * c.C) return "hidden_state_size must equal prod(observation_shape) (Constructors.jl:73)";
@@ -116,7 +118,7 @@ inline const char *build_model(const mz_config &c, model &M) {
     P.tie_mode = c.tie_mode; P.pb_c_base = c.pb_c_base; P.intermediate_rewards = c.intermediate_rewards;
     P.batch_size = c.batch_size;
     P.pb_c_init = c.pb_c_init; P.discount = c.discount; P.dirichlet_alpha = c.dirichlet_alpha; P.exploration_eps = c.exploration_eps;
-    P.seed = c.seed; P.per = c.per ? 1 : 0; P.per_alpha = c.per_alpha;
+    P.seed = c.seed; P.per = c.per ? 1 : 0; P.per_alpha = c.per_alpha; P.temp_threshold = c.temperature_threshold;
     P.arena_player = 0; P.arena_opponent = MZ_OPP_SELF; P.arena_tally = 0;
     for (int i = 0; i < MZ_MAX_A; i++) P.order[i] = c.child_order[i];
     for (int a = 0; a <= c.A; a++) {

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
         } else {
             // play_game loop body after run_mcts (SelfPlay.jl:360-379)
             int T = a.slots.T[g];
-            int action = mz_select_action_counts(P, vc, legal, a.temperature, game, move);  // :360
+            int action = mz_select_action_counts(P, vc, legal, mz_play_temperature(P, T, a.temperature), game, move);  // :344-346, :360
             mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
             int p = b.player;
             mz_env_step_b(P, b, action);                                                    // :366

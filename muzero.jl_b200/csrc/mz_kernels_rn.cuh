@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
             a.root_value[g] = rv;
         } else {
             int T = a.slots.T[g];
-            int action = mz_select_action_counts(P, vc, legal[p], a.temperature, game[p], move[p]);
+            int action = mz_select_action_counts(P, vc, legal[p], mz_play_temperature(P, T, a.temperature), game[p], move[p]);
             mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
             int pl = b.player;
             mz_env_step_b(P, b, action);

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
             a.root_value[g] = rv;
         } else {
             int T = a.slots.T[g];
-            int action = mz_select_action_counts(P, vc, legal, a.temperature, game, move);
+            int action = mz_select_action_counts(P, vc, legal, mz_play_temperature(P, T, a.temperature), game, move);
             mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
             int p = b.player;
             mz_env_step_b(P, b, action);

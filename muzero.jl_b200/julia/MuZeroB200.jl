@@ -26,6 +26,7 @@ mutable struct MzConfig
     num_slots::Int32; nn_mode::Int32
     net_type::Int32; rn_num_blocks::Int32; rn_num_filters::Int32; rn_kernel::Int32; rn_first_head_filters::Int32; rn_second_head_filters::Int32
     per::Int32; per_alpha::Int32
+    temperature_threshold::Int32
     MzConfig() = new()
 end
 
@@ -39,6 +40,8 @@ mutable struct Engine          # one mz_ctx = one GPU; replaces the RemoteChanne
     cfg::MzConfig
     training_step::Int
     next_game::Int
+    mcts_calls::Int            # keys the random streams of the reference-signature run_mcts (the reference draws from a global RNG)
+    nn_token::UInt             # objectid of the Flux NNs last uploaded by sync_networks!
 end
 
 check(e::Engine, rc) = rc == 0 ? nothing : throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx))))
@@ -55,6 +58,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
     c.intermediate_rewards = conf.intermediate_rewards; c.pb_c_init = conf.pb_c_init; c.discount = conf.discount
     c.dirichlet_alpha = conf.dirichlet_α; c.exploration_eps = conf.exploration_ϵ; c.seed = conf.seed
     c.per = conf.PER; c.per_alpha = conf.PER_alpha
+    c.temperature_threshold = isnothing(conf.temperature_threshold) ? -1 : conf.temperature_threshold   # src/SelfPlay.jl:344-346
     order = zeros(Int32, MZ_MAX_A)
     ccall((:mz_julia_dict_order, LIB), Cint, (Cint, Ptr{Int32}), c.A, order)   # or: collect(keys(Dict(a => 0 for a in conf.action_space)))
     c.child_order = Tuple(order)
@@ -62,7 +66,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
         c.net_type = 1; c.nn_mode = 1
         c.rn_num_blocks = hyper.num_blocks; c.rn_num_filters = hyper.num_filters; c.rn_kernel = hyper.conv_kernel_size[1]
         c.rn_first_head_filters = hyper.num_first_head_filters; c.rn_second_head_filters = hyper.num_second_head_filters
-        c.depth_value = hyper.depth_value; c.width_hidden = 64
+        c.depth_value = hyper.depth_value; c.width_hidden = hyper.hidden_state_size   # width of the heads' dense layers (Learning.jl:205-222)
         c.hidden_state_size = c.W * c.H * c.rn_num_filters
     else                                    # FeedForwardHP (src/Constructors.jl:62-75)
         c.width_hidden = hyper.width_hidden; c.depth_representation = hyper.depth_representation
@@ -74,7 +78,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:mz_create, LIB), Cint, (Ref{MzConfig}, Cint, Ref{Ptr{Cvoid}}), c, device, ctx)
     rc == 0 || throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
-    e = Engine(ctx[], c, 0, 0)
+    e = Engine(ctx[], c, 0, 0, 0, UInt(0))
     finalizer(x -> ccall((:mz_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), e)
     return e
 end
@@ -251,6 +255,131 @@ function learning!(e::Engine, steps::Integer; grad_mode::Integer=0)
     check(e, ccall((:mz_learn_steps, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Ptr{Float32}), e.ctx, e.training_step + 1, steps, grad_mode, losses))
     e.training_step += steps
     return (l_representation=losses[1], l_prediction=losses[2], l_dynamics=losses[3])
+end
+
+# =====================================================================================================================================
+# The reference's own signatures (SURVEY.md 8b), bound to a module-global engine exactly as the reference binds the globals `conf` and
+# `hyper` (games/tictactoe/params.jl:2,18).  After `bind!(Engine(conf, hyper), conf, GameHistory)` the driver script
+# games/tictactoe/main.jl:14-41 runs unchanged: the RemoteChannel arguments are kept and carry the counters; networks, replay buffer and
+# games live on the GPU.  self_play! plays one wave of `num_slots` concurrent games per iteration (the reference's lock-step
+# take!(training_step), SelfPlay.jl:396 / Learning.jl:411, is the ceiling this path removes).  Run the two actors as tasks of one process
+# (`@async self_play!(...)`, `@async learning!(...)`): a context is used by one host thread at a time.
+# =====================================================================================================================================
+const ENGINE = Ref{Union{Nothing,Engine}}(nothing)
+const CONF = Ref{Any}(nothing)
+const GAME_HISTORY = Ref{Any}(nothing)      # the reference's GameHistory type (src/Constructors.jl:6-16)
+function bind!(e::Engine, conf, GameHistory)
+    ENGINE[] = e; CONF[] = conf; GAME_HISTORY[] = GameHistory
+    return e
+end
+engine() = ENGINE[] === nothing ? error("no engine bound: MuZeroB200.bind!(Engine(conf, hyper), conf, GameHistory) first") : ENGINE[]
+
+"NNs from `init_networks` are closures over the device weights (nothing to do); Flux models are flattened and uploaded when they change."
+function sync_networks!(e::Engine, NNs)
+    NNs.representation isa Function && return e
+    id = objectid(NNs.representation) ⊻ objectid(NNs.prediction) ⊻ objectid(NNs.dynamics)
+    if id != e.nn_token
+        blob = e.cfg.net_type == 1 ? flux_blob_resnet : flux_blob
+        set_weights!(e, 0, blob(NNs.representation)); set_weights!(e, 1, blob(NNs.prediction)); set_weights!(e, 2, blob(NNs.dynamics))
+        e.nn_token = id
+    end
+    return e
+end
+"init_representation / init_prediction / init_dynamics (src/Learning.jl:87,100,118): the three callables of `init_networks`, initialised once per engine."
+const NETWORKS = Ref{Any}(nothing)
+_nets() = (NETWORKS[] === nothing && (NETWORKS[] = init_networks(engine())); NETWORKS[])
+init_representation(hyper) = _nets().representation
+init_prediction(hyper) = _nets().prediction
+init_dynamics(hyper) = _nets().dynamics
+
+# src/SelfPlay.jl:230
+function run_mcts(observation::Array{Float32,3}, legal_actions::Vector{Int}, to_play::Int, exploration::Bool, NNs)::Node
+    e = sync_networks!(engine(), NNs)
+    e.mcts_calls += 1
+    return run_mcts(e, observation, legal_actions, to_play, exploration; game_id=(1 << 31) + e.mcts_calls, move_idx=1)
+end
+# src/SelfPlay.jl:293
+select_action(node::Node, temperature) = (e = engine(); select_action(e, node, Float32(temperature); game_id=(1 << 31) + e.mcts_calls, move_idx=1))
+
+"n games of play_game through mz_play_games: GameHistory objects in game-id order; nothing is saved."
+function play_games(e::Engine, n::Integer, temperature, opponent::String, muzero_player::Integer)
+    haskey(OPPONENTS, opponent) || error("Wrong argument: opponent argument should be self, human, expert or random")   # SelfPlay.jl:323
+    Tm = Int(e.cfg.max_moves) + 1; A = Int(e.cfg.A); W, H, C = Int(e.cfg.W), Int(e.cfg.H), Int(e.cfg.C)
+    gid = zeros(Int64, n); T = zeros(Int32, n); obs = zeros(Float32, W, H, C, Tm, n); act = zeros(Int32, Tm, n); rew = zeros(Float32, Tm, n)
+    tp = zeros(Int32, Tm, n); cv = zeros(Float32, A, Tm, n); rv = zeros(Float32, Tm, n); sims = Ref{Int64}(0)
+    check(e, ccall((:mz_play_games, LIB), Cint,
+        (Ptr{Cvoid}, UInt64, Cint, Cfloat, Cint, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}, Ref{Int64}),
+        e.ctx, e.next_game, n, temperature, OPPONENTS[opponent], muzero_player, gid, T, obs, act, rew, tp, cv, rv, sims))
+    e.next_game += n
+    GH = GAME_HISTORY[]
+    return [(t = T[j]; GH(obs[:, :, :, 1:t, j], Int.(act[1:t, j]), rew[1:t, j], Int.(tp[1:t, j]), cv[:, 1:t, j], rv[1:t, j], nothing, nothing, nothing)) for j in sortperm(gid)]
+end
+# src/SelfPlay.jl:330
+function play_game(env, temperature, render::Bool, opponent::String, muzero_player::Int, NNs)
+    e = sync_networks!(engine(), NNs)
+    return play_games(e, 1, Float32(temperature), opponent, muzero_player)[1]
+end
+
+_bump!(ch, delta) = put!(ch, take!(ch) + delta)      # src/Constructors.jl:55-59
+function _counters(e::Engine)
+    c = zeros(Int64, 3)
+    check(e, ccall((:mz_replay_counters, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), e.ctx, c))
+    return c
+end
+# src/ReplayBuffer.jl:133-135
+function save_game(history, remote_buffer, num_played_games, num_played_steps, total_samples)
+    e = engine(); before = _counters(e)
+    Tm = Int(e.cfg.max_moves) + 1; A = Int(e.cfg.A); W, H, C = Int(e.cfg.W), Int(e.cfg.H), Int(e.cfg.C)
+    t = length(history.action_history)
+    obs = zeros(Float32, W, H, C, Tm); obs[:, :, :, 1:t] .= history.observation_history[:, :, :, 1:t]
+    pad(v, T) = (o = zeros(T, Tm); o[1:t] .= v[1:t]; o)
+    cv = zeros(Float32, A, Tm); cv[:, 1:t] .= history.child_visits[:, 1:t]
+    check(e, ccall((:mz_history_import, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Int32}, Ptr{Float32}, Ptr{Float32}),
+        e.ctx, 1, Int64[before[1]], Int32[t], obs, pad(history.action_history, Int32), pad(history.reward_history, Float32),
+        pad(history.to_play_history, Int32), cv, pad(history.root_values, Float32)))
+    after = _counters(e)
+    _bump!(num_played_games, after[1] - before[1]); _bump!(num_played_steps, after[2] - before[2])   # :149-151
+    take!(total_samples); put!(total_samples, after[3])                                              # :152, evictions included (:156-160)
+    return nothing
+end
+# src/SelfPlay.jl:384-390
+function self_play!(env, training_step, num_played_games, num_played_steps, total_samples, remote_NNs, remote_buffer)::Bool
+    e = sync_networks!(engine(), fetch(remote_NNs))                          # :392
+    conf = CONF[]; training_step_ = 0
+    while training_step_ ≤ conf.training_steps                               # :394
+        training_step_ = fetch(training_step)                                # :396, without the lock-step take!
+        e.training_step = training_step_
+        before = _counters(e)
+        self_play!(e, Int(e.cfg.num_slots))                                  # play_game + save_game for a wave of games (:405-417)
+        after = _counters(e)
+        _bump!(num_played_games, after[1] - before[1]); _bump!(num_played_steps, after[2] - before[2])
+        take!(total_samples); put!(total_samples, after[3])
+        yield()
+    end
+    return true
+end
+# src/ReplayBuffer.jl:188
+function get_batch(buffer)
+    return get_batch(engine())
+end
+# src/Learning.jl:306-309
+function learning!(num_played_games, training_step, remote_NNs, remote_buffer)::Bool
+    e = engine(); conf = CONF[]
+    while fetch(num_played_games) < 1                                        # :311-314
+        yield()
+    end
+    training_step_ = fetch(training_step)
+    while training_step_ ≤ conf.training_steps                               # :327
+        n = min(conf.checkpoint_interval, conf.training_steps - training_step_ + 1)
+        e.training_step = training_step_
+        losses = learning!(e, n)                                             # :329-404, n iterations queued back to back
+        training_step_ += n
+        take!(training_step); put!(training_step, training_step_)            # :411
+        @info "Training Progress" training_step_ losses...                   # :421-424
+        yield()
+    end
+    return true
 end
 
 end # module

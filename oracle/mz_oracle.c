@@ -155,7 +155,7 @@ void mzo_default_config(mzo_config *c) { /* games/tictactoe/params.jl:2-29; src/
     c->width_hidden = 64; c->depth_representation = 3; c->depth_prediction = 3; c->depth_dynamics = 3;
     c->depth_policy = 1; c->depth_value = 1; c->depth_reward = 1; c->depth_state_head = 3;
     c->hidden_state_size = 27; c->reward_activation_tanh = 1;
-    c->per = 0; c->per_alpha = 1;
+    c->per = 0; c->per_alpha = 1; c->temperature_threshold = -1;
     c->net_type = 0; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
@@ -927,6 +927,7 @@ static void play_game(const model_t *m, tree_t *t, uint64_t game_id, float tempe
     mzo_env env; float stacked[MZO_MAX_OBS * 3];
     mzo_env_reset(c, &env);
     while (!done && T <= c->max_moves) {                                  /* :343 */
+        if (c->temperature_threshold >= 0 && T >= c->temperature_threshold) temperature = 0.0f;   /* :344-346 */
         int p = env.player;                                               /* :351 */
         mzo_env_observation(c, &env, obs_h + (size_t)T * on);             /* :352 (obs of the board before the move) */
         mzo_stack_observations(c, obs_h, act_h, T + 1, stacked);          /* :355 */

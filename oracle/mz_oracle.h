@@ -76,6 +76,7 @@ typedef struct mzo_config {
     int32_t rn_second_head_filters; /* num_second_head_filters = 2 (policy head) */
     int32_t per;                    /* conf.PER (params.jl:11: false) */
     int32_t per_alpha;              /* conf.PER_alpha (Constructors.jl:44: 1) */
+    int32_t temperature_threshold;  /* conf.temperature_threshold (Constructors.jl:31): -1 = nothing */
 } mzo_config;
 
 void mzo_default_config(mzo_config *cfg);            /* params.jl:2-29 defaults */

@@ -33,7 +33,7 @@ class Config(C.Structure):
         ("reward_activation_tanh", C.c_int32),
         ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
         ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
-        ("per", C.c_int32), ("per_alpha", C.c_int32),
+        ("per", C.c_int32), ("per_alpha", C.c_int32), ("temperature_threshold", C.c_int32),
     ]
 
 
@@ -67,8 +67,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO) or not (_cpu_has("avx2") and _cpu_has("fma")):
-        build(force=not os.path.exists(_SO) or not (_cpu_has("avx2") and _cpu_has("fma")))
+    build(force=not os.path.exists(_SO) or not (_cpu_has("avx2") and _cpu_has("fma")))   # no-op when the library is newer than its sources
     L = C.CDLL(_SO)
     f32p, i32p, i64p, u32p = (C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_uint32))
     cfgp = C.POINTER(Config)

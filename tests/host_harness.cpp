@@ -133,7 +133,7 @@ int64_t hh_self_play(const mz_config *c, const float *src, uint64_t first_game, 
             search_one(M, nn, pool, stacked.data(), legal, b.player, 1, game, (uint32_t)T + 1u, o);
             sims += P.S;
             int sum_visits = 0; for (int i = 0; i < P.A; i++) sum_visits += o.vc[i];
-            int action = mz_select_action_counts(P, o.vc, legal, temperature, game, (uint32_t)T + 1u);
+            int action = mz_select_action_counts(P, o.vc, legal, mz_play_temperature(P, T, temperature), game, (uint32_t)T + 1u);
             int p = b.player;
             size_t oo = (size_t)gi * P.Tmax + T;
             for (int k = 0; k < P.obs_size; k++) obs[oo * P.obs_size + k] = mz_env_obs_value(P, b, k / P.cells, k % P.cells);

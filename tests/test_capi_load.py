@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libmuzero_b200.so does not export %s" % n
     assert set(names) == set(L._mz_symbols), "capi.py binding and header disagree"
-    assert L.mz_abi_version() == 4
+    assert L.mz_abi_version() == 5
 
 
 def test_config_defaults_follow_params_jl():
@@ -96,3 +96,38 @@ def test_python_interface_mirrors_reference_names():
         if name in ("replay_buffer_size", "child_order"):
             continue
         assert getattr(o, name) == getattr(ref, name), name
+
+
+def test_dropin_entry_points_keep_the_reference_signatures():
+    """the signatures the wrapper "must keep exactly" -- argument names and order of the reference's functions
+    (SelfPlay.jl:230, 330, 384-390; ReplayBuffer.jl:133-135, 188; Learning.jl:306-309), `!` spelt `_`."""
+    import inspect
+    import muzero_jl_b200 as mz
+    d = mz.dropin
+    want = {
+        "run_mcts": ["observation", "legal_actions", "to_play", "exploration", "NNs_"],
+        "play_game": ["env", "temperature", "render", "opponent", "muzero_player", "NNs_"],
+        "self_play_": ["env", "training_step", "num_played_games", "num_played_steps", "total_samples", "remote_NNs", "remote_buffer"],
+        "save_game": ["history", "remote_buffer", "num_played_games", "num_played_steps", "total_samples"],
+        "get_batch": ["buffer"],
+        "learning_": ["num_played_games", "training_step", "remote_NNs", "remote_buffer"],
+        "select_action": ["node", "temperature"],
+        "init_representation": ["hyper_"], "init_prediction": ["hyper_"], "init_dynamics": ["hyper_"],
+    }
+    for name, args in want.items():
+        params = [p for p in inspect.signature(getattr(d, name)).parameters.values() if p.default is inspect.Parameter.empty]
+        assert [p.name for p in params] == args, name
+    # the capacity-1 channel of main.jl:15-19
+    ch = d.RemoteChannel(lambda: d.Channel(1))
+    d.put(ch, 0); assert d.fetch(ch) == 0 and d.take(ch) == 0 and not ch.isready()
+    with pytest.raises(RuntimeError):
+        d._engine = None; d.run_mcts(None, [1], 1, True, None)
+    # the Julia wrapper declares the same methods (source only: no Julia in this image)
+    src = open(os.path.join(common.ROOT, "muzero.jl_b200", "julia", "MuZeroB200.jl")).read()
+    for sig in ("function run_mcts(observation::Array{Float32,3}, legal_actions::Vector{Int}, to_play::Int, exploration::Bool, NNs)",
+                "function play_game(env, temperature, render::Bool, opponent::String, muzero_player::Int, NNs)",
+                "function self_play!(env, training_step, num_played_games, num_played_steps, total_samples, remote_NNs, remote_buffer)",
+                "function save_game(history, remote_buffer, num_played_games, num_played_steps, total_samples)",
+                "function get_batch(buffer)",
+                "function learning!(num_played_games, training_step, remote_NNs, remote_buffer)"):
+        assert sig in src, sig

@@ -156,3 +156,50 @@ def test_new_entry_points_error_behaviour(mz):
     with pytest.raises(capi.MuZeroB200Error):
         rn.checkpoint()
     rn.close()
+
+
+def test_dropin_main_jl_call_sequence(mz):
+    """games/tictactoe/main.jl:14-41 line for line through the reference-signature layer (muzero.jl_b200/dropin.py)."""
+    d = mz.dropin
+    conf = mz.Config(num_iters=8, training_steps=40, checkpoint_interval=10, replay_buffer_size=512)
+    hyper = mz.FeedForwardHP()
+    eng = d.bind(mz.Engine(conf, hyper, num_slots=64))
+    env = d.TicTacToe()                                                       # main.jl:14
+    training_step = d.RemoteChannel(lambda: d.Channel(1))                     # :15-19
+    num_played_games = d.RemoteChannel(lambda: d.Channel(1))
+    num_played_steps = d.RemoteChannel(lambda: d.Channel(1))
+    num_reanalysed_games = d.RemoteChannel(lambda: d.Channel(1))
+    total_samples = d.RemoteChannel(lambda: d.Channel(1))
+    remote_NNs = d.RemoteChannel(lambda: d.Channel(1))                        # :20
+    remote_buffer = d.RemoteChannel(lambda: d.BufferChannel())                # :21
+    d.put(remote_NNs, d.NNs(representation=d.init_representation(d.hyper), prediction=d.init_prediction(d.hyper), dynamics=d.init_dynamics(d.hyper)))   # :23
+    for ch in (training_step, num_played_games, num_played_steps, num_reanalysed_games, total_samples):
+        d.put(ch, 0)                                                          # :24-28
+    w0 = eng.ctx.get_weights()
+    # the pieces, with the reference's own argument lists
+    nns = d.fetch(remote_NNs)
+    obs = d.reset_(env)
+    stacked = np.concatenate([obs.reshape(-1), np.zeros(36, np.float32)])
+    root = d.run_mcts(stacked.reshape(7, 3, 3), d.legal_action_space(env, d.current_player(env)), d.current_player(env), True, nns)   # SelfPlay.jl:359
+    assert root.visit_counts.sum() == 8 and 1 <= d.select_action(root, 1.0) <= 9
+    hist = d.play_game(env, 1.0, False, "self", conf.muzero_player, nns)       # SelfPlay.jl:405
+    assert 6 <= len(hist.action_history) <= 9 and len(remote_buffer) == 0      # returned, not saved
+    d.save_game(hist, remote_buffer, num_played_games, num_played_steps, total_samples)   # :414
+    assert len(remote_buffer) == 1 and d.fetch(num_played_games) == 1 and d.fetch(total_samples) == len(hist.action_history)
+    assert remote_buffer[1].action_history.tolist() == hist.action_history.tolist()
+    index_batch, batch = d.get_batch(remote_buffer)                            # Learning.jl:331
+    assert len(index_batch) == 32 and len(batch) == 7 and batch[5] is None
+    hist_r = d.play_game(env, 0.0, False, "random", 2, nns)
+    assert set(hist_r.to_play_history.tolist()) == {1, 2}
+    # the two actors (main.jl:30-41)
+    sp = d.spawnat(d.self_play_, env, training_step, num_played_games, num_played_steps, total_samples, remote_NNs, remote_buffer)
+    learn = d.spawnat(d.learning_, num_played_games, training_step, remote_NNs, remote_buffer)
+    learn.join(timeout=120); sp.join(timeout=120)
+    assert not learn.is_alive() and not sp.is_alive() and learn.error is None and sp.error is None
+    assert learn.result is True and sp.result is True
+    assert d.fetch(training_step) == 41 and eng.training_step == 41            # while training_step_ <= conf.training_steps
+    n = d.fetch(num_played_games)
+    assert n >= 65 and (n - 1) % 64 == 0 and len(remote_buffer) == min(n, 512)
+    assert d.fetch(total_samples) == eng.ctx.replay_info()["total_samples"] and d.fetch(num_played_steps) >= d.fetch(total_samples)
+    assert not np.array_equal(eng.ctx.get_weights(), w0) and np.all(np.isfinite(list(eng.last_losses.values())))
+    eng.close()

@@ -65,9 +65,9 @@ def test_run_mcts_bit_exact(hh, S, eps, tie):
         assert np.array_equal(pri, opri)
 
 
-@pytest.mark.parametrize("temperature,eps", [(1.0, 0.0), (0.0, 0.0), (1.0, 0.25), (0.5, 0.25)])
-def test_self_play_bit_exact(hh, temperature, eps):
-    cfg = common.product_config(num_iters=10, exploration_eps=eps); ocfg = common.oracle_config(cfg)
+@pytest.mark.parametrize("temperature,eps,thr", [(1.0, 0.0, -1), (0.0, 0.0, -1), (1.0, 0.25, -1), (0.5, 0.25, -1), (1.0, 0.25, 3), (1.0, 0.0, 0)])
+def test_self_play_bit_exact(hh, temperature, eps, thr):
+    cfg = common.product_config(num_iters=10, exploration_eps=eps, temperature_threshold=thr); ocfg = common.oracle_config(cfg)
     blob = O.init_weights(ocfg, 3)
     n = 24; s = O.sizes(ocfg)
     T = np.zeros(n, np.int32); obs = np.zeros((n, s["Tmax"], s["obs"]), np.float32); act = np.zeros((n, s["Tmax"]), np.int32)

@@ -343,3 +343,30 @@ def test_golden_bptt_per_resnet_fixture_is_reproduced():
         assert np.array_equal(np.stack([O.representation(rcfg, rblob, x) for x in g["rn_stacked"][:4]]), g["rn_hidden_bf16"][:4])
     finally:
         O.set_bf16(False)
+
+
+def test_temperature_threshold_switches_to_greedy_play():
+    """conf.temperature_threshold (SelfPlay.jl:344-346): once length(action_history) >= threshold the rest of the game is played at
+    temperature 0.  Moves are independent given the position (every draw is keyed by (game, move)), so: threshold 0 == a game at
+    temperature 0; threshold 3 == the temperature-1 game for its first 3 plies, and from then on the argmax of the visit counts."""
+    cfg = O.default_config(num_iters=12, exploration_eps=0.25)
+    blob = O.init_weights(cfg, 21)
+    n = 40
+    warm = O.self_play(cfg, blob, 500, n, 1.0, 2)
+    greedy = O.self_play(cfg, blob, 500, n, 0.0, 2)
+    cfg.temperature_threshold = 0
+    t0 = O.self_play(cfg, blob, 500, n, 1.0, 2)
+    for k in ("T", "actions", "child_visits", "root_values"):
+        assert np.array_equal(t0[k], greedy[k]), k
+    cfg.temperature_threshold = 3
+    t3 = O.self_play(cfg, blob, 500, n, 1.0, 2)
+    assert np.array_equal(t3["actions"][:, :3], warm["actions"][:, :3])
+    assert not np.array_equal(t3["actions"], warm["actions"])            # some later ply differs from the sampled game
+    order = cfg.child_order[:9]
+    for g in range(n):
+        for t in range(3, int(t3["T"][g])):
+            cv = t3["child_visits"][g, t]
+            best = max(order, key=lambda a: (cv[a - 1], -order.index(a)))   # argmax over the children in Dict order, first maximum wins
+            assert int(t3["actions"][g, t]) == best, (g, t)
+    cfg.temperature_threshold = 64                                        # never reached: identical to nothing
+    assert np.array_equal(O.self_play(cfg, blob, 500, n, 1.0, 2)["actions"], warm["actions"])
