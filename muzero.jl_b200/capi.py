@@ -19,7 +19,7 @@ TIE_PHILOX, TIE_FIRST = 0, 1
 GRAD_REFERENCE_L2, GRAD_BPTT = 0, 1
 NET_FEEDFORWARD, NET_RESNET = 0, 1
 OPP_SELF, OPP_RANDOM, OPP_EXPERT = 0, 1, 2
-NN_FP32_EXACT, NN_BF16_TC = 0, 1
+NN_FP32_EXACT, NN_BF16_TC, NN_SPLIT_MMA = 0, 1, 2
 NET_REPRESENTATION, NET_PREDICTION, NET_DYNAMICS, NET_ALL = 0, 1, 2, 3
 KERNEL_FAMILIES = ("selfplay_move", "save_refill", "replay_gather", "learn_forward_loss", "adam", "nn_batch", "env")
 

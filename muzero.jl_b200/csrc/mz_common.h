@@ -167,6 +167,29 @@ struct mz_params {
 };
 
 // ------------------------------------------------------------------------------------------------
+// Split-precision network path (nn_mode = MZ_NN_SPLIT_MMA, mz_kernels_mma.cuh): every Dense layer as warp-level tensor-core MMAs
+// (mma.sync m16n8k16, bf16 operands, fp32 accumulate) with BOTH operands split into bf16 hi + lo parts and the three products
+// hi*lo + lo*hi + hi*hi accumulated, i.e. 16 mantissa bits per operand.  A warp owns 16 rows (trees) for a whole chain of layers: the
+// accumulator fragments of one layer are, after bias + activation + hi/lo split in registers, the A fragments of the next one, so a
+// chain needs no shared-memory round trip and no barrier.  Weights stream through a shared-memory ring per network in "fragment
+// order" (host-packed: one 16-byte load per lane per (n-tile, k-step) = {hi b0, hi b1, lo b0, lo b1}).
+// A network is a STREAM of layers [trunk..., head 1 and head 2 interleaved]; the warps of a 16-row tile are specialised per head
+// (each runs the trunk and one head), bit 0 / bit 1 of `use` say which of them runs a stream entry.
+// ------------------------------------------------------------------------------------------------
+#define MZ_MMA_MAX_STREAM 24
+#define MZ_MMA_SLOTS 3
+struct mz_mma_plan {
+    int32_t n[3];                                   // stream length per network
+    uint8_t layer[3][MZ_MMA_MAX_STREAM];            // layer index (into mz_params::layers)
+    uint8_t use[3][MZ_MMA_MAX_STREAM];              // bit 0: the head-1 warps run it, bit 1: the head-2 warps
+    uint8_t first[3][MZ_MMA_MAX_STREAM];            // bit h: the layer reads the network input (head h's chain starts here)
+    uint8_t last[3][MZ_MMA_MAX_STREAM];             // bit h: the layer is the end of head h's chain (fp32 outputs)
+    int32_t w_off[MZ_MAX_LAYERS], w_bytes[MZ_MAX_LAYERS];   // the layer's fragment block inside the global image (16-byte aligned)
+    int32_t ks[MZ_MAX_LAYERS], nt[MZ_MAX_LAYERS];   // k-steps (in / 16) and n-tiles (out / 8), rounded up
+    int32_t image_bytes, slot_bytes, bias_floats, ok;
+};
+
+// ------------------------------------------------------------------------------------------------
 // Learner backward pass (grad_mode = MZ_GRAD_BPTT): host-built program of backward layer applications.
 // One CTA = 32 samples; group 0 walks the prediction rows (and finally the representation), group 1 the
 // dynamics steps, in lock-step "steps" separated by CTA barriers (see mz_learner_bptt.cuh).

@@ -44,6 +44,7 @@ __device__ __forceinline__ void mz_mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t spin = 0; !mz_mbar_try_wait(bar, parity); spin++)
         if (spin > (1u << 24)) __trap();
 }
+__device__ __forceinline__ void mz_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // named barrier over one 128-thread group (ids 1 and 2; 0 is __syncthreads)
 template <int GT = MZ_GROUP>
 __device__ __forceinline__ void mz_group_sync(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GT) : "memory"); }

@@ -244,6 +244,60 @@ inline void pack_weights_tc(const mz_params &P, const float *src, std::vector<ui
     }
 }
 
+// ---- split-precision MMA path (mz_kernels_mma.cuh): stream plan + fragment-ordered weight image ---------------------------------
+inline void build_mma_plan(const mz_params &P, mz_mma_plan &M) {
+    memset(&M, 0, sizeof(M));
+    M.ok = 1;
+    int off = 0;
+    for (int i = 0; i < P.n_layers; i++) {
+        const mz_layer &l = P.layers[i];
+        if (l.in > 64 || l.out > 64) M.ok = 0;
+        M.ks[i] = (l.in + 15) / 16; M.nt[i] = (l.out + 7) / 8;
+        M.w_off[i] = off; M.w_bytes[i] = M.ks[i] * M.nt[i] * 512;
+        off += M.w_bytes[i];
+        if (M.w_bytes[i] > M.slot_bytes) M.slot_bytes = M.w_bytes[i];
+    }
+    M.image_bytes = off; M.bias_floats = P.n_layers * 64;
+    for (int n = 0; n < 3; n++) {
+        const mz_net &N = P.nets[n];
+        int k = 0;
+        for (int i = 0; i < N.n_trunk; i++) {
+            M.layer[n][k] = (uint8_t)(N.first + i); M.use[n][k] = N.n_h1 == 0 ? 1 : 3;
+            M.first[n][k] = i == 0 ? 3 : 0; M.last[n][k] = (N.n_h1 == 0 && i == N.n_trunk - 1) ? 1 : 0; k++;
+        }
+        const int f1 = N.first + N.n_trunk, f2 = f1 + N.n_h1;
+        for (int i = 0; i < (N.n_h1 > N.n_h2 ? N.n_h1 : N.n_h2); i++) {   // the two heads interleaved: their warps advance side by side
+            if (i < N.n_h1) { M.layer[n][k] = (uint8_t)(f1 + i); M.use[n][k] = 1; M.last[n][k] = i == N.n_h1 - 1 ? 1 : 0; k++; }
+            if (i < N.n_h2) { M.layer[n][k] = (uint8_t)(f2 + i); M.use[n][k] = 2; M.last[n][k] = i == N.n_h2 - 1 ? 2 : 0; k++; }
+        }
+        M.n[n] = k;
+        if (k > MZ_MMA_MAX_STREAM) M.ok = 0;
+    }
+}
+inline float bf16_to_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+// reference-order blob -> fragment-ordered image.  Per layer, n-tile j, k-step s, lane (g = lane / 4, t = lane % 4): the B fragment of
+// mma.m16n8k16 for output feature n = 8j + g: b0 = W[n][16s + 2t, +1], b1 = W[n][16s + 2t + 8, +9], each as a bf16 hi part (round to
+// nearest) and a bf16 lo part (w - hi, round to nearest): 16 bytes {hi b0, hi b1, lo b0, lo b1}.  Biases: fp32, 64 per layer.
+inline void pack_weights_mma(const mz_params &P, const mz_mma_plan &M, const float *src, std::vector<uint32_t> &image, std::vector<float> &bias) {
+    image.assign((size_t)M.image_bytes / 4 + 4, 0u); bias.assign((size_t)M.bias_floats, 0.0f);
+    for (int i = 0; i < P.n_layers; i++) {
+        const mz_layer &l = P.layers[i];
+        auto W = [&](int n, int k) -> float { return (n < l.out && k < l.in) ? src[l.src_w_off + k * l.out + n] : 0.0f; };
+        for (int j = 0; j < M.nt[i]; j++) for (int s = 0; s < M.ks[i]; s++) for (int lane = 0; lane < 32; lane++) {
+            const int g = lane >> 2, t = lane & 3, n = 8 * j + g;
+            uint32_t *q = image.data() + (size_t)M.w_off[i] / 4 + ((size_t)(j * M.ks[i] + s) * 32 + lane) * 4;
+            for (int half = 0; half < 2; half++) {
+                const int k0 = 16 * s + 2 * t + 8 * half;
+                uint16_t hi[2], lo[2];
+                for (int e = 0; e < 2; e++) { const float w = W(n, k0 + e); hi[e] = f2bf16(w); lo[e] = f2bf16(w - bf16_to_f(hi[e])); }
+                q[half] = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16);
+                q[2 + half] = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16);
+            }
+        }
+        for (int o = 0; o < l.out; o++) bias[(size_t)i * 64 + o] = src[l.src_b_off + o];
+    }
+}
+
 // Flux.glorot_uniform (un-vendored): (rand(Float32,out,in) .- 0.5f0) .* sqrt(24f0/(in+out)); bias zeros.  The reference
 // never seeds it (Constructors.jl:19); contract: element i of layer l of net n = Philox(seed, INIT, n, l, i/4)[i%4].
 inline void init_weights(const mz_params &P, uint64_t seed, float *src) {

@@ -178,6 +178,29 @@ __device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const m
     __syncwarp(segmask);
 }
 
+// play_game's loop body after run_mcts (src/SelfPlay.jl:344-346, 360-379) for one game slot: temperature rule, select_action, environment
+// step, store_search_stats! (Q12), history append, termination.  Shared by every search kernel (lane 0 of the tree).
+__device__ __forceinline__ void mz_slot_epilogue(const mz_params &P, const mz_slots &s, int64_t g, const int32_t *vc, int sum_visits, uint32_t legal, float rv,
+                                                 float temperature, uint32_t game, uint32_t move) {
+    int T = s.T[g];
+    const int action = mz_select_action_counts(P, vc, legal, mz_play_temperature(P, T, temperature), game, move);  // :344-346, :360
+    mz_board b; b.p1 = s.p1[g]; b.p2 = s.p2[g]; b.player = s.player[g];
+    const int p = b.player;
+    mz_env_step_b(P, b, action);                                                    // :366
+    const float reward = (float)mz_env_reward_b(P, b, p);                           // :367
+    const bool done = mz_env_terminated_b(P, b);                                    // :368
+    float *cv = s.h_cv + ((size_t)g * P.Tmax + T) * P.A;                            // store_search_stats! :115-122 (Q12)
+    for (int i = 0; i < P.A; i++) cv[i] = ((legal >> i) & 1u) ? (float)((double)vc[i] / (double)sum_visits) : 0.0f;
+    s.h_rv[(size_t)g * P.Tmax + T] = rv;
+    s.h_action[(size_t)g * P.Tmax + T] = action;                                    // :377-379
+    s.h_reward[(size_t)g * P.Tmax + T] = reward;
+    s.h_to_play[(size_t)g * P.Tmax + T] = (uint8_t)p;
+    T += 1;
+    s.p1[g] = b.p1; s.p2[g] = b.p2; s.player[g] = b.player; s.T[g] = T;
+    if (T < P.Tmax) { s.h_p1[(size_t)g * P.Tmax + T] = b.p1; s.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
+    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED;                    // loop condition :343
+}
+
 // GT = threads per network group: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps for the same work; the tree
 // phases still use 8 lanes x 32 trees = the first 256 threads).
 // Self-play launches run one iteration ahead of the host (run_wave, mz_api.cu): a CTA none of whose slots has a ply to search -- every
@@ -337,24 +360,7 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
             }
             a.root_value[g] = rv;
         } else {
-            // play_game loop body after run_mcts (SelfPlay.jl:360-379)
-            int T = a.slots.T[g];
-            int action = mz_select_action_counts(P, vc, legal, mz_play_temperature(P, T, a.temperature), game, move);  // :344-346, :360
-            mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
-            int p = b.player;
-            mz_env_step_b(P, b, action);                                                    // :366
-            float reward = (float)mz_env_reward_b(P, b, p);                                 // :367
-            bool done = mz_env_terminated_b(P, b);                                          // :368
-            float *cv = a.slots.h_cv + ((size_t)g * P.Tmax + T) * P.A;                      // store_search_stats! :115-122 (Q12)
-            for (int i = 0; i < P.A; i++) cv[i] = ((legal >> i) & 1u) ? (float)((double)vc[i] / (double)sum_visits) : 0.0f;
-            a.slots.h_rv[(size_t)g * P.Tmax + T] = rv;
-            a.slots.h_action[(size_t)g * P.Tmax + T] = action;                              // :377-379
-            a.slots.h_reward[(size_t)g * P.Tmax + T] = reward;
-            a.slots.h_to_play[(size_t)g * P.Tmax + T] = (uint8_t)p;
-            T += 1;
-            a.slots.p1[g] = b.p1; a.slots.p2[g] = b.p2; a.slots.player[g] = b.player; a.slots.T[g] = T;
-            if (T < P.Tmax) { a.slots.h_p1[(size_t)g * P.Tmax + T] = b.p1; a.slots.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
-            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED;              // loop condition :343
+            mz_slot_epilogue(P, a.slots, g, vc, sum_visits, legal, rv, a.temperature, game, move);
         }
     }
 }

@@ -195,23 +195,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_search_tc(const __grid_consta
             }
             a.root_value[g] = rv;
         } else {
-            int T = a.slots.T[g];
-            int action = mz_select_action_counts(P, vc, legal, mz_play_temperature(P, T, a.temperature), game, move);
-            mz_board b; b.p1 = a.slots.p1[g]; b.p2 = a.slots.p2[g]; b.player = a.slots.player[g];
-            int p = b.player;
-            mz_env_step_b(P, b, action);
-            float reward = (float)mz_env_reward_b(P, b, p);
-            bool done = mz_env_terminated_b(P, b);
-            float *cv = a.slots.h_cv + ((size_t)g * P.Tmax + T) * P.A;
-            for (int i = 0; i < P.A; i++) cv[i] = ((legal >> i) & 1u) ? (float)((double)vc[i] / (double)sum_visits) : 0.0f;
-            a.slots.h_rv[(size_t)g * P.Tmax + T] = rv;
-            a.slots.h_action[(size_t)g * P.Tmax + T] = action;
-            a.slots.h_reward[(size_t)g * P.Tmax + T] = reward;
-            a.slots.h_to_play[(size_t)g * P.Tmax + T] = (uint8_t)p;
-            T += 1;
-            a.slots.p1[g] = b.p1; a.slots.p2[g] = b.p2; a.slots.player[g] = b.player; a.slots.T[g] = T;
-            if (T < P.Tmax) { a.slots.h_p1[(size_t)g * P.Tmax + T] = b.p1; a.slots.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
-            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED;
+            mz_slot_epilogue(P, a.slots, g, vc, sum_visits, legal, rv, a.temperature, game, move);
         }
     }
     // ---- teardown: every tcgen05 operation has completed (all layers were waited on) ----

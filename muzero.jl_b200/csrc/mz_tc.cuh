@@ -22,7 +22,6 @@
 
 __device__ __forceinline__ void mz_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void mz_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void mz_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).  K-major SW128: SBO = 1024 B between 8-row groups, LBO unused (1).
 __device__ __forceinline__ uint64_t mz_tc_desc(uint32_t smem_addr) {

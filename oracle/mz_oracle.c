@@ -256,7 +256,30 @@ static void dense(const float *blob, const layer_t *l, const float *x, float *y)
     const float *W = blob + l->w_off, *b = blob + l->b_off;
     int out = l->out;
     for (int o = 0; o < out; o++) acc[o] = 0.0f;
-    if (g_bf16) {
+    if (g_bf16 >= 2) {
+        /* split-precision operands (mzo_set_bf16(2 | 3)): x = xh + xl (+ xm), every part a bfloat16, products exact in Float32, the small
+         * cross terms accumulated first and the hi*hi terms on top -- the order the tensor-core kernel issues its MMAs in.
+         * 2: hi*lo + lo*hi + hi*hi (16 mantissa bits per operand); 3: all six terms down to 2^-24 (24 bits). */
+        float xs[3][256];
+        for (int k = 0; k < l->in; k++) {
+            float h = bf16_round(x[k]), m = bf16_round(x[k] - h), lo = bf16_round((x[k] - h) - m);
+            xs[0][k] = h; xs[1][k] = m; xs[2][k] = lo;
+        }
+        static const int t2[3][2] = {{0, 1}, {1, 0}, {0, 0}};
+        static const int t3[6][2] = {{0, 2}, {2, 0}, {1, 1}, {0, 1}, {1, 0}, {0, 0}};
+        const int nt = g_bf16 == 2 ? 3 : 6;
+        for (int t = 0; t < nt; t++) {
+            const int xi = g_bf16 == 2 ? t2[t][0] : t3[t][0], wi = g_bf16 == 2 ? t2[t][1] : t3[t][1];
+            for (int k = 0; k < l->in; k++) {
+                const float xk = xs[xi][k];
+                const float *wk = W + (size_t)k * out;
+                for (int o = 0; o < out; o++) {
+                    float h = bf16_round(wk[o]), m = bf16_round(wk[o] - h), lo = bf16_round((wk[o] - h) - m);
+                    acc[o] = fmaf(wi == 0 ? h : wi == 1 ? m : lo, xk, acc[o]);
+                }
+            }
+        }
+    } else if (g_bf16) {
         for (int k = 0; k < l->in; k++) {
             float xk = bf16_round(x[k]);
             const float *wk = W + (size_t)k * out;

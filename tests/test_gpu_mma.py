@@ -1,0 +1,126 @@
+"""GPU tests of the split-precision tensor-core path (nn_mode = MZ_NN_SPLIT_MMA, mz_kernels_mma.cuh): bf16 hi + lo operands on
+warp-level MMAs, fp32 accumulation.  Not bit-exact by construction (the tensor core sums in its own order); what is asserted:
+network outputs within 2e-5 of the Float32 oracle, visit counts identical to the FLOAT32 oracle on >= 99 % of 1024 roots, the same
+most-visited action on >= 99.9 %, and everything that does not depend on network arithmetic (histories' structure, temperature rule,
+slot-count independence) exactly."""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+MMA_ATOL = 2e-5
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from muzero_jl_b200 import capi
+    return capi
+
+
+def make(capi, **kw):
+    kw.setdefault("num_slots", 256); kw.setdefault("replay_buffer_size", 1024)
+    cfg = capi.default_config(nn_mode=capi.NN_SPLIT_MMA, **kw)
+    return capi.Context(cfg), common.oracle_config(cfg)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(width_hidden=48, depth_prediction=1, depth_value=0, depth_policy=2, depth_dynamics=0, depth_state_head=1, depth_reward=2),
+                                dict(width_hidden=32, stacked_observations=0, depth_representation=0)])
+def test_mma_networks_match_float32_oracle(capi, kw):
+    ctx, ocfg = make(capi, **kw)
+    ctx.init_weights(1337); blob = ctx.get_weights()
+    rng = np.random.default_rng(5)
+    blob[:] = blob + np.where(blob == 0, rng.uniform(-0.2, 0.2, blob.shape), 0).astype(np.float32)     # non-zero biases
+    ctx.set_weights(blob)
+    n = 70
+    st, legal, tp = common.random_stacked(ocfg, n, seed=9)
+    h = ctx.representation(st)
+    oh = np.stack([O.representation(ocfg, blob, x) for x in st])
+    assert np.max(np.abs(h - oh)) <= MMA_ATOL * max(1.0, float(np.max(np.abs(oh))))
+    v, p = ctx.prediction(oh)
+    ov, op = zip(*[O.prediction(ocfg, blob, x) for x in oh])
+    assert np.max(np.abs(v - np.array(ov))) <= MMA_ATOL and np.max(np.abs(p - np.stack(op))) <= MMA_ATOL
+    for scale in (1.0, 64.0):                                             # hidden states after several in-place doublings (Q6)
+        sa = np.concatenate([oh * 2 * scale, np.full((n, 9), np.float32(5.0 / 9.0), np.float32)], axis=1)
+        nh, r = ctx.dynamics(sa)
+        onh, orr = zip(*[O.dynamics(ocfg, blob, x) for x in sa])
+        onh = np.stack(onh)
+        assert np.max(np.abs(nh - onh)) <= MMA_ATOL * max(1.0, float(np.max(np.abs(onh)))) and np.max(np.abs(r - np.array(orr))) <= MMA_ATOL
+    # the oracle's emulation of the same operand split (same products, sequential accumulation): an order of magnitude closer
+    O.set_bf16(2)
+    try:
+        eh = np.stack([O.representation(ocfg, blob, x) for x in st])
+    finally:
+        O.set_bf16(0)
+    assert np.max(np.abs(h - eh)) <= 0.3 * MMA_ATOL * max(1.0, float(np.max(np.abs(oh))))
+    ctx.close()
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.25])
+def test_mma_run_mcts_agrees_with_float32_oracle(capi, eps):
+    n, S = 1024, 50
+    ctx, ocfg = make(capi, num_iters=S, exploration_eps=eps, num_slots=1024)
+    ctx.init_weights(7); blob = ctx.get_weights()
+    st, legal, tp = common.random_stacked(ocfg, n, seed=77)
+    game = np.arange(n, dtype=np.uint64) + 100; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    assert np.all(vc.sum(1) == S) and np.all((vc > 0) <= ((legal[:, None] >> np.arange(9)) & 1).astype(bool))
+    exact = [O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i])) for i in range(n)]
+    same = np.mean([vc[i].tolist() == exact[i][0].tolist() for i in range(n)])
+    best = np.mean([int(np.argmax(vc[i])) == int(np.argmax(exact[i][0])) for i in range(n)])
+    perr = max(float(np.max(np.abs(pri[i] - exact[i][2]))) for i in range(n))
+    print("split-precision MMA path, %d roots x %d simulations, eps %.2f: visit counts identical to the Float32 oracle %.4f, same most-visited action %.4f, "
+          "max prior error %.2e" % (n, S, eps, same, best, perr))
+    assert same >= 0.99 and best >= 0.999 and perr <= 1e-5
+    ident = [i for i in range(n) if vc[i].tolist() == exact[i][0].tolist()]
+    assert np.max(np.abs(rv[ident] - np.array([exact[i][1] for i in ident]))) <= 1e-4
+    ctx.close()
+
+
+def test_mma_self_play_agrees_with_float32_oracle_and_is_independent_of_slot_count(capi):
+    res = []
+    for slots in (64, 4096):                                              # 1 and 28 trees per CTA
+        ctx, ocfg = make(capi, num_slots=slots, replay_buffer_size=max(1024, slots), num_iters=30)
+        ctx.init_weights(11); blob = ctx.get_weights()
+        sims, moves = ctx.self_play(0, 600, 1.0)
+        assert sims == moves * 30
+        h = ctx.history_export(); order = np.argsort(h["game_id"])
+        res.append({k: h[k][order] for k in common.HIST_KEYS}); ctx.close()
+    for k in common.HIST_KEYS:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    o = O.self_play(ocfg, blob, 0, 600, 1.0, 8)
+    same_game = np.mean([all(np.array_equal(res[0][k][i], o[k][i]) for k in ("T", "actions", "child_visits")) for i in range(600)])
+    same_first = np.mean([np.array_equal(res[0]["child_visits"][i, 0], o["child_visits"][i, 0]) for i in range(600)])
+    print("split-precision MMA self-play: %.4f of 600 games identical to the Float32 oracle in every ply, %.4f in the first ply" % (same_game, same_first))
+    assert same_first >= 0.99 and same_game >= 0.93
+    for j in range(600):
+        T = res[0]["T"][j]
+        assert 6 <= T <= 9 and np.allclose(res[0]["child_visits"][j, :T].sum(1), 1.0, atol=1e-6) and np.all(res[0]["rewards"][j, :T - 1] == 0)
+
+
+def test_mma_randomised_configurations_agree(capi):
+    for seed in range(4):
+        rng = np.random.default_rng(300 + seed)
+        kw = dict(num_iters=int(rng.integers(5, 41)), stacked_observations=int(rng.integers(0, 2)), depth_representation=int(rng.integers(0, 4)),
+                  depth_prediction=int(rng.integers(0, 4)), depth_dynamics=int(rng.integers(0, 4)), depth_policy=int(rng.integers(0, 3)),
+                  depth_value=int(rng.integers(0, 3)), depth_reward=int(rng.integers(0, 3)), depth_state_head=int(rng.integers(0, 4)),
+                  width_hidden=int(rng.choice([32, 48, 64])), num_slots=int(rng.integers(8, 200)), seed=int(rng.integers(1, 1 << 30)),
+                  exploration_eps=float(np.float32(rng.choice([0.0, 0.25]))))
+        ctx, ocfg = make(capi, **kw)
+        ctx.init_weights(seed + 3); blob = ctx.get_weights()
+        n = 200
+        st, legal, tp = common.random_stacked(ocfg, n, seed=seed)
+        gid = np.arange(n, dtype=np.uint64) + 50; mv = np.ones(n, np.int32)
+        vc, rv = ctx.run_mcts(st, legal, tp, True, gid, mv)
+        same = np.mean([vc[i].tolist() == O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(gid[i]), 1)[0].tolist() for i in range(n)])
+        assert same >= 0.97, (same, kw)
+        ctx.close()
+
+
+def test_mma_rejects_wide_layers_and_resnet(capi):
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        capi.Context(capi.default_config(num_slots=32, nn_mode=capi.NN_SPLIT_MMA, stacked_observations=2))     # 99 inputs
+    assert e.value.code == capi.E_UNSUPPORTED
+    with pytest.raises(capi.MuZeroB200Error):
+        capi.Context(capi.resnet_config(num_slots=32, nn_mode=capi.NN_SPLIT_MMA))
