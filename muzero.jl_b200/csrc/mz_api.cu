@@ -531,7 +531,8 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
         launch_scope ls(c, 5); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
     } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
         mz_nn_mma_args t{}; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
-        launch_scope ls(c, 5); mz_k_nn_forward_mma<<<(B + MZ_ROWS - 1) / MZ_ROWS, 128, mz_mma_smem_bytes(c->mma.slot_bytes, c->mma.bias_floats, P.hidden_pad, P.S, 0), c->stream>>>(P, c->mma, t);
+        if (const char *rp = getenv("MZ_MMA_PROBE_REPEAT")) t.repeat = atoi(rp);   // measurement switch (profiles/nn_rate.py)
+        launch_scope ls(c, 5); mz_k_nn_forward_mma<<<(B + MZ_ROWS - 1) / MZ_ROWS, 160, mz_mma_smem_bytes(c->mma.slot_bytes, c->mma.bias_floats, P.hidden_pad, P.S, 0), c->stream>>>(P, c->mma, t);
     } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
         mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
         launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -637,7 +638,7 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
             mz_search_mma_args t{}; t.base = a; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.pbc_in_smem = c->mma_pbc_smem;
             int rows = (m + c->sm_count - 1) / c->sm_count; t.rows = rows < 1 ? 1 : rows > MZ_ROWS ? MZ_ROWS : rows;
-            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_API><<<(m + t.rows - 1) / t.rows, MZ_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
+            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_API><<<(m + t.rows - 1) / t.rows, MZ_MMA_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -729,7 +730,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
             launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
         } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
             mz_search_mma_args t{}; t.base = a; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.pbc_in_smem = c->mma_pbc_smem; t.rows = c->mma_rows;
-            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_SLOTS><<<(G + t.rows - 1) / t.rows, MZ_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
+            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_SLOTS><<<(G + t.rows - 1) / t.rows, MZ_MMA_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);

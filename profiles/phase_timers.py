@@ -7,7 +7,7 @@ from muzero_jl_b200 import capi
 
 G, S = 4096, 50
 names = ["select", "stage", "-", "network(+wait)", "-", "hidden write(+wait)", "expand", "backup"]
-for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_tcgen05")):
+for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_tcgen05"), (capi.NN_SPLIT_MMA, "split_mma")):
     ctx = capi.Context(capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=10000, nn_mode=mode))
     ctx.init_weights(1337)
     ctx.self_play(0, G, 1.0)
@@ -24,5 +24,7 @@ for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_
         q = raw[o + 6]
         if q > 0:
             lab = ['issue', 'mbarrier wait', 'tcgen05.ld', 'epilogue', 'fence.proxy.async', 'group barrier']
+            if mode == capi.NN_SPLIT_MMA:      # per simulation of one dynamics warp (o = 12: trunk + state head, 20: trunk + reward head)
+                lab = ['wait for weights', 'load input', 'MMAs', 'epilogue', 'release slot + refill', '-']
             print('%s TC round (%s): %.0f cycles; ' % (label, who, raw[o:o + 6].sum() / q) + ', '.join('%s %.0f' % (lab[i], raw[o + i] / q) for i in range(6)))
     ctx.close()

@@ -7,6 +7,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#ifndef UNROLL
+#define UNROLL 1
+#endif
+#define PRAGMA_(x) _Pragma(#x)
+#define PRAGMA(x) PRAGMA_(x)
 
 __device__ __forceinline__ void hmma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -29,6 +34,7 @@ __global__ void __launch_bounds__(256, 1) probe(int layers, long long *out, floa
     uint32_t ah[4][4], al[4][4];
     for (int s = 0; s < 4; s++) for (int i = 0; i < 4; i++) { ah[s][i] = 0x3c003c00u + lane; al[s][i] = 0x38003800u; }
     long long t0 = clock64();
+PRAGMA(unroll UNROLL)
     for (int L = 0; L < layers; L++) {
         float d[8][4];
 #pragma unroll
