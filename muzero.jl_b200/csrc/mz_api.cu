@@ -11,7 +11,7 @@
 #include "mz_learner_bptt.cuh"
 #include "mz_rn_host.h"
 #include "mz_kernels_rn.cuh"
-#include "mz_kernels_mma.cuh"
+#include "mz_kernels_sp.cuh"
 
 namespace {
 
@@ -64,7 +64,7 @@ struct mz_ctx {
     int exact_gt = 128;   // threads per network group of the exact search kernel: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps; measured no faster: the layer is bound by shared-memory wavefronts)
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     unsigned char *d_w_tc = nullptr; float *d_bias_tc = nullptr; size_t smem_bytes_tc = 0;   // tensor-core weight image
-    mz_mma_plan mma{}; unsigned char *d_w_mma = nullptr; float *d_bias_mma = nullptr; size_t smem_bytes_mma = 0; int mma_rows = 32, mma_pbc_smem = 0;   // split-precision MMA path
+    mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
     void *d_trees = nullptr;
     mz_slots slots{}; mz_ring ring{};
@@ -188,11 +188,11 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
         MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_tc, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     }
-    if (c->d_w_mma && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // bf16 hi/lo fragment-ordered image + fp32 biases for the split-precision MMA path
-        std::vector<uint32_t> image; std::vector<float> bias;
-        mzh::pack_weights_mma(c->M.P, c->mma, src.data(), image, bias);
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_w_mma, image.data(), (size_t)c->mma.image_bytes, cudaMemcpyHostToDevice, c->stream));
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_mma, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (c->d_w_sp && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // bf16 hi / lo A-operand image + fp32 biases for the split-precision tensor-core path
+        std::vector<uint16_t> image; std::vector<float> bias;
+        mzh::pack_weights_sp(c->M.P, c->spp, src.data(), image, bias);
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_w_sp, image.data(), (size_t)c->spp.image_bytes, cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_sp, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -327,8 +327,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (cfg->replay_buffer_size < cfg->num_slots) { int r = fail(nullptr, MZ_E_ARG, "replay_buffer_size must be >= num_slots"); delete c; return r; }
     if (cfg->nn_mode != MZ_NN_FP32_EXACT && cfg->nn_mode != MZ_NN_BF16_TC && cfg->nn_mode != MZ_NN_SPLIT_MMA) { int r = fail(nullptr, MZ_E_ARG, "unknown nn_mode %d", cfg->nn_mode); delete c; return r; }
     if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
-    if (cfg->net_type == MZ_NET_FEEDFORWARD) mzh::build_mma_plan(c->M.P, c->mma);
-    if (cfg->nn_mode == MZ_NN_SPLIT_MMA && (cfg->net_type != MZ_NET_FEEDFORWARD || !c->mma.ok)) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA needs the FeedForwardHP networks with every layer in <= 64 and out <= 64"); delete c; return r; }
+    if (cfg->nn_mode == MZ_NN_SPLIT_MMA && (cfg->net_type != MZ_NET_FEEDFORWARD || !c->M.P.tc_ok)) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA needs the FeedForwardHP networks with every layer in <= 64 and out <= 64"); delete c; return r; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }
@@ -383,20 +382,25 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
             mz_destroy(c); return r;
         }
     }
-    if (!resnet && c->mma.ok) {
-        // trees per CTA: all SMs busy (4096 games on 148 SMs -> 28 trees on 147 CTAs); the PUCT table goes to shared memory when it fits
-        int rows = (cfg->num_slots + c->sm_count - 1) / c->sm_count;
-        c->mma_rows = rows < 1 ? 1 : rows > MZ_ROWS ? MZ_ROWS : rows;
-        c->mma_pbc_smem = mz_mma_smem_bytes(c->mma.slot_bytes, c->mma.bias_floats, P.hidden_pad, P.S, 1) + 2048 <= (size_t)prop.sharedMemPerBlockOptin ? 1 : 0;
-        c->smem_bytes_mma = mz_mma_smem_bytes(c->mma.slot_bytes, c->mma.bias_floats, P.hidden_pad, P.S, c->mma_pbc_smem);
-        if (c->smem_bytes_mma <= (size_t)prop.sharedMemPerBlockOptin) {
-            MZ_CREATE(allow_max_smem(mz_k_search_mma<MZ_MODE_API>, prop));
-            MZ_CREATE(allow_max_smem(mz_k_search_mma<MZ_MODE_SLOTS>, prop));
-            MZ_CREATE(allow_max_smem(mz_k_nn_forward_mma, prop));
-            MZ_CREATE(cudaMalloc((void **)&c->d_w_mma, (size_t)c->mma.image_bytes + 256));
-            MZ_CREATE(dmalloc(&c->d_bias_mma, (size_t)c->mma.bias_floats));
+    if (!resnet && P.tc_ok) {
+        // rounds + weight sets for this device's shared memory (mz_host.h: build_sp_plan); the table of rounds lives in global memory
+        mzh::build_sp_plan(P, (size_t)prop.sharedMemPerBlockOptin, c->spp);
+        if (c->spp.ok) {
+            const mz_sp_plan &S = c->spp;
+            c->smem_bytes_sp = mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S);
+            MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_API>, prop));
+            MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_SLOTS>, prop));
+            MZ_CREATE(allow_max_smem(mz_k_nn_forward_sp, prop));
+            MZ_CREATE(cudaMalloc((void **)&c->d_w_sp, (size_t)S.image_bytes + 256));
+            MZ_CREATE(dmalloc(&c->d_bias_sp, (size_t)S.bias_floats));
+            MZ_CREATE(cudaMalloc((void **)&c->d_rounds_sp, sizeof(mz_sp_round) * MZ_SP_MAX_ROUNDS));
+            MZ_CREATE(cudaMemcpy(c->d_rounds_sp, S.round, sizeof(mz_sp_round) * MZ_SP_MAX_ROUNDS, cudaMemcpyHostToDevice));
+            mz_sp_args &A = c->spa;
+            A.image = c->d_w_sp; A.bias = c->d_bias_sp; A.rounds = c->d_rounds_sp;
+            for (int n = 0; n < 3; n++) { A.first[n] = S.first[n]; A.n_rounds[n] = S.n_rounds[n]; A.set_first[n] = S.set_first[n]; A.n_sets[n] = S.n_sets[n]; }
+            A.total_rounds = S.total_rounds; A.total_sets = S.total_sets; A.warea_bytes = S.warea_bytes; A.bias_floats = S.bias_floats;
         } else if (cfg->nn_mode == MZ_NN_SPLIT_MMA) {
-            int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes_mma, (size_t)prop.sharedMemPerBlockOptin);
+            int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA: the networks do not fit the shared memory of this device (%zu B per CTA)", (size_t)prop.sharedMemPerBlockOptin);
             mz_destroy(c); return r;
         }
     }
@@ -445,7 +449,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    void *ptrs[] = {c->d_w_mma, c->d_bias_mma, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -530,9 +534,8 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
         const int nt = c->rn.R.ntrees;
         launch_scope ls(c, 5); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
     } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
-        mz_nn_mma_args t{}; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
-        if (const char *rp = getenv("MZ_MMA_PROBE_REPEAT")) t.repeat = atoi(rp);   // measurement switch (profiles/nn_rate.py)
-        launch_scope ls(c, 5); mz_k_nn_forward_mma<<<(B + MZ_ROWS - 1) / MZ_ROWS, 160, mz_mma_smem_bytes(c->mma.slot_bytes, c->mma.bias_floats, P.hidden_pad, P.S, 0), c->stream>>>(P, c->mma, t);
+        mz_nn_sp_args t{}; t.sp = c->spa; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
+        launch_scope ls(c, 5); mz_k_nn_forward_sp<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t);
     } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
         mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
         launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -636,9 +639,8 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
             const int nt = c->rn.R.ntrees;
             launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_API><<<(m + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
         } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
-            mz_search_mma_args t{}; t.base = a; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.pbc_in_smem = c->mma_pbc_smem;
-            int rows = (m + c->sm_count - 1) / c->sm_count; t.rows = rows < 1 ? 1 : rows > MZ_ROWS ? MZ_ROWS : rows;
-            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_API><<<(m + t.rows - 1) / t.rows, MZ_MMA_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
+            mz_search_sp_args t{}; t.base = a; t.sp = c->spa;
+            launch_scope ls(c, 0); mz_k_search_sp<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
@@ -729,8 +731,8 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
             const int nt = c->rn.R.ntrees;
             launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
         } else if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {
-            mz_search_mma_args t{}; t.base = a; t.image = c->d_w_mma; t.bias = c->d_bias_mma; t.pbc_in_smem = c->mma_pbc_smem; t.rows = c->mma_rows;
-            launch_scope ls(c, 0); mz_k_search_mma<MZ_MODE_SLOTS><<<(G + t.rows - 1) / t.rows, MZ_MMA_THREADS, c->smem_bytes_mma, c->stream>>>(P, c->mma, t);
+            mz_search_sp_args t{}; t.base = a; t.sp = c->spa;
+            launch_scope ls(c, 0); mz_k_search_sp<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t);
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);

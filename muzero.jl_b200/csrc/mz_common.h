@@ -167,27 +167,59 @@ struct mz_params {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Split-precision network path (nn_mode = MZ_NN_SPLIT_MMA, mz_kernels_mma.cuh): every Dense layer as warp-level tensor-core MMAs
-// (mma.sync m16n8k16, bf16 operands, fp32 accumulate) with BOTH operands split into bf16 hi + lo parts and the three products
-// hi*lo + lo*hi + hi*hi accumulated, i.e. 16 mantissa bits per operand.  A warp owns 16 rows (trees) for a whole chain of layers: the
-// accumulator fragments of one layer are, after bias + activation + hi/lo split in registers, the A fragments of the next one, so a
-// chain needs no shared-memory round trip and no barrier.  Weights stream through a shared-memory ring per network in "fragment
-// order" (host-packed: one 16-byte load per lane per (n-tile, k-step) = {hi b0, hi b1, lo b0, lo b1}).
-// A network is a STREAM of layers [trunk..., head 1 and head 2 interleaved]; the warps of a 16-row tile are specialised per head
-// (each runs the trunk and one head), bit 0 / bit 1 of `use` say which of them runs a stream entry.
+// Split-precision network path (nn_mode = MZ_NN_SPLIT_MMA; mz_sp.cuh, mz_kernels_sp.cuh): every Dense layer on the tcgen05 tensor
+// cores with BOTH operands split into bf16 hi + lo parts, x = hi + lo, and the three products W_hi X_hi + W_lo X_hi + W_hi X_lo
+// accumulated in fp32 in TMEM: 16 mantissa bits per operand.  The host compiles the three networks into ROUNDS (up to two independent
+// layers that are issued together: e.g. the first layers of the two heads of a network) and decides where each round's weights live:
+// hi + lo images of prediction + dynamics (240 KB) do not fit an SM next to the activation tiles, so the rounds of a network share
+// WEIGHT SETS -- shared-memory regions that alternate between the rounds assigned to them (round r and round r + n_sets): when a round's
+// MMAs have completed, its set is refilled by TMA with the weights of the round that uses the set next.  The sequence is the same in
+// every simulation, so addresses (and UMMA descriptors) are static and the refill runs half a network pass ahead of its use.
 // ------------------------------------------------------------------------------------------------
-#define MZ_MMA_MAX_STREAM 24
-#define MZ_MMA_SLOTS 3
-struct mz_mma_plan {
-    int32_t n[3];                                   // stream length per network
-    uint8_t layer[3][MZ_MMA_MAX_STREAM];            // layer index (into mz_params::layers)
-    uint8_t use[3][MZ_MMA_MAX_STREAM];              // bit 0: the head-1 warps run it, bit 1: the head-2 warps
-    uint8_t first[3][MZ_MMA_MAX_STREAM];            // bit h: the layer reads the network input (head h's chain starts here)
-    uint8_t last[3][MZ_MMA_MAX_STREAM];             // bit h: the layer is the end of head h's chain (fp32 outputs)
-    int32_t w_off[MZ_MAX_LAYERS], w_bytes[MZ_MAX_LAYERS];   // the layer's fragment block inside the global image (16-byte aligned)
-    int32_t ks[MZ_MAX_LAYERS], nt[MZ_MAX_LAYERS];   // k-steps (in / 16) and n-tiles (out / 8), rounded up
-    int32_t image_bytes, slot_bytes, bias_floats, ok;
+#define MZ_SP_MAX_ROUNDS 40
+#define MZ_SP_MAX_SETS 48
+#define MZ_SP_TILE_BYTES 4096                      // one operand tile: [64 k][32 trees] bf16, N-major, SWIZZLE_64B
+#define MZ_SP_TILES_PER_GROUP 3                    // input / ping / pong, each as a hi tile followed by a lo tile
+struct mz_sp_job {
+    int32_t a_off;                                  // byte offset of the layer's hi weight block in the CTA's weight area (lo block = + a_bytes)
+    int32_t a_bytes;                                // bytes of one block: rows8(out) x 128
+    int32_t bias_off;                               // float offset of the layer's bias in the bias block
+    int32_t f32_off;                                // final layer: float offset of its fp32 output in the output area, else -1
+    int16_t src_tile, dst_tile;                     // operand tiles of the group (0 = input, 1, 2); dst_tile = -1 for a final layer
+    int16_t ks, out, act, perm;                     // k-steps, real outputs, activation, column order of the input tile (0 natural, 1 permuted)
+    int16_t layer, pad_[3];
 };
+struct mz_sp_copy { int32_t src_off, bytes, dst_off, pad_; };   // global image offset -> weight-area offset
+struct mz_sp_round {
+    mz_sp_job job[2];
+    mz_sp_copy copy[2];
+    int16_t njobs, ncopy;
+    int16_t set;                                    // weight set = mbarrier index
+    int16_t next;                                   // global index of the round whose weights replace this round's when it has completed (-1: none)
+    int16_t per_pass, ord;                          // fills of the set per pass over the network (0: loaded once) and which of them this round consumes
+};
+struct mz_sp_plan {
+    int32_t first[3], n_rounds[3];                  // per network (representation, prediction, dynamics): rounds [first, first + n)
+    int32_t set_first[3], n_sets[3];                // per network: its weight sets (the representation has one, loaded once, over the dynamics area)
+    int32_t total_rounds, total_sets;
+    int32_t image_bytes, warea_bytes, bias_floats, divisor, ok;
+    int32_t out_off[4];                             // float offsets of value / logits / reward / hidden outputs in the output area
+    int32_t w_off[MZ_MAX_LAYERS], w_bytes[MZ_MAX_LAYERS];   // image: hi block at w_off, lo block at w_off + w_bytes
+    mz_sp_round round[MZ_SP_MAX_ROUNDS];
+};
+
+#define MZ_SP_RDESC_BYTES 128                       // sizeof(mz_sp_rdesc), the device form of a round (mz_sp.cuh)
+#define MZ_SP_CTRL_BYTES 1024                       // mbarriers, TMEM slot, per-set use counters
+// dynamic shared memory of a kernel on this path (the carve-up is mz_sp_carve in mz_sp.cuh)
+MZ_HD size_t mz_sp_smem_bytes(int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S) {
+    size_t tiles = (size_t)2 * MZ_SP_TILES_PER_GROUP * 2 * MZ_SP_TILE_BYTES;
+    size_t bias = ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
+    size_t out = (size_t)(24 + hidden_pad) * 32 * 4;
+    size_t tab = (((size_t)S + 2) * 16 + 127) & ~(size_t)127;
+    size_t path = (((size_t)S + 2) * 2 * 32 + 127) & ~(size_t)127;
+    size_t prog = ((size_t)total_rounds * MZ_SP_RDESC_BYTES + 127) & ~(size_t)127;
+    return 1024 + (size_t)warea_bytes + tiles + MZ_SP_CTRL_BYTES + bias + out + tab + path + prog;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Learner backward pass (grad_mode = MZ_GRAD_BPTT): host-built program of backward layer applications.

@@ -244,57 +244,161 @@ inline void pack_weights_tc(const mz_params &P, const float *src, std::vector<ui
     }
 }
 
-// ---- split-precision MMA path (mz_kernels_mma.cuh): stream plan + fragment-ordered weight image ---------------------------------
-inline void build_mma_plan(const mz_params &P, mz_mma_plan &M) {
-    memset(&M, 0, sizeof(M));
-    M.ok = 1;
+// ---- split-precision tensor-core path (mz_sp.cuh, mz_kernels_sp.cuh): rounds, weight sets, hi / lo weight image ----------------
+inline float bf16_to_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+
+struct sp_builder { const mz_params *P; mz_sp_plan *S; };
+inline mz_sp_job sp_job(const mz_params &P, const mz_sp_plan &S, int layer, int src, int dst, int f32_off, int perm) {
+    const mz_layer &l = P.layers[layer];
+    mz_sp_job j; memset(&j, 0, sizeof(j));
+    j.a_off = 0; j.a_bytes = S.w_bytes[layer]; j.bias_off = layer * 64; j.f32_off = f32_off;
+    j.src_tile = (int16_t)src; j.dst_tile = (int16_t)dst; j.ks = (int16_t)((l.in + 15) / 16); j.out = (int16_t)l.out; j.act = (int16_t)l.act;
+    j.perm = (int16_t)perm; j.layer = (int16_t)layer;
+    return j;
+}
+inline void sp_emit(mz_sp_plan &S, const mz_sp_job *j0, const mz_sp_job *j1) {
+    if (S.total_rounds >= MZ_SP_MAX_ROUNDS) { S.ok = 0; return; }
+    mz_sp_round &R = S.round[S.total_rounds++];
+    memset(&R, 0, sizeof(R));
+    R.job[0] = *j0; R.njobs = 1;
+    if (j1) { R.job[1] = *j1; R.njobs = 2; }
+    R.set = -1; R.next = -1;
+}
+// Rounds of one network.  Three operand tiles per group: 0 = the network input (free again once the first layer has run), 1, 2.
+// Trunk layers ping-pong; the two heads advance in lock-step when the second head is at most two layers deep (so three tiles suffice),
+// otherwise one after the other.  Every hidden layer flips the column order of the activations (mz_sp.cuh: the epilogue writes the
+// eight columns a thread holds as one 16-byte chunk), `perm` tracks it so the final layer can undo it.
+inline void sp_build_net(const mz_params &P, mz_sp_plan &S, int net, int h1_off, int h2_off) {
+    const mz_net &N = P.nets[net];
+    const int f = N.first;
+    S.first[net] = S.total_rounds;
+    int cur = 0, perm = 0;
+    for (int i = 0; i < N.n_trunk; i++) {
+        const bool last = i == N.n_trunk - 1;
+        if (last && N.n_h1 == 0) { mz_sp_job j = sp_job(P, S, f + i, cur, -1, h1_off, perm); sp_emit(S, &j, nullptr); }
+        else { const int d = cur == 1 ? 2 : 1; mz_sp_job j = sp_job(P, S, f + i, cur, d, -1, perm); sp_emit(S, &j, nullptr); cur = d; perm ^= 1; }
+    }
+    if (N.n_h1 > 0) {
+        const int f1 = f + N.n_trunk, f2 = f1 + N.n_h1, T = cur;
+        int other[2], k = 0;
+        for (int t = 0; t < 3; t++) if (t != T) other[k++] = t;
+        if (N.n_h2 <= 2 && N.n_h2 <= N.n_h1) {
+            int c1 = T, c2 = T, p1 = perm, p2 = perm;
+            for (int i = 0; i < N.n_h1; i++) {
+                const bool last1 = i == N.n_h1 - 1, has2 = i < N.n_h2, last2 = i == N.n_h2 - 1;
+                int d1 = -1, d2 = -1;
+                if (!last1) { for (int t = 0; t < 3; t++) if (t != c1 && !(has2 && t == c2)) { d1 = t; break; } }
+                if (has2 && !last2) { for (int t = 0; t < 3; t++) if (t != c1 && t != c2 && t != d1) { d2 = t; break; } }
+                mz_sp_job j1 = sp_job(P, S, f1 + i, c1, d1, last1 ? h1_off : -1, p1);
+                if (has2) { mz_sp_job j2 = sp_job(P, S, f2 + i, c2, d2, last2 ? h2_off : -1, p2); sp_emit(S, &j1, &j2); }
+                else sp_emit(S, &j1, nullptr);
+                if (!last1) { c1 = d1; p1 ^= 1; }
+                if (has2 && !last2) { c2 = d2; p2 ^= 1; }
+            }
+        } else {
+            for (int h = 0; h < 2; h++) {
+                const int fh = h == 0 ? f1 : f2, nh = h == 0 ? N.n_h1 : N.n_h2, off = h == 0 ? h1_off : h2_off;
+                int c = T, p = perm;
+                for (int i = 0; i < nh; i++) {
+                    const bool last = i == nh - 1;
+                    const int d = last ? -1 : (c == other[0] ? other[1] : other[0]);
+                    mz_sp_job j = sp_job(P, S, fh + i, c, d, last ? off : -1, p); sp_emit(S, &j, nullptr);
+                    if (!last) { c = d; p ^= 1; }
+                }
+            }
+        }
+    }
+    S.n_rounds[net] = S.total_rounds - S.first[net];
+}
+inline int sp_round_bytes(const mz_sp_round &R) { int b = 0; for (int j = 0; j < R.njobs; j++) b += 2 * R.job[j].a_bytes; return b; }
+// places the weights of network `net` at `base` with its rounds spread over n weight sets (round i of the network uses set i % n);
+// returns the bytes used
+inline int sp_place(mz_sp_plan &S, int net, int n, int base, int set_first) {
+    const int f = S.first[net], R = S.n_rounds[net];
+    int off = base;
+    for (int s = 0; s < n; s++) {
+        int size = 0;
+        for (int i = s; i < R; i += n) { const int b = sp_round_bytes(S.round[f + i]); if (b > size) size = b; }
+        for (int i = s; i < R; i += n) {
+            mz_sp_round &Rd = S.round[f + i];
+            Rd.set = (int16_t)(set_first + s);
+            const int nx = i + n < R ? i + n : s;
+            Rd.next = (int16_t)(nx == i ? -1 : f + nx);
+            const int members = (R - s + n - 1) / n;
+            Rd.per_pass = (int16_t)(members > 1 ? members : 0); Rd.ord = (int16_t)(members > 1 ? i / n : 0);
+            int o = off; Rd.ncopy = Rd.njobs;
+            for (int j = 0; j < Rd.njobs; j++) {
+                Rd.job[j].a_off = o;
+                Rd.copy[j].src_off = S.w_off[Rd.job[j].layer]; Rd.copy[j].bytes = 2 * Rd.job[j].a_bytes; Rd.copy[j].dst_off = o; Rd.copy[j].pad_ = 0;
+                o += 2 * Rd.job[j].a_bytes;
+            }
+        }
+        off += size;
+    }
+    S.set_first[net] = set_first; S.n_sets[net] = n;
+    return off - base;
+}
+// the representation: every round's weights side by side, one set (mbarrier), loaded once per kernel
+inline int sp_place_linear(mz_sp_plan &S, int net, int base, int set) {
+    const int f = S.first[net], R = S.n_rounds[net];
+    int off = base;
+    for (int i = 0; i < R; i++) {
+        mz_sp_round &Rd = S.round[f + i];
+        Rd.set = (int16_t)set; Rd.next = -1; Rd.per_pass = 0; Rd.ord = 0; Rd.ncopy = Rd.njobs;
+        for (int j = 0; j < Rd.njobs; j++) {
+            Rd.job[j].a_off = off;
+            Rd.copy[j].src_off = S.w_off[Rd.job[j].layer]; Rd.copy[j].bytes = 2 * Rd.job[j].a_bytes; Rd.copy[j].dst_off = off; Rd.copy[j].pad_ = 0;
+            off += 2 * Rd.job[j].a_bytes;
+        }
+    }
+    S.set_first[net] = set; S.n_sets[net] = 1;
+    return off - base;
+}
+inline void build_sp_plan(const mz_params &P, size_t smem_limit, mz_sp_plan &S) {
+    memset(&S, 0, sizeof(S));
+    S.ok = 1;
     int off = 0;
     for (int i = 0; i < P.n_layers; i++) {
         const mz_layer &l = P.layers[i];
-        if (l.in > 64 || l.out > 64) M.ok = 0;
-        M.ks[i] = (l.in + 15) / 16; M.nt[i] = (l.out + 7) / 8;
-        M.w_off[i] = off; M.w_bytes[i] = M.ks[i] * M.nt[i] * 512;
-        off += M.w_bytes[i];
-        if (M.w_bytes[i] > M.slot_bytes) M.slot_bytes = M.w_bytes[i];
+        if (l.in > 64 || l.out > 64) S.ok = 0;
+        S.w_off[i] = off; S.w_bytes[i] = ((l.out + 7) / 8) * 1024;
+        off += 2 * S.w_bytes[i];
     }
-    M.image_bytes = off; M.bias_floats = P.n_layers * 64;
-    for (int n = 0; n < 3; n++) {
-        const mz_net &N = P.nets[n];
-        int k = 0;
-        for (int i = 0; i < N.n_trunk; i++) {
-            M.layer[n][k] = (uint8_t)(N.first + i); M.use[n][k] = N.n_h1 == 0 ? 1 : 3;
-            M.first[n][k] = i == 0 ? 3 : 0; M.last[n][k] = (N.n_h1 == 0 && i == N.n_trunk - 1) ? 1 : 0; k++;
-        }
-        const int f1 = N.first + N.n_trunk, f2 = f1 + N.n_h1;
-        for (int i = 0; i < (N.n_h1 > N.n_h2 ? N.n_h1 : N.n_h2); i++) {   // the two heads interleaved: their warps advance side by side
-            if (i < N.n_h1) { M.layer[n][k] = (uint8_t)(f1 + i); M.use[n][k] = 1; M.last[n][k] = i == N.n_h1 - 1 ? 1 : 0; k++; }
-            if (i < N.n_h2) { M.layer[n][k] = (uint8_t)(f2 + i); M.use[n][k] = 2; M.last[n][k] = i == N.n_h2 - 1 ? 2 : 0; k++; }
-        }
-        M.n[n] = k;
-        if (k > MZ_MMA_MAX_STREAM) M.ok = 0;
+    S.image_bytes = off; S.bias_floats = P.n_layers * 64;
+    if (!S.ok) return;
+    S.out_off[0] = 0; S.out_off[1] = 4 * 32; S.out_off[2] = 20 * 32; S.out_off[3] = 24 * 32;
+    sp_build_net(P, S, 0, S.out_off[3], -1);
+    sp_build_net(P, S, 1, S.out_off[0], S.out_off[1]);
+    sp_build_net(P, S, 2, S.out_off[3], S.out_off[2]);
+    if (!S.ok) return;
+    // smallest divisor d (sets per network = ceil(rounds / d)) whose weight area fits; d = 1 keeps every weight resident
+    for (int d = 1; d <= MZ_SP_MAX_ROUNDS; d++) {
+        const int np = (S.n_rounds[1] + d - 1) / d, nd = (S.n_rounds[2] + d - 1) / d;
+        if (np + nd + 1 > MZ_SP_MAX_SETS) continue;
+        const int pb = sp_place(S, 1, np, 0, 0);
+        const int db = sp_place(S, 2, nd, pb, np);
+        const int rb = sp_place_linear(S, 0, pb, np + nd);      // over the dynamics area: the representation runs before the first dynamics pass
+        S.total_sets = np + nd + 1; S.divisor = d;
+        S.warea_bytes = pb + (db > rb ? db : rb);
+        if (mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S) <= smem_limit) return;
     }
+    S.ok = 0;
 }
-inline float bf16_to_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
-// reference-order blob -> fragment-ordered image.  Per layer, n-tile j, k-step s, lane (g = lane / 4, t = lane % 4): the B fragment of
-// mma.m16n8k16 for output feature n = 8j + g: b0 = W[n][16s + 2t, +1], b1 = W[n][16s + 2t + 8, +9], each as a bf16 hi part (round to
-// nearest) and a bf16 lo part (w - hi, round to nearest): 16 bytes {hi b0, hi b1, lo b0, lo b1}.  Biases: fp32, 64 per layer.
-inline void pack_weights_mma(const mz_params &P, const mz_mma_plan &M, const float *src, std::vector<uint32_t> &image, std::vector<float> &bias) {
-    image.assign((size_t)M.image_bytes / 4 + 4, 0u); bias.assign((size_t)M.bias_floats, 0.0f);
+// reference-order blob -> per layer a bf16 hi block (round to nearest) followed by a bf16 lo block (w - hi, round to nearest), each a
+// [rows8(out) x 64] K-major SWIZZLE_128B A-operand tile (tc_tile_offset); biases fp32, 64 per layer
+inline void pack_weights_sp(const mz_params &P, const mz_sp_plan &S, const float *src, std::vector<uint16_t> &image, std::vector<float> &bias) {
+    image.assign((size_t)S.image_bytes / 2 + 8, 0); bias.assign((size_t)S.bias_floats, 0.0f);
     for (int i = 0; i < P.n_layers; i++) {
         const mz_layer &l = P.layers[i];
-        auto W = [&](int n, int k) -> float { return (n < l.out && k < l.in) ? src[l.src_w_off + k * l.out + n] : 0.0f; };
-        for (int j = 0; j < M.nt[i]; j++) for (int s = 0; s < M.ks[i]; s++) for (int lane = 0; lane < 32; lane++) {
-            const int g = lane >> 2, t = lane & 3, n = 8 * j + g;
-            uint32_t *q = image.data() + (size_t)M.w_off[i] / 4 + ((size_t)(j * M.ks[i] + s) * 32 + lane) * 4;
-            for (int half = 0; half < 2; half++) {
-                const int k0 = 16 * s + 2 * t + 8 * half;
-                uint16_t hi[2], lo[2];
-                for (int e = 0; e < 2; e++) { const float w = W(n, k0 + e); hi[e] = f2bf16(w); lo[e] = f2bf16(w - bf16_to_f(hi[e])); }
-                q[half] = (uint32_t)hi[0] | ((uint32_t)hi[1] << 16);
-                q[2 + half] = (uint32_t)lo[0] | ((uint32_t)lo[1] << 16);
+        for (int o = 0; o < l.out; o++) {
+            for (int k = 0; k < l.in; k++) {
+                const float w = src[l.src_w_off + k * l.out + o];
+                const uint16_t hi = f2bf16(w), lo = f2bf16(w - bf16_to_f(hi));
+                image[(size_t)(S.w_off[i] + tc_tile_offset(o, k)) / 2] = hi;
+                image[(size_t)(S.w_off[i] + S.w_bytes[i] + tc_tile_offset(o, k)) / 2] = lo;
             }
+            bias[(size_t)i * 64 + o] = src[l.src_b_off + o];
         }
-        for (int o = 0; o < l.out; o++) bias[(size_t)i * 64 + o] = src[l.src_b_off + o];
     }
 }
 

@@ -24,7 +24,10 @@ for mode, label in ((capi.NN_FP32_EXACT, "fp32_exact"), (capi.NN_BF16_TC, "bf16_
         q = raw[o + 6]
         if q > 0:
             lab = ['issue', 'mbarrier wait', 'tcgen05.ld', 'epilogue', 'fence.proxy.async', 'group barrier']
-            if mode == capi.NN_SPLIT_MMA:      # per simulation of one dynamics warp (o = 12: trunk + state head, 20: trunk + reward head)
-                lab = ['wait for weights', 'load input', 'MMAs', 'epilogue', 'release slot + refill', '-']
+            if mode == capi.NN_SPLIT_MMA:      # epilogue threads only (the issuer is a warp of its own): wait for the MMAs, read, compute + store, fences, arrive
+                lab = ['mbarrier wait', 'tcgen05.ld', 'epilogue', 'fences', 'bar.arrive', '-']
             print('%s TC round (%s): %.0f cycles; ' % (label, who, raw[o:o + 6].sum() / q) + ', '.join('%s %.0f' % (lab[i], raw[o + i] / q) for i in range(6)))
+    if raw[53] > 0:   # kernel-level stamps of thread 0 (split-precision kernel)
+        ks = ['set-up', 'stage observations', 'representation', 'root prediction', 'root expansion + noise', 'simulation loop', 'move epilogue + teardown']
+        print('%s whole kernel (thread 0, mean cycles per launch): ' % label + ', '.join('%s %.0f' % (ks[i], raw[46 + i] / raw[53]) for i in range(7)) + '; slowest CTA of any launch %.0f vs mean %.0f' % (raw[54], raw[46:53].sum() / raw[53]))
     ctx.close()

@@ -1,5 +1,5 @@
-"""GPU tests of the split-precision tensor-core path (nn_mode = MZ_NN_SPLIT_MMA, mz_kernels_mma.cuh): bf16 hi + lo operands on
-warp-level MMAs, fp32 accumulation.  Not bit-exact by construction (the tensor core sums in its own order); what is asserted:
+"""GPU tests of the split-precision tensor-core path (nn_mode = MZ_NN_SPLIT_MMA, mz_kernels_sp.cuh): bf16 hi + lo operands on
+tcgen05.mma, fp32 accumulation in TMEM.  Not bit-exact by construction (the tensor core sums in its own order); what is asserted:
 network outputs within 2e-5 of the Float32 oracle, visit counts identical to the FLOAT32 oracle on >= 99 % of 1024 roots, the same
 most-visited action on >= 99.9 %, and everything that does not depend on network arithmetic (histories' structure, temperature rule,
 slot-count independence) exactly."""
@@ -75,7 +75,9 @@ def test_mma_run_mcts_agrees_with_float32_oracle(capi, eps):
           "max prior error %.2e" % (n, S, eps, same, best, perr))
     assert same >= 0.99 and best >= 0.999 and perr <= 1e-5
     ident = [i for i in range(n) if vc[i].tolist() == exact[i][0].tolist()]
-    assert np.max(np.abs(rv[ident] - np.array([exact[i][1] for i in ident]))) <= 1e-4
+    # identical root visit counts do not imply identical subtrees: a different path below the root moves the root value by O(1 / S)
+    rerr = np.abs(rv[ident] - np.array([exact[i][1] for i in ident]))
+    assert np.median(rerr) <= 1e-5 and np.max(rerr) <= 0.05
     ctx.close()
 
 
