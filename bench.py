@@ -45,9 +45,10 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-learner", action="store_true")
-    ap.add_argument("--nn", default="fp32", choices=["fp32", "tc"],
-                    help="network arithmetic of the headline number: fp32 = exact (bit-identical to the oracle), tc = bf16 tcgen05")
-    ap.add_argument("--no-tc-extra", action="store_true", help="skip the additional tensor-core measurement in fp32 mode")
+    ap.add_argument("--nn", default="split", choices=["split", "fp32", "tc"],
+                    help="network arithmetic of the headline number: split = tcgen05 with bf16 hi+lo operands (near-Float32: visit counts identical to the "
+                         "Float32 oracle on > 99 %% of roots), fp32 = exact SIMT (bit-identical to the oracle), tc = plain bf16 tcgen05")
+    ap.add_argument("--no-tc-extra", action="store_true", help="skip the additional measurements of the other network modes")
     ap.add_argument("--no-resnet-extra", action="store_true", help="skip the additional ResNet measurement (BASELINE.json configs[2]: 16384 games, bf16)")
     ap.add_argument("--resnet-games", type=int, default=16384)
     ap.add_argument("--no-connect-extra", action="store_true", help="skip the additional Connect measurement (BASELINE.json configs[3]: 6x7 board, 7 actions, ResNet, 200 simulations/move)")
@@ -233,7 +234,9 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     G, S = a.games, a.sims
-    nn_mode = capi.NN_BF16_TC if a.nn == "tc" else capi.NN_FP32_EXACT
+    MODES = {"split": (capi.NN_SPLIT_MMA, "split_bf16x2_tcgen05", "mz_k_search_sp", "bf16 hi+lo (tcgen05), f32 accumulate"),
+             "fp32": (capi.NN_FP32_EXACT, "fp32_exact", "mz_k_search", "f32"), "tc": (capi.NN_BF16_TC, "bf16_tcgen05", "mz_k_search_tc", "bf16")}
+    nn_mode, nn_name, nn_kernel, nn_dtype = MODES[a.nn]
     cfg = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=nn_mode)
     stream = torch.cuda.Stream()
     ctx = capi.Context(cfg, device=local, stream=stream.cuda_stream)
@@ -279,19 +282,30 @@ def run_b200(a):
         clocks = sampler.stop()
         stats = ctx.search_stats()
         # ---- parity of what was just timed: every GameHistory of the last timed wave against the oracle (outside the timed region) ----
+        def compare_with_oracle(c_, last_first_game):
+            """Every GameHistory of the wave that started at `last_first_game` against the Float32 oracle."""
+            from oracle import oracle as O
+            info = c_.replay_info()
+            h = c_.history_export(key0=info["first_key"] + info["n_games"] - G, n=G)
+            o = O.self_play(ocfg, blob, last_first_game, G, 1.0, max(1, (os.cpu_count() or 1) // max(1, world)))
+            bad = same_first = same_game = 0
+            rv_err = 0.0
+            discrete = [k for k in common.HIST_KEYS if k != "root_values"]      # everything but the Float32 root values: plies, actions, visit distributions, rewards, players
+            for j in range(G):
+                i = int(h["game_id"][j]) - last_first_game
+                ok = 0 <= i < G
+                bad += int(not (ok and all(np.array_equal(h[k][j], o[k][i]) for k in common.HIST_KEYS)))
+                same_first += int(ok and np.array_equal(h["child_visits"][j, 0], o["child_visits"][i, 0]))
+                if ok and all(np.array_equal(h[k][j], o[k][i]) for k in discrete):
+                    same_game += 1
+                    rv_err = max(rv_err, float(np.max(np.abs(h["root_values"][j] - o["root_values"][i]))))
+            return {"games": G, "mismatches": bad, "games_with_a_different_move_or_visit_count": G - same_game, "first_ply_visit_counts_identical": same_first / G,
+                    "whole_game_identical": same_game / G, "max_root_value_error_of_identical_games": rv_err, "oracle_simulations": int(o["sims"])}
+
         parity = None
         if not a.no_parity_check:
-            from oracle import oracle as O
-            info = ctx.replay_info()
-            h = ctx.history_export(key0=info["first_key"] + info["n_games"] - G, n=G)
-            fg = game_base + (a.warmup + a.steps - 1) * G
-            o = O.self_play(ocfg, blob, fg, G, 1.0, max(1, (os.cpu_count() or 1) // max(1, world)))
-            bad = 0
-            for j in range(G):
-                i = int(h["game_id"][j]) - fg
-                if not (0 <= i < G) or not all(np.array_equal(h[k][j], o[k][i]) for k in common.HIST_KEYS):
-                    bad += 1
-            parity = (G, bad, int(s == o["sims"]))
+            parity = compare_with_oracle(ctx, game_base + (a.warmup + a.steps - 1) * G)
+            parity["simulation_count_equal"] = bool(s == parity.pop("oracle_simulations"))
         # ---- end-to-end region: host weights in, GameHistory out, every step ----
         e2e_ms, e2e_sims, d2h = 0.0, 0, 0
         wave(a.warmup + 2 * a.steps, e2e=True)                              # untimed: first use of the export path allocates its device staging buffers
@@ -304,39 +318,33 @@ def run_b200(a):
             e2e_ms += e0.elapsed_time(e1); e2e_sims += s
             d2h = sum(v.nbytes for v in hist.values())
         barrier()
-        # ---- the same waves with the networks on the tcgen05 tensor cores (bf16 operands): reported beside the headline ----
-        tc_extra = None
-        if a.nn == "fp32" and not a.no_tc_extra:
-            cfg_tc = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=capi.NN_BF16_TC)
-            ctx_tc = capi.Context(cfg_tc, device=local, stream=stream.cuda_stream)
-            ctx_tc.set_weights(blob)
-            for i in range(a.warmup):
-                ctx_tc.self_play(game_base + i * G, G, 1.0)
-            tms, tsims = 0.0, 0
-            ctx_tc.kernel_time_reset(True)
-            for i in range(a.steps):
-                flush.zero_(); torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                s_, _ = ctx_tc.self_play(game_base + (a.warmup + i) * G, G, 1.0)
-                e1.record(stream); e1.synchronize()
-                tms += e0.elapsed_time(e1); tsims += s_
-            tk_ms, tk_n = ctx_tc.kernel_time(0)
-            tc_agree = None
-            if not a.no_parity_check:                                       # agreement of the tensor-core games with the Float32 oracle
-                from oracle import oracle as O
-                info = ctx_tc.replay_info()
-                h = ctx_tc.history_export(key0=info["first_key"] + info["n_games"] - G, n=G)
-                fg = game_base + (a.warmup + a.steps - 1) * G
-                o = O.self_play(ocfg, blob, fg, G, 1.0, max(1, (os.cpu_count() or 1) // max(1, world)))
-                same_game = same_first = 0
-                for j in range(G):
-                    i = int(h["game_id"][j]) - fg
-                    same_first += int(np.array_equal(h["child_visits"][j, 0], o["child_visits"][i, 0]))
-                    same_game += int(all(np.array_equal(h[k][j], o[k][i]) for k in ("T", "actions", "child_visits")))
-                tc_agree = (same_first / G, same_game / G)
-            tc_extra = (tms, tsims, tk_ms, tk_n, tc_agree)
-            ctx_tc.close()
+        # ---- the same waves in the other network modes, reported beside the headline ----
+        mode_extra = {}
+        if not a.no_tc_extra:
+            for key in ("fp32", "tc", "split"):
+                if key == a.nn:
+                    continue
+                cfg_x = capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=MODES[key][0])
+                ctx_x = capi.Context(cfg_x, device=local, stream=stream.cuda_stream)
+                ctx_x.set_weights(blob)
+                for i in range(a.warmup):
+                    ctx_x.self_play(game_base + i * G, G, 1.0)
+                tms, tsims = 0.0, 0
+                ctx_x.kernel_time_reset(True)
+                for i in range(a.steps):
+                    flush.zero_(); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    s_, _ = ctx_x.self_play(game_base + (a.warmup + i) * G, G, 1.0)
+                    e1.record(stream); e1.synchronize()
+                    tms += e0.elapsed_time(e1); tsims += s_
+                tk_ms, tk_n = ctx_x.kernel_time(0)
+                agree = None
+                if not a.no_parity_check:
+                    agree = compare_with_oracle(ctx_x, game_base + (a.warmup + a.steps - 1) * G)
+                    agree["simulation_count_equal"] = bool(s_ == agree.pop("oracle_simulations"))
+                mode_extra[key] = (tms, tsims, tk_ms, tk_n, agree)
+                ctx_x.close()
         barrier()
         # ---- BASELINE.json configs[2]: TicTacToe ResNet, 16384 concurrent games, bf16 inference on tcgen05 (reported beside the headline) ----
         rn_extra = None
@@ -455,12 +463,15 @@ def run_b200(a):
                     learner["large_batch"]["reference_l2"] = entry
             big.close()
 
-    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), tc_extra[0] if tc_extra else 0.0, rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([sims_total, e2e_sims, launches, tc_extra[1] if tc_extra else 0, rn_extra[1] if rn_extra else 0, strong[1] if strong else 0], dtype=torch.float64, device="cuda")
+    xk = [k for k in ("fp32", "tc", "split") if k in mode_extra]
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0] + [mode_extra[k][0] for k in xk], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches, rn_extra[1] if rn_extra else 0, strong[1] if strong else 0] + [mode_extra[k][1] for k in xk], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, learn_ms_max, tc_ms_max, rn_ms_max, strong_ms_max = [float(x) for x in t.cpu()]
-    sims_all, e2e_sims_all, launches_all, tc_sims_all, rn_sims_all, strong_sims_all = [float(x) for x in cnt.cpu()]
+    tl, cl = [float(x) for x in t.cpu()], [float(x) for x in cnt.cpu()]
+    ms_max, e2e_ms_max, learn_ms_max, rn_ms_max, strong_ms_max = tl[:5]
+    sims_all, e2e_sims_all, launches_all, rn_sims_all, strong_sims_all = cl[:5]
+    x_ms_max = {k: tl[5 + i] for i, k in enumerate(xk)}; x_sims_all = {k: cl[5 + i] for i, k in enumerate(xk)}
 
     if rank == 0:
         peaks = {}
@@ -474,31 +485,48 @@ def run_b200(a):
         sims_per_launch = sims_total / max(k_n, 1)
         avg_launch_s = (k_ms / max(k_n, 1)) * 1e-3
         achieved = bytes_per_sim * sims_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
-        traffic = profiled_traffic("mz_k_search_tc" if a.nn == "tc" else "mz_k_search<")
+        traffic = profiled_traffic(nn_kernel + "<")
+        bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        NN_FLOPS = 111232                                                    # useful (unpadded, unsplit) network FLOPs per simulation: prediction + dynamics
+        tflops = NN_FLOPS * sims_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+        hbm = {"formula": "SURVEY 8d", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+               "algorithmic_bytes_per_simulation": bytes_per_sim, "algorithmic_bytes_per_launch": bytes_per_sim * sims_per_launch,
+               "note": "node pools are L2-resident (65 MB < 126 MB L2), so HBM is not the binding resource; see DESIGN.md section 4"}
+        if a.nn == "fp32":
+            roof = {"bound": "latency (L2-resident)", "hbm_bound_formula": "SURVEY 8d", "kernel": nn_kernel + "<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes_per_launch": bytes_per_sim * sims_per_launch,
+                    "algorithmic_bytes_per_simulation": bytes_per_sim, "note": hbm["note"], "nn_flops_per_simulation": NN_FLOPS, "nn_tflops_achieved": tflops}
+        else:
+            roof = {"bound": "tensor", "kernel": nn_kernel + "<MODE_SLOTS>", "achieved": tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tflops / bf16_peak,
+                    "algorithmic_flops_per_simulation": NN_FLOPS, "algorithmic_flops_per_launch": NN_FLOPS * sims_per_launch,
+                    "executed_tensor_flops_per_simulation": (3 if a.nn == "split" else 1) * 2 * (64 * 64 * 32 * 4) * (14 + 6) / 32,
+                    "note": "useful network FLOPs only (the hi / lo split executes three bf16 products per useful one, and every layer as an M=64 x N=32 x K=64 tile); "
+                            "a simulation is a dependent chain of 8 layer rounds between two tree phases, so the kernel is latency-bound: "
+                            "throughput = concurrent trees / chain latency (DESIGN.md section 4)",
+                    "hbm": hbm}
+        roof.update({"traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
+                     "simulations_per_launch": sims_per_launch, "avg_launch_ms": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms if ms > 0 else None})
+        if parity and a.nn != "fp32":
+            parity["mismatches_note"] = "`mismatches` counts games that differ in ANY field, including the Float32 root values, which a tensor-core sum order always moves by ~1e-7"
+        if parity:
+            parity["what"] = ("every GameHistory of the last timed wave (rank 0) vs the CPU oracle in Float32 (oracle/mz_oracle.c, a restatement of the reference: parity "
+                              "unpinned against Julia); " + ("bit-exact path: mismatches must be 0" if a.nn == "fp32" else
+                                                           "tensor-core path: not bit-exact by construction, the agreement rates are the result"))
         out = {
             "metric": METRIC, "value": sims_all / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if a.nn == "tc" else "f32", "data": "synthetic",
+            "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": nn_dtype, "data": "synthetic",
             "config": {"workload": workload_name(a), "games_per_gpu": G, "simulations_per_move": S,
-                       "nn_mode": "bf16_tcgen05" if a.nn == "tc" else "fp32_exact", "parallelism": "dp%d" % world,
+                       "nn_mode": nn_name, "parallelism": "dp%d" % world,
                        "l2": "L2 flushed (384 MiB memset) between timed iterations", "mean_legal_actions": Lm, "mean_select_depth": d,
                        "moves_per_step": moves_total / a.steps},
             "e2e": {"value": e2e_sims_all / (e2e_ms_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(blob.nbytes), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
-            "parity_checked": ({"games": parity[0], "mismatches": parity[1], "simulation_count_equal": bool(parity[2]),
-                                "what": "every GameHistory of the last timed wave (rank 0) vs the CPU oracle (oracle/mz_oracle.c, a restatement of the reference: parity unpinned against Julia)"}
-                               if parity else None),
+            "parity_checked": parity,
             "single_root_latency_ms": single_root_ms,
-            "roofline": {"bound": "latency (L2-resident)" if a.nn != "tc" else "tensor", "hbm_bound_formula": "SURVEY 8d", "kernel": "mz_k_search_tc<MODE_SLOTS>" if a.nn == "tc" else "mz_k_search<MODE_SLOTS>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic["bytes"] if traffic else None,
-                         "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_sim * sims_per_launch,
-                         "note": "node pools are L2-resident (65 MB < 126 MB L2), so the kernel is latency-bound, not HBM-bound; see DESIGN.md section 4",
-                         "algorithmic_bytes_per_simulation": bytes_per_sim, "simulations_per_launch": sims_per_launch,
-                         "avg_launch_ms": k_ms / max(k_n, 1), "kernel_share_of_step": k_ms / ms if ms > 0 else None,
-                         "nn_flops_per_simulation": 111232, "nn_tflops_achieved": 111232 * sims_per_launch / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0},
+            "roofline": roof,
         }
-        if a.nn != "tc" and avg_launch_s > 0 and clocks.get("sm_mhz"):
+        if a.nn == "fp32" and avg_launch_s > 0 and clocks.get("sm_mhz"):
             # the resource the exact network phase actually saturates: shared-memory wavefronts (one per clock per SM).  A 4x4 register tile
             # issues two 128-bit shared loads (4 wavefronts each) per 8 packed FMAs: 64 wavefront-cycles against 32 FMA-pipe cycles per k step
             # for the 8 warps of a CTA; ncu counts 830 wavefronts per simulation over the whole kernel.
@@ -513,22 +541,20 @@ def run_b200(a):
                                      "games_total": strong[2] * world, "games_per_gpu": strong[2],
                                      "note": "the 1-GPU workload split over the ranks (fixed total games); a move of the exact path is a latency chain "
                                              "whose length does not depend on the number of trees per SM, so strong scaling is flat by construction"}
-        if tc_extra:
-            bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            tc_launch_s = (tc_extra[2] / max(tc_extra[3], 1)) * 1e-3
-            tc_tflops = 111232 * (tc_extra[1] / max(tc_extra[3], 1)) / tc_launch_s / 1e12 if tc_launch_s > 0 else 0.0
-            out["tensor_core"] = {"value": tc_sims_all / (tc_ms_max * 1e-3), "unit": UNIT, "ms_per_step": tc_ms_max / a.steps, "dtype": "bf16",
-                                  "kernel": "mz_k_search_tc<MODE_SLOTS>", "avg_launch_ms": tc_extra[2] / max(tc_extra[3], 1),
-                                  "roofline": {"bound": "tensor", "achieved": tc_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tc_tflops / bf16_peak,
-                                               "note": "useful (unpadded) network FLOPs only; M=64 x N=32 x K<=64 MMAs in a 8-round dependent chain are latency-bound"},
-                                  "agreement_with_float32_oracle": ({"first_ply_visit_counts_identical": tc_extra[4][0], "whole_game_identical": tc_extra[4][1], "games": G}
-                                                                    if tc_extra[4] else None),
-                                  "note": "same waves with the networks on tcgen05 (fp32 accumulate); results agree with the Float32 "
-                                          "oracle at the stated rate, not bit-exactly, so the headline value is the exact-fp32 path"}
+        for key in xk:
+            tms_, tsims_, tk_ms_, tk_n_, agree_ = mode_extra[key]
+            x_launch_s = (tk_ms_ / max(tk_n_, 1)) * 1e-3
+            x_tflops = NN_FLOPS * (tsims_ / max(tk_n_, 1)) / x_launch_s / 1e12 if x_launch_s > 0 else 0.0
+            out[{"fp32": "exact_fp32", "tc": "bf16_tensor_core", "split": "split_tensor_core"}[key]] = {
+                "value": x_sims_all[key] / (x_ms_max[key] * 1e-3), "unit": UNIT, "ms_per_step": x_ms_max[key] / a.steps, "dtype": MODES[key][3],
+                "nn_mode": MODES[key][1], "kernel": MODES[key][2] + "<MODE_SLOTS>", "avg_launch_ms": tk_ms_ / max(tk_n_, 1), "nn_tflops_achieved": x_tflops,
+                "parity_checked": agree_,
+                "note": {"fp32": "the same waves with the networks in exact fp32 on the CUDA cores: bit-identical to the Float32 oracle (mismatches 0)",
+                         "tc": "the same waves with plain bf16 operands on tcgen05: fastest, but the games differ from the Float32 oracle's",
+                         "split": "the same waves with bf16 hi+lo operands on tcgen05"}[key]}
         if rn_extra:
             # useful network MACs per simulation, nf = 64, 2 blocks, hs = 64, depth_value = 1 (DESIGN.md "ResNet"): prediction 196,608 + dynamics 374,528;
             # + per move (1/S of it per simulation): representation 3x3 tower (in-bounds taps only) 824,768 + prediction 196,608
-            bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             flops_per_sim = 2 * (196608 + 374528) + 2 * (824768 + 196608) / S
             rn_launch_s = (rn_extra[2] / max(rn_extra[3], 1)) * 1e-3
             rn_tflops = flops_per_sim * (rn_extra[1] / max(rn_extra[3], 1)) / rn_launch_s / 1e12 if rn_launch_s > 0 else 0.0
@@ -543,7 +569,6 @@ def run_b200(a):
                                           "note": "useful FLOPs only; K = 64 per layer: each warpgroup's step is a dependent chain (MMA issue -> commit -> tcgen05.ld -> "
                                                   "epilogue -> barrier, ~4 k cycles) and shared memory allows four chains per SM; see DESIGN.md 2.4"}}
         if cn_extra:
-            bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
             # useful network MACs per simulation on the 6x7 board (42 cells): the 1x1 towers scale with the cells, the dense heads do not
             cells = 42
             tower = lambda cin, cout: cells * cin * cout

@@ -387,7 +387,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
         mzh::build_sp_plan(P, (size_t)prop.sharedMemPerBlockOptin, c->spp);
         if (c->spp.ok) {
             const mz_sp_plan &S = c->spp;
-            c->smem_bytes_sp = mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S);
+            c->smem_bytes_sp = mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S, S.pbc_smem);
             MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_API>, prop));
             MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_SLOTS>, prop));
             MZ_CREATE(allow_max_smem(mz_k_nn_forward_sp, prop));
@@ -398,7 +398,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
             mz_sp_args &A = c->spa;
             A.image = c->d_w_sp; A.bias = c->d_bias_sp; A.rounds = c->d_rounds_sp;
             for (int n = 0; n < 3; n++) { A.first[n] = S.first[n]; A.n_rounds[n] = S.n_rounds[n]; A.set_first[n] = S.set_first[n]; A.n_sets[n] = S.n_sets[n]; }
-            A.total_rounds = S.total_rounds; A.total_sets = S.total_sets; A.warea_bytes = S.warea_bytes; A.bias_floats = S.bias_floats;
+            A.total_rounds = S.total_rounds; A.total_sets = S.total_sets; A.warea_bytes = S.warea_bytes; A.bias_floats = S.bias_floats; A.pbc_smem = S.pbc_smem;
         } else if (cfg->nn_mode == MZ_NN_SPLIT_MMA) {
             int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA: the networks do not fit the shared memory of this device (%zu B per CTA)", (size_t)prop.sharedMemPerBlockOptin);
             mz_destroy(c); return r;

@@ -202,7 +202,7 @@ struct mz_sp_plan {
     int32_t first[3], n_rounds[3];                  // per network (representation, prediction, dynamics): rounds [first, first + n)
     int32_t set_first[3], n_sets[3];                // per network: its weight sets (the representation has one, loaded once, over the dynamics area)
     int32_t total_rounds, total_sets;
-    int32_t image_bytes, warea_bytes, bias_floats, divisor, ok;
+    int32_t image_bytes, warea_bytes, bias_floats, divisor, ok, pbc_smem;
     int32_t out_off[4];                             // float offsets of value / logits / reward / hidden outputs in the output area
     int32_t w_off[MZ_MAX_LAYERS], w_bytes[MZ_MAX_LAYERS];   // image: hi block at w_off, lo block at w_off + w_bytes
     mz_sp_round round[MZ_SP_MAX_ROUNDS];
@@ -211,11 +211,12 @@ struct mz_sp_plan {
 #define MZ_SP_RDESC_BYTES 128                       // sizeof(mz_sp_rdesc), the device form of a round (mz_sp.cuh)
 #define MZ_SP_CTRL_BYTES 1024                       // mbarriers, TMEM slot, per-set use counters
 // dynamic shared memory of a kernel on this path (the carve-up is mz_sp_carve in mz_sp.cuh)
-MZ_HD size_t mz_sp_smem_bytes(int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S) {
+// pbc_smem: the kernel keeps a compact copy of ucb_score's Float64 table (rows N = 0..S+1, entries n = 0..N) in shared memory
+MZ_HD size_t mz_sp_smem_bytes(int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S, int pbc_smem) {
     size_t tiles = (size_t)2 * MZ_SP_TILES_PER_GROUP * 2 * MZ_SP_TILE_BYTES;
     size_t bias = ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
     size_t out = (size_t)(24 + hidden_pad) * 32 * 4;
-    size_t tab = (((size_t)S + 2) * 16 + 127) & ~(size_t)127;
+    size_t tab = pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     size_t path = (((size_t)S + 2) * 2 * 32 + 127) & ~(size_t)127;
     size_t prog = ((size_t)total_rounds * MZ_SP_RDESC_BYTES + 127) & ~(size_t)127;
     return 1024 + (size_t)warea_bytes + tiles + MZ_SP_CTRL_BYTES + bias + out + tab + path + prog;
@@ -414,10 +415,10 @@ struct mz_minmax { float mn, mx; };
 // (pbc0[N] = log2((N+base+1)/base) + init, sqrtN[N] = sqrt(N)), Float32 value term, Float32 result.
 // `pbc` is the host-built table pbc[N * (S + 2) + n] = pbc0[N] * (sqrtN[N] / (double)(n + 1)): the same IEEE double operations in
 // the same order, evaluated once on the host -- the device does no Float64 division (slow on this part) in the selection loop.
-MZ_HD float mz_ucb(const mz_params &P, const double *pbc, const double *unused_, int N, mz_f4 child, mz_minmax mm) {
-    (void)unused_;
+// `row` = the table row of the parent's visit count N (pbc + N * (S + 2), or the kernel's own compact copy of it)
+MZ_HD float mz_ucb_row(const mz_params &P, const double *row, mz_f4 child, mz_minmax mm) {
     int n = mz_nx_visit(mz_f2bits(child.x));
-    double pb_c = pbc[N * (P.S + 2) + n];
+    double pb_c = row[n];
     double prior_score = pb_c * (double)child.z;
     if (n > 0) {
         float nv = child.y / (float)n;                                    // node_value :76-82
@@ -426,6 +427,10 @@ MZ_HD float mz_ucb(const mz_params &P, const double *pbc, const double *unused_,
         return (float)(prior_score + (double)vs);
     }
     return (float)(prior_score + 0.0);
+}
+MZ_HD float mz_ucb(const mz_params &P, const double *pbc, const double *unused_, int N, mz_f4 child, mz_minmax mm) {
+    (void)unused_;
+    return mz_ucb_row(P, pbc + N * (P.S + 2), child, mm);
 }
 
 // leaf of a selection: node indices, the leaf's prior (its record is rebuilt by expand), the parent's packed x word

@@ -380,7 +380,8 @@ inline void build_sp_plan(const mz_params &P, size_t smem_limit, mz_sp_plan &S) 
         const int rb = sp_place_linear(S, 0, pb, np + nd);      // over the dynamics area: the representation runs before the first dynamics pass
         S.total_sets = np + nd + 1; S.divisor = d;
         S.warea_bytes = pb + (db > rb ? db : rb);
-        if (mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S) <= smem_limit) return;
+        for (S.pbc_smem = 1; S.pbc_smem >= 0; S.pbc_smem--)
+            if (mz_sp_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, P.hidden_pad, P.S, S.pbc_smem) <= smem_limit) return;
     }
     S.ok = 0;
 }

@@ -87,7 +87,7 @@ __device__ __forceinline__ int mz_seg_add(int v, uint32_t segmask) {
 // prior come by shuffle from the lane that loaded its record to score it.
 __device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, const mz_tree &t, const double *pbc0, const double *sqrtN, uint32_t legal,
                                                         uint32_t posmask, mz_minmax mm, uint32_t game, uint32_t move, uint32_t sim, int ln,
-                                                        uint32_t segmask, uint16_t *path) {
+                                                        uint32_t segmask, uint16_t *path, bool tri = false) {
     mz_leaf L; L.node = 0; L.parent = 0; L.action = 0; L.depth = 0; L.prior = 0.0f; L.parent_x = 0;
     const int a0 = ln < P.A ? P.order[ln] : 1, a1 = ln + 8 < P.A ? P.order[ln + 8] : 1;
     const bool ok0 = (posmask >> ln) & 1u, ok1 = (posmask >> (ln + 8)) & 1u;
@@ -101,8 +101,10 @@ __device__ __forceinline__ mz_leaf mz_tree_select_lanes(const mz_params &P, cons
         if (ok0) c0 = t.A[base + a0 - 1];
         if (ok1) c1 = t.A[base + a1 - 1];
         float s0 = 0.0f, s1 = 0.0f;
-        if (ok0) s0 = mz_ucb(P, pbc0, sqrtN, N, c0, mm);
-        if (ok1) s1 = mz_ucb(P, pbc0, sqrtN, N, c1, mm);
+        // tri: pbc0 is a compact (triangular) copy of the table: a child has at most as many visits as its parent, so row N holds n = 0..N
+        const double *row = pbc0 + (tri ? (N * (N + 1)) / 2 : N * (P.S + 2));
+        if (ok0) s0 = mz_ucb_row(P, row, c0, mm);
+        if (ok1) s1 = mz_ucb_row(P, row, c1, mm);
         float b = ok0 ? s0 : -INFINITY;
         if (ok1) b = s1 > b ? s1 : b;
         const float best = mz_seg_max(b, segmask);
@@ -164,7 +166,7 @@ __device__ __forceinline__ void mz_tree_backup_lanes(const mz_params &P, const m
             const uint32_t x = __shfl_sync(segmask, mz_f2bits(rec.x), u, MZ_LANES) + 1u;     // visit_count += 1
             const float y = __shfl_sync(segmask, rec.y, u, MZ_LANES), w = __shfl_sync(segmask, rec.w, u, MZ_LANES);
             const int j = depth - (top - u);
-            const bool same = (P.P == 1) || ((j % P.P) == 0);
+            const bool same = (P.P == 1) || ((j & 1) == 0);       // j % P, P <= 2
             const float ny = same ? y + value : y - value;
             const int vc = mz_nx_visit(x);
             const float upd = w + P.discount * (ny / (float)vc);

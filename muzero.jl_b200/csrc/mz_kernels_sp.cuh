@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
     const mz_search_args &a = sa.base;
     const mz_sp_args &A = sa.sp;
     if (mz_cta_idle<MODE>(P, a, MZ_ROWS)) return;
-    const mz_sp_plan_s sp = mz_sp_carve(mz_smem_sp, A.warea_bytes, A.bias_floats, A.total_rounds, P.hidden_pad, P.S);
+    const mz_sp_plan_s sp = mz_sp_carve(mz_smem_sp, A.warea_bytes, A.bias_floats, A.total_rounds, P.hidden_pad, P.S, A.pbc_smem);
     const int tid = threadIdx.x;
     const int r = tid >> 3, ln = tid & (MZ_LANES - 1);
     const uint32_t segmask = 0xffu << ((tid & 31) & ~7);
@@ -67,6 +67,11 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
     const uint32_t tmem_base = mz_sp_setup(sp, A, MZ_SP_THREADS);
     MZ_KSTAMP(0);
     mz_sp_ctx C; C.prog = mz_smem_u32(sp.prog); C.image = A.image; C.bars = mz_smem_u32(sp.bars);
+    const double *pbc = a.pbc0;
+    if (A.pbc_smem) {                                                   // compact copy of ucb_score's table: row N holds n = 0..N
+        for (int N = tid; N < P.S + 2; N += MZ_SP_THREADS) for (int n = 0; n <= N; n++) sp.pbc[(N * (N + 1)) / 2 + n] = a.pbc0[N * (P.S + 2) + n];
+        pbc = sp.pbc;
+    }
     const bool worker = tid < MZ_THREADS;                               // warps 0..7: tree phases + epilogues; warp 8 / 9: issuer of group 0 / 1
     const int grp = worker ? tid >> 7 : (tid - MZ_THREADS) >> 5, gtid = tid & (MZ_GROUP - 1);
     const bool issuer0 = !worker && (tid & 31) == 0;                    // lane 0 of an issuer warp: one-off TMA work
@@ -166,16 +171,23 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
         mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
         MZ_TIMER(0);
         if (active) {
-            leaf = mz_tree_select_lanes(P, tree, a.pbc0, a.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path);
+            leaf = mz_tree_select_lanes(P, tree, pbc, a.sqrtN, legal, posmask, mm, game, move, (uint32_t)sim, ln, segmask, path, A.pbc_smem != 0);
             depth_sum += (unsigned long long)leaf.depth;
             MZ_TIMER(1);
             const int pe = mz_nx_exp(leaf.parent_x), dbl = mz_nx_dbl(leaf.parent_x);
             const float *h = tree.hidden + (size_t)pe * P.hidden_pad;
             const float sc = mz_bits2f((uint32_t)(127 + dbl) << 23);
-            for (int k = ln; k < P.hidden; k += MZ_LANES) {
-                const float v = h[k] * sc;
-                mz_sp_stage(in_pred, k, r, v);                     // prediction(parent.hidden_state) (Q5)
-                mz_sp_stage(in_dyn, k, r, v * 2.0f);               // make_state_action: state .*= 2 (Q6)
+            float hv[8];                                           // all loads first: the staging stores are volatile asm, loads do not move across them
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const int k = ln + MZ_LANES * i; hv[i] = k < P.hidden ? h[k] : 0.0f; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int k = ln + MZ_LANES * i;
+                if (k < P.hidden) {
+                    const float v = hv[i] * sc;
+                    mz_sp_stage(in_pred, k, r, v);                 // prediction(parent.hidden_state) (Q5)
+                    mz_sp_stage(in_dyn, k, r, v * 2.0f);           // make_state_action: state .*= 2 (Q6)
+                }
             }
             const float plane = P.act_plane_play[leaf.action];
             for (int k = P.obs_size + ln; k < P.sa_size; k += MZ_LANES) mz_sp_stage(in_dyn, k, r, plane);
@@ -199,10 +211,15 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
             for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
             MZ_TIMER(6);
-            const float rw = sp.outR[r], vl = sp.outV[r];
-            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, tanh_r ? mz_tanhf(rw) : rw, leaf.prior, ln, segmask);
+            float rw = sp.outR[r], vl = sp.outV[r];
+            if (tanh_r || tanh_v) {                                // both tanh side by side: even lanes the value, odd lanes the reward
+                float x = (ln & 1) ? rw : vl;
+                if ((ln & 1) ? tanh_r : tanh_v) x = mz_tanhf(x);
+                vl = __shfl_sync(segmask, x, 0, MZ_LANES); rw = __shfl_sync(segmask, x, 1, MZ_LANES);
+            }
+            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, rw, leaf.prior, ln, segmask);
             MZ_TIMER(7);
-            mz_tree_backup_lanes(P, tree, path, leaf.depth, tanh_v ? mz_tanhf(vl) : vl, mm, ln, segmask);
+            mz_tree_backup_lanes(P, tree, path, leaf.depth, vl, mm, ln, segmask);
         }
         MZ_TIMER(8);
     }
@@ -249,7 +266,7 @@ struct mz_nn_sp_args { mz_sp_args sp; int32_t B, net; const float *in; float *ou
 __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_nn_forward_sp(const __grid_constant__ mz_params P, const __grid_constant__ mz_nn_sp_args a) {
     extern __shared__ __align__(1024) unsigned char mz_smem_sp[];
     const mz_sp_args &A = a.sp;
-    const mz_sp_plan_s sp = mz_sp_carve(mz_smem_sp, A.warea_bytes, A.bias_floats, A.total_rounds, P.hidden_pad, P.S);
+    const mz_sp_plan_s sp = mz_sp_carve(mz_smem_sp, A.warea_bytes, A.bias_floats, A.total_rounds, P.hidden_pad, P.S, A.pbc_smem);
     const int tid = threadIdx.x;
     const uint32_t tmem_base = mz_sp_setup(sp, A, MZ_SP_THREADS);
     mz_sp_ctx C; C.prog = mz_smem_u32(sp.prog); C.image = A.image; C.bars = mz_smem_u32(sp.bars);

@@ -77,9 +77,9 @@ struct mz_sp_plan_s {                               // carve-up of the dynamic s
     unsigned char *tiles_ptr;
     uint64_t *bars;                                 // [MZ_SP_MAX_SETS] weight-set barriers
     uint64_t *mbar_mma[2]; uint32_t *tmem_slot;
-    float *bias, *outV, *outL, *outR, *outH; double *pbc0, *sqrtN; uint16_t *path; mz_sp_rdesc *prog;
+    float *bias, *outV, *outL, *outR, *outH; double *pbc; uint16_t *path; mz_sp_rdesc *prog;
 };
-__device__ __forceinline__ mz_sp_plan_s mz_sp_carve(unsigned char *raw, int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S) {
+__device__ __forceinline__ mz_sp_plan_s mz_sp_carve(unsigned char *raw, int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S, int pbc_smem) {
     mz_sp_plan_s p;
     const uint32_t a = mz_smem_u32(raw);
     unsigned char *c = raw + (((a + 1023u) & ~1023u) - a);              // swizzled tiles need 1024-byte alignment
@@ -89,7 +89,7 @@ __device__ __forceinline__ mz_sp_plan_s mz_sp_carve(unsigned char *raw, int ware
     c += MZ_SP_CTRL_BYTES;
     p.bias = (float *)c; c += ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
     p.outV = (float *)c; p.outL = p.outV + 4 * 32; p.outR = p.outV + 20 * 32; p.outH = p.outV + 24 * 32; c += (size_t)(24 + hidden_pad) * 32 * 4;
-    p.pbc0 = (double *)c; p.sqrtN = p.pbc0 + (S + 2); c += (((size_t)S + 2) * 16 + 127) & ~(size_t)127;
+    p.pbc = (double *)c; c += pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     p.path = (uint16_t *)c; c += (((size_t)S + 2) * 2 * 32 + 127) & ~(size_t)127;
     p.prog = (mz_sp_rdesc *)c;
     (void)total_rounds;
@@ -99,7 +99,7 @@ __device__ __forceinline__ mz_sp_plan_s mz_sp_carve(unsigned char *raw, int ware
 struct mz_sp_args {                                 // what a kernel on this path needs besides mz_params
     const unsigned char *image; const float *bias; const mz_sp_round *rounds;
     int32_t first[3], n_rounds[3], set_first[3], n_sets[3];
-    int32_t total_rounds, total_sets, warea_bytes, bias_floats;
+    int32_t total_rounds, total_sets, warea_bytes, bias_floats, pbc_smem;
 };
 
 // one-time set-up by all threads: barriers, TMEM, zeroed tiles, biases, the round table.  Ends with a CTA barrier.

@@ -3,7 +3,10 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from muzero_jl_b200 import capi
 G, S = int(os.environ.get("G", 4096)), int(os.environ.get("S", 50))
+ONLY = os.environ.get("MODES", "split_mma,bf16_tcgen05,fp32_exact").split(",")
 for mode, name in ((capi.NN_SPLIT_MMA, "split_mma"), (capi.NN_BF16_TC, "bf16_tcgen05"), (capi.NN_FP32_EXACT, "fp32_exact")):
+    if name not in ONLY:
+        continue
     ctx = capi.Context(capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G), nn_mode=mode)); ctx.init_weights(1337)
     ctx.self_play(0, G, 1.0)
     ctx.kernel_time_reset(True)
