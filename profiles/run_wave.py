@@ -1,5 +1,5 @@
 """Profiling driver: N self-play waves of G games x S simulations (what bench.py times), nothing else.
-env: G, S, N, NN (fp32 | tc | rn | cn)"""
+env: G, S, N, NN (fp32 | tc | sp | rn | cn)"""
 import os
 import sys
 
@@ -9,7 +9,7 @@ from muzero_jl_b200 import capi
 G = int(os.environ.get("G", 4096)); S = int(os.environ.get("S", 50)); N = int(os.environ.get("N", 2))
 import time
 nn = os.environ.get("NN", "fp32")
-mode = capi.NN_BF16_TC if nn == "tc" else capi.NN_FP32_EXACT
+mode = capi.NN_BF16_TC if nn == "tc" else capi.NN_SPLIT_MMA if nn == "sp" else capi.NN_FP32_EXACT
 if nn == "cn":     # 6x7 Connect game + ResNet (BASELINE.json configs[3]: 200 simulations per move)
     ctx = capi.Context(capi.connect_config(num_slots=G, num_iters=S, replay_buffer_size=max(10000, G)))
 elif nn == "rn":     # ResNet networks (BASELINE.json config 3: 16384 concurrent games, bf16 inference)
