@@ -64,6 +64,7 @@ struct mz_ctx {
     int exact_gt = 128;   // threads per network group of the exact search kernel: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps; measured no faster: the layer is bound by shared-memory wavefronts)
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     unsigned char *d_w_tc = nullptr; float *d_bias_tc = nullptr; size_t smem_bytes_tc = 0;   // tensor-core weight image
+    uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
     void *d_trees = nullptr;
@@ -181,20 +182,7 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
     std::vector<float> dev((size_t)c->M.P.total_floats);
     mzh::pack_weights(c->M.P, src.data(), dev.data());
     MZ_CUDA(c, cudaMemcpyAsync(c->d_w, dev.data(), dev.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    if (c->d_w_tc && c->cfg.nn_mode == MZ_NN_BF16_TC) {   // bf16 pre-swizzled A-operand image + fp32 biases for the tcgen05 path
-        std::vector<uint16_t> image; std::vector<float> bias;
-        mzh::pack_weights_tc(c->M.P, src.data(), image, bias);
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_w_tc, image.data(), image.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_tc, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
-    if (c->d_w_sp && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // bf16 hi / lo A-operand image + fp32 biases for the split-precision tensor-core path
-        std::vector<uint16_t> image; std::vector<float> bias;
-        mzh::pack_weights_sp(c->M.P, c->spp, src.data(), image, bias);
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_w_sp, image.data(), (size_t)c->spp.image_bytes, cudaMemcpyHostToDevice, c->stream));
-        MZ_CUDA(c, cudaMemcpyAsync(c->d_bias_sp, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
-    }
+    c->w_version++;                                      // the tensor-core images are rebuilt on the device before their next use (ensure_images)
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
@@ -239,6 +227,25 @@ template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
 }
 #define MZ_TRY(x) do { int r_ = (x); if (r_ != MZ_OK) return r_; } while (0)
 
+// The tensor-core paths read bf16 images of the weights; whenever d_w has changed (set_weights, an ADAM step) the image of the context's
+// nn_mode is rebuilt on the device before the next kernel that reads it.
+int ensure_images(mz_ctx *c) {
+    if (c->img_version == c->w_version || c->cfg.net_type != MZ_NET_FEEDFORWARD) return MZ_OK;
+    const mz_params &P = c->M.P;
+    mz_pack_args a{}; a.w = c->d_w;
+    if (c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->d_w_sp) {
+        a.mode = 2; a.image = c->d_w_sp; a.bias = c->d_bias_sp;
+        for (int i = 0; i < P.n_layers; i++) { a.off[i] = c->spp.w_off[i]; a.bytes[i] = c->spp.w_bytes[i]; a.bias_off[i] = i * 64; }
+    } else if (c->cfg.nn_mode == MZ_NN_BF16_TC && c->d_w_tc) {
+        a.mode = 1; a.image = c->d_w_tc; a.bias = c->d_bias_tc;
+        for (int i = 0; i < P.n_layers; i++) { a.off[i] = P.tc_a_off[i]; a.bytes[i] = 0; a.bias_off[i] = P.tc_bias_off[i]; }
+    } else { c->img_version = c->w_version; return MZ_OK; }
+    { launch_scope ls(c, 5); mz_k_pack_images<<<P.n_layers, 256, 0, c->stream>>>(P, a); }
+    MZ_CUDA(c, cudaGetLastError());
+    c->img_version = c->w_version;
+    return MZ_OK;
+}
+
 int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2) {
     const mz_params &P = c->M.P;
     if (c->cfg.net_type == MZ_NET_RESNET) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only (the ResNet path is self-play inference)");
@@ -258,6 +265,10 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         mz_bptt_args b{}; b.f = a; b.act = c->d_act; b.gpart = c->d_gpart; b.stages[0] = c->d_bstages[0]; b.stages[1] = c->d_bstages[1];
         { launch_scope ls(c, 3); mz_k_learn_bptt<<<tiles, MZ_THREADS, c->smem_bytes_bptt, c->stream>>>(P, c->bptt.plan, b); }
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, c->d_grad); }
+    } else if (grad_mode == MZ_GRAD_REFERENCE_L2 && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // the unroll on the tensor cores (mz_kernels_sp.cuh)
+        MZ_TRY(ensure_images(c));
+        mz_learn_sp_args t{}; t.sp = c->spa; t.B = B; t.batch = c->batch; t.pred_values = c->d_pv; t.pred_rewards = c->d_pr; t.pred_policies = c->d_pp;
+        launch_scope ls(c, 3); mz_k_learn_forward_sp<<<tiles, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t);
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2) {
         launch_scope ls(c, 3); mz_k_learn_forward<<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
     } else return fail(c, MZ_E_ARG, "unknown grad_mode %d", grad_mode);
@@ -296,6 +307,7 @@ int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
     { launch_scope ls(c, 4); mz_k_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_m, c->d_v, c->d_grad, mzh::cos_schedule(t), c->bp1, c->bp2, scale); }
     MZ_CUDA(c, cudaGetLastError());
     c->bp1 *= 0.9; c->bp2 *= 0.999; c->adam_t++;
+    c->w_version++;
     return MZ_OK;
 }
 
@@ -376,6 +388,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
             MZ_CREATE(allow_max_smem(mz_k_search_tc<MZ_MODE_SLOTS>, prop));
             MZ_CREATE(allow_max_smem(mz_k_nn_forward_tc, prop));
             MZ_CREATE(cudaMalloc((void **)&c->d_w_tc, (size_t)P.tc_net_off[3] + 8192));
+            MZ_CREATE(cudaMemset(c->d_w_tc, 0, (size_t)P.tc_net_off[3] + 8192));
             MZ_CREATE(dmalloc(&c->d_bias_tc, (size_t)P.tc_bias_floats));
         } else if (cfg->nn_mode == MZ_NN_BF16_TC) {
             int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs %zu B of shared memory per CTA, device allows %zu", c->smem_bytes_tc, (size_t)prop.sharedMemPerBlockOptin);
@@ -391,7 +404,9 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
             MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_API>, prop));
             MZ_CREATE(allow_max_smem(mz_k_search_sp<MZ_MODE_SLOTS>, prop));
             MZ_CREATE(allow_max_smem(mz_k_nn_forward_sp, prop));
+            MZ_CREATE(allow_max_smem(mz_k_learn_forward_sp, prop));
             MZ_CREATE(cudaMalloc((void **)&c->d_w_sp, (size_t)S.image_bytes + 256));
+            MZ_CREATE(cudaMemset(c->d_w_sp, 0, (size_t)S.image_bytes + 256));
             MZ_CREATE(dmalloc(&c->d_bias_sp, (size_t)S.bias_floats));
             MZ_CREATE(cudaMalloc((void **)&c->d_rounds_sp, sizeof(mz_sp_round) * MZ_SP_MAX_ROUNDS));
             MZ_CREATE(cudaMemcpy(c->d_rounds_sp, S.round, sizeof(mz_sp_round) * MZ_SP_MAX_ROUNDS, cudaMemcpyHostToDevice));
@@ -519,6 +534,7 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
     MZ_CHECK_CTX(c);
     if (B < 0 || (B > 0 && (!in || !out1))) return fail(c, MZ_E_ARG, "NULL buffer");
     if (B == 0) return MZ_OK;
+    MZ_TRY(ensure_images(c));
     const mz_params &P = c->M.P;
     const bool resnet = c->cfg.net_type == MZ_NET_RESNET;
     const int in_dim = resnet ? (net == 0 ? P.stack_size : net == 1 ? P.hidden : P.sa_size) : P.layers[P.nets[net].first].in;
@@ -623,6 +639,7 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
     read_counters(c);
     if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
     const int cap = c->cfg.num_slots;
+    MZ_TRY(ensure_images(c));
     for (int off = 0; off < n; off += cap) {
         int m = n - off < cap ? n - off : cap;
         float *d_st, *d_rv, *d_pri; uint32_t *d_legal; int32_t *d_tp, *d_mv, *d_vc; uint64_t *d_gid;
@@ -709,6 +726,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     c->h_counters[3] = (int64_t)first_game; c->h_counters[4] = (int64_t)first_game + n_games; c->h_counters[5] = 0;
     MZ_TRY(write_counters(c));
     MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 64 * sizeof(unsigned long long), c->stream));
+    MZ_TRY(ensure_images(c));
     mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = G; a.max_dim = c->M.max_dim;
     a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
     a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;

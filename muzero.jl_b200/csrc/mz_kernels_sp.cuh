@@ -311,3 +311,100 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_nn_forward_sp(const __grid
     __syncthreads();
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MZ_SP_TMEM_COLS) : "memory");
 }
+
+// ---- tensor-core weight images from the device weights (after every update of d_w: set_weights, ADAM) ----------------------------
+// mode 1: MZ_NN_BF16_TC image (one bf16 block per layer), mode 2: MZ_NN_SPLIT_MMA image (hi block, lo block).  One CTA per layer.
+struct mz_pack_args { const float *w; unsigned char *image; float *bias; int32_t mode; int32_t off[MZ_MAX_LAYERS], bytes[MZ_MAX_LAYERS], bias_off[MZ_MAX_LAYERS]; };
+__global__ void __launch_bounds__(256) mz_k_pack_images(const __grid_constant__ mz_params P, const __grid_constant__ mz_pack_args a) {
+    const mz_layer &l = P.layers[blockIdx.x];
+    const int L = blockIdx.x;
+    for (int i = threadIdx.x; i < l.in * l.out; i += 256) {
+        const int k = i / l.out, o = i - k * l.out;
+        const float w = a.w[l.w_off + k * l.out_pad + o];
+        const uint32_t off = (uint32_t)a.off[L] + mz_tc_tile_offset(o, k);
+        if (a.mode == 2) {
+            unsigned short hi, lo; mz_sp_split(w, hi, lo);
+            *reinterpret_cast<unsigned short *>(a.image + off) = hi;
+            *reinterpret_cast<unsigned short *>(a.image + off + a.bytes[L]) = lo;
+        } else *reinterpret_cast<unsigned short *>(a.image + off) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
+    }
+    for (int o = threadIdx.x; o < l.out; o += 256) a.bias[a.bias_off[L] + o] = a.w[l.b_off + o];
+}
+
+// ---- learner: the K-step unroll forward (src/Learning.jl:347-370, Q19) with the networks on this path ------------------------------
+// Same schedule as mz_k_learn_forward (32 samples per CTA, prediction(h_i) || dynamics(h_i, a_i) on the two groups), the layers as
+// split-precision tcgen05 rounds.  Used when the context's nn_mode is MZ_NN_SPLIT_MMA and grad_mode = MZ_GRAD_REFERENCE_L2: the
+// reference's gradient does not depend on the forward pass (Q20: 2 * theta), so the update stays bit-identical to the exact path
+// and only the reported losses carry the ~1e-6 of the tensor-core arithmetic.
+struct mz_learn_sp_args { mz_sp_args sp; int32_t B; mz_batch batch; float *pred_values, *pred_rewards, *pred_policies; };
+__global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_learn_forward_sp(const __grid_constant__ mz_params P, const __grid_constant__ mz_learn_sp_args a) {
+    extern __shared__ __align__(1024) unsigned char mz_smem_sp[];
+    const mz_sp_args &A = a.sp;
+    const mz_sp_plan_s sp = mz_sp_carve(mz_smem_sp, A.warea_bytes, A.bias_floats, A.total_rounds, P.hidden_pad, P.S, A.pbc_smem);
+    const int tid = threadIdx.x, K1 = P.K + 1;
+    const uint32_t tmem_base = mz_sp_setup(sp, A, MZ_SP_THREADS);
+    mz_sp_ctx C; C.prog = mz_smem_u32(sp.prog); C.image = A.image; C.bars = mz_smem_u32(sp.bars);
+    const bool worker = tid < MZ_THREADS;
+    const int grp = worker ? tid >> 7 : (tid - MZ_THREADS) >> 5, gtid = tid & (MZ_GROUP - 1);
+    const bool issuer0 = !worker && (tid & 31) == 0;
+    if (issuer0) { if (grp == 0) mz_sp_prime(C, A, 1); else mz_sp_fill_many(C, A.first[0], A.n_rounds[0]); }
+    const uint32_t tmem_d = tmem_base + (uint32_t)(128 * grp), mbar_mma = mz_smem_u32(sp.mbar_mma[grp]);
+    const uint32_t in_pred = mz_sp_group_tile(sp, 0, 0), in_dyn = mz_sp_group_tile(sp, 1, 0);
+    const bool tanh_v = P.layers[P.nets[1].first + P.nets[1].n_trunk + P.nets[1].n_h1 - 1].act == MZ_ACT_TANH;
+    const bool tanh_r = P.layers[P.nets[2].first + P.nets[2].n_trunk + P.nets[2].n_h1 + P.nets[2].n_h2 - 1].act == MZ_ACT_TANH;
+    const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
+    const bool row_ok = tid < MZ_ROWS && g < a.B;
+    uint32_t q = 0, pass = 0;
+    for (int i = tid; i < MZ_ROWS * P.stack_size; i += MZ_SP_THREADS) {
+        const int rr = i / P.stack_size, k = i % P.stack_size;
+        const int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + rr;
+        mz_sp_stage(in_dyn, k, rr, gg < a.B ? a.batch.obs[gg * P.stack_size + k] : 0.0f);
+    }
+    mz_fence_proxy_async();
+    __syncthreads();
+    if (grp == 1) {                                                     // representation (:347); then the dynamics weights take its place
+        if (worker) q = mz_sp_run(C, A.first[0], A.n_rounds[0], tmem_d, mbar_mma, q, grp, gtid, nullptr);
+        else { q = mz_sp_run_issuer(C, A.first[0], A.n_rounds[0], tmem_d, mbar_mma, q, 0u, grp); if (issuer0 && P.K > 0) mz_sp_prime(C, A, 2); }
+    }
+    __syncthreads();
+    const int n_eval = P.K > 0 ? P.K : 1;
+    const bool dyn = P.K > 0;
+    for (int e = 0; e < n_eval; e++) {                                  // evaluation e: prediction(h_e) || dynamics(h_e, a_e)
+        for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_SP_THREADS) {
+            const int k = i / MZ_ROWS, rr = i % MZ_ROWS;
+            const float h = sp.outH[k * MZ_ROWS + rr];
+            mz_sp_stage(in_pred, k, rr, h);
+            if (dyn) mz_sp_stage(in_dyn, k, rr, h * 2.0f);             // make_dynamics_input (:293-304): state * 2 (a copy), action plane = Float32(a) / A
+        }
+        if (dyn && tid < MZ_ROWS) {
+            const float plane = row_ok ? a.batch.actions[g * K1 + e] / (float)P.A : 0.0f;
+            for (int k = P.obs_size; k < P.sa_size; k++) mz_sp_stage(in_dyn, k, tid, plane);
+        }
+        mz_fence_proxy_async();
+        __syncthreads();
+        if (grp == 0 || dyn) {
+            const int net = grp == 0 ? 1 : 2;
+            if (worker) q = mz_sp_run(C, A.first[net], A.n_rounds[net], tmem_d, mbar_mma, q, grp, gtid, nullptr);
+            else q = mz_sp_run_issuer(C, A.first[net], A.n_rounds[net], tmem_d, mbar_mma, q, pass, grp);
+            pass++;
+        }
+        __syncthreads();
+        if (row_ok) {   // evaluation e is row e + 1, and also row 0 when e == 0 (Q19: row i >= 1 = prediction(h_{i-1})); rewards: row 0 = 0 (:352)
+            float logits[MZ_MAX_A], policy[MZ_MAX_A];
+            for (int k = 0; k < P.A; k++) logits[k] = sp.outL[k * MZ_ROWS + tid];
+            mz_softmax(logits, P.A, policy);
+            const float v = tanh_v ? mz_tanhf(sp.outV[tid]) : sp.outV[tid];
+            const float rw = dyn ? (tanh_r ? mz_tanhf(sp.outR[tid]) : sp.outR[tid]) : 0.0f;
+            for (int rr = (e == 0 ? 0 : e + 1); rr <= (dyn ? e + 1 : 0); rr++) {
+                a.pred_values[g * K1 + rr] = v;
+                for (int k = 0; k < P.A; k++) a.pred_policies[(g * K1 + rr) * P.A + k] = policy[k];
+                a.pred_rewards[g * K1 + rr] = rr == 0 ? 0.0f : rw;
+            }
+        }
+        __syncthreads();                                                // outH = h_{e+1} is staged at the top of the next evaluation
+    }
+    if (issuer0) mz_sp_drain(C, A, grp == 0 ? 1 : 2, pass);
+    mz_tc_fence_before();
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MZ_SP_TMEM_COLS) : "memory");
+}

@@ -127,3 +127,34 @@ def test_mma_rejects_wide_layers_and_resnet(capi):
     assert e.value.code == capi.E_UNSUPPORTED
     with pytest.raises(capi.MuZeroB200Error):
         capi.Context(capi.resnet_config(num_slots=32, nn_mode=capi.NN_SPLIT_MMA))
+
+
+def test_mma_learner_forward_and_stale_image(capi):
+    """The K-step unroll on this path (mz_k_learn_forward_sp): predictions and losses against the Float32 oracle; the reference_l2 update
+    does not depend on the forward pass, so the weights after learning steps are BIT-identical to the exact path's; and self-play after
+    an update uses the updated weights (the tensor-core image is rebuilt on the device)."""
+    ctx, ocfg = make(capi, num_slots=256, replay_buffer_size=1024, batch_size=96)
+    ex = capi.Context(capi.default_config(num_slots=256, replay_buffer_size=1024, batch_size=96))
+    ctx.init_weights(21); blob = ctx.get_weights(); ex.set_weights(blob)
+    ex.self_play(0, 300, 1.0)
+    ctx.history_import(ex.history_export())
+    b = ctx.get_batch(3)
+    pv, pr, pp, losses = ctx.learn_forward(b)
+    opv, opr, opp, ol = O.learn_forward(ocfg, blob, b)
+    assert np.max(np.abs(pv - opv)) <= MMA_ATOL and np.max(np.abs(pr - opr)) <= MMA_ATOL and np.max(np.abs(pp - opp)) <= MMA_ATOL
+    assert np.allclose(losses, ol, rtol=2e-5)
+    assert np.array_equal(pv[:, 0], pv[:, 1]) and np.array_equal(pp[:, 0], pp[:, 1]) and np.all(pr[:, 0] == 0)        # Q19, Learning.jl:352
+    la = ctx.learn_steps(1, 5); lb = ex.learn_steps(1, 5)
+    assert np.array_equal(ctx.get_weights(), ex.get_weights())            # gradient = 2 * theta (Q20): independent of the forward arithmetic
+    assert np.allclose(la, lb, rtol=2e-5)
+    # the search now runs on the updated weights
+    w2 = ctx.get_weights()
+    st, legal, tp = common.random_stacked(ocfg, 64, seed=5)
+    gid = np.arange(64, dtype=np.uint64) + 7; mv = np.ones(64, np.int32)
+    vc, _ = ctx.run_mcts(st, legal, tp, True, gid, mv)
+    same = sum(vc[i].tolist() == O.run_mcts(ocfg, w2, st[i], int(legal[i]), int(tp[i]), True, int(gid[i]), 1)[0].tolist() for i in range(64))
+    assert same >= 62, same
+    h = ctx.representation(st)
+    oh = np.stack([O.representation(ocfg, w2, x) for x in st])
+    assert np.max(np.abs(h - oh)) <= MMA_ATOL * max(1.0, float(np.max(np.abs(oh))))
+    ctx.close(); ex.close()
