@@ -427,9 +427,11 @@ def run_b200(a):
             e1.record(stream); e1.synchronize()
             lms = e0.elapsed_time(e1)
             learner = {"batch_per_gpu": cfg.batch_size, "grad_mode": "reference_l2", "ms_per_step": lms / a.learner_steps,
-                       "losses": [float(x) for x in losses]}
+                       "losses": [float(x) for x in losses],
+                       "unroll_forward": "mz_k_learn_forward_sp (tcgen05, split precision)" if a.nn == "split" else "mz_k_learn_forward (fp32 SIMT)",
+                       "collective": {0: None, 1: "ncclAllReduce + mz_k_adam", 2: "mz_k_dp_adam: one kernel, gradients summed in rank order over peer memory (NVLink) + ADAM"}[ctx.comm_mode()]}
             # the same learner at a throughput-sized batch (the reference's batch_size is 32, params.jl:14)
-            big = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=max(10000, G), batch_size=4096), device=local, stream=stream.cuda_stream)
+            big = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=max(10000, G), batch_size=4096, nn_mode=nn_mode), device=local, stream=stream.cuda_stream)
             big.set_weights(blob)
             info = ctx.replay_info()
             n_imp = min(info["n_games"], 4096)
@@ -462,6 +464,20 @@ def run_b200(a):
                 else:
                     learner["large_batch"]["reference_l2"] = entry
             big.close()
+            if world > 1 and ctx.comm_mode() == 2:
+                # the same B = 32 steps with the library forced back to ncclAllReduce + mz_k_adam: what the fused peer-memory update replaces
+                ctx.comm_destroy()
+                os.environ["MUZERO_B200_DP"] = "nccl"
+                mzdist.attach_communicator(ctx, rank, world, device="cuda")
+                del os.environ["MUZERO_B200_DP"]
+                for mode_, key_ in ((capi.GRAD_REFERENCE_L2, "nccl_ms_per_step"), (capi.GRAD_BPTT, "nccl_bptt_ms_per_step")):
+                    ctx.learn_steps(1, 3, mode_)
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    ctx.learn_steps(4, a.learner_steps, mode_)
+                    e1.record(stream); e1.synchronize()
+                    learner[key_] = e0.elapsed_time(e1) / a.learner_steps
 
     xk = [k for k in ("fp32", "tc", "split") if k in mode_extra]
     t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0] + [mode_extra[k][0] for k in xk], dtype=torch.float64, device="cuda")

@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 5
+#define MZ_ABI_VERSION 6
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
@@ -225,6 +225,10 @@ int mz_set_optimizer_state(mz_ctx *ctx, const float *m, const float *v, int64_t 
 int mz_comm_unique_id(uint8_t id[128]);
 int mz_comm_init(mz_ctx *ctx, int rank, int nranks, const uint8_t id[128]);
 int mz_comm_destroy(mz_ctx *ctx);
+/* How the data-parallel learner exchanges gradients: 0 = no communicator, 1 = ncclAllReduce followed by the ADAM kernel, 2 = one kernel that
+ * reads every rank's gradient over peer memory (CUDA IPC mappings, NVLink), sums in rank order and applies ADAM (the default on one node;
+ * MUZERO_B200_DP=nccl in the environment of mz_comm_init keeps mode 1). */
+int mz_comm_mode(mz_ctx *ctx);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */

@@ -128,6 +128,7 @@ def lib():
         "mz_comm_unique_id": ([u8p], C.c_int),
         "mz_comm_init": ([ctx, C.c_int, C.c_int, u8p], C.c_int),
         "mz_comm_destroy": ([ctx], C.c_int),
+        "mz_comm_mode": ([ctx], C.c_int),
         "mz_launch_count": ([ctx, i64p], C.c_int),
         "mz_kernel_time": ([ctx, C.c_int, C.POINTER(C.c_double), i64p], C.c_int),
         "mz_kernel_time_reset": ([ctx, C.c_int], C.c_int),
@@ -528,6 +529,10 @@ class Context:
 
     def comm_destroy(self):
         self._ck(self.L.mz_comm_destroy(self._h))
+
+    def comm_mode(self):
+        """0 = no communicator, 1 = ncclAllReduce + ADAM kernel, 2 = fused reduction over peer memory + ADAM (mz_k_dp_adam)."""
+        return int(self.L.mz_comm_mode(self._h))
 
     # ---- instrumentation ----
     def launch_count(self):

@@ -39,6 +39,7 @@ struct nccl_api {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (handle) return true;
@@ -49,12 +50,15 @@ struct nccl_api {
         CommInitRank = (decltype(CommInitRank))dlsym(handle, "ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))dlsym(handle, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(handle, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(handle, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(handle, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && GetErrorString;
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && AllGather && GetErrorString;
     }
 } g_nccl;
 
 }  // namespace
+
+extern "C" { static void p2p_teardown(mz_ctx *c); }
 
 struct mz_ctx {
     mz_config cfg; mzh::model M; int device = 0;
@@ -64,6 +68,9 @@ struct mz_ctx {
     int exact_gt = 128;   // threads per network group of the exact search kernel: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps; measured no faster: the layer is bound by shared-memory wavefronts)
     float *d_w = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     unsigned char *d_w_tc = nullptr; float *d_bias_tc = nullptr; size_t smem_bytes_tc = 0;   // tensor-core weight image
+    // data-parallel learner over peer memory (mz_k_dp_adam): gradient exchange buffers (double-buffered) and arrival flags of every rank
+    float *d_xgrad = nullptr; uint32_t *d_xflags = nullptr; float *peer_grad[MZ_DP_MAX_RANKS] = {}; uint32_t *peer_flags[MZ_DP_MAX_RANKS] = {};
+    bool p2p = false; uint32_t dp_step = 0;
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
@@ -227,6 +234,10 @@ template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
 }
 #define MZ_TRY(x) do { int r_ = (x); if (r_ != MZ_OK) return r_; } while (0)
 
+// where this step's local gradient goes: d_grad, or -- data-parallel over peer memory -- the half of the exchange buffer the next
+// update reads (the other half may still be read by a peer that is one step behind)
+float *grad_out(mz_ctx *c) { return c->p2p ? c->d_xgrad + (size_t)((c->dp_step + 1u) & 1u) * (size_t)c->M.P.total_floats : c->d_grad; }
+
 // The tensor-core paths read bf16 images of the weights; whenever d_w has changed (set_weights, an ADAM step) the image of the context's
 // nn_mode is rebuilt on the device before the next kernel that reads it.
 int ensure_images(mz_ctx *c) {
@@ -264,7 +275,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         }
         mz_bptt_args b{}; b.f = a; b.act = c->d_act; b.gpart = c->d_gpart; b.stages[0] = c->d_bstages[0]; b.stages[1] = c->d_bstages[1];
         { launch_scope ls(c, 3); mz_k_learn_bptt<<<tiles, MZ_THREADS, c->smem_bytes_bptt, c->stream>>>(P, c->bptt.plan, b); }
-        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, c->d_grad); }
+        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2 && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // the unroll on the tensor cores (mz_kernels_sp.cuh)
         MZ_TRY(ensure_images(c));
         mz_learn_sp_args t{}; t.sp = c->spa; t.B = B; t.batch = c->batch; t.pred_values = c->d_pv; t.pred_rewards = c->d_pr; t.pred_policies = c->d_pp;
@@ -297,14 +308,20 @@ int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
     }
     if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
     // MZ_GRAD_BPTT: d_grad was produced by launch_learn_forward (mz_k_learn_bptt + mz_k_grad_reduce)
-    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     float scale = 1.0f;
-    if (c->comm) {   // data-parallel: sum gradients over ranks, average in the update
-        ncclResult_t r = g_nccl.AllReduce(c->d_grad, c->d_grad, (size_t)n, ncclFloat, ncclSum, c->comm, c->stream);
-        if (r != ncclSuccess) return fail(c, MZ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
-        scale = 1.0f / (float)c->nranks;
+    if (c->p2p) {    // data-parallel over peer memory: ONE kernel waits for the peers' gradients, sums them in rank order over NVLink and applies ADAM
+        mz_dp_args d{}; d.rank = c->rank; d.nranks = c->nranks; d.step = ++c->dp_step; d.n = n; d.flags_local = c->d_xflags;
+        for (int r = 0; r < c->nranks; r++) { d.peer_grad[r] = c->peer_grad[r] + (size_t)(d.step & 1u) * (size_t)n; d.peer_flags[r] = c->peer_flags[r]; }
+        launch_scope ls(c, 4); mz_k_dp_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_w, c->d_m, c->d_v, d, mzh::cos_schedule(t), c->bp1, c->bp2, 1.0f / (float)c->nranks);
+    } else {
+        if (c->comm) {   // data-parallel through NCCL: sum gradients over ranks, average in the update
+            ncclResult_t r = g_nccl.AllReduce(c->d_grad, c->d_grad, (size_t)n, ncclFloat, ncclSum, c->comm, c->stream);
+            if (r != ncclSuccess) return fail(c, MZ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+            scale = 1.0f / (float)c->nranks;
+        }
+        launch_scope ls(c, 4); mz_k_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_m, c->d_v, c->d_grad, mzh::cos_schedule(t), c->bp1, c->bp2, scale);
     }
-    { launch_scope ls(c, 4); mz_k_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_m, c->d_v, c->d_grad, mzh::cos_schedule(t), c->bp1, c->bp2, scale); }
     MZ_CUDA(c, cudaGetLastError());
     c->bp1 *= 0.9; c->bp2 *= 0.999; c->adam_t++;
     c->w_version++;
@@ -463,7 +480,7 @@ int mz_destroy(mz_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
-    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->comm && g_nccl.CommDestroy) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); }
     void *ptrs[] = {c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
@@ -1117,9 +1134,9 @@ int mz_learn_gradients_w(mz_ctx *c, int grad_mode, int B, const float *obs_batch
     if (weight_batch) MZ_CUDA(c, cudaMemcpyAsync(c->batch.weights, weight_batch, (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
     MZ_TRY(launch_learn_forward(c, B, grad_mode));
     const int n = c->M.P.total_floats;
-    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_grad); }
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     std::vector<float> dev((size_t)n), src((size_t)c->M.P.n_params);
-    MZ_CUDA(c, cudaMemcpyAsync(dev.data(), c->d_grad, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaMemcpyAsync(dev.data(), grad_out(c), dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     MZ_TRY(finish_losses(c, B, losses));
     mzh::unpack_weights(c->M.P, dev.data(), src.data());
     memcpy(grad, src.data(), src.size() * sizeof(float));
@@ -1200,23 +1217,85 @@ int mz_comm_unique_id(uint8_t id[128]) {
     memcpy(id, &u, 128);
     return MZ_OK;
 }
+// closes the peer mappings and frees the exchange buffers (after a barrier: a peer may still be reading them)
+static void p2p_teardown(mz_ctx *c) {
+    if (!c->d_xgrad) return;
+    if (c->comm && c->d_xflags) {   // barrier through NCCL, then nobody touches anybody's buffers again
+        g_nccl.AllReduce(c->d_xflags + MZ_DP_MAX_RANKS, c->d_xflags + MZ_DP_MAX_RANKS, 1, ncclInt32, ncclSum, c->comm, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    for (int r = 0; r < MZ_DP_MAX_RANKS; r++) {
+        if (r != c->rank && c->peer_grad[r]) cudaIpcCloseMemHandle(c->peer_grad[r]);
+        if (r != c->rank && c->peer_flags[r]) cudaIpcCloseMemHandle(c->peer_flags[r]);
+        c->peer_grad[r] = nullptr; c->peer_flags[r] = nullptr;
+    }
+    cudaFree(c->d_xgrad); cudaFree(c->d_xflags);
+    c->d_xgrad = nullptr; c->d_xflags = nullptr; c->p2p = false; c->dp_step = 0;
+}
+// Maps every rank's gradient exchange buffer and flag block into this process (CUDA IPC; the 128 bytes of handles per rank travel through
+// ncclAllGather).  Any failure leaves the NCCL allreduce in charge.  MUZERO_B200_DP=nccl forces that, too.
+static void p2p_setup(mz_ctx *c) {
+    const char *force = getenv("MUZERO_B200_DP");
+    if ((force && !strcmp(force, "nccl")) || c->nranks < 2 || c->nranks > MZ_DP_MAX_RANKS || c->cfg.net_type != MZ_NET_FEEDFORWARD) return;
+    const size_t n = (size_t)c->M.P.total_floats;
+    unsigned char mine[128], *d_all = nullptr; std::vector<unsigned char> all((size_t)128 * c->nranks);
+    bool ok = cudaMalloc((void **)&c->d_xgrad, 2 * n * sizeof(float)) == cudaSuccess && cudaMalloc((void **)&c->d_xflags, 2 * MZ_DP_MAX_RANKS * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMemset(c->d_xgrad, 0, 2 * n * sizeof(float)) == cudaSuccess && cudaMemset(c->d_xflags, 0, 2 * MZ_DP_MAX_RANKS * sizeof(uint32_t)) == cudaSuccess;
+    memset(mine, 0, sizeof(mine));
+    cudaIpcMemHandle_t hg, hf;
+    ok = ok && cudaIpcGetMemHandle(&hg, c->d_xgrad) == cudaSuccess && cudaIpcGetMemHandle(&hf, c->d_xflags) == cudaSuccess;
+    if (ok) { memcpy(mine, &hg, 64); memcpy(mine + 64, &hf, 64); }
+    // every rank takes part in the gather even when its own set-up failed: a zeroed blob tells the others
+    unsigned char flag_ok = ok ? 1 : 0;
+    if (cudaMalloc((void **)&d_all, (size_t)129 * c->nranks + 129 + 16) != cudaSuccess) { cudaGetLastError(); return; }
+    std::vector<unsigned char> sendv(129); memcpy(sendv.data(), mine, 128); sendv[128] = flag_ok;
+    cudaMemcpyAsync(d_all + (size_t)129 * c->nranks, sendv.data(), 129, cudaMemcpyHostToDevice, c->stream);
+    ncclResult_t r = g_nccl.AllGather(d_all + (size_t)129 * c->nranks, d_all, 129, ncclUint8, c->comm, c->stream);
+    std::vector<unsigned char> recv((size_t)129 * c->nranks);
+    cudaMemcpyAsync(recv.data(), d_all, recv.size(), cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    bool all_ok = ok && r == ncclSuccess;
+    for (int q = 0; q < c->nranks; q++) all_ok = all_ok && recv[(size_t)129 * q + 128] == 1;
+    if (all_ok) {
+        for (int q = 0; q < c->nranks && all_ok; q++) {
+            if (q == c->rank) { c->peer_grad[q] = c->d_xgrad; c->peer_flags[q] = c->d_xflags; continue; }
+            cudaIpcMemHandle_t pg, pf; memcpy(&pg, &recv[(size_t)129 * q], 64); memcpy(&pf, &recv[(size_t)129 * q + 64], 64);
+            all_ok = cudaIpcOpenMemHandle((void **)&c->peer_grad[q], pg, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+                     cudaIpcOpenMemHandle((void **)&c->peer_flags[q], pf, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        }
+    }
+    // unanimous or not at all: a rank that could not map a peer must not leave the others waiting for its flags
+    int32_t vote = all_ok ? 1 : 0, *d_vote = reinterpret_cast<int32_t *>(d_all + (((size_t)129 * c->nranks + 129 + 15) & ~(size_t)15) - 0);
+    d_vote = reinterpret_cast<int32_t *>(d_all);     // the gather buffer is free again (cudaMalloc memory is 256-byte aligned)
+    cudaMemcpyAsync(d_vote, &vote, 4, cudaMemcpyHostToDevice, c->stream);
+    g_nccl.AllReduce(d_vote, d_vote, 1, ncclInt32, ncclMin, c->comm, c->stream);
+    cudaMemcpyAsync(&vote, d_vote, 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_all);
+    cudaGetLastError();
+    if (vote == 1) { c->p2p = true; c->dp_step = 0; }
+    else p2p_teardown(c);
+}
 int mz_comm_init(mz_ctx *c, int rank, int nranks, const uint8_t id[128]) {
     MZ_CHECK_CTX(c);
     if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, MZ_E_ARG, "bad rank/nranks/id");
     if (!g_nccl.load()) return fail(c, MZ_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
-    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    if (c->comm) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     ncclUniqueId u; memcpy(&u, id, 128);
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, u, rank);
     if (r != ncclSuccess) { c->comm = nullptr; return fail(c, MZ_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     c->rank = rank; c->nranks = nranks;
+    p2p_setup(c);
     return MZ_OK;
 }
 int mz_comm_destroy(mz_ctx *c) {
     MZ_CHECK_CTX(c);
-    if (c->comm) { MZ_CUDA(c, cudaStreamSynchronize(c->stream)); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
+    if (c->comm) { MZ_CUDA(c, cudaStreamSynchronize(c->stream)); p2p_teardown(c); g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     c->rank = 0; c->nranks = 1;
     return MZ_OK;
 }
+// 0 = no communicator, 1 = ncclAllReduce + mz_k_adam, 2 = mz_k_dp_adam over peer memory (NVLink loads, fused with the update)
+int mz_comm_mode(mz_ctx *c) { if (!c) return 0; return c->p2p ? 2 : c->comm ? 1 : 0; }
 
 // ---- instrumentation ---------------------------------------------------------------------------------------------
 int mz_launch_count(mz_ctx *c, int64_t *n) { if (!c || !n) return fail(c, MZ_E_ARG, "NULL"); *n = c->launches; return MZ_OK; }

@@ -207,3 +207,38 @@ __global__ void mz_k_adam(int n, float *theta, float *m, float *v, const float *
     float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
     theta[i] = theta[i] - delta;
 }
+
+// Data-parallel update over peer memory: every rank's gradient lies in a buffer that all ranks have mapped (CUDA IPC, NVLink / NVSwitch).
+// One kernel: announce "my gradient of step s is complete" in every peer's flag block, wait until every peer has announced the same,
+// then each thread sums its element over the ranks IN RANK ORDER (so all ranks compute bit-identical sums) with loads straight from the
+// peers' memory and applies Flux.ADAM (mz_k_adam's arithmetic).  Replaces ncclAllReduce + mz_k_adam: the 300 KB exchange is latency
+// bound, and here it costs one flag round trip plus nranks - 1 remote loads per thread instead of a ring of launches.
+// Buffers are double-buffered by step parity: a rank can only be one barrier ahead of a peer, so the half it overwrites at step s + 2
+// is no longer read by anyone.
+#define MZ_DP_MAX_RANKS 8
+struct mz_dp_args { int32_t rank, nranks, n; uint32_t step; const float *peer_grad[MZ_DP_MAX_RANKS]; uint32_t *peer_flags[MZ_DP_MAX_RANKS]; uint32_t *flags_local; };
+__global__ void __launch_bounds__(256) mz_k_dp_adam(float *theta, float *m, float *v, const __grid_constant__ mz_dp_args a, double eta, double bp1, double bp2, float grad_scale) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.nranks) {              // the local gradient was written by earlier kernels of this stream
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_flags[threadIdx.x] + a.rank), "r"(a.step) : "memory");
+    }
+    if ((int)threadIdx.x < a.nranks) {
+        uint32_t seen = 0, spin = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.flags_local + threadIdx.x) : "memory");
+            if (++spin > (1u << 28)) __trap();                          // a rank that never arrives must fault the kernel, not hang the GPU
+        } while ((int32_t)(seen - a.step) < 0);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float g = 0.0f;
+    for (int r = 0; r < a.nranks; r++) g = g + __ldcv(a.peer_grad[r] + i);
+    g = g * grad_scale;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * (double)g);
+    const float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * (double)(g * g));
+    m[i] = mi; v[i] = vi;
+    const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+    theta[i] = theta[i] - delta;
+}

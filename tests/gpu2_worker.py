@@ -26,6 +26,7 @@ h = ctx.history_export()
 out.update(lo=lo, cnt=cnt, sims=sims, hist={k: h[k] for k in h})
 # ---- data-parallel learner ----
 ctx.comm_init(rank, world, job["uid"])
+out["comm_mode"] = ctx.comm_mode()
 for name in ("halves", "equal_gscale"):
     ctx.set_weights(job["blob"]); ctx.optimizer_reset()
     shard = {k: v[rank::world] if name == "halves" else np.array_split(v, world)[rank] for k, v in job["batch_" + name].items()}
@@ -35,6 +36,17 @@ for name in ("halves", "equal_gscale"):
 ctx.set_weights(job["blob"]); ctx.optimizer_reset()
 ctx.learn_steps(1, 3, capi.GRAD_BPTT)
 out["w_own_batches"] = ctx.get_weights()
+ctx.comm_destroy()
+# the same data-parallel steps through ncclAllReduce + the ADAM kernel (MUZERO_B200_DP=nccl): for two ranks a + b has one rounding, so
+# the fused peer-memory update must give the same bits
+os.environ["MUZERO_B200_DP"] = "nccl"
+ctx.comm_init(rank, world, job["uid2"])
+out["comm_mode_nccl"] = ctx.comm_mode()
+ctx.set_weights(job["blob"]); ctx.optimizer_reset()
+shard = {k: v[rank::world] for k, v in job["batch_halves"].items()}
+for t in (1, 2):
+    ctx.learn_step(t, capi.GRAD_BPTT, shard)
+out["w_halves_nccl"] = ctx.get_weights()
 ctx.comm_destroy()
 ctx.close()
 pickle.dump(out, open(os.path.join(work, "out%d.pkl" % rank), "wb"))

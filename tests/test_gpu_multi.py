@@ -38,7 +38,7 @@ def test_two_gpu_self_play_and_data_parallel_learner(tmp_path):
     for b in (b1, b2):
         b.pop("index")
     b2["gscale"][Bh:] = b2["gscale"][:Bh]
-    job = dict(cfg=kw, blob=blob, first_game=first, n_games=n_games, uid=capi.Context.comm_unique_id(), batch_halves=b1, batch_equal_gscale=b2)
+    job = dict(cfg=kw, blob=blob, first_game=first, n_games=n_games, uid=capi.Context.comm_unique_id(), uid2=capi.Context.comm_unique_id(), batch_halves=b1, batch_equal_gscale=b2)
     pickle.dump(job, open(tmp_path / "job.pkl", "wb"))
     procs = [subprocess.Popen([sys.executable, os.path.join(common.ROOT, "tests", "gpu2_worker.py"), str(r), "2", str(tmp_path)]) for r in range(2)]
     for p in procs:
@@ -49,6 +49,9 @@ def test_two_gpu_self_play_and_data_parallel_learner(tmp_path):
     got = {k: np.concatenate([r["hist"][k][np.argsort(r["hist"]["game_id"])] for r in res]) for k in ("game_id",) + common.HIST_KEYS}
     for k in ("game_id",) + common.HIST_KEYS:
         assert np.array_equal(got[k], href[k][order]), k
+    # ---- the collective: one kernel over peer memory (mz_k_dp_adam) by default, ncclAllReduce + ADAM when forced; same bits for two ranks ----
+    assert res[0]["comm_mode"] == 2 and res[1]["comm_mode"] == 2 and res[0]["comm_mode_nccl"] == 1
+    assert np.array_equal(res[0]["w_halves"], res[0]["w_halves_nccl"]) and np.array_equal(res[1]["w_halves_nccl"], res[0]["w_halves_nccl"])
     # ---- identical weights on both ranks after the allreduce ----
     for name in ("halves", "equal_gscale", "own_batches"):
         assert np.array_equal(res[0]["w_" + name], res[1]["w_" + name]), name
