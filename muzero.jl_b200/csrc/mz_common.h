@@ -179,6 +179,8 @@ struct mz_params {
 #define MZ_SP_MAX_ROUNDS 40
 #define MZ_SP_MAX_SETS 48
 #define MZ_SP_TILE_BYTES 4096                      // one operand tile: [64 k][32 trees] bf16, N-major, SWIZZLE_64B
+#define MZ_SP_OS 36                               // floats per feature row of the fp32 network outputs [feature][tree]: 36 = 4 mod 32 keeps the
+                                                   // trees' reads (8 lanes per tree, lane = feature) free of bank conflicts; 16-byte aligned rows
 #define MZ_SP_TILES_PER_GROUP 3                    // input / ping / pong, each as a hi tile followed by a lo tile
 struct mz_sp_job {
     int32_t a_off;                                  // byte offset of the layer's hi weight block in the CTA's weight area (lo block = + a_bytes)
@@ -215,7 +217,7 @@ struct mz_sp_plan {
 MZ_HD size_t mz_sp_smem_bytes(int warea_bytes, int bias_floats, int total_rounds, int hidden_pad, int S, int pbc_smem) {
     size_t tiles = (size_t)2 * MZ_SP_TILES_PER_GROUP * 2 * MZ_SP_TILE_BYTES;
     size_t bias = ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
-    size_t out = (size_t)(24 + hidden_pad) * 32 * 4;
+    size_t out = (size_t)(24 + hidden_pad) * MZ_SP_OS * 4;
     size_t tab = pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     size_t path = (((size_t)S + 2) * 2 * 32 + 127) & ~(size_t)127;
     size_t prog = ((size_t)total_rounds * MZ_SP_RDESC_BYTES + 127) & ~(size_t)127;

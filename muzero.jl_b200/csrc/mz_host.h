@@ -366,7 +366,7 @@ inline void build_sp_plan(const mz_params &P, size_t smem_limit, mz_sp_plan &S) 
     }
     S.image_bytes = off; S.bias_floats = P.n_layers * 64;
     if (!S.ok) return;
-    S.out_off[0] = 0; S.out_off[1] = 4 * 32; S.out_off[2] = 20 * 32; S.out_off[3] = 24 * 32;
+    S.out_off[0] = 0; S.out_off[1] = 4 * MZ_SP_OS; S.out_off[2] = 20 * MZ_SP_OS; S.out_off[3] = 24 * MZ_SP_OS;
     sp_build_net(P, S, 0, S.out_off[3], -1);
     sp_build_net(P, S, 1, S.out_off[0], S.out_off[1]);
     sp_build_net(P, S, 2, S.out_off[3], S.out_off[2]);

@@ -136,15 +136,23 @@ __device__ __forceinline__ void mz_tree_expand_lanes(const mz_params &P, const m
     const float l0 = v0 ? logits[ln * ls] : -INFINITY, l1 = v1 ? logits[(ln + 8) * ls] : -INFINITY;
     float m = mz_seg_max(l1 > l0 ? l1 : l0, segmask);
     float e0 = v0 ? mz_expf(l0 - m) : 0.0f, e1 = v1 ? mz_expf(l1 - m) : 0.0f;
+    // ordered sums (ascending action, like the scalar code): all shuffles are issued first, then the dependent adds
+    float ev[MZ_MAX_A];
+#pragma unroll
+    for (int a = 0; a < MZ_MAX_A; a++) ev[a] = __shfl_sync(segmask, a < 8 ? e0 : e1, a & 7, MZ_LANES);
     float s = 0.0f;
-    for (int a = 0; a < P.A; a++) { float v = __shfl_sync(segmask, a < 8 ? e0 : e1, a & 7, MZ_LANES); s = s + v; }
+#pragma unroll
+    for (int a = 0; a < MZ_MAX_A; a++) if (a < P.A) s = s + ev[a];
     const float p0 = e0 / s, p1 = e1 / s;                       // policy[ln], policy[ln+8]
     const bool g0 = v0 && ((legal >> ln) & 1u), g1 = v1 && ((legal >> (ln + 8)) & 1u);
     float q = g0 ? p0 : -INFINITY; if (g1) q = p1 > q ? p1 : q;
     const float m2 = mz_seg_max(q, segmask);
     const float f0 = g0 ? mz_expf(p0 - m2) : 0.0f, f1 = g1 ? mz_expf(p1 - m2) : 0.0f;
+#pragma unroll
+    for (int a = 0; a < MZ_MAX_A; a++) ev[a] = __shfl_sync(segmask, a < 8 ? f0 : f1, a & 7, MZ_LANES);
     float s2 = 0.0f;
-    for (int a = 0; a < P.A; a++) { float v = __shfl_sync(segmask, a < 8 ? f0 : f1, a & 7, MZ_LANES); if ((legal >> a) & 1u) s2 = s2 + v; }
+#pragma unroll
+    for (int a = 0; a < MZ_MAX_A; a++) if (a < P.A && ((legal >> a) & 1u)) s2 = s2 + ev[a];
     const int base = 1 + e * P.A;
     mz_f4 c; c.x = mz_bits2f(mz_nx_pack(0, -1, 0)); c.y = 0.0f; c.w = 0.0f;
     if (v0) { c.z = g0 ? f0 / s2 : 0.0f; t.A[base + ln] = c; }

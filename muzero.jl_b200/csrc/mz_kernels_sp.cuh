@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
     }
     __syncthreads();
     MZ_KSTAMP(2);
-    for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_SP_THREADS) { const int k = i / MZ_ROWS, rr = i % MZ_ROWS; mz_sp_stage(in_pred, k, rr, sp.outH[k * MZ_ROWS + rr]); }
+    for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_SP_THREADS) { const int k = i / MZ_ROWS, rr = i % MZ_ROWS; mz_sp_stage(in_pred, k, rr, sp.outH[k * MZ_SP_OS + rr]); }
     mz_fence_proxy_async();
     __syncthreads();
     if (grp == 0) {
@@ -154,18 +154,22 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
     unsigned long long depth_sum = 0;
     MZ_TIMER_DECL;
     if (active) {
-        for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_ROWS + r];
+        for (int k = ln; k < P.hidden; k += MZ_LANES) tree.hidden[k] = sp.outH[k * MZ_SP_OS + r];
         if (ln == 0) {
             mz_f4 root; root.x = mz_bits2f(mz_nx_pack(0, -1, 0)); root.y = 0.0f; root.z = 0.0f; root.w = 0.0f;
             tree.A[0] = root;
         }
         __syncwarp(segmask);
-        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, 0.0f, ln, segmask);
+        mz_tree_expand_lanes(P, tree, 0, 0, legal, sp.outL + r, 0.0f, 0.0f, ln, segmask, MZ_SP_OS);
         if (ln == 0 && a.exploration && P.exploration_eps != 0.0f) mz_tree_add_noise(P, tree, legal, game, move);
         __syncwarp(segmask);
     }
 
     MZ_KSTAMP(4);
+    // byte offsets of this lane's staging positions (k = ln + 8 i, tree r) inside an operand tile: the same in every simulation
+    uint32_t soff[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) soff[i] = mz_sp_tile_offset(ln + MZ_LANES * i, r & (MZ_ROWS - 1));
     // ---- simulations ----
     for (int sim = 1; sim <= P.S; sim++) {
         mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
@@ -185,12 +189,13 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
                 const int k = ln + MZ_LANES * i;
                 if (k < P.hidden) {
                     const float v = hv[i] * sc;
-                    mz_sp_stage(in_pred, k, r, v);                 // prediction(parent.hidden_state) (Q5)
-                    mz_sp_stage(in_dyn, k, r, v * 2.0f);           // make_state_action: state .*= 2 (Q6)
+                    mz_sp_stage_at(in_pred + soff[i], v);          // prediction(parent.hidden_state) (Q5)
+                    mz_sp_stage_at(in_dyn + soff[i], v * 2.0f);    // make_state_action: state .*= 2 (Q6)
                 }
             }
             const float plane = P.act_plane_play[leaf.action];
-            for (int k = P.obs_size + ln; k < P.sa_size; k += MZ_LANES) mz_sp_stage(in_dyn, k, r, plane);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const int k = ln + MZ_LANES * i; if (k >= P.obs_size && k < P.sa_size) mz_sp_stage_at(in_dyn + soff[i], plane); }
             __syncwarp(segmask);
             if (ln == 0) reinterpret_cast<uint32_t *>(&tree.A[leaf.parent])[0] = leaf.parent_x + (1u << 24);   // one more doubling (Q6)
         }
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
         MZ_TIMER(5);
         if (active) {
             float *nh = tree.hidden + (size_t)sim * P.hidden_pad;
-            for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_ROWS + r];
+            for (int k = ln; k < P.hidden; k += MZ_LANES) nh[k] = sp.outH[k * MZ_SP_OS + r];
             MZ_TIMER(6);
             float rw = sp.outR[r], vl = sp.outV[r];
             if (tanh_r || tanh_v) {                                // both tanh side by side: even lanes the value, odd lanes the reward
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
                 if ((ln & 1) ? tanh_r : tanh_v) x = mz_tanhf(x);
                 vl = __shfl_sync(segmask, x, 0, MZ_LANES); rw = __shfl_sync(segmask, x, 1, MZ_LANES);
             }
-            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, rw, leaf.prior, ln, segmask);
+            mz_tree_expand_lanes(P, tree, leaf.node, sim, legal, sp.outL + r, rw, leaf.prior, ln, segmask, MZ_SP_OS);
             MZ_TIMER(7);
             mz_tree_backup_lanes(P, tree, path, leaf.depth, vl, mm, ln, segmask);
         }
@@ -293,13 +298,13 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_nn_forward_sp(const __grid
     if (tid < MZ_ROWS && g < a.B) {
         if (a.net == 1) {
             float logits[MZ_MAX_A], policy[MZ_MAX_A];
-            for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_ROWS + tid];
+            for (int i = 0; i < P.A; i++) logits[i] = sp.outL[i * MZ_SP_OS + tid];
             mz_softmax(logits, P.A, policy);
             const bool th = P.layers[P.nets[1].first + P.nets[1].n_trunk + P.nets[1].n_h1 - 1].act == MZ_ACT_TANH;
             a.out1[g] = th ? mz_tanhf(sp.outV[tid]) : sp.outV[tid];
             for (int i = 0; i < P.A; i++) a.out2[g * P.A + i] = policy[i];
         } else {
-            for (int k = 0; k < P.hidden; k++) a.out1[g * P.hidden + k] = sp.outH[k * MZ_ROWS + tid];
+            for (int k = 0; k < P.hidden; k++) a.out1[g * P.hidden + k] = sp.outH[k * MZ_SP_OS + tid];
             if (a.net == 2) {
                 const bool th = P.layers[P.nets[2].first + P.nets[2].n_trunk + P.nets[2].n_h1 + P.nets[2].n_h2 - 1].act == MZ_ACT_TANH;
                 a.out2[g] = th ? mz_tanhf(sp.outR[tid]) : sp.outR[tid];
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_learn_forward_sp(const __g
     for (int e = 0; e < n_eval; e++) {                                  // evaluation e: prediction(h_e) || dynamics(h_e, a_e)
         for (int i = tid; i < MZ_ROWS * P.hidden; i += MZ_SP_THREADS) {
             const int k = i / MZ_ROWS, rr = i % MZ_ROWS;
-            const float h = sp.outH[k * MZ_ROWS + rr];
+            const float h = sp.outH[k * MZ_SP_OS + rr];
             mz_sp_stage(in_pred, k, rr, h);
             if (dyn) mz_sp_stage(in_dyn, k, rr, h * 2.0f);             // make_dynamics_input (:293-304): state * 2 (a copy), action plane = Float32(a) / A
         }
@@ -391,7 +396,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_learn_forward_sp(const __g
         __syncthreads();
         if (row_ok) {   // evaluation e is row e + 1, and also row 0 when e == 0 (Q19: row i >= 1 = prediction(h_{i-1})); rewards: row 0 = 0 (:352)
             float logits[MZ_MAX_A], policy[MZ_MAX_A];
-            for (int k = 0; k < P.A; k++) logits[k] = sp.outL[k * MZ_ROWS + tid];
+            for (int k = 0; k < P.A; k++) logits[k] = sp.outL[k * MZ_SP_OS + tid];
             mz_softmax(logits, P.A, policy);
             const float v = tanh_v ? mz_tanhf(sp.outV[tid]) : sp.outV[tid];
             const float rw = dyn ? (tanh_r ? mz_tanhf(sp.outR[tid]) : sp.outR[tid]) : 0.0f;

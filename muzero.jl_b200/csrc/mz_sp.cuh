@@ -28,7 +28,7 @@
 struct __align__(16) mz_sp_rdesc {                  // device form of mz_sp_round: everything a round needs, shared addresses resolved
     unsigned long long a_hi[2], a_lo[2], b_hi[2];   // words  0..11: UMMA descriptors at k-step 0
     uint32_t dst[2];                                // words 12..13: hi output tile (lo = + MZ_SP_TILE_BYTES) or 0
-    uint32_t f32[2];                                // words 14..15: fp32 output [m * 32 + tree] or 0
+    uint32_t f32[2];                                // words 14..15: fp32 output [m * MZ_SP_OS + tree] or 0
     uint32_t bias[2];                               // words 16..17
     int16_t ks[2], out[2];                          // words 18, 19
     int16_t act[2], perm[2];                        // words 20, 21
@@ -65,6 +65,11 @@ __device__ __forceinline__ void mz_sp_stage(uint32_t tile_hi, int k, int n, floa
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(hi) : "memory");
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(a + MZ_SP_TILE_BYTES), "h"(lo) : "memory");
 }
+__device__ __forceinline__ void mz_sp_stage_at(uint32_t addr_hi, float v) {
+    unsigned short hi, lo; mz_sp_split(v, hi, lo);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr_hi), "h"(hi) : "memory");
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr_hi + MZ_SP_TILE_BYTES), "h"(lo) : "memory");
+}
 // (x0, x1) -> packed bf16 hi parts (x0 in the low half) and packed bf16 lo parts
 __device__ __forceinline__ void mz_sp_split2(float x0, float x1, uint32_t &h, uint32_t &l) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
@@ -88,7 +93,7 @@ __device__ __forceinline__ mz_sp_plan_s mz_sp_carve(unsigned char *raw, int ware
     p.bars = (uint64_t *)c; p.mbar_mma[0] = (uint64_t *)(c + 8 * MZ_SP_MAX_SETS); p.mbar_mma[1] = p.mbar_mma[0] + 1; p.tmem_slot = (uint32_t *)(c + 8 * MZ_SP_MAX_SETS + 16);
     c += MZ_SP_CTRL_BYTES;
     p.bias = (float *)c; c += ((size_t)bias_floats * 4 + 127) & ~(size_t)127;
-    p.outV = (float *)c; p.outL = p.outV + 4 * 32; p.outR = p.outV + 20 * 32; p.outH = p.outV + 24 * 32; c += (size_t)(24 + hidden_pad) * 32 * 4;
+    p.outV = (float *)c; p.outL = p.outV + 4 * MZ_SP_OS; p.outR = p.outV + 20 * MZ_SP_OS; p.outH = p.outV + 24 * MZ_SP_OS; c += (size_t)(24 + hidden_pad) * MZ_SP_OS * 4;
     p.pbc = (double *)c; c += pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     p.path = (uint16_t *)c; c += (((size_t)S + 2) * 2 * 32 + 127) & ~(size_t)127;
     p.prog = (mz_sp_rdesc *)c;
@@ -193,13 +198,13 @@ __device__ __forceinline__ void mz_sp_epilogue(const uint32_t (&v)[16], const ui
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + MZ_SP_TILE_BYTES), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
             } else if (perm) {          // final layer, permuted input order: column 8q + 2c + e is tree 8c + 2q + e
-                const uint32_t a = f32 + (uint32_t)((m * MZ_ROWS + 8 * c) * 4);
+                const uint32_t a = f32 + (uint32_t)((m * MZ_SP_OS + 8 * c) * 4);
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + 16u), "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(f32 + (uint32_t)((m * MZ_ROWS + 8 * q + 2 * c) * 4)), "f"(x[2 * q]), "f"(x[2 * q + 1]) : "memory");
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(f32 + (uint32_t)((m * MZ_SP_OS + 8 * q + 2 * c) * 4)), "f"(x[2 * q]), "f"(x[2 * q + 1]) : "memory");
             }
         }
     }
