@@ -384,6 +384,15 @@ def run_b200(a):
             cn_extra = (e0.elapsed_time(e1), cs_, ck_ms, ck_n, Gc, Sc, cm_)
             ctx_cn.close()
         barrier()
+        # ---- steady state: the same 4096 slots kept busy -- a finished game's slot is refilled with the next game at once (what self_play! does when it
+        #      is asked for more games than there are slots), so the last plies of a wave no longer run on a thinning set of trees ----
+        flush.zero_(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ss_sims, ss_moves = ctx.self_play(game_base + 5 * 10 ** 6, 4 * G, 1.0)
+        e1.record(stream); e1.synchronize()
+        steady = (e0.elapsed_time(e1), ss_sims, ss_moves)
+        barrier()
         # ---- latency of ONE run_mcts call with one root through the host API (what the reference's play_game calls per move) ----
         st1 = np.zeros((1, 63), np.float32); st1[:, 18:27] = 1
         one = (st1, np.full(1, 0x1ff, np.uint32), np.ones(1, np.int32), True, np.arange(1, dtype=np.uint64), np.ones(1, np.int32))
@@ -480,14 +489,14 @@ def run_b200(a):
                     learner[key_] = e0.elapsed_time(e1) / a.learner_steps
 
     xk = [k for k in ("fp32", "tc", "split") if k in mode_extra]
-    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0] + [mode_extra[k][0] for k in xk], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([sims_total, e2e_sims, launches, rn_extra[1] if rn_extra else 0, strong[1] if strong else 0] + [mode_extra[k][1] for k in xk], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_ms, (learner or {}).get("ms_per_step", 0.0), rn_extra[0] if rn_extra else 0.0, strong[0] if strong else 0.0, steady[0]] + [mode_extra[k][0] for k in xk], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([sims_total, e2e_sims, launches, rn_extra[1] if rn_extra else 0, strong[1] if strong else 0, steady[1]] + [mode_extra[k][1] for k in xk], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     tl, cl = [float(x) for x in t.cpu()], [float(x) for x in cnt.cpu()]
-    ms_max, e2e_ms_max, learn_ms_max, rn_ms_max, strong_ms_max = tl[:5]
-    sims_all, e2e_sims_all, launches_all, rn_sims_all, strong_sims_all = cl[:5]
-    x_ms_max = {k: tl[5 + i] for i, k in enumerate(xk)}; x_sims_all = {k: cl[5 + i] for i, k in enumerate(xk)}
+    ms_max, e2e_ms_max, learn_ms_max, rn_ms_max, strong_ms_max, steady_ms_max = tl[:6]
+    sims_all, e2e_sims_all, launches_all, rn_sims_all, strong_sims_all, steady_sims_all = cl[:6]
+    x_ms_max = {k: tl[6 + i] for i, k in enumerate(xk)}; x_sims_all = {k: cl[6 + i] for i, k in enumerate(xk)}
 
     if rank == 0:
         peaks = {}
@@ -552,6 +561,9 @@ def run_b200(a):
                                                 "achieved_per_clk_per_sm": wf_rate, "peak_per_clk_per_sm": 1.0, "frac": wf_rate, "sms_with_a_cta": ctas,
                                                 "note": "whole-launch average incl. the tree phases; inside the network phase the wavefront pipe is the bound "
                                                         "(64 wavefront-cycles vs 32 FMA-cycles per k step), which caps the FMA pipe at 50 %"}
+        out["steady_state"] = {"value": steady_sims_all / (steady_ms_max * 1e-3), "unit": UNIT, "games": 4 * G * world, "moves": steady[2],
+                               "note": "one self_play call of 4 x %d games per GPU on the same %d slots: finished slots are refilled at once, so all slots stay busy until the "
+                                       "last games run out; `value` above plays exactly %d games per step, whose last plies run on a thinning set of trees" % (G, G, G)}
         if strong and strong_ms_max > 0:
             out["strong_scaling"] = {"value": strong_sims_all / (strong_ms_max * 1e-3), "unit": UNIT, "ms_per_step": strong_ms_max / a.steps,
                                      "games_total": strong[2] * world, "games_per_gpu": strong[2],

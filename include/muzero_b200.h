@@ -37,9 +37,10 @@ enum { MZ_OPP_SELF = 0, MZ_OPP_RANDOM = 1, MZ_OPP_EXPERT = 2 };
 /* network arithmetic of self-play / run_mcts / the network callables:
  *   MZ_NN_FP32_EXACT  fp32 SIMT, sequential-k fmaf: bit-identical to the oracle's arithmetic contract
  *   MZ_NN_BF16_TC     bf16 operands on tcgen05.mma, fp32 accumulation in TMEM
- *   MZ_NN_SPLIT_MMA   tensor cores at near-Float32 accuracy: both operands split into bf16 hi + lo, hi*lo + lo*hi + hi*hi accumulated
- *                     in fp32 (warp-level MMAs, a whole layer chain stays in registers); visit counts agree with the Float32 oracle on
- *                     > 99 % of roots.  The learner always computes in fp32. */
+ *   MZ_NN_SPLIT_MMA   tcgen05.mma at near-Float32 accuracy: both operands split into bf16 hi + lo, W_hi X_hi + W_lo X_hi + W_hi X_lo
+ *                     accumulated in fp32 in TMEM; network outputs within ~1e-6 of Float32, visit counts identical to the Float32 oracle
+ *                     on > 99 % of roots.  In this mode the learner's unroll forward (MZ_GRAD_REFERENCE_L2) runs on the same path;
+ *                     MZ_GRAD_BPTT always computes in fp32. */
 enum { MZ_NN_FP32_EXACT = 0, MZ_NN_BF16_TC = 1, MZ_NN_SPLIT_MMA = 2 };
 enum { MZ_NET_FEEDFORWARD = 0, MZ_NET_RESNET = 1 };
 enum { MZ_NET_REPRESENTATION = 0, MZ_NET_PREDICTION = 1, MZ_NET_DYNAMICS = 2, MZ_NET_ALL = 3 };
