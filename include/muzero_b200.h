@@ -230,6 +230,11 @@ int mz_comm_destroy(mz_ctx *ctx);
  * reads every rank's gradient over peer memory (CUDA IPC mappings, NVLink), sums in rank order and applies ADAM (the default on one node;
  * MUZERO_B200_DP=nccl in the environment of mz_comm_init keeps mode 1). */
 int mz_comm_mode(mz_ctx *ctx);
+/* Which kernels a learner step of `grad_mode` runs on in this context: 0 = fp32 SIMT (bit-exact forward; nn_mode = MZ_NN_FP32_EXACT / MZ_NN_BF16_TC,
+ * or networks the tensor-core learner does not cover), 1 = unroll forward on the tensor cores (MZ_NN_SPLIT_MMA, MZ_GRAD_REFERENCE_L2), 2 = forward and
+ * backward on the tensor cores (MZ_NN_SPLIT_MMA, MZ_GRAD_BPTT: split-precision forward, bf16 backward, gradients within 1e-2 of the largest entry per
+ * network; MUZERO_B200_BPTT_SIMT=1 in the environment forces path 0). */
+int mz_learner_path(mz_ctx *ctx, int grad_mode);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */

@@ -129,6 +129,7 @@ def lib():
         "mz_comm_init": ([ctx, C.c_int, C.c_int, u8p], C.c_int),
         "mz_comm_destroy": ([ctx], C.c_int),
         "mz_comm_mode": ([ctx], C.c_int),
+        "mz_learner_path": ([ctx, C.c_int], C.c_int),
         "mz_launch_count": ([ctx, i64p], C.c_int),
         "mz_kernel_time": ([ctx, C.c_int, C.POINTER(C.c_double), i64p], C.c_int),
         "mz_kernel_time_reset": ([ctx, C.c_int], C.c_int),
@@ -529,6 +530,10 @@ class Context:
 
     def comm_destroy(self):
         self._ck(self.L.mz_comm_destroy(self._h))
+
+    def learner_path(self, grad_mode=GRAD_REFERENCE_L2):
+        """0 = fp32 SIMT kernels, 1 = unroll forward on the tensor cores, 2 = forward + backward on the tensor cores."""
+        return int(self.L.mz_learner_path(self._h, grad_mode))
 
     def comm_mode(self):
         """0 = no communicator, 1 = ncclAllReduce + ADAM kernel, 2 = fused reduction over peer memory + ADAM (mz_k_dp_adam)."""

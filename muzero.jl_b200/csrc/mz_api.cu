@@ -12,6 +12,7 @@
 #include "mz_rn_host.h"
 #include "mz_kernels_rn.cuh"
 #include "mz_kernels_sp.cuh"
+#include "mz_learner_tc.cuh"
 
 namespace {
 
@@ -71,6 +72,9 @@ struct mz_ctx {
     // data-parallel learner over peer memory (mz_k_dp_adam): gradient exchange buffers (double-buffered) and arrival flags of every rank
     float *d_xgrad = nullptr; uint32_t *d_xflags = nullptr; float *peer_grad[MZ_DP_MAX_RANKS] = {}; uint32_t *peer_flags[MZ_DP_MAX_RANKS] = {};
     bool p2p = false; uint32_t dp_step = 0;
+    // MZ_GRAD_BPTT on the tensor cores (mz_learner_tc.cuh): backward rounds, saved activation / gradient tiles, per-chunk partial gradients
+    mz_lr_plan lrp{}; mz_lr_bround *d_brounds = nullptr; unsigned char *d_xsave = nullptr, *d_dzsave = nullptr; float *d_gpart_tc = nullptr;
+    int lr_tiles_cap = 0, lr_chunks_cap = 0; size_t smem_bytes_lr = 0;
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
@@ -251,7 +255,7 @@ int ensure_images(mz_ctx *c) {
         a.mode = 1; a.image = c->d_w_tc; a.bias = c->d_bias_tc;
         for (int i = 0; i < P.n_layers; i++) { a.off[i] = P.tc_a_off[i]; a.bytes[i] = 0; a.bias_off[i] = P.tc_bias_off[i]; }
     } else { c->img_version = c->w_version; return MZ_OK; }
-    { launch_scope ls(c, 5); mz_k_pack_images<<<P.n_layers, 256, 0, c->stream>>>(P, a); }
+    { launch_scope ls(c, 5); mz_k_pack_images<<<dim3((unsigned)P.n_layers, 4), 256, 0, c->stream>>>(P, a); }
     MZ_CUDA(c, cudaGetLastError());
     c->img_version = c->w_version;
     return MZ_OK;
@@ -263,7 +267,40 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
-    if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
+    if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) {
+        // forward + backward on the tensor cores (mz_learner_tc.cuh): kernel 1 = unroll forward + dX chain with saved tiles, kernel 2 = dW / db
+        MZ_TRY(ensure_images(c));
+        const mz_lr_plan &L = c->lrp;
+        const int chunks = tiles < 16 ? tiles : 16;
+        if (tiles > c->lr_tiles_cap) {
+            if (c->d_xsave) cudaFree(c->d_xsave);
+            if (c->d_dzsave) cudaFree(c->d_dzsave);
+            c->d_xsave = c->d_dzsave = nullptr; c->lr_tiles_cap = 0;
+            const size_t bytes = (size_t)tiles * L.slots_per_cta * MZ_SP_TILE_BYTES;
+            MZ_CUDA(c, cudaMalloc((void **)&c->d_xsave, bytes)); MZ_CUDA(c, cudaMalloc((void **)&c->d_dzsave, bytes));
+            MZ_CUDA(c, cudaMemsetAsync(c->d_xsave, 0, bytes, c->stream)); MZ_CUDA(c, cudaMemsetAsync(c->d_dzsave, 0, bytes, c->stream));
+            c->lr_tiles_cap = tiles;
+        }
+        if (chunks > c->lr_chunks_cap) {
+            if (c->d_gpart_tc) cudaFree(c->d_gpart_tc);
+            c->d_gpart_tc = nullptr; c->lr_chunks_cap = 0;
+            MZ_CUDA(c, dmalloc(&c->d_gpart_tc, (size_t)chunks * P.total_floats));
+            MZ_CUDA(c, cudaMemsetAsync(c->d_gpart_tc, 0, (size_t)chunks * P.total_floats * sizeof(float), c->stream));
+            c->lr_chunks_cap = chunks;
+        }
+        mz_lr_args t{}; t.sp = c->spa; t.sp.pbc_smem = 0; t.brounds = c->d_brounds;
+        for (int n = 0; n < 3; n++) {
+            t.bfirst[n] = L.bfirst[n]; t.bn_rounds[n] = L.bn_rounds[n]; t.slot_base[n] = L.slot_base[n]; t.layers_in_net[n] = L.layers_in_net[n]; t.first_layer[n] = P.nets[n].first;
+            for (int h = 0; h < 2; h++) { t.start_tile[n][h] = L.start_tile[n][h]; t.start_layer[n][h] = L.start_layer[n][h]; t.start_perm[n][h] = L.start_perm[n][h]; }
+        }
+        t.btotal_rounds = L.btotal_rounds; t.slots_per_cta = L.slots_per_cta; t.n_eval = L.n_eval; t.lg_off = (L.bwarea_bytes + 127) & ~127; t.dh_extra = mz_lr_alias_fits(c->spp.bias_floats, P.hidden_pad) ? 0 : 1;
+        t.f.f = a; t.xsave = c->d_xsave; t.dzsave = c->d_dzsave; t.dbg = getenv("MUZERO_B200_LR_STAMPS") ? c->d_stats + 4 : nullptr;
+        { launch_scope ls(c, 3); mz_k_learn_bptt_tc<<<tiles, MZ_SP_THREADS, c->smem_bytes_lr, c->stream>>>(P, t); }
+        mz_dw_args d{}; d.xsave = c->d_xsave; d.dzsave = c->d_dzsave; d.gpart = c->d_gpart_tc; d.tiles = tiles; d.chunks = chunks; d.slots_per_cta = L.slots_per_cta; d.n_eval = L.n_eval;
+        for (int n = 0; n < 3; n++) { d.slot_base[n] = L.slot_base[n]; d.layers_in_net[n] = L.layers_in_net[n]; d.first_layer[n] = P.nets[n].first; }
+        { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, 0, c->stream>>>(P, d); }
+        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
+    } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
         if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT needs more shared memory per CTA than the device allows for this network");
         if (tiles > c->bptt_tiles_cap) {
             if (c->d_act) cudaFree(c->d_act);
@@ -283,8 +320,9 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2) {
         launch_scope ls(c, 3); mz_k_learn_forward<<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
     } else return fail(c, MZ_E_ARG, "unknown grad_mode %d", grad_mode);
-    { launch_scope ls(c, 3); mz_k_loss_rows<<<(B + 127) / 128, 128, 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
-    { launch_scope ls(c, 3); mz_k_loss_reduce<<<1, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
+    { launch_scope ls(c, 3); const int ry = P.K + 1 < MZ_LOSS_RY ? P.K + 1 : MZ_LOSS_RY;
+      mz_k_loss_rows<<<(B + 31) / 32, dim3(32, (unsigned)ry), 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
+    { launch_scope ls(c, 3); mz_k_loss_reduce<<<7, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
     MZ_CUDA(c, cudaGetLastError());
     return MZ_OK;
 }
@@ -431,6 +469,16 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
             A.image = c->d_w_sp; A.bias = c->d_bias_sp; A.rounds = c->d_rounds_sp;
             for (int n = 0; n < 3; n++) { A.first[n] = S.first[n]; A.n_rounds[n] = S.n_rounds[n]; A.set_first[n] = S.set_first[n]; A.n_sets[n] = S.n_sets[n]; }
             A.total_rounds = S.total_rounds; A.total_sets = S.total_sets; A.warea_bytes = S.warea_bytes; A.bias_floats = S.bias_floats; A.pbc_smem = S.pbc_smem;
+            // the learner's backward rounds on the same machinery
+            mzh::build_lr_plan(P, S, c->lrp);
+            c->smem_bytes_lr = mz_lr_smem_bytes(S.warea_bytes, S.bias_floats, S.total_rounds, c->lrp.btotal_rounds, P.hidden_pad);
+            if (c->lrp.ok && (c->smem_bytes_lr + 64 > (size_t)prop.sharedMemPerBlockOptin ||
+                              ((c->lrp.bwarea_bytes + 127) & ~127) + c->lrp.n_eval * MZ_LR_LG_ROWS * MZ_ROWS * 4 > S.warea_bytes || P.A > 16)) c->lrp.ok = 0;
+            if (c->lrp.ok) {
+                MZ_CREATE(allow_max_smem(mz_k_learn_bptt_tc, prop));
+                MZ_CREATE(cudaMalloc((void **)&c->d_brounds, sizeof(mz_lr_bround) * MZ_LR_MAX_ROUNDS));
+                MZ_CREATE(cudaMemcpy(c->d_brounds, c->lrp.bround, sizeof(mz_lr_bround) * MZ_LR_MAX_ROUNDS, cudaMemcpyHostToDevice));
+            }
         } else if (cfg->nn_mode == MZ_NN_SPLIT_MMA) {
             int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA: the networks do not fit the shared memory of this device (%zu B per CTA)", (size_t)prop.sharedMemPerBlockOptin);
             mz_destroy(c); return r;
@@ -481,7 +529,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); }
-    void *ptrs[] = {c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -1294,6 +1342,13 @@ int mz_comm_destroy(mz_ctx *c) {
     c->rank = 0; c->nranks = 1;
     return MZ_OK;
 }
+// which kernels a learner step of `grad_mode` runs on in this context: 0 = fp32 SIMT (mz_k_learn_forward / mz_k_learn_bptt), 1 = the unroll forward
+// on the tensor cores (mz_k_learn_forward_sp), 2 = forward and backward on the tensor cores (mz_k_learn_bptt_tc + mz_k_learn_dw)
+int mz_learner_path(mz_ctx *c, int grad_mode) {
+    if (!c || c->cfg.net_type != MZ_NET_FEEDFORWARD || c->cfg.nn_mode != MZ_NN_SPLIT_MMA) return 0;
+    if (grad_mode == MZ_GRAD_BPTT) return (c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) ? 2 : 0;
+    return 1;
+}
 // 0 = no communicator, 1 = ncclAllReduce + mz_k_adam, 2 = mz_k_dp_adam over peer memory (NVLink loads, fused with the update)
 int mz_comm_mode(mz_ctx *c) { if (!c) return 0; return c->p2p ? 2 : c->comm ? 1 : 0; }
 
@@ -1316,6 +1371,8 @@ int mz_kernel_time(mz_ctx *c, int family, double *ms, int64_t *launches) {
 }
 int mz_phase_cycles(mz_ctx *c, uint64_t out[60]) {   // only meaningful in a -DMZ_PHASE_TIMERS build
     if (!c || !out) return fail(c, MZ_E_ARG, "NULL");
+    MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 60; i++) out[i] = (uint64_t)c->h_stats[4 + i];
     return MZ_OK;
 }

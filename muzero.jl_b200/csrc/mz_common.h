@@ -225,6 +225,43 @@ MZ_HD size_t mz_sp_smem_bytes(int warea_bytes, int bias_floats, int total_rounds
 }
 
 // ------------------------------------------------------------------------------------------------
+// Learner on the tensor cores (grad_mode = MZ_GRAD_BPTT with nn_mode = MZ_NN_SPLIT_MMA; mz_learner_tc.cuh).  32 samples per CTA.
+//   forward   the rounds of mz_sp_plan (split precision); every round also stores the hi tile of each job's INPUT to global memory
+//             (TMA bulk store): X[slot], slot = slot_base[net] + evaluation * layers(net) + (layer - first layer of net)
+//   backward  per evaluation, last to first: dX = W^T dZ through BACKWARD ROUNDS (the hi weight block read as an M-major A operand,
+//             bf16 operands), relu mask from X[slot], the result is the previous layer's dZ tile; every round stores its dZ input
+//             tiles: dZ[slot].  The first layers of the two heads accumulate into one accumulator (the trunk output's gradient).
+//   weights   a second kernel computes dW[layer] = sum over (CTA, evaluation) dZ[slot] X[slot]^T with the samples as the K dimension.
+// ------------------------------------------------------------------------------------------------
+#define MZ_LR_MAX_ROUNDS 40
+struct mz_lr_bjob {
+    int32_t a_off[2];                               // weight-area offsets of the hi blocks (two for the merge of the heads' first layers, else [1] = -1)
+    int32_t f32_off;                                // first layer of a network: float offset of the fp32 input gradient in the output area, else -1
+    int16_t layer[2];                               // the layer(s) whose input gradient this job computes
+    int16_t src_tile[2], dst_tile;                  // 4 KB tiles of the group (0..5): dZ of layer[i]; dst = dZ of the layer below (-1: none)
+    int16_t ks[2];                                  // k-steps = ceil(out / 16) of layer[i]
+    int16_t rows;                                   // real rows of the result = inputs of layer[0]
+    int16_t mask;                                   // 1: multiply by (X[slot of layer[0]] > 0) (the layer below ends in relu)
+    int16_t perm;                                   // column order of the src tiles (= the forward tile order of layer[0]'s input)
+    int16_t discard;                                // 1: the result is not needed (first layer of the representation): no MMA, only the dZ store
+    int16_t pad_;
+};
+struct mz_lr_bround {
+    mz_lr_bjob job[2];
+    mz_sp_copy copy[4];                             // this round's hi weight blocks
+    int16_t njobs, ncopy, set, next, per_pass, ord, pad_[2];
+};
+struct mz_lr_plan {
+    int32_t ok, n_eval, slots_per_cta;
+    int32_t slot_base[3], layers_in_net[3];
+    int32_t bfirst[3], bn_rounds[3];                // backward rounds per network
+    int32_t bset_first[3], bn_sets[3], btotal_rounds, btotal_sets, bwarea_bytes;
+    int32_t start_tile[3][2], start_layer[3][2], start_perm[3][2];   // where the loss / hidden-state gradients are staged: tile, layer (-1: none), column order
+    int32_t fwd_perm[MZ_MAX_LAYERS];                // column order of every layer's forward input tile
+    mz_lr_bround bround[MZ_LR_MAX_ROUNDS];
+};
+
+// ------------------------------------------------------------------------------------------------
 // Learner backward pass (grad_mode = MZ_GRAD_BPTT): host-built program of backward layer applications.
 // One CTA = 32 samples; group 0 walks the prediction rows (and finally the representation), group 1 the
 // dynamics steps, in lock-step "steps" separated by CTA barriers (see mz_learner_bptt.cuh).

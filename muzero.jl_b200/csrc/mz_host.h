@@ -403,6 +403,97 @@ inline void pack_weights_sp(const mz_params &P, const mz_sp_plan &S, const float
     }
 }
 
+// ---- learner on the tensor cores: backward rounds (mz_learner_tc.cuh) ------------------------------------------------------------
+inline mz_lr_bjob lr_bjob(const mz_params &P, const mz_lr_plan &L, int l0, int src0, int l1, int src1, int dst, int f32_off, int rows, int mask, int discard) {
+    mz_lr_bjob j; memset(&j, 0, sizeof(j));
+    j.a_off[0] = 0; j.a_off[1] = -1; j.f32_off = f32_off;
+    j.layer[0] = (int16_t)l0; j.layer[1] = (int16_t)l1; j.src_tile[0] = (int16_t)src0; j.src_tile[1] = (int16_t)src1; j.dst_tile = (int16_t)dst;
+    j.ks[0] = (int16_t)((P.layers[l0].out + 15) / 16); j.ks[1] = (int16_t)(l1 >= 0 ? (P.layers[l1].out + 15) / 16 : 0);
+    j.rows = (int16_t)rows; j.mask = (int16_t)mask; j.perm = (int16_t)L.fwd_perm[l0]; j.discard = (int16_t)discard;
+    return j;
+}
+inline void lr_emit(mz_lr_plan &L, const mz_lr_bjob *j0, const mz_lr_bjob *j1) {
+    if (L.btotal_rounds >= MZ_LR_MAX_ROUNDS) { L.ok = 0; return; }
+    mz_lr_bround &R = L.bround[L.btotal_rounds++];
+    memset(&R, 0, sizeof(R));
+    R.job[0] = *j0; R.njobs = 1;
+    if (j1) { R.job[1] = *j1; R.njobs = 2; }
+}
+// Backward rounds of one network, last layer first.  Six 4 KB tiles per group: head 1 walks tiles 0 <-> 1, head 2 tiles 2 <-> 3 (in
+// lock-step, aligned so that both reach their first layer together), the merged gradient of the trunk output lands in tile 4 and the
+// trunk walks 4 <-> 5.  f32_off: where the gradient w.r.t. the network input goes (-1: not needed -- the representation).
+inline void lr_build_net(const mz_params &P, mz_lr_plan &L, int net, int f32_off, int in_rows) {
+    const mz_net &N = P.nets[net];
+    const int f = N.first, nt = N.n_trunk, n1 = N.n_h1, n2 = N.n_h2;
+    L.bfirst[net] = L.btotal_rounds;
+    auto relu_below = [&](int l) { return l > f && P.layers[(l == f + nt || l == f + nt + n1) ? f + nt - 1 : l - 1].act == MZ_ACT_RELU ? 1 : 0; };
+    int cur;
+    if (n1 == 0) {
+        L.start_tile[net][0] = 0; L.start_layer[net][0] = f + nt - 1; L.start_tile[net][1] = -1; L.start_layer[net][1] = -1;
+        cur = 0;
+    } else {
+        const int fa = f + nt, fb = fa + n1;
+        L.start_tile[net][0] = 0; L.start_layer[net][0] = fa + n1 - 1; L.start_tile[net][1] = 2; L.start_layer[net][1] = fb + n2 - 1;
+        if (L.fwd_perm[fa] != L.fwd_perm[fb]) L.ok = 0;
+        int ca = 0, cb = 2;
+        const int la = n1 - 1, lb = n2 - 1, maxl = la > lb ? la : lb;
+        for (int i = 0; i < maxl; i++) {
+            const bool ha = i >= maxl - la, hb = i >= maxl - lb;
+            mz_lr_bjob ja, jb;
+            if (ha) { const int l = fa + n1 - 1 - (i - (maxl - la)); ja = lr_bjob(P, L, l, ca, -1, -1, ca ^ 1, -1, P.layers[l].in, relu_below(l), 0); ca ^= 1; }
+            if (hb) { const int l = fb + n2 - 1 - (i - (maxl - lb)); jb = lr_bjob(P, L, l, cb, -1, -1, cb == 2 ? 3 : 2, -1, P.layers[l].in, relu_below(l), 0); cb = cb == 2 ? 3 : 2; }
+            if (ha && hb) lr_emit(L, &ja, &jb); else lr_emit(L, ha ? &ja : &jb, nullptr);
+        }
+        mz_lr_bjob jm = lr_bjob(P, L, fa, ca, fb, cb, 4, -1, P.layers[fa].in, relu_below(fa), 0);
+        lr_emit(L, &jm, nullptr);
+        cur = 4;
+    }
+    for (int i = nt - 1; i >= 1; i--) {
+        const int d = n1 == 0 ? (cur ^ 1) : (cur == 4 ? 5 : 4);
+        mz_lr_bjob j = lr_bjob(P, L, f + i, cur, -1, -1, d, -1, P.layers[f + i].in, relu_below(f + i), 0);
+        lr_emit(L, &j, nullptr);
+        cur = d;
+    }
+    { mz_lr_bjob j = lr_bjob(P, L, f, cur, -1, -1, -1, f32_off, in_rows, 0, f32_off < 0 ? 1 : 0); lr_emit(L, &j, nullptr); }
+    L.bn_rounds[net] = L.btotal_rounds - L.bfirst[net];
+    for (int h = 0; h < 2; h++) L.start_perm[net][h] = L.start_layer[net][h] >= 0 ? L.fwd_perm[L.start_layer[net][h]] : 0;
+}
+inline int lr_place(mz_lr_plan &L, const mz_sp_plan &S, int net, int base, int set) {
+    int off = base;
+    for (int r = L.bfirst[net]; r < L.bfirst[net] + L.bn_rounds[net]; r++) {
+        mz_lr_bround &R = L.bround[r];
+        R.set = (int16_t)set; R.next = -1; R.per_pass = 0; R.ord = 0; R.ncopy = 0;
+        for (int j = 0; j < R.njobs; j++) for (int t = 0; t < 2; t++) {
+            const int l = R.job[j].layer[t];
+            if (l < 0 || R.job[j].discard) continue;
+            R.job[j].a_off[t] = off;
+            mz_sp_copy &c = R.copy[R.ncopy++]; c.src_off = S.w_off[l]; c.bytes = S.w_bytes[l]; c.dst_off = off; c.pad_ = 0;
+            off += S.w_bytes[l];
+        }
+    }
+    L.bset_first[net] = set; L.bn_sets[net] = 1;
+    return off - base;
+}
+// dh buffers of the backward pass: float offsets in the learner kernel's gradient area ([feature][MZ_SP_OS], hidden_pad rows each)
+inline void build_lr_plan(const mz_params &P, const mz_sp_plan &S, mz_lr_plan &L) {
+    memset(&L, 0, sizeof(L));
+    L.ok = S.ok;
+    if (!L.ok) return;
+    L.n_eval = P.K > 0 ? P.K : 1;
+    for (int n = 0; n < 3; n++) L.layers_in_net[n] = P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2;
+    L.slot_base[0] = 0; L.slot_base[1] = L.layers_in_net[0]; L.slot_base[2] = L.slot_base[1] + L.n_eval * L.layers_in_net[1];
+    L.slots_per_cta = L.slot_base[2] + L.n_eval * L.layers_in_net[2];
+    for (int r = 0; r < S.total_rounds; r++) for (int j = 0; j < S.round[r].njobs; j++) L.fwd_perm[S.round[r].job[j].layer] = S.round[r].job[j].perm;
+    lr_build_net(P, L, 0, -1, P.stack_size);
+    lr_build_net(P, L, 1, 0, P.hidden);                                  // d loss / d h_e through prediction: rows [0, hidden_pad)
+    lr_build_net(P, L, 2, P.hidden_pad * MZ_SP_OS, P.hidden);            // ... through dynamics (the state rows of its input; the action plane's gradient is not needed)
+    if (!L.ok) return;
+    const int pb = lr_place(L, S, 1, 0, 0), db = lr_place(L, S, 2, pb, 1), rb = lr_place(L, S, 0, pb, 2);
+    L.btotal_sets = 3;
+    L.bwarea_bytes = pb + (db > rb ? db : rb);
+    if (L.bwarea_bytes > S.warea_bytes) L.ok = 0;                        // the backward weights (hi blocks only) must fit the forward's weight area
+}
+
 // Flux.glorot_uniform (un-vendored): (rand(Float32,out,in) .- 0.5f0) .* sqrt(24f0/(in+out)); bias zeros.  The reference
 // never seeds it (Constructors.jl:19); contract: element i of layer l of net n = Philox(seed, INIT, n, l, i/4)[i%4].
 inline void init_weights(const mz_params &P, uint64_t seed, float *src) {

@@ -318,12 +318,12 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_nn_forward_sp(const __grid
 }
 
 // ---- tensor-core weight images from the device weights (after every update of d_w: set_weights, ADAM) ----------------------------
-// mode 1: MZ_NN_BF16_TC image (one bf16 block per layer), mode 2: MZ_NN_SPLIT_MMA image (hi block, lo block).  One CTA per layer.
+// mode 1: MZ_NN_BF16_TC image (one bf16 block per layer), mode 2: MZ_NN_SPLIT_MMA image (hi block, lo block).  Grid = (layers, slices).
 struct mz_pack_args { const float *w; unsigned char *image; float *bias; int32_t mode; int32_t off[MZ_MAX_LAYERS], bytes[MZ_MAX_LAYERS], bias_off[MZ_MAX_LAYERS]; };
 __global__ void __launch_bounds__(256) mz_k_pack_images(const __grid_constant__ mz_params P, const __grid_constant__ mz_pack_args a) {
     const mz_layer &l = P.layers[blockIdx.x];
     const int L = blockIdx.x;
-    for (int i = threadIdx.x; i < l.in * l.out; i += 256) {
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < l.in * l.out; i += 256 * gridDim.y) {
         const int k = i / l.out, o = i - k * l.out;
         const float w = a.w[l.w_off + k * l.out_pad + o];
         const uint32_t off = (uint32_t)a.off[L] + mz_tc_tile_offset(o, k);
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256) mz_k_pack_images(const __grid_constant__ 
             *reinterpret_cast<unsigned short *>(a.image + off + a.bytes[L]) = lo;
         } else *reinterpret_cast<unsigned short *>(a.image + off) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
     }
-    for (int o = threadIdx.x; o < l.out; o += 256) a.bias[a.bias_off[L] + o] = a.w[l.b_off + o];
+    if (blockIdx.y == 0) for (int o = threadIdx.x; o < l.out; o += 256) a.bias[a.bias_off[L] + o] = a.w[l.b_off + o];
 }
 
 // ---- learner: the K-step unroll forward (src/Learning.jl:347-370, Q19) with the networks on this path ------------------------------

@@ -139,27 +139,35 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_co
     }
 }
 
-// loss (src/Learning.jl:261-288, Q21): per-sample partial sums, one thread per sample.
-__global__ void mz_k_loss_rows(const __grid_constant__ mz_params P, int B, mz_batch batch, const float *pv, const float *pr, const float *pp,
-                               float *row_v, double *row_r, float *row_p, float *row_invg) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+// loss (src/Learning.jl:261-288, Q21): per-sample partial sums.  Block = 32 samples x up to 16 unroll rows: every (sample, row) term is
+// computed by its own thread, then the sample's thread adds the rows in row order (the same sums as a loop over the rows).
+#define MZ_LOSS_RY 16
+__global__ void __launch_bounds__(32 * MZ_LOSS_RY) mz_k_loss_rows(const __grid_constant__ mz_params P, int B, mz_batch batch, const float *pv, const float *pr, const float *pp,
+                                                                 float *row_v, double *row_r, float *row_p, float *row_invg) {
+    __shared__ float t_v[40][32], t_p[40][32];
+    __shared__ double t_r[40][32];
+    const int b = blockIdx.x * 32 + threadIdx.x;
     const int K1 = P.K + 1, A = P.A;
-    float sv = 0.0f, spol = 0.0f; double sr = 0.0;
-    for (int k = 0; k < K1; k++) {
-        float d = pv[(size_t)b * K1 + k] - batch.values[(size_t)b * K1 + k];
-        sv = sv + d * d;
-        double dr = (double)pr[(size_t)b * K1 + k] - (double)batch.rewards[(size_t)b * K1 + k];
-        sr = sr + dr * dr;
-        const float *p = pp + ((size_t)b * K1 + k) * A, *y = batch.policies + ((size_t)b * K1 + k) * A;
-        float mx = p[0];
-        for (int i = 1; i < A; i++) mx = p[i] > mx ? p[i] : mx;
-        float se = 0.0f;
-        for (int i = 0; i < A; i++) se = se + mz_expf(p[i] - mx);
-        float lse = mz_logf(se), acc = 0.0f;
-        for (int i = 0; i < A; i++) acc = acc + y[i] * ((p[i] - mx) - lse);   // logitcrossentropy on ALREADY softmaxed P
-        spol = spol + (-acc);
+    if (b < B) {
+        for (int k = threadIdx.y; k < K1; k += blockDim.y) {
+            const float d = pv[(size_t)b * K1 + k] - batch.values[(size_t)b * K1 + k];
+            t_v[k][threadIdx.x] = d * d;
+            const double dr = (double)pr[(size_t)b * K1 + k] - (double)batch.rewards[(size_t)b * K1 + k];
+            t_r[k][threadIdx.x] = dr * dr;
+            const float *p = pp + ((size_t)b * K1 + k) * A, *y = batch.policies + ((size_t)b * K1 + k) * A;
+            float mx = p[0];
+            for (int i = 1; i < A; i++) mx = p[i] > mx ? p[i] : mx;
+            float se = 0.0f;
+            for (int i = 0; i < A; i++) se = se + mz_expf(p[i] - mx);
+            float lse = mz_logf(se), acc = 0.0f;
+            for (int i = 0; i < A; i++) acc = acc + y[i] * ((p[i] - mx) - lse);   // logitcrossentropy on ALREADY softmaxed P
+            t_p[k][threadIdx.x] = -acc;
+        }
     }
+    __syncthreads();
+    if (b >= B || threadIdx.y != 0) return;
+    float sv = 0.0f, spol = 0.0f; double sr = 0.0;
+    for (int k = 0; k < K1; k++) { sv = sv + t_v[k][threadIdx.x]; sr = sr + t_r[k][threadIdx.x]; spol = spol + t_p[k][threadIdx.x]; }
     float gs = batch.gscale[b];
     if (P.per && batch.weights) {   // (sum ./ gradient_scale) .* weight_batch (Learning.jl:272-281)
         const float w = batch.weights[b];
@@ -172,7 +180,8 @@ __global__ void __launch_bounds__(1024) mz_k_loss_reduce(const __grid_constant__
                                                           const float *row_p, const float *row_invg, const float *theta, double *out) {
     __shared__ double red[1024];
     const int tid = threadIdx.x;
-    for (int what = 0; what < 7; what++) {
+    // one CTA per quantity (grid = 7): the seven reductions are independent; each keeps its own fixed summation tree
+    for (int what = blockIdx.x; what < 7; what += gridDim.x) {
         double acc = 0.0;
         if (what < 4) {
             for (int i = tid; i < B; i += 1024) acc += what == 0 ? (double)row_v[i] : what == 1 ? (double)row_p[i] : what == 2 ? (double)row_invg[i] : row_r[i];

@@ -228,7 +228,17 @@ __device__ __forceinline__ void mz_sp_wait_mma(uint32_t mbar, uint32_t q) {
 }
 // q = rounds executed by the group so far (parity of its MMA barrier), pass = passes over this network so far (which fill of a weight set a
 // round consumes).  Both functions return the advanced q.
-__device__ __noinline__ uint32_t mz_sp_run_issuer(const mz_sp_ctx C, int first, int count, uint32_t tmem_d, uint32_t mbar, uint32_t q, uint32_t pass, int grp) {
+// TMA bulk store of one 4 KB operand tile to global memory (the learner saves every layer's input for the backward pass)
+__device__ __forceinline__ void mz_sp_store_tile(unsigned char *gdst, uint32_t smem_tile) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_tile), "r"((uint32_t)MZ_SP_TILE_BYTES) : "memory");
+}
+__device__ __forceinline__ void mz_sp_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mz_sp_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mz_sp_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// save / fslot: learner only -- the hi tile of every job's input goes to save + fslot[2 * round + job] * 4 KB (fslot: shared address of an int16 table)
+__device__ __noinline__ uint32_t mz_sp_run_issuer(const mz_sp_ctx C, int first, int count, uint32_t tmem_d, uint32_t mbar, uint32_t q, uint32_t pass, int grp,
+                                                  unsigned char *save = nullptr, uint32_t fslot = 0) {
     uint32_t R = C.prog + (uint32_t)first * MZ_SP_RDESC_BYTES;
     for (int r = 0; r < count; r++, R += MZ_SP_RDESC_BYTES, q++) {
         const uint4 d0 = mz_lds_u4(R), d1 = mz_lds_u4(R + 16), d2 = mz_lds_u4(R + 32), e1 = mz_lds_u4(R + 64), e2 = mz_lds_u4(R + 80);
@@ -250,7 +260,16 @@ __device__ __noinline__ uint32_t mz_sp_run_issuer(const mz_sp_ctx C, int first, 
                     mz_sp_mma(d, al + ka, bh + kb, MZ_SP_IDESC32, 1u);                       // W_lo X_hi          -> columns 0..31
                 }
             }
+            // learner: the commit releases this round's epilogue, which may overwrite tiles the previous round's stores still read
+            if (save) mz_sp_store_wait_read();
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+            if (save) {                                                 // this round's input tiles -> global (they stay untouched until a later round's epilogue)
+                for (int j = 0; j < njobs; j++) {
+                    short sl; asm volatile("ld.shared.s16 %0, [%1];" : "=h"(sl) : "r"(fslot + 2u * (uint32_t)(2 * (first + r) + j)));
+                    mz_sp_store_tile(save + (size_t)sl * MZ_SP_TILE_BYTES, (uint32_t)((j ? d2.z : d2.x) & 0x3fffu) << 4);
+                }
+                mz_sp_store_commit();
+            }
             mz_sp_wait_mma(mbar, q);
             if (next >= 0) mz_sp_fill(C, C.prog + (uint32_t)next * MZ_SP_RDESC_BYTES);      // the round's weights are free: hand the set to its next user
         }

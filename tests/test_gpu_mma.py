@@ -158,3 +158,86 @@ def test_mma_learner_forward_and_stale_image(capi):
     oh = np.stack([O.representation(ocfg, w2, x) for x in st])
     assert np.max(np.abs(h - oh)) <= MMA_ATOL * max(1.0, float(np.max(np.abs(oh))))
     ctx.close(); ex.close()
+
+
+# ---- MZ_GRAD_BPTT on the tensor cores (mz_learner_tc.cuh): forward in split precision, backward with bf16 operands ----------------
+# Stated tolerance: per network, max |g - g_oracle| <= 1e-2 * max |g_oracle| against the oracle's Float64 backward (bf16 operands carry 8
+# mantissa bits; measured 1e-3 .. 3e-3).  The exact fp32 kernel (nn_mode = fp32, tests/test_gpu_parity.py: 2e-5) stays the tight check.
+BPTT_TC_RTOL = 1e-2
+
+
+def _tc_batch(ocfg, blob, B, seed):
+    rng = np.random.default_rng(seed)
+    hist = O.self_play(ocfg, blob, 0, 16, 1.0, 2)
+    c2 = O.Config.from_buffer_copy(ocfg); c2.batch_size = B
+    batch = O.get_batch(c2, hist, step=seed)
+    batch["rewards"] = batch["rewards"] + (rng.standard_normal(batch["rewards"].shape) * 0.3).astype(np.float32)
+    return batch
+
+
+def _tc_check(ocfg, g, og, tol=BPTT_TC_RTOL):
+    nr, npred = O.num_params(ocfg, 0), O.num_params(ocfg, 1)
+    worst = 0.0
+    for lo, hi in ((0, nr), (nr, nr + npred), (nr + npred, g.shape[0])):
+        scale = np.max(np.abs(og[lo:hi]))
+        err = np.max(np.abs(g[lo:hi].astype(np.float64) - og[lo:hi]))
+        assert err <= tol * scale, (lo, hi, err, scale)
+        worst = max(worst, err / scale)
+    return worst
+
+
+@pytest.mark.parametrize("kw,B", [({}, 32), ({"intermediate_rewards": 1}, 77), ({}, 5), ({"num_unroll_steps": 1, "intermediate_rewards": 1}, 40),
+                                  ({"num_unroll_steps": 2}, 33), ({"depth_value": 0, "depth_policy": 2, "depth_reward": 0, "depth_state_head": 1, "intermediate_rewards": 1}, 64),
+                                  ({"width_hidden": 48, "depth_prediction": 1, "depth_dynamics": 0, "depth_representation": 1, "intermediate_rewards": 1}, 100)])
+def test_bptt_on_tensor_cores_matches_oracle(capi, kw, B):
+    ctx, ocfg = make(capi, batch_size=B, **kw)
+    ctx.init_weights(5)
+    rng = np.random.default_rng(8)
+    blob = ctx.get_weights() + (rng.standard_normal(ctx.num_params()) * 0.02).astype(np.float32)
+    ctx.set_weights(blob)
+    batch = _tc_batch(ocfg, blob, B, 3)
+    assert ctx.learner_path(capi.GRAD_BPTT) == 2 and ctx.learner_path(capi.GRAD_REFERENCE_L2) == 1
+    g, losses = ctx.learn_gradients(batch, capi.GRAD_BPTT)
+    _, og = O.learn_gradients(ocfg, blob, batch, fwd64=False)
+    worst = _tc_check(ocfg, g, og)
+    print("tensor-core BPTT, %s, B = %d: worst per-network gradient error %.2e of the network's largest entry" % (kw, B, worst))
+    # the forward of the fused kernel is the forward-only kernel's: same predictions and losses, within 2e-5 of the Float32 oracle
+    pv, pr, pp, l_fwd = ctx.learn_forward(batch)
+    assert np.array_equal(losses, l_fwd)
+    opv, opr, opp, ol = O.learn_forward(ocfg, blob, batch)
+    assert np.max(np.abs(pv - opv)) <= MMA_ATOL and np.max(np.abs(pp - opp)) <= MMA_ATOL and np.allclose(losses, ol, rtol=2e-5)
+    g2, _ = ctx.learn_gradients(batch, capi.GRAD_BPTT)
+    assert np.array_equal(g, g2)                                          # deterministic
+    ctx.close()
+
+
+def test_bptt_on_tensor_cores_large_batch_and_training(capi):
+    ctx, ocfg = make(capi, batch_size=4096, replay_buffer_size=4096)
+    ctx.init_weights(9); blob = ctx.get_weights()
+    small = _tc_batch(ocfg, blob, 32, 4)
+    big = {k: np.concatenate([v] * 128) for k, v in small.items()}
+    gs, _ = ctx.learn_gradients(small, capi.GRAD_BPTT)
+    gb, _ = ctx.learn_gradients(big, capi.GRAD_BPTT)                       # 128 tiles, 16 chunks: the mean gradient of 128 copies is the gradient of one
+    assert np.max(np.abs(gs - gb)) <= 1e-4 * np.max(np.abs(gs))
+    _, og = O.learn_gradients(ocfg, blob, small, fwd64=False)
+    _tc_check(ocfg, gb, og)
+    ctx.close()
+    # the update is ADAM on that gradient, and training lowers the objective (Learning.jl:287)
+    ctx, ocfg = make(capi, num_slots=256, replay_buffer_size=1024, batch_size=256)
+    ctx.init_weights(12)
+    ex = capi.Context(capi.default_config(num_slots=256, replay_buffer_size=1024, batch_size=256)); ex.set_weights(ctx.get_weights())
+    ex.self_play(0, 512, 1.0); ctx.history_import(ex.history_export()); ex.close()
+
+    def objective():
+        _, _, _, l = ctx.learn_forward(ctx.get_batch(999))
+        return float(np.sum(l.astype(np.float64)))
+    before = objective()
+    w0 = ctx.get_weights(); m = np.zeros_like(w0); v = np.zeros_like(w0)
+    b1 = ctx.get_batch(1); g1, _ = ctx.learn_gradients(b1, capi.GRAD_BPTT)
+    ctx.learn_step(1, capi.GRAD_BPTT, b1)
+    O.adam_apply(w0, m, v, g1, 1)
+    assert np.array_equal(ctx.get_weights(), w0)
+    ctx.learn_steps(2, 60, capi.GRAD_BPTT)
+    after = objective()
+    assert np.isfinite(after) and after < 0.5 * before, (before, after)
+    ctx.close()
