@@ -465,7 +465,9 @@ def run_b200(a):
                 fk_ms, fk_n = c_.kernel_time(3)          # family 3: unroll forward (+ backward) + loss kernels
                 c_.kernel_time_reset(False)
                 Bp = c_.cfg.batch_size
-                entry = {"batch_per_gpu": Bp, "ms_per_step": lms_, "unroll_and_loss_kernels_ms_per_step": fk_ms / a.learner_steps}
+                entry = {"batch_per_gpu": Bp, "ms_per_step": lms_, "unroll_and_loss_kernels_ms_per_step": fk_ms / a.learner_steps,
+                         "kernels": {0: "fp32 SIMT (mz_k_learn_forward / mz_k_learn_bptt)", 1: "unroll forward on tcgen05 (mz_k_learn_forward_sp)",
+                                     2: "forward + backward on tcgen05 (mz_k_learn_bptt_tc + mz_k_learn_dw)"}[c_.learner_path(mode)]}
                 if name == "bptt":
                     learner["bptt"] = entry
                 elif name == "large_batch_bptt":
@@ -618,6 +620,12 @@ def run_b200(a):
                 e_["samples_per_s"] = e_["batch_per_gpu"] * world / (e_["ms_per_step"] * 1e-3)      # per-rank time of rank 0; ranks run in lock-step through the allreduce
                 e_["fwd_bwd_flops_per_sample"] = 1913856 if e_ is not learner["large_batch"]["reference_l2"] else 637952
                 e_["tflops"] = e_["fwd_bwd_flops_per_sample"] * e_["samples_per_s"] / 1e12
+            lb = learner["large_batch"]["bptt"]
+            learner["roofline"] = {"bound": "tensor", "kernel": "mz_k_learn_bptt_tc + mz_k_learn_dw" if "tcgen05" in lb["kernels"] else "mz_k_learn_bptt (fp32 SIMT)",
+                                   "achieved": lb["tflops"] / world, "peak": bf16_peak, "unit": "TFLOP/s", "frac": lb["tflops"] / world / bf16_peak,
+                                   "algorithmic_flops_per_sample": lb["fwd_bwd_flops_per_sample"], "batch_per_gpu": 4096,
+                                   "note": "useful forward + backward FLOPs of the K = 5 unroll per sample x samples/s of the whole step (gather, unroll, loss, reduce, ADAM) per GPU; "
+                                           "32 samples per CTA walk a chain of ~140 dependent tensor-core rounds, so the step is latency-bound (DESIGN.md 2.3c)"}
             out["learner"] = learner
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(ocfg, blob, a.cpu_seconds)

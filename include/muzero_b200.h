@@ -39,8 +39,8 @@ enum { MZ_OPP_SELF = 0, MZ_OPP_RANDOM = 1, MZ_OPP_EXPERT = 2 };
  *   MZ_NN_BF16_TC     bf16 operands on tcgen05.mma, fp32 accumulation in TMEM
  *   MZ_NN_SPLIT_MMA   tcgen05.mma at near-Float32 accuracy: both operands split into bf16 hi + lo, W_hi X_hi + W_lo X_hi + W_hi X_lo
  *                     accumulated in fp32 in TMEM; network outputs within ~1e-6 of Float32, visit counts identical to the Float32 oracle
- *                     on > 99 % of roots.  In this mode the learner's unroll forward (MZ_GRAD_REFERENCE_L2) runs on the same path;
- *                     MZ_GRAD_BPTT always computes in fp32. */
+ *                     on > 99 % of roots.  In this mode the learner runs on the same path too (mz_learner_path): the unroll forward in split
+ *                     precision, MZ_GRAD_BPTT's backward with bf16 operands (gradients within 1e-2 of the largest entry per network). */
 enum { MZ_NN_FP32_EXACT = 0, MZ_NN_BF16_TC = 1, MZ_NN_SPLIT_MMA = 2 };
 enum { MZ_NET_FEEDFORWARD = 0, MZ_NET_RESNET = 1 };
 enum { MZ_NET_REPRESENTATION = 0, MZ_NET_PREDICTION = 1, MZ_NET_DYNAMICS = 2, MZ_NET_ALL = 3 };
