@@ -241,8 +241,12 @@ __global__ void __launch_bounds__(256) mz_k_dp_adam(float *theta, float *m, floa
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
+    float pv[MZ_DP_MAX_RANKS];                                          // all remote loads in flight before the first add
+#pragma unroll
+    for (int r = 0; r < MZ_DP_MAX_RANKS; r++) pv[r] = r < a.nranks ? __ldcv(a.peer_grad[r] + i) : 0.0f;
     float g = 0.0f;
-    for (int r = 0; r < a.nranks; r++) g = g + __ldcv(a.peer_grad[r] + i);
+#pragma unroll
+    for (int r = 0; r < MZ_DP_MAX_RANKS; r++) if (r < a.nranks) g = g + pv[r];
     g = g * grad_scale;
     const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
     const float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * (double)g);

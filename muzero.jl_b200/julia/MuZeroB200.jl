@@ -47,7 +47,9 @@ end
 check(e::Engine, rc) = rc == 0 ? nothing : throw(MzError(rc, unsafe_string(ccall((:mz_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx))))
 
 "Build the engine from the reference's `conf::Config` and `hyper::FeedForwardHP` or `hyper::ResNetHP` (src/Constructors.jl:18-90)."
-function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
+# nn_mode: 0 = exact fp32 (bit-identical to the CPU restatement of the reference), 2 = tensor cores at near-Float32 accuracy (bf16 hi + lo
+# operands; > 99 % of the Float32 search decisions at twice the throughput, learner on the tensor cores too), 1 = plain bf16 tensor cores
+function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096, nn_mode::Integer=0)
     c = MzConfig()
     ccall((:mz_default_config, LIB), Cint, (Ref{MzConfig},), c)
     c.W, c.H, c.C = conf.observation_shape
@@ -73,6 +75,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096)
         c.depth_prediction = hyper.depth_prediction; c.depth_dynamics = hyper.depth_dynamics; c.depth_policy = hyper.depth_policy
         c.depth_value = hyper.depth_value; c.depth_reward = hyper.depth_reward; c.depth_state_head = hyper.depth_state_head
         c.hidden_state_size = hyper.hidden_state_size; c.reward_activation_tanh = hyper.reward_activation === tanh
+        c.nn_mode = nn_mode
     end
     c.num_slots = num_slots
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
