@@ -364,7 +364,14 @@ def run_b200(a):
                 e1.record(stream); e1.synchronize()
                 rms += e0.elapsed_time(e1); rsims += s_
             rk_ms, rk_n = ctx_rn.kernel_time(0)
-            rn_extra = (rms, rsims, rk_ms, rk_n, Gr)
+            ctx_rn.kernel_time_reset(False)
+            # learning! on the ResNet networks (the reference's update: unroll in test mode + ADAM on 2*theta), B = 32
+            ctx_rn.learn_steps(1, 2)
+            torch.cuda.synchronize()
+            t0_ = time.perf_counter()
+            ctx_rn.learn_steps(3, 10)
+            rn_learn_ms = (time.perf_counter() - t0_) / 10 * 1e3
+            rn_extra = (rms, rsims, rk_ms, rk_n, Gr, rn_learn_ms)
             ctx_rn.close()
         barrier()
         # ---- BASELINE.json configs[3]: synthetic 6x7 Connect board, 7 actions, ResNet, 200 simulations/move ----
@@ -591,6 +598,7 @@ def run_b200(a):
             out["resnet"] = {"value": rn_sims_all / (rn_ms_max * 1e-3), "unit": UNIT, "ms_per_step": rn_ms_max / a.steps, "dtype": "bf16",
                              "config": {"workload": "TicTacToe ResNet (repaired ResNetHP: 64 filters, 2 blocks, 3x3 representation, 1x1 elsewhere), %d concurrent games x %d simulations/move per GPU, bf16 inference" % (rn_extra[4], S)},
                              "kernel": "mz_k_search_rn<MODE_SLOTS>", "avg_launch_ms": rn_extra[2] / max(rn_extra[3], 1),
+                             "learner_reference_l2_ms_per_step_B32": rn_extra[5],
                              "roofline": {"bound": "tensor", "achieved": rn_tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": rn_tflops / bf16_peak,
                                           "flops_per_simulation": flops_per_sim,
                                           "traffic": (lambda t: t["bytes"] * rn_extra[4] / 8288.0 if t else None)(profiled_traffic("mz_k_search_rn")),

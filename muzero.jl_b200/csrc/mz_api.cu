@@ -72,6 +72,10 @@ struct mz_ctx {
     // data-parallel learner over peer memory (mz_k_dp_adam): gradient exchange buffers (double-buffered) and arrival flags of every rank
     float *d_xgrad = nullptr; uint32_t *d_xflags = nullptr; float *peer_grad[MZ_DP_MAX_RANKS] = {}; uint32_t *peer_flags[MZ_DP_MAX_RANKS] = {};
     bool p2p = false; uint32_t dp_step = 0;
+    // ResNet learner (reference_l2): fp32 parameters in blob order, ADAM moments, gradient, trainable mask, unroll scratch; the bf16 image is
+    // rebuilt from the parameters (rn_dirty) before the next kernel that reads it
+    float *d_rn_theta = nullptr, *d_rn_m = nullptr, *d_rn_v = nullptr, *d_rn_grad = nullptr, *d_rn_h = nullptr, *d_rn_nh = nullptr, *d_rn_sa = nullptr, *d_rn_o1 = nullptr, *d_rn_o2 = nullptr, *d_rn_r = nullptr;
+    unsigned char *d_rn_mask = nullptr, *d_rn_pool = nullptr; int rn_learn_cap = 0; bool rn_dirty = false;
     // MZ_GRAD_BPTT on the tensor cores (mz_learner_tc.cuh): backward rounds, saved activation / gradient tiles, per-chunk partial gradients
     mz_lr_plan lrp{}; mz_lr_bround *d_brounds = nullptr; unsigned char *d_xsave = nullptr, *d_dzsave = nullptr; float *d_gpart_tc = nullptr;
     int lr_tiles_cap = 0, lr_chunks_cap = 0; size_t smem_bytes_lr = 0;
@@ -187,7 +191,9 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
         std::vector<unsigned char> image;
         mzh::rn_pack(c->rn, src.data(), image);
         MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_image, image.data(), (size_t)c->rn.image_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (c->d_rn_theta) MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_theta, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
         MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->rn_dirty = false;
         return MZ_OK;
     }
     std::vector<float> dev((size_t)c->M.P.total_floats);
@@ -197,8 +203,9 @@ int upload_weights(mz_ctx *c, const std::vector<float> &src) {
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
+int rn_sync_image(mz_ctx *c);
 int download_weights(mz_ctx *c, std::vector<float> &src) {
-    if (c->cfg.net_type == MZ_NET_RESNET) { src = c->rn_blob; return MZ_OK; }   // inference-only networks: the blob is kept on the host
+    if (c->cfg.net_type == MZ_NET_RESNET) { const int r_ = rn_sync_image(c); if (r_ != MZ_OK) return r_; src = c->rn_blob; return MZ_OK; }   // the blob is mirrored on the host
     std::vector<float> dev((size_t)c->M.P.total_floats);
     MZ_CUDA(c, cudaMemcpyAsync(dev.data(), c->d_w, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -242,9 +249,24 @@ template <typename T> int d2h(mz_ctx *c, T *host, const T *dev, size_t n) {
 // update reads (the other half may still be read by a peer that is one step behind)
 float *grad_out(mz_ctx *c) { return c->p2p ? c->d_xgrad + (size_t)((c->dp_step + 1u) & 1u) * (size_t)c->M.P.total_floats : c->d_grad; }
 
+// ResNet: after a learner update the device parameters are ahead of the bf16 image: fetch them, fold BatchNorm and re-pack on the host
+// (rn_pack), upload the image.  (A device-side packer would save the round trip; the ResNet learner is a functional path, not a tuned one.)
+int rn_sync_image(mz_ctx *c) {
+    if (!c->rn_dirty) return MZ_OK;
+    MZ_CUDA(c, cudaMemcpyAsync(c->rn_blob.data(), c->d_rn_theta, c->rn_blob.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<unsigned char> image;
+    mzh::rn_pack(c->rn, c->rn_blob.data(), image);
+    MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_image, image.data(), (size_t)c->rn.image_bytes, cudaMemcpyHostToDevice, c->stream));
+    MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->rn_dirty = false;
+    return MZ_OK;
+}
+
 // The tensor-core paths read bf16 images of the weights; whenever d_w has changed (set_weights, an ADAM step) the image of the context's
 // nn_mode is rebuilt on the device before the next kernel that reads it.
 int ensure_images(mz_ctx *c) {
+    if (c->cfg.net_type == MZ_NET_RESNET) return rn_sync_image(c);
     if (c->img_version == c->w_version || c->cfg.net_type != MZ_NET_FEEDFORWARD) return MZ_OK;
     const mz_params &P = c->M.P;
     mz_pack_args a{}; a.w = c->d_w;
@@ -261,9 +283,55 @@ int ensure_images(mz_ctx *c) {
     return MZ_OK;
 }
 
+// ---- ResNet learner (grad_mode = MZ_GRAD_REFERENCE_L2: the reference's actual update, Q20) ---------------------------------------------
+// The K-step unroll (Learning.jl:347-370) as a sequence of the batched network kernel mz_k_rn_forward on device buffers (bf16 inference
+// arithmetic, BatchNorm with its stored statistics: the reference computes the predictions outside the pullback, i.e. in test mode), then
+// the generic loss kernels; the update is ADAM on 2 * theta over Flux.params (mz_k_grad_l2_masked), after which the bf16 image is rebuilt.
+int rn_forward_dev(mz_ctx *c, int net, int B, const float *d_in, float *d_o1, float *d_o2) {
+    mz_search_rn_args t{}; t.image = c->d_rn_image; t.steps = c->d_rn_steps; t.net = net; t.B = B; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2; t.scratch_pool = c->d_rn_pool;
+    const int nt = c->rn.R.ntrees;
+    launch_scope ls(c, 3); mz_k_rn_forward<<<(B + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(c->M.P, c->rn.R, t);
+    return MZ_OK;
+}
+int rn_learn_forward(mz_ctx *c, int B, int grad_mode) {
+    const mz_params &P = c->M.P;
+    if (grad_mode != MZ_GRAD_REFERENCE_L2) return fail(c, MZ_E_UNSUPPORTED, "the ResNet learner implements MZ_GRAD_REFERENCE_L2 (the reference's update); the backward pass through the convolution towers is not built");
+    MZ_TRY(ensure_images(c));
+    if (B > c->rn_learn_cap) {
+        void **ptrs[] = {(void **)&c->d_rn_h, (void **)&c->d_rn_nh, (void **)&c->d_rn_sa, (void **)&c->d_rn_o1, (void **)&c->d_rn_o2, (void **)&c->d_rn_r, (void **)&c->d_rn_pool};
+        for (void **q : ptrs) { if (*q) cudaFree(*q); *q = nullptr; }
+        c->rn_learn_cap = 0;
+        MZ_CUDA(c, dmalloc(&c->d_rn_h, (size_t)B * P.hidden)); MZ_CUDA(c, dmalloc(&c->d_rn_nh, (size_t)B * P.hidden)); MZ_CUDA(c, dmalloc(&c->d_rn_sa, (size_t)B * P.sa_size));
+        MZ_CUDA(c, dmalloc(&c->d_rn_o1, (size_t)B)); MZ_CUDA(c, dmalloc(&c->d_rn_o2, (size_t)B * P.A)); MZ_CUDA(c, dmalloc(&c->d_rn_r, (size_t)B));
+        MZ_CUDA(c, cudaMalloc((void **)&c->d_rn_pool, (size_t)B * c->rn.R.node_bytes + 256));
+        c->rn_learn_cap = B;
+    }
+    const int K1 = P.K + 1, tb = (B + 127) / 128;
+    float *h = c->d_rn_h, *nh = c->d_rn_nh;
+    MZ_TRY(rn_forward_dev(c, 0, B, c->batch.obs, h, nullptr));                                            // :347
+    MZ_TRY(rn_forward_dev(c, 1, B, h, c->d_rn_o1, c->d_rn_o2));                                           // :351 (= row 1's prediction, Q19)
+    { launch_scope ls(c, 3); mz_k_rn_scatter<<<tb, 128, 0, c->stream>>>(B, P.A, K1, 0, P.K > 0 ? 1 : -1, c->d_rn_o1, c->d_rn_o2, nullptr, 1, c->d_pv, c->d_pp, c->d_pr); }
+    for (int i = 1; i <= P.K; i++) {                                                                       // :355-370
+        if (i > 1) {
+            MZ_TRY(rn_forward_dev(c, 1, B, h, c->d_rn_o1, c->d_rn_o2));
+            launch_scope ls(c, 3); mz_k_rn_scatter<<<tb, 128, 0, c->stream>>>(B, P.A, K1, i, -1, c->d_rn_o1, c->d_rn_o2, nullptr, 0, c->d_pv, c->d_pp, c->d_pr);
+        }
+        { launch_scope ls(c, 3); mz_k_rn_make_sa<<<(B * P.sa_size + 255) / 256, 256, 0, c->stream>>>(B, P.hidden, P.cells, P.A, K1, i - 1, h, c->batch.actions, c->d_rn_sa); }
+        MZ_TRY(rn_forward_dev(c, 2, B, c->d_rn_sa, nh, c->d_rn_r));
+        { launch_scope ls(c, 3); mz_k_rn_scatter<<<tb, 128, 0, c->stream>>>(B, P.A, K1, i, -1, nullptr, nullptr, c->d_rn_r, 0, c->d_pv, c->d_pp, c->d_pr); }
+        float *t = h; h = nh; nh = t;
+    }
+    const int ry = K1 < MZ_LOSS_RY ? K1 : MZ_LOSS_RY;
+    { launch_scope ls(c, 3); mz_k_loss_rows<<<(B + 31) / 32, dim3(32, (unsigned)ry), 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
+    { launch_scope ls(c, 3); mz_k_loss_reduce<<<4, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_rn_theta, c->d_lossout, 4); }
+    { launch_scope ls(c, 3); mz_k_rn_sqnorm<<<3, 1024, 0, c->stream>>>(c->rn.base[0], c->rn.base[1], c->rn.base[2], c->M.P.n_params, c->d_rn_theta, c->d_rn_mask, c->d_lossout); }
+    MZ_CUDA(c, cudaGetLastError());
+    return MZ_OK;
+}
+
 int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2) {
     const mz_params &P = c->M.P;
-    if (c->cfg.net_type == MZ_NET_RESNET) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only (the ResNet path is self-play inference)");
+    if (c->cfg.net_type == MZ_NET_RESNET) return rn_learn_forward(c, B, grad_mode);
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
@@ -340,6 +408,23 @@ int finish_losses(mz_ctx *c, int B, float *losses) {
     return MZ_OK;
 }
 int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
+    if (c->cfg.net_type == MZ_NET_RESNET) {   // ADAM on 2 * theta over Flux.params; the BatchNorm statistics have zero gradient and stay put
+        const int n = c->M.P.n_params;
+        if (t == 1 && c->adam_t > 1) { MZ_CUDA(c, cudaMemsetAsync(c->d_rn_m, 0, (size_t)n * 4, c->stream)); MZ_CUDA(c, cudaMemsetAsync(c->d_rn_v, 0, (size_t)n * 4, c->stream)); }
+        if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
+        { launch_scope ls(c, 4); mz_k_grad_l2_masked<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_rn_theta, c->d_rn_mask, c->d_rn_grad); }
+        float scale = 1.0f;
+        if (c->comm) {
+            ncclResult_t r = g_nccl.AllReduce(c->d_rn_grad, c->d_rn_grad, (size_t)n, ncclFloat, ncclSum, c->comm, c->stream);
+            if (r != ncclSuccess) return fail(c, MZ_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+            scale = 1.0f / (float)c->nranks;
+        }
+        { launch_scope ls(c, 4); mz_k_adam<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, mzh::cos_schedule(t), c->bp1, c->bp2, scale); }
+        MZ_CUDA(c, cudaGetLastError());
+        c->bp1 *= 0.9; c->bp2 *= 0.999; c->adam_t++;
+        c->rn_dirty = true;
+        return MZ_OK;
+    }
     const int n = c->M.P.total_floats;
     if (t == 1 && c->adam_t > 1) {   // learning! builds a fresh optimiser (Learning.jl:318): restarting at step 1 clears the moments too
         MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)n * 4, c->stream)); MZ_CUDA(c, cudaMemsetAsync(c->d_v, 0, (size_t)n * 4, c->stream));
@@ -415,6 +500,15 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
         MZ_CREATE(dmalloc(&c->d_rn_steps, c->rn.steps.size() + 1));
         MZ_CREATE(cudaMemcpy(c->d_rn_steps, c->rn.steps.data(), c->rn.steps.size() * sizeof(mz_rn_step), cudaMemcpyHostToDevice));
         c->rn_blob.assign((size_t)c->M.P.n_params, 0.0f);
+        {   // learner state: fp32 parameters (blob order), ADAM moments, gradient, the mask of Flux.params (everything but the BatchNorm statistics)
+            const size_t np = (size_t)c->M.P.n_params;
+            MZ_CREATE(dmalloc(&c->d_rn_theta, np)); MZ_CREATE(dmalloc(&c->d_rn_m, np)); MZ_CREATE(dmalloc(&c->d_rn_v, np)); MZ_CREATE(dmalloc(&c->d_rn_grad, np));
+            MZ_CREATE(cudaMalloc((void **)&c->d_rn_mask, np + 16));
+            MZ_CREATE(cudaMemset(c->d_rn_theta, 0, np * 4)); MZ_CREATE(cudaMemset(c->d_rn_m, 0, np * 4)); MZ_CREATE(cudaMemset(c->d_rn_v, 0, np * 4));
+            std::vector<unsigned char> mask(np, 1);
+            for (int n = 0; n < 3; n++) for (const mzh::rn_unit &u : c->rn.units[n]) if (u.kind == 0) for (int i = 0; i < u.cout; i++) { mask[(size_t)u.mu_off + i] = 0; mask[(size_t)u.var_off + i] = 0; }
+            MZ_CREATE(cudaMemcpy(c->d_rn_mask, mask.data(), np, cudaMemcpyHostToDevice));
+        }
     }
     const mz_params &P = c->M.P;
     c->smem_bytes = resnet ? 0 : mz_smem_bytes(c->M.max_dim, c->M.max_layer_floats, P.hidden_pad, P.S);
@@ -529,7 +623,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); }
-    void *ptrs[] = {c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, c->d_rn_h, c->d_rn_nh, c->d_rn_sa, c->d_rn_o1, c->d_rn_o2, c->d_rn_r, c->d_rn_mask, c->d_rn_pool, c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -1181,6 +1275,12 @@ int mz_learn_gradients_w(mz_ctx *c, int grad_mode, int B, const float *obs_batch
     MZ_TRY(upload_batch(c, B, obs_batch, action_batch, value_batch, reward_batch, policy_batch, gscale));
     if (weight_batch) MZ_CUDA(c, cudaMemcpyAsync(c->batch.weights, weight_batch, (size_t)B * 4, cudaMemcpyHostToDevice, c->stream));
     MZ_TRY(launch_learn_forward(c, B, grad_mode));
+    if (c->cfg.net_type == MZ_NET_RESNET) {   // parameters, and therefore the gradient, are in blob order already
+        const int np = c->M.P.n_params;
+        { launch_scope ls(c, 4); mz_k_grad_l2_masked<<<(np + 255) / 256, 256, 0, c->stream>>>(np, c->d_rn_theta, c->d_rn_mask, c->d_rn_grad); }
+        MZ_CUDA(c, cudaMemcpyAsync(grad, c->d_rn_grad, (size_t)np * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        return finish_losses(c, B, losses);
+    }
     const int n = c->M.P.total_floats;
     if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     std::vector<float> dev((size_t)n), src((size_t)c->M.P.n_params);
@@ -1221,8 +1321,13 @@ int mz_learn_steps(mz_ctx *c, int64_t t0, int n, int grad_mode, float *losses) {
 // Flux.ADAM keeps (mt, vt, beta powers) per parameter array (Learning.jl:318, 395-397); m and v cross the ABI in the blob order.
 int mz_get_optimizer_state(mz_ctx *c, float *m, float *v, int64_t n, int64_t *steps_done) {
     MZ_CHECK_CTX(c);
-    if (c->cfg.net_type != MZ_NET_FEEDFORWARD) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only");
     if (!m || !v || !steps_done || n != c->M.P.n_params) return fail(c, MZ_E_ARG, "bad arguments (need %d floats per moment)", c->M.P.n_params);
+    if (c->cfg.net_type == MZ_NET_RESNET) {   // the ResNet learner keeps its state in blob order
+        MZ_CUDA(c, cudaMemcpyAsync(m, c->d_rn_m, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream)); MZ_CUDA(c, cudaMemcpyAsync(v, c->d_rn_v, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        *steps_done = c->adam_t > 0 ? c->adam_t - 1 : 0;
+        return MZ_OK;
+    }
     std::vector<float> dev((size_t)c->M.P.total_floats);
     for (int which = 0; which < 2; which++) {
         MZ_CUDA(c, cudaMemcpyAsync(dev.data(), which ? c->d_v : c->d_m, dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1234,8 +1339,15 @@ int mz_get_optimizer_state(mz_ctx *c, float *m, float *v, int64_t n, int64_t *st
 }
 int mz_set_optimizer_state(mz_ctx *c, const float *m, const float *v, int64_t n, int64_t steps_done) {
     MZ_CHECK_CTX(c);
-    if (c->cfg.net_type != MZ_NET_FEEDFORWARD) return fail(c, MZ_E_UNSUPPORTED, "the learner is implemented for the FeedForwardHP networks only");
     if (!m || !v || steps_done < 0 || n != c->M.P.n_params) return fail(c, MZ_E_ARG, "bad arguments (need %d floats per moment)", c->M.P.n_params);
+    if (c->cfg.net_type == MZ_NET_RESNET) {
+        MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_m, m, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream)); MZ_CUDA(c, cudaMemcpyAsync(c->d_rn_v, v, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->adam_t = steps_done + 1; c->bp1 = 0.9; c->bp2 = 0.999;
+        for (int64_t i = 0; i < steps_done; i++) { c->bp1 *= 0.9; c->bp2 *= 0.999; }
+        if (steps_done == 0) c->adam_t = 0;
+        return MZ_OK;
+    }
     std::vector<float> dev((size_t)c->M.P.total_floats);
     for (int which = 0; which < 2; which++) {
         mzh::pack_weights(c->M.P, which ? v : m, dev.data());
@@ -1249,6 +1361,11 @@ int mz_set_optimizer_state(mz_ctx *c, const float *m, const float *v, int64_t n,
 }
 int mz_optimizer_reset(mz_ctx *c) {
     MZ_CHECK_CTX(c);
+    if (c->cfg.net_type == MZ_NET_RESNET) {
+        MZ_CUDA(c, cudaMemsetAsync(c->d_rn_m, 0, (size_t)c->M.P.n_params * 4, c->stream)); MZ_CUDA(c, cudaMemsetAsync(c->d_rn_v, 0, (size_t)c->M.P.n_params * 4, c->stream));
+        c->adam_t = 0; c->bp1 = 0.9; c->bp2 = 0.999;
+        return MZ_OK;
+    }
     MZ_CUDA(c, cudaMemsetAsync(c->d_m, 0, (size_t)c->M.P.total_floats * 4, c->stream));
     MZ_CUDA(c, cudaMemsetAsync(c->d_v, 0, (size_t)c->M.P.total_floats * 4, c->stream));
     c->adam_t = 0; c->bp1 = 0.9; c->bp2 = 0.999;

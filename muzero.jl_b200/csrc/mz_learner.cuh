@@ -177,11 +177,11 @@ __global__ void __launch_bounds__(32 * MZ_LOSS_RY) mz_k_loss_rows(const __grid_c
 // deterministic single-CTA tree reductions: out[0] = sum row_v, out[1] = sum row_p, out[2] = sum row_invg, out[3] = sum row_r,
 // out[4..6] = sum(theta^2) per net (double accumulation; compared against the oracle with a stated tolerance)
 __global__ void __launch_bounds__(1024) mz_k_loss_reduce(const __grid_constant__ mz_params P, int B, const float *row_v, const double *row_r,
-                                                          const float *row_p, const float *row_invg, const float *theta, double *out) {
+                                                          const float *row_p, const float *row_invg, const float *theta, double *out, int nwhat = 7) {
     __shared__ double red[1024];
     const int tid = threadIdx.x;
     // one CTA per quantity (grid = 7): the seven reductions are independent; each keeps its own fixed summation tree
-    for (int what = blockIdx.x; what < 7; what += gridDim.x) {
+    for (int what = blockIdx.x; what < nwhat; what += gridDim.x) {   // nwhat = 4: the data terms only (ResNet: mz_k_rn_sqnorm adds the rest)
         double acc = 0.0;
         if (what < 4) {
             for (int i = tid; i < B; i += 1024) acc += what == 0 ? (double)row_v[i] : what == 1 ? (double)row_p[i] : what == 2 ? (double)row_invg[i] : row_r[i];
@@ -254,4 +254,42 @@ __global__ void __launch_bounds__(256) mz_k_dp_adam(float *theta, float *m, floa
     m[i] = mi; v[i] = vi;
     const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
     theta[i] = theta[i] - delta;
+}
+
+// ---- ResNet learner (reference_l2): glue kernels around the batched network kernel mz_k_rn_forward --------------------------------
+// make_dynamics_input (Learning.jl:293-304) for the (W,H,num_filters) state: sa[b] = [2 * h[b] | action plane = Float32(a) / A]
+__global__ void mz_k_rn_make_sa(int B, int hidden, int cells, int A, int K1, int step, const float *h, const float *actions, float *sa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, sz = hidden + cells;
+    if (i >= B * sz) return;
+    const int b = i / sz, j = i - b * sz;
+    sa[i] = j < hidden ? h[(size_t)b * hidden + j] * 2.0f : actions[(size_t)b * K1 + step] / (float)A;
+}
+// one row of the unroll's predictions: value + policy of prediction(h) into rows `row` (and `row2` if >= 0: rows 0 and 1 share prediction(h_0),
+// Q19) when v != nullptr; the reward of the dynamics step into row `row` when r != nullptr; rzero: rewards of row 0 are 0 (Learning.jl:352)
+__global__ void mz_k_rn_scatter(int B, int A, int K1, int row, int row2, const float *v, const float *pol, const float *r, int rzero, float *pv, float *pp, float *pr) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (v) for (int q = 0; q < 2; q++) {
+        const int rw = q == 0 ? row : row2;
+        if (rw < 0) continue;
+        pv[(size_t)b * K1 + rw] = v[b];
+        for (int k = 0; k < A; k++) pp[((size_t)b * K1 + rw) * A + k] = pol[(size_t)b * A + k];
+    }
+    if (r) pr[(size_t)b * K1 + row] = r[b];
+    if (rzero) pr[(size_t)b * K1] = 0.0f;
+}
+// gradient of sum(abs2, theta) over Flux.params: 2 * theta for conv / dense weights and biases and BatchNorm beta / gamma, 0 for the running statistics
+__global__ void mz_k_grad_l2_masked(int n, const float *theta, const unsigned char *mask, float *grad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = mask[i] ? theta[i] + theta[i] : 0.0f;
+}
+// out[4 + net] = sum of theta^2 over the trainable entries of each network (one CTA per network, double accumulation)
+__global__ void __launch_bounds__(1024) mz_k_rn_sqnorm(int b0, int b1, int b2, int b3, const float *theta, const unsigned char *mask, double *out) {
+    __shared__ double red[1024];
+    const int tid = threadIdx.x, lo = blockIdx.x == 0 ? b0 : blockIdx.x == 1 ? b1 : b2, hi = blockIdx.x == 0 ? b1 : blockIdx.x == 1 ? b2 : b3;
+    double acc = 0.0;
+    for (int i = lo + tid; i < hi; i += 1024) if (mask[i]) { const double t = (double)theta[i]; acc += t * t; }
+    red[tid] = acc; __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) { if (tid < s) red[tid] += red[tid + s]; __syncthreads(); }
+    if (tid == 0) out[4 + blockIdx.x] = red[0];
 }

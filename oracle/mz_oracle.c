@@ -1200,14 +1200,45 @@ static float sqnorm_net(const float *blob, const net_t *n) { /* sum(sqnorm, para
     return total;
 }
 
+/* ResNet: sum(sqnorm, Flux.params(net)) -- Conv weight, bias, BatchNorm beta and gamma, Dense weight and bias; the running statistics
+ * mu / var are not parameters (Flux.trainable(BatchNorm) = (beta, gamma)) */
+static float rn_sqnorm_net(const mzo_config *c, const float *blob, int net) {
+    rn_model_t m; rn_build(c, &m);
+    float total = 0.0f; int first = 1;
+    for (int ui = 0; ui < m.net[net].n; ui++) {
+        const rn_unit_t *u = &m.net[net].u[ui];
+        int offs[4] = {u->w_off, u->b_off, u->beta_off, u->gamma_off}, cnt[4] = {u->k * u->k * u->cin * u->cout, u->cout, u->cout, u->cout};
+        for (int a = 0; a < (u->kind == RN_CONV ? 4 : 2); a++) {
+            float s = 0.0f;
+            for (int i = 0; i < cnt[a]; i++) s = s + blob[offs[a] + i] * blob[offs[a] + i];
+            if (first) { total = s; first = 0; } else total = total + s;
+        }
+    }
+    return total;
+}
+/* 1 where the blob entry is a Flux parameter (what the reference_l2 gradient 2*theta and ADAM touch), 0 for the BatchNorm statistics */
+void mzo_trainable_mask(const mzo_config *c, unsigned char *mask) {
+    int np = mzo_num_params(c, 3);
+    memset(mask, 1, (size_t)np);
+    if (c->net_type != 1) return;
+    rn_model_t m; rn_build(c, &m);
+    for (int n = 0; n < 3; n++) for (int ui = 0; ui < m.net[n].n; ui++) {
+        const rn_unit_t *u = &m.net[n].u[ui];
+        if (u->kind != RN_CONV) continue;
+        for (int i = 0; i < u->cout; i++) { mask[u->mu_off + i] = 0; mask[u->var_off + i] = 0; }
+    }
+}
+
 static void learn_forward_impl(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
                        const float *value_batch, const float *reward_batch, const float *policy_batch, const float *gscale,
                        const float *weights /* PER importance weights (1,B), or NULL: weight_batch = 1.0f0 (:266-268) */,
                        float *pred_values, float *pred_rewards, float *pred_policies, float *losses) {
     model_t m; model_init(&m, c, blob);
-    int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), on = obs_size(c), plane = c->W * c->H;
+    int K = c->num_unroll_steps, K1 = K + 1, A = c->A, ss = stack_size(c), plane = c->W * c->H;
+    int on = c->net_type == 1 ? c->hidden_state_size : obs_size(c);   /* ResNet: the state is the (W,H,num_filters) hidden state itself */
+    static __thread float h[MZO_MAX_HIDDEN], nh[MZO_MAX_HIDDEN], sa[MZO_MAX_HIDDEN + 256];
     for (int b = 0; b < B; b++) {
-        float h[256], nh[256], sa[MZO_MAX_OBS + 64], v, r;
+        float v, r;
         representation(&m, obs_batch + (size_t)b * ss, h);                           /* :347 */
         prediction(&m, h, &v, pred_policies + ((size_t)b * K1) * A);                 /* :351 */
         pred_values[(size_t)b * K1] = v; pred_rewards[(size_t)b * K1] = 0.0f;        /* :352 zeros */
@@ -1254,7 +1285,7 @@ static void learn_forward_impl(const mzo_config *c, const float *blob, int B, co
     float data_loss;
     if (c->intermediate_rewards) data_loss = (float)(((double)value_loss + rsum / (double)B) + (double)policy_loss);
     else data_loss = (value_loss + 0.0f) + policy_loss;
-    for (int n = 0; n < 3; n++) losses[n] = data_loss + sqnorm_net(blob, &m.nets[n]);
+    for (int n = 0; n < 3; n++) losses[n] = data_loss + (c->net_type == 1 ? rn_sqnorm_net(c, blob, n) : sqnorm_net(blob, &m.nets[n]));
 }
 
 void mzo_learn_forward(const mzo_config *c, const float *blob, int B, const float *obs_batch, const float *action_batch,
@@ -1481,7 +1512,10 @@ void mzo_learn_step(const mzo_config *c, float *blob, float *adam_m, float *adam
     } else {
         /* Q20: predictions are computed OUTSIDE Zygote.pullback (Learning.jl:347-374 vs 385-393), so the only
          * parameter-dependent term is sum(sqnorm, params): grad = 2*theta for every array. */
-        for (int i = 0; i < np; i++) grad[i] = blob[i] + blob[i];
+        unsigned char *mask = (unsigned char *)malloc((size_t)np);
+        mzo_trainable_mask(c, mask);
+        for (int i = 0; i < np; i++) grad[i] = mask[i] ? blob[i] + blob[i] : 0.0f;     /* ADAM leaves an entry with zero gradient and zero moments untouched */
+        free(mask);
     }
     adam_update(blob, adam_m, adam_v, grad, np, mzo_cos_schedule(t), t);
     free(pv); free(pr); free(pp); free(grad);

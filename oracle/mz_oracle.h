@@ -164,6 +164,8 @@ void mzo_learn_forward(const mzo_config *cfg, const float *blob, int B, const fl
 /* one learning! iteration on a given batch: eta from the Cos schedule at step t (1-based), gradients
  * per grad_mode, shared ADAM state (m, v float[n_params]; beta powers kept as doubles per net array). */
 double mzo_cos_schedule(int t);
+/* 1 per blob entry that is a Flux parameter, 0 for the BatchNorm running statistics of the ResNet networks (length mzo_num_params(cfg, 3)) */
+void mzo_trainable_mask(const mzo_config *cfg, unsigned char *mask);
 void mzo_learn_step(const mzo_config *cfg, float *blob, float *adam_m, float *adam_v, int t, int grad_mode, int B,
                     const float *obs_batch, const float *action_batch, const float *value_batch,
                     const float *reward_batch, const float *policy_batch, const float *gscale, float *losses);

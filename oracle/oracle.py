@@ -349,3 +349,11 @@ def learn_gradients_w(cfg, blob, batch, fwd64=False, perturb=None, want_grad=Tru
                                        _p(batch["rewards"]), _p(batch["policies"]), _p(batch["gscale"]), _p(batch["weights"]), int(fwd64),
                                        int(idx), float(delta), grad.ctypes.data_as(C.POINTER(C.c_double)) if want_grad else None)
     return loss, grad
+
+
+def trainable_mask(cfg):
+    """1 per blob entry that is a Flux parameter, 0 for the BatchNorm running statistics of the ResNet networks."""
+    n = num_params(cfg, 3)
+    m = np.zeros(n, np.uint8)
+    lib().mzo_trainable_mask(C.byref(cfg), m.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return m

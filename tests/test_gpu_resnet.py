@@ -99,12 +99,57 @@ def test_resnet_self_play_is_well_formed_and_deterministic(capi):
         assert np.array_equal(hs[0][k][o0], hs[1][k][o1]), k
 
 
-def test_resnet_learner_is_refused(capi):
-    ctx, _ = make(capi)
-    ctx.init_weights(1)
-    ctx.self_play(0, 8, 1.0)
-    with pytest.raises(capi.MuZeroB200Error):
-        ctx.learn_step(1)
+def test_resnet_learner_reference_l2(capi):
+    """learning! with the ResNet networks in the reference's own semantics (Q20: the gradient of every Flux parameter is 2 * theta; the BatchNorm
+    statistics are not parameters): the K-step unroll runs as bf16 inference on the tensor cores, so predictions and losses are held to the
+    bf16-emulating oracle with the networks' tolerance, while the update does not depend on the forward pass and must be BIT-exact."""
+    ctx, ocfg = make(capi, batch_size=48)
+    blob = _randomised_blob(ocfg, 11)
+    ctx.set_weights(blob)
+    ctx.self_play(0, 150, 1.0)
+    batch = ctx.get_batch(3)
+    batch.pop("index", None)
+    pv, pr, pp, losses = ctx.learn_forward(batch)
+    O.set_bf16(True)
+    try:
+        opv, opr, opp, ol = O.learn_forward(ocfg, blob, batch)
+    finally:
+        O.set_bf16(False)
+    assert np.max(np.abs(pv - opv)) <= RN_ATOL and np.max(np.abs(pr - opr)) <= RN_ATOL and np.max(np.abs(pp - opp)) <= RN_ATOL
+    assert np.array_equal(pv[:, 0], pv[:, 1]) and np.array_equal(pp[:, 0], pp[:, 1]) and np.all(pr[:, 0] == 0)        # Q19, Learning.jl:352
+    assert np.allclose(losses, ol, rtol=2e-2)
+    # gradient = 2 * theta on Flux.params, 0 on the running statistics
+    mask = O.trainable_mask(ocfg).astype(bool)
+    assert 0 < (~mask).sum() < mask.size
+    g, _ = ctx.learn_gradients(batch, capi.GRAD_REFERENCE_L2)
+    assert np.array_equal(g[mask], (blob + blob)[mask]) and np.all(g[~mask] == 0)
+    # three learning! iterations: weights bit-identical to the oracle's ADAM on that gradient; statistics untouched
+    w = blob.copy(); m = np.zeros_like(w); v = np.zeros_like(w)
+    for t in (1, 2, 3):
+        ctx.learn_step(t, capi.GRAD_REFERENCE_L2, batch)
+        O.learn_step(ocfg, w, m, v, t, batch)
+    got = ctx.get_weights()
+    assert np.array_equal(got, w) and np.array_equal(got[~mask], blob[~mask]) and not np.array_equal(got[mask], blob[mask])
+    # the networks (and the search) now run on the updated weights: the bf16 image was rebuilt
+    st, legal, tp = common.random_stacked(ocfg, 20, seed=2)
+    O.set_bf16(True)
+    try:
+        oh = np.stack([O.representation(ocfg, w, x) for x in st])
+    finally:
+        O.set_bf16(False)
+    h = ctx.representation(st)
+    assert np.max(np.abs(h - oh)) < RN_ATOL * max(1.0, float(np.max(np.abs(oh))))
+    # the library's own sampling path + optimiser checkpoint
+    ctx.learn_steps(4, 2)
+    ck = ctx.checkpoint()
+    assert int(ck["steps_done"]) == 5 and np.all(ck["adam_m"][~mask] == 0) and np.any(ck["adam_m"][mask] != 0)
+    wa = ctx.learn_steps(6, 2); after = ctx.get_weights()
+    ctx.restore(ck)                                                       # weights, moments, step count, replay: the next steps repeat bit for bit
+    wb = ctx.learn_steps(6, 2)
+    assert np.array_equal(ctx.get_weights(), after) and np.array_equal(wa, wb)
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.learn_step(8, capi.GRAD_BPTT, batch)                         # the backward through the convolution towers is not built
+    assert e.value.code == capi.E_UNSUPPORTED
     ctx.close()
 
 
