@@ -233,7 +233,8 @@ int mz_comm_mode(mz_ctx *ctx);
 /* Which kernels a learner step of `grad_mode` runs on in this context: 0 = fp32 SIMT (bit-exact forward; nn_mode = MZ_NN_FP32_EXACT / MZ_NN_BF16_TC,
  * or networks the tensor-core learner does not cover), 1 = unroll forward on the tensor cores (MZ_NN_SPLIT_MMA, MZ_GRAD_REFERENCE_L2), 2 = forward and
  * backward on the tensor cores (MZ_NN_SPLIT_MMA, MZ_GRAD_BPTT: split-precision forward, bf16 backward, gradients within 1e-2 of the largest entry per
- * network; MUZERO_B200_BPTT_SIMT=1 in the environment forces path 0). */
+ * network; MUZERO_B200_BPTT_SIMT=1 in the environment forces path 0), 3 = ResNet networks with MZ_GRAD_REFERENCE_L2 (the unroll runs through the bf16 inference
+ * kernel), -1 = not available (ResNet networks with MZ_GRAD_BPTT). */
 int mz_learner_path(mz_ctx *ctx, int grad_mode);
 
 /* ---- instrumentation --------------------------------------------------------------------------- */

@@ -1460,8 +1460,10 @@ int mz_comm_destroy(mz_ctx *c) {
     return MZ_OK;
 }
 // which kernels a learner step of `grad_mode` runs on in this context: 0 = fp32 SIMT (mz_k_learn_forward / mz_k_learn_bptt), 1 = the unroll forward
-// on the tensor cores (mz_k_learn_forward_sp), 2 = forward and backward on the tensor cores (mz_k_learn_bptt_tc + mz_k_learn_dw)
+// on the tensor cores (mz_k_learn_forward_sp), 2 = forward and backward on the tensor cores (mz_k_learn_bptt_tc + mz_k_learn_dw), 3 = ResNet: unroll
+// through the bf16 inference kernel (mz_k_rn_forward), -1 = not available (ResNet with MZ_GRAD_BPTT)
 int mz_learner_path(mz_ctx *c, int grad_mode) {
+    if (c && c->cfg.net_type == MZ_NET_RESNET) return grad_mode == MZ_GRAD_REFERENCE_L2 ? 3 : -1;
     if (!c || c->cfg.net_type != MZ_NET_FEEDFORWARD || c->cfg.nn_mode != MZ_NN_SPLIT_MMA) return 0;
     if (grad_mode == MZ_GRAD_BPTT) return (c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) ? 2 : 0;
     return 1;

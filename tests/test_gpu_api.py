@@ -153,8 +153,9 @@ def test_new_entry_points_error_behaviour(mz):
     assert rn.representation(np.zeros((0, 63), np.float32)).shape == (0, 576)
     with pytest.raises(capi.MuZeroB200Error):
         rn.reanalyse(key0=1, n=1)
-    with pytest.raises(capi.MuZeroB200Error):
-        rn.checkpoint()
+    ck = rn.checkpoint()                              # the ResNet learner keeps an optimiser state too (reference_l2 semantics)
+    assert int(ck["steps_done"]) == 0 and not ck["adam_m"].any()
+    assert rn.learner_path(capi.GRAD_REFERENCE_L2) == 3 and rn.learner_path(capi.GRAD_BPTT) == -1
     rn.close()
 
 
