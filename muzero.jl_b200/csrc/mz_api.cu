@@ -366,7 +366,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         { launch_scope ls(c, 3); mz_k_learn_bptt_tc<<<tiles, MZ_SP_THREADS, c->smem_bytes_lr, c->stream>>>(P, t); }
         mz_dw_args d{}; d.xsave = c->d_xsave; d.dzsave = c->d_dzsave; d.gpart = c->d_gpart_tc; d.tiles = tiles; d.chunks = chunks; d.slots_per_cta = L.slots_per_cta; d.n_eval = L.n_eval;
         for (int n = 0; n < 3; n++) { d.slot_base[n] = L.slot_base[n]; d.layers_in_net[n] = L.layers_in_net[n]; d.first_layer[n] = P.nets[n].first; }
-        { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, 0, c->stream>>>(P, d); }
+        { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, MZ_DW_STAGES * 2 * MZ_SP_TILE_BYTES + 1024, c->stream>>>(P, d); }
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
         if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT needs more shared memory per CTA than the device allows for this network");
@@ -570,6 +570,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
                               ((c->lrp.bwarea_bytes + 127) & ~127) + c->lrp.n_eval * MZ_LR_LG_ROWS * MZ_ROWS * 4 > S.warea_bytes || P.A > 16)) c->lrp.ok = 0;
             if (c->lrp.ok) {
                 MZ_CREATE(allow_max_smem(mz_k_learn_bptt_tc, prop));
+                MZ_CREATE(allow_max_smem(mz_k_learn_dw, prop));
                 MZ_CREATE(cudaMalloc((void **)&c->d_brounds, sizeof(mz_lr_bround) * MZ_LR_MAX_ROUNDS));
                 MZ_CREATE(cudaMemcpy(c->d_brounds, c->lrp.bround, sizeof(mz_lr_bround) * MZ_LR_MAX_ROUNDS, cudaMemcpyHostToDevice));
             }

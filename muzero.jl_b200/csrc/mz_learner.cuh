@@ -47,21 +47,22 @@ __global__ void __launch_bounds__(64) mz_k_replay_gather(const __grid_constant__
         }
         s_pos = pos; s_T = T; s_ring = ring;
         out.index[2 * b] = (int32_t)key; out.index[2 * b + 1] = pos;
-        const float *rew = r.h_reward + (size_t)ring * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)ring * P.Tmax;
-        const float *rv = (r.reanalysed[ring] ? r.h_rrv : r.h_rv) + (size_t)ring * P.Tmax;   // ReplayBuffer.jl:8
-        const int32_t *act = r.h_action + (size_t)ring * P.Tmax;
-        for (int k = 0; k < K1; k++) {
-            int ci = pos + k; float tv, tr; int a;
-            if (ci < T) { tv = mz_target_value(P, T, rew, tp, rv, ci); tr = rew[ci - 1]; a = act[ci - 1]; }
-            else if (ci == T) { tv = 0.0f; tr = rew[ci - 1]; a = act[ci - 1]; }
-            else { tv = 0.0f; tr = 0.0f; a = 1 + (int)mz_u32_below(mz_philox(P.seed, MZ_STREAM_ABSORB, (uint32_t)step, (uint32_t)b, (uint32_t)k, 0).x, (uint32_t)P.A); }
-            out.values[(size_t)b * K1 + k] = tv; out.rewards[(size_t)b * K1 + k] = tr; out.actions[(size_t)b * K1 + k] = (float)a;
-        }
         int gs = T + 1 - pos; if (P.K < gs) gs = P.K;                      // :212
         out.gscale[b] = (float)gs;
     }
     __syncthreads();
     const int pos = s_pos, T = s_T; const int64_t ring = s_ring;
+    // make_target (:25-50, Q17-Q18): the K + 1 unroll positions are independent of each other: one thread each
+    for (int k = tid; k < K1; k += 64) {
+        const float *rew = r.h_reward + (size_t)ring * P.Tmax; const uint8_t *tp = r.h_to_play + (size_t)ring * P.Tmax;
+        const float *rv = (r.reanalysed[ring] ? r.h_rrv : r.h_rv) + (size_t)ring * P.Tmax;   // ReplayBuffer.jl:8
+        const int32_t *act = r.h_action + (size_t)ring * P.Tmax;
+        int ci = pos + k; float tv, tr; int a;
+        if (ci < T) { tv = mz_target_value(P, T, rew, tp, rv, ci); tr = rew[ci - 1]; a = act[ci - 1]; }
+        else if (ci == T) { tv = 0.0f; tr = rew[ci - 1]; a = act[ci - 1]; }
+        else { tv = 0.0f; tr = 0.0f; a = 1 + (int)mz_u32_below(mz_philox(P.seed, MZ_STREAM_ABSORB, (uint32_t)step, (uint32_t)b, (uint32_t)k, 0).x, (uint32_t)P.A); }
+        out.values[(size_t)b * K1 + k] = tv; out.rewards[(size_t)b * K1 + k] = tr; out.actions[(size_t)b * K1 + k] = (float)a;
+    }
     for (int k = tid; k < P.stack_size; k += 64)                            // :207
         out.obs[(size_t)b * P.stack_size + k] = mz_stacked_value(P, r.h_p1 + (size_t)ring * P.Tmax, r.h_p2 + (size_t)ring * P.Tmax,
                                                                  r.h_action + (size_t)ring * P.Tmax, pos, k);

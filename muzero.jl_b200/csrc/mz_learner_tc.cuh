@@ -440,11 +440,15 @@ struct mz_dw_args {
     int32_t tiles, chunks, slots_per_cta, n_eval;
     int32_t slot_base[3], layers_in_net[3], first_layer[3];
 };
+#define MZ_DW_STAGES 8                             // 8 KB each (dZ tile + X tile); dynamic shared memory
+#define MZ_DW_GROUP 4                              // instances per synchronisation
 __global__ void __launch_bounds__(128) mz_k_learn_dw(const __grid_constant__ mz_params P, const __grid_constant__ mz_dw_args a) {
-    constexpr int NS = 5;                                                             // pipeline stages (8 KB each)
-    __shared__ __align__(1024) unsigned char buf[NS][2][MZ_SP_TILE_BYTES];           // [stage][dZ | X]
+    extern __shared__ __align__(1024) unsigned char mz_smem_dw[];
+    constexpr int NS = MZ_DW_STAGES, GI = MZ_DW_GROUP;
     __shared__ __align__(8) uint64_t full[NS], empty[NS], done;
     __shared__ uint32_t tmem_slot;
+    unsigned char *base = mz_smem_dw + ((1024u - (mz_smem_u32(mz_smem_dw) & 1023u)) & 1023u);
+    auto bufp = [&](int s, int which) { return base + (size_t)(2 * s + which) * MZ_SP_TILE_BYTES; };     // [stage][dZ | X]
     const int L = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x, w = tid >> 5, t = tid & 31;
     const mz_layer &l = P.layers[L];
     const int net = L >= a.first_layer[2] ? 2 : L >= a.first_layer[1] ? 1 : 0;
@@ -468,20 +472,22 @@ __global__ void __launch_bounds__(128) mz_k_learn_dw(const __grid_constant__ mz_
     auto load = [&](int i) {
         const int s = i % NS; size_t off; slot_of(i, off);
         mz_mbar_expect_tx(&full[s], 2 * MZ_SP_TILE_BYTES);
-        mz_bulk_g2s(buf[s][0], a.dzsave + off, MZ_SP_TILE_BYTES, &full[s]);
-        mz_bulk_g2s(buf[s][1], a.xsave + off, MZ_SP_TILE_BYTES, &full[s]);
+        mz_bulk_g2s(bufp(s, 0), a.dzsave + off, MZ_SP_TILE_BYTES, &full[s]);
+        mz_bulk_g2s(bufp(s, 1), a.xsave + off, MZ_SP_TILE_BYTES, &full[s]);
     };
     if (tid == 0) for (int i = 0; i < NS && i < n_inst; i++) load(i);
     float db = 0.0f;                                                                  // thread (o = tid >> 1, half = tid & 1): sum of dZ[o][16 samples]
-    for (int i = 0; i < n_inst; i++) {
-        const int s = i % NS;
-        mz_mbar_wait(&full[s], (uint32_t)(i / NS) & 1u);
-        {   // bias gradient: row sums of the dZ tile (fixed order)
+    for (int i0 = 0; i0 < n_inst; i0 += GI) {
+        const int i1 = i0 + GI < n_inst ? i0 + GI : n_inst;
+        for (int i = i0; i < i1; i++) {
+            const int s = i % NS;
+            mz_mbar_wait(&full[s], (uint32_t)(i / NS) & 1u);
+            // bias gradient: row sums of the dZ tile (fixed order)
             const int o = tid >> 1, hf = tid & 1;
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
                 const int chunk16 = 2 * hf + ch;                                       // logical chunk (8 samples) of row o
-                const uint4 v = *reinterpret_cast<const uint4 *>(buf[s][0] + o * 64 + (((chunk16 ^ (o >> 1)) & 3) << 4));
+                const uint4 v = *reinterpret_cast<const uint4 *>(bufp(s, 0) + o * 64 + (((chunk16 ^ (o >> 1)) & 3) << 4));
                 const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) { db = db + __uint_as_float(u[k] << 16); db = db + __uint_as_float(u[k] & 0xffff0000u); }
@@ -490,11 +496,15 @@ __global__ void __launch_bounds__(128) mz_k_learn_dw(const __grid_constant__ mz_
         __syncthreads();
         if (tid == 0) {
             mz_tc_fence_after();
-            const uint64_t ad = mz_lr_kdesc(mz_smem_u32(buf[s][0])), bd = mz_lr_kdesc(mz_smem_u32(buf[s][1]));
-            for (int k = 0; k < 2; k++) mz_lr_mma(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), MZ_LR_IDESC_DW, (i > 0 || k > 0) ? 1u : 0u);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&empty[s])) : "memory");
-            // refill the stage of the PREVIOUS instance (its MMAs have had a whole iteration to complete), not this one's
-            if (i >= 1 && i - 1 + NS < n_inst) { const int ps = (i - 1) % NS; mz_mbar_wait(&empty[ps], (uint32_t)((i - 1) / NS) & 1u); load(i - 1 + NS); }
+            for (int i = i0; i < i1; i++) {
+                const int s = i % NS;
+                const uint64_t ad = mz_lr_kdesc(mz_smem_u32(bufp(s, 0))), bd = mz_lr_kdesc(mz_smem_u32(bufp(s, 1)));
+                for (int k = 0; k < 2; k++) mz_lr_mma(tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), MZ_LR_IDESC_DW, (i > 0 || k > 0) ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mz_smem_u32(&empty[s])) : "memory");
+            }
+            // refill the stages of the PREVIOUS group (its MMAs have had a whole group to complete), not this one's
+            for (int i = i0 - GI; i >= 0 && i < i0; i++)
+                if (i + NS < n_inst) { const int ps = i % NS; mz_mbar_wait(&empty[ps], (uint32_t)(i / NS) & 1u); load(i + NS); }
         }
     }
     if (tid == 0) {
