@@ -11,10 +11,12 @@ from muzero_jl_b200 import capi
 
 ROUNDS = int(os.environ.get("ROUNDS", 8)); GAMES = int(os.environ.get("GAMES", 4096)); STEPS = int(os.environ.get("STEPS", 50))
 BATCH = int(os.environ.get("BATCH", 1024)); LR = float(os.environ.get("LR", 0.003)); S = int(os.environ.get("S", 50))
-kw = dict(num_slots=4096, num_iters=S, replay_buffer_size=20000, batch_size=BATCH, lr_init=LR, training_steps=ROUNDS * STEPS)
+NN = {"fp32": capi.NN_FP32_EXACT, "split": capi.NN_SPLIT_MMA, "tc": capi.NN_BF16_TC}[os.environ.get("NN", "fp32")]   # split: search and learner on the tensor cores
+kw = dict(num_slots=4096, num_iters=S, replay_buffer_size=20000, batch_size=BATCH, lr_init=LR, training_steps=ROUNDS * STEPS, nn_mode=NN)
 cfg = capi.default_config(**{k: v for k, v in kw.items() if hasattr(capi.default_config(), k)})
 train = capi.Context(cfg); train.init_weights(1337)
-arena = capi.Context(capi.default_config(num_slots=2048, num_iters=S, replay_buffer_size=4096))
+arena = capi.Context(capi.default_config(num_slots=2048, num_iters=S, replay_buffer_size=4096, nn_mode=NN))
+print("nn_mode", os.environ.get("NN", "fp32"), "learner path", train.learner_path(capi.GRAD_BPTT))
 
 
 def evaluate(tag):
