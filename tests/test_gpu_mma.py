@@ -241,3 +241,27 @@ def test_bptt_on_tensor_cores_large_batch_and_training(capi):
     after = objective()
     assert np.isfinite(after) and after < 0.5 * before, (before, after)
     ctx.close()
+
+
+def test_bptt_on_tensor_cores_with_per_weights(capi):
+    """conf.PER on the tensor-core learner: the importance weights enter the loss and its gradient (Learning.jl:272-281); gradient against the
+    oracle's weighted Float64 backward within the stated tolerance, losses within 2e-5, and the weights matter."""
+    ctx, ocfg = make(capi, num_slots=64, replay_buffer_size=160, per=1, batch_size=40, intermediate_rewards=1)
+    ctx.init_weights(6)
+    rng = np.random.default_rng(4)
+    blob = ctx.get_weights() + (rng.standard_normal(ctx.num_params()) * 0.02).astype(np.float32)
+    ctx.set_weights(blob)
+    ex = capi.Context(capi.default_config(num_slots=64, replay_buffer_size=160, per=1, batch_size=40, intermediate_rewards=1)); ex.set_weights(blob)
+    ex.self_play(0, 100, 1.0)
+    b = ex.get_batch_per(2); ex.close()
+    b["rewards"] = b["rewards"] + (rng.standard_normal(b["rewards"].shape) * 0.3).astype(np.float32)
+    assert ctx.learner_path(capi.GRAD_BPTT) == 2
+    g, losses = ctx.learn_gradients(b, capi.GRAD_BPTT)
+    _, _, _, ol = O.learn_forward_w(ocfg, blob, b)
+    assert np.allclose(losses, ol, rtol=2e-5)
+    _, og = O.learn_gradients_w(ocfg, blob, b, fwd64=False)
+    _tc_check(ocfg, g, og)
+    b1 = dict(b); b1["weights"] = np.ones_like(b["weights"])
+    g1, l1 = ctx.learn_gradients(b1, capi.GRAD_BPTT)
+    assert not np.array_equal(l1, losses) and not np.array_equal(g1, g)
+    ctx.close()
