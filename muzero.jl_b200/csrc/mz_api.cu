@@ -363,6 +363,8 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         }
         t.btotal_rounds = L.btotal_rounds; t.slots_per_cta = L.slots_per_cta; t.n_eval = L.n_eval; t.lg_off = (L.bwarea_bytes + 127) & ~127; t.dh_extra = mz_lr_alias_fits(c->spp.bias_floats, P.hidden_pad) ? 0 : 1;
         t.f.f = a; t.xsave = c->d_xsave; t.dzsave = c->d_dzsave; t.dbg = getenv("MUZERO_B200_LR_STAMPS") ? c->d_stats + 4 : nullptr;
+        t.inv_g_sum = c->d_lossout + 7;                                    // (slot 7 of the loss scratch is free)
+        { launch_scope ls(c, 3); mz_k_inv_g_sum<<<1, 1024, 0, c->stream>>>(B, c->batch.gscale, (P.per && c->batch.weights) ? c->batch.weights : nullptr, c->d_lossout + 7); }
         { launch_scope ls(c, 3); mz_k_learn_bptt_tc<<<tiles, MZ_SP_THREADS, c->smem_bytes_lr, c->stream>>>(P, t); }
         mz_dw_args d{}; d.xsave = c->d_xsave; d.dzsave = c->d_dzsave; d.gpart = c->d_gpart_tc; d.tiles = tiles; d.chunks = chunks; d.slots_per_cta = L.slots_per_cta; d.n_eval = L.n_eval;
         for (int n = 0; n < 3; n++) { d.slot_base[n] = L.slot_base[n]; d.layers_in_net[n] = L.layers_in_net[n]; d.first_layer[n] = P.nets[n].first; }

@@ -63,7 +63,18 @@ struct mz_lr_args {
     mz_bptt_args f;                                  // batch, predictions (mz_bwd_loss_grad reads a.f)
     unsigned char *xsave, *dzsave;                   // [tiles][slots_per_cta][4 KB]
     unsigned long long *dbg;                         // profiling build: cycle stamps of CTA 0 (thread 0 and thread 128)
+    const double *inv_g_sum;                         // sum_i w_i / g_i over the whole batch (mz_k_inv_g_sum)
 };
+// sum over the batch of (importance weight) / gradient_scale in a fixed order: Q21's mean_i(1/g_i) couples every sample's policy term to it
+__global__ void __launch_bounds__(1024) mz_k_inv_g_sum(int B, const float *gscale, const float *weights, double *out) {
+    __shared__ double red[1024];
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int i = tid; i < B; i += 1024) s += (weights ? (double)weights[i] : 1.0) / (double)gscale[i];
+    red[tid] = s; __syncthreads();
+    for (int k = 512; k > 0; k >>= 1) { if (tid < k) red[tid] += red[tid + k]; __syncthreads(); }
+    if (tid == 0) out[0] = red[0];
+}
 #ifdef MZ_PHASE_TIMERS
 #define MZ_LSTAMP(i) do { if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 128)) { const long long c_ = clock64(); a.dbg[(tid ? 16 : 0) + (i)] += (unsigned long long)(c_ - lt_); lt_ = c_; } } while (0)
 #else
@@ -226,7 +237,6 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_learn_bptt_tc(const __grid
         // the hidden-state gradients live where the forward kept its biases and fp32 outputs (free once the forward is over)
         ls.dhp = a.dh_extra ? reinterpret_cast<float *>(c + 4096 + 128) : sp.bias; ls.dhd = ls.dhp + (size_t)P.hidden_pad * MZ_SP_OS; ls.dh = ls.dhd + (size_t)P.hidden_pad * MZ_SP_OS;
     }
-    double *s_red = ls.red;
     const uint32_t tmem_base = mz_sp_setup(sp, A, MZ_SP_THREADS);
     mz_sp_ctx C; C.prog = mz_smem_u32(sp.prog); C.image = A.image; C.bars = mz_smem_u32(sp.bars);
     const bool worker = tid < MZ_THREADS;
@@ -270,18 +280,11 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_learn_bptt_tc(const __grid
         ls.bprog[tid] = R;
     }
     if (tid == 0) { for (int i = 0; i < 3; i++) mz_mbar_init(&ls.bbar[i], 1); mz_fence_mbar_init(); }
-    // mean_i(1/g_i) over the whole batch (Q21), the same fixed-order sum in every CTA
-    {
-        double s = 0.0;
-        const bool per = P.per && a.f.f.batch.weights;
-        for (int i = tid; i < a.f.f.B; i += MZ_SP_THREADS) s += (per ? (double)a.f.f.batch.weights[i] : 1.0) / (double)a.f.f.batch.gscale[i];
-        s_red[tid] = s;
-    }
     __syncthreads();
-    if (tid == 0) { double s = 0.0; for (int i = 0; i < MZ_SP_THREADS; i++) s += s_red[i]; s_red[0] = s; }
-    __syncthreads();
+    // mean_i(1/g_i) over the whole batch (Q21): one sum for all CTAs (mz_k_inv_g_sum)
+    double *s_red = ls.red; (void)s_red;
     const float invB = 1.0f / (float)a.f.f.B;
-    const float up_pol = (float)(s_red[0] / (double)a.f.f.B / (double)a.f.f.B);
+    const float up_pol = (float)(a.inv_g_sum[0] / (double)a.f.f.B / (double)a.f.f.B);
 #ifdef MZ_PHASE_TIMERS
     long long lt_ = clock64();
 #endif
