@@ -391,8 +391,8 @@ def run_b200(a):
             cn_extra = (e0.elapsed_time(e1), cs_, ck_ms, ck_n, Gc, Sc, cm_)
             ctx_cn.close()
         barrier()
-        # ---- steady state: the same 4096 slots kept busy -- a finished game's slot is refilled with the next game at once (what self_play! does when it
-        #      is asked for more games than there are slots), so the last plies of a wave no longer run on a thinning set of trees ----
+        # ---- several waves per call: 4 x G games on the same G slots in ONE self_play call (what self_play! does when it is asked for more games
+        #      than there are slots).  New games start when every slot is free, so all trees of a launch are at the same ply ----
         flush.zero_(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -571,8 +571,8 @@ def run_b200(a):
                                                 "note": "whole-launch average incl. the tree phases; inside the network phase the wavefront pipe is the bound "
                                                         "(64 wavefront-cycles vs 32 FMA-cycles per k step), which caps the FMA pipe at 50 %"}
         out["steady_state"] = {"value": steady_sims_all / (steady_ms_max * 1e-3), "unit": UNIT, "games": 4 * G * world, "moves": steady[2],
-                               "note": "one self_play call of 4 x %d games per GPU on the same %d slots: finished slots are refilled at once, so all slots stay busy until the "
-                                       "last games run out; `value` above plays exactly %d games per step, whose last plies run on a thinning set of trees" % (G, G, G)}
+                               "note": "one self_play call of 4 x %d games per GPU on the same %d slots (four waves back to back inside the library, no host work in "
+                                       "between); `value` above plays exactly %d games per step" % (G, G, G)}
         if strong and strong_ms_max > 0:
             out["strong_scaling"] = {"value": strong_sims_all / (strong_ms_max * 1e-3), "unit": UNIT, "ms_per_step": strong_ms_max / a.steps,
                                      "games_total": strong[2] * world, "games_per_gpu": strong[2],

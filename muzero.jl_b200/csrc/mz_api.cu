@@ -79,6 +79,7 @@ struct mz_ctx {
     // MZ_GRAD_BPTT on the tensor cores (mz_learner_tc.cuh): backward rounds, saved activation / gradient tiles, per-chunk partial gradients
     mz_lr_plan lrp{}; mz_lr_bround *d_brounds = nullptr; unsigned char *d_xsave = nullptr, *d_dzsave = nullptr; float *d_gpart_tc = nullptr;
     int lr_tiles_cap = 0, lr_chunks_cap = 0; size_t smem_bytes_lr = 0;
+    int refill_wave_sync = 1;   // 1: mz_k_save_refill starts new games only when every slot is free (default; MUZERO_B200_REFILL=immediate refills at once)
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
     double *d_pbc0 = nullptr, *d_sqrtN = nullptr;
@@ -490,6 +491,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     cudaDeviceProp prop; MZ_CREATE(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); mz_destroy(c); return r; }
     c->sm_count = prop.multiProcessorCount;
+    if (const char *rf = getenv("MUZERO_B200_REFILL")) c->refill_wave_sync = !strcmp(rf, "wave") ? 1 : 0;
     const bool resnet = cfg->net_type == MZ_NET_RESNET;
     if (resnet) {
         if (const char *er = mzh::rn_build(*cfg, c->M.P, c->rn)) { int r = fail(nullptr, MZ_E_ARG, "%s", er); mz_destroy(c); return r; }
@@ -853,7 +855,7 @@ int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32
 // ---- self-play ---------------------------------------------------------------------------------------------
 // save_game + refill: number the finished games and hand out new ones (one CTA, ordered), copy their histories (many CTAs), priorities
 static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally) {
-    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally); }
+    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally, c->refill_wave_sync); }
     { launch_scope ls(c, 1); mz_k_save_copy<<<c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
     if (P.per) { launch_scope ls(c, 1); mz_k_save_per<<<(G + 255) / 256 < c->sm_count ? (G + 255) / 256 : c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
     return MZ_OK;

@@ -465,7 +465,7 @@ __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n,
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
 #define MZ_SAVE_MAX_K 64   // slots per thread of mz_k_save_refill: num_slots <= 65536
 #define MZ_FIN_KEY(n) (((n) + 3) & ~1)   // fin_list[n] = number of games; the 64-bit first key - 1 sits at the next 8-byte aligned pair (fin_list has n + 6 entries)
-__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr) {
+__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr, int wave_sync = 0) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ int active_count;
     __shared__ long long add_steps, add_samples;
@@ -513,19 +513,22 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
     __syncthreads();
     // (3) hand the next game ids to the free slots, in slot order; reset! (game.jl:15-20).  The board before move 0 is empty in every
     //     history, so h_p1 / h_p2 [g][0] stay zero.
+    //     wave_sync: new games start only when EVERY slot is free, so that all trees of a launch are at the same ply (a launch lasts as
+    //     long as its deepest tree, and late plies search deeper: mixing plies makes every launch as slow as the last plies')
+    const bool hand_out = !wave_sync || total_free == n_slots;
     int nact = 0, free_rank = free_rank0;
     for (int i = 0; lo + i < hi; i++) {
         const int g = lo + i;
         if ((free_bits >> i) & 1ull) {
             const int64_t id = next_game + free_rank++;
-            if (id < end_game) { s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1; nact++; }
+            if (hand_out && id < end_game) { s.game_id[g] = id; s.status[g] = MZ_SLOT_ACTIVE; s.T[g] = 0; s.p1[g] = 0; s.p2[g] = 0; s.player[g] = 1; nact++; }
             else s.status[g] = MZ_SLOT_IDLE;
         } else nact++;                                                     // neither finished nor idle: active
     }
     if (nact) atomicAdd(&active_count, nact);
     __syncthreads();
     if (tid == 0) {
-        const int64_t handed = next_game + total_free < end_game ? total_free : (end_game - next_game > 0 ? end_game - next_game : 0);
+        const int64_t handed = !hand_out ? 0 : next_game + total_free < end_game ? total_free : (end_game - next_game > 0 ? end_game - next_game : 0);
         r.counters[0] = base_key + total_fin;
         r.counters[1] += add_steps;
         r.counters[2] += add_samples;
