@@ -53,6 +53,30 @@ def test_configs1_4096_slots_50_sims_every_history_bit_exact(capi, eps, temperat
     ctx.close()
 
 
+def test_configs1_split_precision_headline_agrees_with_float32_oracle(capi):
+    """The bench's headline path at the bench's size: 4096 slots x 50 simulations with the networks on tcgen05 (bf16 hi + lo operands),
+    10000 games = 2.4 waves.  Not bit-exact by construction; asserted: every game is played exactly once and is well formed, the counters
+    are right, >= 99.5 % of first plies and >= 98 % of whole games are identical to the FLOAT32 oracle's (measured 99.95 % / 99.3 %)."""
+    G, S, games, first = 4096, 50, 10000, 7000
+    ctx = capi.Context(capi.default_config(num_slots=G, num_iters=S, replay_buffer_size=16384, nn_mode=capi.NN_SPLIT_MMA))
+    ocfg = common.oracle_config(ctx.cfg)
+    ctx.init_weights(1337); blob = ctx.get_weights()
+    sims, moves = ctx.self_play(first, games, 1.0)
+    o = O.self_play(ocfg, blob, first, games, 1.0, 16)
+    h = ctx.history_export()
+    assert sorted(h["game_id"].tolist()) == list(range(first, first + games)) and sims == moves * S and moves == int(h["T"].sum())
+    same_first = same_game = 0
+    for j in range(games):
+        i = int(h["game_id"][j]) - first
+        same_first += int(np.array_equal(h["child_visits"][j, 0], o["child_visits"][i, 0]))
+        same_game += int(all(np.array_equal(h[k][j], o[k][i]) for k in ("T", "obs", "actions", "rewards", "to_play", "child_visits")))
+    print("split-precision headline config: %.4f of %d first plies, %.4f of whole games identical to the Float32 oracle" % (same_first / games, games, same_game / games))
+    assert same_first >= 0.995 * games and same_game >= 0.98 * games
+    c = ctx.replay_counters()
+    assert c[0] == games and c[1] == moves
+    ctx.close()
+
+
 def test_configs2_resnet_16384_slots_sampled_games_agree_with_bf16_oracle(capi):
     """BASELINE.json configs[2]: 16384 concurrent ResNet games (bf16 tcgen05).  A sample of the games is replayed by the bf16-emulating
     oracle; the executor accumulates in a different order, so agreement is a rate: stated and asserted."""
