@@ -26,7 +26,7 @@ extern "C" {
 #endif
 
 #define MZ_MAX_A 16
-#define MZ_ABI_VERSION 6
+#define MZ_ABI_VERSION 7
 
 enum { MZ_OK = 0, MZ_E_ARG = -1, MZ_E_CUDA = -2, MZ_E_STATE = -3, MZ_E_NCCL = -4, MZ_E_UNSUPPORTED = -5 };
 enum { MZ_GAME_TICTACTOE = 0, MZ_GAME_CONNECT = 1 };
@@ -90,6 +90,11 @@ typedef struct mz_config {
     /* conf.temperature_threshold (src/Constructors.jl:31): play_game switches to temperature 0 once
      * length(history.action_history) >= threshold (src/SelfPlay.jl:344-346); -1 = nothing (the default) */
     int32_t temperature_threshold;
+    /* FeedForwardHP.use_batch_norm (src/Constructors.jl:71): make_dense = Chain(Dense(in, out), BatchNorm(out, relu)) (src/Learning.jl:70-79).
+     * BatchNorm runs in test mode everywhere (the reference never differentiates a forward pass and never calls trainmode!).  Exact-fp32
+     * path only: the tensor-core modes and MZ_GRAD_BPTT answer MZ_E_UNSUPPORTED.  Blob: such a layer's W, b are followed by
+     * beta[out], gamma[out] (Flux.params order) and the running statistics mu[out], sigma2[out] (not parameters: ADAM leaves them alone). */
+    int32_t use_batch_norm;
 } mz_config;
 
 typedef struct mz_ctx mz_ctx;

@@ -105,8 +105,8 @@ class GameHistory:
 def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.GAME_TICTACTOE, tie_mode=capi.TIE_PHILOX,
                  child_order=None, nn_mode=capi.NN_FP32_EXACT):
     resnet = isinstance(hyper, ResNetHP)
-    if not resnet and hyper.use_batch_norm:
-        raise NotImplementedError("use_batch_norm=true is not supported (default false, Constructors.jl:71)")
+    if not resnet and hyper.use_batch_norm and nn_mode != capi.NN_FP32_EXACT:
+        raise NotImplementedError("use_batch_norm=true (Constructors.jl:71) runs on the exact fp32 path only: nn_mode must be NN_FP32_EXACT")
     if list(conf.action_space) != list(range(1, len(conf.action_space) + 1)):
         raise ValueError("action_space must be 1:A")
     c = capi.default_config()
@@ -150,6 +150,7 @@ def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.G
                   "depth_reward", "depth_state_head", "hidden_state_size"):
             setattr(c, k, getattr(hyper, k))
         c.reward_activation_tanh = 1 if hyper.reward_activation in ("tanh", np.tanh) else 0
+        c.use_batch_norm = 1 if hyper.use_batch_norm else 0          # make_dense = Dense + BatchNorm(relu), Learning.jl:70-79
     c.temperature_threshold = -1 if conf.temperature_threshold is None else int(conf.temperature_threshold)   # SelfPlay.jl:344-346
     c.per = 1 if conf.PER else 0          # repaired specification of the prioritised replay
     c.per_alpha = int(conf.PER_alpha)

@@ -46,7 +46,7 @@ class MzConfig(C.Structure):
         ("reward_activation_tanh", C.c_int32), ("num_slots", C.c_int32), ("nn_mode", C.c_int32),
         ("net_type", C.c_int32), ("rn_num_blocks", C.c_int32), ("rn_num_filters", C.c_int32), ("rn_kernel", C.c_int32),
         ("rn_first_head_filters", C.c_int32), ("rn_second_head_filters", C.c_int32),
-        ("per", C.c_int32), ("per_alpha", C.c_int32), ("temperature_threshold", C.c_int32),
+        ("per", C.c_int32), ("per_alpha", C.c_int32), ("temperature_threshold", C.c_int32), ("use_batch_norm", C.c_int32),
     ]
 
     def copy(self):

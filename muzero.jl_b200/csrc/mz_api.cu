@@ -12,6 +12,7 @@
 #include "mz_rn_host.h"
 #include "mz_kernels_rn.cuh"
 #include "mz_kernels_sp.cuh"
+#include "mz_kernels_lat.cuh"
 #include "mz_learner_tc.cuh"
 
 namespace {
@@ -79,6 +80,11 @@ struct mz_ctx {
     // MZ_GRAD_BPTT on the tensor cores (mz_learner_tc.cuh): backward rounds, saved activation / gradient tiles, per-chunk partial gradients
     mz_lr_plan lrp{}; mz_lr_bround *d_brounds = nullptr; unsigned char *d_xsave = nullptr, *d_dzsave = nullptr; float *d_gpart_tc = nullptr;
     int lr_tiles_cap = 0, lr_chunks_cap = 0; size_t smem_bytes_lr = 0;
+    // mz_k_search_lat (one tree per 2-CTA cluster, networks and tree resident in shared memory): calls with at most lat_max_roots roots
+    unsigned char *d_fc_mask = nullptr; int fc_net_bounds[4] = {0, 0, 0, 0};   // use_batch_norm: 1 = Flux parameter, 0 = BatchNorm statistics (padded device blob); network boundaries
+    float *d_w_lat = nullptr; uint64_t lat_version = 0; int lat_image_floats = 0;
+    unsigned char *h_lat_stage = nullptr, *d_lat_stage = nullptr; size_t lat_stage_cap = 0;   // one pinned / device block for all inputs and outputs of a small run_mcts call
+    bool lat_ok = false; int lat_w_floats = 0, lat_pbc_smem = 0, lat_max_roots = 0, lat_max_slots = 0; size_t smem_bytes_lat = 0;
     int refill_wave_sync = 1;   // 1: mz_k_save_refill starts new games only when every slot is free (default; MUZERO_B200_REFILL=immediate refills at once)
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
@@ -284,6 +290,19 @@ int ensure_images(mz_ctx *c) {
     return MZ_OK;
 }
 
+// the weight image of mz_k_search_lat (rows = outputs), rebuilt from the device weights when they have changed since it was last used
+int ensure_lat_image(mz_ctx *c) {
+    if (c->lat_version == c->w_version) return MZ_OK;
+    const mz_params &P = c->M.P;
+    mz_pack_lat_args a{}; a.w = c->d_w; a.image = c->d_w_lat;
+    int off = 0;
+    for (int n = 0; n < 3; n++) for (int l = P.nets[n].first; l < P.nets[n].first + P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2; l++) { a.off[l] = off; off += mz_lat_layer_floats(P.layers[l].in, P.layers[l].out); }
+    { launch_scope ls(c, 5); mz_k_pack_lat<<<dim3((unsigned)P.n_layers, 4), 256, 0, c->stream>>>(P, a); }
+    MZ_CUDA(c, cudaGetLastError());
+    c->lat_version = c->w_version;
+    return MZ_OK;
+}
+
 // ---- ResNet learner (grad_mode = MZ_GRAD_REFERENCE_L2: the reference's actual update, Q20) ---------------------------------------------
 // The K-step unroll (Learning.jl:347-370) as a sequence of the batched network kernel mz_k_rn_forward on device buffers (bf16 inference
 // arithmetic, BatchNorm with its stored statistics: the reference computes the predictions outside the pullback, i.e. in test mode), then
@@ -372,6 +391,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, MZ_DW_STAGES * 2 * MZ_SP_TILE_BYTES + 1024, c->stream>>>(P, d); }
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
+        if (c->cfg.use_batch_norm) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for use_batch_norm networks (the reference's own update, MZ_GRAD_REFERENCE_L2, is)");
         if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT needs more shared memory per CTA than the device allows for this network");
         if (tiles > c->bptt_tiles_cap) {
             if (c->d_act) cudaFree(c->d_act);
@@ -393,7 +413,10 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     } else return fail(c, MZ_E_ARG, "unknown grad_mode %d", grad_mode);
     { launch_scope ls(c, 3); const int ry = P.K + 1 < MZ_LOSS_RY ? P.K + 1 : MZ_LOSS_RY;
       mz_k_loss_rows<<<(B + 31) / 32, dim3(32, (unsigned)ry), 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
-    { launch_scope ls(c, 3); mz_k_loss_reduce<<<7, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
+    if (c->d_fc_mask) {   // use_batch_norm: sum(theta^2) over Flux.params leaves out the BatchNorm statistics
+        { launch_scope ls(c, 3); mz_k_loss_reduce<<<4, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout, 4); }
+        { launch_scope ls(c, 3); mz_k_rn_sqnorm<<<3, 1024, 0, c->stream>>>(c->fc_net_bounds[0], c->fc_net_bounds[1], c->fc_net_bounds[2], c->fc_net_bounds[3], c->d_w, c->d_fc_mask, c->d_lossout); }
+    } else { launch_scope ls(c, 3); mz_k_loss_reduce<<<7, 1024, 0, c->stream>>>(P, B, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg, c->d_w, c->d_lossout); }
     MZ_CUDA(c, cudaGetLastError());
     return MZ_OK;
 }
@@ -434,7 +457,7 @@ int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
     }
     if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
     // MZ_GRAD_BPTT: d_grad was produced by launch_learn_forward (mz_k_learn_bptt + mz_k_grad_reduce)
-    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); if (c->d_fc_mask) mz_k_grad_l2_masked<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_fc_mask, grad_out(c)); else mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     float scale = 1.0f;
     if (c->p2p) {    // data-parallel over peer memory: ONE kernel waits for the peers' gradients, sums them in rank order over NVLink and applies ADAM
         mz_dp_args d{}; d.rank = c->rank; d.nranks = c->nranks; d.step = ++c->dp_step; d.n = n; d.flags_local = c->d_xflags;
@@ -483,6 +506,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (cfg->nn_mode != MZ_NN_FP32_EXACT && cfg->nn_mode != MZ_NN_BF16_TC && cfg->nn_mode != MZ_NN_SPLIT_MMA) { int r = fail(nullptr, MZ_E_ARG, "unknown nn_mode %d", cfg->nn_mode); delete c; return r; }
     if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
     if (cfg->nn_mode == MZ_NN_SPLIT_MMA && (cfg->net_type != MZ_NET_FEEDFORWARD || !c->M.P.tc_ok)) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA needs the FeedForwardHP networks with every layer in <= 64 and out <= 64"); delete c; return r; }
+    if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->use_batch_norm && cfg->nn_mode != MZ_NN_FP32_EXACT) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "use_batch_norm runs on the exact fp32 path only (nn_mode = MZ_NN_FP32_EXACT)"); delete c; return r; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }
@@ -525,6 +549,25 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
     MZ_CREATE(allow_max_smem(mz_k_reanalyse, prop));
     MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
+    if (!resnet) {   // the low-latency search kernel for few roots: does a network pair fit one SM's shared memory in fp32?
+        int nf[3] = {0, 0, 0}; bool narrow = true;
+        for (int n = 0; n < 3; n++) for (int l = P.nets[n].first; l < P.nets[n].first + P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2; l++) {
+            nf[n] += mz_lat_layer_floats(P.layers[l].in, P.layers[l].out); if (P.layers[l].out > MZ_LAT_HALF) narrow = false;
+            if (P.layers[l].in > MZ_LAT_KMAX && l != P.nets[n].first) narrow = false;   // only a network's first layer may be wider than 64 inputs
+        }
+        c->lat_image_floats = nf[0] + nf[1] + nf[2];
+        c->lat_w_floats = nf[0] + nf[1] > nf[2] ? nf[0] + nf[1] : nf[2];
+        c->lat_pbc_smem = 1;
+        c->smem_bytes_lat = mz_lat_smem_bytes(c->lat_w_floats, c->M.max_dim, P.hidden_pad, P.tree_stride_bytes, P.S, 1);
+        if (c->smem_bytes_lat + 1024 > (size_t)prop.sharedMemPerBlockOptin) { c->lat_pbc_smem = 0; c->smem_bytes_lat = mz_lat_smem_bytes(c->lat_w_floats, c->M.max_dim, P.hidden_pad, P.tree_stride_bytes, P.S, 0); }
+        c->lat_ok = narrow && !cfg->use_batch_norm && P.A <= 16 && c->smem_bytes_lat + 1024 <= (size_t)prop.sharedMemPerBlockOptin && (size_t)c->lat_w_floats * 4 < (1u << 20);
+        // run_mcts: two SMs per root.  Measured (profiles/r2j_run_mcts_latency.log): against the exact batched kernel it wins up to two rounds of
+        // clusters, against the split-precision one up to one round
+        c->lat_max_roots = cfg->nn_mode == MZ_NN_FP32_EXACT ? c->sm_count : c->sm_count / 2;
+        c->lat_max_slots = 16;                                           // self-play: contexts built for one or a few games at a time (play_game)
+        if (const char *el = getenv("MUZERO_B200_LAT")) c->lat_max_roots = c->lat_max_slots = atoi(el);   // measurement / test switch; 0 = off
+        if (c->lat_ok) { MZ_CREATE(allow_max_smem(mz_k_search_lat<MZ_MODE_API>, prop)); MZ_CREATE(allow_max_smem(mz_k_search_lat<MZ_MODE_SLOTS>, prop)); MZ_CREATE(dmalloc(&c->d_w_lat, (size_t)c->lat_image_floats + 64)); }
+    }
     if (!resnet) { if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; } }
     c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
     if (!resnet && c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {   // 4 KB head-room for the kernel's static shared memory
@@ -587,6 +630,13 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     const size_t nf = (size_t)P.total_floats;
     MZ_CREATE(dmalloc(&c->d_w, nf)); MZ_CREATE(dmalloc(&c->d_m, nf)); MZ_CREATE(dmalloc(&c->d_v, nf)); MZ_CREATE(dmalloc(&c->d_grad, nf));
     MZ_CREATE(cudaMemset(c->d_w, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_m, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_v, 0, nf * 4));
+    if (!resnet && cfg->use_batch_norm) {   // Flux.params of a BatchNorm are beta and gamma: the running statistics take no part in sum(abs2, theta), its gradient or ADAM
+        std::vector<unsigned char> mask(nf + 16, 1);
+        for (int i = 0; i < P.n_layers; i++) if (P.layers[i].bn) for (int o = 0; o < 2 * P.layers[i].out_pad; o++) mask[(size_t)P.layers[i].b_off + 3 * P.layers[i].out_pad + o] = 0;
+        MZ_CREATE(cudaMalloc((void **)&c->d_fc_mask, nf + 16)); MZ_CREATE(cudaMemcpy(c->d_fc_mask, mask.data(), nf + 16, cudaMemcpyHostToDevice));
+        for (int n = 0; n < 3; n++) c->fc_net_bounds[n] = P.layers[P.nets[n].first].w_off;
+        c->fc_net_bounds[3] = (int)nf;
+    }
     MZ_CREATE(dmalloc(&c->d_pbc0, c->M.pbc0.size())); MZ_CREATE(dmalloc(&c->d_sqrtN, c->M.sqrtN.size()));
     MZ_CREATE(cudaMemcpy(c->d_pbc0, c->M.pbc0.data(), c->M.pbc0.size() * 8, cudaMemcpyHostToDevice));
     MZ_CREATE(cudaMemcpy(c->d_sqrtN, c->M.sqrtN.data(), c->M.sqrtN.size() * 8, cudaMemcpyHostToDevice));
@@ -628,7 +678,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); }
-    void *ptrs[] = {c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, c->d_rn_h, c->d_rn_nh, c->d_rn_sa, c->d_rn_o1, c->d_rn_o2, c->d_rn_r, c->d_rn_mask, c->d_rn_pool, c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_fc_mask, c->d_w_lat, c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, c->d_rn_h, c->d_rn_nh, c->d_rn_sa, c->d_rn_o1, c->d_rn_o2, c->d_rn_r, c->d_rn_mask, c->d_rn_pool, c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,
@@ -637,6 +687,8 @@ int mz_destroy(mz_ctx *c) {
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &b : c->scratch) b.release();
     free_ring(c->play_ring);
+    if (c->h_lat_stage) cudaFreeHost(c->h_lat_stage);
+    if (c->d_lat_stage) cudaFree(c->d_lat_stage);
     if (c->h_counters) cudaFreeHost(c->h_counters);
     if (c->h_wave) cudaFreeHost(c->h_wave);
     for (int i = 0; i < 2; i++) if (c->ev_wave[i]) cudaEventDestroy(c->ev_wave[i]);
@@ -800,6 +852,40 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         if (legal_mask[i] == 0 || (legal_mask[i] >> P.A) != 0) return fail(c, MZ_E_ARG, "legal actions of root %d must be a non-empty subset of the action space (SelfPlay.jl:243-244)", i);
         if (to_play[i] < 1 || to_play[i] > P.P) return fail(c, MZ_E_ARG, "to_play of root %d out of range", i);
     }
+    if (c->lat_ok && n > 0 && n <= c->lat_max_roots && c->cfg.nn_mode != MZ_NN_BF16_TC) {
+        // few roots: one tree per cluster in exact fp32 (mz_kernels_lat.cuh); every input in ONE pinned block and one copy each way -- at
+        // this size the call's latency is what the caller sees (the reference calls run_mcts with one root at a time).  No game can be in
+        // flight here: a wave ends with every slot idle or resets the slots.
+        MZ_TRY(ensure_lat_image(c));
+        auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        const size_t o_st = 0, o_legal = al(o_st + (size_t)n * P.stack_size * 4), o_tp = al(o_legal + (size_t)n * 4), o_gid = al(o_tp + (size_t)n * 4), o_mv = al(o_gid + (size_t)n * 8),
+                     o_vc = al(o_mv + (size_t)n * 4), o_rv = al(o_vc + (size_t)n * P.A * 4), o_pri = al(o_rv + (size_t)n * 4), total = al(o_pri + (size_t)n * P.A * 4);
+        if (total > c->lat_stage_cap) {
+            if (c->h_lat_stage) cudaFreeHost(c->h_lat_stage);
+            if (c->d_lat_stage) cudaFree(c->d_lat_stage);
+            c->h_lat_stage = nullptr; c->d_lat_stage = nullptr; c->lat_stage_cap = 0;
+            const size_t want = (total + 65535) & ~(size_t)65535;
+            MZ_CUDA(c, cudaMallocHost((void **)&c->h_lat_stage, want)); MZ_CUDA(c, cudaMalloc((void **)&c->d_lat_stage, want));
+            c->lat_stage_cap = want;
+        }
+        unsigned char *h = c->h_lat_stage, *d = c->d_lat_stage;
+        memcpy(h + o_st, stacked_obs, (size_t)n * P.stack_size * 4); memcpy(h + o_legal, legal_mask, (size_t)n * 4); memcpy(h + o_tp, to_play, (size_t)n * 4);
+        memcpy(h + o_gid, game_id, (size_t)n * 8); memcpy(h + o_mv, move_idx, (size_t)n * 4);
+        MZ_CUDA(c, cudaMemcpyAsync(d, h, o_vc, cudaMemcpyHostToDevice, c->stream));
+        mz_lat_args t{};
+        mz_search_args &a = t.base; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = n; a.max_dim = c->M.max_dim;
+        a.max_layer_floats = c->M.max_layer_floats; a.exploration = exploration; a.stacked = (const float *)(d + o_st); a.legal = (const uint32_t *)(d + o_legal);
+        a.to_play = (const int32_t *)(d + o_tp); a.game_id = (const uint64_t *)(d + o_gid); a.move_idx = (const int32_t *)(d + o_mv);
+        a.visit_counts = (int32_t *)(d + o_vc); a.root_value = (float *)(d + o_rv); a.root_priors = (float *)(d + o_pri); a.stats = nullptr;
+        t.image = c->d_w_lat; t.w_floats = c->lat_w_floats; t.pbc_smem = c->lat_pbc_smem;
+        { launch_scope ls(c, 0); mz_k_search_lat<MZ_MODE_API><<<2 * n, MZ_LAT_THREADS, c->smem_bytes_lat, c->stream>>>(P, t); }
+        MZ_CUDA(c, cudaGetLastError());
+        MZ_CUDA(c, cudaMemcpyAsync(h + o_vc, d + o_vc, total - o_vc, cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(visit_counts, h + o_vc, (size_t)n * P.A * 4); memcpy(root_value, h + o_rv, (size_t)n * 4);
+        if (root_priors) memcpy(root_priors, h + o_pri, (size_t)n * P.A * 4);
+        return MZ_OK;
+    }
     read_counters(c);
     if (c->h_counters[5] != 0) return fail(c, MZ_E_STATE, "self-play in progress");
     const int cap = c->cfg.num_slots;
@@ -908,7 +994,11 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         if (arena_player != 0) { launch_scope ls(c, 6); mz_k_opponent_move<<<(G + 127) / 128, 128, 0, c->stream>>>(P, c->slots, G); }
-        if (c->cfg.net_type == MZ_NET_RESNET) {
+        if (c->lat_ok && G <= c->lat_max_slots && c->cfg.nn_mode == MZ_NN_FP32_EXACT) {   // few slots (play_game one game at a time): one tree per cluster
+            MZ_TRY(ensure_lat_image(c));
+            mz_lat_args t{}; t.base = a; t.image = c->d_w_lat; t.w_floats = c->lat_w_floats; t.pbc_smem = c->lat_pbc_smem;
+            launch_scope ls(c, 0); mz_k_search_lat<MZ_MODE_SLOTS><<<2 * G, MZ_LAT_THREADS, c->smem_bytes_lat, c->stream>>>(P, t);
+        } else if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
             const int nt = c->rn.R.ntrees;
             launch_scope ls(c, 0); mz_k_search_rn<MZ_MODE_SLOTS><<<(G + nt - 1) / nt, MZ_RN_THREADS, c->smem_bytes_rn, c->stream>>>(P, c->rn.R, t);
@@ -1287,7 +1377,7 @@ int mz_learn_gradients_w(mz_ctx *c, int grad_mode, int B, const float *obs_batch
         return finish_losses(c, B, losses);
     }
     const int n = c->M.P.total_floats;
-    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
+    if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); if (c->d_fc_mask) mz_k_grad_l2_masked<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_fc_mask, grad_out(c)); else mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     std::vector<float> dev((size_t)n), src((size_t)c->M.P.n_params);
     MZ_CUDA(c, cudaMemcpyAsync(dev.data(), grad_out(c), dev.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     MZ_TRY(finish_losses(c, B, losses));

@@ -132,9 +132,12 @@ struct mz_layer {            // one Dense layer in the padded device layout
     int32_t in, out, out_pad, act;
     int32_t w_off, b_off;    // float offsets into the padded device blob (16-byte aligned)
     int32_t src_w_off, src_b_off; // float offsets into the reference-order blob
-    int32_t floats;          // in*out_pad + out_pad: one contiguous bulk copy
-    int32_t pad_;
+    int32_t floats;          // in*out_pad + out_pad (+ 4 * out_pad: BatchNorm): one contiguous bulk copy
+    int32_t bn;              // 1: followed by BatchNorm (FeedForwardHP.use_batch_norm): device block = W | b | beta | gamma | mu | sigma2 (out_pad floats each);
+                             // reference-order blob: W, b, beta[out], gamma[out], mu[out], sigma2[out]
 };
+// BatchNorm in test mode (Flux 0.12.4): gamma .* (x .- mu) ./ sqrt.(sigma2 .+ 1f-5) .+ beta, every operation rounded on its own
+MZ_HD float mz_batchnorm(float v, float beta, float gamma, float mu, float var) { return ((gamma * (v - mu)) / sqrtf(var + 1e-5f)) + beta; }
 struct mz_net {              // trunk + two heads (representation has no heads)
     int32_t n_trunk, n_h1, n_h2, first;  // layers [first, first+n_trunk) trunk, then h1, then h2
 };

@@ -94,8 +94,9 @@ __device__ __forceinline__ void mz_fma_step(unsigned long long (&acc2)[4][2], co
 // y[o][row] = act( sum_k fmaf(W[k][o], x[k][row]) + b[o] ),  activations k-major: x[k*32 + row].
 // SAVE also streams the outputs to global memory in the same k-major [o][32] layout (the learner's backward pass reads
 // them back as the next layer's input activations).
+// bn: the layer is followed by BatchNorm in test mode (FeedForwardHP.use_batch_norm, Learning.jl:70-79); beta | gamma | mu | sigma2 lie behind the bias
 template <bool SAVE>
-__device__ __forceinline__ void mz_dense_tile_body(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid, float *gsave) {
+__device__ __forceinline__ void mz_dense_tile_body(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid, float *gsave, int bn = 0) {
     const int lane = gtid & 31, warp = gtid >> 5;
     const int rg = lane & 7;
     const int opq = out_pad >> 2;
@@ -121,10 +122,17 @@ MZ_UNROLL_K
         }
         const float4 bv = mz_lds128(w_smem + (uint32_t)in * wstride + (uint32_t)g * 16u);
         const float bj[4] = {bv.x, bv.y, bv.z, bv.w};
+        float bnp[4][4];                                           // [beta, gamma, mu, sigma2][j]
+        if (bn) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const float4 t = mz_lds128(w_smem + (uint32_t)(in + 1 + q) * wstride + (uint32_t)g * 16u); bnp[q][0] = t.x; bnp[q][1] = t.y; bnp[q][2] = t.z; bnp[q][3] = t.w; }
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float4 r;
             r.x = acc[0][j] + bj[j]; r.y = acc[1][j] + bj[j]; r.z = acc[2][j] + bj[j]; r.w = acc[3][j] + bj[j];
+            if (bn) { r.x = mz_batchnorm(r.x, bnp[0][j], bnp[1][j], bnp[2][j], bnp[3][j]); r.y = mz_batchnorm(r.y, bnp[0][j], bnp[1][j], bnp[2][j], bnp[3][j]);
+                      r.z = mz_batchnorm(r.z, bnp[0][j], bnp[1][j], bnp[2][j], bnp[3][j]); r.w = mz_batchnorm(r.w, bnp[0][j], bnp[1][j], bnp[2][j], bnp[3][j]); }
             if (act == MZ_ACT_RELU) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); r.z = fmaxf(r.z, 0.0f); r.w = fmaxf(r.w, 0.0f); }
             else if (act == MZ_ACT_TANH) { r.x = mz_tanhf_ni(r.x); r.y = mz_tanhf_ni(r.y); r.z = mz_tanhf_ni(r.z); r.w = mz_tanhf_ni(r.w); }
             mz_sts128(dst_smem + (uint32_t)((4 * g + j) * MZ_ROWS * 4) + (uint32_t)rg * 16u, r);
@@ -136,6 +144,9 @@ MZ_UNROLL_K
 // One copy of each in the binary (noinline): every layer of every network goes through them.
 __device__ __noinline__ void mz_dense_tile(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
     mz_dense_tile_body<false>(in, out_pad, act, w_smem, src_smem, dst_smem, gtid, nullptr);
+}
+__device__ __noinline__ void mz_dense_tile_bn(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid) {
+    mz_dense_tile_body<false>(in, out_pad, act, w_smem, src_smem, dst_smem, gtid, nullptr, 1);
 }
 __device__ __noinline__ void mz_dense_tile_save(int in, int out_pad, int act, uint32_t w_smem, uint32_t src_smem, uint32_t dst_smem, int gtid, float *gsave) {
     mz_dense_tile_body<true>(in, out_pad, act, w_smem, src_smem, dst_smem, gtid, gsave);
@@ -197,7 +208,8 @@ __device__ __forceinline__ void mz_nn_layer(mz_nn_pipe &s, const mz_params &P, i
     if (s.gtid == 0 && next >= 0) mz_nn_issue(s, P, next, (s.q + 1) & 1u);
     mz_mbar_wait(&s.mbar[s.q & 1u], (s.q >> 1) & 1u);
     const mz_layer &L = P.layers[layer];
-    if (GT == 256) mz_dense_tile_g256(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
+    if (L.bn) mz_dense_tile_bn(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);   // (both group sizes: 4 warps do the layer)
+    else if (GT == 256) mz_dense_tile_g256(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
     else mz_dense_tile(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
     mz_group_sync<GT>(s.grp);
     s.q++;

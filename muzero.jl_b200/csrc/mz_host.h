@@ -45,6 +45,7 @@ inline void default_config(mz_config *c) {   // games/tictactoe/params.jl:2-29, 
     c->num_slots = 4096; c->nn_mode = MZ_NN_FP32_EXACT;
     c->per = 0; c->per_alpha = 1;
     c->temperature_threshold = -1;
+    c->use_batch_norm = 0;
     c->net_type = MZ_NET_FEEDFORWARD; c->rn_num_blocks = 2; c->rn_num_filters = 64; c->rn_kernel = 3; c->rn_first_head_filters = 1; c->rn_second_head_filters = 2;
 }
 
@@ -81,12 +82,13 @@ struct model {
     int max_layer_floats;              // largest bulk-copied layer
 };
 
-inline void add_layer(mz_params &P, int in, int out, int act, int &src_off, int &dev_off) {
+// bn: the layer comes from make_dense with use_batch_norm (Learning.jl:70-79): exactly the relu layers
+inline void add_layer(mz_params &P, int in, int out, int act, int &src_off, int &dev_off, bool bn = false) {
     mz_layer &l = P.layers[P.n_layers++];
-    l.in = in; l.out = out; l.out_pad = (out + 3) & ~3; l.act = act;
-    l.src_w_off = src_off; src_off += in * out; l.src_b_off = src_off; src_off += out;
-    l.w_off = dev_off; dev_off += in * l.out_pad; l.b_off = dev_off; dev_off += l.out_pad;
-    l.floats = in * l.out_pad + l.out_pad; l.pad_ = 0;
+    l.in = in; l.out = out; l.out_pad = (out + 3) & ~3; l.act = act; l.bn = bn && act == MZ_ACT_RELU ? 1 : 0;
+    l.src_w_off = src_off; src_off += in * out; l.src_b_off = src_off; src_off += out + (l.bn ? 4 * out : 0);
+    l.w_off = dev_off; dev_off += in * l.out_pad; l.b_off = dev_off; dev_off += l.out_pad * (l.bn ? 5 : 1);
+    l.floats = in * l.out_pad + l.out_pad * (l.bn ? 5 : 1);
 }
 
 inline int count_layers(const mz_config &c) {
@@ -149,25 +151,26 @@ inline const char *build_model(const mz_config &c, model &M) {
     }
     // networks (src/Learning.jl:87-142), Flux.params order
     int src = 0, dev = 0, w = c.width_hidden;
+    const bool bn = c.use_batch_norm != 0;
     P.nets[0].first = P.n_layers;
-    add_layer(P, P.stack_size, w, MZ_ACT_RELU, src, dev);
-    for (int i = 0; i < c.depth_representation; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, P.stack_size, w, MZ_ACT_RELU, src, dev, bn);
+    for (int i = 0; i < c.depth_representation; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
     add_layer(P, w, P.hidden, MZ_ACT_ID, src, dev);
     P.nets[0].n_trunk = c.depth_representation + 2; P.nets[0].n_h1 = 0; P.nets[0].n_h2 = 0;
     P.nets[1].first = P.n_layers;
-    add_layer(P, P.hidden, w, MZ_ACT_RELU, src, dev);
-    for (int i = 0; i < c.depth_prediction; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
-    for (int i = 0; i < c.depth_value; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, P.hidden, w, MZ_ACT_RELU, src, dev, bn);
+    for (int i = 0; i < c.depth_prediction; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
+    for (int i = 0; i < c.depth_value; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
     add_layer(P, w, 1, MZ_ACT_TANH, src, dev);
-    for (int i = 0; i < c.depth_policy; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_policy; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
     add_layer(P, w, c.A, MZ_ACT_ID, src, dev);
     P.nets[1].n_trunk = c.depth_prediction + 1; P.nets[1].n_h1 = c.depth_value + 1; P.nets[1].n_h2 = c.depth_policy + 1;
     P.nets[2].first = P.n_layers;
-    add_layer(P, P.sa_size, w, MZ_ACT_RELU, src, dev);
-    for (int i = 0; i < c.depth_dynamics; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
-    for (int i = 0; i < c.depth_state_head; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    add_layer(P, P.sa_size, w, MZ_ACT_RELU, src, dev, bn);
+    for (int i = 0; i < c.depth_dynamics; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
+    for (int i = 0; i < c.depth_state_head; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
     add_layer(P, w, P.hidden, MZ_ACT_ID, src, dev);
-    for (int i = 0; i < c.depth_reward; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev);
+    for (int i = 0; i < c.depth_reward; i++) add_layer(P, w, w, MZ_ACT_RELU, src, dev, bn);
     add_layer(P, w, 1, c.reward_activation_tanh ? MZ_ACT_TANH : MZ_ACT_ID, src, dev);
     P.nets[2].n_trunk = c.depth_dynamics + 1; P.nets[2].n_h1 = c.depth_state_head + 1; P.nets[2].n_h2 = c.depth_reward + 1;
     P.n_params = src; P.total_floats = dev;
@@ -180,7 +183,7 @@ inline const char *build_model(const mz_config &c, model &M) {
             int first = P.nets[n].first, cnt = P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2;
             for (int i = first; i < first + cnt; i++) {
                 const mz_layer &l = P.layers[i];
-                if (l.in > 64 || l.out > 64) P.tc_ok = 0;
+                if (l.in > 64 || l.out > 64 || l.bn) P.tc_ok = 0;
                 P.tc_a_off[i] = off; P.tc_ksteps[i] = (l.in + 15) / 16; P.tc_bias_off[i] = boff;
                 off += ((l.out + 7) / 8) * 1024; boff += 64;
             }
@@ -200,7 +203,7 @@ inline const char *build_model(const mz_config &c, model &M) {
 inline int net_params(const mz_params &P, int net) {
     if (net == MZ_NET_ALL) return P.n_params;
     int first = P.nets[net].first, n = P.nets[net].n_trunk + P.nets[net].n_h1 + P.nets[net].n_h2, s = 0;
-    for (int i = first; i < first + n; i++) s += P.layers[i].in * P.layers[i].out + P.layers[i].out;
+    for (int i = first; i < first + n; i++) s += P.layers[i].in * P.layers[i].out + P.layers[i].out * (P.layers[i].bn ? 5 : 1);
     return s;
 }
 inline int net_src_offset(const mz_params &P, int net) { return net == MZ_NET_ALL ? 0 : P.layers[P.nets[net].first].src_w_off; }
@@ -212,6 +215,7 @@ inline void pack_weights(const mz_params &P, const float *src, float *dev) {
         const mz_layer &l = P.layers[i];
         for (int k = 0; k < l.in; k++) for (int o = 0; o < l.out; o++) dev[l.w_off + k * l.out_pad + o] = src[l.src_w_off + k * l.out + o];
         for (int o = 0; o < l.out; o++) dev[l.b_off + o] = src[l.src_b_off + o];
+        if (l.bn) for (int j = 0; j < 4; j++) for (int o = 0; o < l.out; o++) dev[l.b_off + (j + 1) * l.out_pad + o] = src[l.src_b_off + (j + 1) * l.out + o];
     }
 }
 inline void unpack_weights(const mz_params &P, const float *dev, float *src) {
@@ -219,6 +223,7 @@ inline void unpack_weights(const mz_params &P, const float *dev, float *src) {
         const mz_layer &l = P.layers[i];
         for (int k = 0; k < l.in; k++) for (int o = 0; o < l.out; o++) src[l.src_w_off + k * l.out + o] = dev[l.w_off + k * l.out_pad + o];
         for (int o = 0; o < l.out; o++) src[l.src_b_off + o] = dev[l.b_off + o];
+        if (l.bn) for (int j = 0; j < 4; j++) for (int o = 0; o < l.out; o++) src[l.src_b_off + (j + 1) * l.out + o] = dev[l.b_off + (j + 1) * l.out_pad + o];
     }
 }
 
@@ -509,6 +514,7 @@ inline void init_weights(const mz_params &P, uint64_t seed, float *src) {
                 for (int j = 0; j < 4 && i + j < nw; j++) src[l.src_w_off + i + j] = (mz_u32_to_unit(rr[j]) - 0.5f) * scale;
             }
             for (int o = 0; o < l.out; o++) src[l.src_b_off + o] = 0.0f;
+            if (l.bn) for (int o = 0; o < l.out; o++) { src[l.src_b_off + l.out + o] = 0.0f; src[l.src_b_off + 2 * l.out + o] = 1.0f; src[l.src_b_off + 3 * l.out + o] = 0.0f; src[l.src_b_off + 4 * l.out + o] = 1.0f; }   // Flux.BatchNorm(out): beta, gamma, mu, sigma2
         }
     }
 }

@@ -164,13 +164,21 @@ void mzo_default_config(mzo_config *c) { /* games/tictactoe/params.jl:2-29; src/
  * Blob layout: nets in order (representation, prediction, dynamics); inside a net the Dense layers
  * in Flux.params order (trunk, then Split path 1, then Split path 2); per layer W (out,in) in
  * Julia column-major (W[o + out*k]) followed by b[out].
+ * FeedForwardHP.use_batch_norm (Constructors.jl:71): make_dense (Learning.jl:70-79) is Chain(Dense(in, out), BatchNorm(out, relu)); such a
+ * layer is followed in the blob by BatchNorm's beta[out], gamma[out] (Flux.trainable(BatchNorm) = (beta, gamma), Flux.params order) and
+ * its running statistics mu[out], sigma2[out] (not parameters).  The reference never differentiates a forward pass (Q20) and never calls
+ * trainmode!, so BatchNorm always runs in test mode: relu.(gamma .* (x .- mu) ./ sqrt.(sigma2 .+ 1f-5) .+ beta) (Flux 0.12.4).
  * ------------------------------------------------------------------------------------------ */
 enum { ACT_ID = 0, ACT_RELU = 1, ACT_TANH = 2 };
-typedef struct { int in, out, act, w_off, b_off; } layer_t;
+typedef struct { int in, out, act, w_off, b_off, bn, beta_off, gamma_off, mu_off, var_off; } layer_t;
 typedef struct { int n_trunk, n_h1, n_h2; layer_t trunk[24], h1[24], h2[24]; int base, n_params; } net_t;
 
+static int g_add_bn = 0;   /* build_net: the layer being added comes from make_dense with use_batch_norm */
 static int add_layer(layer_t *l, int in, int out, int act, int *off) {
     l->in = in; l->out = out; l->act = act; l->w_off = *off; *off += in * out; l->b_off = *off; *off += out;
+    l->bn = g_add_bn && act == ACT_RELU;   /* make_dense layers are exactly the relu layers; the final Dense of every chain has no BatchNorm */
+    l->beta_off = l->gamma_off = l->mu_off = l->var_off = 0;
+    if (l->bn) { l->beta_off = *off; *off += out; l->gamma_off = *off; *off += out; l->mu_off = *off; *off += out; l->var_off = *off; *off += out; }
     return 1;
 }
 static int obs_planes(const mzo_config *c) { return c->C * (c->stacked_observations + 1) + c->stacked_observations; }
@@ -181,6 +189,7 @@ static int sa_size(const mzo_config *c) { return c->W * c->H * (c->C + 1); }
 static void build_net(const mzo_config *c, int which, net_t *n, int base) {
     int off = base, w = c->width_hidden;
     memset(n, 0, sizeof(*n)); n->base = base;
+    g_add_bn = c->use_batch_norm != 0;
     if (which == 0) { /* Learning.jl:87-98 */
         n->n_trunk += add_layer(&n->trunk[n->n_trunk], stack_size(c), w, ACT_RELU, &off);
         for (int i = 0; i < c->depth_representation; i++) n->n_trunk += add_layer(&n->trunk[n->n_trunk], w, w, ACT_RELU, &off);
@@ -234,6 +243,7 @@ void mzo_init_weights(const mzo_config *c, uint64_t seed, float *blob) {
                     for (int j = 0; j < 4 && i + j < nw; j++) blob[ls[l].w_off + i + j] = (u32_to_unit(r[j]) - 0.5f) * scale;
                 }
                 for (int o = 0; o < ls[l].out; o++) blob[ls[l].b_off + o] = 0.0f;
+                if (ls[l].bn) for (int o = 0; o < ls[l].out; o++) { blob[ls[l].beta_off + o] = 0.0f; blob[ls[l].gamma_off + o] = 1.0f; blob[ls[l].mu_off + o] = 0.0f; blob[ls[l].var_off + o] = 1.0f; }   /* Flux.BatchNorm(out) */
             }
         }
     }
@@ -293,6 +303,7 @@ static void dense(const float *blob, const layer_t *l, const float *x, float *y)
     }
     for (int o = 0; o < out; o++) {
         float v = acc[o] + b[o];
+        if (l->bn) v = ((blob[l->gamma_off + o] * (v - blob[l->mu_off + o])) / sqrtf(blob[l->var_off + o] + 1e-5f)) + blob[l->beta_off + o];   /* BatchNorm, test mode */
         if (l->act == ACT_RELU) v = v > 0.0f ? v : 0.0f;       /* NNlib relu(x) = max(0, x) */
         else if (l->act == ACT_TANH) v = mzo_tanhf(v);
         y[o] = v;
@@ -1195,6 +1206,12 @@ static float sqnorm_net(const float *blob, const net_t *n) { /* sum(sqnorm, para
             for (int i = 0; i < ls[l].out; i++) sb = sb + blob[ls[l].b_off + i] * blob[ls[l].b_off + i];
             if (first) { total = sw; first = 0; } else total = total + sw;
             total = total + sb;
+            if (ls[l].bn) {   /* Flux.params: ..., BatchNorm beta, gamma */
+                float s1 = 0.0f, s2 = 0.0f;
+                for (int i = 0; i < ls[l].out; i++) s1 = s1 + blob[ls[l].beta_off + i] * blob[ls[l].beta_off + i];
+                for (int i = 0; i < ls[l].out; i++) s2 = s2 + blob[ls[l].gamma_off + i] * blob[ls[l].gamma_off + i];
+                total = total + s1; total = total + s2;
+            }
         }
     }
     return total;
@@ -1220,7 +1237,16 @@ static float rn_sqnorm_net(const mzo_config *c, const float *blob, int net) {
 void mzo_trainable_mask(const mzo_config *c, unsigned char *mask) {
     int np = mzo_num_params(c, 3);
     memset(mask, 1, (size_t)np);
-    if (c->net_type != 1) return;
+    if (c->net_type != 1) {
+        if (!c->use_batch_norm) return;
+        net_t nets[3]; build_nets(c, nets);
+        for (int n = 0; n < 3; n++) for (int part = 0; part < 3; part++) {
+            int cnt = part == 0 ? nets[n].n_trunk : part == 1 ? nets[n].n_h1 : nets[n].n_h2;
+            const layer_t *ls = part == 0 ? nets[n].trunk : part == 1 ? nets[n].h1 : nets[n].h2;
+            for (int l = 0; l < cnt; l++) if (ls[l].bn) for (int i = 0; i < ls[l].out; i++) { mask[ls[l].mu_off + i] = 0; mask[ls[l].var_off + i] = 0; }
+        }
+        return;
+    }
     rn_model_t m; rn_build(c, &m);
     for (int n = 0; n < 3; n++) for (int ui = 0; ui < m.net[n].n; ui++) {
         const rn_unit_t *u = &m.net[n].u[ui];

@@ -77,6 +77,7 @@ typedef struct mzo_config {
     int32_t per;                    /* conf.PER (params.jl:11: false) */
     int32_t per_alpha;              /* conf.PER_alpha (Constructors.jl:44: 1) */
     int32_t temperature_threshold;  /* conf.temperature_threshold (Constructors.jl:31): -1 = nothing */
+    int32_t use_batch_norm;         /* FeedForwardHP.use_batch_norm (Constructors.jl:71): make_dense = Dense + BatchNorm(relu) (Learning.jl:70-79) */
 } mzo_config;
 
 void mzo_default_config(mzo_config *cfg);            /* params.jl:2-29 defaults */

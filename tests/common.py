@@ -13,7 +13,7 @@ _COMMON = ["game", "W", "H", "C", "A", "num_players", "stacked_observations", "m
            "dirichlet_alpha", "exploration_eps", "seed", "width_hidden", "depth_representation", "depth_prediction",
            "depth_dynamics", "depth_policy", "depth_value", "depth_reward", "depth_state_head", "hidden_state_size",
            "reward_activation_tanh", "net_type", "rn_num_blocks", "rn_num_filters", "rn_kernel", "rn_first_head_filters",
-           "rn_second_head_filters", "per", "per_alpha", "temperature_threshold"]
+           "rn_second_head_filters", "per", "per_alpha", "temperature_threshold", "use_batch_norm"]
 
 
 def oracle_config(mzcfg):

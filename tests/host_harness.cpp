@@ -17,7 +17,9 @@ struct net_runner {
         for (int o = 0; o < L.out_pad; o++) {
             float acc = 0.0f;
             for (int k = 0; k < L.in; k++) acc = fmaf(dev[(size_t)L.w_off + (size_t)k * L.out_pad + o], x[k], acc);
-            y[o] = mz_activate(acc + dev[(size_t)L.b_off + o], L.act);
+            float v = acc + dev[(size_t)L.b_off + o];
+            if (L.bn) v = mz_batchnorm(v, dev[(size_t)L.b_off + L.out_pad + o], dev[(size_t)L.b_off + 2 * L.out_pad + o], dev[(size_t)L.b_off + 3 * L.out_pad + o], dev[(size_t)L.b_off + 4 * L.out_pad + o]);
+            y[o] = mz_activate(v, L.act);
         }
     }
     void chain(int first, int n, const float *x, float *y) const {

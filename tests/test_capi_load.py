@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "libmuzero_b200.so does not export %s" % n
     assert set(names) == set(L._mz_symbols), "capi.py binding and header disagree"
-    assert L.mz_abi_version() == 6
+    assert L.mz_abi_version() == 7
 
 
 def test_config_defaults_follow_params_jl():

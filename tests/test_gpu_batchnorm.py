@@ -1,0 +1,94 @@
+"""FeedForwardHP.use_batch_norm (src/Constructors.jl:71, src/Learning.jl:70-79): every make_dense layer is Dense + BatchNorm(relu).  The
+reference never differentiates a forward pass (Q20) and never calls trainmode!, so BatchNorm runs in test mode everywhere; its beta / gamma
+are Flux parameters (they take part in sum(abs2, theta) and in the ADAM update), the running statistics are not.  Exact fp32 path, bit-exact
+against the oracle."""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+from test_host_harness import _randomise_batchnorm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from muzero_jl_b200 import capi
+    return capi
+
+
+def make_ctx(capi, **kw):
+    kw.setdefault("num_slots", 256); kw.setdefault("replay_buffer_size", 1024); kw.setdefault("use_batch_norm", 1)
+    cfg = capi.default_config(**kw)
+    return capi.Context(cfg), common.oracle_config(cfg)
+
+
+def test_bn_networks_and_run_mcts_bit_exact(capi):
+    ctx, ocfg = make_ctx(capi, num_iters=25, exploration_eps=0.25)
+    ctx.init_weights(9)
+    assert np.array_equal(ctx.get_weights(), O.init_weights(ocfg, 9))
+    blob = _randomise_batchnorm(ocfg, ctx.get_weights(), 4); ctx.set_weights(blob)
+    assert np.array_equal(ctx.get_weights(), blob)
+    st, legal, tp = common.random_stacked(ocfg, 300, seed=6)
+    h = ctx.representation(st); v, p = ctx.prediction(h)
+    oh = np.stack([O.representation(ocfg, blob, x) for x in st])
+    assert np.array_equal(h, oh)
+    for i in range(0, 300, 37):
+        ov, op = O.prediction(ocfg, blob, oh[i])
+        assert v[i] == ov and np.array_equal(p[i], op)
+    game = np.arange(300, dtype=np.uint64) + 7; move = np.ones(300, np.int32)
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)     # 300 roots: the batched kernel mz_k_search
+    for i in range(0, 300, 7):
+        ovc, orv, opri = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), 1)
+        assert vc[i].tolist() == ovc.tolist() and rv[i] == orv and np.array_equal(pri[i], opri), i
+    vc1, rv1, _ = ctx.run_mcts(st[:5], legal[:5], tp[:5], True, game[:5], move[:5], priors=True)   # few roots: still the batched kernel (the resident-weights kernel has no BatchNorm)
+    assert np.array_equal(vc1, vc[:5]) and np.array_equal(rv1, rv[:5])
+    ctx.close()
+
+
+def test_bn_self_play_and_learner_bit_exact(capi):
+    ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=256, num_iters=12)
+    ctx.init_weights(3)
+    blob = _randomise_batchnorm(ocfg, ctx.get_weights(), 8); ctx.set_weights(blob)
+    sims, moves = ctx.self_play(100, 150, 1.0)
+    o = O.self_play(ocfg, blob, 100, 150, 1.0, 4)
+    assert sims == o["sims"]
+    h = ctx.history_export()
+    for j in range(150):
+        i = int(h["game_id"][j]) - 100
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][i]), (k, i)
+    # learning! (Learning.jl:327-397): losses, then ADAM on 2 * theta over Flux.params: beta and gamma move, mu and sigma2 do not
+    mask = O.trainable_mask(ocfg)
+    w = blob.copy(); m = np.zeros_like(w); v = np.zeros_like(w)
+    for t in (1, 2, 3):
+        batch = ctx.get_batch(t)
+        losses = ctx.learn_step(t)
+        ol = O.learn_step(ocfg, w, m, v, t, batch)
+        np.testing.assert_allclose(losses, ol, rtol=2e-6)
+        got = ctx.get_weights()
+        assert np.array_equal(got, w), t
+        assert np.array_equal(got[mask == 0], blob[mask == 0])
+    assert not np.array_equal(got[mask == 1], blob[mask == 1])
+    ctx.close()
+
+
+def test_bn_unsupported_combinations_say_so(capi):
+    for mode in (capi.NN_BF16_TC, capi.NN_SPLIT_MMA):
+        with pytest.raises(capi.MuZeroB200Error):
+            capi.Context(capi.default_config(use_batch_norm=1, nn_mode=mode))
+    ctx, _ = make_ctx(capi, num_slots=32, replay_buffer_size=64, num_iters=5)
+    ctx.init_weights(1); ctx.self_play(0, 32, 1.0)
+    with pytest.raises(capi.MuZeroB200Error):
+        ctx.learn_step(1, grad_mode=capi.GRAD_BPTT)
+    ctx.close()
+
+
+def test_bn_through_the_reference_level_api(capi):
+    from muzero_jl_b200 import api
+    conf = api.Config(); hyper = api.FeedForwardHP(use_batch_norm=True)
+    cfg = api.to_mz_config(conf, hyper, num_slots=32)
+    assert cfg.use_batch_norm == 1
+    with pytest.raises(NotImplementedError):
+        api.to_mz_config(conf, hyper, num_slots=32, nn_mode=capi.NN_SPLIT_MMA)

@@ -1,0 +1,95 @@
+"""mz_k_search_lat (mz_kernels_lat.cuh): the low-latency search kernel for few roots -- one tree per two-CTA cluster, networks, tree and
+PUCT table resident in shared memory -- against the Float32 oracle.  It computes in the exact arithmetic contract, so everything is
+bit-exact: visit counts, priors, root values (run_mcts, SelfPlay.jl:230-285) and whole GameHistories (play_game, :330-382)."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from muzero_jl_b200 import capi
+    return capi
+
+
+def make_ctx(capi, lat=None, **kw):
+    kw.setdefault("num_slots", 256); kw.setdefault("replay_buffer_size", 1024)
+    cfg = capi.default_config(**kw)
+    old = os.environ.get("MUZERO_B200_LAT")
+    if lat is not None:
+        os.environ["MUZERO_B200_LAT"] = str(lat)
+    try:
+        ctx = capi.Context(cfg)
+    finally:
+        if lat is not None:
+            if old is None:
+                del os.environ["MUZERO_B200_LAT"]
+            else:
+                os.environ["MUZERO_B200_LAT"] = old
+    return ctx, common.oracle_config(cfg)
+
+
+@pytest.mark.parametrize("S,eps,tie,n,kw", [(50, 0.25, 0, 1, {}), (50, 0.0, 0, 7, {}), (25, 0.25, 1, 148, {}), (10, 0.25, 0, 40, {"stacked_observations": 0}),
+                                            (30, 0.25, 0, 20, {"stacked_observations": 2}), (50, 0.25, 0, 12, {"nn_mode": "split"})])
+def test_lat_run_mcts_bit_exact(capi, S, eps, tie, n, kw):
+    kw = dict(kw)
+    if kw.get("nn_mode") == "split":
+        kw["nn_mode"] = capi.NN_SPLIT_MMA          # small calls of a split-precision context run the exact kernel
+    ctx, ocfg = make_ctx(capi, num_iters=S, exploration_eps=eps, tie_mode=tie, **kw)
+    ctx.init_weights(7); blob = ctx.get_weights()
+    st, legal, tp = common.random_stacked(ocfg, n, seed=S + n)
+    game = np.arange(n, dtype=np.uint64) + 100; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    before = ctx.launch_count()
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    assert ctx.launch_count() <= before + 3            # the search (+ the weight-image rebuilds after init_weights)
+    for i in range(n):
+        ovc, orv, opri = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i]))
+        assert vc[i].tolist() == ovc.tolist(), i
+        assert rv[i] == orv and np.array_equal(pri[i], opri), i
+    assert np.all(vc.sum(1) == S)
+    ctx.close()
+
+
+def test_lat_equals_batched_kernel(capi):
+    """the same roots through mz_k_search (MUZERO_B200_LAT=0) and mz_k_search_lat"""
+    res = []
+    for lat in (0, 200):
+        ctx, ocfg = make_ctx(capi, lat=lat, num_iters=50)
+        ctx.init_weights(21)
+        st, legal, tp = common.random_stacked(ocfg, 100, seed=9)
+        game = np.arange(100, dtype=np.uint64); move = np.ones(100, np.int32)
+        res.append(ctx.run_mcts(st, legal, tp, True, game, move, priors=True)); ctx.close()
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("temperature,eps,slots,games,kw", [(1.0, 0.25, 1, 5, {}), (0.5, 0.25, 16, 100, {}), (0.0, 0.0, 7, 30, {"temperature_threshold": 3}),
+                                                            (1.0, 0.25, 64, 200, {"stacked_observations": 2, "num_iters": 20})])
+def test_lat_self_play_bit_exact(capi, temperature, eps, slots, games, kw):
+    ctx, ocfg = make_ctx(capi, lat=64, exploration_eps=eps, num_slots=slots, replay_buffer_size=256, **kw)
+    ctx.init_weights(3); blob = ctx.get_weights()
+    sims, moves = ctx.self_play(1000, games, temperature)
+    o = O.self_play(ocfg, blob, 1000, games, temperature, 4)
+    assert sims == o["sims"] and moves == int(o["T"].sum())
+    h = ctx.history_export()
+    assert sorted(h["game_id"].tolist()) == list(range(1000, 1000 + games))
+    for j in range(games):
+        i = int(h["game_id"][j]) - 1000
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][i]), (k, i)
+    ctx.close()
+
+
+def test_lat_arena_bit_exact(capi):
+    ctx, ocfg = make_ctx(capi, lat=64, num_slots=8, replay_buffer_size=64, num_iters=20)
+    ctx.init_weights(5); blob = ctx.get_weights()
+    ar = ctx.arena(50, 24, capi.OPP_EXPERT, 2, 0.0)
+    oa = O.arena(ocfg, blob, 50, 24, O.OPP_EXPERT, 2, 0.0, 4)["outcome"]
+    assert (ar["wins"], ar["draws"], ar["losses"]) == (int((oa == 1).sum()), int((oa == 0).sum()), int((oa == -1).sum()))
+    ctx.close()

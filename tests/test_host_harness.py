@@ -135,3 +135,48 @@ def test_resnet_program_replay_matches_bf16_oracle(hh, kw):
     assert hh.hh_rn_forward(C.byref(cfg), _p(blob), 2, n, _p(sa), _p(nh), _p(r)) == 0
     onh = np.stack(onh)
     assert np.max(np.abs(nh - onh)) < 2e-2 * max(1.0, float(np.max(np.abs(onh)))) and np.max(np.abs(r - np.array(orr))) < 2e-2
+
+
+def _randomise_batchnorm(ocfg, blob, seed):
+    """give every BatchNorm non-trivial beta / gamma / mu / sigma2 (a fresh one is the identity up to 1/sqrt(1 + 1f-5))"""
+    rng = np.random.default_rng(seed)
+    mask = O.trainable_mask(ocfg)
+    stats = np.flatnonzero(mask == 0)                      # mu, sigma2 blocks: [mu(out) | sigma2(out)] per BatchNorm
+    assert len(stats) > 0 and len(stats) % 2 == 0
+    out = blob.copy()
+    # beta, gamma sit right before mu in the blob: walk the runs of statistics
+    runs = np.split(stats, np.flatnonzero(np.diff(stats) > 1) + 1)
+    for r in runs:
+        n = len(r) // 2
+        out[r[0] - 2 * n:r[0] - n] = rng.normal(0, 0.3, n)            # beta
+        out[r[0] - n:r[0]] = rng.uniform(0.5, 1.5, n)                 # gamma
+        out[r[:n]] = rng.normal(0, 0.3, n)                            # mu
+        out[r[n:]] = rng.uniform(0.3, 2.0, n)                         # sigma2
+    return out.astype(np.float32)
+
+
+def test_use_batch_norm_networks_and_search_bit_exact(hh):
+    """FeedForwardHP.use_batch_norm (Learning.jl:70-79): Dense + BatchNorm(relu) in test mode, blob W, b, beta, gamma, mu, sigma2"""
+    cfg = common.product_config(use_batch_norm=1, num_iters=20, exploration_eps=0.25); ocfg = common.oracle_config(cfg)
+    n = hh.hh_num_params(C.byref(cfg))
+    assert n == O.num_params(ocfg) == 74881 + 4 * 64 * 18          # 18 make_dense layers of width 64
+    blob = np.zeros(n, np.float32); hh.hh_init_weights(C.byref(cfg), 5, _p(blob))
+    assert np.array_equal(blob, O.init_weights(ocfg, 5))
+    blob = _randomise_batchnorm(ocfg, blob, 1)
+    rng = np.random.default_rng(2)
+    for _ in range(4):
+        st = rng.normal(size=63).astype(np.float32)
+        h = np.zeros(27, np.float32); hh.hh_nn(C.byref(cfg), _p(blob), 0, _p(st), _p(h), None)
+        assert np.array_equal(h, O.representation(ocfg, blob, st))
+        v = np.zeros(1, np.float32); p = np.zeros(9, np.float32); hh.hh_nn(C.byref(cfg), _p(blob), 1, _p(h), _p(v), _p(p))
+        ov, op = O.prediction(ocfg, blob, h)
+        assert v[0] == ov and np.array_equal(p, op)
+    # the BatchNorm must matter: the same weights without it give another hidden state
+    cfg0 = common.product_config(); ocfg0 = common.oracle_config(cfg0)
+    assert not np.array_equal(O.representation(ocfg0, O.init_weights(ocfg0, 5), st), h)
+    st, legal, tp = common.random_stacked(ocfg, 6, seed=3)
+    for i in range(len(st)):
+        vc = np.zeros(9, np.int32); rv = np.zeros(1, np.float32); pri = np.zeros(9, np.float32)
+        hh.hh_run_mcts(C.byref(cfg), _p(blob), _p(st[i]), int(legal[i]), int(tp[i]), 1, 40 + i, 1, _p(vc, C.c_int32), _p(rv), _p(pri))
+        ovc, orv, opri = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, 40 + i, 1)
+        assert vc.tolist() == ovc.tolist() and rv[0] == orv and np.array_equal(pri, opri)
