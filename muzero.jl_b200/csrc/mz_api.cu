@@ -409,7 +409,9 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         mz_learn_sp_args t{}; t.sp = c->spa; t.B = B; t.batch = c->batch; t.pred_values = c->d_pv; t.pred_rewards = c->d_pr; t.pred_policies = c->d_pp;
         launch_scope ls(c, 3); mz_k_learn_forward_sp<<<tiles, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t);
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2) {
-        launch_scope ls(c, 3); mz_k_learn_forward<<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
+        launch_scope ls(c, 3);
+        if (c->cfg.use_batch_norm) mz_k_learn_forward<true><<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
+        else mz_k_learn_forward<false><<<tiles, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
     } else return fail(c, MZ_E_ARG, "unknown grad_mode %d", grad_mode);
     { launch_scope ls(c, 3); const int ry = P.K + 1 < MZ_LOSS_RY ? P.K + 1 : MZ_LOSS_RY;
       mz_k_loss_rows<<<(B + 31) / 32, dim3(32, (unsigned)ry), 0, c->stream>>>(P, B, c->batch, c->d_pv, c->d_pr, c->d_pp, c->d_rowv, c->d_rowr, c->d_rowp, c->d_rowinvg); }
@@ -546,9 +548,14 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API, 256>, prop));
     MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS, 256>, prop));
     if (const char *eg = getenv("MZ_EXACT_GROUP")) c->exact_gt = atoi(eg) == 256 ? 256 : 128;   // measurement switch
-    MZ_CREATE(allow_max_smem(mz_k_nn_forward, prop));
-    MZ_CREATE(allow_max_smem(mz_k_reanalyse, prop));
-    MZ_CREATE(allow_max_smem(mz_k_learn_forward, prop));
+    MZ_CREATE(allow_max_smem(mz_k_nn_forward<false>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_reanalyse<false>, prop));
+    MZ_CREATE(allow_max_smem(mz_k_learn_forward<false>, prop));
+    if (!resnet && cfg->use_batch_norm) {   // the same kernels instantiated with the BatchNorm epilogue
+        MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_API, MZ_GROUP, true>, prop)); MZ_CREATE(allow_max_smem(mz_k_search<MZ_MODE_SLOTS, MZ_GROUP, true>, prop));
+        MZ_CREATE(allow_max_smem(mz_k_nn_forward<true>, prop)); MZ_CREATE(allow_max_smem(mz_k_reanalyse<true>, prop)); MZ_CREATE(allow_max_smem(mz_k_learn_forward<true>, prop));
+        c->exact_gt = 128;
+    }
     if (!resnet) {   // the low-latency search kernel for few roots: does a network pair fit one SM's shared memory in fp32?
         int nf[3] = {0, 0, 0}; bool narrow = true;
         for (int n = 0; n < 3; n++) for (int l = P.nets[n].first; l < P.nets[n].first + P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2; l++) {
@@ -771,7 +778,8 @@ static int nn_forward(mz_ctx *c, int net, int B, const float *in, float *out1, s
     } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
         mz_nn_tc_args t{}; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc; t.B = B; t.net = net; t.in = d_in; t.out1 = d_o1; t.out2 = d_o2;
         launch_scope ls(c, 5); mz_k_nn_forward_tc<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
-    } else { launch_scope ls(c, 5); mz_k_nn_forward<<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    } else if (c->cfg.use_batch_norm) { launch_scope ls(c, 5); mz_k_nn_forward<true><<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    else { launch_scope ls(c, 5); mz_k_nn_forward<false><<<(B + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
     MZ_CUDA(c, cudaGetLastError());
     MZ_TRY(d2h(c, out1, d_o1, (size_t)B * n1));
     if (n2 && out2) MZ_TRY(d2h(c, out2, d_o2, (size_t)B * n2));
@@ -911,7 +919,8 @@ int mz_run_mcts(mz_ctx *c, int n, const float *stacked_obs, const uint32_t *lega
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
-        } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API, 256><<<(m + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
+        } else if (c->cfg.use_batch_norm) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API, MZ_GROUP, true><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API, 256><<<(m + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_API><<<(m + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         MZ_CUDA(c, cudaGetLastError());
         MZ_TRY(d2h(c, visit_counts + (size_t)off * P.A, d_vc, (size_t)m * P.A)); MZ_TRY(d2h(c, root_value + off, d_rv, (size_t)m));
@@ -1008,7 +1017,8 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         } else if (c->cfg.nn_mode == MZ_NN_BF16_TC) {
             mz_search_tc_args t{}; t.base = a; t.w_image = c->d_w_tc; t.bias = c->d_bias_tc;
             launch_scope ls(c, 0); mz_k_search_tc<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes_tc, c->stream>>>(P, t);
-        } else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
+        } else if (c->cfg.use_batch_norm) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, MZ_GROUP, true><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+        else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         const size_t search_entry = c->timed.size();                       // (timing builds) index just past this iteration's search launch
         MZ_TRY(launch_save_refill(c, P, G, tally));
@@ -1181,7 +1191,9 @@ int mz_reanalyse(mz_ctx *c, int64_t key0, int n) {
     const mz_params &P = c->M.P;
     mz_reanalyse_args a{}; a.wglob = c->d_w; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.n = n; a.key0 = key0; a.ring = c->ring;
     const int64_t total = (int64_t)n * P.Tmax;
-    { launch_scope ls(c, 5); mz_k_reanalyse<<<(unsigned)((total + MZ_ROWS - 1) / MZ_ROWS), MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
+    { launch_scope ls(c, 5);
+      if (c->cfg.use_batch_norm) mz_k_reanalyse<true><<<(unsigned)((total + MZ_ROWS - 1) / MZ_ROWS), MZ_THREADS, c->smem_bytes, c->stream>>>(P, a);
+      else mz_k_reanalyse<false><<<(unsigned)((total + MZ_ROWS - 1) / MZ_ROWS), MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
     MZ_CUDA(c, cudaGetLastError());
     return MZ_OK;
 }

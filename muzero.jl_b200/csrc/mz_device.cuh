@@ -203,37 +203,39 @@ MZ_UNROLL_K
 // One layer for one group: prefetch `next` (or nothing when next < 0) into the other buffer, wait for this layer's
 // weights, compute, group barrier.  Preconditions: this layer's copy was issued earlier; a barrier separates the last
 // reads of the other buffer (layer q-1) and of `dst`'s previous contents from this call.
-template <int GT = MZ_GROUP>
+// BN: the kernel was instantiated for use_batch_norm networks.  A template parameter, not a run-time test: with the test (or the BatchNorm
+// epilogue inside mz_dense_tile) the ordinary networks' search kernel ran 9 - 20 % slower (88 - 98 M instead of 107 M simulations/s).
+template <int GT = MZ_GROUP, bool BN = false>
 __device__ __forceinline__ void mz_nn_layer(mz_nn_pipe &s, const mz_params &P, int layer, int next, const float *src, float *dst) {
     if (s.gtid == 0 && next >= 0) mz_nn_issue(s, P, next, (s.q + 1) & 1u);
     mz_mbar_wait(&s.mbar[s.q & 1u], (s.q >> 1) & 1u);
     const mz_layer &L = P.layers[layer];
-    if (L.bn) mz_dense_tile_bn(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);   // (both group sizes: 4 warps do the layer)
+    if (BN && L.bn) mz_dense_tile_bn(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);   // (both group sizes: 4 warps do the layer)
     else if (GT == 256) mz_dense_tile_g256(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
     else mz_dense_tile(L.in, L.out_pad, L.act, mz_smem_u32(s.wbuf[s.q & 1u]), mz_smem_u32(src), mz_smem_u32(dst), s.gtid);
     mz_group_sync<GT>(s.grp);
     s.q++;
 }
-template <int GT = MZ_GROUP>
+template <int GT = MZ_GROUP, bool BN = false>
 __device__ __forceinline__ void mz_nn_chain(mz_nn_pipe &s, const mz_params &P, int first, int n, int after, const float *src,
                                             float *dst, float *t0, float *t1) {
     const float *cur = src;
     for (int i = 0; i < n; i++) {
         float *d = (i == n - 1) ? dst : ((i & 1) ? t1 : t0);
-        mz_nn_layer<GT>(s, P, first + i, (i == n - 1) ? after : first + i + 1, cur, d);
+        mz_nn_layer<GT, BN>(s, P, first + i, (i == n - 1) ? after : first + i + 1, cur, d);
         cur = d;
     }
 }
 // trunk -> bufT, head 1 -> h1dst, head 2 -> h2dst (Split, src/Learning.jl:60-68); `after` = layer prefetched last
-template <int GT = MZ_GROUP>
+template <int GT = MZ_GROUP, bool BN = false>
 __device__ __noinline__ void mz_nn_net(mz_nn_pipe &s, const mz_params &P, int net, int after, const float *src, float *bufT,
                                        float *h1dst, float *h2dst, float *t0, float *t1) {
     const mz_net &N = P.nets[net];
     int f = N.first;
-    if (N.n_h1 == 0) { mz_nn_chain<GT>(s, P, f, N.n_trunk, after, src, h1dst, t0, t1); return; }
-    mz_nn_chain<GT>(s, P, f, N.n_trunk, f + N.n_trunk, src, bufT, t0, t1);
-    mz_nn_chain<GT>(s, P, f + N.n_trunk, N.n_h1, f + N.n_trunk + N.n_h1, bufT, h1dst, t0, t1);
-    mz_nn_chain<GT>(s, P, f + N.n_trunk + N.n_h1, N.n_h2, after, bufT, h2dst, t0, t1);
+    if (N.n_h1 == 0) { mz_nn_chain<GT, BN>(s, P, f, N.n_trunk, after, src, h1dst, t0, t1); return; }
+    mz_nn_chain<GT, BN>(s, P, f, N.n_trunk, f + N.n_trunk, src, bufT, t0, t1);
+    mz_nn_chain<GT, BN>(s, P, f + N.n_trunk, N.n_h1, f + N.n_trunk + N.n_h1, bufT, h1dst, t0, t1);
+    mz_nn_chain<GT, BN>(s, P, f + N.n_trunk + N.n_h1, N.n_h2, after, bufT, h2dst, t0, t1);
 }
 
 // shared-memory carve-up used by every NN-running kernel

@@ -224,7 +224,7 @@ __device__ __forceinline__ bool mz_cta_idle(const mz_params &P, const mz_search_
     return __syncthreads_or(any) == 0;
 }
 
-template <int MODE, int GT = MZ_GROUP>
+template <int MODE, int GT = MZ_GROUP, bool BN = false>
 __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz_params P, const mz_search_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     if (mz_cta_idle<MODE>(P, a, MZ_ROWS)) return;
@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
 
     // ---- root: representation -> h0; prediction(h0) -> (v0, p0)  (SelfPlay.jl:233-245), group 0 only ----
     if (pipe.grp == 0) {
-        mz_nn_net<GT>(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
-        mz_nn_net<GT>(pipe, P, 1, pred_first, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // prefetches simulation 1's first layer
+        mz_nn_net<GT, BN>(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net<GT, BN>(pipe, P, 1, pred_first, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // prefetches simulation 1's first layer
     }
     __syncthreads();
 
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(2 * GT) mz_k_search(const __grid_constant__ mz
         MZ_TIMER(2);
         __syncthreads();
         MZ_TIMER(3);
-        if (pipe.grp == 0) mz_nn_net<GT>(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
-        else               mz_nn_net<GT>(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
+        if (pipe.grp == 0) mz_nn_net<GT, BN>(pipe, P, 1, sim < P.S ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+        else               mz_nn_net<GT, BN>(pipe, P, 2, sim < P.S ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);
         MZ_TIMER(4);
         __syncthreads();
         MZ_TIMER(5);
@@ -566,6 +566,7 @@ __global__ void mz_k_save_per(const __grid_constant__ mz_params P, mz_slots s, m
 
 // ---- batched network callables (init_*(hyper) callables, src/Learning.jl:87-142) -------------------
 struct mz_nn_args { const float *wglob; int32_t B, max_dim, max_layer_floats, net; const float *in; float *out1; float *out2; };
+template <bool BN = false>
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_constant__ mz_params P, const mz_nn_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_const
     }
     __syncthreads();
     float *h1 = a.net == 1 ? sp.outV : sp.outH, *h2 = a.net == 1 ? sp.outL : sp.outR;
-    if (pipe.grp == 0) mz_nn_net(pipe, P, a.net, -1, sp.in0, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0]);
+    if (pipe.grp == 0) mz_nn_net<MZ_GROUP, BN>(pipe, P, a.net, -1, sp.in0, sp.bufT[0], h1, h2, sp.t0[0], sp.t1[0]);
     __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
     if (tid < MZ_ROWS && g < a.B) {
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_nn_forward(const __grid_const
 // counter).  Producer, as in MuZero Reanalyze: for every stored position of games key0 .. key0+n-1 the value head of the CURRENT
 // networks on the stacked observation, prediction(representation(get_stacked_observations(history, i))).  32 positions per CTA.
 struct mz_reanalyse_args { const float *wglob; int32_t max_dim, max_layer_floats, n; int64_t key0; mz_ring ring; };
+template <bool BN = false>
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_reanalyse(const __grid_constant__ mz_params P, const mz_reanalyse_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
@@ -628,8 +630,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_reanalyse(const __grid_consta
     }
     __syncthreads();
     if (pipe.grp == 0) {
-        mz_nn_net(pipe, P, 0, P.nets[1].first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
-        mz_nn_net(pipe, P, 1, -1, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+        mz_nn_net<MZ_GROUP, BN>(pipe, P, 0, P.nets[1].first, sp.in0, sp.bufT[0], sp.outH, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net<MZ_GROUP, BN>(pipe, P, 1, -1, sp.outH, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
     }
     __syncthreads();
     const int64_t item = (int64_t)blockIdx.x * MZ_ROWS + tid;

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(1024) mz_k_per_normalise(int B, float *w) {
 // K-step unroll forward for 32 samples per CTA (src/Learning.jl:347-370, Q19): row 0 = prediction(h0); for
 // i = 1..K: row i = prediction(h_{i-1}) evaluated BEFORE the dynamics step; rewards row 0 = 0.
 struct mz_learn_args { const float *wglob; int32_t B, max_dim, max_layer_floats, pad_; mz_batch batch; float *pred_values, *pred_rewards, *pred_policies; };
+template <bool BN = false>
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_constant__ mz_params P, const mz_learn_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
     const mz_smem_plan sp = mz_smem_carve(mz_smem, a.max_dim, a.max_layer_floats, P.hidden_pad, P.S);
@@ -108,8 +109,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_co
     __syncthreads();
     // representation (:347) then row 0 = prediction(h0) (:351) on group 0; in1 keeps the current hidden state
     if (pipe.grp == 0) {
-        mz_nn_net(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.in1, nullptr, sp.t0[0], sp.t1[0]);
-        mz_nn_net(pipe, P, 1, P.K > 0 ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
+        mz_nn_net<MZ_GROUP, BN>(pipe, P, 0, pred_first, sp.in0, sp.bufT[0], sp.in1, nullptr, sp.t0[0], sp.t1[0]);
+        mz_nn_net<MZ_GROUP, BN>(pipe, P, 1, P.K > 0 ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);
     }
     __syncthreads();
     for (int i = 0; i <= P.K; i++) {
@@ -132,8 +133,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_forward(const __grid_co
         }
         __syncthreads();
         const bool more = i + 1 < P.K;
-        if (pipe.grp == 0) mz_nn_net(pipe, P, 1, more ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // :356
-        else               mz_nn_net(pipe, P, 2, more ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);     // :362
+        if (pipe.grp == 0) mz_nn_net<MZ_GROUP, BN>(pipe, P, 1, more ? pred_first : -1, sp.in1, sp.bufT[0], sp.outV, sp.outL, sp.t0[0], sp.t1[0]);   // :356
+        else               mz_nn_net<MZ_GROUP, BN>(pipe, P, 2, more ? dyn_first : -1, sp.in0, sp.bufT[1], sp.outH, sp.outR, sp.t0[1], sp.t1[1]);     // :362
         __syncthreads();
         for (int k = tid; k < P.hidden * MZ_ROWS; k += MZ_THREADS) sp.in1[k] = sp.outH[k];          // h_{i+1}
         __syncthreads();
