@@ -84,9 +84,8 @@ __device__ __forceinline__ void mz_lat_preload(mz_lat_col &c, const mz_lat_plan 
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.b) : "r"(mz_smem_u32(sp.w + L.w) + 4u * (uint32_t)(c.out * L.y + t)));
     }
 }
-__device__ __forceinline__ void mz_lat_apply(const mz_lat_col &c, const float *x, float *y, int t, long long *nt = nullptr) {
+__device__ __forceinline__ void mz_lat_apply(const mz_lat_col &c, const float *x, float *y, int t) {
     if (t >= c.out) return;
-    long long a0 = nt ? clock64() : 0;
     float acc = 0.0f;
     const uint32_t xa = mz_smem_u32(x);
     float4 xv[MZ_LAT_KMAX / 4];                                           // every activation buffer holds at least MZ_LAT_KMAX floats
@@ -100,12 +99,10 @@ __device__ __forceinline__ void mz_lat_apply(const mz_lat_col &c, const float *x
         acc = fmaf(c.w[k4].x, xv[k4].x, acc); acc = fmaf(c.w[k4].y, xv[k4].y, acc);
         acc = fmaf(c.w[k4].z, xv[k4].z, acc); acc = fmaf(c.w[k4].w, xv[k4].w, acc);
     }
-    if (nt) { if (acc == 123.456f) y[t] = acc; long long a1 = clock64(); nt[5] += a1 - a0; a0 = a1; }
     float r = acc + c.b;
     if (c.act == MZ_ACT_RELU) r = fmaxf(r, 0.0f);
     else if (c.act == MZ_ACT_TANH) r = mz_tanhf_ni(r);
     y[t] = r;
-    if (nt) nt[6] += clock64() - a0;
 }
 // layers wider than MZ_LAT_KMAX inputs (the representation's first layer with a deep observation stack; root only)
 __device__ __noinline__ void mz_lat_dense_wide(const float *w, int in, int rs, int out, int act, const float *x, float *y, int t) {
@@ -120,51 +117,40 @@ __device__ __noinline__ void mz_lat_dense_wide(const float *w, int in, int rs, i
 }
 // one network on the 128 threads of the CTA: trunk on the first half, then head 1 on the first half and head 2 on the second (Split,
 // src/Learning.jl:60-68).  The layer descriptors come from the shared-memory copy sp.lay: reading mz_params through a reference costs an
-// L2 round trip per field, which is most of a layer's time at this size.  Layers are separated by an mbarrier of the whole CTA: a thread
-// ARRIVES as soon as its output is stored, fetches the weights of its next layer, and only then waits -- the fetch overlaps the barrier.
-// `input_ready` runs after the first fetch: the barrier (or nothing) that makes the network's input visible.
+// L2 round trip per field, which is most of a layer's time at this size.
+// A thread keeps TWO weight rows in registers: the fetch of its next layer's row is issued before the fmaf chain of the current one, so
+// it costs nothing.  The layers of a chain are separated by a named barrier of the 64 threads that run it (bar.sync 1 + half, 64); the
+// hand-off trunk -> heads is one barrier of all 128 threads (bar.sync 3).  The barrier that publishes the network's outputs (and the one
+// that makes its input visible when `cluster_sync_first`) is the caller's: a cluster barrier during the simulations.
 struct mz_lat_net_s { int first, n_trunk, n_h1, n_h2; };
-#ifdef MZ_LAT_TIMERS
-#define MZ_NT(i) do { if (nt) { long long c_ = clock64(); nt[i] += c_ - nt0; nt0 = c_; } } while (0)
-#else
-#define MZ_NT(i)
-#endif
-__device__ __forceinline__ void mz_lat_net(const mz_lat_plan &sp, const mz_lat_net_s N, const float *src, float *h1dst, float *h2dst, uint32_t &phase, bool cluster_sync_first, long long *nt = nullptr) {
+__device__ __forceinline__ void mz_lat_net(const mz_lat_plan &sp, const mz_lat_net_s N, const float *src, float *h1dst, float *h2dst, bool cluster_sync_first) {
     const int half = threadIdx.x >> 6, t = threadIdx.x & (MZ_LAT_HALF - 1);
-#ifdef MZ_LAT_TIMERS
-    long long nt0 = clock64();
-#endif
-    // the layers this thread computes: half 0 = trunk then head 1, half 1 = head 2; step s of the network = trunk layer s or head layer s - n_trunk
-    const int n_steps = N.n_trunk + (N.n_h1 > N.n_h2 ? N.n_h1 : N.n_h2);
-    const int my_first = half == 0 ? 0 : N.n_trunk, my_n = half == 0 ? N.n_trunk + N.n_h1 : N.n_h2;
-    const int lbase = half == 0 ? N.first : N.first + N.n_trunk + N.n_h1;           // layer of my step my_first
-    mz_lat_col c; c.in = 0; c.out = 0; c.act = 0; c.b = 0.0f;
-    bool wide = false;
-    const float *cur = src;
-    const uint32_t bar = mz_smem_u32(sp.lbar);
-    for (int s = -1; s < n_steps; s++) {                                          // s = -1: only the first fetch and the input barrier
-        const int i = s - my_first;                                               // index into my layers
-        if (s >= 0) {
-            if (i >= 0 && i < my_n) {
-                const bool trunk = half == 0 && s < N.n_trunk;
-                const bool last_of_chain = trunk ? s == N.n_trunk - 1 : i == my_n - 1;
-                float *d = trunk ? (last_of_chain ? (N.n_h1 == 0 ? h1dst : sp.bufT) : sp.tb + (s & 1) * sp.md) : (last_of_chain ? (half == 0 ? h1dst : h2dst) : sp.tb + (2 * half + (i & 1)) * sp.md);
-                if (!trunk && s == N.n_trunk) cur = sp.bufT;
-                if (wide) { const int4 L = sp.lay[lbase + i]; mz_lat_dense_wide(sp.w + L.w, L.x, L.y, L.z & 0xffff, L.z >> 16, cur, d, t); }
-                else mz_lat_apply(c, cur, d, t, nt);
-                cur = d;
-            }
-            MZ_NT(0);
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-        }
-        if (i + 1 >= 0 && i + 1 < my_n) {                                         // my next layer's weights: the fetch overlaps the barrier
-            wide = sp.lay[lbase + i + 1].x > MZ_LAT_KMAX;
-            if (!wide) mz_lat_preload(c, sp, lbase + i + 1, t);
-        }
-        MZ_NT(1);
-        if (s < 0) { if (cluster_sync_first) cooperative_groups::this_cluster().sync(); }
-        else { mz_mbar_wait(sp.lbar, phase & 1u); phase++; }
-        MZ_NT(2);
+    const bool heads = N.n_h1 > 0;
+    const int my_n = half == 0 ? N.n_trunk + N.n_h1 : N.n_h2;                        // my layers: half 0 = trunk then head 1, half 1 = head 2
+    const int lbase = half == 0 ? N.first : N.first + N.n_trunk + N.n_h1;
+    mz_lat_col c0, c1; c0.in = c0.out = c0.act = 0; c0.b = 0.0f; c1 = c0;
+    const bool wide = my_n > 0 && sp.lay[lbase].x > MZ_LAT_KMAX;                     // only a network's first layer may be wider than 64 inputs
+    if (my_n > 0 && !wide) mz_lat_preload(c0, sp, lbase, t);
+    if (cluster_sync_first) cooperative_groups::this_cluster().sync();
+    if (half == 1 && my_n > 0) asm volatile("bar.sync 3, 128;" ::: "memory");        // the trunk's output
+    const float *cur = half == 0 ? src : sp.bufT;
+    int i = 0;
+    auto layer = [&](mz_lat_col &c, mz_lat_col &n) {
+        if (i + 1 < my_n) mz_lat_preload(n, sp, lbase + i + 1, t);
+        const bool trunk = half == 0 && i < N.n_trunk;
+        const bool last_of_chain = trunk ? i == N.n_trunk - 1 : i == my_n - 1;
+        float *d = trunk ? (last_of_chain ? (heads ? sp.bufT : h1dst) : sp.tb + (i & 1) * sp.md) : (last_of_chain ? (half == 0 ? h1dst : h2dst) : sp.tb + (2 * half + (i & 1)) * sp.md);
+        if (i == 0 && wide) { const int4 L = sp.lay[lbase]; mz_lat_dense_wide(sp.w + L.w, L.x, L.y, L.z & 0xffff, L.z >> 16, cur, d, t); }
+        else mz_lat_apply(c, cur, d, t);
+        cur = d;
+        if (trunk && last_of_chain && heads) asm volatile("bar.sync 3, 128;" ::: "memory");
+        else if (i + 1 < my_n) asm volatile("bar.sync %0, 64;" ::"r"(half + 1) : "memory");
+        i++;
+    };
+    while (i < my_n) {
+        layer(c0, c1);
+        if (i >= my_n) break;
+        layer(c1, c0);
     }
 }
 
@@ -191,7 +177,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
     const mz_lat_net_s net_rep = {P.nets[0].first, P.nets[0].n_trunk, P.nets[0].n_h1, P.nets[0].n_h2}, net_pre = {P.nets[1].first, P.nets[1].n_trunk, P.nets[1].n_h1, P.nets[1].n_h2},
                        net_dyn = {P.nets[2].first, P.nets[2].n_trunk, P.nets[2].n_h1, P.nets[2].n_h2};
     if (tid == 0) {
-        mz_mbar_init(sp.mbar, 1); mz_mbar_init(sp.lbar, MZ_LAT_THREADS); mz_fence_mbar_init();
+        mz_mbar_init(sp.mbar, 1); mz_fence_mbar_init();
         int goff = 0, off = 0;                                            // float offsets: in the global image (all layers in order), in this CTA's area
         for (int n = 0; n < 3; n++) {
             const mz_net &N = P.nets[n];
@@ -240,7 +226,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
     for (int j = 0; j < P.A; j++) if ((legal >> (P.order[j] - 1)) & 1u) posmask |= 1u << j;
     __syncthreads();
     mz_mbar_wait(sp.mbar, 0);
-    uint32_t phase = 0;                                                 // completed phases of the layer barrier
     cluster.sync();                                                     // both CTAs are resident: distributed shared memory may be written
 
     // One loop for both CTAs of the cluster (one call site per routine keeps the kernel's code small: with one warp per scheduler an
@@ -251,12 +236,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
     unsigned long long depth_sum = 0;
     mz_leaf leaf; leaf.node = 0; leaf.parent = 0; leaf.action = 1; leaf.depth = 0; leaf.prior = 0.0f; leaf.parent_x = 0;
 #ifdef MZ_LAT_TIMERS
-    long long ntl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define MZ_NTP ntl
     long long lt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lt0 = clock64();
 #define MZ_LT(i) do { long long c_ = clock64(); lt[i] += c_ - lt0; lt0 = c_; } while (0)
 #else
-#define MZ_NTP nullptr
 #define MZ_LT(i)
 #endif
     for (int it = rank == 0 ? -1 : 1; it <= P.S; it++) {
@@ -283,10 +265,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
             const mz_lat_net_s N = rank == 1 ? net_dyn : it < 0 ? net_rep : net_pre;
             const float *src = rank == 1 ? sp.xdyn : it == 0 ? sp.outH : sp.xin;
             float *d1 = rank == 1 ? r_outH : it < 0 ? sp.outH : sp.outV, *d2 = rank == 1 ? r_outR : sp.outL;
-            mz_lat_net(sp, N, src, d1, d2, phase, it >= 1, it >= 1 ? MZ_NTP : nullptr);
+            mz_lat_net(sp, N, src, d1, d2, it >= 1);
         }
         MZ_LT(3);
-        if (it >= 1) cluster.sync();                                                         // dynamics outputs have landed in CTA 0
+        if (it >= 1) cluster.sync();                                                         // both networks' outputs are visible; dynamics' have landed in CTA 0
+        else __syncthreads();
         MZ_LT(4);
         if (lanes && active && it >= 0) {
             float *nh = tree.hidden + (size_t)it * P.hidden_pad;
@@ -304,7 +287,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
     }
     if (rank == 1) return;
 #ifdef MZ_LAT_TIMERS
-    if (tid == 0 && g == 0) printf("net timers (cycles / simulation, thread 0): apply %lld preload %lld barrier %lld chain %lld epilogue %lld\n", ntl[0] / P.S, ntl[1] / P.S, ntl[2] / P.S, ntl[5] / P.S, ntl[6] / P.S);
     if (tid == 0 && g == 0) printf("lat timers (cycles / simulation): select %lld stage %lld sync1 %lld pred %lld sync2(wait dyn) %lld expand %lld backup %lld loop %lld\n",
                                    lt[0] / P.S, lt[1] / P.S, lt[2] / P.S, lt[3] / P.S, lt[4] / P.S, lt[5] / P.S, lt[6] / P.S, lt[7] / P.S);
 #endif
