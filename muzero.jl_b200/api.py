@@ -14,6 +14,8 @@ deveshjawla/MuZero.jl; citations are file:line under /root/reference).  Every fu
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
+import warnings
+
 import numpy as np
 
 from . import capi
@@ -121,6 +123,8 @@ def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.G
     c.td_steps = conf.td_steps
     c.batch_size = conf.batch_size
     c.replay_buffer_size = max(conf.replay_buffer_size, num_slots)
+    if c.replay_buffer_size != conf.replay_buffer_size:   # a wave saves up to num_slots games at once: the ring cannot be smaller (say so, do not do it silently)
+        warnings.warn("replay_buffer_size %d raised to num_slots = %d" % (conf.replay_buffer_size, num_slots))
     c.pb_c_base = conf.pb_c_base
     c.intermediate_rewards = int(conf.intermediate_rewards)
     c.tie_mode = tie_mode

@@ -989,6 +989,10 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = G; a.max_dim = c->M.max_dim;
     a.max_layer_floats = c->M.max_layer_floats; a.exploration = 1 /* play_game hard-codes exploration=true, SelfPlay.jl:359 */;
     a.slots = c->slots; a.temperature = temperature; a.stats = c->d_stats;
+    // A wave starts with every slot idle and games are handed out in slot order, so a call for n_games <= num_slots games only ever uses the
+    // slots [0, n_games): few games go to the low-latency kernel whatever the context's size (the bf16 mode keeps its own arithmetic)
+    const int G_lat = (int64_t)G < n_games ? G : (int)n_games;
+    const bool use_lat = c->lat_ok && G_lat >= 1 && G_lat <= c->lat_max_slots && c->cfg.nn_mode != MZ_NN_BF16_TC;
     int64_t total_moves = 0;
     // The host runs one iteration behind the device: iteration k (opponent plies, search, save/refill, counter snapshot) is queued before
     // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,
@@ -1003,10 +1007,10 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         if (arena_player != 0) { launch_scope ls(c, 6); mz_k_opponent_move<<<(G + 127) / 128, 128, 0, c->stream>>>(P, c->slots, G); }
-        if (c->lat_ok && G <= c->lat_max_slots && c->cfg.nn_mode == MZ_NN_FP32_EXACT) {   // few slots (play_game one game at a time): one tree per cluster
+        if (use_lat) {   // few games (play_game one game at a time): one tree per cluster (mz_kernels_lat.cuh), exact fp32
             MZ_TRY(ensure_lat_image(c));
             mz_lat_args t{}; t.base = a; t.image = c->d_w_lat; t.w_floats = c->lat_w_floats; t.pbc_smem = c->lat_pbc_smem;
-            launch_scope ls(c, 0); mz_k_search_lat<MZ_MODE_SLOTS><<<2 * G, MZ_LAT_THREADS, c->smem_bytes_lat, c->stream>>>(P, t);
+            launch_scope ls(c, 0); mz_k_search_lat<MZ_MODE_SLOTS><<<2 * G_lat, MZ_LAT_THREADS, c->smem_bytes_lat, c->stream>>>(P, t);
         } else if (c->cfg.net_type == MZ_NET_RESNET) {
             mz_search_rn_args t{}; t.base = a; t.image = c->d_rn_image; t.steps = c->d_rn_steps;
             const int nt = c->rn.R.ntrees;

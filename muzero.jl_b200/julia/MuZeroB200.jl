@@ -57,6 +57,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096, nn_mode
     c.A = length(conf.action_space); c.num_players = length(conf.players)
     c.stacked_observations = conf.stacked_observations; c.max_moves = conf.max_moves; c.num_iters = conf.num_iters
     c.num_unroll_steps = conf.num_unroll_steps; c.td_steps = conf.td_steps; c.batch_size = conf.batch_size
+    conf.replay_buffer_size < num_slots && @warn "replay_buffer_size raised to num_slots (a wave saves up to num_slots games at once)" conf.replay_buffer_size num_slots
     c.replay_buffer_size = max(conf.replay_buffer_size, num_slots); c.pb_c_base = conf.pb_c_base
     c.intermediate_rewards = conf.intermediate_rewards; c.pb_c_init = conf.pb_c_init; c.discount = conf.discount
     c.dirichlet_alpha = conf.dirichlet_α; c.exploration_eps = conf.exploration_ϵ; c.seed = conf.seed

@@ -93,3 +93,22 @@ def test_lat_arena_bit_exact(capi):
     oa = O.arena(ocfg, blob, 50, 24, O.OPP_EXPERT, 2, 0.0, 4)["outcome"]
     assert (ar["wins"], ar["draws"], ar["losses"]) == (int((oa == 1).sum()), int((oa == 0).sum()), int((oa == -1).sum()))
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["exact", "split"])
+def test_lat_few_games_on_a_large_context(capi, mode):
+    """play_game one game at a time on an engine built for 4096 concurrent games: the call goes to mz_k_search_lat (exact fp32 in both modes)"""
+    import time
+    ctx, ocfg = make_ctx(capi, num_slots=4096, replay_buffer_size=8192, num_iters=50, exploration_eps=0.25,
+                         nn_mode=capi.NN_SPLIT_MMA if mode == "split" else capi.NN_FP32_EXACT)
+    ctx.init_weights(12); blob = ctx.get_weights()
+    ctx.self_play(0, 1, 1.0)                                   # warm-up (weight image)
+    t0 = time.perf_counter(); sims, moves = ctx.self_play(500, 3, 1.0); dt = time.perf_counter() - t0
+    o = O.self_play(ocfg, blob, 500, 3, 1.0, 1)
+    assert sims == o["sims"] and moves == int(o["T"].sum())
+    h = ctx.history_export()
+    sel = [int(np.flatnonzero(h["game_id"] == 500 + i)[0]) for i in range(3)]
+    for k in common.HIST_KEYS:
+        assert np.array_equal(h[k][sel], o[k]), k
+    print("3 games on a 4096-slot %s context: %.2f ms (%d plies)" % (mode, dt * 1e3, int(o["T"].max())))
+    ctx.close()
