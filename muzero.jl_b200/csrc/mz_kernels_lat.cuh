@@ -31,7 +31,7 @@ struct mz_lat_plan {
 MZ_HD size_t mz_lat_smem_bytes(int w_floats, int max_dim, int hidden_pad, int tree_bytes, int S, int pbc_smem) {
     size_t w = ((size_t)w_floats * 4 + 256 + 127) & ~(size_t)127;   // + slack: a row fetch reads 64 floats whatever `in` is
     size_t md = ((size_t)(max_dim > 64 ? max_dim : 64) * 4 + 15) & ~(size_t)15;
-    size_t out = ((size_t)(4 + 16 + 4 + hidden_pad) * 4 + 127) & ~(size_t)127;
+    size_t out = ((size_t)(4 + 16 + 4 + (hidden_pad > 64 ? hidden_pad : 64)) * 4 + 127) & ~(size_t)127;   // outH is also a layer INPUT (root prediction): 64 readable floats
     size_t tree = ((size_t)tree_bytes + 127) & ~(size_t)127;
     size_t tab = pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     size_t path = (((size_t)S + 2) * 2 + 127) & ~(size_t)127;
@@ -43,7 +43,7 @@ __device__ __forceinline__ mz_lat_plan mz_lat_carve(unsigned char *c, int w_floa
     p.w = (float *)c; c += ((size_t)w_floats * 4 + 256 + 127) & ~(size_t)127;
     p.xin = (float *)c; c += md; p.xdyn = (float *)c; c += md; p.bufT = (float *)c; c += md;
     p.tb = (float *)c; p.md = (int)(md / 4); c += 4 * md;
-    p.outV = (float *)c; p.outL = p.outV + 4; p.outR = p.outV + 20; p.outH = p.outV + 24; c += ((size_t)(24 + hidden_pad) * 4 + 127) & ~(size_t)127;
+    p.outV = (float *)c; p.outL = p.outV + 4; p.outR = p.outV + 20; p.outH = p.outV + 24; c += ((size_t)(24 + (hidden_pad > 64 ? hidden_pad : 64)) * 4 + 127) & ~(size_t)127;
     p.tree = c; c += ((size_t)tree_bytes + 127) & ~(size_t)127;
     p.pbc = (double *)c; c += pbc_smem ? ((((size_t)S + 2) * ((size_t)S + 3) / 2) * 8 + 127) & ~(size_t)127 : 0;
     p.path = (uint16_t *)c; c += (((size_t)S + 2) * 2 + 127) & ~(size_t)127;
@@ -195,7 +195,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MZ_LAT_THREADS) mz_k
                 mz_bulk_g2s(sp.w + sp.lay[l].w, la.image + sp.gofs[l], (uint32_t)mz_lat_layer_floats(P.layers[l].in, P.layers[l].out) * 4u, sp.mbar);
         }
     }
-    for (int i = tid; i < (int)((sp.outV - sp.xin)); i += MZ_LAT_THREADS) sp.xin[i] = 0.0f;   // xin, xdyn, bufT, t[][]: finite beyond every layer's `in`
+    // every buffer a layer reads its input from holds 64 readable floats, finite beyond the layer's `in` (zero weights meet them there):
+    // xin, xdyn, bufT, the ping / pong buffers and the output block (outH is the root prediction's input)
+    for (int i = tid; i < (int)((float *)sp.tree - sp.xin); i += MZ_LAT_THREADS) sp.xin[i] = 0.0f;
     __syncthreads();
     const int ln = tid & (MZ_LANES - 1);
     const uint32_t segmask = 0xffu;
