@@ -97,7 +97,7 @@ struct mz_ctx {
     float *d_pv = nullptr, *d_pr = nullptr, *d_pp = nullptr, *d_rowv = nullptr, *d_rowp = nullptr, *d_rowinvg = nullptr;
     double *d_rowr = nullptr, *d_lossout = nullptr;
     int64_t *h_counters = nullptr; double *h_lossout = nullptr; unsigned long long *h_stats = nullptr;   // pinned
-    int64_t *h_wave = nullptr; cudaEvent_t ev_wave[2] = {nullptr, nullptr};   // pinned: two snapshots of the counters, self-play runs one iteration ahead of the host
+    int64_t *h_wave = nullptr, *d_wave = nullptr; cudaEvent_t ev_wave[2] = {nullptr, nullptr};   // pinned: two snapshots of the counters, self-play runs one iteration ahead of the host
     dev_buf scratch[12];
     int64_t adam_t = 0; double bp1 = 0.9, bp2 = 0.999;
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
@@ -669,7 +669,8 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     MZ_CREATE(dmalloc(&c->d_stats, 64)); MZ_CREATE(cudaMemset(c->d_stats, 0, 64 * sizeof(unsigned long long)));
     MZ_CREATE(dmalloc(&c->d_lossout, 8));
     MZ_CREATE(cudaMallocHost((void **)&c->h_counters, 8 * sizeof(int64_t)));
-    MZ_CREATE(cudaMallocHost((void **)&c->h_wave, 16 * sizeof(int64_t)));
+    MZ_CREATE(cudaHostAlloc((void **)&c->h_wave, 16 * sizeof(int64_t), cudaHostAllocMapped));   // mz_k_save_refill writes its counter snapshot straight into it
+    MZ_CREATE(cudaHostGetDevicePointer((void **)&c->d_wave, c->h_wave, 0));
     for (int i = 0; i < 2; i++) MZ_CREATE(cudaEventCreateWithFlags(&c->ev_wave[i], cudaEventDisableTiming));
     MZ_CREATE(cudaMallocHost((void **)&c->h_lossout, 8 * sizeof(double)));
     MZ_CREATE(cudaMallocHost((void **)&c->h_stats, 64 * sizeof(unsigned long long)));
@@ -949,8 +950,8 @@ int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32
 
 // ---- self-play ---------------------------------------------------------------------------------------------
 // save_game + refill: number the finished games and hand out new ones (one CTA, ordered), copy their histories (many CTAs), priorities
-static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally) {
-    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally, c->refill_wave_sync); }
+static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally, int64_t *snap = nullptr) {
+    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally, c->refill_wave_sync, snap); }
     { launch_scope ls(c, 1); mz_k_save_copy<<<c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
     if (P.per) { launch_scope ls(c, 1); mz_k_save_per<<<(G + 255) / 256 < c->sm_count ? (G + 255) / 256 : c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
     return MZ_OK;
@@ -998,11 +999,10 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,
     // the iteration already queued finds every slot idle: each search CTA returns at its first instruction.
     auto snapshot = [&](int i) -> int {
-        MZ_CUDA(c, cudaMemcpyAsync(c->h_wave + 8 * i, c->ring.counters, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
         MZ_CUDA(c, cudaEventRecord(c->ev_wave[i], c->stream));
         return MZ_OK;
     };
-    MZ_TRY(launch_save_refill(c, P, G, tally));
+    MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave));
     MZ_TRY(snapshot(0));
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
@@ -1025,7 +1025,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         const size_t search_entry = c->timed.size();                       // (timing builds) index just past this iteration's search launch
-        MZ_TRY(launch_save_refill(c, P, G, tally));
+        MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave + 8 * ((k + 1) & 1)));
         MZ_TRY(snapshot((int)((k + 1) & 1)));
         MZ_CUDA(c, cudaGetLastError());
         MZ_CUDA(c, cudaEventSynchronize(c->ev_wave[k & 1]));

@@ -465,7 +465,8 @@ __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n,
 // free slots.  Single CTA: the order in which games receive their game number must be deterministic.
 #define MZ_SAVE_MAX_K 64   // slots per thread of mz_k_save_refill: num_slots <= 65536
 #define MZ_FIN_KEY(n) (((n) + 3) & ~1)   // fin_list[n] = number of games; the 64-bit first key - 1 sits at the next 8-byte aligned pair (fin_list has n + 6 entries)
-__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr, int wave_sync = 0) {
+__global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__ mz_params P, mz_slots s, mz_ring r, int n_slots, unsigned long long *arena_tally = nullptr, int wave_sync = 0,
+                                                          int64_t *snap = nullptr /* mapped host memory: the counters after this kernel, read by the self-play loop */) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ int active_count;
     __shared__ long long add_steps, add_samples;
@@ -534,6 +535,11 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
         r.counters[2] += add_samples;
         r.counters[3] = next_game + handed;
         r.counters[5] = active_count;
+        if (snap) {   // instead of a device-to-host copy between the kernels of every move (a copy-engine operation in the stream costs more than the kernel)
+            snap[0] = base_key + total_fin; snap[1] = r.counters[1]; snap[2] = r.counters[2]; snap[3] = next_game + handed; snap[4] = end_game; snap[5] = active_count;
+            snap[6] = r.counters[6]; snap[7] = r.counters[7];
+            __threadfence_system();
+        }
     }
 }
 
