@@ -408,6 +408,16 @@ def run_b200(a):
         for _ in range(20):
             ctx.run_mcts(*one)
         single_root_ms = (time.perf_counter() - t0_) / 20 * 1e3
+        # the same call with a few more roots (mz_k_search_lat serves calls of up to 74 roots in this mode: one tree per two-SM cluster)
+        small_calls = {}
+        for n_roots in (8, 74):
+            stn = np.zeros((n_roots, 63), np.float32); stn[:, 18:27] = 1
+            few = (stn, np.full(n_roots, 0x1ff, np.uint32), np.ones(n_roots, np.int32), True, np.arange(n_roots, dtype=np.uint64), np.ones(n_roots, np.int32))
+            ctx.run_mcts(*few)
+            t0_ = time.perf_counter()
+            for _ in range(10):
+                ctx.run_mcts(*few)
+            small_calls["%d_roots_ms" % n_roots] = (time.perf_counter() - t0_) / 10 * 1e3
         barrier()
         # ---- strong scaling ("also report fixed total G"): the 4096 games of the 1-GPU workload split over the ranks ----
         strong = None
@@ -558,6 +568,8 @@ def run_b200(a):
             "clocks": clocks,
             "parity_checked": parity,
             "single_root_latency_ms": single_root_ms,
+            "small_call_latency": dict(small_calls, kernel="mz_k_search_lat (one tree per 2-CTA cluster, exact fp32, bit-identical to the oracle)",
+                                       note="one run_mcts call through the host API, host buffers in and out; the C port of the reference needs ~0.24 ms per root on one core"),
             "roofline": roof,
         }
         if a.nn == "fp32" and avg_launch_s > 0 and clocks.get("sm_mhz"):
