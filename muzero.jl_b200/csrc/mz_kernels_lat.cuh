@@ -84,13 +84,17 @@ __device__ __forceinline__ void mz_lat_preload(mz_lat_col &c, const mz_lat_plan 
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.b) : "r"(mz_smem_u32(sp.w + L.w) + 4u * (uint32_t)(c.out * L.y + t)));
     }
 }
-__device__ __forceinline__ void mz_lat_apply(const mz_lat_col &c, const float *x, float *y, int t) {
-    if (t >= c.out) return;
-    float acc = 0.0f;
+// `fetch_next` runs between the loads of the input vector and the fmaf chain: the fetch of the next layer's weight row (64 shared-memory
+// wavefronts per warp) must not be queued in FRONT of the 16 broadcast loads the chain waits for
+template <typename F>
+__device__ __forceinline__ void mz_lat_apply(const mz_lat_col &c, const float *x, float *y, int t, F fetch_next) {
     const uint32_t xa = mz_smem_u32(x);
-    float4 xv[MZ_LAT_KMAX / 4];                                           // every activation buffer holds at least MZ_LAT_KMAX floats
+    float4 xv[MZ_LAT_KMAX / 4];                                           // every activation buffer holds at least MZ_LAT_KMAX readable floats
 #pragma unroll
     for (int k4 = 0; k4 < MZ_LAT_KMAX / 4; k4++) xv[k4] = mz_lds128(xa + 16u * (uint32_t)k4);
+    fetch_next();
+    if (t >= c.out) return;
+    float acc = 0.0f;
     // One straight chain of 64 fmaf for every layer: the image's rows are zero beyond `in` and the activation buffers hold finite values
     // there (zeroed at kernel start, later only layer outputs), so the extra links add +-0 to the sum.  That leaves the sum unchanged
     // bit for bit (x + (+-0) = x for every x but -0, and a sum that starts at +0 only becomes -0 through an fp32 underflow).
@@ -136,12 +140,12 @@ __device__ __forceinline__ void mz_lat_net(const mz_lat_plan &sp, const mz_lat_n
     const float *cur = half == 0 ? src : sp.bufT;
     int i = 0;
     auto layer = [&](mz_lat_col &c, mz_lat_col &n) {
-        if (i + 1 < my_n) mz_lat_preload(n, sp, lbase + i + 1, t);
         const bool trunk = half == 0 && i < N.n_trunk;
         const bool last_of_chain = trunk ? i == N.n_trunk - 1 : i == my_n - 1;
         float *d = trunk ? (last_of_chain ? (heads ? sp.bufT : h1dst) : sp.tb + (i & 1) * sp.md) : (last_of_chain ? (half == 0 ? h1dst : h2dst) : sp.tb + (2 * half + (i & 1)) * sp.md);
-        if (i == 0 && wide) { const int4 L = sp.lay[lbase]; mz_lat_dense_wide(sp.w + L.w, L.x, L.y, L.z & 0xffff, L.z >> 16, cur, d, t); }
-        else mz_lat_apply(c, cur, d, t);
+        auto fetch_next = [&] { if (i + 1 < my_n) mz_lat_preload(n, sp, lbase + i + 1, t); };
+        if (i == 0 && wide) { fetch_next(); const int4 L = sp.lay[lbase]; mz_lat_dense_wide(sp.w + L.w, L.x, L.y, L.z & 0xffff, L.z >> 16, cur, d, t); }
+        else mz_lat_apply(c, cur, d, t, fetch_next);
         cur = d;
         if (trunk && last_of_chain && heads) asm volatile("bar.sync 3, 128;" ::: "memory");
         else if (i + 1 < my_n) asm volatile("bar.sync %0, 64;" ::"r"(half + 1) : "memory");
