@@ -131,6 +131,10 @@ int mz_env_legal(mz_ctx *ctx, int n, const uint64_t *p1, const uint64_t *p2, con
 int mz_env_observation(mz_ctx *ctx, int n, const uint64_t *p1, const uint64_t *p2, float *obs /* [n][C][H][W] */);
 
 /* ---- MCTS: run_mcts (src/SelfPlay.jl:230-285), batched over n independent roots -------------- */
+/* Calls with few roots (FeedForwardHP networks without BatchNorm: n <= 148 in MZ_NN_FP32_EXACT contexts, n <= 74 in MZ_NN_SPLIT_MMA
+ * contexts) are served by the low-latency kernel mz_k_search_lat -- one tree per two-SM thread-block cluster, networks and tree
+ * resident in shared memory, exact fp32, results bit-identical to the batched exact kernel (0.44 ms for one root); the same holds
+ * for mz_self_play / mz_arena / mz_play_games calls of <= 16 games.  Environment MUZERO_B200_LAT=n moves both limits (0 = off). */
 int mz_run_mcts(mz_ctx *ctx, int n, const float *stacked_obs /* [n][stack] */, const uint32_t *legal_mask,
                 const int32_t *to_play, int exploration, const uint64_t *game_id, const int32_t *move_idx,
                 int32_t *visit_counts /* [n][A] */, float *root_value /* [n] */, float *root_priors /* [n][A], may be NULL */);
