@@ -112,3 +112,38 @@ def test_lat_few_games_on_a_large_context(capi, mode):
         assert np.array_equal(h[k][sel], o[k]), k
     print("3 games on a 4096-slot %s context: %.2f ms (%d plies)" % (mode, dt * 1e3, int(o["T"].max())))
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lat_randomised_configurations_bit_exact(capi, seed):
+    """randomly drawn network shapes (depth 0 heads and trunks, widths 32 / 48 / 64, stacking depth 0..2), PUCT constants and simulation
+    counts: run_mcts with a few roots and a few whole games through mz_k_search_lat, bit-identical to the oracle"""
+    rng = np.random.default_rng(700 + seed)
+    kw = dict(num_iters=int(rng.integers(3, 60)), stacked_observations=int(rng.integers(0, 3)), pb_c_base=int(rng.integers(50, 30000)),
+              pb_c_init=float(np.float32(rng.uniform(0.5, 2.5))), discount=float(np.float32(rng.uniform(0.8, 1.0))),
+              dirichlet_alpha=float(np.float32(rng.uniform(0.1, 1.0))), exploration_eps=float(np.float32(rng.choice([0.0, 0.25, 0.5]))),
+              depth_representation=int(rng.integers(0, 4)), depth_prediction=int(rng.integers(0, 4)), depth_dynamics=int(rng.integers(0, 4)),
+              depth_policy=int(rng.integers(0, 3)), depth_value=int(rng.integers(0, 3)), depth_reward=int(rng.integers(0, 3)),
+              depth_state_head=int(rng.integers(0, 4)), width_hidden=int(rng.choice([32, 48, 64])), seed=int(rng.integers(1, 1 << 30)),
+              tie_mode=int(rng.integers(0, 2)), num_slots=int(rng.integers(1, 40)))
+    ctx, ocfg = make_ctx(capi, replay_buffer_size=256, **kw)
+    ctx.init_weights(seed + 90); blob = ctx.get_weights()
+    n = int(rng.integers(1, 30))
+    st, legal, tp = common.random_stacked(ocfg, n, seed=seed)
+    game = np.arange(n, dtype=np.uint64) + 3; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    before = ctx.launch_count()
+    vc, rv, pri = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    assert ctx.launch_count() <= before + 2, kw                          # one search launch (+ the weight image): not chunks of num_slots roots
+    for i in range(n):
+        ovc, orv, opri = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i]))
+        assert vc[i].tolist() == ovc.tolist() and rv[i] == orv and np.array_equal(pri[i], opri), (i, kw)
+    games = int(rng.integers(1, 17)); temperature = float(rng.choice([0.0, 0.5, 1.0]))
+    sims, moves = ctx.self_play(50, games, temperature)
+    o = O.self_play(ocfg, blob, 50, games, temperature, 2)
+    assert sims == o["sims"] and moves == int(o["T"].sum()), kw
+    h = ctx.history_export()
+    for j in range(games):
+        i = int(h["game_id"][j]) - 50
+        for k in common.HIST_KEYS:
+            assert np.array_equal(h[k][j], o[k][i]), (k, i, kw)
+    ctx.close()
