@@ -65,6 +65,7 @@ extern "C" { static void p2p_teardown(mz_ctx *c); }
 struct mz_ctx {
     mz_config cfg; mzh::model M; int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = false;
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_search[2] = {nullptr, nullptr};   // save / refill of move k beside the search of move k + 1 (run_wave)
     std::string err;
     size_t smem_bytes = 0; int sm_count = 0;
     int exact_gt = 128;   // threads per network group of the exact search kernel: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps; measured no faster: the layer is bound by shared-memory wavefronts)
@@ -122,18 +123,19 @@ int fail(mz_ctx *c, int code, const char *fmt, ...) {
 #define MZ_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail((c), MZ_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define MZ_CHECK_CTX(c) do { if (!(c)) return fail(nullptr, MZ_E_ARG, "ctx is NULL"); MZ_CUDA((c), cudaSetDevice((c)->device)); } while (0)
 
-struct launch_scope {   // counts launches and, when enabled, brackets them with events on the ctx stream
-    mz_ctx *c; int family; cudaEvent_t a = nullptr, b = nullptr;
-    launch_scope(mz_ctx *c_, int fam) : c(c_), family(fam) {
+struct launch_scope {   // counts launches and, when enabled, brackets them with events on the stream they go to (default: the ctx stream)
+    mz_ctx *c; int family; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    launch_scope(mz_ctx *c_, int fam, cudaStream_t st_ = nullptr) : c(c_), family(fam), st(st_ ? st_ : c_->stream) {
         c->launches++;
-        if (c->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+        if (c->timing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
-    ~launch_scope() { if (c->timing) { cudaEventRecord(b, c->stream); c->timed.push_back({a, b, family}); } }
+    ~launch_scope() { if (c->timing) { cudaEventRecord(b, st); c->timed.push_back({a, b, family}); } }
 };
 
 void collect_timings(mz_ctx *c) {
     if (c->timed.empty()) return;
     cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     for (auto &t : c->timed) {
         float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
         c->fam_ms[t.family] += ms; c->fam_n[t.family]++;
@@ -634,6 +636,8 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
         }
     }
     MZ_CREATE(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
+    MZ_CREATE(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) MZ_CREATE(cudaEventCreateWithFlags(&c->ev_search[i], cudaEventDisableTiming));
     const size_t nf = (size_t)P.total_floats;
     MZ_CREATE(dmalloc(&c->d_w, nf)); MZ_CREATE(dmalloc(&c->d_m, nf)); MZ_CREATE(dmalloc(&c->d_v, nf)); MZ_CREATE(dmalloc(&c->d_grad, nf));
     MZ_CREATE(cudaMemset(c->d_w, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_m, 0, nf * 4)); MZ_CREATE(cudaMemset(c->d_v, 0, nf * 4));
@@ -702,6 +706,8 @@ int mz_destroy(mz_ctx *c) {
     for (int i = 0; i < 2; i++) if (c->ev_wave[i]) cudaEventDestroy(c->ev_wave[i]);
     if (c->h_lossout) cudaFreeHost(c->h_lossout);
     if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    for (int i = 0; i < 2; i++) if (c->ev_search[i]) cudaEventDestroy(c->ev_search[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MZ_OK;
@@ -950,15 +956,17 @@ int mz_select_action(mz_ctx *c, int n, const int32_t *visit_counts, const uint32
 
 // ---- self-play ---------------------------------------------------------------------------------------------
 // save_game + refill: number the finished games and hand out new ones (one CTA, ordered), copy their histories (many CTAs), priorities
-static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally, int64_t *snap = nullptr) {
-    { launch_scope ls(c, 1); mz_k_save_refill<<<1, 1024, 0, c->stream>>>(P, c->slots, c->ring, G, tally, c->refill_wave_sync, snap); }
-    { launch_scope ls(c, 1); mz_k_save_copy<<<c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
-    if (P.per) { launch_scope ls(c, 1); mz_k_save_per<<<(G + 255) / 256 < c->sm_count ? (G + 255) / 256 : c->sm_count, 256, 0, c->stream>>>(P, c->slots, c->ring, G); }
+static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned long long *tally, int64_t *snap = nullptr, cudaStream_t st = nullptr) {
+    if (!st) st = c->stream;
+    { launch_scope ls(c, 1, st); mz_k_save_refill<<<1, 1024, 0, st>>>(P, c->slots, c->ring, G, tally, c->refill_wave_sync, snap); }
+    { launch_scope ls(c, 1, st); mz_k_save_copy<<<c->sm_count, 256, 0, st>>>(P, c->slots, c->ring, G); }
+    if (P.per) { launch_scope ls(c, 1, st); mz_k_save_per<<<(G + 255) / 256 < c->sm_count ? (G + 255) / 256 : c->sm_count, 256, 0, st>>>(P, c->slots, c->ring, G); }
     return MZ_OK;
 }
 // one wave of games on the slots; arena_player != 0: competitive play, `arena_opponent` moves for the other side
 // every slot idle, no game in flight: the state a wave starts from (also the recovery after a wave that ended with an error)
 static int slots_reset(mz_ctx *c) {
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     MZ_CUDA(c, cudaMemsetAsync(c->slots.status, 0, (size_t)c->cfg.num_slots * sizeof(int32_t), c->stream));
     MZ_CUDA(c, cudaMemsetAsync(c->ring.counters + 5, 0, sizeof(int64_t), c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -998,14 +1006,22 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     // The host runs one iteration behind the device: iteration k (opponent plies, search, save/refill, counter snapshot) is queued before
     // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,
     // the iteration already queued finds every slot idle: each search CTA returns at its first instruction.
+    // Single-wave calls (n_games <= num_slots: every game is handed out by the first refill): the save / refill kernels of move k only touch
+    // slots that finished in move k (status tag P.fin_tag) and the ring, the search of move k + 1 only active slots -- so they run side by
+    // side: save / refill on a second stream behind an event of search k, the searches back to back on the main stream.  The 128 search CTAs
+    // leave 20 SMs free, which is where the small kernels go.
+    const bool overlap = n_games <= (int64_t)G && c->stream2 != nullptr && !getenv("MUZERO_B200_NO_OVERLAP");
+    cudaStream_t sB = overlap ? c->stream2 : c->stream;
     auto snapshot = [&](int i) -> int {
-        MZ_CUDA(c, cudaEventRecord(c->ev_wave[i], c->stream));
+        MZ_CUDA(c, cudaEventRecord(c->ev_wave[i], sB));
         return MZ_OK;
     };
+    P.fin_tag = 0;
     MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave));
-    MZ_TRY(snapshot(0));
+    MZ_CUDA(c, cudaEventRecord(c->ev_wave[0], c->stream));
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
+        P.fin_tag = (int32_t)(k & 1);
         if (arena_player != 0) { launch_scope ls(c, 6); mz_k_opponent_move<<<(G + 127) / 128, 128, 0, c->stream>>>(P, c->slots, G); }
         if (use_lat) {   // few games (play_game one game at a time): one tree per cluster (mz_kernels_lat.cuh), exact fp32
             MZ_TRY(ensure_lat_image(c));
@@ -1025,7 +1041,8 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         else if (c->exact_gt == 256) { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS, 256><<<(G + MZ_ROWS - 1) / MZ_ROWS, 512, c->smem_bytes, c->stream>>>(P, a); }
         else { launch_scope ls(c, 0); mz_k_search<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_THREADS, c->smem_bytes, c->stream>>>(P, a); }
         const size_t search_entry = c->timed.size();                       // (timing builds) index just past this iteration's search launch
-        MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave + 8 * ((k + 1) & 1)));
+        if (overlap) { MZ_CUDA(c, cudaEventRecord(c->ev_search[k & 1], c->stream)); MZ_CUDA(c, cudaStreamWaitEvent(sB, c->ev_search[k & 1], 0)); }
+        MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave + 8 * ((k + 1) & 1), sB));
         MZ_TRY(snapshot((int)((k + 1) & 1)));
         MZ_CUDA(c, cudaGetLastError());
         MZ_CUDA(c, cudaEventSynchronize(c->ev_wave[k & 1]));
@@ -1038,6 +1055,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         }
         total_moves += active;
     }
+    if (overlap) MZ_CUDA(c, cudaStreamSynchronize(sB));                   // the last save / refill (tallies, counters) before anything else runs on the main stream
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     if (simulations) *simulations = (int64_t)c->h_stats[1];

@@ -166,7 +166,9 @@ struct mz_params {
     int32_t tc_ksteps[MZ_MAX_LAYERS];  // ceil(in / 16) tcgen05.mma instructions per layer
     int32_t tc_net_off[4];             // byte offset of each network's block; [3] = total image bytes
     int32_t tc_bias_off[MZ_MAX_LAYERS];// float offset of the layer's bias inside the bias block
-    int32_t tc_bias_floats, tc_ok, tc_pad_[2];
+    int32_t tc_bias_floats, tc_ok;
+    int32_t fin_tag, tc_pad_;          // fin_tag: parity of the self-play iteration (set per launch): a slot finished in iteration k carries status MZ_SLOT_FINISHED + (k & 1),
+                                       // so that the save / refill kernels of iteration k can run beside the search of iteration k + 1 without taking its finishes
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ enum { MZ_MODE_API = 0, MZ_MODE_SLOTS = 1 };
 #define MZ_TIMER(i)
 #define MZ_TIMER_FLUSH(stats)
 #endif
-enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 };
+enum { MZ_SLOT_IDLE = 0, MZ_SLOT_ACTIVE = 1, MZ_SLOT_FINISHED = 2 /* + P.fin_tag: 2 or 3 */ };
 
 struct mz_slots {          // device-resident concurrent games, SoA
     uint64_t *p1, *p2; int32_t *player, *T, *status; int64_t *game_id;
@@ -208,7 +208,7 @@ __device__ __forceinline__ void mz_slot_epilogue(const mz_params &P, const mz_sl
     T += 1;
     s.p1[g] = b.p1; s.p2[g] = b.p2; s.player[g] = b.player; s.T[g] = T;
     if (T < P.Tmax) { s.h_p1[(size_t)g * P.Tmax + T] = b.p1; s.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
-    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED;                    // loop condition :343
+    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED + P.fin_tag;                    // loop condition :343
 }
 
 // GT = threads per network group: 128 (4x4 register tiles) or 256 (2x4 tiles, twice the warps for the same work; the tree
@@ -451,7 +451,7 @@ __global__ void mz_k_opponent_move(const __grid_constant__ mz_params P, mz_slots
     T += 1;
     s.p1[g] = b.p1; s.p2[g] = b.p2; s.player[g] = b.player; s.T[g] = T;
     if (T < P.Tmax) { s.h_p1[(size_t)g * P.Tmax + T] = b.p1; s.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
-    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED;
+    if (done || T > P.max_moves) s.status[g] = MZ_SLOT_FINISHED + P.fin_tag;
 }
 __global__ void mz_k_opponent_action(const __grid_constant__ mz_params P, int n, const uint64_t *p1, const uint64_t *p2, const int32_t *player, int opponent,
                                      const uint64_t *game_id, const int32_t *move_idx, int32_t *action) {
@@ -479,8 +479,10 @@ __global__ void __launch_bounds__(1024) mz_k_save_refill(const __grid_constant__
     unsigned long long fin_bits = 0, free_bits = 0;                        // per owned slot (K <= 64)
     for (int i = 0; lo + i < hi; i++) {
         const int st = s.status[lo + i];
-        if (st == MZ_SLOT_FINISHED) fin_bits |= 1ull << i;
-        if (st == MZ_SLOT_FINISHED || st == MZ_SLOT_IDLE) free_bits |= 1ull << i;
+        // finished in THIS iteration (tag = its parity); a slot the search of the next iteration -- which may run beside this kernel -- is
+        // finishing right now carries the other tag and counts as active: the next save / refill takes it
+        if (st == MZ_SLOT_FINISHED + P.fin_tag) fin_bits |= 1ull << i;
+        if (st == MZ_SLOT_FINISHED + P.fin_tag || st == MZ_SLOT_IDLE) free_bits |= 1ull << i;
     }
     const unsigned long long mine = ((unsigned long long)__popcll(fin_bits) << 32) | (unsigned long long)__popcll(free_bits);
     unsigned long long inc = mine;

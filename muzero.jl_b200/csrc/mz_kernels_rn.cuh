@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(MZ_RN_THREADS) mz_k_search_rn(const __grid_con
             T += 1;
             a.slots.p1[g] = b.p1; a.slots.p2[g] = b.p2; a.slots.player[g] = b.player; a.slots.T[g] = T;
             if (T < P.Tmax) { a.slots.h_p1[(size_t)g * P.Tmax + T] = b.p1; a.slots.h_p2[(size_t)g * P.Tmax + T] = b.p2; }
-            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED;
+            if (done || T > P.max_moves) a.slots.status[g] = MZ_SLOT_FINISHED + P.fin_tag;
         }
     }
     mz_rn_teardown(X);
