@@ -86,6 +86,7 @@ struct mz_ctx {
     float *d_w_lat = nullptr; uint64_t lat_version = 0; int lat_image_floats = 0;
     unsigned char *h_lat_stage = nullptr, *d_lat_stage = nullptr; size_t lat_stage_cap = 0;   // one pinned / device block for all inputs and outputs of a small run_mcts call
     bool lat_ok = false; int lat_w_floats = 0, lat_pbc_smem = 0, lat_max_roots = 0, lat_max_slots = 0; size_t smem_bytes_lat = 0;
+    bool slots_dirty = false;   // a wave is in progress or ended with an error: the slots are reset before the next one
     int refill_wave_sync = 1;   // 1: mz_k_save_refill starts new games only when every slot is free (default; MUZERO_B200_REFILL=immediate refills at once)
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
     mz_sp_plan spp{}; mz_sp_args spa{}; unsigned char *d_w_sp = nullptr; float *d_bias_sp = nullptr; mz_sp_round *d_rounds_sp = nullptr; size_t smem_bytes_sp = 0;   // split-precision tensor-core path
@@ -967,6 +968,7 @@ static int launch_save_refill(mz_ctx *c, const mz_params &P, int G, unsigned lon
 // every slot idle, no game in flight: the state a wave starts from (also the recovery after a wave that ended with an error)
 static int slots_reset(mz_ctx *c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    c->slots_dirty = false;
     MZ_CUDA(c, cudaMemsetAsync(c->slots.status, 0, (size_t)c->cfg.num_slots * sizeof(int32_t), c->stream));
     MZ_CUDA(c, cudaMemsetAsync(c->ring.counters + 5, 0, sizeof(int64_t), c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -989,10 +991,13 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     P.arena_player = arena_player; P.arena_opponent = arena_opponent; P.arena_tally = tally_player;
     unsigned long long *tally = c->d_stats + 61;   // wins, draws, losses (the last three of the 64 counters)
     const int G = c->cfg.num_slots;
-    MZ_TRY(read_counters(c));
-    if (c->h_counters[5] != 0) { MZ_TRY(slots_reset(c)); MZ_TRY(read_counters(c)); }   // left over from a wave that ended with an error
+    // A wave starts from idle slots: a successful wave ends with every slot idle, a failed one is followed by slots_reset (run_wave), so the
+    // device counters need not be read back here (two stream synchronisations per wave): only {next game id, end id, active games} go down,
+    // in stream order, from pinned memory
+    if (c->slots_dirty) MZ_TRY(slots_reset(c));
+    c->slots_dirty = true;
     c->h_counters[3] = (int64_t)first_game; c->h_counters[4] = (int64_t)first_game + n_games; c->h_counters[5] = 0;
-    MZ_TRY(write_counters(c));
+    MZ_CUDA(c, cudaMemcpyAsync(c->ring.counters + 3, c->h_counters + 3, 3 * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     MZ_CUDA(c, cudaMemsetAsync(c->d_stats, 0, 64 * sizeof(unsigned long long), c->stream));
     MZ_TRY(ensure_images(c));
     mz_search_args a{}; a.wglob = c->d_w; a.pbc0 = c->d_pbc0; a.sqrtN = c->d_sqrtN; a.tree_pool = c->d_trees; a.n = G; a.max_dim = c->M.max_dim;
@@ -1002,7 +1007,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     // slots [0, n_games): few games go to the low-latency kernel whatever the context's size (the bf16 mode keeps its own arithmetic)
     const int G_lat = (int64_t)G < n_games ? G : (int)n_games;
     const bool use_lat = c->lat_ok && G_lat >= 1 && G_lat <= c->lat_max_slots && c->cfg.nn_mode != MZ_NN_BF16_TC;
-    int64_t total_moves = 0;
+    int64_t total_moves = 0; int last_snap = 0;
     // The host runs one iteration behind the device: iteration k (opponent plies, search, save/refill, counter snapshot) is queued before
     // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,
     // the iteration already queued finds every slot idle: each search CTA returns at its first instruction.
@@ -1044,6 +1049,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         if (overlap) { MZ_CUDA(c, cudaEventRecord(c->ev_search[k & 1], c->stream)); MZ_CUDA(c, cudaStreamWaitEvent(sB, c->ev_search[k & 1], 0)); }
         MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave + 8 * ((k + 1) & 1), sB));
         MZ_TRY(snapshot((int)((k + 1) & 1)));
+        last_snap = (int)((k + 1) & 1);
         MZ_CUDA(c, cudaGetLastError());
         MZ_CUDA(c, cudaEventSynchronize(c->ev_wave[k & 1]));
         const int64_t active = c->h_wave[8 * (k & 1) + 5];                 // games active when iteration k started
@@ -1055,9 +1061,10 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
         }
         total_moves += active;
     }
-    if (overlap) MZ_CUDA(c, cudaStreamSynchronize(sB));                   // the last save / refill (tallies, counters) before anything else runs on the main stream
+    if (overlap) MZ_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_wave[last_snap], 0));   // the last save / refill (tallies, counters) before anything else runs on the main stream
     MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->slots_dirty = false;
     if (simulations) *simulations = (int64_t)c->h_stats[1];
     if (moves) *moves = total_moves;
     c->last_mean_depth = c->h_stats[1] ? (double)c->h_stats[0] / (double)c->h_stats[1] : 0.0;
