@@ -147,3 +147,24 @@ def test_lat_randomised_configurations_bit_exact(capi, seed):
         for k in common.HIST_KEYS:
             assert np.array_equal(h[k][j], o[k][i]), (k, i, kw)
     ctx.close()
+
+
+def test_lat_weight_image_follows_the_learner(capi):
+    """the kernel's own weight image is rebuilt on the device after an ADAM step / set_weights before the next small call"""
+    ctx, ocfg = make_ctx(capi, num_slots=64, replay_buffer_size=128, num_iters=20, exploration_eps=0.25)
+    ctx.init_weights(31)
+    st, legal, tp = common.random_stacked(ocfg, 6, seed=2)
+    game = np.arange(6, dtype=np.uint64); move = np.ones(6, np.int32)
+    ctx.run_mcts(st, legal, tp, True, game, move)                  # builds the image for the initial weights
+    ctx.self_play(0, 64, 1.0); ctx.learn_step(1); ctx.learn_step(2)
+    blob = ctx.get_weights()
+    vc, rv = ctx.run_mcts(st, legal, tp, True, game, move)
+    for i in range(6):
+        ovc, orv, _ = O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), 1)
+        assert vc[i].tolist() == ovc.tolist() and rv[i] == orv, i
+    blob2 = O.init_weights(ocfg, 77); ctx.set_weights(blob2)
+    vc, rv = ctx.run_mcts(st, legal, tp, True, game, move)
+    for i in range(6):
+        ovc, orv, _ = O.run_mcts(ocfg, blob2, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), 1)
+        assert vc[i].tolist() == ovc.tolist() and rv[i] == orv, i
+    ctx.close()
