@@ -86,6 +86,7 @@ struct mz_ctx {
     float *d_w_lat = nullptr; uint64_t lat_version = 0; int lat_image_floats = 0;
     unsigned char *h_lat_stage = nullptr, *d_lat_stage = nullptr; size_t lat_stage_cap = 0;   // one pinned / device block for all inputs and outputs of a small run_mcts call
     bool lat_ok = false; int lat_w_floats = 0, lat_pbc_smem = 0, lat_max_roots = 0, lat_max_slots = 0; size_t smem_bytes_lat = 0;
+    bool persist_ok = true;     // MUZERO_B200_PERSIST=0: one search launch per move also for single-wave self-play on the split-precision path
     bool slots_dirty = false;   // a wave is in progress or ended with an error: the slots are reset before the next one
     int refill_wave_sync = 1;   // 1: mz_k_save_refill starts new games only when every slot is free (default; MUZERO_B200_REFILL=immediate refills at once)
     uint64_t w_version = 1, img_version = 0;   // device weights vs the tensor-core image built from them (ensure_images)
@@ -521,6 +522,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (prop.major < 10) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); mz_destroy(c); return r; }
     c->sm_count = prop.multiProcessorCount;
     if (const char *rf = getenv("MUZERO_B200_REFILL")) c->refill_wave_sync = !strcmp(rf, "wave") ? 1 : 0;
+    if (const char *pe = getenv("MUZERO_B200_PERSIST")) c->persist_ok = atoi(pe) != 0;
     const bool resnet = cfg->net_type == MZ_NET_RESNET;
     if (resnet) {
         if (const char *er = mzh::rn_build(*cfg, c->M.P, c->rn)) { int r = fail(nullptr, MZ_E_ARG, "%s", er); mz_destroy(c); return r; }
@@ -1024,6 +1026,25 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     P.fin_tag = 0;
     MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave));
     MZ_CUDA(c, cudaEventRecord(c->ev_wave[0], c->stream));
+    // Single-wave self-play on the split-precision path: ONE launch plays the games to the end (mz_k_search_sp, a.persist).  CTA i of move
+    // k + 1 depends only on CTA i of move k, while a launch per move lasts as long as its slowest CTA (12 % above the mean) and every move
+    // pays launch gaps: here a CTA starts its next move when its own trees are done.  All finished games are saved by one save / refill at
+    // the end, in slot order (= game id order).  MUZERO_B200_PERSIST=0 keeps one launch per move.
+    if (overlap && !use_lat && arena_player == 0 && c->cfg.net_type == MZ_NET_FEEDFORWARD && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->persist_ok) {
+        mz_search_sp_args t{}; t.base = a; t.base.persist = 1; t.sp = c->spa;
+        { launch_scope ls(c, 0); mz_k_search_sp<MZ_MODE_SLOTS><<<(G + MZ_ROWS - 1) / MZ_ROWS, MZ_SP_THREADS, c->smem_bytes_sp, c->stream>>>(P, t); }
+        MZ_TRY(launch_save_refill(c, P, G, tally, c->d_wave + 8));
+        MZ_CUDA(c, cudaGetLastError());
+        MZ_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        MZ_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->h_wave[8 + 5] != 0) return fail(c, MZ_E_STATE, "self-play did not terminate");
+        c->slots_dirty = false;
+        if (simulations) *simulations = (int64_t)c->h_stats[1];
+        if (moves) *moves = (int64_t)c->h_stats[3];
+        c->last_mean_depth = c->h_stats[1] ? (double)c->h_stats[0] / (double)c->h_stats[1] : 0.0;
+        c->last_mean_legal = c->h_stats[3] ? (double)c->h_stats[2] / (double)c->h_stats[3] : 0.0;
+        return MZ_OK;
+    }
     for (int64_t k = 0;; k++) {
         if (k > n_games * (int64_t)(P.max_moves + 2) + 8) return fail(c, MZ_E_STATE, "self-play did not terminate");
         P.fin_tag = (int32_t)(k & 1);

@@ -55,6 +55,8 @@ struct mz_ring {           // device replay buffer: key k lives at (k-1) % capac
 struct mz_search_args {
     const float *wglob; const double *pbc0; const double *sqrtN; void *tree_pool;
     int32_t n, max_dim, max_layer_floats, exploration;
+    int32_t persist;             // MODE_SLOTS, mz_k_search_sp: 1 = the kernel plays every game of its CTA to the end (one launch per wave: a CTA starts its next
+                                 // move when ITS trees are done instead of waiting for the slowest CTA of the grid)
     // MODE_API inputs / outputs
     const float *stacked; const uint32_t *legal; const int32_t *to_play; const uint64_t *game_id; const int32_t *move_idx;
     int32_t *visit_counts; float *root_value; float *root_priors;

@@ -43,11 +43,11 @@ __device__ __forceinline__ void mz_sp_prime(const mz_sp_ctx &C, const mz_sp_args
     for (int s = 0; s < A.n_sets[net] && s < A.n_rounds[net]; s++) mz_sp_fill(C, C.prog + (uint32_t)(A.first[net] + s) * MZ_SP_RDESC_BYTES);
 }
 // one thread, before the CTA ends: the refills issued after the last pass must have landed (passes = passes over the network so far)
-__device__ __forceinline__ void mz_sp_drain(const mz_sp_ctx &C, const mz_sp_args &A, int net, uint32_t passes) {
+__device__ __forceinline__ void mz_sp_drain(const mz_sp_ctx &C, const mz_sp_args &A, int net, uint32_t passes, uint32_t bias = 0) {
     for (int s = 0; s < A.n_sets[net] && s < A.n_rounds[net]; s++) {
         const uint32_t R = C.prog + (uint32_t)(A.first[net] + s) * MZ_SP_RDESC_BYTES;
         const uint32_t per_pass = mz_lds_u4(R + 96).y & 0xffffu;
-        if (per_pass) mz_sp_wait_weights(C, (int)(short)(mz_lds_u4(R + 80).w & 0xffffu), passes * per_pass);
+        if (per_pass) mz_sp_wait_weights(C, (int)(short)(mz_lds_u4(R + 80).w & 0xffffu), passes * per_pass + bias);
     }
 }
 __device__ __forceinline__ uint32_t mz_sp_group_tile(const mz_sp_plan_s &sp, int grp, int tile) { return sp.tiles + (uint32_t)((grp * MZ_SP_TILES_PER_GROUP + tile) * 2 * MZ_SP_TILE_BYTES); }
@@ -91,11 +91,18 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
 #endif
     uint16_t *path = sp.path + (size_t)r * (P.S + 2);
 
+    mz_tree tree; tree.A = nullptr; tree.hidden = nullptr;
+    if (worker && g < a.n) tree = mz_tree_at(P, a.tree_pool, g);
+    const bool persist = MODE == MZ_MODE_SLOTS && a.persist != 0 && P.arena_player == 0;
+    uint32_t ply = 0;                                                   // moves played by this launch so far (persist: one launch plays the games to the end)
+  for (;; ply++) {
+    // the representation's weights lie over the dynamics sets: at every further ply they are fetched again (after the refills issued behind
+    // the last dynamics pass have landed) and the dynamics sets are primed again after the representation -- one extra fill per set and ply,
+    // which is the `bias` of the weight waits
+    if (ply > 0 && issuer0 && grp == 1) { mz_sp_drain(C, A, 2, pass, ply - 1); mz_sp_fill_many(C, A.first[0], A.n_rounds[0]); }
     // ---- per-tree state, replicated in the 8 lanes of the tree ----
     bool active = false; uint32_t legal = 0, game = 0, move = 0; int to_play = 1;
-    mz_tree tree; tree.A = nullptr; tree.hidden = nullptr;
     if (worker && g < a.n) {
-        tree = mz_tree_at(P, a.tree_pool, g);
         if (MODE == MZ_MODE_API) {
             active = true; legal = a.legal[g]; to_play = a.to_play[g]; game = (uint32_t)a.game_id[g]; move = (uint32_t)a.move_idx[g];
         } else {
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
     //      group 0 runs prediction(h0) -> (v0, p0) ----
     if (grp == 1) {
         if (worker) q = mz_sp_run(C, A.first[0], A.n_rounds[0], tmem_d, mbar_mma, q, grp, gtid, nullptr);
-        else { q = mz_sp_run_issuer(C, A.first[0], A.n_rounds[0], tmem_d, mbar_mma, q, 0u, grp); if (issuer0) mz_sp_prime(C, A, 2); }
+        else { q = mz_sp_run_issuer(C, A.first[0], A.n_rounds[0], tmem_d, mbar_mma, q, 0u, grp, nullptr, 0u, ply); if (issuer0) mz_sp_prime(C, A, 2); }
     }
     __syncthreads();
     MZ_KSTAMP(2);
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
         {
             const int net = grp == 0 ? 1 : 2;
             if (worker) q = mz_sp_run(C, A.first[net], A.n_rounds[net], tmem_d, mbar_mma, q, grp, gtid, tk);
-            else q = mz_sp_run_issuer(C, A.first[net], A.n_rounds[net], tmem_d, mbar_mma, q, pass, grp);
+            else q = mz_sp_run_issuer(C, A.first[net], A.n_rounds[net], tmem_d, mbar_mma, q, pass, grp, nullptr, 0u, grp == 1 ? ply : 0u);
             pass++;
         }
         MZ_TIMER(4);
@@ -256,9 +263,18 @@ __global__ void __launch_bounds__(MZ_SP_THREADS) mz_k_search_sp(const __grid_con
             a.root_value[g] = rv;
         } else mz_slot_epilogue(P, a.slots, g, vc, sum_visits, legal, rv, a.temperature, game, move);
     }
+    if (!persist) break;
+    __syncthreads();                                                    // the epilogues' slot updates are visible to the CTA: the next ply starts from them
+    {
+        int more = 0;
+        const int64_t gg = (int64_t)blockIdx.x * MZ_ROWS + tid;
+        if (tid < MZ_ROWS && gg < a.n) more = a.slots.status[gg] == MZ_SLOT_ACTIVE;
+        if (!__syncthreads_or(more)) break;
+    }
+  }
     // ---- teardown: every MMA has been waited on; weight copies still in flight (the refills after the last pass) must land before the
     //      CTA's shared memory is released ----
-    if (issuer0) mz_sp_drain(C, A, grp == 0 ? 1 : 2, pass);
+    if (issuer0) mz_sp_drain(C, A, grp == 0 ? 1 : 2, pass, grp == 0 ? 0u : ply);
     mz_tc_fence_before();
     __syncthreads();
     MZ_KSTAMP(6);

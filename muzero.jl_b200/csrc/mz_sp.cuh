@@ -237,14 +237,15 @@ __device__ __forceinline__ void mz_sp_store_wait_read() { asm volatile("cp.async
 __device__ __forceinline__ void mz_sp_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // save / fslot: learner only -- the hi tile of every job's input goes to save + fslot[2 * round + job] * 4 KB (fslot: shared address of an int16 table)
+// bias: extra fills every weight set of this network has seen (a persistent self-play kernel primes the representation / dynamics sets anew at every ply)
 __device__ __noinline__ uint32_t mz_sp_run_issuer(const mz_sp_ctx C, int first, int count, uint32_t tmem_d, uint32_t mbar, uint32_t q, uint32_t pass, int grp,
-                                                  unsigned char *save = nullptr, uint32_t fslot = 0) {
+                                                  unsigned char *save = nullptr, uint32_t fslot = 0, uint32_t bias = 0) {
     uint32_t R = C.prog + (uint32_t)first * MZ_SP_RDESC_BYTES;
     for (int r = 0; r < count; r++, R += MZ_SP_RDESC_BYTES, q++) {
         const uint4 d0 = mz_lds_u4(R), d1 = mz_lds_u4(R + 16), d2 = mz_lds_u4(R + 32), e1 = mz_lds_u4(R + 64), e2 = mz_lds_u4(R + 80);
         const uint32_t fo = mz_lds_u4(R + 96).y;                        // per_pass | ord << 16
         const int njobs = (int)(short)(e2.z & 0xffffu), set = (int)(short)(e2.w & 0xffffu), next = (int)(short)(e2.w >> 16);
-        if (mz_elect_one()) mz_sp_wait_weights(C, set, pass * (fo & 0xffffu) + (fo >> 16));
+        if (mz_elect_one()) mz_sp_wait_weights(C, set, pass * (fo & 0xffffu) + (fo >> 16) + bias);
         if (r > 0) mz_sp_bar_sync(grp);                                 // the previous round's outputs are in the operand tiles, its accumulators have been read
         mz_tc_fence_after();
         if (mz_elect_one()) {
