@@ -978,7 +978,25 @@ static int slots_reset(mz_ctx *c) {
 }
 static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves);
 static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
-    const int rc = run_wave_body(c, first_game, n_games, temperature, arena_player, arena_opponent, tally_player, simulations, moves);
+    int rc = MZ_OK;
+    const int64_t G = c->cfg.num_slots;
+    if (n_games > G && c->refill_wave_sync && arena_player == 0 && c->cfg.net_type == MZ_NET_FEEDFORWARD && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->persist_ok && c->stream2 &&
+        !getenv("MUZERO_B200_NO_OVERLAP") && first_game + (uint64_t)n_games <= 0xffffffffull) {
+        // wave-synchronous refill hands out games num_slots at a time, in slot order: a call for more games than slots is a sequence of
+        // single-wave calls, each of which the headline path plays in one launch
+        unsigned long long acc[4] = {0, 0, 0, 0};
+        for (int64_t off = 0; off < n_games && rc == MZ_OK; off += G) {
+            rc = run_wave_body(c, first_game + (uint64_t)off, n_games - off < G ? n_games - off : G, temperature, arena_player, arena_opponent, tally_player, nullptr, nullptr);
+            for (int i = 0; i < 4; i++) acc[i] += c->h_stats[i];
+        }
+        if (rc == MZ_OK) {
+            for (int i = 0; i < 4; i++) c->h_stats[i] = acc[i];
+            if (simulations) *simulations = (int64_t)acc[1];
+            if (moves) *moves = (int64_t)acc[3];
+            c->last_mean_depth = acc[1] ? (double)acc[0] / (double)acc[1] : 0.0;
+            c->last_mean_legal = acc[3] ? (double)acc[2] / (double)acc[3] : 0.0;
+        }
+    } else rc = run_wave_body(c, first_game, n_games, temperature, arena_player, arena_opponent, tally_player, simulations, moves);
     if (rc != MZ_OK && rc != MZ_E_ARG) {   // a wave that failed half-way must not leave games in flight: later calls would answer MZ_E_STATE for ever
         const std::string keep = c->err;
         slots_reset(c);
