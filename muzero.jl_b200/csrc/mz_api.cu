@@ -976,7 +976,7 @@ static int slots_reset(mz_ctx *c) {
     MZ_CUDA(c, cudaStreamSynchronize(c->stream));
     return MZ_OK;
 }
-static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves);
+static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves, bool allow_lat = true);
 static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
     int rc = MZ_OK;
     const int64_t G = c->cfg.num_slots;
@@ -986,7 +986,8 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
         // single-wave calls, each of which the headline path plays in one launch
         unsigned long long acc[4] = {0, 0, 0, 0};
         for (int64_t off = 0; off < n_games && rc == MZ_OK; off += G) {
-            rc = run_wave_body(c, first_game + (uint64_t)off, n_games - off < G ? n_games - off : G, temperature, arena_player, arena_opponent, tally_player, nullptr, nullptr);
+            rc = run_wave_body(c, first_game + (uint64_t)off, n_games - off < G ? n_games - off : G, temperature, arena_player, arena_opponent, tally_player, nullptr, nullptr,
+                               false /* a short last wave stays on this path's arithmetic: one call, one kernel family */);
             for (int i = 0; i < 4; i++) acc[i] += c->h_stats[i];
         }
         if (rc == MZ_OK) {
@@ -1004,7 +1005,7 @@ static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float tempe
     }
     return rc;
 }
-static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
+static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves, bool allow_lat) {
     if (n_games < 0) return fail(c, MZ_E_ARG, "n_games < 0");
     if (first_game + (uint64_t)n_games > 0xffffffffull) return fail(c, MZ_E_ARG, "game ids must fit in 32 bits (Philox counter)");
     mz_params P = c->M.P;
@@ -1026,7 +1027,7 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
     // A wave starts with every slot idle and games are handed out in slot order, so a call for n_games <= num_slots games only ever uses the
     // slots [0, n_games): few games go to the low-latency kernel whatever the context's size (the bf16 mode keeps its own arithmetic)
     const int G_lat = (int64_t)G < n_games ? G : (int)n_games;
-    const bool use_lat = c->lat_ok && G_lat >= 1 && G_lat <= c->lat_max_slots && c->cfg.nn_mode != MZ_NN_BF16_TC;
+    const bool use_lat = allow_lat && c->lat_ok && G_lat >= 1 && G_lat <= c->lat_max_slots && c->cfg.nn_mode != MZ_NN_BF16_TC;
     int64_t total_moves = 0; int last_snap = 0;
     // The host runs one iteration behind the device: iteration k (opponent plies, search, save/refill, counter snapshot) is queued before
     // the snapshot of iteration k - 1 is read, so the GPU never waits for a launch.  When that snapshot says no game is active any more,

@@ -265,3 +265,42 @@ def test_bptt_on_tensor_cores_with_per_weights(capi):
     g1, l1 = ctx.learn_gradients(b1, capi.GRAD_BPTT)
     assert not np.array_equal(l1, losses) and not np.array_equal(g1, g)
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_split_one_launch_per_wave_equals_one_launch_per_move(seed):
+    """mz_k_search_sp plays a whole wave in one launch (single-wave self-play; calls for more games than slots are cut into waves); the
+    weight-set fill accounting then carries a per-ply bias.  Under randomly drawn network shapes (different numbers of rounds, weight
+    sets and members per set) the games must be the ones the one-launch-per-move loop plays (MUZERO_B200_PERSIST=0)."""
+    import os
+    from muzero_jl_b200 import capi
+    rng = np.random.default_rng(900 + seed)
+    kw = dict(num_iters=int(rng.integers(3, 40)), stacked_observations=int(rng.integers(0, 2)), exploration_eps=float(np.float32(rng.choice([0.0, 0.25]))),
+              depth_representation=int(rng.integers(0, 4)), depth_prediction=int(rng.integers(0, 4)), depth_dynamics=int(rng.integers(0, 4)),
+              depth_policy=int(rng.integers(0, 3)), depth_value=int(rng.integers(0, 3)), depth_reward=int(rng.integers(0, 3)),
+              depth_state_head=int(rng.integers(0, 4)), width_hidden=int(rng.choice([32, 64])), max_moves=int(rng.choice([9, 9, 5])),
+              num_slots=int(rng.choice([32, 64, 100])), replay_buffer_size=1024, nn_mode=capi.NN_SPLIT_MMA, seed=int(rng.integers(1, 1 << 30)))
+    games = int(rng.choice([kw["num_slots"], kw["num_slots"] // 2 + 1, 2 * kw["num_slots"] + 7]))
+    temperature = float(rng.choice([0.0, 1.0]))
+    res = []
+    for persist in ("1", "0"):
+        old = os.environ.get("MUZERO_B200_PERSIST"); os.environ["MUZERO_B200_PERSIST"] = persist
+        try:
+            ctx = capi.Context(capi.default_config(**kw))
+        finally:
+            if old is None:
+                del os.environ["MUZERO_B200_PERSIST"]
+            else:
+                os.environ["MUZERO_B200_PERSIST"] = old
+        ctx.init_weights(seed + 5)
+        n0 = ctx.launch_count()
+        sims, moves = ctx.self_play(100, games, temperature)
+        launches = ctx.launch_count() - n0
+        h = ctx.history_export(); order = np.argsort(h["game_id"])
+        res.append((sims, moves, launches, {k: h[k][order] for k in common.HIST_KEYS}, ctx.replay_info()))
+        ctx.close()
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1], kw
+    assert res[0][2] < res[1][2], (res[0][2], res[1][2])                  # fewer launches: one search per wave instead of one per move
+    for k in common.HIST_KEYS:
+        assert np.array_equal(res[0][3][k], res[1][3][k]), (k, kw)
+    assert res[0][4]["n_games"] == res[1][4]["n_games"] and res[0][4]["total_samples"] == res[1][4]["total_samples"]
