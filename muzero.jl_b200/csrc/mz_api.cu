@@ -980,10 +980,11 @@ static int run_wave_body(mz_ctx *c, uint64_t first_game, int64_t n_games, float 
 static int run_wave(mz_ctx *c, uint64_t first_game, int64_t n_games, float temperature, int arena_player, int arena_opponent, int tally_player, int64_t *simulations, int64_t *moves) {
     int rc = MZ_OK;
     const int64_t G = c->cfg.num_slots;
-    if (n_games > G && c->refill_wave_sync && arena_player == 0 && c->cfg.net_type == MZ_NET_FEEDFORWARD && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->persist_ok && c->stream2 &&
+    if (n_games > G && c->refill_wave_sync && arena_player == 0 && c->cfg.net_type == MZ_NET_FEEDFORWARD && c->stream2 &&
         !getenv("MUZERO_B200_NO_OVERLAP") && first_game + (uint64_t)n_games <= 0xffffffffull) {
         // wave-synchronous refill hands out games num_slots at a time, in slot order: a call for more games than slots is a sequence of
-        // single-wave calls, each of which the headline path plays in one launch
+        // single-wave calls, each of which the headline path plays in one launch (the other feed-forward paths: one launch per move with the
+        // save / refill beside the next search)
         unsigned long long acc[4] = {0, 0, 0, 0};
         for (int64_t off = 0; off < n_games && rc == MZ_OK; off += G) {
             rc = run_wave_body(c, first_game + (uint64_t)off, n_games - off < G ? n_games - off : G, temperature, arena_player, arena_opponent, tally_player, nullptr, nullptr,
