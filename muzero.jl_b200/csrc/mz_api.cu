@@ -108,7 +108,7 @@ struct mz_ctx {
     mzh::rn_model rn; unsigned char *d_rn_image = nullptr; mz_rn_step *d_rn_steps = nullptr; size_t smem_bytes_rn = 0; std::vector<float> rn_blob;
     // grad_mode = MZ_GRAD_BPTT
     mzh::bptt_program bptt; mz_bstage *d_bstages[2] = {nullptr, nullptr}; size_t smem_bytes_bptt = 0;
-    float *d_act = nullptr, *d_gpart = nullptr; int bptt_tiles_cap = 0;
+    float *d_act = nullptr, *d_gpart = nullptr; int bptt_tiles_cap = 0; int bptt_dims[4] = {0, 0, 0, 0};   // mz_bptt_args: dim_wide, dim_narrow, wfloats[2]
     int64_t launches = 0; bool timing = false; std::vector<timed_launch> timed; double fam_ms[8] = {0}; int64_t fam_n[8] = {0};
     double last_mean_legal = 0, last_mean_depth = 0;
 };
@@ -396,7 +396,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
         if (c->cfg.use_batch_norm) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for use_batch_norm networks (the reference's own update, MZ_GRAD_REFERENCE_L2, is)");
-        if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT needs more shared memory per CTA than the device allows for this network");
+        if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for this network: it needs every layer output and every layer input other than the observation stack to be at most 64 wide, and its buffers to fit one CTA's shared memory");
         if (tiles > c->bptt_tiles_cap) {
             if (c->d_act) cudaFree(c->d_act);
             if (c->d_gpart) cudaFree(c->d_gpart);
@@ -406,6 +406,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
             c->bptt_tiles_cap = tiles;
         }
         mz_bptt_args b{}; b.f = a; b.act = c->d_act; b.gpart = c->d_gpart; b.stages[0] = c->d_bstages[0]; b.stages[1] = c->d_bstages[1];
+        b.dim_wide = c->bptt_dims[0]; b.dim_narrow = c->bptt_dims[1]; b.wfloats[0] = c->bptt_dims[2]; b.wfloats[1] = c->bptt_dims[3];
         { launch_scope ls(c, 3); mz_k_learn_bptt<<<tiles, MZ_THREADS, c->smem_bytes_bptt, c->stream>>>(P, c->bptt.plan, b); }
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2 && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // the unroll on the tensor cores (mz_kernels_sp.cuh)
@@ -581,14 +582,33 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
         if (c->lat_ok) { MZ_CREATE(allow_max_smem(mz_k_search_lat<MZ_MODE_API>, prop)); MZ_CREATE(allow_max_smem(mz_k_search_lat<MZ_MODE_SLOTS>, prop)); MZ_CREATE(dmalloc(&c->d_w_lat, (size_t)c->lat_image_floats + 64)); }
     }
     if (!resnet) { if (const char *eb = mzh::build_bptt(P, c->bptt)) { int r = fail(nullptr, MZ_E_ARG, "%s", eb); mz_destroy(c); return r; } }
-    c->smem_bytes_bptt = c->smem_bytes + mz_bptt_smem_extra(c->M.max_dim);
-    if (!resnet && c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin) {   // 4 KB head-room for the kernel's static shared memory
+    bool bptt_fits = !resnet;
+    if (!resnet) {
+        // mz_k_learn_bptt's own carve-up (mz_bptt_carve): only in0 and group 0's staged-input slots are as wide as the observation stack.
+        // The backward tile covers 64 outputs (bias sums: 4 warps x 16) and 64 inputs wherever an input gradient is needed, i.e. everywhere
+        // except the representation's first layer (dx_mode = NONE)
+        int narrow = 4, wf[2] = {0, 0};
+        for (int n = 0; n < 3; n++) {
+            const mz_net &N = P.nets[n];
+            for (int i = 0; i < N.n_trunk + N.n_h1 + N.n_h2; i++) {
+                const mz_layer &L = P.layers[N.first + i];
+                if (L.out_pad > narrow) narrow = L.out_pad;
+                if (!(n == 0 && i == 0) && L.in > narrow) narrow = L.in;
+                if (L.floats > wf[n == 2]) wf[n == 2] = L.floats;
+            }
+        }
+        narrow = (narrow + 3) & ~3;
+        c->bptt_dims[0] = c->M.max_dim; c->bptt_dims[1] = narrow; c->bptt_dims[2] = wf[0]; c->bptt_dims[3] = wf[1];
+        c->smem_bytes_bptt = mz_bptt_smem_bytes(c->M.max_dim, narrow, wf[0], wf[1], P.hidden_pad);
+        bptt_fits = narrow <= 64 && c->smem_bytes_bptt + 4096 <= (size_t)prop.sharedMemPerBlockOptin;   // 4 KB head-room for the kernel's static shared memory
+    }
+    if (bptt_fits) {
         MZ_CREATE(allow_max_smem(mz_k_learn_bptt, prop));
         for (int g = 0; g < 2; g++) {
             MZ_CREATE(dmalloc(&c->d_bstages[g], c->bptt.stages[g].size() + 1));
             if (!c->bptt.stages[g].empty()) MZ_CREATE(cudaMemcpy(c->d_bstages[g], c->bptt.stages[g].data(), c->bptt.stages[g].size() * sizeof(mz_bstage), cudaMemcpyHostToDevice));
         }
-    } else c->smem_bytes_bptt = 0;   // MZ_GRAD_BPTT reports MZ_E_UNSUPPORTED for this configuration
+    } else c->smem_bytes_bptt = 0;  // MZ_GRAD_BPTT reports MZ_E_UNSUPPORTED for this configuration
     if (c->M.P.tc_ok) {
         c->smem_bytes_tc = mz_tc_smem_bytes(P.tc_net_off[3], P.tc_bias_floats, P.hidden_pad, P.S);
         if (c->smem_bytes_tc <= (size_t)prop.sharedMemPerBlockOptin) {

@@ -23,6 +23,9 @@ struct mz_bptt_args {
     float *act;                 // [tiles][plan.tile_floats] activation blocks
     float *gpart;               // [tiles][P.total_floats] partial gradients (device weight layout)
     const mz_bstage *stages[2]; // backward programs of the two groups
+    int32_t dim_wide;           // rows of in0 and of group 0's staged-input slots: the widest layer input (the observation stack)
+    int32_t dim_narrow;         // rows of every other activation buffer: widest layer output / input of a layer other than the representation's first
+    int32_t wfloats[2];         // largest {W,b} block of the layers group g runs (0: representation + prediction, 1: dynamics)
 };
 
 __device__ __forceinline__ void mz_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -221,15 +224,37 @@ __device__ __forceinline__ void mz_bwd_loss_grad(const mz_params &P, const mz_bp
     }
 }
 
-// extra shared memory of the backward pass on top of mz_smem_bytes: two staged-input slots per group + one exchange buffer
-__host__ __device__ inline size_t mz_bptt_smem_extra(int max_dim) { return (size_t)5 * max_dim * MZ_ROWS * 4; }
+// Shared memory of the kernel.  Only the representation's first layer sees the observation stack (99 inputs at stacked_observations = 2), and
+// only group 0 runs it: in0 and group 0's two staged-input slots have `wide` rows, the other ten activation buffers `narrow` rows, and each
+// group's weight slots are as large as ITS largest layer (the selection tables of the search kernels' carve-up are not needed here).
+struct mz_bptt_smem { mz_smem_plan sp; float *xbuf[2][2]; float *exch; size_t bytes; };
+__host__ __device__ inline mz_bptt_smem mz_bptt_carve(unsigned char *base, int wide, int narrow, int wf0, int wf1, int hidden_pad) {
+    mz_bptt_smem r;
+    const size_t w[2] = {((size_t)wf0 * 4 + 127) & ~(size_t)127, ((size_t)wf1 * 4 + 127) & ~(size_t)127};
+    const size_t bw = (size_t)wide * MZ_ROWS * 4, bn = (size_t)narrow * MZ_ROWS * 4;
+    unsigned char *c = base;
+    for (int g = 0; g < 2; g++) for (int i = 0; i < 2; i++) { r.sp.wbuf[g][i] = (float *)c; c += w[g]; }
+    r.sp.mbar[0] = (uint64_t *)c; r.sp.mbar[1] = (uint64_t *)(c + 32); c += 128;
+    r.sp.in0 = (float *)c; c += bw;              // in0, in1, bufT, t0, t1 are contiguous (zeroed together)
+    r.sp.in1 = (float *)c; c += bn;
+    for (int g = 0; g < 2; g++) { r.sp.bufT[g] = (float *)c; c += bn; r.sp.t0[g] = (float *)c; c += bn; r.sp.t1[g] = (float *)c; c += bn; }
+    r.sp.outV = (float *)c; c += 4 * MZ_ROWS * 4;
+    r.sp.outL = (float *)c; c += 16 * MZ_ROWS * 4;
+    r.sp.outR = (float *)c; c += 4 * MZ_ROWS * 4;
+    r.sp.outH = (float *)c; c += (size_t)hidden_pad * MZ_ROWS * 4;
+    r.sp.pbc0 = nullptr; r.sp.sqrtN = nullptr; r.sp.path = nullptr;
+    for (int i = 0; i < 2; i++) { r.xbuf[0][i] = (float *)c; c += bw; }
+    for (int i = 0; i < 2; i++) { r.xbuf[1][i] = (float *)c; c += bn; }
+    r.exch = (float *)c; c += bn;
+    r.bytes = (size_t)(c - base) + 128;
+    return r;
+}
+__host__ inline size_t mz_bptt_smem_bytes(int wide, int narrow, int wf0, int wf1, int hidden_pad) { return mz_bptt_carve(nullptr, wide, narrow, wf0, wf1, hidden_pad).bytes; }
 
 __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_bptt(const __grid_constant__ mz_params P, const __grid_constant__ mz_bptt_plan pl, const mz_bptt_args a) {
     extern __shared__ __align__(128) unsigned char mz_smem[];
-    const int max_dim = a.f.max_dim;
-    const mz_smem_plan sp = mz_smem_carve(mz_smem, max_dim, a.f.max_layer_floats, P.hidden_pad, P.S);
-    const size_t bufsz = (size_t)max_dim * MZ_ROWS;   // floats
-    float *extra = reinterpret_cast<float *>(mz_smem + mz_smem_bytes(max_dim, a.f.max_layer_floats, P.hidden_pad, P.S));
+    const mz_bptt_smem bs = mz_bptt_carve(mz_smem, a.dim_wide, a.dim_narrow, a.wfloats[0], a.wfloats[1], P.hidden_pad);
+    const mz_smem_plan &sp = bs.sp;
     __shared__ double s_red[MZ_THREADS];
     const int tid = threadIdx.x, K1 = P.K + 1;
     const int64_t g = (int64_t)blockIdx.x * MZ_ROWS + tid;
@@ -238,7 +263,7 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_bptt(const __grid_const
     float *gpart = a.gpart + (size_t)blockIdx.x * P.total_floats;
     mz_nn_pipe pipe;
     mz_pipe_init(pipe, sp, a.f.wglob);
-    mz_zero_activations(sp, max_dim);
+    for (int i = threadIdx.x; i < (a.dim_wide + 7 * a.dim_narrow) * MZ_ROWS; i += MZ_THREADS) sp.in0[i] = 0.0f;
     // mean_i(1/g_i) over the whole batch (Q21's broadcast couples every sample's policy term to it): same fixed-order sum in every CTA
     {
         double s = 0.0;
@@ -308,8 +333,8 @@ __global__ void __launch_bounds__(MZ_THREADS) mz_k_learn_bptt(const __grid_const
     __threadfence();
     mz_fence_proxy_async_all();
     __syncthreads();
-    float *bufs[6] = {sp.bufT[pipe.grp], sp.t0[pipe.grp], sp.t1[pipe.grp], sp.in0, sp.in1, extra + 4 * bufsz};
-    float *xbuf[2] = {extra + (size_t)(2 * pipe.grp) * bufsz, extra + (size_t)(2 * pipe.grp + 1) * bufsz};
+    float *bufs[6] = {sp.bufT[pipe.grp], sp.t0[pipe.grp], sp.t1[pipe.grp], sp.in0, sp.in1, bs.exch};
+    float *xbuf[2] = {bs.xbuf[pipe.grp][0], bs.xbuf[pipe.grp][1]};
     const mz_bstage *prog = a.stages[pipe.grp];
     const int nst = pl.n_stages[pipe.grp];
     auto issue = [&](int idx, uint32_t slot) {

@@ -356,7 +356,8 @@ def _check_grad(ocfg, g, og):
 
 @pytest.mark.parametrize("kw,B", [({}, 32), ({"intermediate_rewards": 1}, 32), ({"intermediate_rewards": 1}, 77), ({}, 5),
                                   ({"num_unroll_steps": 1, "intermediate_rewards": 1}, 40), ({"num_unroll_steps": 2}, 33),   # (K = 0 is degenerate in the reference: gradient_scale = min(K, ..) = 0, ReplayBuffer.jl:212)
-                                  ({"depth_value": 0, "depth_policy": 2, "depth_reward": 0, "depth_state_head": 1, "intermediate_rewards": 1}, 64)])
+                                  ({"depth_value": 0, "depth_policy": 2, "depth_reward": 0, "depth_state_head": 1, "intermediate_rewards": 1}, 64),
+                                  ({"stacked_observations": 2}, 32), ({"stacked_observations": 2, "intermediate_rewards": 1, "num_unroll_steps": 3}, 45)])   # 99 inputs: wider than the 64-row buffers
 def test_bptt_gradients_match_oracle(capi, kw, B):
     ctx, ocfg = make_ctx(capi, batch_size=B, **kw)
     ctx.init_weights(5)
@@ -378,6 +379,23 @@ def test_bptt_gradients_match_oracle(capi, kw, B):
     # reference_l2 mode through the same entry point: exactly 2*theta (Q20)
     g3, _ = ctx.learn_gradients(batch, capi.GRAD_REFERENCE_L2)
     assert np.array_equal(g3, blob + blob)
+    ctx.close()
+
+
+def test_bptt_refuses_layers_wider_than_its_backward_tile(capi):
+    """the backward tile covers 64 outputs / 64 inputs with an input gradient: a 72-wide hidden layer is refused (not silently truncated),
+    while everything else of such a context (forward, the reference's own update) works"""
+    ctx, ocfg = make_ctx(capi, batch_size=16, width_hidden=72)
+    ctx.init_weights(5); blob = ctx.get_weights()
+    batch = _bptt_batch(ocfg, blob, 16, 3)
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.learn_gradients(batch, capi.GRAD_BPTT)
+    assert e.value.code == capi.E_UNSUPPORTED
+    pv, pr, pp, _ = ctx.learn_forward(batch)
+    opv, opr, opp, _ = O.learn_forward(ocfg, blob, batch)
+    assert np.array_equal(pv, opv) and np.array_equal(pp, opp)
+    g, _ = ctx.learn_gradients(batch, capi.GRAD_REFERENCE_L2)
+    assert np.array_equal(g, blob + blob)
     ctx.close()
 
 
