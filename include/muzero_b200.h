@@ -216,7 +216,9 @@ int mz_learn_steps(mz_ctx *ctx, int64_t t0, int n, int grad_mode, float *losses 
 /* gradients of one caller-supplied batch without an update (parity entry point): grad[n_params] in the reference blob
  * order.  MZ_GRAD_REFERENCE_L2: what the reference's three Zygote pullbacks actually return, 2*theta (Learning.jl:385-393
  * differentiate a closure whose predictions were computed outside of it).  MZ_GRAD_BPTT: the gradient of the same loss
- * value (Learning.jl:261-288) through the unroll (Learning.jl:347-370), plus 2*theta. */
+ * value (Learning.jl:261-288) through the unroll (Learning.jl:347-370), plus 2*theta.  MZ_GRAD_BPTT is built for the FeedForwardHP
+ * networks without BatchNorm whose hidden layers are at most 64 wide; the observation stack itself may be wider (stacked_observations = 2:
+ * 99 inputs); everything else answers MZ_E_UNSUPPORTED. */
 int mz_learn_gradients(mz_ctx *ctx, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
                        const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses /* [3] */);
 /* the same with importance-sampling weights weight_batch [B] (conf.PER; NULL = 1) */
