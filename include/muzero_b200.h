@@ -91,8 +91,9 @@ typedef struct mz_config {
      * length(history.action_history) >= threshold (src/SelfPlay.jl:344-346); -1 = nothing (the default) */
     int32_t temperature_threshold;
     /* FeedForwardHP.use_batch_norm (src/Constructors.jl:71): make_dense = Chain(Dense(in, out), BatchNorm(out, relu)) (src/Learning.jl:70-79).
-     * BatchNorm runs in test mode everywhere (the reference never differentiates a forward pass and never calls trainmode!).  Exact-fp32
-     * path only: the tensor-core modes and MZ_GRAD_BPTT answer MZ_E_UNSUPPORTED.  Blob: such a layer's W, b are followed by
+     * BatchNorm runs in test mode everywhere (the reference never differentiates a forward pass and never calls trainmode!).  Runs on the
+     * exact-fp32 path and, folded into the weight image (W' = diag(gamma / sqrt(sigma2 + 1f-5)) W), on MZ_NN_SPLIT_MMA; MZ_NN_BF16_TC and
+     * MZ_GRAD_BPTT answer MZ_E_UNSUPPORTED.  Blob: such a layer's W, b are followed by
      * beta[out], gamma[out] (Flux.params order) and the running statistics mu[out], sigma2[out] (not parameters: ADAM leaves them alone). */
     int32_t use_batch_norm;
 } mz_config;

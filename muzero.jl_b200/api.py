@@ -107,8 +107,8 @@ class GameHistory:
 def to_mz_config(conf: Config, hyper: FeedForwardHP, num_slots=4096, game=capi.GAME_TICTACTOE, tie_mode=capi.TIE_PHILOX,
                  child_order=None, nn_mode=capi.NN_FP32_EXACT):
     resnet = isinstance(hyper, ResNetHP)
-    if not resnet and hyper.use_batch_norm and nn_mode != capi.NN_FP32_EXACT:
-        raise NotImplementedError("use_batch_norm=true (Constructors.jl:71) runs on the exact fp32 path only: nn_mode must be NN_FP32_EXACT")
+    if not resnet and hyper.use_batch_norm and nn_mode == capi.NN_BF16_TC:
+        raise NotImplementedError("use_batch_norm=true (Constructors.jl:71) runs on the exact fp32 path and (folded into the weight image) on the split-precision path: nn_mode must be NN_FP32_EXACT or NN_SPLIT_MMA")
     if list(conf.action_space) != list(range(1, len(conf.action_space) + 1)):
         raise ValueError("action_space must be 1:A")
     c = capi.default_config()

@@ -359,6 +359,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
+    if (grad_mode == MZ_GRAD_BPTT && c->cfg.use_batch_norm) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for use_batch_norm networks (the reference's own update, MZ_GRAD_REFERENCE_L2, is)");
     if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) {
         // forward + backward on the tensor cores (mz_learner_tc.cuh): kernel 1 = unroll forward + dX chain with saved tiles, kernel 2 = dW / db
         MZ_TRY(ensure_images(c));
@@ -513,7 +514,7 @@ int mz_create(const mz_config *cfg, int device, mz_ctx **out) {
     if (cfg->nn_mode != MZ_NN_FP32_EXACT && cfg->nn_mode != MZ_NN_BF16_TC && cfg->nn_mode != MZ_NN_SPLIT_MMA) { int r = fail(nullptr, MZ_E_ARG, "unknown nn_mode %d", cfg->nn_mode); delete c; return r; }
     if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->nn_mode == MZ_NN_BF16_TC && !c->M.P.tc_ok) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_BF16_TC needs every layer to have in <= 64 and out <= 64"); delete c; return r; }
     if (cfg->nn_mode == MZ_NN_SPLIT_MMA && (cfg->net_type != MZ_NET_FEEDFORWARD || !c->M.P.tc_ok)) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "MZ_NN_SPLIT_MMA needs the FeedForwardHP networks with every layer in <= 64 and out <= 64"); delete c; return r; }
-    if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->use_batch_norm && cfg->nn_mode != MZ_NN_FP32_EXACT) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "use_batch_norm runs on the exact fp32 path only (nn_mode = MZ_NN_FP32_EXACT)"); delete c; return r; }
+    if (cfg->net_type == MZ_NET_FEEDFORWARD && cfg->use_batch_norm && cfg->nn_mode == MZ_NN_BF16_TC) { int r = fail(nullptr, MZ_E_UNSUPPORTED, "use_batch_norm runs on the exact fp32 path (MZ_NN_FP32_EXACT) and, folded into the weight image, on the split-precision path (MZ_NN_SPLIT_MMA); not in MZ_NN_BF16_TC"); delete c; return r; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) { int r = fail(nullptr, MZ_E_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); delete c; return r; }

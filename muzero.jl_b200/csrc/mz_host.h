@@ -183,7 +183,7 @@ inline const char *build_model(const mz_config &c, model &M) {
             int first = P.nets[n].first, cnt = P.nets[n].n_trunk + P.nets[n].n_h1 + P.nets[n].n_h2;
             for (int i = first; i < first + cnt; i++) {
                 const mz_layer &l = P.layers[i];
-                if (l.in > 64 || l.out > 64 || l.bn) P.tc_ok = 0;
+                if (l.in > 64 || l.out > 64) P.tc_ok = 0;   // (BatchNorm layers: folded into the image by mz_k_pack_images)
                 P.tc_a_off[i] = off; P.tc_ksteps[i] = (l.in + 15) / 16; P.tc_bias_off[i] = boff;
                 off += ((l.out + 7) / 8) * 1024; boff += 64;
             }

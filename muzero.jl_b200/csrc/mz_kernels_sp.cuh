@@ -339,9 +339,13 @@ struct mz_pack_args { const float *w; unsigned char *image; float *bias; int32_t
 __global__ void __launch_bounds__(256) mz_k_pack_images(const __grid_constant__ mz_params P, const __grid_constant__ mz_pack_args a) {
     const mz_layer &l = P.layers[blockIdx.x];
     const int L = blockIdx.x;
+    // FeedForwardHP.use_batch_norm (Learning.jl:70-79): BatchNorm runs in test mode everywhere (mz_common.h: mz_batchnorm), i.e. it is the affine map
+    // y = s * (W x + b - mu) + beta with s = gamma / sqrt(sigma2 + 1f-5) in front of the relu: folded into the image as W' = diag(s) W, b' = s * (b - mu) + beta
+    const float *bnp = l.bn ? a.w + l.b_off + l.out_pad : nullptr;      // beta | gamma | mu | sigma2, out_pad floats each
     for (int i = blockIdx.y * 256 + threadIdx.x; i < l.in * l.out; i += 256 * gridDim.y) {
         const int k = i / l.out, o = i - k * l.out;
-        const float w = a.w[l.w_off + k * l.out_pad + o];
+        float w = a.w[l.w_off + k * l.out_pad + o];
+        if (bnp) w = w * (bnp[l.out_pad + o] / sqrtf(bnp[3 * l.out_pad + o] + 1e-5f));
         const uint32_t off = (uint32_t)a.off[L] + mz_tc_tile_offset(o, k);
         if (a.mode == 2) {
             unsigned short hi, lo; mz_sp_split(w, hi, lo);
@@ -349,7 +353,11 @@ __global__ void __launch_bounds__(256) mz_k_pack_images(const __grid_constant__ 
             *reinterpret_cast<unsigned short *>(a.image + off + a.bytes[L]) = lo;
         } else *reinterpret_cast<unsigned short *>(a.image + off) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
     }
-    if (blockIdx.y == 0) for (int o = threadIdx.x; o < l.out; o += 256) a.bias[a.bias_off[L] + o] = a.w[l.b_off + o];
+    if (blockIdx.y == 0) for (int o = threadIdx.x; o < l.out; o += 256) {
+        float b = a.w[l.b_off + o];
+        if (bnp) b = (bnp[l.out_pad + o] / sqrtf(bnp[3 * l.out_pad + o] + 1e-5f)) * (b - bnp[2 * l.out_pad + o]) + bnp[o];
+        a.bias[a.bias_off[L] + o] = b;
+    }
 }
 
 // ---- learner: the K-step unroll forward (src/Learning.jl:347-370, Q19) with the networks on this path ------------------------------

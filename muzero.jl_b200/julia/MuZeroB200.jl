@@ -63,7 +63,7 @@ function Engine(conf, hyper; device::Integer=0, num_slots::Integer=4096, nn_mode
     c.dirichlet_alpha = conf.dirichlet_α; c.exploration_eps = conf.exploration_ϵ; c.seed = conf.seed
     c.per = conf.PER; c.per_alpha = conf.PER_alpha
     c.temperature_threshold = isnothing(conf.temperature_threshold) ? -1 : conf.temperature_threshold   # src/SelfPlay.jl:344-346
-    c.use_batch_norm = hasproperty(hyper, :use_batch_norm) && hyper.use_batch_norm ? 1 : 0             # src/Learning.jl:70-79 (exact fp32 path only)
+    c.use_batch_norm = hasproperty(hyper, :use_batch_norm) && hyper.use_batch_norm ? 1 : 0             # src/Learning.jl:70-79 (exact fp32 and split-precision paths)
     order = zeros(Int32, MZ_MAX_A)
     ccall((:mz_julia_dict_order, LIB), Cint, (Cint, Ptr{Int32}), c.A, order)   # or: collect(keys(Dict(a => 0 for a in conf.action_space)))
     c.child_order = Tuple(order)

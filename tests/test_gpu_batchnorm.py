@@ -1,7 +1,7 @@
 """FeedForwardHP.use_batch_norm (src/Constructors.jl:71, src/Learning.jl:70-79): every make_dense layer is Dense + BatchNorm(relu).  The
 reference never differentiates a forward pass (Q20) and never calls trainmode!, so BatchNorm runs in test mode everywhere; its beta / gamma
 are Flux parameters (they take part in sum(abs2, theta) and in the ADAM update), the running statistics are not.  Exact fp32 path, bit-exact
-against the oracle."""
+against the oracle; split-precision tensor-core path (BatchNorm folded into the weight image): within that path's tolerance."""
 import numpy as np
 import pytest
 
@@ -74,10 +74,52 @@ def test_bn_self_play_and_learner_bit_exact(capi):
     ctx.close()
 
 
+def test_bn_on_the_split_precision_path(capi):
+    """MZ_NN_SPLIT_MMA: mz_k_pack_images folds gamma / sqrt(sigma2 + 1f-5) into W and (b - mu, beta) into the bias, so the tcgen05 kernels run
+    BatchNorm networks unchanged: network outputs within 2e-5 * max(1, |y|) of the Float32 oracle, run_mcts visit counts identical on >= 99 %
+    of the roots, the learner's update (2 * theta over Flux.params) bit-exact, and the image follows the update."""
+    S, n = 50, 512
+    ctx, ocfg = make_ctx(capi, nn_mode=capi.NN_SPLIT_MMA, num_iters=S, exploration_eps=0.25, num_slots=512)
+    ctx.init_weights(9)
+    blob = _randomise_batchnorm(ocfg, ctx.get_weights(), 4); ctx.set_weights(blob)
+    st, legal, tp = common.random_stacked(ocfg, n, seed=6)
+    h = ctx.representation(st)
+    oh = np.stack([O.representation(ocfg, blob, x) for x in st])
+    assert np.max(np.abs(h - oh)) <= 2e-5 * max(1.0, float(np.max(np.abs(oh))))
+    v, p = ctx.prediction(oh)
+    ov, op = zip(*[O.prediction(ocfg, blob, x) for x in oh])
+    assert np.max(np.abs(v - np.array(ov))) <= 2e-5 and np.max(np.abs(p - np.stack(op))) <= 2e-5
+    sa = np.concatenate([oh * 2, np.full((n, 9), np.float32(4.0 / 9.0), np.float32)], axis=1)
+    nh, r = ctx.dynamics(sa)
+    onh, orr = zip(*[O.dynamics(ocfg, blob, x) for x in sa])
+    assert np.max(np.abs(nh - np.stack(onh))) <= 2e-5 * max(1.0, float(np.max(np.abs(np.stack(onh))))) and np.max(np.abs(r - np.array(orr))) <= 2e-5
+    game = np.arange(n, dtype=np.uint64) + 7; move = (np.arange(n) % 9 + 1).astype(np.int32)
+    vc, rv, _ = ctx.run_mcts(st, legal, tp, True, game, move, priors=True)
+    exact = [O.run_mcts(ocfg, blob, st[i], int(legal[i]), int(tp[i]), True, int(game[i]), int(move[i])) for i in range(n)]
+    same = np.mean([vc[i].tolist() == exact[i][0].tolist() for i in range(n)])
+    print("BatchNorm networks on the split-precision path: visit counts identical to the Float32 oracle on %.4f of %d roots" % (same, n))
+    assert np.all(vc.sum(1) == S) and same >= 0.99
+    # self-play + learning!: the update does not depend on the forward pass (Q20), so the weights stay bit-exact; the losses carry the path's 1e-6
+    ctx.self_play(100, 600, 1.0)
+    w = blob.copy(); m = np.zeros_like(w); vv = np.zeros_like(w)
+    for t in (1, 2):
+        batch = ctx.get_batch(t)
+        losses = ctx.learn_step(t)
+        ol = O.learn_step(ocfg, w, m, vv, t, batch)
+        np.testing.assert_allclose(losses, ol, rtol=1e-4)
+        assert np.array_equal(ctx.get_weights(), w), t
+    h2 = ctx.representation(st[:64])                         # the image was rebuilt from the updated beta / gamma / W / b
+    oh2 = np.stack([O.representation(ocfg, w, x) for x in st[:64]])
+    assert np.max(np.abs(h2 - oh2)) <= 2e-5 * max(1.0, float(np.max(np.abs(oh2)))) and not np.array_equal(oh2, oh[:64])
+    with pytest.raises(capi.MuZeroB200Error) as e:
+        ctx.learn_step(3, grad_mode=capi.GRAD_BPTT)
+    assert e.value.code == capi.E_UNSUPPORTED
+    ctx.close()
+
+
 def test_bn_unsupported_combinations_say_so(capi):
-    for mode in (capi.NN_BF16_TC, capi.NN_SPLIT_MMA):
-        with pytest.raises(capi.MuZeroB200Error):
-            capi.Context(capi.default_config(use_batch_norm=1, nn_mode=mode))
+    with pytest.raises(capi.MuZeroB200Error):
+        capi.Context(capi.default_config(use_batch_norm=1, nn_mode=capi.NN_BF16_TC))
     ctx, _ = make_ctx(capi, num_slots=32, replay_buffer_size=64, num_iters=5)
     ctx.init_weights(1); ctx.self_play(0, 32, 1.0)
     with pytest.raises(capi.MuZeroB200Error):
@@ -90,5 +132,6 @@ def test_bn_through_the_reference_level_api(capi):
     conf = api.Config(); hyper = api.FeedForwardHP(use_batch_norm=True)
     cfg = api.to_mz_config(conf, hyper, num_slots=32)
     assert cfg.use_batch_norm == 1
+    assert api.to_mz_config(conf, hyper, num_slots=32, nn_mode=capi.NN_SPLIT_MMA).use_batch_norm == 1
     with pytest.raises(NotImplementedError):
-        api.to_mz_config(conf, hyper, num_slots=32, nn_mode=capi.NN_SPLIT_MMA)
+        api.to_mz_config(conf, hyper, num_slots=32, nn_mode=capi.NN_BF16_TC)
