@@ -92,8 +92,8 @@ typedef struct mz_config {
     int32_t temperature_threshold;
     /* FeedForwardHP.use_batch_norm (src/Constructors.jl:71): make_dense = Chain(Dense(in, out), BatchNorm(out, relu)) (src/Learning.jl:70-79).
      * BatchNorm runs in test mode everywhere (the reference never differentiates a forward pass and never calls trainmode!).  Runs on the
-     * exact-fp32 path and, folded into the weight image (W' = diag(gamma / sqrt(sigma2 + 1f-5)) W), on MZ_NN_SPLIT_MMA; MZ_NN_BF16_TC and
-     * MZ_GRAD_BPTT answer MZ_E_UNSUPPORTED.  Blob: such a layer's W, b are followed by
+     * exact-fp32 path and, folded into the weight image (W' = diag(gamma / sqrt(sigma2 + 1f-5)) W), on MZ_NN_SPLIT_MMA; MZ_GRAD_BPTT
+     * differentiates the folded layers and maps the result back to W, b, beta, gamma by the chain rule.  MZ_NN_BF16_TC answers MZ_E_UNSUPPORTED.  Blob: such a layer's W, b are followed by
      * beta[out], gamma[out] (Flux.params order) and the running statistics mu[out], sigma2[out] (not parameters: ADAM leaves them alone). */
     int32_t use_batch_norm;
 } mz_config;
@@ -218,7 +218,7 @@ int mz_learn_steps(mz_ctx *ctx, int64_t t0, int n, int grad_mode, float *losses 
  * order.  MZ_GRAD_REFERENCE_L2: what the reference's three Zygote pullbacks actually return, 2*theta (Learning.jl:385-393
  * differentiate a closure whose predictions were computed outside of it).  MZ_GRAD_BPTT: the gradient of the same loss
  * value (Learning.jl:261-288) through the unroll (Learning.jl:347-370), plus 2*theta.  MZ_GRAD_BPTT is built for the FeedForwardHP
- * networks without BatchNorm whose hidden layers are at most 64 wide; the observation stack itself may be wider (stacked_observations = 2:
+ * networks (with or without BatchNorm) whose hidden layers are at most 64 wide; the observation stack itself may be wider (stacked_observations = 2:
  * 99 inputs); everything else answers MZ_E_UNSUPPORTED. */
 int mz_learn_gradients(mz_ctx *ctx, int grad_mode, int B, const float *obs_batch, const float *action_batch, const float *value_batch,
                        const float *reward_batch, const float *policy_batch, const float *gscale, float *grad, float *losses /* [3] */);

@@ -108,6 +108,7 @@ struct mz_ctx {
     mzh::rn_model rn; unsigned char *d_rn_image = nullptr; mz_rn_step *d_rn_steps = nullptr; size_t smem_bytes_rn = 0; std::vector<float> rn_blob;
     // grad_mode = MZ_GRAD_BPTT
     mzh::bptt_program bptt; mz_bstage *d_bstages[2] = {nullptr, nullptr}; size_t smem_bytes_bptt = 0;
+    float *d_w_fold = nullptr;   // use_batch_norm + MZ_GRAD_BPTT: the weights with every BatchNorm folded into its Dense layer
     float *d_act = nullptr, *d_gpart = nullptr; int bptt_tiles_cap = 0; int bptt_dims[4] = {0, 0, 0, 0};   // mz_bptt_args: dim_wide, dim_narrow, wfloats[2]
     int64_t launches = 0; bool timing = false; std::vector<timed_launch> timed; double fam_ms[8] = {0}; int64_t fam_n[8] = {0};
     double last_mean_legal = 0, last_mean_depth = 0;
@@ -359,8 +360,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
-    if (grad_mode == MZ_GRAD_BPTT && c->cfg.use_batch_norm) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for use_batch_norm networks (the reference's own update, MZ_GRAD_REFERENCE_L2, is)");
-    if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) {
+    if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !c->cfg.use_batch_norm && !getenv("MUZERO_B200_BPTT_SIMT")) {
         // forward + backward on the tensor cores (mz_learner_tc.cuh): kernel 1 = unroll forward + dX chain with saved tiles, kernel 2 = dW / db
         MZ_TRY(ensure_images(c));
         const mz_lr_plan &L = c->lrp;
@@ -396,7 +396,6 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, MZ_DW_STAGES * 2 * MZ_SP_TILE_BYTES + 1024, c->stream>>>(P, d); }
         { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
-        if (c->cfg.use_batch_norm) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for use_batch_norm networks (the reference's own update, MZ_GRAD_REFERENCE_L2, is)");
         if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for this network: it needs every layer output and every layer input other than the observation stack to be at most 64 wide, and its buffers to fit one CTA's shared memory");
         if (tiles > c->bptt_tiles_cap) {
             if (c->d_act) cudaFree(c->d_act);
@@ -408,8 +407,14 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         }
         mz_bptt_args b{}; b.f = a; b.act = c->d_act; b.gpart = c->d_gpart; b.stages[0] = c->d_bstages[0]; b.stages[1] = c->d_bstages[1];
         b.dim_wide = c->bptt_dims[0]; b.dim_narrow = c->bptt_dims[1]; b.wfloats[0] = c->bptt_dims[2]; b.wfloats[1] = c->bptt_dims[3];
+        if (c->cfg.use_batch_norm) {   // BatchNorm in test mode = a Dense layer with folded weights: the kernel runs on the folded copy, the reduce applies the chain rule
+            if (!c->d_w_fold) MZ_CUDA(c, dmalloc(&c->d_w_fold, (size_t)P.total_floats));
+            { launch_scope ls(c, 5); mz_k_bn_fold<<<dim3((unsigned)P.n_layers, 4), 256, 0, c->stream>>>(P, c->d_w, c->d_w_fold); }
+            b.f.wglob = c->d_w_fold;
+        }
         { launch_scope ls(c, 3); mz_k_learn_bptt<<<tiles, MZ_THREADS, c->smem_bytes_bptt, c->stream>>>(P, c->bptt.plan, b); }
-        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, grad_out(c)); }
+        if (c->cfg.use_batch_norm) { launch_scope ls(c, 4); mz_k_grad_reduce_bn<<<dim3((unsigned)P.n_layers, 16), 256, 0, c->stream>>>(P, tiles, c->d_gpart, c->d_w, grad_out(c)); }
+        else { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, tiles, c->d_gpart, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_REFERENCE_L2 && c->cfg.nn_mode == MZ_NN_SPLIT_MMA) {   // the unroll on the tensor cores (mz_kernels_sp.cuh)
         MZ_TRY(ensure_images(c));
         mz_learn_sp_args t{}; t.sp = c->spa; t.B = B; t.batch = c->batch; t.pred_values = c->d_pv; t.pred_rewards = c->d_pr; t.pred_policies = c->d_pp;
@@ -714,7 +719,7 @@ int mz_destroy(mz_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     collect_timings(c);
     if (c->comm && g_nccl.CommDestroy) { p2p_teardown(c); g_nccl.CommDestroy(c->comm); }
-    void *ptrs[] = {c->d_fc_mask, c->d_w_lat, c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, c->d_rn_h, c->d_rn_nh, c->d_rn_sa, c->d_rn_o1, c->d_rn_o2, c->d_rn_r, c->d_rn_mask, c->d_rn_pool, c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
+    void *ptrs[] = {c->d_fc_mask, c->d_w_fold, c->d_w_lat, c->d_rn_theta, c->d_rn_m, c->d_rn_v, c->d_rn_grad, c->d_rn_h, c->d_rn_nh, c->d_rn_sa, c->d_rn_o1, c->d_rn_o2, c->d_rn_r, c->d_rn_mask, c->d_rn_pool, c->d_brounds, c->d_xsave, c->d_dzsave, c->d_gpart_tc, c->d_w_sp, c->d_bias_sp, c->d_rounds_sp, c->d_rn_image, c->d_rn_steps, c->d_bstages[0], c->d_bstages[1], c->d_act, c->d_gpart, c->d_w_tc, c->d_bias_tc, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_pbc0, c->d_sqrtN, c->d_trees, c->slots.p1, c->slots.p2, c->slots.player, c->slots.T,
                     c->slots.status, c->slots.game_id, c->slots.fin_list, c->slots.h_p1, c->slots.h_p2, c->slots.h_action, c->slots.h_reward, c->slots.h_to_play,
                     c->slots.h_cv, c->slots.h_rv, c->ring.game_id, c->ring.T, c->ring.h_p1, c->ring.h_p2, c->ring.h_action, c->ring.h_reward,
                     c->ring.h_to_play, c->ring.h_cv, c->ring.h_rv, c->ring.h_rrv, c->ring.reanalysed, c->ring.q_pos, c->ring.q_game, c->ring.prefix, c->ring.upd, c->ring.counters, c->d_stats, c->d_lossout, c->batch.index, c->batch.obs,

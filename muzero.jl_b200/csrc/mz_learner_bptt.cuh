@@ -387,3 +387,47 @@ __global__ void mz_k_grad_reduce(int n, int tiles, const float *gpart, const flo
     for (int t = 0; t < tiles; t++) s = s + gpart[(size_t)t * n + i];
     grad[i] = s + (theta[i] + theta[i]);
 }
+
+// ---- FeedForwardHP.use_batch_norm (Learning.jl:70-79) in grad_mode = MZ_GRAD_BPTT ---------------------------------------------------
+// BatchNorm runs in test mode, so Dense + BatchNorm(relu) is the Dense layer W' = diag(s) W, b' = s (b - mu) + beta with
+// s = gamma / sqrt(sigma2 + 1f-5): mz_k_learn_bptt runs unchanged on a folded copy of the weights (mz_k_bn_fold) and mz_k_grad_reduce_bn maps
+// its dW', db' back by the chain rule: dW = s dW', db = s db', dbeta = db', dgamma = (sum_k dW'[k][o] W[k][o] + db'[o] (b[o] - mu[o])) / sqrt(sigma2 + 1f-5);
+// mu and sigma2 are not Flux parameters (gradient 0, no L2 term).  Grid = (layers, slices).
+__global__ void __launch_bounds__(256) mz_k_bn_fold(const __grid_constant__ mz_params P, const float *w, float *wf) {
+    const mz_layer &l = P.layers[blockIdx.x];
+    const int wn = l.in * l.out_pad;
+    const float *bnp = w + l.b_off + l.out_pad;                          // beta | gamma | mu | sigma2
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < l.floats; i += 256 * gridDim.y) {
+        float v = w[l.w_off + i];
+        if (l.bn && i < wn + l.out_pad) {
+            const int o = i < wn ? i % l.out_pad : i - wn;
+            const float s = bnp[l.out_pad + o] / sqrtf(bnp[3 * l.out_pad + o] + 1e-5f);
+            v = i < wn ? v * s : s * (v - bnp[2 * l.out_pad + o]) + bnp[o];
+        }
+        wf[l.w_off + i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) mz_k_grad_reduce_bn(const __grid_constant__ mz_params P, int tiles, const float *gpart, const float *theta, float *grad) {
+    const mz_layer &l = P.layers[blockIdx.x];
+    const int wn = l.in * l.out_pad, n = P.total_floats;
+    const float *bnp = theta + l.b_off + l.out_pad;
+    auto tsum = [&](int idx) { float s = 0.0f; for (int t = 0; t < tiles; t++) s = s + gpart[(size_t)t * n + idx]; return s; };
+    for (int i = blockIdx.y * 256 + threadIdx.x; i < l.floats; i += 256 * gridDim.y) {
+        const int idx = l.w_off + i;
+        const float th = theta[idx];
+        float g;
+        if (!l.bn) g = tsum(idx) + (th + th);
+        else {
+            const int part = i < wn ? 0 : 1 + (i - wn) / l.out_pad, o = i < wn ? i % l.out_pad : (i - wn) % l.out_pad;
+            const float sd = sqrtf(bnp[3 * l.out_pad + o] + 1e-5f);
+            if (part <= 1) g = (bnp[l.out_pad + o] / sd) * tsum(idx) + (th + th);                       // W, b
+            else if (part == 2) g = tsum(l.b_off + o) + (th + th);                                      // beta
+            else if (part == 3) {                                                                       // gamma
+                float acc = tsum(l.b_off + o) * (theta[l.b_off + o] - bnp[2 * l.out_pad + o]);
+                for (int k = 0; k < l.in; k++) acc = acc + tsum(l.w_off + k * l.out_pad + o) * theta[l.w_off + k * l.out_pad + o];
+                g = acc / sd + (th + th);
+            } else g = 0.0f;                                                                            // mu, sigma2
+        }
+        grad[idx] = g;
+    }
+}

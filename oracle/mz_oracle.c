@@ -1366,6 +1366,7 @@ static void dense_fwd(const float *blob, const double *wd, const layer_t *l, con
             double acc = 0.0;
             for (int k = 0; k < l->in; k++) acc += wd[l->w_off + o + (size_t)l->out * k] * x[k];
             acc += wd[l->b_off + o];
+            if (l->bn) acc = wd[l->gamma_off + o] * (acc - wd[l->mu_off + o]) / sqrt(wd[l->var_off + o] + (double)1e-5f) + wd[l->beta_off + o];   /* BatchNorm, test mode */
             y[o] = l->act == ACT_RELU ? (acc > 0.0 ? acc : 0.0) : l->act == ACT_TANH ? tanh(acc) : acc;
         }
     } else {
@@ -1391,6 +1392,13 @@ static void chain_bwd(const double *wd, double *G, const layer_t *ls, int n, con
         for (int o = 0; o < L->out; o++) {
             double d = L->act == ACT_RELU ? (y[o] > 0.0 ? 1.0 : 0.0) : L->act == ACT_TANH ? 1.0 - y[o] * y[o] : 1.0;
             cur[o] *= d;
+            if (L->bn) {   /* y = act(gamma * (z - mu) / sd + beta), z = W x + b: beta and gamma are Flux parameters, mu and sigma2 are not (no gradient) */
+                double z = wd[L->b_off + o], sd = sqrt(wd[L->var_off + o] + (double)1e-5f);
+                for (int k = 0; k < L->in; k++) z += wd[L->w_off + o + (size_t)L->out * k] * x[k];
+                G[L->beta_off + o] += cur[o];
+                G[L->gamma_off + o] += cur[o] * (z - wd[L->mu_off + o]) / sd;
+                cur[o] *= wd[L->gamma_off + o] / sd;
+            }
             G[L->b_off + o] += cur[o];
         }
         for (int k = 0; k < L->in; k++) {
@@ -1500,7 +1508,12 @@ static double learn_gradients_impl(const mzo_config *c, const float *blob, int B
             net_bwd(wd, grad, &m.nets[0], ar, dh, NULL, NULL);
         }
     }
-    if (grad) for (int i = 0; i < np; i++) grad[i] += 2.0 * wd[i];                          /* sum(sqnorm, params), :287 */
+    if (grad) {                                                                             /* sum(sqnorm, params), :287: Flux.params leave the BatchNorm statistics out */
+        unsigned char *mask = (unsigned char *)malloc((size_t)np);
+        mzo_trainable_mask(c, mask);
+        for (int i = 0; i < np; i++) grad[i] = mask[i] ? grad[i] + 2.0 * wd[i] : 0.0;
+        free(mask);
+    }
     double value_loss = vsum / (double)B, policy_loss = (ssum / (double)B) * G;
     double data = value_loss + (c->intermediate_rewards ? rsum / (double)B : 0.0) + policy_loss;
     free(wd); free(ar); free(ap); free(ad);

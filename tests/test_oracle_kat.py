@@ -297,6 +297,43 @@ def test_bptt_gradient_matches_finite_differences(ir):
         assert np.allclose(grad[n - tail:], 2.0 * blob[n - tail:].astype(np.float64), rtol=0, atol=1e-12)
 
 
+def test_bptt_gradient_with_batchnorm_matches_finite_differences():
+    """FeedForwardHP.use_batch_norm (Learning.jl:70-79), test mode: the Float64 backward through gamma * (W x + b - mu) / sqrt(sigma2 + 1f-5) + beta
+    against finite differences of the oracle's own Float64 loss, for W, b, beta and gamma entries; mu and sigma2 are not Flux parameters: 0."""
+    from test_host_harness import _randomise_batchnorm
+    c = O.default_config(batch_size=4, intermediate_rewards=1, exploration_eps=0.0, use_batch_norm=1)
+    blob = O.init_weights(c, 3)
+    rng = np.random.default_rng(3)
+    blob = _randomise_batchnorm(c, blob + (rng.standard_normal(blob.shape[0]) * 0.02).astype(f32), 5)
+    hist = O.self_play(c, blob, 0, 8, 1.0, 1)
+    batch = O.get_batch(c, hist, step=3)
+    batch["rewards"] = batch["rewards"] + (rng.standard_normal(batch["rewards"].shape) * 0.3).astype(f32)
+    loss, grad = O.learn_gradients(c, blob, batch, fwd64=True)
+    assert np.isfinite(loss) and np.all(np.isfinite(grad))
+    mask = O.trainable_mask(c)
+    assert np.all(grad[mask == 0] == 0.0)
+    stats = np.flatnonzero(mask == 0)
+    runs = np.split(stats, np.flatnonzero(np.diff(stats) > 1) + 1)
+    picks = []
+    for r in runs:                                          # per BatchNorm: two beta, two gamma, two bias and two weight entries in front of it
+        n = len(r) // 2
+        picks += [r[0] - 2 * n + 1, r[0] - n - 1, r[0] - n, r[0] - 1, r[0] - 3 * n, r[0] - 2 * n - 1, r[0] - 3 * n - 1, r[0] - 3 * n - 7]
+    picks += list(rng.integers(0, blob.shape[0], 20))
+    h = 1e-6
+    worst = 0.0
+    for i in picks:
+        if not mask[i]:
+            continue
+        lp, _ = O.learn_gradients(c, blob, batch, fwd64=True, perturb=(int(i), +h), want_grad=False)
+        lm, _ = O.learn_gradients(c, blob, batch, fwd64=True, perturb=(int(i), -h), want_grad=False)
+        fd = (lp - lm) / (2 * h) + 2.0 * float(blob[i])
+        worst = max(worst, abs(fd - grad[i]) / (abs(grad[i]) + 1e-6))
+    assert worst < 2e-4, worst
+    # the Float32-forward variant (what the CUDA path is compared with) linearises around almost the same point
+    _, g32 = O.learn_gradients(c, blob, batch, fwd64=False)
+    assert np.max(np.abs(g32 - grad)) <= 1e-3 * np.max(np.abs(grad))
+
+
 def test_bptt_float32_forward_is_close_to_float64_forward():
     c, blob, batch = _bptt_case(1)
     l64, g64 = O.learn_gradients(c, blob, batch, fwd64=True)
