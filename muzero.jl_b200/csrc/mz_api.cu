@@ -360,7 +360,7 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
     mz_learn_args a{}; a.wglob = c->d_w; a.B = B; a.max_dim = c->M.max_dim; a.max_layer_floats = c->M.max_layer_floats; a.batch = c->batch;
     a.pred_values = c->d_pv; a.pred_rewards = c->d_pr; a.pred_policies = c->d_pp;
     const int tiles = (B + MZ_ROWS - 1) / MZ_ROWS;
-    if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !c->cfg.use_batch_norm && !getenv("MUZERO_B200_BPTT_SIMT")) {
+    if (grad_mode == MZ_GRAD_BPTT && c->cfg.nn_mode == MZ_NN_SPLIT_MMA && c->lrp.ok && !getenv("MUZERO_B200_BPTT_SIMT")) {
         // forward + backward on the tensor cores (mz_learner_tc.cuh): kernel 1 = unroll forward + dX chain with saved tiles, kernel 2 = dW / db
         MZ_TRY(ensure_images(c));
         const mz_lr_plan &L = c->lrp;
@@ -394,7 +394,9 @@ int launch_learn_forward(mz_ctx *c, int B, int grad_mode = MZ_GRAD_REFERENCE_L2)
         mz_dw_args d{}; d.xsave = c->d_xsave; d.dzsave = c->d_dzsave; d.gpart = c->d_gpart_tc; d.tiles = tiles; d.chunks = chunks; d.slots_per_cta = L.slots_per_cta; d.n_eval = L.n_eval;
         for (int n = 0; n < 3; n++) { d.slot_base[n] = L.slot_base[n]; d.layers_in_net[n] = L.layers_in_net[n]; d.first_layer[n] = P.nets[n].first; }
         { launch_scope ls(c, 3); mz_k_learn_dw<<<dim3((unsigned)P.n_layers, (unsigned)chunks), 128, MZ_DW_STAGES * 2 * MZ_SP_TILE_BYTES + 1024, c->stream>>>(P, d); }
-        { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
+        // (use_batch_norm: the images these kernels read are the folded layers (mz_k_pack_images), so the sums are dW', db': same chain rule as below)
+        if (c->cfg.use_batch_norm) { launch_scope ls(c, 4); mz_k_grad_reduce_bn<<<dim3((unsigned)P.n_layers, 16), 256, 0, c->stream>>>(P, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
+        else { launch_scope ls(c, 4); mz_k_grad_reduce<<<(P.total_floats + 255) / 256, 256, 0, c->stream>>>(P.total_floats, chunks, c->d_gpart_tc, c->d_w, grad_out(c)); }
     } else if (grad_mode == MZ_GRAD_BPTT) {   // forward + backward through the unroll in one kernel; per-tile partial gradients
         if (!c->smem_bytes_bptt) return fail(c, MZ_E_UNSUPPORTED, "MZ_GRAD_BPTT is not built for this network: it needs every layer output and every layer input other than the observation stack to be at most 64 wide, and its buffers to fit one CTA's shared memory");
         if (tiles > c->bptt_tiles_cap) {
