@@ -472,6 +472,13 @@ int launch_update(mz_ctx *c, int64_t t, int grad_mode) {
     }
     if (t == 1 || c->adam_t == 0) { c->bp1 = 0.9; c->bp2 = 0.999; c->adam_t = 1; }
     // MZ_GRAD_BPTT: d_grad was produced by launch_learn_forward (mz_k_learn_bptt + mz_k_grad_reduce)
+    if (grad_mode == MZ_GRAD_REFERENCE_L2 && !c->p2p && !c->comm) {   // one GPU: gradient (2 * theta) and update in one launch
+        { launch_scope ls(c, 4); mz_k_adam_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_m, c->d_v, c->d_grad, c->d_fc_mask, mzh::cos_schedule(t), c->bp1, c->bp2); }
+        MZ_CUDA(c, cudaGetLastError());
+        c->bp1 *= 0.9; c->bp2 *= 0.999; c->adam_t++;
+        c->w_version++;
+        return MZ_OK;
+    }
     if (grad_mode == MZ_GRAD_REFERENCE_L2) { launch_scope ls(c, 4); if (c->d_fc_mask) mz_k_grad_l2_masked<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, c->d_fc_mask, grad_out(c)); else mz_k_grad_l2<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->d_w, grad_out(c)); }
     float scale = 1.0f;
     if (c->p2p) {    // data-parallel over peer memory: ONE kernel waits for the peers' gradients, sums them in rank order over NVLink and applies ADAM

@@ -219,6 +219,22 @@ __global__ void mz_k_adam(int n, float *theta, float *m, float *v, const float *
     theta[i] = theta[i] - delta;
 }
 
+// MZ_GRAD_REFERENCE_L2 on one GPU: the gradient is 2 * theta over Flux.params (Q20), so mz_k_grad_l2 + mz_k_adam are one kernel (a B = 32 step is
+// bound by its launches).  Same arithmetic, same bits; the gradient is still written out.  mask: use_batch_norm (NULL = all ones).
+__global__ void mz_k_adam_l2(int n, float *theta, float *m, float *v, float *grad, const unsigned char *mask, double eta, double bp1, double bp2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    const float th = theta[i];
+    const float g = (!mask || mask[i]) ? th + th : 0.0f;
+    grad[i] = g;
+    float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * (double)g);
+    float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * (double)(g * g));
+    m[i] = mi; v[i] = vi;
+    float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+    theta[i] = th - delta;
+}
+
 // Data-parallel update over peer memory: every rank's gradient lies in a buffer that all ranks have mapped (CUDA IPC, NVLink / NVSwitch).
 // One kernel: announce "my gradient of step s is complete" in every peer's flag block, wait until every peer has announced the same,
 // then each thread sums its element over the ranks IN RANK ORDER (so all ranks compute bit-identical sums) with loads straight from the
